@@ -1,0 +1,681 @@
+// BAM -> struct-of-arrays decoder, k-way merge, and BAM writer.
+//
+// Host-side mirror of the reference's reader stack for the hot path:
+//   openBam / openBams              src/lib/io/BamIo.cpp:6-31          (primary && tid >= 0 filter)
+//   RegionLimitedBamReader          src/lib/io/RegionLimitedBamReader.hpp:36-71   (-o region)
+//   BamMerger                       src/lib/io/BamMerger.cpp:40-126    ((tid,pos,strand) merge)
+//   Alignment ctor / determine_*    src/lib/io/Alignment.cpp:12-64     (field extraction, AM, RG)
+//   AlignmentSource::next           src/lib/io/AlignmentSource.hpp:48-65 (read group -> library)
+// Written from the SAM/BAM specification (BGZF = concatenated gzip members with a "BC" extra
+// field; BAM records = 32-byte core + name + cigar + seq + qual + aux). Unlike the reference
+// (one zlib stream, one record and two heap objects at a time) a file is mapped, its BGZF
+// blocks are inflated in parallel into one buffer, and fields are extracted by all cores
+// straight into the columns the GPU consumes.
+#include "host.hpp"
+
+#include <zlib.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <queue>
+#include <stdexcept>
+#include <thread>
+#include <unordered_map>
+
+#include <cuda_runtime_api.h>
+
+namespace bdh {
+
+int default_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    const char* e = getenv("BDK_THREADS");
+    if (e && atoi(e) > 0) return atoi(e);
+    return n ? (int)n : 1;
+}
+
+void parallel_for(uint64_t n, uint64_t grain, int threads, const std::function<void(uint64_t, uint64_t)>& fn) {
+    if (n == 0) return;
+    if (grain == 0) grain = 1;
+    if (threads <= 1 || n <= grain) { fn(0, n); return; }
+    std::atomic<uint64_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            uint64_t b = next.fetch_add(grain);
+            if (b >= n) return;
+            fn(b, std::min(n, b + grain));
+        }
+    };
+    std::vector<std::thread> pool;
+    int nt = (int)std::min<uint64_t>(threads, (n + grain - 1) / grain);
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+}
+
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+
+struct MappedFile {
+    const uint8_t* data = 0;
+    size_t size = 0;
+    int fd = -1;
+    void open(const std::string& path) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("Failed to open samfile " + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) throw std::runtime_error("Failed to open samfile " + path);
+        size = (size_t)st.st_size;
+        if (size) {
+            void* p = mmap(0, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) throw std::runtime_error("Failed to open samfile " + path);
+            data = (const uint8_t*)p;
+            madvise(p, size, MADV_SEQUENTIAL);
+        }
+    }
+    ~MappedFile() {
+        if (data) munmap((void*)data, size);
+        if (fd >= 0) ::close(fd);
+    }
+};
+
+struct Block { size_t in_off; uint32_t in_len; uint32_t out_len; size_t out_off; };
+
+// Inflate a whole BGZF file into `out` with `threads` workers.
+void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads, std::vector<uint8_t>& out) {
+    std::vector<Block> blocks;
+    size_t off = 0, total = 0;
+    while (off < f.size) {
+        if (off + 18 > f.size) throw std::runtime_error(path + " is not a valid bam file");
+        const uint8_t* h = f.data + off;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) throw std::runtime_error(path + " is not a valid bam file");
+        uint32_t xlen = rd16(h + 10);
+        uint32_t bsize = 0; bool found = false;
+        size_t x = 12;
+        while (x + 4 <= 12 + xlen) {
+            uint8_t si1 = h[x], si2 = h[x + 1]; uint32_t slen = rd16(h + x + 2);
+            if (si1 == 'B' && si2 == 'C' && slen == 2) { bsize = rd16(h + x + 4); found = true; }
+            x += 4 + slen;
+        }
+        if (!found) throw std::runtime_error(path + " is not a valid bam file");
+        size_t blen = (size_t)bsize + 1;
+        if (off + blen > f.size || blen < 12 + xlen + 8) throw std::runtime_error(path + " is truncated");
+        Block b;
+        b.in_off = off + 12 + xlen;
+        b.in_len = (uint32_t)(blen - 12 - xlen - 8);
+        b.out_len = rd32(f.data + off + blen - 4);
+        b.out_off = total;
+        total += b.out_len;
+        blocks.push_back(b);
+        off += blen;
+    }
+    out.resize(total);
+    std::atomic<bool> bad(false);
+    parallel_for(blocks.size(), 64, threads, [&](uint64_t b0, uint64_t b1) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+        for (uint64_t i = b0; i < b1; ++i) {
+            Block const& b = blocks[i];
+            if (b.out_len == 0) continue;
+            inflateReset(&zs);
+            zs.next_in = (Bytef*)(f.data + b.in_off); zs.avail_in = b.in_len;
+            zs.next_out = out.data() + b.out_off; zs.avail_out = b.out_len;
+            int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
+        }
+        inflateEnd(&zs);
+    });
+    if (bad) throw std::runtime_error(path + ": BGZF inflate failed");
+}
+
+struct BamData {
+    std::string path;
+    std::vector<uint8_t> raw;             // whole inflated file
+    std::string text;
+    std::vector<std::string> tid_names;
+    std::vector<uint32_t> tid_lens;
+    std::vector<uint64_t> rec_off;        // offset of each record's core (after block_size)
+    void parse_header() {
+        const uint8_t* p = raw.data();
+        size_t n = raw.size();
+        if (n < 12 || memcmp(p, "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a valid bam file");
+        uint32_t l_text = rd32(p + 4);
+        if (8 + (size_t)l_text + 4 > n) throw std::runtime_error(path + " is not a valid bam file");
+        text.assign((const char*)p + 8, l_text);
+        size_t o = 8 + l_text;
+        uint32_t n_ref = rd32(p + o); o += 4;
+        for (uint32_t i = 0; i < n_ref; ++i) {
+            if (o + 4 > n) throw std::runtime_error(path + " is not a valid bam file");
+            uint32_t l_name = rd32(p + o); o += 4;
+            if (o + l_name + 4 > n) throw std::runtime_error(path + " is not a valid bam file");
+            tid_names.push_back(std::string((const char*)p + o, l_name ? l_name - 1 : 0)); o += l_name;
+            tid_lens.push_back(rd32(p + o)); o += 4;
+        }
+        // record boundaries: a chain of block_size prefixes
+        rec_off.reserve((n - o) / 96 + 16);
+        while (o + 4 <= n) {
+            uint32_t bs = rd32(p + o);
+            if (bs < 32 || o + 4 + bs > n) throw std::runtime_error(path + ": truncated BAM record");
+            rec_off.push_back(o + 4);
+            o += 4 + bs;
+        }
+    }
+};
+
+// 32-byte BAM core (little-endian on disk)
+struct Core {
+    int32_t tid, pos; uint8_t l_qname, mapq; uint16_t bin; uint16_t n_cigar, flag; int32_t l_qseq, mtid, mpos, isize;
+};
+inline Core read_core(const uint8_t* r) {
+    Core c;
+    c.tid = rdi32(r); c.pos = rdi32(r + 4);
+    c.l_qname = r[8]; c.mapq = r[9]; c.bin = rd16(r + 10);
+    c.n_cigar = rd16(r + 12); c.flag = rd16(r + 14);
+    c.l_qseq = rdi32(r + 16); c.mtid = rdi32(r + 20); c.mpos = rdi32(r + 24); c.isize = rdi32(r + 28);
+    return c;
+}
+
+// samtools bam_calend: reference span from the CIGAR (ops M,D,N,=,X consume the reference)
+inline uint32_t calend(const Core& c, const uint8_t* cigar) {
+    uint32_t end = c.pos;
+    for (int k = 0; k < c.n_cigar; ++k) {
+        uint32_t v = rd32(cigar + 4 * k), op = v & 0xf;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += v >> 4;
+    }
+    return end;
+}
+
+// Walk the aux area; return pointer to the value type byte of `tag` or null (bam_aux_get).
+const uint8_t* aux_get(const uint8_t* s, const uint8_t* e, const char tag[2]) {
+    while (s + 3 <= e) {
+        bool hit = s[0] == (uint8_t)tag[0] && s[1] == (uint8_t)tag[1];
+        const uint8_t* v = s + 2;
+        if (hit) return v;
+        uint8_t t = *v++;
+        switch (t) {
+            case 'A': case 'c': case 'C': v += 1; break;
+            case 's': case 'S': v += 2; break;
+            case 'i': case 'I': case 'f': v += 4; break;
+            case 'd': v += 8; break;
+            case 'Z': case 'H': while (v < e && *v) ++v; ++v; break;
+            case 'B': {
+                if (v + 5 > e) return 0;
+                uint8_t st = *v; uint32_t cnt = rd32(v + 1); v += 5;
+                size_t sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                v += sz * cnt; break;
+            }
+            default: return 0;
+        }
+        s = v;
+    }
+    return 0;
+}
+
+inline int32_t aux2i(const uint8_t* v) {  // bam_aux2i
+    switch (*v) {
+        case 'c': return (int8_t)v[1];
+        case 'C': return v[1];
+        case 's': return (int16_t)rd16(v + 1);
+        case 'S': return rd16(v + 1);
+        case 'i': case 'I': return rdi32(v + 1);
+        default: return 0;
+    }
+}
+
+inline uint64_t hash_name(const uint8_t* s, size_t n) {  // 64-bit name key (wyhash-style multiply-mix)
+    auto mix = [](uint64_t a, uint64_t b) { __uint128_t r = (__uint128_t)a * b; return (uint64_t)r ^ (uint64_t)(r >> 64); };
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xA0761D6478BD642Full);
+    while (n >= 8) { uint64_t w; memcpy(&w, s, 8); h = mix(h ^ w, 0xE7037ED1A0B428DBull); s += 8; n -= 8; }
+    uint64_t w = 0; memcpy(&w, s, n);
+    h = mix(h ^ w ^ ((uint64_t)n << 56), 0x8EBC6AF09C88C6E3ull);
+    return mix(h, 0x589965CC75374CC3ull);
+}
+
+struct Region { bool on = false; int tid = -1; int beg = 0, end = 1 << 29; };
+
+// bam_parse_region: "name", "name:beg", "name:beg-end" (1-based inclusive, commas ignored)
+Region parse_region(const std::string& s, const std::vector<std::string>& names, const std::string& path) {
+    Region r; r.on = true;
+    std::string name = s; int beg = 0, end = 1 << 29;
+    auto find_tid = [&](const std::string& nm) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == nm) return (int)i; return -1; };
+    int tid = find_tid(s);
+    if (tid < 0) {
+        size_t colon = s.rfind(':');
+        if (colon != std::string::npos) {
+            name = s.substr(0, colon);
+            std::string rest;
+            for (char c : s.substr(colon + 1)) if (c != ',') rest += c;
+            size_t dash = rest.find('-');
+            beg = atoi(rest.substr(0, dash).c_str());
+            if (dash != std::string::npos) end = atoi(rest.substr(dash + 1).c_str());
+            if (beg > 0) --beg;
+            tid = find_tid(name);
+        }
+    }
+    if (tid < 0 || beg > end)
+        throw std::runtime_error("Failed to parse bam region '" + s + "' in file " + path + ". ");
+    r.tid = tid; r.beg = beg; r.end = end;
+    return r;
+}
+
+struct Columns {
+    std::vector<int32_t> pos, mpos, tid, mtid, isize, qlen;
+    std::vector<uint16_t> flag, rgid;
+    std::vector<uint8_t> mapq;
+    std::vector<uint64_t> qid, rec;  // rec = offset of the raw record in its BamData
+    void resize(size_t n) {
+        pos.resize(n); mpos.resize(n); tid.resize(n); mtid.resize(n); isize.resize(n); qlen.resize(n);
+        flag.resize(n); rgid.resize(n); mapq.resize(n); qid.resize(n); rec.resize(n);
+    }
+};
+
+struct RgTable {
+    std::mutex mu;
+    std::map<std::pair<int, std::string>, int> ids;
+    std::vector<int32_t> rg_lib, rg_bam;
+    const Config* cfg;
+    int get(int bam, const std::string& rg) {
+        std::lock_guard<std::mutex> g(mu);
+        auto key = std::make_pair(bam, rg);
+        auto it = ids.find(key);
+        if (it != ids.end()) return it->second;
+        int id = (int)rg_lib.size();
+        ids[key] = id;
+        rg_lib.push_back(cfg->rg_lib(rg));
+        rg_bam.push_back(bam);
+        return id;
+    }
+};
+
+}  // namespace
+
+}  // namespace bdh
+
+// ------------------------------------------------------------------------------------------------
+struct bdh_stream {
+    std::vector<bdh::BamData> bams;
+    uint64_t n = 0;
+    // final merged columns (malloc'ed or cudaHostAlloc'ed)
+    int pinned = 0;
+    int32_t *pos = 0, *mpos = 0, *tid = 0, *mtid = 0, *isize = 0, *qlen = 0;
+    uint16_t *flag = 0, *rgid = 0;
+    uint8_t* mapq = 0;
+    uint64_t* qid = 0;
+    std::vector<uint8_t> rec_bam;     // per merged record: source bam (keep_records)
+    std::vector<uint64_t> rec_off;    // per merged record: raw offset (keep_records)
+    std::vector<int32_t> rg_lib, rg_bam;
+    std::vector<std::string> tid_names;
+    double t_inflate = 0, t_extract = 0, t_merge = 0;
+    std::string tmp_name;
+
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        void* p = 0;
+        if (pinned) {
+            if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+                throw std::runtime_error("cudaHostAlloc failed for the record columns");
+        } else {
+            if (posix_memalign(&p, 256, bytes) != 0) throw std::bad_alloc();
+        }
+        return p;
+    }
+    void release(void* p) { if (!p) return; if (pinned) cudaFreeHost(p); else free(p); }
+    ~bdh_stream() {
+        release(pos); release(mpos); release(tid); release(mtid); release(isize); release(qlen);
+        release(flag); release(rgid); release(mapq); release(qid);
+    }
+};
+
+namespace bdh {
+namespace {
+
+void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, int threads, Columns& out) {
+    size_t nrec = bd.rec_off.size();
+    const uint8_t* raw = bd.raw.data();
+    // pass 1: filter flags (primary && tid >= 0 [&& region overlap]) -> keep mask + prefix
+    std::vector<uint8_t> keep(nrec);
+    parallel_for(nrec, 1 << 16, threads, [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; ++i) {
+            const uint8_t* r = raw + bd.rec_off[i];
+            Core c = read_core(r);
+            bool ok = !(c.flag & (0x100 | 0x800)) && c.tid >= 0;
+            if (ok && region.on) {
+                // bam_iter_read's is_overlap(): rend > beg && pos < end within the target
+                uint32_t rend = c.n_cigar ? calend(c, r + 32 + c.l_qname) : (uint32_t)c.pos + 1;
+                ok = c.tid == region.tid && rend > (uint32_t)region.beg && c.pos < region.end;
+            }
+            keep[i] = ok;
+        }
+    });
+    const uint64_t G = 1 << 16;
+    size_t ng = (nrec + G - 1) / G;
+    std::vector<uint64_t> goff(ng + 1, 0);
+    for (size_t g = 0; g < ng; ++g) {
+        uint64_t c = 0;
+        for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) c += keep[i];
+        goff[g + 1] = goff[g] + c;
+    }
+    out.resize(goff[ng]);
+    // pass 2: field extraction
+    parallel_for(ng, 1, threads, [&](uint64_t g0, uint64_t g1) {
+        std::string last_rg; int last_id = -1; bool have_last = false;
+        std::unordered_map<std::string, int> seen;  // per-thread cache in front of the shared table
+        for (uint64_t g = g0; g < g1; ++g) {
+            uint64_t o = goff[g];
+            for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) {
+                if (!keep[i]) continue;
+                const uint8_t* r = raw + bd.rec_off[i];
+                uint32_t bs = rd32(r - 4);
+                Core c = read_core(r);
+                const uint8_t* name = r + 32;
+                const uint8_t* aux = name + c.l_qname + 4 * (size_t)c.n_cigar + ((size_t)c.l_qseq + 1) / 2 + (size_t)c.l_qseq;
+                const uint8_t* end = r + bs;
+                out.pos[o] = c.pos; out.mpos[o] = c.mpos; out.tid[o] = c.tid; out.mtid[o] = c.mtid;
+                out.isize[o] = c.isize; out.qlen[o] = c.l_qseq; out.flag[o] = c.flag;
+                uint8_t q = c.mapq;
+                if (aux <= end) {
+                    if (const uint8_t* am = aux_get(aux, end, "AM")) q = (uint8_t)aux2i(am);  // determine_bdqual
+                }
+                out.mapq[o] = q;
+                size_t nl = c.l_qname ? strnlen((const char*)name, c.l_qname) : 0;
+                out.qid[o] = hash_name(name, nl);
+                out.rec[o] = bd.rec_off[i];
+                const char* rgs = ""; size_t rgl = 0;
+                if (aux <= end) {
+                    if (const uint8_t* rg = aux_get(aux, end, "RG")) {
+                        if (*rg == 'Z' || *rg == 'H') { rgs = (const char*)rg + 1; rgl = strnlen(rgs, end - (rg + 1)); }
+                    }
+                }
+                if (!have_last || last_rg.size() != rgl || memcmp(last_rg.data(), rgs, rgl) != 0) {
+                    last_rg.assign(rgs, rgl);
+                    auto it = seen.find(last_rg);
+                    if (it != seen.end()) last_id = it->second;
+                    else { last_id = rgt.get(bam_idx, last_rg); seen[last_rg] = last_id; }
+                    have_last = true;
+                }
+                out.rgid[o] = (uint16_t)last_id;
+                ++o;
+            }
+        }
+    });
+}
+
+struct Head { int bam; uint64_t i; };
+
+}  // namespace
+}  // namespace bdh
+
+static void set_err2(char* err, int cap, const char* msg) {
+    if (err && cap > 0) { strncpy(err, msg, cap - 1); err[cap - 1] = 0; }
+}
+
+extern "C" {
+
+bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, int npaths, const char* region,
+                            int threads, int pinned, int keep_records, char* err, int errcap) {
+    using namespace bdh;
+    bdh_stream* s = 0;
+    try {
+        const Config& cfg = cfgh->cfg;
+        if (threads <= 0) threads = default_threads();
+        std::vector<std::string> files;
+        if (paths) for (int i = 0; i < npaths; ++i) files.push_back(paths[i]);
+        else files = cfg.bam_files;
+        if (files.empty()) throw std::runtime_error("BamMerger created with no input streams!");
+        s = new bdh_stream;
+        s->pinned = pinned;
+        s->bams.resize(files.size());
+        RgTable rgt; rgt.cfg = &cfg;
+        std::vector<Columns> cols(files.size());
+        for (size_t b = 0; b < files.size(); ++b) {
+            BamData& bd = s->bams[b];
+            bd.path = files[b];
+            double t0 = now_s();
+            {
+                MappedFile mf; mf.open(files[b]);
+                bgzf_inflate_all(mf, files[b], threads, bd.raw);
+            }
+            double t1 = now_s();
+            bd.parse_header();
+            Region rg;
+            if (region && region[0]) rg = parse_region(region, bd.tid_names, files[b]);
+            extract_bam(bd, (int)b, rg, rgt, threads, cols[b]);
+            double t2 = now_s();
+            s->t_inflate += t1 - t0; s->t_extract += t2 - t1;
+            if (rgt.rg_lib.size() > 65536) throw std::runtime_error("more than 65536 (bam, read group) combinations");
+            if (!keep_records) { std::vector<uint8_t>().swap(bd.raw); std::vector<uint64_t>().swap(bd.rec_off); }
+        }
+        s->tid_names = s->bams[0].tid_names;  // BamMerger uses the first stream's header (BamMerger.cpp:78)
+        s->rg_lib = rgt.rg_lib; s->rg_bam = rgt.rg_bam;
+        uint64_t n = 0;
+        for (auto& c : cols) n += c.pos.size();
+        s->n = n;
+        s->pos = (int32_t*)s->alloc(n * 4); s->mpos = (int32_t*)s->alloc(n * 4); s->tid = (int32_t*)s->alloc(n * 4);
+        s->mtid = (int32_t*)s->alloc(n * 4); s->isize = (int32_t*)s->alloc(n * 4); s->qlen = (int32_t*)s->alloc(n * 4);
+        s->flag = (uint16_t*)s->alloc(n * 2); s->rgid = (uint16_t*)s->alloc(n * 2);
+        s->mapq = (uint8_t*)s->alloc(n); s->qid = (uint64_t*)s->alloc(n * 8);
+        if (keep_records) { s->rec_bam.resize(n); s->rec_off.resize(n); }
+        double t3 = now_s();
+        // merge order: for each output slot o, (bam, i)
+        auto put = [&](uint64_t o, int b, uint64_t i) {
+            Columns& c = cols[b];
+            s->pos[o] = c.pos[i]; s->mpos[o] = c.mpos[i]; s->tid[o] = c.tid[i]; s->mtid[o] = c.mtid[i];
+            s->isize[o] = c.isize[i]; s->qlen[o] = c.qlen[i]; s->flag[o] = c.flag[i]; s->rgid[o] = c.rgid[i];
+            s->mapq[o] = c.mapq[i]; s->qid[o] = c.qid[i];
+            if (keep_records) { s->rec_bam[o] = (uint8_t)b; s->rec_off[o] = c.rec[i]; }
+        };
+        if (files.size() == 1) {
+            parallel_for(n, 1 << 18, threads, [&](uint64_t a, uint64_t e) { for (uint64_t i = a; i < e; ++i) put(i, 0, i); });
+        } else {
+            // Same container, comparator and push/pop sequence as the reference's BamMerger, so
+            // ties between bams resolve the same way.
+            auto greater = [&](const Head& x, const Head& y) {
+                Columns const& cx = cols[x.bam]; Columns const& cy = cols[y.bam];
+                if (cx.tid[x.i] != cy.tid[y.i]) return cx.tid[x.i] > cy.tid[y.i];
+                if (cx.pos[x.i] != cy.pos[y.i]) return cx.pos[x.i] > cy.pos[y.i];
+                return ((cx.flag[x.i] & 0x10) != 0) > ((cy.flag[y.i] & 0x10) != 0);
+            };
+            std::priority_queue<Head, std::vector<Head>, decltype(greater)> pq(greater);
+            for (size_t b = 0; b < files.size(); ++b)
+                if (!cols[b].pos.empty()) pq.push(Head{(int)b, 0});
+            uint64_t o = 0;
+            while (!pq.empty()) {
+                Head h = pq.top(); pq.pop();
+                put(o++, h.bam, h.i);
+                if (h.i + 1 < cols[h.bam].pos.size()) pq.push(Head{h.bam, h.i + 1});
+            }
+        }
+        s->t_merge = now_s() - t3;
+        return s;
+    } catch (std::exception const& e) {
+        set_err2(err, errcap, e.what());
+        delete s;
+        return 0;
+    }
+}
+
+void bdh_stream_free(bdh_stream* s) { delete s; }
+uint64_t bdh_stream_n(const bdh_stream* s) { return s->n; }
+void bdh_stream_cols(const bdh_stream* s, bdk_soa* o) {
+    o->pos = s->pos; o->mpos = s->mpos; o->tid = s->tid; o->mtid = s->mtid; o->isize = s->isize;
+    o->flag = s->flag; o->mapq = s->mapq; o->rgid = s->rgid; o->qlen = s->qlen; o->qid = s->qid;
+}
+int bdh_stream_nrg(const bdh_stream* s) { return (int)s->rg_lib.size(); }
+const int32_t* bdh_stream_rg_lib(const bdh_stream* s) { return s->rg_lib.data(); }
+const int32_t* bdh_stream_rg_bam(const bdh_stream* s) { return s->rg_bam.data(); }
+int bdh_stream_ntid(const bdh_stream* s) { return (int)s->tid_names.size(); }
+const char* bdh_stream_tid_name(const bdh_stream* s, int tid) {
+    return tid >= 0 && tid < (int)s->tid_names.size() ? s->tid_names[tid].c_str() : "";
+}
+void bdh_stream_timings(const bdh_stream* s, double* a, double* b, double* c) {
+    if (a) *a = s->t_inflate; if (b) *b = s->t_extract; if (c) *c = s->t_merge;
+}
+
+const char* bdh_stream_qname(const bdh_stream* s, uint64_t i) {
+    if (i >= s->n || s->rec_off.empty()) return 0;
+    return (const char*)(s->bams[s->rec_bam[i]].raw.data() + s->rec_off[i] + 32);
+}
+
+int bdh_stream_fastq(const bdh_stream* s, uint64_t i, char* buf, int cap) {
+    using namespace bdh;
+    if (i >= s->n || s->rec_off.empty()) return -1;
+    const uint8_t* r = s->bams[s->rec_bam[i]].raw.data() + s->rec_off[i];
+    Core c = read_core(r);
+    const char* name = (const char*)r + 32;
+    const uint8_t* seq = r + 32 + c.l_qname + 4 * (size_t)c.n_cigar;
+    const uint8_t* qual = seq + ((size_t)c.l_qseq + 1) / 2;
+    std::string out = "@"; out += name; out += "\n";
+    static const char* nt16 = "=ACMGRSVTWYHKDBN";
+    for (int k = 0; k < c.l_qseq; ++k) out += nt16[(seq[k >> 1] >> ((~k & 1) << 2)) & 0xf];
+    out += "\n+\n";
+    if (c.l_qseq > 0 && qual[0] != 0xff) for (int k = 0; k < c.l_qseq; ++k) out += char(qual[k] + 33);
+    out += "\n";
+    if ((int)out.size() + 1 > cap) return -1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+}
+
+// ---- writer -------------------------------------------------------------------------------------
+int bdh_write_bam(const char* path, int ntid, const char* const* tid_names, const uint32_t* tid_lens,
+                  int nrg, const char* const* rg_names, const bdk_soa* cols, uint64_t n,
+                  const char* name_prefix, int write_am, int level, int threads, char* err, int errcap) {
+    using namespace bdh;
+    try {
+        if (threads <= 0) threads = default_threads();
+        FILE* fp = fopen(path, "wb");
+        if (!fp) throw std::runtime_error(std::string("cannot create ") + path);
+        std::vector<uint8_t> stream;
+        auto put32 = [&](std::vector<uint8_t>& v, uint32_t x) { uint8_t b[4]; memcpy(b, &x, 4); v.insert(v.end(), b, b + 4); };
+        // header
+        std::string text = "@HD\tVN:1.0\tSO:coordinate\n";
+        for (int i = 0; i < ntid; ++i) text += std::string("@SQ\tSN:") + tid_names[i] + "\tLN:" + std::to_string(tid_lens[i]) + "\n";
+        for (int i = 0; i < nrg; ++i) text += std::string("@RG\tID:") + rg_names[i] + "\tSM:s\tLB:" + rg_names[i] + "\n";
+        stream.insert(stream.end(), {'B', 'A', 'M', 1});
+        put32(stream, (uint32_t)text.size());
+        stream.insert(stream.end(), text.begin(), text.end());
+        put32(stream, (uint32_t)ntid);
+        for (int i = 0; i < ntid; ++i) {
+            uint32_t l = (uint32_t)strlen(tid_names[i]) + 1;
+            put32(stream, l);
+            stream.insert(stream.end(), tid_names[i], tid_names[i] + l);
+            put32(stream, tid_lens[i]);
+        }
+        const uint64_t BATCH = 1 << 21;
+        const size_t BLK = 0xff00;
+        auto flush_blocks = [&](std::vector<uint8_t>& data, bool final) {
+            size_t nblk = final ? (data.size() + BLK - 1) / BLK : data.size() / BLK;
+            std::vector<std::vector<uint8_t>> comp(nblk);
+            std::atomic<bool> bad(false);
+            parallel_for(nblk, 16, threads, [&](uint64_t a, uint64_t b) {
+                z_stream zs; memset(&zs, 0, sizeof(zs));
+                if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = true; return; }
+                for (uint64_t k = a; k < b; ++k) {
+                    size_t off = k * BLK, len = std::min(BLK, data.size() - off);
+                    std::vector<uint8_t>& o = comp[k];
+                    o.resize(18 + compressBound(len) + 64 + 8);
+                    deflateReset(&zs);
+                    zs.next_in = data.data() + off; zs.avail_in = (uInt)len;
+                    zs.next_out = o.data() + 18; zs.avail_out = (uInt)(o.size() - 18 - 8);
+                    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad = true; break; }
+                    size_t clen = zs.total_out;
+                    size_t total = 18 + clen + 8;
+                    if (total > 65536) { bad = true; break; }
+                    const uint8_t hdr[16] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0};
+                    memcpy(o.data(), hdr, 16);
+                    uint16_t bs = (uint16_t)(total - 1); memcpy(o.data() + 16, &bs, 2);
+                    uint32_t crc = crc32(crc32(0, 0, 0), data.data() + off, (uInt)len), isz = (uint32_t)len;
+                    memcpy(o.data() + 18 + clen, &crc, 4); memcpy(o.data() + 18 + clen + 4, &isz, 4);
+                    o.resize(total);
+                }
+                deflateEnd(&zs);
+            });
+            if (bad) throw std::runtime_error("BGZF deflate failed");
+            for (auto& o : comp) if (fwrite(o.data(), 1, o.size(), fp) != o.size()) throw std::runtime_error("short write");
+            data.erase(data.begin(), data.begin() + std::min(data.size(), nblk * BLK));
+        };
+        std::string prefix = name_prefix ? name_prefix : "r";
+        for (uint64_t b0 = 0; b0 < n; b0 += BATCH) {
+            uint64_t b1 = std::min(n, b0 + BATCH);
+            // build records of the batch in parallel pieces, then append in order
+            const uint64_t PIECE = 1 << 15;
+            size_t np = (b1 - b0 + PIECE - 1) / PIECE;
+            std::vector<std::vector<uint8_t>> pieces(np);
+            parallel_for(np, 1, threads, [&](uint64_t p0, uint64_t p1) {
+                for (uint64_t p = p0; p < p1; ++p) {
+                    std::vector<uint8_t>& v = pieces[p];
+                    v.reserve(PIECE * 160);
+                    for (uint64_t i = b0 + p * PIECE; i < std::min(b1, b0 + (p + 1) * PIECE); ++i) {
+                        char nm[64];
+                        int nl = snprintf(nm, sizeof nm, "%s%llu", prefix.c_str(), (unsigned long long)cols->qid[i]) + 1;
+                        int32_t ql = cols->qlen[i];
+                        uint16_t fl = cols->flag[i];
+                        int ncig = (ql > 0 && !(fl & 4)) ? 1 : 0;
+                        const char* rg = rg_names[cols->rgid[i]];
+                        size_t rgl = strlen(rg) + 1;
+                        size_t auxl = 3 + rgl + (write_am ? 4 : 0);
+                        uint32_t bs = 32 + nl + 4 * ncig + (ql + 1) / 2 + ql + (uint32_t)auxl;
+                        size_t at = v.size();
+                        v.resize(at + 4 + bs);
+                        uint8_t* r = v.data() + at;
+                        memcpy(r, &bs, 4); r += 4;
+                        int32_t pos = cols->pos[i], tid = cols->tid[i];
+                        uint32_t endp = ncig ? (uint32_t)pos + ql : (uint32_t)pos + 1, beg = (uint32_t)pos, e = endp - 1;
+                        uint16_t bin;
+                        if (beg >> 14 == e >> 14) bin = 4681 + (beg >> 14);
+                        else if (beg >> 17 == e >> 17) bin = 585 + (beg >> 17);
+                        else if (beg >> 20 == e >> 20) bin = 73 + (beg >> 20);
+                        else if (beg >> 23 == e >> 23) bin = 9 + (beg >> 23);
+                        else if (beg >> 26 == e >> 26) bin = 1 + (beg >> 26);
+                        else bin = 0;
+                        memcpy(r, &tid, 4); memcpy(r + 4, &pos, 4);
+                        r[8] = (uint8_t)nl; r[9] = cols->mapq[i]; memcpy(r + 10, &bin, 2);
+                        uint16_t nc = (uint16_t)ncig; memcpy(r + 12, &nc, 2); memcpy(r + 14, &fl, 2);
+                        memcpy(r + 16, &ql, 4); memcpy(r + 20, &cols->mtid[i], 4); memcpy(r + 24, &cols->mpos[i], 4);
+                        memcpy(r + 28, &cols->isize[i], 4);
+                        uint8_t* q = r + 32;
+                        memcpy(q, nm, nl); q += nl;
+                        if (ncig) { uint32_t cg = ((uint32_t)ql << 4) | 0; memcpy(q, &cg, 4); q += 4; }
+                        uint64_t h = cols->qid[i] * 0x9E3779B97F4A7C15ull + fl;
+                        for (int k = 0; k < (ql + 1) / 2; ++k) {
+                            static const uint8_t code[4] = {1, 2, 4, 8};
+                            h = h * 6364136223846793005ull + 1442695040888963407ull;
+                            uint8_t hi = code[(h >> 60) & 3], lo = (2 * k + 1 < ql) ? code[(h >> 58) & 3] : 0;
+                            *q++ = (uint8_t)(hi << 4 | lo);
+                        }
+                        for (int k = 0; k < ql; ++k) *q++ = (uint8_t)(20 + ((h >> (k & 31)) & 15));
+                        q[0] = 'R'; q[1] = 'G'; q[2] = 'Z'; memcpy(q + 3, rg, rgl); q += 3 + rgl;
+                        if (write_am) { q[0] = 'A'; q[1] = 'M'; q[2] = 'C'; q[3] = cols->mapq[i]; q += 4; }
+                    }
+                }
+            });
+            for (auto& p : pieces) stream.insert(stream.end(), p.begin(), p.end());
+            flush_blocks(stream, false);
+        }
+        flush_blocks(stream, true);
+        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        fwrite(eof, 1, 28, fp);
+        if (fclose(fp) != 0) throw std::runtime_error("close failed");
+        return 0;
+    } catch (std::exception const& e) {
+        set_err2(err, errcap, e.what());
+        return -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+/*
+ * bdk.h -- C ABI of the B200-native BreakDancerMax hot path ("bdk" = BreakDancer kernels).
+ *
+ * The reference (genome/breakdancer) has no FFI of its own for this path: the hot path is the
+ * in-process call chain  main -> BamSummary::_analyze_bam -> BreakDancer::run -> push_read ->
+ * process_breakpoint -> build_connection -> process_sv  (SURVEY.md section 8a).  This header is
+ * the seam a maintainer would cut there: the reference's reader keeps producing records, they
+ * are laid out as position-sorted struct-of-arrays columns, and everything from
+ * "classify a record" to "one scored SV row" happens behind these entry points on the GPU.
+ * Each declaration cites the reference code it replaces (paths relative to the reference
+ * root, lines as of commit 4e44b43).
+ *
+ * Conventions: plain C, no C++/torch types; every function returns 0 on success or a negative
+ * bdk_status; bdk_last_error() gives the message.  One context per GPU, calls on one context
+ * are serialised by the caller.  Inputs must be sorted by (tid, pos) the way the reference's
+ * BamMerger (src/lib/io/BamMerger.cpp:40-61) delivers them, contain only primary records with
+ * tid >= 0 (src/lib/io/BamIo.cpp:11-18), and a read name key (qid) may occur at most twice.
+ */
+#ifndef BDK_H
+#define BDK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ReadFlag enum values, src/lib/common/ReadFlags.hpp:14-27 */
+enum {
+    BDK_NA = 0, BDK_ARP_FF = 1, BDK_ARP_LARGE_INSERT = 2, BDK_ARP_SMALL_INSERT = 3,
+    BDK_ARP_RF = 4, BDK_ARP_RR = 5, BDK_NORMAL_FR = 6, BDK_NORMAL_RF = 7, BDK_ARP_CTX = 8,
+    BDK_MATE_UNMAPPED = 9, BDK_UNMAPPED = 10, BDK_NUM_FLAGS = 11
+};
+
+enum bdk_status {
+    BDK_OK = 0,
+    BDK_ERR_ARG = -1,        /* bad argument / unsupported option value */
+    BDK_ERR_CUDA = -2,       /* CUDA runtime error (message has the cudaError string) */
+    BDK_ERR_NOMEM = -3,
+    BDK_ERR_STATE = -4,      /* call order violated */
+    BDK_ERR_DATA = -5,       /* input violates the contract (unknown rgid, library-less read group) */
+    BDK_ERR_NCCL = -6
+};
+
+/* One library: LibraryConfig, src/lib/io/LibraryConfig.hpp:11-27 (index = position in the array,
+ * i.e. rank of the library name, src/lib/io/BamConfig.cpp:97-101). */
+typedef struct bdk_lib {
+    float mean_insertsize;
+    float std_insertsize;
+    float uppercutoff;
+    float lowercutoff;
+    float readlens;
+    int32_t min_mapping_quality;   /* -1: use bdk_params.min_map_qual (BreakDancer.cpp:155-156) */
+    int32_t bam_index;             /* LibraryConfig::bam_file_index (sorted bam list) */
+} bdk_lib;
+
+/* Options (src/lib/common/Options.hpp:12-71) + the config-derived tables the kernels need. */
+typedef struct bdk_params {
+    int32_t min_len;              /* -s */
+    int32_t max_sd;               /* -m */
+    int32_t min_map_qual;         /* -q */
+    int32_t min_read_pair;        /* -r  (must be >= 1) */
+    int32_t seq_coverage_lim;     /* -x */
+    int32_t buffer_size;          /* -b */
+    int32_t score_threshold;      /* -y */
+    int32_t transchr_rearrange;   /* -t */
+    int32_t fisher;               /* -f */
+    int32_t illumina_long_insert; /* -l */
+    int32_t cn_lib;               /* -a */
+    int32_t chr_restricted;       /* 1 iff -o was given (ReadRegionData.cpp:118,133) */
+    int32_t initial_window;       /* BamConfig::max_read_window_size(), BamConfig.cpp:92-93,121 */
+    int32_t nlib;                 /* <= BDK_MAX_LIBS */
+    int32_t nbam;                 /* <= BDK_MAX_BAMS */
+    int32_t nrg;                  /* number of read-group ids, <= 65536 */
+    int32_t ntid;                 /* number of reference sequences (bam_header_t::n_targets) */
+    const bdk_lib* libs;          /* [nlib] */
+    const int32_t* rg_lib;        /* [nrg] read-group id -> library index (AlignmentSource.hpp:57-63);
+                                     -1 = read group without a library: the reference throws
+                                     "library index out of range" (BamConfig.hpp:51-55) -> BDK_ERR_DATA */
+    const int32_t* rg_bam;        /* [nrg] read-group id -> index of the BAM the record was read from
+                                     (BamSummary.cpp:120: counts are per reader) */
+} bdk_params;
+
+#define BDK_MAX_LIBS 255
+#define BDK_MAX_BAMS 64
+
+/* Position-sorted struct-of-arrays record columns: what Alignment's constructor extracts from a
+ * bam1_t (src/lib/io/Alignment.cpp:45-64).  25 bytes per record in the hot columns; qlen and qid
+ * are only read for anomalous records. */
+typedef struct bdk_soa {
+    const int32_t* pos;     /* core.pos   */
+    const int32_t* mpos;    /* core.mpos  */
+    const int32_t* tid;     /* core.tid   */
+    const int32_t* mtid;    /* core.mtid  */
+    const int32_t* isize;   /* core.isize (signed; abs() taken on the device) */
+    const uint16_t* flag;   /* core.flag  */
+    const uint8_t* mapq;    /* bdqual: AM aux tag if present else core.qual (Alignment.cpp:12-23) */
+    const uint16_t* rgid;   /* read-group id assigned by the decoder (index into rg_lib / rg_bam) */
+    const int32_t* qlen;    /* core.l_qseq */
+    const uint64_t* qid;    /* read-name key: equal iff the query names are equal */
+} bdk_soa;
+
+/* BamSummary (src/lib/io/BamSummary.cpp:47-150) + the window/density block of main()
+ * (src/exe/breakdancer-max/BreakDancerMax.cpp:83-116). */
+typedef struct bdk_summary_t {
+    uint32_t covered_ref_len;                               /* BamSummary.cpp:125-126 */
+    int32_t window;                                         /* final _max_read_window_size */
+    uint64_t n_records;
+    uint64_t n_anomalous;                                   /* records entering regions */
+    uint32_t read_count_per_bam[BDK_MAX_BAMS];              /* BamSummary.cpp:120 */
+    uint64_t ref_len_per_bam[BDK_MAX_BAMS];                 /* size_t ref_len, BamSummary.cpp:56 */
+    uint32_t lib_read_count[BDK_MAX_LIBS];                  /* BamSummary.cpp:84 */
+    uint32_t read_counts_by_flag[BDK_MAX_LIBS][BDK_NUM_FLAGS]; /* BamSummary.cpp:113 */
+    float seq_coverage[BDK_MAX_LIBS];                       /* BamSummary.cpp:140-145 */
+    float read_density[BDK_MAX_LIBS];                       /* keyed by library index; -a off: the
+                                                               density of the library's bam */
+} bdk_summary_t;
+
+/* One SV call = one process_sv() that reached the output statement
+ * (src/lib/breakdancer/BreakDancer.cpp:348-512, SvBuilder.cpp:18-118). */
+typedef struct bdk_sv {
+    int32_t chr[2];         /* tid of the two breakpoints */
+    int32_t pos[2];         /* 1-based, after padding (BreakDancer.cpp:387-388,463-464) */
+    int32_t fwd[2];         /* region fwd_read_count */
+    int32_t rev[2];
+    int32_t flag;           /* ReadFlag of the call (SV type = Options::SVtype[flag]) */
+    int32_t diffspan;       /* Size column */
+    int32_t score;          /* PhredQ */
+    int32_t num_pairs;      /* flag_counts[flag] */
+    double logp;            /* ComputeProbScore result (natural log) */
+    float allele_frequency; /* SvBuilder::allele_frequency */
+    uint32_t cn_present;    /* reserved */
+    int32_t region[2];      /* region indices (snodes); region[1] = -1 for a one-region call */
+    int32_t window;         /* flush window the call was made in */
+    int32_t order;          /* position in the reference's output order */
+} bdk_sv;
+
+typedef struct bdk_result {
+    uint64_t n_sv;
+    const bdk_sv* sv;              /* [n_sv], in the reference's output order */
+    const int32_t* lib_count;      /* [n_sv][nlib] type_library_readcount[flag][lib] (0 = absent) */
+    const uint32_t* cn_count;      /* [n_sv][nkey] proper-pair reads between the regions per key
+                                      (key = library if cn_lib else bam); 0 = key absent */
+    const float* copy_number;      /* [n_sv][nkey] SvBuilder::copy_number (valid where cn_count>0) */
+    int32_t nkey;
+} bdk_result;
+
+/* Registered region = BasicRegion (src/lib/breakdancer/BasicRegion.hpp:24-45) plus the flush
+ * window it was registered in. Debug/inspection view (BD_DUMP_REGION_SUMMARY equivalent). */
+typedef struct bdk_region {
+    int32_t tid, start, end;
+    int32_t fwd, rev;
+    int32_t first_read, n_reads;   /* range in the anomalous-read stream */
+    int32_t stored;                /* reads kept (ReadRegionData.cpp:118-121) */
+    int32_t window;
+} bdk_region;
+
+/* One anomalous read as it enters push_read()'s region builder (BreakDancer.cpp:209-241). */
+typedef struct bdk_aread {
+    int32_t pos, tid, qlen, abs_isize;
+    uint32_t meta;        /* bits 0-3 ReadFlag after re-flagging, bit 4 reverse strand,
+                             bits 8-15 library index, bits 16-23 bdqual */
+    uint32_t record;      /* index of the record in the pushed stream */
+    uint64_t qid;
+} bdk_aread;
+
+typedef struct bdk_ctx bdk_ctx;
+
+/* Construct the per-GPU context (replaces the BreakDancer / ReadRegionData / BamSummary object
+ * graph wired in BreakDancerMax.cpp:38-73). device = CUDA ordinal. */
+int bdk_create(bdk_ctx** out, int device, const bdk_params* params);
+void bdk_destroy(bdk_ctx* ctx);
+/* Message of the last failure on ctx (or of the last failed bdk_create when ctx is NULL). */
+const char* bdk_last_error(const bdk_ctx* ctx);
+/* Run on a caller-provided CUDA stream (cudaStream_t); default is the context's own stream. */
+int bdk_set_stream(bdk_ctx* ctx, void* cuda_stream);
+/* Forget all pushed records and results; keeps the allocations (one context per job step). */
+int bdk_reset(bdk_ctx* ctx);
+
+/* Feed n position-sorted records from HOST memory (pinned memory makes the copies asynchronous
+ * and overlapped with the classify kernel). Replaces the per-record loops
+ * BamSummary::_analyze_bam (BamSummary.cpp:69-114) and BreakDancer::run/push_read up to the
+ * point where a read is found anomalous (BreakDancer.cpp:139-207). May be called repeatedly. */
+int bdk_push(bdk_ctx* ctx, const bdk_soa* host_cols, uint64_t n);
+/* Same, columns already resident in this GPU's memory (16-byte aligned). */
+int bdk_push_device(bdk_ctx* ctx, const bdk_soa* dev_cols, uint64_t n);
+
+/* Pass-1 statistics and the derived window (BamSummary + BreakDancerMax.cpp:83-116). */
+int bdk_summary(bdk_ctx* ctx, bdk_summary_t* out);
+
+/* Region building, link graph, connection walk, SV evaluation and scoring
+ * (BreakDancer.cpp:209-512, ReadRegionData.cpp:70-227, SvBuilder.cpp, Graph.hpp). The result
+ * arrays are owned by ctx and stay valid until the next bdk_reset/bdk_finish/bdk_destroy. */
+int bdk_finish(bdk_ctx* ctx, bdk_result* out);
+
+/* Inspection of intermediate stages (valid after bdk_finish). */
+int bdk_get_regions(bdk_ctx* ctx, const bdk_region** regions, uint64_t* n);
+int bdk_get_areads(bdk_ctx* ctx, const bdk_aread** reads, const int32_t** region_of_read, uint64_t* n);
+/* For every anomalous read: order index of the SV call whose process_sv() consumed it as part
+ * of a pair, or -1 (BreakDancer.cpp:367-368; feeds the -g BED / -d FASTQ writers). */
+int bdk_get_support(bdk_ctx* ctx, const int32_t** sv_of_read, uint64_t* n);
+
+/* Device time of the kernels of the last push/finish, milliseconds, measured with CUDA events
+ * on the context's stream. names[i] are static strings. Returns the number of entries. */
+int bdk_kernel_times(bdk_ctx* ctx, const char** names, float* ms, int* launches, int cap);
+
+/* Pinned host memory helpers for callers without their own CUDA binding. */
+void* bdk_host_alloc(uint64_t bytes);
+void bdk_host_free(void* p);
+
+/* Multi-GPU: attach an NCCL communicator (ncclComm_t) for the inter-chromosomal mate-link
+ * exchange of whole-genome / -t runs. Per-chromosome sharding needs no communicator. */
+int bdk_set_comm(bdk_ctx* ctx, void* nccl_comm, int rank, int nranks);
+
+/* Poisson tail used by ComputeProbScore (BreakDancer.cpp:62-68): log P[Pois(lambda) > k],
+ * evaluated on the device (for known-answer tests). */
+int bdk_poisson_logsf(bdk_ctx* ctx, const double* lambda, const int32_t* k, double* out, uint64_t n);
+
+const char* bdk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDK_H */

@@ -1,0 +1,89 @@
+/*
+ * bdk_host.h -- C ABI of the host side of the hot path: bam2cfg config parsing, BAM -> pinned
+ * struct-of-arrays decoding (the producer of bdk_soa), the k-way merge of several BAMs, the
+ * BAM writer used by the synthetic-data tools, and the TSV formatter.  It mirrors the
+ * reference's L2 "io" layer for this path; each entry point cites
+ * the reference code it stands in for (paths relative to the reference root).
+ *
+ * These helpers are plain host code (no GPU needed) and live in the same shared library as
+ * the bdk_* kernels entry points.
+ */
+#ifndef BDK_HOST_H
+#define BDK_HOST_H
+
+#include <stdint.h>
+#include "bdk.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- bam2cfg configuration file: BamConfig / BamConfigEntry --------------------------------
+ * src/lib/io/BamConfig.cpp:19-122, BamConfigEntry.cpp:31-86.  Library index = rank of the
+ * library name; bam list = sorted unique "map:" paths. */
+typedef struct bdh_config bdh_config;
+bdh_config* bdh_config_parse(const char* text, int cut_sd, char* err, int errcap);
+bdh_config* bdh_config_load(const char* path, int cut_sd, char* err, int errcap);
+void bdh_config_free(bdh_config* c);
+int bdh_config_nlib(const bdh_config* c);
+int bdh_config_nbam(const bdh_config* c);
+int bdh_config_window(const bdh_config* c);                    /* max_read_window_size() */
+const bdk_lib* bdh_config_libs(const bdh_config* c);           /* [nlib] */
+const char* bdh_config_lib_name(const bdh_config* c, int i);
+const char* bdh_config_bam_name(const bdh_config* c, int i);
+/* readgroup_library(rg) -> library index (BamConfig.hpp:63-72): unknown read groups fall back
+ * to the library of the first bam; returns -1 when that library name is empty. */
+int bdh_config_rg_lib(const bdh_config* c, const char* rg);
+
+/* ---- decoded, merged record stream --------------------------------------------------------
+ * openBams + BamMerger + AlignmentSource::next (src/lib/io/BamIo.cpp:6-31, BamMerger.cpp:40-126,
+ * AlignmentSource.hpp:48-65, Alignment.cpp:12-64): every primary record with tid >= 0 of every
+ * bam in the config (optionally limited to a region, RegionLimitedBamReader.hpp:36-71), merged
+ * by (tid, pos, strand), as struct-of-arrays columns. */
+typedef struct bdh_stream bdh_stream;
+/* paths == NULL: open the config's bam files (relative to the current directory). threads <= 0:
+ * all cores. pinned != 0: allocate the columns with cudaHostAlloc. keep_records != 0: keep the
+ * raw records so names / sequences can be fetched afterwards (-g / -d). */
+bdh_stream* bdh_stream_open(const bdh_config* cfg, const char* const* paths, int npaths,
+                            const char* region, int threads, int pinned, int keep_records,
+                            char* err, int errcap);
+void bdh_stream_free(bdh_stream* s);
+uint64_t bdh_stream_n(const bdh_stream* s);
+void bdh_stream_cols(const bdh_stream* s, bdk_soa* out);
+int bdh_stream_nrg(const bdh_stream* s);
+const int32_t* bdh_stream_rg_lib(const bdh_stream* s);
+const int32_t* bdh_stream_rg_bam(const bdh_stream* s);
+int bdh_stream_ntid(const bdh_stream* s);
+const char* bdh_stream_tid_name(const bdh_stream* s, int tid);
+/* Raw record access (keep_records): query name, and FASTQ text of record i
+ * (Alignment::to_fastq, src/lib/io/Alignment.cpp:66-84). Returns bytes written or -1. */
+const char* bdh_stream_qname(const bdh_stream* s, uint64_t i);
+int bdh_stream_fastq(const bdh_stream* s, uint64_t i, char* buf, int cap);
+/* seconds spent in (inflate, parse+extract, merge) by the last open */
+void bdh_stream_timings(const bdh_stream* s, double* inflate_s, double* extract_s, double* merge_s);
+
+/* ---- BAM writer for synthetic inputs (stands in for samtools' bam_write1) ------------------
+ * Writes n records from struct-of-arrays columns as a BGZF-compressed BAM with query names
+ * "<prefix><qid>", one RG:Z tag per record (rg_names[rgid]), AM:i = mapq when write_am != 0,
+ * CIGAR <qlen>M, and a deterministic base/quality pattern. */
+int bdh_write_bam(const char* path, int ntid, const char* const* tid_names, const uint32_t* tid_lens,
+                  int nrg, const char* const* rg_names, const bdk_soa* cols, uint64_t n,
+                  const char* name_prefix, int write_am, int level, int threads, char* err, int errcap);
+
+/* ---- output --------------------------------------------------------------------------------
+ * Text of the reference's stdout: the "#Library Statistics" header block
+ * (src/exe/breakdancer-max/BreakDancerMax.cpp:82-153) and the SV rows
+ * (src/lib/breakdancer/BreakDancer.cpp:377-497). names = { lib_names, bam_names } (two arrays of
+ * C strings); sticky carries the stream's "fixed, precision 2" state between calls. Both return
+ * the text length; the text is stored only if it fits in cap (with NUL). */
+int64_t bdh_format_header(const bdk_params* p, const bdk_summary_t* s, const void* names, int print_af,
+                          char* buf, int64_t cap);
+int64_t bdh_format_rows(const bdk_params* p, const bdk_result* r, const void* names, const void* tid_names,
+                        int print_af, int* sticky, char* buf, int64_t cap);
+/* BamConfigEntry::translate_token (src/lib/io/BamConfigEntry.cpp:31-59): Field ordinal, 10 = UNKNOWN */
+int bdh_config_translate_token(const char* key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDK_HOST_H */
