@@ -1,0 +1,531 @@
+// bdk_logic.h -- the per-record and per-connection logic of the hot path, written once as
+// __host__ __device__ inline functions.  The CUDA kernels (k1..k4 in this directory) call these
+// from device code; tests/hostsim compiles the very same functions for the host so the logic
+// (not the parallel mechanics) can be checked against the oracle without a GPU.
+//
+// Reference code restated here (paths relative to the reference root, commit 4e44b43):
+//   classify_record    IlluminaPEReadClassifier.cpp:13-101, Alignment.hpp:72-159,
+//                      BamSummary.cpp:70-113 (pass 1), BreakDancer.cpp:150-207 (pass 2)
+//   poisson_log_sf     boost poisson complement cdf as used by ComputeProbScore, BreakDancer.cpp:62-68
+//   k4_*               build_connection / process_sv / SvBuilder / is_region_final / clear_region,
+//                      BreakDancer.cpp:266-512, SvBuilder.cpp:18-118, ReadRegionData.cpp:70-175
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "../../include/bdk.h"
+
+#if defined(__CUDACC__)
+#define BDK_HD __host__ __device__ __forceinline__
+#else
+#define BDK_HD inline
+#endif
+
+namespace bdk {
+
+// ---- IEEE fp32 without contraction (the reference is compiled for x86-64 without FMA) -------
+BDK_HD float f_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+BDK_HD float f_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+BDK_HD float f_sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
+BDK_HD float f_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+
+// ---- per-library constants as the kernels see them -------------------------------------------
+struct LibDev {
+    float upper, lower, mean;
+    int32_t min_mapq;   // effective: library override or -q
+    int32_t key;        // copy-number key: library index (-a) or the library's bam index
+};
+
+// ---- classification --------------------------------------------------------------------------
+// Result bits of classify_record()
+enum : uint32_t {
+    CR_FLAG_MASK = 0xF,        // pass-2 ReadFlag (after -l re-flag and RR->FF), valid if CR_KEPT
+    CR_KEPT = 1u << 4,         // survives push_read's filters (BreakDancer.cpp:159-167)
+    CR_MPROPER = 1u << 5,      // kept && proper_pair(): counts into nread_ROI/nread_FR (:172-175)
+    CR_ANOM = 1u << 6,         // kept && not NORMAL_FR/NORMAL_RF: enters the region builder
+    CR_SPROPER = 1u << 7,      // pass 1: bdqual > min_mapq && proper_pair() (BamSummary.cpp:80-87)
+    CR_HIST_SHIFT = 8,         // bits 8-11: pass-1 flag to count in read_counts_by_flag, 0 = none
+    CR_REV = 1u << 12          // reverse strand (ori() == REV)
+};
+
+BDK_HD int pe_classify_flags(uint32_t f, bool interchrom, bool leftmost, bool large_insert, bool small_insert) {
+    if ((f & 0x400u) || !(f & 0x1u)) return BDK_NA;          // dup || !paired
+    if (f & 0x4u) return BDK_UNMAPPED;
+    if (f & 0x8u) return BDK_MATE_UNMAPPED;
+    if (interchrom) return BDK_ARP_CTX;
+    bool rr = (f & 0x10u) != 0, mr = (f & 0x20u) != 0;
+    if (rr == mr) return rr ? BDK_ARP_RR : BDK_ARP_FF;
+    if (leftmost == rr) return BDK_ARP_RF;
+    if (large_insert) return BDK_ARP_LARGE_INSERT;
+    if (small_insert) return BDK_ARP_SMALL_INSERT;
+    return BDK_NORMAL_FR;
+}
+
+BDK_HD int long_insert_reflag(int flag, bool gt_upper, bool lt_upper, bool lt_lower) {
+    if (gt_upper && flag == BDK_NORMAL_RF) flag = BDK_ARP_RF;
+    if (lt_upper && flag == BDK_ARP_RF) flag = BDK_NORMAL_RF;
+    if (lt_lower && flag == BDK_NORMAL_RF) flag = BDK_ARP_SMALL_INSERT;
+    return flag;
+}
+
+struct ClassifyOpts {
+    int32_t max_sd;
+    int32_t transchr;
+    int32_t long_insert;
+};
+
+BDK_HD uint32_t classify_record(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
+                                uint32_t bdqual, const LibDev& L, const ClassifyOpts& o) {
+    int32_t a = isize < 0 ? -isize : isize;   // abs(core.isize)
+    float af = (float)a;                      // int -> float conversion of the reference's compares
+    bool gt_upper = af > L.upper, lt_upper = af < L.upper, lt_lower = af < L.lower;
+    bool inter = tid != mtid;
+    int cls = pe_classify_flags(flag, inter, pos < mpos, gt_upper, lt_lower);
+    bool proper = (flag & (0x2u | 0x4u | 0x8u | 0x1u | 0x400u)) == (0x2u | 0x1u);
+    bool either_unmapped = (flag & (0x4u | 0x8u)) != 0;
+    bool mapq_ok = (int32_t)bdqual > L.min_mapq;
+    uint32_t r = (flag & 0x10u) ? CR_REV : 0u;
+    bool base_ok = cls != BDK_NA && !either_unmapped && !(o.transchr && !inter);
+    int cls2 = o.long_insert ? long_insert_reflag(cls, gt_upper, lt_upper, lt_lower) : cls;
+    if (mapq_ok) {
+        if (proper) r |= CR_SPROPER;
+        if (base_ok && cls2 != BDK_NORMAL_FR && cls2 != BDK_NORMAL_RF) r |= (uint32_t)cls2 << CR_HIST_SHIFT;
+        if (base_ok && !(cls != BDK_ARP_CTX && a > o.max_sd)) {
+            int cls3 = cls2 == BDK_ARP_RR ? BDK_ARP_FF : cls2;
+            r |= CR_KEPT | (uint32_t)cls3;
+            if (proper) r |= CR_MPROPER;
+            if (cls3 != BDK_NORMAL_FR && cls3 != BDK_NORMAL_RF) r |= CR_ANOM;
+        }
+    }
+    return r;
+}
+
+// meta word of bdk_aread
+BDK_HD uint32_t make_meta(uint32_t cr, int lib, uint32_t bdqual) {
+    return (cr & CR_FLAG_MASK) | ((cr & CR_REV) ? 16u : 0u) | ((uint32_t)lib << 8) | ((bdqual & 0xFFu) << 16);
+}
+BDK_HD int meta_flag(uint32_t m) { return (int)(m & 0xF); }
+BDK_HD int meta_rev(uint32_t m) { return (int)((m >> 4) & 1); }
+BDK_HD int meta_lib(uint32_t m) { return (int)((m >> 8) & 0xFF); }
+
+// ---- Poisson / gamma -------------------------------------------------------------------------
+// Regularised lower incomplete gamma P(a, x) in double: series for x < a + 1, modified Lentz
+// continued fraction of Q otherwise. log P[Pois(lambda) > k] = log P(k + 1, lambda).
+// Each of P and Q is computed directly where it is the small one.
+BDK_HD void gamma_pq_d(double a, double x, double* p, double* q) {
+    if (!(x > 0.0)) { *p = 0.0; *q = 1.0; return; }
+    double lg = lgamma(a);
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 10000; ++n) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        *p = sum * exp(-x + a * log(x) - lg);
+        *q = 1.0 - *p;
+        return;
+    }
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 10000; ++i) {
+        double an = -(double)i * ((double)i - a);
+        b += 2.0;
+        d = an * d + b; if (fabs(d) < tiny) d = tiny;
+        c = b + an / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    *q = exp(-x + a * log(x) - lg) * h;
+    *p = 1.0 - *q;
+}
+BDK_HD double gamma_p_d(double a, double x) { double p, q; gamma_pq_d(a, x, &p, &q); return p; }
+BDK_HD double gamma_q_d(double a, double x) { double p, q; gamma_pq_d(a, x, &p, &q); return q; }
+BDK_HD double poisson_log_sf(double lambda, int k) { return log(gamma_p_d((double)k + 1.0, lambda)); }
+
+// ---- region building (K2) ----------------------------------------------------------------------
+// push_read's break test (BreakDancer.cpp:216)
+BDK_HD bool k2_is_break(int32_t prev_tid, int32_t prev_pos, int32_t tid, int32_t pos, int32_t window) {
+    return tid != prev_tid || pos - prev_pos > window;
+}
+
+struct CandAgg { int32_t ntot, maxlen, fwd, rev, nonctx; };
+
+// Candidate region = anomalous reads [s, e]. _ntotal_nucleotides / _max_readlen skip the
+// candidate's first read and include the read that triggers the break, i.e. range (s, e + 1]
+// (BreakDancer.cpp:209-212 run before the break test); the stream's last candidate has no
+// break read. fwd/rev/non-CTX counts are over [s, e] (ReadRegionData.cpp:99-107).
+BDK_HD CandAgg k2_cand_aggregate(const bdk_aread* ar, int64_t s, int64_t e, int64_t A) {
+    CandAgg g; g.ntot = 0; g.maxlen = 0; g.fwd = 0; g.rev = 0; g.nonctx = 0;
+    for (int64_t j = s; j <= e; ++j) {
+        uint32_t m = ar[j].meta;
+        if ((m & 0xF) != BDK_ARP_CTX) ++g.nonctx;
+        if (m & 16u) ++g.rev; else ++g.fwd;
+    }
+    int64_t hi = e + 1 < A ? e + 1 : A - 1;
+    for (int64_t j = s + 1; j <= hi; ++j) {
+        int32_t q = ar[j].qlen;
+        g.ntot += q;
+        if (q > g.maxlen) g.maxlen = q;
+    }
+    return g;
+}
+
+// process_breakpoint's acceptance test (BreakDancer.cpp:245-247)
+BDK_HD bool k2_accept(int32_t start_pos, int32_t end_pos, const CandAgg& g, int32_t min_len, int32_t cov_lim) {
+    float cov = f_div((float)g.ntot, (float)(end_pos - start_pos + 1 + g.maxlen));
+    return (end_pos - start_pos > min_len) && (cov < (float)cov_lim);
+}
+
+// ---- connection walk (K4) ----------------------------------------------------------------------
+struct RegionRec {            // BasicRegion + bookkeeping
+    int32_t tid, start, end;
+    int32_t fwd, rev;
+    int32_t first_read, n_reads;
+    int32_t stored;           // read vector kept (ReadRegionData.cpp:118-121)
+    int32_t cand;             // index of the candidate region it came from (time stamp)
+};
+
+struct DEdge {                // directed copy of one graph edge inside its flush window
+    int32_t win, src, dst, w;
+    int32_t flags;            // bit0: edge erased, bit1 (on the first edge of a src run): vertex erased
+};
+enum { DE_ERASED = 1, DE_VERASED = 2 };
+
+struct K4Static {
+    const bdk_aread* ar;
+    const int32_t* read_region;   // region index or -1 (collapsed)
+    const int32_t* read_cand;     // candidate index
+    const int32_t* mate;          // mate read index or -1
+    const RegionRec* reg;
+    const uint32_t* P;            // [nkey][A] inclusive proper-pair prefix counts per key
+    const int32_t* cand_maxlen;   // [ncand] _max_readlen when the candidate was closed
+    const LibDev* libs;
+    const uint32_t* hist;         // [nlib][BDK_NUM_FLAGS] pass-1 read_counts_by_flag
+    const float* density;         // [nkey]
+    uint64_t A;
+    int32_t nreg, ncand, period, nkey, nlib;
+    int32_t chr_restricted, min_read_pair, score_threshold, fisher;
+    uint32_t covered_ref_len;
+};
+
+struct K4Mut {
+    uint8_t* alive;         // [A] read still in its region's vector
+    uint8_t* freed;         // [A] name erased by erase_read (set on both mates)
+    uint8_t* deleted;       // [nreg] clear_region() happened
+    int32_t* sv_of_read;    // [A] row slot of the process_sv call that consumed the read, or -1
+    bdk_sv* rows;           // [nrow_cap]
+    int32_t* row_lib_count; // [nrow_cap][nlib]
+    int32_t* row_lib_span;  // [nrow_cap][nlib]
+    uint32_t* row_cn_count; // [nrow_cap][nkey]
+    float* row_cn;          // [nrow_cap][nkey]
+    uint8_t* row_emit;      // [nrow_cap]
+    uint64_t* row_key;      // [nrow_cap] (window << 32 | BFS start vertex)
+};
+
+struct WindowInfo { int32_t cF; int32_t maxlen; int32_t last_region; };
+
+BDK_HD WindowInfo k4_window_info(const K4Static& S, int w) {
+    WindowInfo wi;
+    int64_t trigger = ((int64_t)w + 1) * S.period - 1;
+    if (trigger < S.nreg) {          // flush triggered by the registration of region `trigger`
+        wi.cF = S.reg[trigger].cand;
+        wi.maxlen = S.cand_maxlen[wi.cF];
+        wi.last_region = (int32_t)trigger;
+    } else {                          // final build_connection (BreakDancer.cpp:536-541)
+        wi.cF = 0x7fffffff;
+        wi.maxlen = S.ncand > 0 ? S.cand_maxlen[S.ncand - 1] : 0;
+        wi.last_region = S.nreg - 1;
+    }
+    return wi;
+}
+
+// _read_regions.find(name) != end for read j at the flush whose trigger candidate is cF
+BDK_HD bool k4_exists(const K4Static& S, const K4Mut& M, int j, int cF) {
+    int m = S.mate[j];
+    if (m < 0) return true;
+    if (S.read_region[m] < 0)       // mate sat in a collapsed candidate: its collapse erased the name
+        return !(m > j && S.read_cand[m] < cF);
+    return !M.freed[j];
+}
+
+// _read_regions[name].size() == 2
+BDK_HD bool k4_size2(const K4Static& S, const K4Mut& M, int j, int cF) {
+    int m = S.mate[j];
+    if (m < 0) return false;
+    int rm = S.read_region[m];
+    if (rm < 0) return false;
+    if (S.read_cand[m] > cF) return false;      // mate's region not registered yet
+    if (M.freed[j]) return false;
+    if (M.deleted[rm] && M.alive[m]) return false;  // clear_region(rm) dropped rm from the entry
+    return true;
+}
+
+BDK_HD bool k4_region_final(const K4Static& S, const K4Mut& M, int v, const WindowInfo& wi) {
+    if (M.deleted[v] || v == wi.last_region) return false;
+    const RegionRec& R = S.reg[v];
+    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) {
+        if (!M.alive[j]) continue;
+        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
+        if (!k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF)) return false;
+    }
+    return true;
+}
+
+// process_sv for snodes = {s0, s1} (s1 < 0: single region). Returns true if a row was emitted
+// into slot `row`.
+BDK_HD bool k4_process_sv(const K4Static& S, K4Mut& M, int s0, int s1, int w, int v0, const WindowInfo& wi, int row) {
+    int n = s1 >= 0 ? 2 : 1;
+    int sn[2] = {s0, s1};
+    int flag_counts[BDK_NUM_FLAGS];
+    for (int i = 0; i < BDK_NUM_FLAGS; ++i) flag_counts[i] = 0;
+    int num_pairs = 0;
+    // pass 1: count pairs per flag (flag of the second-seen mate, SvBuilder.cpp:101-118)
+    for (int i = 0; i < n; ++i) {
+        const RegionRec& R = S.reg[sn[i]];
+        for (int y = R.first_read; y < R.first_read + R.n_reads; ++y) {
+            if (!M.alive[y] || !k4_exists(S, M, y, wi.cF)) continue;
+            int x = S.mate[y];
+            if (x < 0 || x >= y) continue;
+            int rx = S.read_region[x];
+            if ((rx != s0 && rx != s1) || rx < 0) continue;
+            if (!M.alive[x] || !k4_exists(S, M, x, wi.cF)) continue;
+            ++flag_counts[meta_flag(S.ar[y].meta)];
+            ++num_pairs;
+        }
+    }
+    int flag = BDK_NA, best = 0;
+    for (int i = 0; i < BDK_NUM_FLAGS; ++i)
+        if (flag_counts[i] > best) { best = flag_counts[i]; flag = i; }  // first maximum in enum order
+    bool early = num_pairs < S.min_read_pair || flag_counts[flag] < S.min_read_pair;
+    int32_t* lib_count = M.row_lib_count + (int64_t)row * S.nlib;
+    int32_t* lib_span = M.row_lib_span + (int64_t)row * S.nlib;
+    if (!early) for (int l = 0; l < S.nlib; ++l) { lib_count[l] = 0; lib_span[l] = 0; }
+    // pass 2: consume the pairs, drop reads whose name no longer exists
+    for (int i = 0; i < n; ++i) {
+        const RegionRec& R = S.reg[sn[i]];
+        for (int y = R.first_read; y < R.first_read + R.n_reads; ++y) {
+            if (!M.alive[y]) continue;
+            if (!k4_exists(S, M, y, wi.cF)) { M.alive[y] = 0; continue; }
+            int x = S.mate[y];
+            if (x < 0 || x >= y) continue;
+            int rx = S.read_region[x];
+            if ((rx != s0 && rx != s1) || rx < 0) continue;
+            if (!M.alive[x]) continue;
+            // pair (x, y): remove_reads_in_region_if(is_supportive) (BreakDancer.cpp:367-368)
+            M.alive[x] = 0; M.alive[y] = 0;
+            M.sv_of_read[x] = row; M.sv_of_read[y] = row;
+            if (!early) {
+                M.freed[x] = 1; M.freed[y] = 1;     // erase_read at the end (BreakDancer.cpp:510-511)
+                uint32_t my = S.ar[y].meta;
+                if (meta_flag(my) == flag) {
+                    int l = meta_lib(my);
+                    ++lib_count[l];
+                    lib_span[l] += S.ar[y].abs_isize;
+                }
+            }
+        }
+    }
+    M.row_emit[row] = 0;
+    if (early) return false;
+
+    const RegionRec& R0 = S.reg[s0];
+    int chr0 = R0.tid, chr1, pos0 = R0.start, pos1 = R0.end;
+    int fwd0 = R0.fwd, rev0 = R0.rev, fwd1, rev1;
+    int ml = wi.maxlen;
+    if (n == 2) {
+        const RegionRec& R1 = S.reg[s1];
+        if (flag == BDK_ARP_RF) pos1 = R1.end + ml - 5;
+        else if (flag == BDK_ARP_FF) { pos0 = pos1; pos1 = R1.end + ml - 5; }
+        else if (flag == BDK_ARP_RR) pos1 = R1.start;
+        else { pos0 = pos1; pos1 = R1.start; }
+        chr1 = R1.tid; fwd1 = R1.fwd; rev1 = R1.rev;
+    } else {
+        fwd1 = fwd0; rev1 = rev0; chr1 = R0.tid; pos1 = R0.end;
+    }
+    // copy number (accumulate_reads_between_regions telescopes to P[first read of s1] - P[last read of s0])
+    uint32_t* cnc = M.row_cn_count + (int64_t)row * S.nkey;
+    float* cnv = M.row_cn + (int64_t)row * S.nkey;
+    float cn_sum = 0.0f; int cn_n = 0;
+    for (int k = 0; k < S.nkey; ++k) {
+        uint32_t c = 0;
+        if (n == 2) {
+            const RegionRec& R1 = S.reg[s1];
+            c = S.P[(uint64_t)k * S.A + R1.first_read] - S.P[(uint64_t)k * S.A + (R0.first_read + R0.n_reads - 1)];
+        }
+        cnc[k] = c;
+        float v = 0.0f;
+        if (c) {
+            v = f_mul(f_div((float)c, f_mul(S.density[k], (float)(pos1 - pos0))), 2.0f);
+            cn_sum = f_add(cn_sum, v);
+            ++cn_n;
+        }
+        cnv[k] = v;
+    }
+    cn_sum = f_div(cn_sum, f_mul(2.0f, (float)cn_n));
+    float af = f_sub(1.0f, cn_sum);
+
+    if (flag != BDK_ARP_RF && flag != BDK_ARP_RR && pos0 + ml - 5 < pos1) pos0 += ml - 5;
+
+    float diff = 0.0f;
+    for (int l = 0; l < S.nlib; ++l)
+        if (lib_count[l])
+            diff = f_add(diff, f_sub((float)lib_span[l], f_mul((float)lib_count[l], S.libs[l].mean)));
+    int diffspan = (int)((double)f_div(diff, (float)flag_counts[flag]) + 0.5);
+
+    int total_region_size = (R0.end - R0.start + 1) + (n == 2 ? (S.reg[s1].end - S.reg[s1].start + 1) : 0);
+    double logp = 0.0, err = 0.0;
+    int nl = 0;
+    for (int l = 0; l < S.nlib; ++l) {
+        if (!lib_count[l]) continue;
+        ++nl;
+        uint32_t cnt = S.hist[l * BDK_NUM_FLAGS + flag];
+        double lambda = (double)total_region_size * ((double)cnt / (double)S.covered_ref_len);
+        lambda = 1.0e-10 < lambda ? lambda : 1.0e-10;      // std::max(1e-10, lambda)
+        double tmp_a = poisson_log_sf(lambda, lib_count[l]) - err;
+        double tmp_b = logp + tmp_a;
+        err = (tmp_b - logp) - tmp_a;
+        logp = tmp_b;
+    }
+    if (S.fisher && logp < 0) {
+        double fp = gamma_q_d((double)nl, -logp);
+        logp = fp > exp(-99.0) ? log(fp) : -99.0;
+    }
+    double phred_tmp = -10.0 * logp / log(10.0);
+    int phred = phred_tmp > 99 ? 99 : (int)(phred_tmp + 0.5);
+    ++pos0; ++pos1;
+    if (!(phred > S.score_threshold)) return false;
+    bdk_sv& o = M.rows[row];
+    o.chr[0] = chr0; o.chr[1] = chr1; o.pos[0] = pos0; o.pos[1] = pos1;
+    o.fwd[0] = fwd0; o.fwd[1] = fwd1; o.rev[0] = rev0; o.rev[1] = rev1;
+    o.flag = flag; o.diffspan = diffspan; o.score = phred; o.num_pairs = flag_counts[flag];
+    o.logp = logp; o.allele_frequency = af; o.cn_present = 0;
+    o.region[0] = s0; o.region[1] = s1; o.window = w; o.order = 0;
+    M.row_key[row] = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;
+    M.row_emit[row] = 1;
+    return true;
+}
+
+// ---- in-place heap sort of a component's directed edges by (win, src, dst) --------------------
+BDK_HD bool de_less(const DEdge& a, const DEdge& b) {
+    if (a.win != b.win) return a.win < b.win;
+    if (a.src != b.src) return a.src < b.src;
+    return a.dst < b.dst;
+}
+BDK_HD void de_sift(DEdge* e, int start, int end) {
+    int root = start;
+    while (2 * root + 1 <= end) {
+        int child = 2 * root + 1, sw = root;
+        if (de_less(e[sw], e[child])) sw = child;
+        if (child + 1 <= end && de_less(e[sw], e[child + 1])) sw = child + 1;
+        if (sw == root) return;
+        DEdge t = e[root]; e[root] = e[sw]; e[sw] = t;
+        root = sw;
+    }
+}
+BDK_HD void de_sort(DEdge* e, int n) {
+    for (int s = (n - 2) / 2; s >= 0; --s) de_sift(e, s, n - 1);
+    for (int end = n - 1; end > 0; --end) {
+        DEdge t = e[end]; e[end] = e[0]; e[0] = t;
+        de_sift(e, 0, end - 1);
+    }
+}
+
+// first edge index of the run of `src` inside [lo, hi) (sorted by src within one window), or -1
+BDK_HD int de_find_src(const DEdge* e, int lo, int hi, int src) {
+    int a = lo, b = hi;
+    while (a < b) { int m = (a + b) >> 1; if (e[m].src < src) a = m + 1; else b = m; }
+    return (a < hi && e[a].src == src) ? a : -1;
+}
+
+// One connected component (over all windows) of the region graph: its directed edges
+// e[0..ne) (unsorted on entry), a queue scratch of ne + 2 ints, and row slots [row0, ...).
+// Walks the windows in order, doing for each what build_connection does for the part of the
+// graph that belongs to this component. Returns the number of row slots used.
+BDK_HD int k4_component(const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* queue, int row0) {
+    de_sort(e, ne);
+    int row = row0;
+    int i = 0;
+    while (i < ne) {
+        int w = e[i].win;
+        int j = i;
+        while (j < ne && e[j].win == w) ++j;
+        WindowInfo wi = k4_window_info(S, w);
+        // outer loop over vertices ascending (graph.begin() .. end())
+        int vi = i;
+        while (vi < j) {
+            int v = e[vi].src;
+            int vend = vi;
+            while (vend < j && e[vend].src == v) ++vend;
+            if (!(e[vi].flags & DE_VERASED)) {
+                // BFS from v; tails live in queue[qa..qb), newtails appended after
+                int qa = 0, qb = 0, qn;
+                queue[qb++] = v;
+                while (qa < qb) {
+                    qn = qb;
+                    for (int t = qa; t < qb; ++t) {
+                        int tail = queue[t];
+                        if (M.deleted[tail]) continue;                     // !region_exists(tail)
+                        int ts = de_find_src(e, i, j, tail);
+                        if (ts < 0 || (e[ts].flags & DE_VERASED)) continue; // graph.find(tail) == end
+                        for (int k = ts; k < j && e[k].src == tail; ++k) {
+                            if (e[k].flags & DE_ERASED) continue;
+                            e[k].flags |= DE_ERASED;
+                            int s1 = e[k].dst, nlinks = e[k].w;
+                            if (nlinks < S.min_read_pair || M.deleted[s1]) continue;
+                            if (tail != s1) {                               // erase_edge(s1, tail)
+                                int rs = de_find_src(e, i, j, s1);
+                                if (rs >= 0)
+                                    for (int q = rs; q < j && e[q].src == s1; ++q)
+                                        if (e[q].dst == tail) { e[q].flags |= DE_ERASED; break; }
+                            }
+                            queue[qn++] = s1;                               // newtails.push_back(s1)
+                            int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
+                            k4_process_sv(S, M, a, tail != s1 ? b : -1, w, v, wi, row);
+                            ++row;
+                        }
+                        e[ts].flags |= DE_VERASED;                          // graph.erase(tail)
+                    }
+                    qa = qb; qb = qn;
+                }
+            }
+            vi = vend;
+        }
+        // is_region_final / clear_region over the active nodes, ascending
+        for (vi = i; vi < j;) {
+            int v = e[vi].src;
+            if (k4_region_final(S, M, v, wi)) M.deleted[v] = 1;
+            while (vi < j && e[vi].src == v) ++vi;
+        }
+        i = j;
+    }
+    return row - row0;
+}
+
+}  // namespace bdk

@@ -1,0 +1,225 @@
+// hostsim.cpp -- runs the DEVICE logic of the hot path (breakdancer_b200/csrc/bdk_logic.h,
+// bdk_finalize.h: the __host__ __device__ functions the CUDA kernels call) on the host, stage by
+// stage in the same decomposition the GPU pipeline uses:
+//   K1 classify + compaction + proper-pair prefix counts    K2 break flags / candidates / regions
+//   K3 mate join + link sort + run-length                   K4 components + connection walk + score
+// with the parallel mechanics (scans, radix sort, hash join, atomics) replaced by trivial
+// sequential loops.  TEST HARNESS ONLY: built by tests/conftest.py into tests/_build/, never
+// linked into libbdk.so -- it lets `pytest -m "not gpu"` check the decomposition (telescoped
+// counts, time-stamp rules, per-component independence) against the oracle without a GPU.
+#include "../../breakdancer_b200/csrc/bdk_logic.h"
+#include "../../breakdancer_b200/csrc/bdk_finalize.h"
+#include "../../oracle/bdo_api.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+
+using namespace bdk;
+
+extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, bdo_output* out) {
+    const bdk_params& p = *pp;
+    int nkey = nkey_of(p), nlib = p.nlib;
+    std::vector<LibDev> libs = make_libdev(p);
+    ClassifyOpts co{p.max_sd, p.transchr_rearrange, p.illumina_long_insert};
+
+    // ---- K1 -----------------------------------------------------------------------------------
+    SummaryAcc acc;
+    acc.rg_sproper.assign(p.nrg, 0);
+    acc.hist.assign((size_t)nlib * BDK_NUM_FLAGS, 0);
+    acc.first.assign((size_t)p.nbam * p.ntid, ~0ull);
+    acc.last.assign((size_t)p.nbam * p.ntid, 0);
+    std::vector<bdk_aread> ar;
+    std::vector<std::vector<uint32_t>> P(nkey);
+    std::vector<uint32_t> run(nkey, 0);
+    std::vector<uint8_t> rec_class(n, 255);
+    for (uint64_t i = 0; i < n; ++i) {
+        int rg = c->rgid[i];
+        if (rg >= p.nrg || p.rg_lib[rg] < 0) return BDK_ERR_DATA;
+        int lib = p.rg_lib[rg], bam = p.rg_bam[rg];
+        uint32_t cr = classify_record(c->pos[i], c->mpos[i], c->tid[i], c->mtid[i], c->isize[i], c->flag[i], c->mapq[i], libs[lib], co);
+        uint64_t key = (i << 32) | (uint32_t)c->pos[i];
+        size_t bt = (size_t)bam * p.ntid + c->tid[i];
+        if (acc.first[bt] == ~0ull) acc.first[bt] = key;   // device: atomicMin / atomicMax of the same key
+        acc.last[bt] = key;
+        if (cr & CR_SPROPER) ++acc.rg_sproper[rg];
+        int hf = (cr >> CR_HIST_SHIFT) & 0xF;
+        if (hf) ++acc.hist[lib * BDK_NUM_FLAGS + hf];
+        if (cr & CR_KEPT) rec_class[i] = cr & CR_FLAG_MASK;
+        if (cr & CR_MPROPER) ++run[libs[lib].key];
+        if (cr & CR_ANOM) {
+            bdk_aread a;
+            a.pos = c->pos[i]; a.tid = c->tid[i]; a.qlen = c->qlen[i];
+            a.abs_isize = c->isize[i] < 0 ? -c->isize[i] : c->isize[i];
+            a.meta = make_meta(cr, lib, c->mapq[i]); a.record = (uint32_t)i; a.qid = c->qid[i];
+            ar.push_back(a);
+            for (int k = 0; k < nkey; ++k) P[k].push_back(run[k]);
+        }
+    }
+    int64_t A = (int64_t)ar.size();
+    bdk_summary_t S;
+    std::vector<float> density;
+    finalize_summary(p, acc, n, A, &S, &density);
+    int window = S.window;
+
+    // ---- K2 -----------------------------------------------------------------------------------
+    std::vector<int32_t> read_cand(A), read_region(A, -1);
+    std::vector<int64_t> cand_first;
+    for (int64_t j = 0; j < A; ++j) {
+        bool brk = j == 0 || k2_is_break(ar[j - 1].tid, ar[j - 1].pos, ar[j].tid, ar[j].pos, window);
+        if (brk) cand_first.push_back(j);
+        read_cand[j] = (int32_t)cand_first.size() - 1;
+    }
+    int ncand = (int)cand_first.size();
+    std::vector<int32_t> cand_maxlen(ncand);
+    std::vector<RegionRec> reg;
+    int dummy = (A > 0) ? dummy_region_of(p) : 0;
+    if (dummy) { RegionRec d; d.tid = -1; d.start = -1; d.end = -1; d.fwd = d.rev = 0; d.first_read = 0; d.n_reads = 0; d.stored = 0; d.cand = -1; reg.push_back(d); }
+    std::vector<uint8_t> alive(A, 0);
+    for (int cidx = 0; cidx < ncand; ++cidx) {
+        int64_t s = cand_first[cidx], e = (cidx + 1 < ncand ? cand_first[cidx + 1] : A) - 1;
+        CandAgg g = k2_cand_aggregate(ar.data(), s, e, A);
+        cand_maxlen[cidx] = g.maxlen;
+        if (k2_accept(ar[s].pos, ar[e].pos, g, p.min_len, p.seq_coverage_lim)) {
+            RegionRec R;
+            R.tid = ar[s].tid; R.start = ar[s].pos; R.end = ar[e].pos; R.fwd = g.fwd; R.rev = g.rev;
+            R.first_read = (int32_t)s; R.n_reads = (int32_t)(e - s + 1);
+            int valid = p.chr_restricted ? g.nonctx : R.n_reads;
+            R.stored = valid >= p.min_read_pair; R.cand = cidx;
+            for (int64_t j = s; j <= e; ++j) { read_region[j] = (int32_t)reg.size(); alive[j] = R.stored; }
+            reg.push_back(R);
+        }
+    }
+    int nreg = (int)reg.size();
+    int period = period_of(p);
+
+    // ---- K3: mate join, links, sort + run-length ------------------------------------------------
+    std::vector<int32_t> mate(A, -1);
+    {
+        std::unordered_map<uint64_t, int32_t> seen;
+        for (int64_t j = 0; j < A; ++j) {
+            auto it = seen.find(ar[j].qid);
+            if (it == seen.end()) seen[ar[j].qid] = (int32_t)j;
+            else { mate[j] = it->second; mate[it->second] = (int32_t)j; }
+        }
+    }
+    std::vector<uint64_t> links;
+    for (int64_t y = 0; y < A; ++y) {
+        int x = mate[y];
+        if (x >= 0 && x < y && read_region[x] >= 0 && read_region[y] >= 0)
+            links.push_back(((uint64_t)(uint32_t)read_region[x] << 32) | (uint32_t)read_region[y]);
+    }
+    std::sort(links.begin(), links.end());
+    struct UEdge { int r0, r1, w; };
+    std::vector<UEdge> ue;
+    for (size_t i = 0; i < links.size();) {
+        size_t j = i;
+        while (j < links.size() && links[j] == links[i]) ++j;
+        ue.push_back({(int)(links[i] >> 32), (int)(links[i] & 0xffffffffu), (int)(j - i)});
+        i = j;
+    }
+    // ---- components (union-find, smaller root wins) ----------------------------------------------
+    std::vector<int> parent(nreg);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (auto const& e : ue) { int a = find(e.r0), b = find(e.r1); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } }
+    std::vector<int> comp_ne(nreg, 0), comp_strong(nreg, 0);
+    for (auto const& e : ue) { int r = find(e.r0); comp_ne[r] += e.r0 == e.r1 ? 1 : 2; if (e.w >= p.min_read_pair) ++comp_strong[r]; }
+    std::vector<int> de_off(nreg + 1, 0), row_off(nreg + 1, 0);
+    for (int r = 0; r < nreg; ++r) { de_off[r + 1] = de_off[r] + comp_ne[r]; row_off[r + 1] = row_off[r] + comp_strong[r]; }
+    std::vector<DEdge> de(de_off[nreg] + 1);
+    std::vector<int> fill(nreg, 0);
+    for (auto const& e : ue) {
+        int r = find(e.r0);
+        int win = e.r1 / period;  // r0 <= r1: the edge is counted when r1 is registered
+        de[de_off[r] + fill[r]++] = DEdge{win, e.r0, e.r1, e.w, 0};
+        if (e.r0 != e.r1) de[de_off[r] + fill[r]++] = DEdge{win, e.r1, e.r0, e.w, 0};
+    }
+    int nrow_cap = row_off[nreg];
+
+    // ---- K4 -----------------------------------------------------------------------------------
+    std::vector<uint32_t> Pflat((size_t)nkey * std::max<int64_t>(A, 1));
+    for (int k = 0; k < nkey; ++k) std::copy(P[k].begin(), P[k].end(), Pflat.begin() + (size_t)k * A);
+    std::vector<uint8_t> freed(A, 0), deleted(nreg, 0), row_emit(nrow_cap + 1, 0);
+    std::vector<int32_t> sv_of_read(A, -1), row_lib_count((size_t)(nrow_cap + 1) * nlib), row_lib_span((size_t)(nrow_cap + 1) * nlib);
+    std::vector<uint32_t> row_cn_count((size_t)(nrow_cap + 1) * nkey);
+    std::vector<float> row_cn((size_t)(nrow_cap + 1) * nkey);
+    std::vector<bdk_sv> rows(nrow_cap + 1);
+    std::vector<uint64_t> row_key(nrow_cap + 1, 0);
+    K4Static KS;
+    KS.ar = ar.data(); KS.read_region = read_region.data(); KS.read_cand = read_cand.data(); KS.mate = mate.data();
+    KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.libs = libs.data();
+    KS.hist = acc.hist.data(); KS.density = density.data(); KS.A = (uint64_t)A; KS.nreg = nreg; KS.ncand = ncand;
+    KS.period = period; KS.nkey = nkey; KS.nlib = nlib; KS.chr_restricted = p.chr_restricted;
+    KS.min_read_pair = p.min_read_pair; KS.score_threshold = p.score_threshold; KS.fisher = p.fisher;
+    KS.covered_ref_len = S.covered_ref_len;
+    K4Mut KM;
+    KM.alive = alive.data(); KM.freed = freed.data(); KM.deleted = deleted.data(); KM.sv_of_read = sv_of_read.data();
+    KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
+    KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
+    std::vector<int32_t> queue;
+    for (int r = 0; r < nreg; ++r) {
+        if (!comp_ne[r]) continue;
+        queue.assign(comp_ne[r] + 2, 0);
+        int used = k4_component(KS, KM, de.data() + de_off[r], comp_ne[r], queue.data(), row_off[r]);
+        if (used > comp_strong[r]) return -100;
+    }
+    // final order: stable by (window, BFS start vertex), slot order inside
+    std::vector<int> order;
+    for (int r = 0; r < nrow_cap; ++r) if (row_emit[r]) order.push_back(r);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_key[a] < row_key[b]; });
+
+    // ---- pack outputs ---------------------------------------------------------------------------
+    memset(out, 0, sizeof(*out));
+    out->summary = S; out->nkey = nkey;
+    size_t ns = order.size();
+    out->n_sv = ns;
+    out->sv = (bdk_sv*)calloc(ns + 1, sizeof(bdk_sv));
+    out->lib_count = (int32_t*)calloc(ns * nlib + 1, 4);
+    out->cn_count = (uint32_t*)calloc(ns * nkey + 1, 4);
+    out->copy_number = (float*)calloc(ns * nkey + 1, 4);
+    std::vector<int> slot_to_order(nrow_cap + 1, -1);
+    for (size_t i = 0; i < ns; ++i) {
+        int r = order[i];
+        slot_to_order[r] = (int)i;
+        out->sv[i] = rows[r]; out->sv[i].order = (int)i;
+        memcpy(out->lib_count + i * nlib, &row_lib_count[(size_t)r * nlib], nlib * 4);
+        memcpy(out->cn_count + i * nkey, &row_cn_count[(size_t)r * nkey], nkey * 4);
+        memcpy(out->copy_number + i * nkey, &row_cn[(size_t)r * nkey], nkey * 4);
+    }
+    out->n_regions = nreg;
+    out->regions = (bdk_region*)calloc(nreg + 1, sizeof(bdk_region));
+    out->region_alive = (uint8_t*)calloc(nreg + 1, 1);
+    for (int r = 0; r < nreg; ++r) {
+        bdk_region& o = out->regions[r];
+        o.tid = reg[r].tid; o.start = reg[r].start; o.end = reg[r].end; o.fwd = reg[r].fwd; o.rev = reg[r].rev;
+        o.first_read = reg[r].first_read; o.n_reads = reg[r].n_reads; o.stored = reg[r].stored; o.window = r / period;
+        out->region_alive[r] = !deleted[r];
+    }
+    out->n_areads = A;
+    out->areads = (bdk_aread*)calloc(A + 1, sizeof(bdk_aread));
+    if (A) memcpy(out->areads, ar.data(), A * sizeof(bdk_aread));
+    out->aread_region = (int32_t*)calloc(A + 1, 4);
+    if (A) memcpy(out->aread_region, read_region.data(), A * 4);
+    out->sv_of_read = (int32_t*)calloc(A + 1, 4);
+    for (int64_t j = 0; j < A; ++j) out->sv_of_read[j] = sv_of_read[j] >= 0 ? slot_to_order[sv_of_read[j]] : -1;
+    out->rec_class = (uint8_t*)malloc(n + 1);
+    memcpy(out->rec_class, rec_class.data(), n);
+    out->support_off = (uint64_t*)calloc(ns + 1, 8);
+    out->support = (uint32_t*)calloc(1, 4);
+    out->n_flush = nreg / period + 1;
+    return 0;
+}
+
+extern "C" double hostsim_poisson_logsf(double lambda, int k) { return poisson_log_sf(lambda, k); }
+extern "C" double hostsim_gamma_q(double a, double x) { return gamma_q_d(a, x); }
+extern "C" uint32_t hostsim_classify(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
+                                     uint32_t bdqual, float upper, float lower, int32_t min_mapq, int32_t max_sd,
+                                     int32_t transchr, int32_t long_insert) {
+    LibDev L{upper, lower, 0.0f, min_mapq, 0};
+    ClassifyOpts o{max_sd, transchr, long_insert};
+    return classify_record(pos, mpos, tid, mtid, isize, flag, bdqual, L, o);
+}
