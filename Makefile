@@ -17,13 +17,13 @@ LIB   := $(PKG)/libbdk.so
 CLI   := $(PKG)/bin/breakdancer_max
 ORA   := oracle/_build/libbdoracle.so
 
-HOST_SRCS := $(SRC)/host/config.cpp $(SRC)/host/bam_io.cpp $(SRC)/host/format.cpp $(SRC)/host/options.cpp
+HOST_SRCS := $(SRC)/host/config.cpp $(SRC)/host/bam_io.cpp $(SRC)/host/format.cpp $(SRC)/host/options.cpp $(SRC)/host/support.cpp
 HOST_OBJS := $(patsubst $(SRC)/host/%.cpp,$(B)/host_%.o,$(HOST_SRCS))
 CU_HDRS   := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/bdk.h
 
 all: $(LIB) $(CLI) $(ORA)
 
-$(B)/host_%.o: $(SRC)/host/%.cpp $(SRC)/host/host.hpp include/bdk.h include/bdk_host.h
+$(B)/host_%.o: $(SRC)/host/%.cpp $(SRC)/host/host.hpp $(SRC)/host/cli.hpp include/bdk.h include/bdk_host.h
 	@mkdir -p $(B)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 

@@ -1,0 +1,692 @@
+// bdk_core.cu -- the per-GPU context behind the bdk C ABI (include/bdk.h): device memory,
+// streams, and the launch sequence  K1 classify -> unit scan -> reorder -> finalize -> K2 regions
+// -> K3 mate join / link sort / run-length / components -> K4 connection walk + score.
+// There is no CPU implementation of any stage in this library: every entry point that computes
+// needs a CUDA device and fails with BDK_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/bdk.h"
+#include "bdk_finalize.h"
+#include "k1_classify.cuh"
+#include "k234_regions_links_sv.cuh"
+#include "scan_sort.cuh"
+
+using namespace bdk;
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_err_mu;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct StageTimer {
+    const char* name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0.0f;
+    int launches = 0;
+    bool pending = false;
+};
+
+enum { T_H2D = 0, T_K1, T_SCAN_REORDER, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_N };
+const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_scan_reorder", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results"};
+
+}  // namespace
+
+struct bdk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+    bdk_params P;
+    std::vector<bdk_lib> libs;
+    std::vector<int32_t> rg_lib, rg_bam;
+    int nkey = 1, period = 1;
+    std::string err;
+
+    // constants on the device
+    DevBuf d_libdev, d_rg_info, d_blibs, d_rg_lib, d_rg_bam;
+    // pass-1 accumulators: one block so it can be snapshotted before a push
+    DevBuf d_acc, d_acc_bak;
+    size_t acc_bytes = 0, off_first = 0, off_last = 0, off_hist = 0, off_err = 0, off_cursor = 0;
+    // per-job state
+    uint64_t n_records = 0;       // records pushed so far
+    uint64_t n_units = 0, n_tiles = 0;
+    uint32_t A = 0;               // anomalous reads staged so far
+    DevBuf d_unit_cnt, d_unit_p, d_tile_seg, d_stage, d_stage_p;
+    uint32_t stage_cap = 0;
+    // chunk buffers for host pushes
+    DevBuf d_chunk[2][10];
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // finish() work space
+    DevBuf d_cnt, d_cnt_off, d_p_off, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
+        d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_links, d_links_tmp,
+        d_sort_hist, d_edge_key, d_edge_start, d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
+        d_deleted, d_de, d_queue, d_rows, d_row_lib_count, d_row_lib_span, d_row_cn_count, d_row_cn, d_row_emit, d_row_key,
+        d_pois_l, d_pois_k, d_pois_o;
+    bool finished = false, summary_ready = false;
+    int k1_blocks_per_sm = 0;
+    // host results
+    bdk_summary_t h_summary;
+    std::vector<bdk_sv> h_sv;
+    std::vector<int32_t> h_lib_count;
+    std::vector<uint32_t> h_cn_count;
+    std::vector<float> h_copy_number;
+    std::vector<bdk_region> h_regions;
+    std::vector<bdk_aread> h_areads;
+    std::vector<int32_t> h_read_region, h_sv_of_read, h_slot_order;
+    uint32_t h_cnt[CNT_N] = {0};
+    StageTimer timers[T_N];
+};
+
+namespace {
+
+int fail(bdk_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    else { std::lock_guard<std::mutex> g(g_err_mu); g_create_error = buf; }
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(c, BDK_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int ensure(bdk_ctx* c, DevBuf& b, size_t bytes, bool preserve = false) {
+    if (bytes <= b.cap && b.p) return 0;
+    size_t ncap = std::max<size_t>(bytes + bytes / 4, 256);
+    void* np = nullptr;
+    CU(cudaMalloc(&np, ncap));
+    if (preserve && b.p && b.cap) CU(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, c->stream));
+    if (b.p) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(b.p)); }
+    b.p = np; b.cap = ncap;
+    return 0;
+}
+#define ENS(buf, bytes) do { int rc_ = ensure(c, buf, (bytes)); if (rc_) return rc_; } while (0)
+#define ENSP(buf, bytes) do { int rc_ = ensure(c, buf, (bytes), true); if (rc_) return rc_; } while (0)
+
+void tstart(bdk_ctx* c, int t) { cudaEventRecord(c->timers[t].e0, c->stream); }
+void tstop(bdk_ctx* c, int t) { cudaEventRecord(c->timers[t].e1, c->stream); c->timers[t].pending = true; c->timers[t].launches++; }
+void tcollect(bdk_ctx* c) {
+    for (int t = 0; t < T_N; ++t)
+        if (c->timers[t].pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->timers[t].e0, c->timers[t].e1) == cudaSuccess) c->timers[t].ms += ms;
+            c->timers[t].pending = false;
+        }
+}
+
+int reset_job(bdk_ctx* c) {
+    c->n_records = 0; c->n_units = 0; c->n_tiles = 0; c->A = 0;
+    c->finished = false; c->summary_ready = false;
+    // accumulators: counts 0, first = ~0, last = 0
+    CU(cudaMemsetAsync(c->d_acc.p, 0, c->acc_bytes, c->stream));
+    size_t nbt = (size_t)c->P.nbam * c->P.ntid;
+    if (nbt) CU(cudaMemsetAsync((char*)c->d_acc.p + c->off_first, 0xff, nbt * 8, c->stream));
+    for (int t = 0; t < T_N; ++t) { c->timers[t].ms = 0; c->timers[t].launches = 0; c->timers[t].pending = false; }
+    return 0;
+}
+
+// one K1 launch over n records whose columns are on the device
+int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, uint64_t unit_base, uint64_t tile_base) {
+    K1Args a;
+    a.c = cols; a.n = n; a.base_index = base_index;
+    a.libs = c->d_libdev.as<LibDev>(); a.rg_info = c->d_rg_info.as<uint32_t>();
+    a.nrg = c->P.nrg; a.nlib = c->P.nlib; a.nbam = c->P.nbam; a.nkey = c->nkey; a.ntid = c->P.ntid;
+    a.nrg_smem = c->P.nrg <= 2048 ? c->P.nrg : 0;
+    a.co.max_sd = c->P.max_sd; a.co.transchr = c->P.transchr_rearrange; a.co.long_insert = c->P.illumina_long_insert;
+    a.stage = c->d_stage.as<bdk_aread>(); a.stage_p = c->d_stage_p.as<uint32_t>(); a.stage_cap = c->stage_cap;
+    char* acc = (char*)c->d_acc.p;
+    a.cursor = (uint32_t*)(acc + c->off_cursor);
+    a.unit_cnt = c->d_unit_cnt.as<uint32_t>(); a.unit_p = c->d_unit_p.as<uint32_t>(); a.tile_seg = c->d_tile_seg.as<uint32_t>();
+    a.unit_base = unit_base; a.tile_base = tile_base;
+    a.rg_sproper = (unsigned long long*)acc;
+    a.first = (unsigned long long*)(acc + c->off_first); a.last = (unsigned long long*)(acc + c->off_last);
+    a.hist = (uint32_t*)(acc + c->off_hist); a.err = (uint32_t*)(acc + c->off_err);
+    const size_t smem = ((size_t)a.nlib * BDK_NUM_FLAGS + a.nrg_smem) * 4;
+    const uint64_t ntiles = div_up<uint64_t>(n, K1_TILE);
+    if (!c->k1_blocks_per_sm) {
+        int bps = 0;
+        if (c->nkey == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_classify_kernel<true>, K1_THREADS, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_classify_kernel<false>, K1_THREADS, smem);
+        c->k1_blocks_per_sm = std::max(1, bps);
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)kNumSMs * c->k1_blocks_per_sm);
+    if (!grid) return 0;
+    if (c->nkey == 1) k1_classify_kernel<true><<<grid, K1_THREADS, smem, c->stream>>>(a);
+    else k1_classify_kernel<false><<<grid, K1_THREADS, smem, c->stream>>>(a);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int grow_tables(bdk_ctx* c, uint64_t add_tiles) {
+    const uint64_t tiles = c->n_tiles + add_tiles, units = tiles * K1_WARPS;
+    ENSP(c->d_unit_cnt, units * 4);
+    ENSP(c->d_unit_p, units * 4 * c->nkey);
+    ENSP(c->d_tile_seg, tiles * 4);
+    return 0;
+}
+
+int grow_stage(bdk_ctx* c, uint64_t want) {
+    if (want <= c->stage_cap) return 0;
+    if (want > 0xfffffff0ull) return fail(c, BDK_ERR_NOMEM, "more than 2^32 anomalous reads in one context");
+    ENSP(c->d_stage, want * sizeof(bdk_aread));
+    ENSP(c->d_stage_p, want * 4 * c->nkey);
+    c->stage_cap = (uint32_t)want;
+    return 0;
+}
+
+// push of one batch whose columns are already device pointers; handles staging overflow by retry
+template <class RunFn>
+int push_common(bdk_ctx* c, uint64_t n, RunFn run) {
+    if (c->finished) return fail(c, BDK_ERR_STATE, "bdk_push after bdk_finish (call bdk_reset first)");
+    if (n == 0) return 0;
+    if (c->n_records + n > 0xffffffffull) return fail(c, BDK_ERR_ARG, "more than 2^32 records in one context");
+    const uint64_t tiles = div_up<uint64_t>(n, K1_TILE);
+    int rc = grow_tables(c, tiles);
+    if (rc) return rc;
+    rc = grow_stage(c, std::max<uint64_t>((uint64_t)c->A + std::max<uint64_t>(n / 16, 1 << 16), c->stage_cap));
+    if (rc) return rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CU(cudaMemcpyAsync(c->d_acc_bak.p, c->d_acc.p, c->acc_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        rc = run();
+        if (rc) return rc;
+        uint32_t tail[2];   // err, cursor
+        CU(cudaMemcpyAsync(tail, (char*)c->d_acc.p + c->off_err, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        tcollect(c);
+        if (tail[0] & K1_ERR_RG)
+            return fail(c, BDK_ERR_DATA, "library index out of range (a record's read group has no library)");
+        if (tail[0] & K1_ERR_OVERFLOW) {   // staging too small: restore the accumulators, grow, run again
+            CU(cudaMemcpyAsync(c->d_acc.p, c->d_acc_bak.p, c->acc_bytes, cudaMemcpyDeviceToDevice, c->stream));
+            rc = grow_stage(c, (uint64_t)tail[1] + (tail[1] - c->A) / 8 + 1024);
+            if (rc) return rc;
+            continue;
+        }
+        c->A = tail[1];
+        c->summary_ready = false;
+        c->n_records += n; c->n_tiles += tiles; c->n_units += tiles * K1_WARPS;
+        return 0;
+    }
+    return fail(c, BDK_ERR_NOMEM, "staging overflow persisted");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bdk_version(void) { return "breakdancer-b200 0.1 (sm_100a)"; }
+
+const char* bdk_last_error(const bdk_ctx* c) {
+    if (c) return c->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mu);
+    return g_create_error.c_str();
+}
+
+void* bdk_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void bdk_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void bdk_destroy(bdk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* all[] = {&c->d_libdev, &c->d_rg_info, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_unit_cnt,
+        &c->d_unit_p, &c->d_tile_seg, &c->d_stage, &c->d_stage_p, &c->d_cnt, &c->d_cnt_off, &c->d_p_off, &c->d_ar, &c->d_P, &c->d_summary,
+        &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
+        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
+        &c->d_edge_key, &c->d_edge_start, &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
+        &c->d_deleted, &c->d_de, &c->d_queue, &c->d_rows, &c->d_row_lib_count, &c->d_row_lib_span, &c->d_row_cn_count, &c->d_row_cn,
+        &c->d_row_emit, &c->d_row_key, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
+    for (DevBuf* b : all) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 2; ++i) {
+        for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    for (int t = 0; t < T_N; ++t) { if (c->timers[t].e0) cudaEventDestroy(c->timers[t].e0); if (c->timers[t].e1) cudaEventDestroy(c->timers[t].e1); }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
+    bdk_ctx* c = nullptr;
+    if (!out || !p) return fail(c, BDK_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (p->nlib < 1 || p->nlib > BDK_MAX_LIBS) return fail(c, BDK_ERR_ARG, "number of libraries must be in [1, %d]", BDK_MAX_LIBS);
+    if (p->nbam < 1 || p->nbam > BDK_MAX_BAMS) return fail(c, BDK_ERR_ARG, "number of bams must be in [1, %d]", BDK_MAX_BAMS);
+    if (p->nrg < 1 || p->nrg > 65536) return fail(c, BDK_ERR_ARG, "number of read groups must be in [1, 65536]");
+    if (p->ntid < 1) return fail(c, BDK_ERR_ARG, "ntid must be >= 1");
+    if (p->min_read_pair < 1) return fail(c, BDK_ERR_ARG, "-r (min_read_pair) must be >= 1");
+    if (p->cn_lib && p->nlib > K1_MAXK) return fail(c, BDK_ERR_ARG, "-a supports at most %d libraries", K1_MAXK);
+    if (!p->libs || !p->rg_lib || !p->rg_bam) return fail(c, BDK_ERR_ARG, "null table in bdk_params");
+    for (int i = 0; i < p->nlib; ++i)
+        if (p->libs[i].bam_index < 0 || p->libs[i].bam_index >= p->nbam) return fail(c, BDK_ERR_ARG, "library %d: bam_index out of range", i);
+    for (int i = 0; i < p->nrg; ++i) {
+        if (p->rg_lib[i] >= p->nlib) return fail(c, BDK_ERR_ARG, "rg_lib[%d] out of range", i);
+        if (p->rg_bam[i] < 0 || p->rg_bam[i] >= p->nbam) return fail(c, BDK_ERR_ARG, "rg_bam[%d] out of range", i);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(c, BDK_ERR_CUDA, "no CUDA device available (%s); the bdk hot path has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(c, BDK_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    c = new bdk_ctx;
+    c->device = device;
+    c->P = *p;
+    c->libs.assign(p->libs, p->libs + p->nlib);
+    c->rg_lib.assign(p->rg_lib, p->rg_lib + p->nrg);
+    c->rg_bam.assign(p->rg_bam, p->rg_bam + p->nrg);
+    c->P.libs = c->libs.data(); c->P.rg_lib = c->rg_lib.data(); c->P.rg_bam = c->rg_bam.data();
+    c->nkey = nkey_of(c->P); c->period = period_of(c->P);
+#define CUC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            int rc_ = fail(nullptr, BDK_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));  \
+            bdk_destroy(c);                                                                         \
+            return rc_;                                                                             \
+        }                                                                                           \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 2; ++i) { CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)); CUC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming)); }
+    for (int t = 0; t < T_N; ++t) { c->timers[t].name = kTimerNames[t]; CUC(cudaEventCreate(&c->timers[t].e0)); CUC(cudaEventCreate(&c->timers[t].e1)); }
+    // constant tables
+    std::vector<LibDev> ld = make_libdev(c->P);
+    std::vector<uint32_t> rgi(p->nrg);
+    for (int i = 0; i < p->nrg; ++i)
+        rgi[i] = p->rg_lib[i] < 0 ? RG_INVALID : ((uint32_t)p->rg_lib[i] | ((uint32_t)p->rg_bam[i] << 8));
+    auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e1 = cudaMalloc(&b.p, std::max<size_t>(bytes, 16));
+        if (e1 != cudaSuccess) return e1;
+        b.cap = bytes;
+        return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CUC(up(c->d_libdev, ld.data(), ld.size() * sizeof(LibDev)));
+    CUC(up(c->d_rg_info, rgi.data(), rgi.size() * 4));
+    CUC(up(c->d_blibs, c->libs.data(), c->libs.size() * sizeof(bdk_lib)));
+    CUC(up(c->d_rg_lib, c->rg_lib.data(), c->rg_lib.size() * 4));
+    CUC(up(c->d_rg_bam, c->rg_bam.data(), c->rg_bam.size() * 4));
+    // accumulator block
+    size_t nbt = (size_t)p->nbam * p->ntid;
+    c->off_first = (size_t)p->nrg * 8;
+    c->off_last = c->off_first + nbt * 8;
+    c->off_hist = c->off_last + nbt * 8;
+    c->off_err = c->off_hist + (size_t)p->nlib * BDK_NUM_FLAGS * 4;
+    c->off_err = (c->off_err + 7) & ~size_t(7);
+    c->off_cursor = c->off_err + 4;
+    c->acc_bytes = c->off_cursor + 4;
+    CUC(cudaMalloc(&c->d_acc.p, c->acc_bytes)); c->d_acc.cap = c->acc_bytes;
+    CUC(cudaMalloc(&c->d_acc_bak.p, c->acc_bytes)); c->d_acc_bak.cap = c->acc_bytes;
+    CUC(cudaMalloc(&c->d_cnt.p, CNT_N * 4)); c->d_cnt.cap = CNT_N * 4;
+    CUC(cudaMalloc(&c->d_summary.p, sizeof(bdk_summary_t))); c->d_summary.cap = sizeof(bdk_summary_t);
+    CUC(cudaMalloc(&c->d_density.p, (size_t)std::max(1, c->nkey) * 4)); c->d_density.cap = (size_t)std::max(1, c->nkey) * 4;
+    CUC(cudaMalloc(&c->d_scan_sums.p, SS_GRID * 4)); c->d_scan_sums.cap = SS_GRID * 4;
+    CUC(cudaMalloc(&c->d_sort_hist.p, 256 * SS_GRID * 4)); c->d_sort_hist.cap = 256 * SS_GRID * 4;
+    CUC(cudaFuncSetAttribute(k1_classify_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    CUC(cudaFuncSetAttribute(k1_classify_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    int rc = reset_job(c);
+    if (rc) { g_create_error = c->err; bdk_destroy(c); return rc; }
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = c;
+    return 0;
+}
+
+int bdk_set_stream(bdk_ctx* c, void* s) {
+    if (!c) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int bdk_reset(bdk_ctx* c) {
+    if (!c) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    return reset_job(c);
+}
+
+int bdk_push_device(bdk_ctx* c, const bdk_soa* cols, uint64_t n) {
+    if (!c || !cols) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    const void* ptrs[10] = {cols->pos, cols->mpos, cols->tid, cols->mtid, cols->isize, cols->flag, cols->mapq, cols->rgid, cols->qlen, cols->qid};
+    for (int i = 0; i < 10; ++i) {
+        if (!ptrs[i] && n) return fail(c, BDK_ERR_ARG, "null column %d", i);
+        if ((uintptr_t)ptrs[i] & 15) return fail(c, BDK_ERR_ARG, "device column %d is not 16-byte aligned", i);
+    }
+    return push_common(c, n, [&]() -> int {
+        tstart(c, T_K1);
+        int rc = launch_k1(c, *cols, n, (uint32_t)c->n_records, c->n_units, c->n_tiles);
+        tstop(c, T_K1);
+        return rc;
+    });
+}
+
+int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
+    if (!c || !h) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    const void* src[10] = {h->pos, h->mpos, h->tid, h->mtid, h->isize, h->flag, h->mapq, h->rgid, h->qlen, h->qid};
+    static const size_t width[10] = {4, 4, 4, 4, 4, 2, 1, 2, 4, 8};
+    for (int i = 0; i < 10; ++i) if (!src[i] && n) return fail(c, BDK_ERR_ARG, "null column %d", i);
+    const uint64_t CH = (uint64_t)K1_TILE * 2048;   // 8 Mi records per chunk (multiple of the tile size)
+    const uint64_t chunk_cap = std::min<uint64_t>(CH, div_up<uint64_t>(std::max<uint64_t>(n, 1), K1_TILE) * K1_TILE);
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 10; ++k) ENS(c->d_chunk[b][k], chunk_cap * width[k]);
+    return push_common(c, n, [&]() -> int {
+        // double-buffered: the copy stream fills chunk i+1 while K1 runs on chunk i
+        CU(cudaEventRecord(c->ev_done[0], c->stream));
+        CU(cudaEventRecord(c->ev_done[1], c->stream));
+        tstart(c, T_H2D);   // spans copies + kernels of this push on the compute stream
+        uint64_t off = 0; int i = 0;
+        uint64_t unit_base = c->n_units, tile_base = c->n_tiles;
+        while (off < n) {
+            const uint64_t m = std::min<uint64_t>(CH, n - off);
+            const int b = i & 1;
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+            for (int k = 0; k < 10; ++k)
+                CU(cudaMemcpyAsync(c->d_chunk[b][k].p, (const char*)src[k] + off * width[k], m * width[k], cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+            bdk_soa d;
+            d.pos = c->d_chunk[b][0].as<int32_t>(); d.mpos = c->d_chunk[b][1].as<int32_t>(); d.tid = c->d_chunk[b][2].as<int32_t>();
+            d.mtid = c->d_chunk[b][3].as<int32_t>(); d.isize = c->d_chunk[b][4].as<int32_t>(); d.flag = c->d_chunk[b][5].as<uint16_t>();
+            d.mapq = c->d_chunk[b][6].as<uint8_t>(); d.rgid = c->d_chunk[b][7].as<uint16_t>(); d.qlen = c->d_chunk[b][8].as<int32_t>();
+            d.qid = c->d_chunk[b][9].as<uint64_t>();
+            int rc = launch_k1(c, d, m, (uint32_t)(c->n_records + off), unit_base, tile_base);
+            if (rc) return rc;
+            CU(cudaEventRecord(c->ev_done[b], c->stream));
+            const uint64_t tiles = div_up<uint64_t>(m, K1_TILE);
+            unit_base += tiles * K1_WARPS; tile_base += tiles;
+            off += m; ++i;
+        }
+        tstop(c, T_H2D);
+        return 0;
+    });
+}
+
+static int run_finalize(bdk_ctx* c) {
+    if (c->summary_ready) return 0;
+    CU(cudaMemsetAsync(c->d_cnt.p, 0, CNT_N * 4, c->stream));
+    CU(cudaMemcpyAsync(c->d_cnt.as<uint32_t>() + CNT_A, &c->A, 4, cudaMemcpyHostToDevice, c->stream));
+    char* acc = (char*)c->d_acc.p;
+    FinalizeIn in{c->P.nlib, c->P.nbam, c->P.nrg, c->P.ntid, c->P.cn_lib, c->P.initial_window, c->d_blibs.as<bdk_lib>(),
+                  c->d_rg_lib.as<int32_t>(), c->d_rg_bam.as<int32_t>(), (unsigned long long*)acc,
+                  (uint32_t*)(acc + c->off_hist), (unsigned long long*)(acc + c->off_first), (unsigned long long*)(acc + c->off_last)};
+    tstart(c, T_FINALIZE);
+    finalize_kernel<<<1, 256, 0, c->stream>>>(in, c->n_records, c->d_cnt.as<uint32_t>(), c->d_summary.as<bdk_summary_t>(), c->d_density.as<float>());
+    tstop(c, T_FINALIZE);
+    CU(cudaGetLastError());
+    c->summary_ready = true;
+    return 0;
+}
+
+int bdk_summary(bdk_ctx* c, bdk_summary_t* out) {
+    if (!c || !out) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    int rc = run_finalize(c);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&c->h_summary, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    tcollect(c);
+    *out = c->h_summary;
+    return 0;
+}
+
+int bdk_finish(bdk_ctx* c, bdk_result* out) {
+    if (!c || !out) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    out->nkey = c->nkey;
+    const uint32_t A = c->A;
+    const int nkey = c->nkey, nlib = c->P.nlib;
+    cudaStream_t st = c->stream;
+    uint32_t* d_cnt = c->d_cnt.as<uint32_t>();
+    int rc = run_finalize(c);
+    if (rc) return rc;
+    c->h_sv.clear(); c->h_lib_count.clear(); c->h_cn_count.clear(); c->h_copy_number.clear();
+    c->h_regions.clear(); c->h_areads.clear(); c->h_read_region.clear(); c->h_sv_of_read.clear();
+    memset(c->h_cnt, 0, sizeof(c->h_cnt));
+    if (A == 0) {
+        CU(cudaMemcpyAsync(&c->h_summary, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        tcollect(c);
+        c->finished = true;
+        out->sv = c->h_sv.data(); out->lib_count = c->h_lib_count.data(); out->cn_count = c->h_cn_count.data(); out->copy_number = c->h_copy_number.data();
+        return 0;
+    }
+    const size_t A1 = (size_t)A + 2;
+    ENS(c->d_cnt_off, c->n_units * 4 + 4); ENS(c->d_p_off, c->n_units * 4 * nkey + 4);
+    ENS(c->d_ar, A1 * sizeof(bdk_aread)); ENS(c->d_P, A1 * 4 * nkey);
+    ENS(c->d_read_cand, A1 * 4); ENS(c->d_read_region, A1 * 4); ENS(c->d_alive, A1); ENS(c->d_freed, A1);
+    ENS(c->d_mate, A1 * 4); ENS(c->d_sv_of_read, A1 * 4); ENS(c->d_cand_first, A1 * 4); ENS(c->d_cand_maxlen, A1 * 4);
+    ENS(c->d_cand_info, A1 * sizeof(CandInfo)); ENS(c->d_reg, A1 * sizeof(RegionRec));
+    uint32_t tsize = 1024; while (tsize < 2 * (uint64_t)A) tsize <<= 1;
+    ENS(c->d_table, (size_t)tsize * 4);
+    const size_t L1 = (size_t)A / 2 + 2;
+    ENS(c->d_links, L1 * 8); ENS(c->d_links_tmp, L1 * 8); ENS(c->d_edge_key, L1 * 8); ENS(c->d_edge_start, L1 * 4);
+    ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
+    ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
+    ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
+
+    // ---- K1 tail: unit offsets, stream order ---------------------------------------------------
+    tstart(c, T_SCAN_REORDER);
+    k1_scan_units_kernel<<<1, SCAN_THREADS, 0, st>>>(c->d_unit_cnt.as<uint32_t>(), c->d_unit_p.as<uint32_t>(), c->n_units, nkey,
+                                                     c->d_cnt_off.as<uint32_t>(), c->d_p_off.as<uint32_t>(), d_cnt + CNT_A);
+    k1_reorder_kernel<<<GS_GRID, 256, 0, st>>>(c->d_stage.as<bdk_aread>(), c->d_stage_p.as<uint32_t>(), c->d_cnt_off.as<uint32_t>(),
+                                               c->d_p_off.as<uint32_t>(), c->d_tile_seg.as<uint32_t>(), c->n_units, d_cnt + CNT_A, nkey,
+                                               c->d_ar.as<bdk_aread>(), c->d_P.as<uint32_t>());
+    tstop(c, T_SCAN_REORDER);
+    CU(cudaGetLastError());
+
+    // ---- K2 ----------------------------------------------------------------------------------
+    const int dummy = dummy_region_of(c->P);
+    ScanScratch ssc{c->d_scan_sums.as<uint32_t>()};
+    tstart(c, T_K2);
+    device_scan(st, BreakFlag{c->d_ar.as<bdk_aread>(), c->d_summary.as<bdk_summary_t>()},
+                BreakOut{c->d_read_cand.as<int32_t>(), c->d_cand_first.as<uint32_t>()}, d_cnt + CNT_A, d_cnt + CNT_NCAND, 0, ssc);
+    k2_candidates_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), c->d_cand_first.as<uint32_t>(), d_cnt, c->P.min_len,
+                                                         c->P.seq_coverage_lim, c->d_cand_maxlen.as<int32_t>(), c->d_cand_info.as<CandInfo>());
+    device_scan(st, AcceptFlag{c->d_cand_info.as<CandInfo>()},
+                RegionOut{c->d_ar.as<bdk_aread>(), c->d_cand_first.as<uint32_t>(), c->d_cand_info.as<CandInfo>(), d_cnt, c->d_reg.as<RegionRec>(),
+                          c->d_read_region.as<int32_t>(), c->d_alive.as<uint8_t>(), dummy, c->P.chr_restricted, c->P.min_read_pair},
+                d_cnt + CNT_NCAND, d_cnt + CNT_NREG, (uint32_t)dummy, ssc);
+    tstop(c, T_K2);
+    CU(cudaGetLastError());
+
+    // ---- K3 ----------------------------------------------------------------------------------
+    tstart(c, T_K3);
+    CU(cudaMemsetAsync(c->d_table.p, 0xff, (size_t)tsize * 4, st));
+    CU(cudaMemsetAsync(c->d_mate.p, 0xff, (size_t)A * 4, st));
+    CU(cudaMemsetAsync(c->d_sv_of_read.p, 0xff, (size_t)A * 4, st));
+    CU(cudaMemsetAsync(c->d_freed.p, 0, A, st));
+    k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
+    k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, c->d_links.as<unsigned long long>(), d_cnt);
+    int rbits = 1; while ((1ull << rbits) < (uint64_t)A + 2) ++rbits;      // region indices < A + 1
+    unsigned long long* keys = c->d_links.as<unsigned long long>();
+    SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_links_tmp.as<unsigned long long>(), nullptr};
+    device_radix_sort(st, &keys, nullptr, d_cnt + CNT_NLINK, 0, rbits, sosc);
+    device_radix_sort(st, &keys, nullptr, d_cnt + CNT_NLINK, 32, 32 + rbits, sosc);
+    device_scan(st, HeadFlag{keys}, HeadOut{keys, c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>()},
+                d_cnt + CNT_NLINK, d_cnt + CNT_NEDGE, 0, ssc);
+    k3_init_regions_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(), c->d_comp_strong.as<uint32_t>(),
+                                                           c->d_comp_fill.as<uint32_t>(), c->d_deleted.as<uint8_t>(), d_cnt);
+    k3_union_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_parent.as<int32_t>(), d_cnt);
+    k3_comp_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>(), c->d_parent.as<int32_t>(),
+                                                         c->d_comp_ne.as<uint32_t>(), c->d_comp_strong.as<uint32_t>(), c->P.min_read_pair, d_cnt);
+    device_scan(st, LoadU32{c->d_comp_ne.as<uint32_t>()}, ExclOut{c->d_de_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NDE, 0, ssc);
+    device_scan(st, LoadU32{c->d_comp_strong.as<uint32_t>()}, ExclOut{c->d_row_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NROW, 0, ssc);
+    k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>(), c->d_parent.as<int32_t>(),
+                                                            c->d_de_off.as<uint32_t>(), c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->period, d_cnt);
+    tstop(c, T_K3);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_cnt, d_cnt, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (c->h_cnt[CNT_ERR] & K3_ERR_DUPNAME)
+        return fail(c, BDK_ERR_DATA, "a read-name key occurs more than twice among the anomalous reads");
+    const uint32_t nrow = c->h_cnt[CNT_NROW], nreg = c->h_cnt[CNT_NREG];
+
+    // ---- K4 ----------------------------------------------------------------------------------
+    const size_t R1 = (size_t)nrow + 1;
+    ENS(c->d_rows, R1 * sizeof(bdk_sv)); ENS(c->d_row_lib_count, R1 * 4 * nlib); ENS(c->d_row_lib_span, R1 * 4 * nlib);
+    ENS(c->d_row_cn_count, R1 * 4 * nkey); ENS(c->d_row_cn, R1 * 4 * nkey); ENS(c->d_row_emit, R1); ENS(c->d_row_key, R1 * 8);
+    CU(cudaMemsetAsync(c->d_row_emit.p, 0, R1, st));
+    K4Static S;
+    S.ar = c->d_ar.as<bdk_aread>(); S.read_region = c->d_read_region.as<int32_t>(); S.read_cand = c->d_read_cand.as<int32_t>();
+    S.mate = c->d_mate.as<int32_t>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
+    S.cand_maxlen = c->d_cand_maxlen.as<int32_t>(); S.libs = c->d_libdev.as<LibDev>();
+    S.hist = (uint32_t*)((char*)c->d_acc.p + c->off_hist); S.density = c->d_density.as<float>();
+    S.A = A; S.nreg = 0; S.ncand = 0; S.period = c->period; S.nkey = nkey; S.nlib = nlib;
+    S.chr_restricted = c->P.chr_restricted; S.min_read_pair = c->P.min_read_pair; S.score_threshold = c->P.score_threshold;
+    S.fisher = c->P.fisher; S.covered_ref_len = 0;
+    K4Mut M;
+    M.alive = c->d_alive.as<uint8_t>(); M.freed = c->d_freed.as<uint8_t>(); M.deleted = c->d_deleted.as<uint8_t>();
+    M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = c->d_rows.as<bdk_sv>();
+    M.row_lib_count = c->d_row_lib_count.as<int32_t>(); M.row_lib_span = c->d_row_lib_span.as<int32_t>();
+    M.row_cn_count = c->d_row_cn_count.as<uint32_t>(); M.row_cn = c->d_row_cn.as<float>();
+    M.row_emit = c->d_row_emit.as<uint8_t>(); M.row_key = c->d_row_key.as<uint64_t>();
+    tstart(c, T_K4);
+    if (nrow || c->h_cnt[CNT_NDE]) {
+        const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(nreg, 128), (uint64_t)kNumSMs * 8);
+        k4_components_kernel<<<std::max(1u, grid), 128, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
+                                                                  c->d_de.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt);
+    }
+    tstop(c, T_K4);
+    CU(cudaGetLastError());
+
+    // ---- results to the host, final order ---------------------------------------------------------
+    tstart(c, T_D2H);
+    std::vector<bdk_sv> rows(nrow);
+    std::vector<int32_t> rlc((size_t)nrow * nlib);
+    std::vector<uint32_t> rcc((size_t)nrow * nkey);
+    std::vector<float> rcn((size_t)nrow * nkey);
+    std::vector<uint8_t> remit(nrow);
+    std::vector<uint64_t> rkey(nrow);
+    CU(cudaMemcpyAsync(&c->h_summary, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, st));
+    if (nrow) {
+        CU(cudaMemcpyAsync(rows.data(), c->d_rows.p, (size_t)nrow * sizeof(bdk_sv), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(rlc.data(), c->d_row_lib_count.p, rlc.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(rcc.data(), c->d_row_cn_count.p, rcc.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(rcn.data(), c->d_row_cn.p, rcn.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(remit.data(), c->d_row_emit.p, nrow, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(rkey.data(), c->d_row_key.p, (size_t)nrow * 8, cudaMemcpyDeviceToHost, st));
+    }
+    tstop(c, T_D2H);
+    CU(cudaStreamSynchronize(st));
+    tcollect(c);
+    // the reference prints window by window, BFS by BFS (key), calls of one BFS in slot order
+    std::vector<uint32_t> order;
+    for (uint32_t r = 0; r < nrow; ++r) if (remit[r]) order.push_back(r);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return rkey[x] < rkey[y]; });
+    const size_t ns = order.size();
+    c->h_sv.resize(ns); c->h_lib_count.resize(ns * nlib); c->h_cn_count.resize(ns * nkey); c->h_copy_number.resize(ns * nkey);
+    for (size_t i = 0; i < ns; ++i) {
+        const uint32_t r = order[i];
+        c->h_sv[i] = rows[r]; c->h_sv[i].order = (int32_t)i;
+        std::copy(rlc.begin() + (size_t)r * nlib, rlc.begin() + (size_t)(r + 1) * nlib, c->h_lib_count.begin() + i * nlib);
+        std::copy(rcc.begin() + (size_t)r * nkey, rcc.begin() + (size_t)(r + 1) * nkey, c->h_cn_count.begin() + i * nkey);
+        std::copy(rcn.begin() + (size_t)r * nkey, rcn.begin() + (size_t)(r + 1) * nkey, c->h_copy_number.begin() + i * nkey);
+    }
+    // slot -> output order, for bdk_get_support
+    c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet
+    c->h_slot_order.assign(nrow, -1);
+    for (size_t i = 0; i < ns; ++i) c->h_slot_order[order[i]] = (int32_t)i;
+    c->finished = true;
+    out->n_sv = ns;
+    out->sv = c->h_sv.data(); out->lib_count = c->h_lib_count.data(); out->cn_count = c->h_cn_count.data();
+    out->copy_number = c->h_copy_number.data(); out->nkey = nkey;
+    return 0;
+}
+
+int bdk_get_regions(bdk_ctx* c, const bdk_region** regions, uint64_t* n) {
+    if (!c || !regions || !n) return BDK_ERR_ARG;
+    if (!c->finished) return fail(c, BDK_ERR_STATE, "bdk_get_regions before bdk_finish");
+    CU(cudaSetDevice(c->device));
+    const uint32_t nreg = c->A ? c->h_cnt[CNT_NREG] : 0;
+    std::vector<RegionRec> reg(nreg);
+    if (nreg) CU(cudaMemcpy(reg.data(), c->d_reg.p, (size_t)nreg * sizeof(RegionRec), cudaMemcpyDeviceToHost));
+    c->h_regions.resize(nreg);
+    for (uint32_t r = 0; r < nreg; ++r) {
+        bdk_region& o = c->h_regions[r];
+        o.tid = reg[r].tid; o.start = reg[r].start; o.end = reg[r].end; o.fwd = reg[r].fwd; o.rev = reg[r].rev;
+        o.first_read = reg[r].first_read; o.n_reads = reg[r].n_reads; o.stored = reg[r].stored; o.window = (int32_t)(r / c->period);
+    }
+    *regions = c->h_regions.data(); *n = nreg;
+    return 0;
+}
+
+int bdk_get_areads(bdk_ctx* c, const bdk_aread** reads, const int32_t** region_of_read, uint64_t* n) {
+    if (!c || !reads || !region_of_read || !n) return BDK_ERR_ARG;
+    if (!c->finished) return fail(c, BDK_ERR_STATE, "bdk_get_areads before bdk_finish");
+    CU(cudaSetDevice(c->device));
+    c->h_areads.resize(c->A); c->h_read_region.resize(c->A);
+    if (c->A) {
+        CU(cudaMemcpy(c->h_areads.data(), c->d_ar.p, (size_t)c->A * sizeof(bdk_aread), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(c->h_read_region.data(), c->d_read_region.p, (size_t)c->A * 4, cudaMemcpyDeviceToHost));
+    }
+    *reads = c->h_areads.data(); *region_of_read = c->h_read_region.data(); *n = c->A;
+    return 0;
+}
+
+int bdk_get_support(bdk_ctx* c, const int32_t** sv_of_read, uint64_t* n) {
+    if (!c || !sv_of_read || !n) return BDK_ERR_ARG;
+    if (!c->finished) return fail(c, BDK_ERR_STATE, "bdk_get_support before bdk_finish");
+    CU(cudaSetDevice(c->device));
+    if (c->h_sv_of_read.size() == 1 && c->h_sv_of_read[0] == -2) {
+        std::vector<int32_t> slots(c->A);
+        if (c->A) CU(cudaMemcpy(slots.data(), c->d_sv_of_read.p, (size_t)c->A * 4, cudaMemcpyDeviceToHost));
+        const std::vector<int32_t>& slot_order = c->h_slot_order;
+        for (auto& s : slots) s = (s >= 0 && (size_t)s < slot_order.size()) ? slot_order[s] : -1;
+        c->h_sv_of_read.swap(slots);
+    }
+    *sv_of_read = c->h_sv_of_read.data(); *n = c->A;
+    return 0;
+}
+
+int bdk_kernel_times(bdk_ctx* c, const char** names, float* ms, int* launches, int cap) {
+    if (!c) return 0;
+    int k = 0;
+    for (int t = 0; t < T_N && k < cap; ++t, ++k) { names[k] = c->timers[t].name; ms[k] = c->timers[t].ms; launches[k] = c->timers[t].launches; }
+    return k;
+}
+
+int bdk_set_comm(bdk_ctx* c, void*, int, int) {
+    if (!c) return BDK_ERR_ARG;
+    return fail(c, BDK_ERR_ARG, "inter-chromosomal mate-link exchange across GPUs is not implemented yet; shard by chromosome (one context per chromosome set)");
+}
+
+int bdk_poisson_logsf(bdk_ctx* c, const double* lambda, const int32_t* k, double* out, uint64_t n) {
+    if (!c || !lambda || !k || !out) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (!n) return 0;
+    ENS(c->d_pois_l, n * 8); ENS(c->d_pois_k, n * 4); ENS(c->d_pois_o, n * 8);
+    CU(cudaMemcpyAsync(c->d_pois_l.p, lambda, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pois_k.p, k, n * 4, cudaMemcpyHostToDevice, c->stream));
+    poisson_logsf_kernel<<<(unsigned)std::min<uint64_t>(div_up<uint64_t>(n, 128), 1184), 128, 0, c->stream>>>(c->d_pois_l.as<double>(), c->d_pois_k.as<int32_t>(), c->d_pois_o.as<double>(), n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_pois_o.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -41,6 +41,10 @@ void format_rows(std::ostream& out, const bdk_params& p, const bdk_result& r,
                  const std::vector<std::string>& lib_names, const std::vector<std::string>& bam_names,
                  const std::vector<std::string>& tid_names, bool print_af);
 
+void write_support_reads(bdk_ctx* ctx, const bdh_stream* stream, const bdk_params& p, const bdk_result& res,
+                         const std::vector<std::string>& lib_names, const std::vector<std::string>& tid_names,
+                         std::ostream* bed, const std::string& fastq_prefix);
+
 }  // namespace bdh
 
 struct bdh_config { bdh::Config cfg; };

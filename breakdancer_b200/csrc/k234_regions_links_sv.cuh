@@ -1,0 +1,252 @@
+// k234_regions_links_sv.cuh -- the stages that run on the compacted anomalous-read stream
+// (about 1-3 % of the records):
+//   K2  break flags -> candidate regions (segmented reductions) -> accepted regions
+//       (BreakDancer::push_read:209-241, process_breakpoint:244-264, ReadRegionData::add_region)
+//   K3  mate join by read-name key (hash table), region-region mate links, radix sort +
+//       run-length -> weighted edges (ReadRegionData.cpp:109-113, Graph.hpp:41-46)
+//   K4  connected components (lock-free union-find), per-component connection walk, SV
+//       evaluation and Poisson score (build_connection, process_sv, SvBuilder, ComputeProbScore)
+// All element counts stay on the device (d_cnt[]); kernels are grid-stride over fixed grids.
+#pragma once
+#include "common.cuh"
+#include "scan_sort.cuh"
+#include "bdk_finalize.h"
+
+namespace bdk {
+
+enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NLINK, CNT_NEDGE, CNT_NDE, CNT_NROW, CNT_ERR, CNT_NREG_REAL, CNT_N };
+constexpr uint32_t K3_ERR_DUPNAME = 1u;
+constexpr int GS_THREADS = 256;
+constexpr int GS_GRID = kNumSMs * 4;
+
+// ---- pass-1 statistics -> BamSummary numbers, densities, window (one CTA) ---------------------
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeIn in, uint64_t n_records, const uint32_t* __restrict__ d_cnt,
+                                                       bdk_summary_t* __restrict__ S, float* __restrict__ density) {
+    __shared__ unsigned long long s_ref[BDK_MAX_BAMS];
+    for (int b = threadIdx.x; b < BDK_MAX_BAMS; b += blockDim.x) s_ref[b] = 0;
+    __syncthreads();
+    const int total = in.nbam * in.ntid;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        long long t = ref_len_term(in.first[i], in.last[i]);
+        if (t) atomicAdd(&s_ref[i / in.ntid], (unsigned long long)t);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) finalize_rest(in, s_ref, n_records, d_cnt[CNT_A], S, density);
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------
+struct BreakFlag {   // scan input: 1 where a read starts a new candidate region
+    const bdk_aread* ar; const bdk_summary_t* S;
+    __device__ uint32_t operator()(uint32_t j, uint32_t) const {
+        if (j == 0) return 1u;
+        const bdk_aread a = ar[j - 1], b = ar[j];
+        return k2_is_break(a.tid, a.pos, b.tid, b.pos, S->window) ? 1u : 0u;
+    }
+};
+struct BreakOut {
+    int32_t* read_cand; uint32_t* cand_first;
+    __device__ void operator()(uint32_t j, uint32_t inc, uint32_t v, uint32_t) const {
+        read_cand[j] = (int32_t)inc - 1;
+        if (v) cand_first[inc - 1] = j;
+    }
+};
+
+struct CandInfo { int32_t fwd, rev, nonctx, accept; };
+
+__global__ void __launch_bounds__(GS_THREADS) k2_candidates_kernel(const bdk_aread* __restrict__ ar, const uint32_t* __restrict__ cand_first,
+        const uint32_t* __restrict__ d_cnt, int32_t min_len, int32_t cov_lim, int32_t* __restrict__ cand_maxlen, CandInfo* __restrict__ cand_info) {
+    const uint32_t A = d_cnt[CNT_A], ncand = d_cnt[CNT_NCAND];
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += gridDim.x * blockDim.x) {
+        const int64_t s = cand_first[c], e = (int64_t)(c + 1 < ncand ? cand_first[c + 1] : A) - 1;
+        const CandAgg g = k2_cand_aggregate(ar, s, e, (int64_t)A);
+        cand_maxlen[c] = g.maxlen;
+        CandInfo ci; ci.fwd = g.fwd; ci.rev = g.rev; ci.nonctx = g.nonctx;
+        ci.accept = k2_accept(ar[s].pos, ar[e].pos, g, min_len, cov_lim) ? 1 : 0;
+        cand_info[c] = ci;
+    }
+}
+
+struct AcceptFlag {
+    const CandInfo* ci;
+    __device__ uint32_t operator()(uint32_t c, uint32_t) const { return (uint32_t)ci[c].accept; }
+};
+struct RegionOut {   // writes the region table and the read -> region map
+    const bdk_aread* ar; const uint32_t* cand_first; const CandInfo* ci; const uint32_t* d_cnt;
+    RegionRec* reg; int32_t* read_region; uint8_t* alive; int32_t dummy, chr_restricted, min_read_pair;
+    __device__ void operator()(uint32_t c, uint32_t inc, uint32_t v, uint32_t ncand) const {
+        const uint32_t A = d_cnt[CNT_A];
+        const uint32_t s = cand_first[c], e = (c + 1 < ncand ? cand_first[c + 1] : A) - 1;
+        int32_t r = -1; uint8_t st = 0;
+        if (v) {
+            r = (int32_t)(inc - 1) + dummy;
+            const CandInfo k = ci[c];
+            RegionRec R;
+            R.tid = ar[s].tid; R.start = ar[s].pos; R.end = ar[e].pos; R.fwd = k.fwd; R.rev = k.rev;
+            R.first_read = (int32_t)s; R.n_reads = (int32_t)(e - s + 1);
+            const int valid = chr_restricted ? k.nonctx : R.n_reads;
+            R.stored = valid >= min_read_pair ? 1 : 0; R.cand = (int32_t)c;
+            reg[r] = R;
+            st = (uint8_t)R.stored;
+        }
+        for (uint32_t j = s; j <= e; ++j) { read_region[j] = r; alive[j] = st; }
+        if (c == 0 && dummy) {   // region 0 of a run with -s < 0: registered from empty state
+            RegionRec D; D.tid = -1; D.start = -1; D.end = -1; D.fwd = 0; D.rev = 0; D.first_read = 0; D.n_reads = 0; D.stored = 0; D.cand = -1;
+            reg[0] = D;
+        }
+    }
+};
+
+// ---- K3 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
+
+// Open-addressing table of read indices keyed by the read-name key; the second read of a name
+// finds the first one and both learn their mate.
+__global__ void __launch_bounds__(GS_THREADS) k3_mate_join_kernel(const bdk_aread* __restrict__ ar, uint32_t A, uint32_t* __restrict__ table,
+        uint32_t mask, int32_t* __restrict__ mate, uint32_t* __restrict__ d_cnt) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A; j += gridDim.x * blockDim.x) {
+        const unsigned long long q = ar[j].qid;
+        uint32_t h = hash64(q) & mask;
+        for (;;) {
+            const uint32_t prev = atomicCAS(table + h, 0xffffffffu, j);
+            if (prev == 0xffffffffu) break;
+            if (ar[prev].qid == q) {
+                const int32_t old = atomicExch(mate + prev, (int32_t)j);
+                if (old != -1) atomicOr(d_cnt + CNT_ERR, K3_ERR_DUPNAME);
+                mate[j] = (int32_t)prev;
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+// one link per pair whose two reads were both registered: key = (earlier region << 32 | later region)
+__global__ void __launch_bounds__(GS_THREADS) k3_links_kernel(const int32_t* __restrict__ mate, const int32_t* __restrict__ read_region, uint32_t A,
+        unsigned long long* __restrict__ links, uint32_t* __restrict__ d_cnt) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t y0 = blockIdx.x * blockDim.x; y0 < A; y0 += stride) {   // warp-uniform trip count
+        const uint32_t y = y0 + threadIdx.x;
+        bool has = false; unsigned long long key = 0;
+        if (y < A) {
+            const int32_t x = mate[y];
+            if (x >= 0 && (uint32_t)x < y) {
+                const int32_t rx = read_region[x], ry = read_region[y];
+                if (rx >= 0 && ry >= 0) { has = true; key = ((unsigned long long)(uint32_t)rx << 32) | (uint32_t)ry; }
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, has);
+        if (m) {
+            uint32_t base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)lane_id() == leader) base = atomicAdd(d_cnt + CNT_NLINK, (uint32_t)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (has) links[base + __popc(m & lanemask_lt())] = key;
+        }
+    }
+}
+
+struct HeadFlag {   // run heads of the sorted link keys
+    const unsigned long long* keys;
+    __device__ uint32_t operator()(uint32_t i, uint32_t) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+};
+struct HeadOut {
+    const unsigned long long* keys; unsigned long long* edge_key; uint32_t* edge_start;
+    __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const {
+        if (v) { edge_key[inc - 1] = keys[i]; edge_start[inc - 1] = i; }
+    }
+};
+
+__device__ __forceinline__ int uf_find(int32_t* parent, int x) {
+    for (;;) {
+        int p = parent[x];
+        if (p == x) return x;
+        int gp = parent[p];
+        if (gp != p) parent[x] = gp;   // path halving (benign race: only ever points further up)
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }          // hook the larger root under the smaller
+        if (atomicCAS(parent + a, a, b) == a) return;
+    }
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k3_init_regions_kernel(int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne,
+        uint32_t* __restrict__ comp_strong, uint32_t* __restrict__ comp_fill, uint8_t* __restrict__ deleted, const uint32_t* __restrict__ d_cnt) {
+    const uint32_t nreg = d_cnt[CNT_NREG];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nreg; r += gridDim.x * blockDim.x) {
+        parent[r] = (int32_t)r; comp_ne[r] = 0; comp_strong[r] = 0; comp_fill[r] = 0; deleted[r] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k3_union_kernel(const unsigned long long* __restrict__ edge_key, int32_t* __restrict__ parent,
+        const uint32_t* __restrict__ d_cnt) {
+    const uint32_t ne = d_cnt[CNT_NEDGE];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = edge_key[e];
+        const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
+        if (r0 != r1) uf_union(parent, r0, r1);
+    }
+}
+
+__global__ void __launch_bounds__(GS_THREADS) k3_comp_count_kernel(const unsigned long long* __restrict__ edge_key, const uint32_t* __restrict__ edge_start,
+        int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ comp_strong, int32_t min_read_pair,
+        const uint32_t* __restrict__ d_cnt) {
+    const uint32_t ne = d_cnt[CNT_NEDGE], nl = d_cnt[CNT_NLINK];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = edge_key[e];
+        const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
+        const int root = uf_find(parent, r0);
+        const uint32_t w = (e + 1 < ne ? edge_start[e + 1] : nl) - edge_start[e];
+        atomicAdd(comp_ne + root, r0 == r1 ? 1u : 2u);
+        if ((int32_t)w >= min_read_pair) atomicAdd(comp_strong + root, 1u);
+    }
+}
+
+struct LoadU32 { const uint32_t* p; __device__ uint32_t operator()(uint32_t i, uint32_t) const { return p[i]; } };
+struct ExclOut { uint32_t* o; __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const { o[i] = inc - v; } };
+
+__global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsigned long long* __restrict__ edge_key, const uint32_t* __restrict__ edge_start,
+        int32_t* __restrict__ parent, const uint32_t* __restrict__ de_off, uint32_t* __restrict__ comp_fill, DEdge* __restrict__ de, int32_t period,
+        const uint32_t* __restrict__ d_cnt) {
+    const uint32_t ne = d_cnt[CNT_NEDGE], nl = d_cnt[CNT_NLINK];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = edge_key[e];
+        const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
+        const int root = uf_find(parent, r0);
+        const int w = (int)((e + 1 < ne ? edge_start[e + 1] : nl) - edge_start[e]);
+        const int win = r1 / period;          // r0 <= r1: the pair is counted when r1 is registered
+        const uint32_t slot = de_off[root] + atomicAdd(comp_fill + root, r0 == r1 ? 1u : 2u);
+        DEdge d; d.win = win; d.src = r0; d.dst = r1; d.w = w; d.flags = 0;
+        de[slot] = d;
+        if (r0 != r1) { d.src = r1; d.dst = r0; de[slot + 1] = d; }
+    }
+}
+
+// ---- K4: one thread walks one connected component ------------------------------------------------
+__global__ void __launch_bounds__(128) k4_components_kernel(K4Static S, K4Mut M, const uint32_t* __restrict__ comp_ne, const uint32_t* __restrict__ de_off,
+        const uint32_t* __restrict__ row_off, DEdge* __restrict__ de, int32_t* __restrict__ queue, const bdk_summary_t* __restrict__ summary,
+        const uint32_t* __restrict__ d_cnt) {
+    S.nreg = (int32_t)d_cnt[CNT_NREG]; S.ncand = (int32_t)d_cnt[CNT_NCAND];
+    S.covered_ref_len = summary->covered_ref_len;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < (uint32_t)S.nreg; r += gridDim.x * blockDim.x) {
+        const uint32_t ne = comp_ne[r];
+        if (!ne) continue;
+        k4_component(S, M, de + de_off[r], (int)ne, queue + de_off[r] + 2 * (size_t)r, (int)row_off[r]);
+    }
+}
+
+// Poisson tail known-answer entry point
+__global__ void poisson_logsf_kernel(const double* __restrict__ lambda, const int32_t* __restrict__ k, double* __restrict__ out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = poisson_log_sf(lambda[i], k[i]);
+}
+
+}  // namespace bdk

@@ -1,0 +1,191 @@
+// scan_sort.cuh -- device-wide prefix scan and stable LSD radix sort with DEVICE-SIDE element
+// counts, so the region/link/graph stages can be chained on one stream without host round trips.
+// Grids are fixed (multiples of the 148 SMs); each block owns a contiguous chunk of the input.
+#pragma once
+#include <utility>
+#include "common.cuh"
+
+namespace bdk {
+
+constexpr int SS_THREADS = 256;
+constexpr int SS_WARPS = SS_THREADS / 32;
+constexpr int SS_GRID = kNumSMs * 2;          // 296 blocks
+
+__device__ __forceinline__ uint32_t ss_chunk(uint32_t n) {   // per-block chunk, multiple of the tile size
+    uint32_t c = div_up<uint32_t>(n, SS_GRID);
+    return div_up<uint32_t>(c, SS_THREADS) * SS_THREADS;
+}
+
+// inclusive scan of one value per thread across the block; returns inclusive value, *total = block sum
+__device__ __forceinline__ uint32_t ss_block_scan(uint32_t v, uint32_t* s_warp /*[SS_WARPS + 1]*/, uint32_t* total) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SS_WARPS ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < SS_WARPS; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, wi, d); if (lane >= d) wi += t; }
+        if (lane < SS_WARPS) s_warp[lane] = wi - w;
+        if (lane == SS_WARPS - 1) s_warp[SS_WARPS] = wi;
+    }
+    __syncthreads();
+    inc += s_warp[warp];
+    *total = s_warp[SS_WARPS];
+    __syncthreads();
+    return inc;
+}
+
+// ---- scan: out(i, inclusive_prefix, value) for i < *n, value = f(i) ------------------------------
+template <class F>
+__global__ void __launch_bounds__(SS_THREADS) scan_reduce_kernel(F f, const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t s_warp[SS_WARPS + 1];
+    const uint32_t n = *n_ptr, chunk = ss_chunk(n);
+    const uint32_t lo = min(n, blockIdx.x * chunk), hi = min(n, lo + chunk);
+    uint32_t s = 0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += SS_THREADS) s += f(i, n);
+    uint32_t total;
+    ss_block_scan(s, s_warp, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// exclusive scan of the SS_GRID block sums in place; total -> *total_out (+ add)
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t* __restrict__ total_out, uint32_t add) {
+    __shared__ uint32_t s[1024];
+    const int t = threadIdx.x;
+    uint32_t v = t < SS_GRID ? block_sums[t] : 0;
+    s[t] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t x = t >= d ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += x;
+        __syncthreads();
+    }
+    if (t < SS_GRID) block_sums[t] = s[t] - v;
+    if (t == 1023 && total_out) *total_out = s[t] + add;
+}
+
+template <class F, class O>
+__global__ void __launch_bounds__(SS_THREADS) scan_apply_kernel(F f, O out, const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ block_offs) {
+    __shared__ uint32_t s_warp[SS_WARPS + 1];
+    const uint32_t n = *n_ptr, chunk = ss_chunk(n);
+    const uint32_t lo = min(n, blockIdx.x * chunk), hi = min(n, lo + chunk);
+    uint32_t carry = block_offs[blockIdx.x];
+    for (uint32_t base = lo; base < hi; base += SS_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < hi ? f(i, n) : 0;
+        uint32_t total;
+        const uint32_t inc = ss_block_scan(v, s_warp, &total) + carry;
+        if (i < hi) out(i, inc, v, n);
+        carry += total;
+    }
+}
+
+struct ScanScratch { uint32_t* block_sums; };   // [SS_GRID]
+
+template <class F, class O>
+inline void device_scan(cudaStream_t st, F f, O out, const uint32_t* n_ptr, uint32_t* total_out, uint32_t total_add, ScanScratch sc) {
+    scan_reduce_kernel<<<SS_GRID, SS_THREADS, 0, st>>>(f, n_ptr, sc.block_sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sc.block_sums, total_out, total_add);
+    scan_apply_kernel<<<SS_GRID, SS_THREADS, 0, st>>>(f, out, n_ptr, sc.block_sums);
+}
+
+// ---- stable LSD radix sort of (u64 key, u32 value) pairs, 8 bits per pass -----------------------
+__global__ void __launch_bounds__(SS_THREADS) sort_hist_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
+                                                               int shift, uint32_t* __restrict__ hist /*[256][SS_GRID]*/) {
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = *n_ptr, chunk = ss_chunk(n);
+    const uint32_t lo = min(n, blockIdx.x * chunk), hi = min(n, lo + chunk);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += SS_THREADS) atomicAdd(&s_h[(keys[i] >> shift) & 0xffu], 1u);
+    __syncthreads();
+    hist[threadIdx.x * SS_GRID + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// exclusive scan over the digit-major [256][SS_GRID] table, in place (one block)
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s[1024];
+    const int t = threadIdx.x;
+    constexpr int TOTAL = 256 * SS_GRID;
+    constexpr int PER = (TOTAL + 1023) / 1024;
+    const int lo = min(TOTAL, t * PER), hi = min(TOTAL, lo + PER);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += hist[i];
+    s[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t x = t >= d ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += x;
+        __syncthreads();
+    }
+    uint32_t run = s[t] - sum;
+    for (int i = lo; i < hi; ++i) { uint32_t v = hist[i]; hist[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(SS_THREADS) sort_scatter_kernel(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+        unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ n_ptr, int shift,
+        const uint32_t* __restrict__ offs /*[256][SS_GRID] exclusive*/) {
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_wcnt[SS_WARPS][256];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s_base[threadIdx.x] = offs[threadIdx.x * SS_GRID + blockIdx.x];
+    const uint32_t n = *n_ptr, chunk = ss_chunk(n);
+    const uint32_t lo = min(n, blockIdx.x * chunk), hi = min(n, lo + chunk);
+    for (uint32_t base = lo; base < hi; base += SS_THREADS) {
+        for (int w = 0; w < SS_WARPS; ++w) s_wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = base + threadIdx.x;
+        const bool v = i < hi;
+        unsigned long long k = 0; uint32_t val = 0; uint32_t d = 0;
+        if (v) { k = keys_in[i]; d = (uint32_t)(k >> shift) & 0xffu; if (vals_in) val = vals_in[i]; }
+        const unsigned vm = __ballot_sync(FULL, v);
+        uint32_t rank = 0;
+        if (v) {
+            const unsigned peers = __match_any_sync(vm, d);
+            rank = __popc(peers & lanemask_lt());
+            if (lane == __ffs(peers) - 1) s_wcnt[warp][d] = __popc(peers);
+        }
+        __syncthreads();
+        {   // per digit: exclusive prefix over the warps; threadIdx.x is the digit
+            uint32_t run = 0;
+            for (int w = 0; w < SS_WARPS; ++w) { uint32_t c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
+            __syncthreads();
+            if (v) {
+                const uint32_t p = s_base[d] + s_wcnt[warp][d] + rank;
+                keys_out[p] = k;
+                if (vals_out) vals_out[p] = val;
+            }
+            __syncthreads();
+            s_base[threadIdx.x] += run;
+        }
+        __syncthreads();
+    }
+}
+
+struct SortScratch { uint32_t* hist; unsigned long long* keys_tmp; uint32_t* vals_tmp; };  // hist [256][SS_GRID]
+
+// Sorts in place by the key bits [bit_lo, bit_hi) (other bits must be equal or irrelevant).
+// Returns through the pointers the buffers that hold the result (ping-pong).
+inline void device_radix_sort(cudaStream_t st, unsigned long long** keys, uint32_t** vals, const uint32_t* n_ptr,
+                              int bit_lo, int bit_hi, SortScratch& sc) {
+    unsigned long long* kin = *keys; unsigned long long* kout = sc.keys_tmp;
+    uint32_t* vin = vals ? *vals : nullptr; uint32_t* vout = vals ? sc.vals_tmp : nullptr;
+    for (int shift = bit_lo; shift < bit_hi; shift += 8) {
+        sort_hist_kernel<<<SS_GRID, SS_THREADS, 0, st>>>(kin, n_ptr, shift, sc.hist);
+        sort_scan_kernel<<<1, 1024, 0, st>>>(sc.hist);
+        sort_scatter_kernel<<<SS_GRID, SS_THREADS, 0, st>>>(kin, vin, kout, vout, n_ptr, shift, sc.hist);
+        std::swap(kin, kout);
+        if (vals) std::swap(vin, vout);
+    }
+    if (kin != *keys) { sc.keys_tmp = *keys; *keys = kin; }
+    if (vals && vin != *vals) { sc.vals_tmp = *vals; *vals = vin; }
+}
+
+}  // namespace bdk

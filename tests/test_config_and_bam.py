@@ -1,0 +1,103 @@
+"""Host side: bam2cfg config grammar, BAM decode / merge / write (CPU only)."""
+import os
+
+import numpy as np
+import pytest
+
+from breakdancer_b200 import api, synth
+from tests import util
+
+# reference test/lib/io/TestBamConfigEntry.cpp:36-100 (field ordinals of BamConfigEntry::Field)
+BAM_FILE, LIBRARY_NAME, READ_GROUP, MEAN, STDDEV, READ_LENGTH, UPPER, LOWER, MIN_MAP_QUAL, SAMPLE, UNKNOWN = range(11)
+ALIASES = {
+    "map": BAM_FILE, "lib": LIBRARY_NAME, "libname": LIBRARY_NAME, "library_name": LIBRARY_NAME,
+    "groUp": READ_GROUP, "ReadgroUp": READ_GROUP, "Read_groUp": READ_GROUP,
+    "mean": MEAN, "mean_insert": MEAN, "mean_insert_size": MEAN,
+    "std": STDDEV, "stddev": STDDEV, "insert_stddev": STDDEV, "insert_size_stddev": STDDEV, "stddev_insert": STDDEV,
+    "stddev_insert_size": STDDEV, "readlen": READ_LENGTH, "rEaDlEnGtH": READ_LENGTH, "average_readlen": READ_LENGTH,
+    "average_readlength": READ_LENGTH, "upp": UPPER, "upper": UPPER, "uppEr_cutOff": UPPER, "inseRt_size_uPper_cutoff": UPPER,
+    "low": LOWER, "lower": LOWER, "lower_cuToff": LOWER, "insert_size_lower_cutoff": LOWER,
+    "mapqual": MIN_MAP_QUAL, "mapPing_quAlity": MIN_MAP_QUAL, "samp": SAMPLE, "sample": SAMPLE, "samplename": SAMPLE,
+    "sample_name": SAMPLE,
+}
+
+
+def test_translate_token_alias_table():
+    L = api.load_library()
+    assert L.bdh_config_translate_token(b"ZIOJFksfjlaiaowinfd") == UNKNOWN
+    for key, field in ALIASES.items():
+        for k in (key, key.upper(), key.lower()):
+            assert L.bdh_config_translate_token(k.encode()) == field, k
+
+
+def test_chr21_config():
+    cfg = api.BamConfig(path=os.path.join(util.CHR21, "inv_del_bam_config"))
+    assert cfg.lib_names == ["H_IJ-NA19238-NA19238-extlibs", "H_IJ-NA19240-NA19240-extlibs"]   # sorted by name
+    assert cfg.bam_files == ["NA19238_chr21_del_inv.bam", "NA19240_chr21_del_inv.bam"]
+    assert cfg.window == 287
+    l0, l1 = cfg.libs
+    assert abs(l0.uppercutoff - 532.53) < 1e-3 and abs(l0.lowercutoff - 311.36) < 1e-3 and l0.bam_index == 0
+    assert abs(l1.mean_insertsize - 467.59) < 1e-3 and l1.min_mapping_quality == -1 and l1.bam_index == 1
+    assert cfg.rg_lib("2880590781-110718_I806_FCD0E3VABXX_L4_HUMxqmRADDIABPEI-142") == 0
+    assert cfg.rg_lib("no-such-read-group") == 0   # falls back to the first bam's library
+
+
+def test_config_rules():
+    text = ("map:b.bam\tlib:L2\tmean:300\tstd:10\treadlen:50\tmapqual:10\n"
+            "map:a.bam\tsample:S1\tmean:400\tstd:20\treadlen:100\tupper:500\tlower:100\n"
+            "\n"
+            "map:ignored.bam\tlib:ZZ\n")
+    cfg = api.BamConfig(text=text, cut_sd=4)
+    assert cfg.bam_files == ["a.bam", "b.bam"] and cfg.lib_names == ["L2", "S1"]   # parse stops at the empty line
+    L2, S1 = cfg.libs
+    assert L2.uppercutoff == 340.0 and L2.lowercutoff == 260.0 and L2.min_mapping_quality == 10 and L2.bam_index == 1
+    assert S1.uppercutoff == 500.0 and S1.lowercutoff == 100.0 and S1.bam_index == 0
+    assert cfg.window == 200                       # min over lines of int(mean - 2 * readlen)
+    with pytest.raises(RuntimeError, match="Required field 'map'"):
+        api.BamConfig(text="lib:x\tmean:1\n")
+
+
+def test_chr21_decode_counts_and_order(tmp_path):
+    cwd = os.getcwd()
+    os.chdir(util.CHR21)
+    try:
+        cfg = api.BamConfig(path="inv_del_bam_config")
+        one = api.BamStream(cfg, paths=["NA19238_chr21_del_inv.bam"])
+        two = api.BamStream(cfg, paths=["NA19240_chr21_del_inv.bam"])
+        assert (one.n, two.n) == (3069, 2848)       # reference test-data/TestData.hpp.in:20-23
+        both = api.BamStream(cfg, keep_records=True)
+        assert both.n == 3069 + 2848
+        c = both.cols
+        key = c["tid"].astype(np.int64) << 33 | c["pos"].astype(np.int64) << 1 | ((c["flag"] & 16) != 0)
+        assert np.all(np.diff(key) >= 0)             # merged by (tid, pos, strand)
+        assert len(both.rg_lib) == 14 and set(both.rg_lib) == {0, 1}
+        assert both.qname(0).startswith("FC")
+        region = api.BamStream(cfg, region="21")
+        assert region.n == both.n and np.array_equal(region.cols["pos"], c["pos"])
+        sub = api.BamStream(cfg, region="21:29185000-29186000")
+        assert 0 < sub.n < both.n and sub.cols["pos"].max() < 29186000
+    finally:
+        os.chdir(cwd)
+
+
+def test_bam_write_read_round_trip(tmp_path):
+    w = synth.generate(util.GENOME3, util.LIBS4, 20000, seed=3)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(bam, [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols)
+        cfg = api.BamConfig(text=w.config_text())
+        st = api.BamStream(cfg, keep_records=True)
+        assert st.n == w.n
+        for name in ("pos", "mpos", "tid", "mtid", "isize", "flag", "mapq", "qlen"):
+            a = np.sort(st.cols[name].astype(np.int64))
+            b = np.sort(w.cols[name].astype(np.int64))
+            assert np.array_equal(a, b), name
+        # names are "r<pair id>": both mates hash to the same key, different pairs to different keys
+        _, counts = np.unique(st.cols["qid"], return_counts=True)
+        assert counts.max() == 2
+        fq = st.fastq(0).split("\n")
+        assert fq[0] == "@" + st.qname(0) and len(fq[1]) == st.cols["qlen"][0] and fq[2] == "+"
+    finally:
+        os.chdir(cwd)
