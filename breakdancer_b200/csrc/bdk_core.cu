@@ -76,6 +76,7 @@ struct bdk_ctx {
         d_pois_l, d_pois_k, d_pois_o;
     bool finished = false, summary_ready = false;
     int k1_blocks_per_sm = 0;
+    uint64_t launches = 0;       // kernels launched since the last bdk_reset
     // host results
     bdk_summary_t h_summary;
     std::vector<bdk_sv> h_sv;
@@ -131,7 +132,7 @@ void tcollect(bdk_ctx* c) {
 
 int reset_job(bdk_ctx* c) {
     c->n_records = 0; c->n_units = 0; c->n_tiles = 0; c->A = 0;
-    c->finished = false; c->summary_ready = false;
+    c->finished = false; c->summary_ready = false; c->launches = 0;
     // accumulators: counts 0, first = ~0, last = 0
     CU(cudaMemsetAsync(c->d_acc.p, 0, c->acc_bytes, c->stream));
     size_t nbt = (size_t)c->P.nbam * c->P.ntid;
@@ -168,6 +169,7 @@ int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, 
     if (!grid) return 0;
     if (c->nkey == 1) k1_classify_kernel<true><<<grid, K1_THREADS, smem, c->stream>>>(a);
     else k1_classify_kernel<false><<<grid, K1_THREADS, smem, c->stream>>>(a);
+    c->launches += 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -435,6 +437,7 @@ static int run_finalize(bdk_ctx* c) {
                   (uint32_t*)(acc + c->off_hist), (unsigned long long*)(acc + c->off_first), (unsigned long long*)(acc + c->off_last)};
     tstart(c, T_FINALIZE);
     finalize_kernel<<<1, 256, 0, c->stream>>>(in, c->n_records, c->d_cnt.as<uint32_t>(), c->d_summary.as<bdk_summary_t>(), c->d_density.as<float>());
+    c->launches += 1;
     tstop(c, T_FINALIZE);
     CU(cudaGetLastError());
     c->summary_ready = true;
@@ -496,6 +499,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     k1_reorder_kernel<<<GS_GRID, 256, 0, st>>>(c->d_stage.as<bdk_aread>(), c->d_stage_p.as<uint32_t>(), c->d_cnt_off.as<uint32_t>(),
                                                c->d_p_off.as<uint32_t>(), c->d_tile_seg.as<uint32_t>(), c->n_units, d_cnt + CNT_A, nkey,
                                                c->d_ar.as<bdk_aread>(), c->d_P.as<uint32_t>());
+    c->launches += 2;
     tstop(c, T_SCAN_REORDER);
     CU(cudaGetLastError());
 
@@ -511,6 +515,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
                 RegionOut{c->d_ar.as<bdk_aread>(), c->d_cand_first.as<uint32_t>(), c->d_cand_info.as<CandInfo>(), d_cnt, c->d_reg.as<RegionRec>(),
                           c->d_read_region.as<int32_t>(), c->d_alive.as<uint8_t>(), dummy, c->P.chr_restricted, c->P.min_read_pair},
                 d_cnt + CNT_NCAND, d_cnt + CNT_NREG, (uint32_t)dummy, ssc);
+    c->launches += 3 + 1 + 3;   // two scans (3 kernels each) + the candidate kernel
     tstop(c, T_K2);
     CU(cudaGetLastError());
 
@@ -538,6 +543,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     device_scan(st, LoadU32{c->d_comp_strong.as<uint32_t>()}, ExclOut{c->d_row_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NROW, 0, ssc);
     k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>(), c->d_parent.as<int32_t>(),
                                                             c->d_de_off.as<uint32_t>(), c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->period, d_cnt);
+    c->launches += 2 + 3 * 2 * (uint64_t)((rbits + 7) / 8) + 3 + 3 + 3 + 3 + 1;   // join, links, sort passes, 3 scans, init/union/count, scatter
     tstop(c, T_K3);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_cnt, d_cnt, CNT_N * 4, cudaMemcpyDeviceToHost, st));
@@ -571,6 +577,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         k4_components_kernel<<<std::max(1u, grid), 128, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
                                                                   c->d_de.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt);
     }
+    if (nrow || c->h_cnt[CNT_NDE]) c->launches += 1;
     tstop(c, T_K4);
     CU(cudaGetLastError());
 
@@ -669,6 +676,8 @@ int bdk_kernel_times(bdk_ctx* c, const char** names, float* ms, int* launches, i
     for (int t = 0; t < T_N && k < cap; ++t, ++k) { names[k] = c->timers[t].name; ms[k] = c->timers[t].ms; launches[k] = c->timers[t].launches; }
     return k;
 }
+
+uint64_t bdk_kernel_launches(bdk_ctx* c) { return c ? c->launches : 0; }
 
 int bdk_set_comm(bdk_ctx* c, void*, int, int) {
     if (!c) return BDK_ERR_ARG;

@@ -204,6 +204,9 @@ int bdk_get_support(bdk_ctx* ctx, const int32_t** sv_of_read, uint64_t* n);
  * on the context's stream. names[i] are static strings. Returns the number of entries. */
 int bdk_kernel_times(bdk_ctx* ctx, const char** names, float* ms, int* launches, int cap);
 
+/* Number of kernels this context has launched since the last bdk_reset / bdk_create. */
+uint64_t bdk_kernel_launches(bdk_ctx* ctx);
+
 /* Pinned host memory helpers for callers without their own CUDA binding. */
 void* bdk_host_alloc(uint64_t bytes);
 void bdk_host_free(void* p);

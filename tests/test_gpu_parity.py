@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the reference's goldens.
+Every test here needs a B200: run with  pytest -m gpu."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from breakdancer_b200 import api, synth
+from oracle import oracle
+from tests import util
+from tests.test_oracle_golden import CASES, _golden_poisson
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(b, cols, what, **kw):
+    ro = oracle.run(b, cols)
+    table, summary, regions, areads, rr, support, ctx = util.run_gpu(b, cols, **kw)
+    util.assert_result_matches_oracle(ro, table, summary, regions, areads, rr, support, what)
+    ctx.close()
+    return ro
+
+
+# ---- the reference's own integration test (integration-test/breakdancer_test.py) through the drop-in CLI
+@pytest.mark.parametrize("chr_,cn_lib,af,golden", CASES)
+def test_cli_reproduces_chr21_goldens(chr_, cn_lib, af, golden):
+    args = (["-a"] if cn_lib else []) + (["-h"] if af else []) + (["-o", chr_] if chr_ else []) + ["inv_del_bam_config"]
+    p = subprocess.run([util.CLI] + args, cwd=util.CHR21, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert util.strip_header(p.stdout) == util.strip_header(open(os.path.join(util.CHR21, golden)).read())
+
+
+def test_cli_bed_dump(tmp_path):
+    bed = tmp_path / "out.bed"
+    p = subprocess.run([util.CLI, "-g", str(bed), "inv_del_bam_config"], cwd=util.CHR21, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert bed.read_text() == open(os.path.join(util.CHR21, "expected.bed")).read()
+
+
+def test_cli_fastq_dump(tmp_path):
+    prefix = tmp_path / "actual"
+    p = subprocess.run([util.CLI, "-o", "21", "-d", str(prefix), "inv_del_bam_config"], cwd=util.CHR21, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert util.strip_header(p.stdout) == util.strip_header(open(os.path.join(util.CHR21, "expected_output")).read())
+    for lib in ("H_IJ-NA19238-NA19238-extlibs", "H_IJ-NA19240-NA19240-extlibs"):
+        for k in (1, 2):
+            got = open(f"{prefix}.{lib}.{k}.fastq").read()
+            assert got == open(os.path.join(util.CHR21, f"expected.{lib}.{k}.fastq")).read(), (lib, k)
+
+
+def test_cli_errors_like_the_reference(tmp_path):
+    p = subprocess.run([util.CLI, str(tmp_path / "missing.cfg")], capture_output=True, text=True)
+    assert p.returncode == 1 and "Error: no bams files in config file!" in p.stdout
+    (tmp_path / "c.cfg").write_text("map:nope.bam\tlib:l\tmean:300\tstd:30\treadlen:75\n")
+    p = subprocess.run([util.CLI, "c.cfg"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and p.stderr.startswith("ERROR: ")
+
+
+# ---- stage-by-stage parity with the oracle on synthetic data ---------------------------------------
+@pytest.mark.parametrize("od", util.OPTION_SETS, ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()) or "default")
+def test_gpu_matches_oracle_option_sweep(od):
+    w = synth.generate(util.GENOME3, util.LIBS4, 100000, seed=1, anomaly_frac=0.04, somatic_frac=0.3)
+    b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+    ro = _check(b, cols, str(od))
+    assert len(ro.table.sv) > 5
+
+
+@pytest.mark.parametrize("seed", [2, 3, 4])
+def test_gpu_matches_oracle_seeds(seed):
+    w = synth.generate(util.GENOME3, util.LIBS4, 200000, seed=seed, anomaly_frac=0.05, somatic_frac=0.3)
+    b, cols, *_ = util.workload_bundle(w, api.Options(min_read_pair=1, score_threshold=-100))
+    _check(b, cols, f"seed {seed}")
+
+
+def test_gpu_chunked_pushes_and_device_push():
+    w = synth.generate(util.GENOME3, util.LIBS4, 150000, seed=6, anomaly_frac=0.04)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    _check(b, cols, "3 chunks", chunks=3)
+    _check(b, cols, "17 chunks", chunks=17)
+    _check(b, cols, "device push", device_push=True)
+
+
+def test_gpu_single_bam_single_key_path():
+    w = synth.config2(300000, seed=20260101)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    ro = _check(b, cols, "config2-shaped")
+    assert len(ro.table.sv) > 10
+
+
+def test_gpu_edge_cases_empty_ragged_tiny():
+    w = synth.generate(util.GENOME3, util.LIBS4, 6000, seed=5, anomaly_frac=0.05)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    for n in (0, 1, 2, 3, 5, 127, 128, 129, 511, 512, 513, 4095, 4096, 4097, 8191, 12000):
+        sub = {k: np.ascontiguousarray(v[:n]) for k, v in cols.items()}
+        _check(b, sub, f"n={n}")
+
+
+def test_gpu_all_anomalous_staging_overflow_and_giant_region():
+    w = synth.generate([("c", 400000)], [synth.LibSpec("l", "b.bam", 300, 30, 75, ["g"])], 40000, seed=9,
+                       anomaly_frac=1.0, cluster_frac=1.0, cluster_mean_pairs=400, odd_frac=0.0)
+    for od in (dict(), dict(seq_coverage_lim=1), dict(min_read_pair=1, score_threshold=-1)):
+        b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+        _check(b, cols, str(od))
+
+
+def test_gpu_reset_and_reuse_is_idempotent():
+    w = synth.generate(util.GENOME3, util.LIBS4, 80000, seed=8, anomaly_frac=0.04)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    ctx = api.Context(b, 0)
+    tables = []
+    for _ in range(3):
+        ctx.reset()
+        ctx.push(cols)
+        tables.append(ctx.finish())
+    for t in tables[1:]:
+        assert t.sv.tobytes() == tables[0].sv.tobytes() and np.array_equal(t.lib_count, tables[0].lib_count)
+    assert ctx.kernel_launches() > 10
+    ctx.close()
+
+
+def test_gpu_poisson_tail_matches_boost_known_answers():
+    w = synth.generate(util.GENOME3, util.LIBS4, 100, seed=1)
+    b, *_ = util.workload_bundle(w, api.Options())
+    ctx = api.Context(b, 0)
+    lam, k, lp = _golden_poisson()
+    got = ctx.poisson_logsf(lam, k)
+    util.assert_logp_close(lp, got)
+    ctx.close()
+
+
+def test_gpu_rejects_read_group_without_library():
+    w = synth.generate(util.GENOME3, util.LIBS4, 5000, seed=1)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    b.rg_lib[0] = -1
+    ctx = api.Context(b, 0)
+    with pytest.raises(api.BdkError, match="library index out of range"):
+        ctx.push(cols)
+    ctx.close()
+
+
+def test_gpu_config2_two_million_pairs_matches_oracle():
+    """BASELINE config 2 shape (single library chr1-like, DEL-only) at 2 M pairs, bit-exact vs the oracle."""
+    w = synth.config2(2_000_000, seed=20260101)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    ro = _check(b, cols, "config2 2M pairs")
+    assert len(ro.table.sv) > 100 and (ro.table.sv["flag"] == 2).sum() > 50   # the planted deletions
+
+
+def test_gpu_config3_shape_matches_oracle():
+    """BASELINE config 3 shape (2 bams x 2 libraries, all five SV types, -c 3 -q 35) at 1.5 M pairs."""
+    w = synth.config3(1_500_000, seed=20260102)
+    b, cols, *_ = util.workload_bundle(w, api.Options(cut_sd=3, min_map_qual=35))
+    ro = _check(b, cols, "config3 1.5M pairs")
+    flags = set(ro.table.sv["flag"].tolist())
+    assert {1, 2, 3, 4, 8} <= flags

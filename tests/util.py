@@ -113,7 +113,17 @@ def assert_tables_equal(ref: api.SvTable, got: api.SvTable, what: str = ""):
 
 
 def assert_summary_equal(a: api.SummaryT, b: api.SummaryT, what: str = ""):
-    assert bytes(a) == bytes(b), f"{what}: summary differs (reflen {a.covered_ref_len} vs {b.covered_ref_len}, window {a.window} vs {b.window})"
+    """Bit-exact, except that NaNs (0/0 densities of an empty input) may differ in sign/payload:
+    x86 produces the negative default NaN, the GPU the positive canonical one."""
+    for name, _ in api.SummaryT._fields_:
+        x = np.frombuffer(bytes(getattr(a, name)) if not isinstance(getattr(a, name), int) else np.array([getattr(a, name)]).tobytes(), np.uint8)
+        y = np.frombuffer(bytes(getattr(b, name)) if not isinstance(getattr(b, name), int) else np.array([getattr(b, name)]).tobytes(), np.uint8)
+        if name in ("seq_coverage", "read_density"):
+            fx, fy = x.view(np.float32), y.view(np.float32)
+            assert np.array_equal(np.isnan(fx), np.isnan(fy)), f"{what}: summary.{name} NaN pattern"
+            assert np.array_equal(fx[~np.isnan(fx)], fy[~np.isnan(fy)]), f"{what}: summary.{name}"
+        else:
+            assert np.array_equal(x, y), f"{what}: summary.{name} differs (reflen {a.covered_ref_len} vs {b.covered_ref_len}, window {a.window} vs {b.window})"
 
 
 def assert_result_matches_oracle(ro: oracle.OracleResult, table: api.SvTable, summary: api.SummaryT, regions=None,
