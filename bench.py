@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- read-pairs/sec to SV calls (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+
+A "step" is one whole job of the hot path over one synthetic batch: BASELINE.json configs[1]
+(single-library 30x chr1, DEL-only, 50 M read pairs = 100 M position-sorted records per GPU):
+classify -> regions -> link graph -> scored SV table.  `value` is measured with the record columns
+already resident in HBM (bdk_push_device); `e2e` is the same job through the C ABI with HOST (pinned)
+columns, so host->device copies and the device->host read of the SV table are inside the timed
+region.  For N > 1 each rank runs its own chromosome-shaped shard (the path shards by chromosome with
+no data-path collective: weak scaling); torch.distributed/NCCL is used only for the barrier and the
+max-over-ranks of the device time.  One JSON line is printed by rank 0.
+
+--impl reference times the unmodified reference executable (oracle/_ref/breakdancer-max; the oracle
+port if that is missing) on the host cores: every step runs one single-threaded process per core, each
+on its own bounded sample of the same workload written as BAM (the reference's documented way to use
+several cores is one process per chromosome).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "read_pairs_per_sec_to_sv_calls"
+UNIT = "read-pairs/s"
+BYTES_PER_RECORD = 25          # pos,mpos,tid,mtid,isize int32 + flag u16 + mapq u8 + rgid u16
+HOST_BYTES_PER_RECORD = 37     # + qlen int32 + qid u64 side columns copied by bdk_push
+
+
+def workload_name(pairs):
+    return f"synthetic single-library 30x chr1-shaped, DEL-only, {pairs / 1e6:g}M read pairs per GPU (BASELINE configs[1])"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ---------------------------------------------------------------------------------------------------
+def _write_sample_bams(tmp, nproc, pairs_each, seed0):
+    """nproc independent BAMs (+ configs) of `pairs_each` read pairs each, config-2 distribution."""
+    from breakdancer_b200 import api, synth
+    jobs = []
+    for i in range(nproc):
+        w = synth.config2(pairs_each, seed=seed0 + i)
+        d = os.path.join(tmp, f"s{i}")
+        os.makedirs(d, exist_ok=True)
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(os.path.join(d, bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=1)
+        open(os.path.join(d, "cfg"), "w").write(w.config_text())
+        jobs.append((d, w.n // 2))
+    return jobs
+
+
+def _run_reference_once(jobs):
+    """One process per job, all concurrently; returns (wall seconds, total pairs, kind)."""
+    from oracle import oracle
+    if oracle.have_reference():
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([oracle.REF_BIN, "cfg"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d, _ in jobs]
+        rcs = [p.wait() for p in procs]
+        dt = time.perf_counter() - t0
+        if any(rcs):
+            raise RuntimeError(f"reference exited with {rcs}")
+        return dt, sum(n for _, n in jobs), "reference"
+    # oracle port (single thread, decode included through our host decoder)
+    from breakdancer_b200 import api
+    t0 = time.perf_counter()
+    for d, _ in jobs:
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            cfg = api.BamConfig(path="cfg")
+            st = api.BamStream(cfg, threads=1)
+            b = api.ParamBundle.from_stream(api.Options(), cfg, st)
+            oracle.run(b, {k: v.copy() for k, v in st.cols.items()})
+        finally:
+            os.chdir(cwd)
+    return time.perf_counter() - t0, sum(n for _, n in jobs), "port"
+
+
+def cpu_baseline(pairs_total, nproc, seed0=20260101):
+    tmp = tempfile.mkdtemp(prefix="bdk_cpu_", dir=os.environ.get("TMPDIR", "/tmp"))
+    try:
+        jobs = _write_sample_bams(tmp, nproc, max(1000, pairs_total // nproc), seed0)
+        dt, pairs, kind = _run_reference_once(jobs)
+        return {"value": pairs / dt, "unit": UNIT, "cores": nproc if kind == "reference" else 1, "kind": kind,
+                "sample": f"{nproc} x {pairs // nproc} read pairs of the same workload as BAM, one single-threaded process each, {dt:.1f} s wall"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nproc = max(1, min(cores, 32))
+    pairs_each = args.ref_pairs
+    tmp = tempfile.mkdtemp(prefix="bdk_ref_", dir=os.environ.get("TMPDIR", "/tmp"))
+    try:
+        jobs = _write_sample_bams(tmp, nproc, pairs_each, 20260101)
+        for _ in range(args.warmup):
+            _run_reference_once(jobs)
+        t = []
+        kind = "reference"
+        pairs = 0
+        for _ in range(args.steps):
+            dt, pairs, kind = _run_reference_once(jobs)
+            t.append(dt)
+        ms = 1e3 * sum(t) / len(t)
+        value = pairs / (ms / 1e3)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic",
+                "config": {"workload": workload_name(args.pairs), "step_sample": f"{nproc} x {pairs_each} read pairs as BAM, one process per host core"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc if kind == "reference" else 1, "kind": kind,
+                                 "sample": f"{nproc} BAMs x {pairs_each} read pairs per step"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, device):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append((time.perf_counter(), l.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                if t0 <= ts <= t1 + 0.2:
+                    sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            if t0 <= ts <= t1 + 0.2:
+                for name, v in zip(self.NAMES, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from breakdancer_b200 import api, synth, synth_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the bdk hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    pairs = args.pairs
+    cols = synth_torch.config2_device(pairs, seed=20260101 + rank, device=dev, tid=0)
+    n = cols["pos"].numel()
+    npairs = n // 2
+    lib = synth.LibSpec("lib1", "syn_chr1.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
+    wl = synth.Workload({}, [("chr1", synth_torch.CHR1_LEN)], [lib], ["rg1"], ["lib1"], ["syn_chr1.bam"])
+    cfg = api.BamConfig(text=wl.config_text())
+    bundle = api.ParamBundle(api.Options(), cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, 1)
+    ctx = api.Context(bundle, local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    dsoa = synth_torch.soa_of(cols)
+
+    ktimes = {}
+    launches = [0]
+
+    def add_times():
+        for k, v in ctx.kernel_times().items():
+            e = ktimes.setdefault(k, {"ms": 0.0, "launches": 0})
+            e["ms"] += v["ms"]; e["launches"] += v["launches"]
+        launches[0] += ctx.kernel_launches()
+
+    def step_device():
+        ctx.reset()
+        ctx.push_soa(dsoa, n, device=True)
+        return ctx.finish_raw()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step_device()
+    n_sv = int(res.n_sv) if args.warmup else 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_device()
+        add_times()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    n_sv = int(res.n_sv)
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop(t0, t1) if sampler else None
+    summ = ctx.summary()
+    n_anom = int(summ.n_anomalous)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([npairs], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_pairs = float(tot.item())
+    else:
+        total_pairs = float(npairs)
+    value = total_pairs / (ms / 1e3)
+
+    # ---- end to end: host (pinned) columns through bdk_push, H2D inside the timed region -------------
+    k1 = dict(ktimes.get("k1_classify", {"ms": 0.0, "launches": 0}))
+    gpu_launches = launches[0]
+    hcols = synth_torch.to_pinned(cols)
+    hsoa = api.soa_from_pointers({k: hcols[k].data_ptr() for k in api.COLUMN_DTYPES})
+
+    def step_host():
+        ctx.reset()
+        ctx.push_soa(hsoa, n, device=False)
+        return ctx.finish_raw()
+
+    for _ in range(min(2, args.warmup)):
+        res = step_host()
+    barrier()
+    e0.record()
+    w0 = time.perf_counter()
+    esteps = max(1, min(args.steps, 5))
+    for _ in range(esteps):
+        res = step_host()
+    e1.record()
+    barrier()
+    e_ms_wall = 1e3 * (time.perf_counter() - w0) / esteps
+    e_ms = max(e0.elapsed_time(e1) / esteps, 0.0)
+    e_ms = max(e_ms, e_ms_wall) if world == 1 else e_ms
+    d2h = int(res.n_sv) * (80 + 4 * bundle.params.nlib + 8 * bundle.nkey) + 15072 + 36
+    if world > 1:
+        t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e2e_value = total_pairs / (e_ms / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        k1_ms = k1["ms"] / max(1, k1["launches"])
+        achieved = n * BYTES_PER_RECORD / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_record")
+            traffic = traffic * n if traffic else None
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(pairs), "records_per_gpu": n, "anomalous_reads_per_gpu": n_anom, "sv_calls_per_gpu": n_sv,
+                       "sharding": "one chromosome-shaped shard per GPU, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "inputs (3.7 GB) are larger than L2, no flush needed", "options": "defaults (-c 3 -q 35 -r 2 -y 30)"},
+            "roofline": {"bound": "hbm", "kernel": "k1_classify_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_RECORD, "kernel_ms": k1_ms},
+            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in ktimes.items()},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_ms, "h2d_bytes_per_step": n * HOST_BYTES_PER_RECORD,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_pairs, max(1, min(os.cpu_count() or 1, 32)))
+            except Exception as ex:   # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=50_000_000, help="read pairs per GPU (BASELINE configs[1]: 50 M)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-pairs", type=int, default=6_000_000, help="total read pairs of the CPU baseline sample")
+    ap.add_argument("--ref-pairs", type=int, default=400_000, help="read pairs per process and step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

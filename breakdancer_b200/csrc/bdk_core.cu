@@ -55,7 +55,7 @@ struct bdk_ctx {
     std::string err;
 
     // constants on the device
-    DevBuf d_libdev, d_rg_info, d_blibs, d_rg_lib, d_rg_bam;
+    DevBuf d_libdev, d_lib_mean, d_rg_info, d_blibs, d_rg_lib, d_rg_bam;
     // pass-1 accumulators: one block so it can be snapshotted before a push
     DevBuf d_acc, d_acc_bak;
     size_t acc_bytes = 0, off_first = 0, off_last = 0, off_hist = 0, off_err = 0, off_cursor = 0;
@@ -249,7 +249,7 @@ void bdk_destroy(bdk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->d_libdev, &c->d_rg_info, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_unit_cnt,
+    DevBuf* all[] = {&c->d_libdev, &c->d_lib_mean, &c->d_rg_info, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_unit_cnt,
         &c->d_unit_p, &c->d_tile_seg, &c->d_stage, &c->d_stage_p, &c->d_cnt, &c->d_cnt_off, &c->d_p_off, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
@@ -315,6 +315,7 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     for (int t = 0; t < T_N; ++t) { c->timers[t].name = kTimerNames[t]; CUC(cudaEventCreate(&c->timers[t].e0)); CUC(cudaEventCreate(&c->timers[t].e1)); }
     // constant tables
     std::vector<LibDev> ld = make_libdev(c->P);
+    std::vector<float> lm = make_lib_mean(c->P);
     std::vector<uint32_t> rgi(p->nrg);
     for (int i = 0; i < p->nrg; ++i)
         rgi[i] = p->rg_lib[i] < 0 ? RG_INVALID : ((uint32_t)p->rg_lib[i] | ((uint32_t)p->rg_bam[i] << 8));
@@ -325,6 +326,7 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
     };
     CUC(up(c->d_libdev, ld.data(), ld.size() * sizeof(LibDev)));
+    CUC(up(c->d_lib_mean, lm.data(), lm.size() * 4));
     CUC(up(c->d_rg_info, rgi.data(), rgi.size() * 4));
     CUC(up(c->d_blibs, c->libs.data(), c->libs.size() * sizeof(bdk_lib)));
     CUC(up(c->d_rg_lib, c->rg_lib.data(), c->rg_lib.size() * 4));
@@ -560,7 +562,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     K4Static S;
     S.ar = c->d_ar.as<bdk_aread>(); S.read_region = c->d_read_region.as<int32_t>(); S.read_cand = c->d_read_cand.as<int32_t>();
     S.mate = c->d_mate.as<int32_t>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
-    S.cand_maxlen = c->d_cand_maxlen.as<int32_t>(); S.libs = c->d_libdev.as<LibDev>();
+    S.cand_maxlen = c->d_cand_maxlen.as<int32_t>(); S.lib_mean = c->d_lib_mean.as<float>();
     S.hist = (uint32_t*)((char*)c->d_acc.p + c->off_hist); S.density = c->d_density.as<float>();
     S.A = A; S.nreg = 0; S.ncand = 0; S.period = c->period; S.nkey = nkey; S.nlib = nlib;
     S.chr_restricted = c->P.chr_restricted; S.min_read_pair = c->P.min_read_pair; S.score_threshold = c->P.score_threshold;

@@ -22,10 +22,16 @@ inline std::vector<LibDev> make_libdev(const bdk_params& p) {
     std::vector<LibDev> v(p.nlib);
     for (int i = 0; i < p.nlib; ++i) {
         const bdk_lib& l = p.libs[i];
-        v[i].upper = l.uppercutoff; v[i].lower = l.lowercutoff; v[i].mean = l.mean_insertsize;
+        v[i].upper = l.uppercutoff; v[i].lower = l.lowercutoff;
         v[i].min_mapq = l.min_mapping_quality < 0 ? p.min_map_qual : l.min_mapping_quality;
         v[i].key = p.cn_lib ? i : l.bam_index;
     }
+    return v;
+}
+
+inline std::vector<float> make_lib_mean(const bdk_params& p) {
+    std::vector<float> v(p.nlib);
+    for (int i = 0; i < p.nlib; ++i) v[i] = p.libs[i].mean_insertsize;
     return v;
 }
 

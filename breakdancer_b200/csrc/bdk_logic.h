@@ -53,8 +53,8 @@ BDK_HD float f_div(float a, float b) {
 }
 
 // ---- per-library constants as the kernels see them -------------------------------------------
-struct LibDev {
-    float upper, lower, mean;
+struct alignas(16) LibDev {   // one 16-byte load per record
+    float upper, lower;
     int32_t min_mapq;   // effective: library override or -q
     int32_t key;        // copy-number key: library index (-a) or the library's bam index
 };
@@ -71,19 +71,6 @@ enum : uint32_t {
     CR_REV = 1u << 12          // reverse strand (ori() == REV)
 };
 
-BDK_HD int pe_classify_flags(uint32_t f, bool interchrom, bool leftmost, bool large_insert, bool small_insert) {
-    if ((f & 0x400u) || !(f & 0x1u)) return BDK_NA;          // dup || !paired
-    if (f & 0x4u) return BDK_UNMAPPED;
-    if (f & 0x8u) return BDK_MATE_UNMAPPED;
-    if (interchrom) return BDK_ARP_CTX;
-    bool rr = (f & 0x10u) != 0, mr = (f & 0x20u) != 0;
-    if (rr == mr) return rr ? BDK_ARP_RR : BDK_ARP_FF;
-    if (leftmost == rr) return BDK_ARP_RF;
-    if (large_insert) return BDK_ARP_LARGE_INSERT;
-    if (small_insert) return BDK_ARP_SMALL_INSERT;
-    return BDK_NORMAL_FR;
-}
-
 BDK_HD int long_insert_reflag(int flag, bool gt_upper, bool lt_upper, bool lt_lower) {
     if (gt_upper && flag == BDK_NORMAL_RF) flag = BDK_ARP_RF;
     if (lt_upper && flag == BDK_ARP_RF) flag = BDK_NORMAL_RF;
@@ -97,29 +84,35 @@ struct ClassifyOpts {
     int32_t long_insert;
 };
 
+// Branch-free restatement of IlluminaPEReadClassifier::classify + the two filter chains.
+// NA (dup || !paired), UNMAPPED and MATE_UNMAPPED reads are dropped by both passes
+// (BamSummary.cpp:89-94, BreakDancer.cpp:159), so only the mapped-pair classes are materialised.
 BDK_HD uint32_t classify_record(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
                                 uint32_t bdqual, const LibDev& L, const ClassifyOpts& o) {
-    int32_t a = isize < 0 ? -isize : isize;   // abs(core.isize)
-    float af = (float)a;                      // int -> float conversion of the reference's compares
-    bool gt_upper = af > L.upper, lt_upper = af < L.upper, lt_lower = af < L.lower;
-    bool inter = tid != mtid;
-    int cls = pe_classify_flags(flag, inter, pos < mpos, gt_upper, lt_lower);
-    bool proper = (flag & (0x2u | 0x4u | 0x8u | 0x1u | 0x400u)) == (0x2u | 0x1u);
-    bool either_unmapped = (flag & (0x4u | 0x8u)) != 0;
-    bool mapq_ok = (int32_t)bdqual > L.min_mapq;
-    uint32_t r = (flag & 0x10u) ? CR_REV : 0u;
-    bool base_ok = cls != BDK_NA && !either_unmapped && !(o.transchr && !inter);
-    int cls2 = o.long_insert ? long_insert_reflag(cls, gt_upper, lt_upper, lt_lower) : cls;
-    if (mapq_ok) {
-        if (proper) r |= CR_SPROPER;
-        if (base_ok && cls2 != BDK_NORMAL_FR && cls2 != BDK_NORMAL_RF) r |= (uint32_t)cls2 << CR_HIST_SHIFT;
-        if (base_ok && !(cls != BDK_ARP_CTX && a > o.max_sd)) {
-            int cls3 = cls2 == BDK_ARP_RR ? BDK_ARP_FF : cls2;
-            r |= CR_KEPT | (uint32_t)cls3;
-            if (proper) r |= CR_MPROPER;
-            if (cls3 != BDK_NORMAL_FR && cls3 != BDK_NORMAL_RF) r |= CR_ANOM;
-        }
-    }
+    const int32_t a = isize < 0 ? -isize : isize;   // abs(core.isize)
+    const float af = (float)a;                      // the reference compares int against float cut-offs
+    const bool gt_upper = af > L.upper, lt_lower = af < L.lower;
+    const bool inter = tid != mtid;
+    const bool rr = (flag & 0x10u) != 0, mr = (flag & 0x20u) != 0;
+    int cls = gt_upper ? BDK_ARP_LARGE_INSERT : (lt_lower ? BDK_ARP_SMALL_INSERT : BDK_NORMAL_FR);
+    cls = ((pos < mpos) == rr) ? BDK_ARP_RF : cls;
+    cls = (rr == mr) ? (rr ? BDK_ARP_RR : BDK_ARP_FF) : cls;
+    cls = inter ? BDK_ARP_CTX : cls;
+    const bool proper = (flag & 0x40Fu) == 0x3u;                 // paired, proper, both mapped, not dup
+    const bool base_ok = (flag & 0x40Du) == 0x1u                 // paired, not dup, neither mate unmapped
+                         && !(o.transchr && !inter);
+    const bool mapq_ok = (int32_t)bdqual > L.min_mapq;
+    int cls2 = cls;
+    if (o.long_insert) cls2 = long_insert_reflag(cls, gt_upper, af < L.upper, lt_lower);
+    const bool normal2 = cls2 == BDK_NORMAL_FR || cls2 == BDK_NORMAL_RF;
+    const int cls3 = cls2 == BDK_ARP_RR ? BDK_ARP_FF : cls2;
+    const bool kept = mapq_ok && base_ok && !(cls != BDK_ARP_CTX && a > o.max_sd);
+    uint32_t r = rr ? CR_REV : 0u;
+    r |= (mapq_ok && proper) ? CR_SPROPER : 0u;
+    r |= (mapq_ok && base_ok && !normal2) ? (uint32_t)cls2 << CR_HIST_SHIFT : 0u;
+    r |= kept ? (CR_KEPT | (uint32_t)cls3) : 0u;
+    r |= (kept && proper) ? CR_MPROPER : 0u;
+    r |= (kept && !normal2) ? CR_ANOM : 0u;
     return r;
 }
 
@@ -226,7 +219,7 @@ struct K4Static {
     const RegionRec* reg;
     const uint32_t* P;            // [nkey][A] inclusive proper-pair prefix counts per key
     const int32_t* cand_maxlen;   // [ncand] _max_readlen when the candidate was closed
-    const LibDev* libs;
+    const float* lib_mean;        // [nlib] LibraryConfig::mean_insertsize
     const uint32_t* hist;         // [nlib][BDK_NUM_FLAGS] pass-1 read_counts_by_flag
     const float* density;         // [nkey]
     uint64_t A;
@@ -396,7 +389,7 @@ BDK_HD bool k4_process_sv(const K4Static& S, K4Mut& M, int s0, int s1, int w, in
     float diff = 0.0f;
     for (int l = 0; l < S.nlib; ++l)
         if (lib_count[l])
-            diff = f_add(diff, f_sub((float)lib_span[l], f_mul((float)lib_count[l], S.libs[l].mean)));
+            diff = f_add(diff, f_sub((float)lib_span[l], f_mul((float)lib_count[l], S.lib_mean[l])));
     int diffspan = (int)((double)f_div(diff, (float)flag_counts[flag]) + 0.5);
 
     int total_region_size = (R0.end - R0.start + 1) + (n == 2 ? (S.reg[s1].end - S.reg[s1].start + 1) : 0);

@@ -1,0 +1,61 @@
+"""Per-chromosome sharding across the GPUs of one node (BASELINE.json configs[3]).
+
+The reference scales by running one `breakdancer-max -o <chr>` process per chromosome (README:31);
+each such run is self-contained (own summary statistics, own window, own region indices). The same
+decomposition is used here: chromosomes are packed onto ranks (longest-processing-time first on the
+record counts), every rank runs its chromosomes one after the other on its own GPU through its own
+bdk context with -o semantics, and the per-chromosome SV tables are gathered to rank 0 in tid order.
+There is NO collective on the data path; torch.distributed only carries the final (small) tables.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence
+
+import numpy as np
+
+
+def lpt_pack(weights: Sequence[int], nranks: int) -> List[List[int]]:
+    """Longest-processing-time-first packing of items (chromosomes) onto nranks bins.
+    Returns, per rank, the ascending list of item indices. Deterministic (ties -> lower index / rank)."""
+    order = sorted(range(len(weights)), key=lambda i: (-int(weights[i]), i))
+    load = [0] * nranks
+    bins: List[List[int]] = [[] for _ in range(nranks)]
+    for i in order:
+        if weights[i] == 0:
+            continue
+        r = min(range(nranks), key=lambda k: (load[k], k))
+        bins[r].append(i)
+        load[r] += int(weights[i])
+    return [sorted(b) for b in bins]
+
+
+def chromosome_counts(cols: Dict[str, np.ndarray], ntid: int) -> np.ndarray:
+    return np.bincount(cols["tid"], minlength=ntid)[:ntid]
+
+
+def chromosome_slices(cols: Dict[str, np.ndarray], ntid: int) -> List[slice]:
+    """Record ranges of each chromosome in a (tid, pos)-sorted stream."""
+    edges = np.searchsorted(cols["tid"], np.arange(ntid + 1))
+    return [slice(int(edges[t]), int(edges[t + 1])) for t in range(ntid)]
+
+
+def run_sharded(cols: Dict[str, np.ndarray], ntid: int, rank: int, world: int,
+                run_chromosome: Callable[[int, Dict[str, np.ndarray]], object], gather: bool = True):
+    """Run `run_chromosome(tid, columns_of_tid)` for this rank's chromosomes; with gather=True return on
+    rank 0 the list [(tid, result)] of ALL ranks ordered by tid (None elsewhere)."""
+    counts = chromosome_counts(cols, ntid)
+    mine = lpt_pack(counts.tolist(), world)[rank]
+    sl = chromosome_slices(cols, ntid)
+    local = []
+    for t in mine:
+        sub = {k: np.ascontiguousarray(v[sl[t]]) for k, v in cols.items()}
+        local.append((t, run_chromosome(t, sub)))
+    if not gather or world == 1:
+        return sorted(local, key=lambda x: x[0]) if rank == 0 or not gather else None
+    import torch.distributed as dist
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(local, out, dst=0)
+    if rank != 0:
+        return None
+    merged = [x for part in out for x in part]
+    return sorted(merged, key=lambda x: x[0])

@@ -24,6 +24,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     const bdk_params& p = *pp;
     int nkey = nkey_of(p), nlib = p.nlib;
     std::vector<LibDev> libs = make_libdev(p);
+    std::vector<float> lib_mean = make_lib_mean(p);
     ClassifyOpts co{p.max_sd, p.transchr_rearrange, p.illumina_long_insert};
 
     // ---- K1 -----------------------------------------------------------------------------------
@@ -151,7 +152,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     std::vector<uint64_t> row_key(nrow_cap + 1, 0);
     K4Static KS;
     KS.ar = ar.data(); KS.read_region = read_region.data(); KS.read_cand = read_cand.data(); KS.mate = mate.data();
-    KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.libs = libs.data();
+    KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.lib_mean = lib_mean.data();
     KS.hist = acc.hist.data(); KS.density = density.data(); KS.A = (uint64_t)A; KS.nreg = nreg; KS.ncand = ncand;
     KS.period = period; KS.nkey = nkey; KS.nlib = nlib; KS.chr_restricted = p.chr_restricted;
     KS.min_read_pair = p.min_read_pair; KS.score_threshold = p.score_threshold; KS.fisher = p.fisher;
@@ -219,7 +220,7 @@ extern "C" double hostsim_gamma_q(double a, double x) { return gamma_q_d(a, x); 
 extern "C" uint32_t hostsim_classify(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
                                      uint32_t bdqual, float upper, float lower, int32_t min_mapq, int32_t max_sd,
                                      int32_t transchr, int32_t long_insert) {
-    LibDev L{upper, lower, 0.0f, min_mapq, 0};
+    LibDev L{upper, lower, min_mapq, 0};
     ClassifyOpts o{max_sd, transchr, long_insert};
     return classify_record(pos, mpos, tid, mtid, isize, flag, bdqual, L, o);
 }

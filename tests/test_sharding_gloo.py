@@ -1,0 +1,64 @@
+"""N > 1 host logic on CPU: chromosome packing and the gather of per-chromosome SV tables over
+torch.distributed (gloo, world_size 2). The per-chromosome engine here is the oracle; on the GPU box the
+same driver (shard.run_sharded) is given a bdk context per rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from breakdancer_b200 import api, shard, synth
+from oracle import oracle
+from tests import util
+
+
+def test_lpt_pack_balances_and_is_deterministic():
+    w = [g[1] for g in synth.GRCH38]
+    for n in (1, 2, 4, 8):
+        bins = shard.lpt_pack(w, n)
+        assert sorted(i for b in bins for i in b) == list(range(len(w)))
+        loads = [sum(w[i] for i in b) for b in bins]
+        assert max(loads) <= sum(w) / n * 1.08 + max(w) * (n == 8) * 0.0 or n == 1
+        assert bins == shard.lpt_pack(w, n)
+    assert shard.lpt_pack([5, 0, 3], 2) == [[0], [2]]
+
+
+def _engine(w, opts_kw):
+    def run(tid, cols):
+        o = api.Options(chr=w.genome[tid][0], **opts_kw)
+        b, _, *_ = util.workload_bundle(w, o)
+        r = oracle.run(b, cols)
+        return r.table.sv.tobytes(), r.table.lib_count.tobytes(), len(r.regions)
+    return run
+
+
+def _worker(rank, world, port, seed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = synth.generate(util.GENOME3, util.LIBS4, 60000, seed=seed, anomaly_frac=0.04)
+    res = shard.run_sharded(w.cols, len(w.genome), rank, world, _engine(w, {}))
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_run_equals_per_chromosome_runs():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 21, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w = synth.generate(util.GENOME3, util.LIBS4, 60000, seed=21, anomaly_frac=0.04)
+    want = shard.run_sharded(w.cols, len(w.genome), 0, 1, _engine(w, {}))
+    assert [t for t, _ in got] == [0, 1, 2] and got == want
+    assert sum(len(r[0]) for _, r in got) > 0
