@@ -1,6 +1,6 @@
 // bdk_core.cu -- the per-GPU context behind the bdk C ABI (include/bdk.h): device memory,
-// streams, and the launch sequence  K1 classify -> unit scan -> reorder -> finalize -> K2 regions
-// -> K3 mate join / link sort / run-length / components -> K4 connection walk + score.
+// streams, and the launch sequence  K1 classify + ordered compaction (+ span search) -> finalize
+// -> K2 regions -> K3 mate join / link sort / run-length / components -> K4 connection walk + score.
 // There is no CPU implementation of any stage in this library: every entry point that computes
 // needs a CUDA device and fails with BDK_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
@@ -40,8 +40,8 @@ struct StageTimer {
     bool pending = false;
 };
 
-enum { T_H2D = 0, T_K1, T_SCAN_REORDER, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_N };
-const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_scan_reorder", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results"};
+enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_N };
+const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_span", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results"};
 
 }  // namespace
 
@@ -55,27 +55,32 @@ struct bdk_ctx {
     std::string err;
 
     // constants on the device
-    DevBuf d_libdev, d_lib_mean, d_rg_info, d_blibs, d_rg_lib, d_rg_bam;
+    DevBuf d_rgtab, d_cnt_rg, d_lib_mean, d_blibs, d_rg_lib, d_rg_bam;
+    int ncnt = 0;                 // private pass-1 counter columns (0: warp-vote fallback)
+    int pad_rg = 0;               // a read group that has a library
     // pass-1 accumulators: one block so it can be snapshotted before a push
     DevBuf d_acc, d_acc_bak;
     size_t acc_bytes = 0, off_first = 0, off_last = 0, off_hist = 0, off_err = 0, off_cursor = 0;
     // per-job state
     uint64_t n_records = 0;       // records pushed so far
-    uint64_t n_units = 0, n_tiles = 0;
-    uint32_t A = 0;               // anomalous reads staged so far
-    DevBuf d_unit_cnt, d_unit_p, d_tile_seg, d_stage, d_stage_p;
-    uint32_t stage_cap = 0;
+    uint32_t A = 0;               // anomalous reads compacted so far
+    uint32_t out_cap = 0;         // capacity of d_ar / d_P in reads
+    // K1 tile chaining (look-back) state, reused by every launch
+    DevBuf d_ticket, d_tile_status, d_tile_agg, d_tile_inc, d_tile_bams;
+    uint64_t tile_cap = 0;
+    uint32_t epoch = 0;
     // chunk buffers for host pushes
     DevBuf d_chunk[2][10];
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // finish() work space
-    DevBuf d_cnt, d_cnt_off, d_p_off, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
+    DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
         d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_links, d_links_tmp,
         d_sort_hist, d_edge_key, d_edge_start, d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
         d_deleted, d_de, d_queue, d_rows, d_row_lib_count, d_row_lib_span, d_row_cn_count, d_row_cn, d_row_emit, d_row_key,
         d_pois_l, d_pois_k, d_pois_o;
     bool finished = false, summary_ready = false;
     int k1_blocks_per_sm = 0;
+    size_t k1_smem = 0;
     uint64_t launches = 0;       // kernels launched since the last bdk_reset
     // host results
     bdk_summary_t h_summary;
@@ -131,7 +136,7 @@ void tcollect(bdk_ctx* c) {
 }
 
 int reset_job(bdk_ctx* c) {
-    c->n_records = 0; c->n_units = 0; c->n_tiles = 0; c->A = 0;
+    c->n_records = 0; c->A = 0;
     c->finished = false; c->summary_ready = false; c->launches = 0;
     // accumulators: counts 0, first = ~0, last = 0
     CU(cudaMemsetAsync(c->d_acc.p, 0, c->acc_bytes, c->stream));
@@ -141,89 +146,108 @@ int reset_job(bdk_ctx* c) {
     return 0;
 }
 
-// one K1 launch over n records whose columns are on the device
-int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, uint64_t unit_base, uint64_t tile_base) {
+typedef void (*K1Fn)(const K1Args);
+K1Fn k1_fn(const bdk_ctx* c) {
+    const bool single = c->nkey == 1, smem = c->P.nrg <= K1_RG_SMEM;
+    return single ? (smem ? k1_classify_kernel<true, true> : k1_classify_kernel<true, false>)
+                  : (smem ? k1_classify_kernel<false, true> : k1_classify_kernel<false, false>);
+}
+
+// one K1 launch (+ the span search) over n records whose columns are on the device; qlen / qid may be
+// mapped host memory (only anomalous records touch them)
+int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, bool timed) {
+    const uint64_t ntiles = div_up<uint64_t>(n, K1_TILE);
+    if (!ntiles) return 0;
     K1Args a;
     a.c = cols; a.n = n; a.base_index = base_index;
-    a.libs = c->d_libdev.as<LibDev>(); a.rg_info = c->d_rg_info.as<uint32_t>();
-    a.nrg = c->P.nrg; a.nlib = c->P.nlib; a.nbam = c->P.nbam; a.nkey = c->nkey; a.ntid = c->P.ntid;
-    a.nrg_smem = c->P.nrg <= 2048 ? c->P.nrg : 0;
+    a.rgtab = c->d_rgtab.as<RgDev>();
+    a.nrg = c->P.nrg; a.nlib = c->P.nlib; a.nbam = c->P.nbam; a.nkey = c->nkey;
+    a.pad_rg = c->pad_rg;
+    a.ncnt = c->ncnt; a.cnt_rg = c->d_cnt_rg.as<int32_t>();
     a.co.max_sd = c->P.max_sd; a.co.transchr = c->P.transchr_rearrange; a.co.long_insert = c->P.illumina_long_insert;
-    a.stage = c->d_stage.as<bdk_aread>(); a.stage_p = c->d_stage_p.as<uint32_t>(); a.stage_cap = c->stage_cap;
+    a.ar = c->d_ar.as<bdk_aread>(); a.P = c->d_P.as<uint32_t>(); a.cap = c->out_cap;
     char* acc = (char*)c->d_acc.p;
-    a.cursor = (uint32_t*)(acc + c->off_cursor);
-    a.unit_cnt = c->d_unit_cnt.as<uint32_t>(); a.unit_p = c->d_unit_p.as<uint32_t>(); a.tile_seg = c->d_tile_seg.as<uint32_t>();
-    a.unit_base = unit_base; a.tile_base = tile_base;
-    a.rg_sproper = (unsigned long long*)acc;
-    a.first = (unsigned long long*)(acc + c->off_first); a.last = (unsigned long long*)(acc + c->off_last);
-    a.hist = (uint32_t*)(acc + c->off_hist); a.err = (uint32_t*)(acc + c->off_err);
-    const size_t smem = ((size_t)a.nlib * BDK_NUM_FLAGS + a.nrg_smem) * 4;
-    const uint64_t ntiles = div_up<uint64_t>(n, K1_TILE);
-    if (!c->k1_blocks_per_sm) {
-        int bps = 0;
-        if (c->nkey == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_classify_kernel<true>, K1_THREADS, smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_classify_kernel<false>, K1_THREADS, smem);
-        c->k1_blocks_per_sm = std::max(1, bps);
+    a.carry = (uint32_t*)(acc + c->off_cursor);
+    a.ticket = c->d_ticket.as<uint32_t>();
+    a.tile_status = c->d_tile_status.as<uint32_t>(); a.tile_agg = c->d_tile_agg.as<uint32_t>(); a.tile_inc = c->d_tile_inc.as<uint32_t>();
+    a.tile_bams = c->d_tile_bams.as<unsigned long long>();
+    a.epoch = ++c->epoch;
+    if (c->epoch >= 0x3fffffffu) {   // epoch space exhausted: start over with clean status words
+        CU(cudaMemsetAsync(c->d_tile_status.p, 0, c->d_tile_status.cap, c->stream));
+        c->epoch = 1; a.epoch = 1;
     }
+    a.rg_sproper = (unsigned long long*)acc;
+    a.hist = (uint32_t*)(acc + c->off_hist); a.err = (uint32_t*)(acc + c->off_err);
+    CU(cudaMemsetAsync(c->d_ticket.p, 0, 4, c->stream));
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)kNumSMs * c->k1_blocks_per_sm);
-    if (!grid) return 0;
-    if (c->nkey == 1) k1_classify_kernel<true><<<grid, K1_THREADS, smem, c->stream>>>(a);
-    else k1_classify_kernel<false><<<grid, K1_THREADS, smem, c->stream>>>(a);
-    c->launches += 1;
+    if (timed) tstart(c, T_K1);
+    k1_fn(c)<<<grid, K1_THREADS, c->k1_smem, c->stream>>>(a);
+    if (timed) tstop(c, T_K1);
+    CU(cudaGetLastError());
+    if (timed) tstart(c, T_SPAN);
+    const int64_t items = (int64_t)c->P.ntid * c->P.nbam;
+    const unsigned sgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(div_up<int64_t>(items, 4), (int64_t)kNumSMs * 8));
+    k1_span_kernel<<<sgrid, 128, 0, c->stream>>>(cols.tid, cols.pos, cols.rgid, n, base_index, c->d_rgtab.as<RgDev>(), c->P.nrg, c->P.nbam, c->P.ntid,
+                                                 c->d_tile_bams.as<unsigned long long>(), (unsigned long long*)(acc + c->off_first),
+                                                 (unsigned long long*)(acc + c->off_last));
+    if (timed) tstop(c, T_SPAN);
+    c->launches += 2;
     CU(cudaGetLastError());
     return 0;
 }
 
-int grow_tables(bdk_ctx* c, uint64_t add_tiles) {
-    const uint64_t tiles = c->n_tiles + add_tiles, units = tiles * K1_WARPS;
-    ENSP(c->d_unit_cnt, units * 4);
-    ENSP(c->d_unit_p, units * 4 * c->nkey);
-    ENSP(c->d_tile_seg, tiles * 4);
+// look-back tables for launches of up to `tiles` tiles
+int grow_tiles(bdk_ctx* c, uint64_t tiles) {
+    if (tiles <= c->tile_cap) return 0;
+    const size_t ncomp = 1 + (size_t)c->nkey;
+    ENS(c->d_tile_status, tiles * 4); ENS(c->d_tile_agg, tiles * 4 * ncomp); ENS(c->d_tile_inc, tiles * 4 * ncomp);
+    ENS(c->d_tile_bams, tiles * 8);
+    CU(cudaMemsetAsync(c->d_tile_status.p, 0, c->d_tile_status.cap, c->stream));
+    c->tile_cap = tiles;
     return 0;
 }
 
-int grow_stage(bdk_ctx* c, uint64_t want) {
-    if (want <= c->stage_cap) return 0;
+int grow_out(bdk_ctx* c, uint64_t want) {
+    if (want <= c->out_cap) return 0;
     if (want > 0xfffffff0ull) return fail(c, BDK_ERR_NOMEM, "more than 2^32 anomalous reads in one context");
-    ENSP(c->d_stage, want * sizeof(bdk_aread));
-    ENSP(c->d_stage_p, want * 4 * c->nkey);
-    c->stage_cap = (uint32_t)want;
+    ENSP(c->d_ar, want * sizeof(bdk_aread));
+    ENSP(c->d_P, want * 4 * c->nkey);
+    c->out_cap = (uint32_t)want;
     return 0;
 }
 
 // push of one batch whose columns are already device pointers; handles staging overflow by retry
 template <class RunFn>
-int push_common(bdk_ctx* c, uint64_t n, RunFn run) {
+int push_common(bdk_ctx* c, uint64_t n, uint64_t max_launch, RunFn run) {
     if (c->finished) return fail(c, BDK_ERR_STATE, "bdk_push after bdk_finish (call bdk_reset first)");
     if (n == 0) return 0;
     if (c->n_records + n > 0xffffffffull) return fail(c, BDK_ERR_ARG, "more than 2^32 records in one context");
-    const uint64_t tiles = div_up<uint64_t>(n, K1_TILE);
-    int rc = grow_tables(c, tiles);
+    int rc = grow_tiles(c, div_up<uint64_t>(std::min(n, max_launch), K1_TILE));
     if (rc) return rc;
-    rc = grow_stage(c, std::max<uint64_t>((uint64_t)c->A + std::max<uint64_t>(n / 16, 1 << 16), c->stage_cap));
+    rc = grow_out(c, std::max<uint64_t>((uint64_t)c->A + std::max<uint64_t>(n / 16, 1 << 16), c->out_cap));
     if (rc) return rc;
     for (int attempt = 0; attempt < 3; ++attempt) {
         CU(cudaMemcpyAsync(c->d_acc_bak.p, c->d_acc.p, c->acc_bytes, cudaMemcpyDeviceToDevice, c->stream));
         rc = run();
         if (rc) return rc;
-        uint32_t tail[2];   // err, cursor
+        uint32_t tail[2];   // err, anomalous reads so far
         CU(cudaMemcpyAsync(tail, (char*)c->d_acc.p + c->off_err, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         tcollect(c);
         if (tail[0] & K1_ERR_RG)
             return fail(c, BDK_ERR_DATA, "library index out of range (a record's read group has no library)");
-        if (tail[0] & K1_ERR_OVERFLOW) {   // staging too small: restore the accumulators, grow, run again
+        if (tail[0] & K1_ERR_OVERFLOW) {   // output too small: restore the accumulators, grow, run again
             CU(cudaMemcpyAsync(c->d_acc.p, c->d_acc_bak.p, c->acc_bytes, cudaMemcpyDeviceToDevice, c->stream));
-            rc = grow_stage(c, (uint64_t)tail[1] + (tail[1] - c->A) / 8 + 1024);
+            rc = grow_out(c, (uint64_t)tail[1] + (tail[1] - c->A) / 8 + 1024);
             if (rc) return rc;
             continue;
         }
         c->A = tail[1];
         c->summary_ready = false;
-        c->n_records += n; c->n_tiles += tiles; c->n_units += tiles * K1_WARPS;
+        c->n_records += n;
         return 0;
     }
-    return fail(c, BDK_ERR_NOMEM, "staging overflow persisted");
+    return fail(c, BDK_ERR_NOMEM, "output overflow persisted");
 }
 
 }  // namespace
@@ -249,8 +273,8 @@ void bdk_destroy(bdk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->d_libdev, &c->d_lib_mean, &c->d_rg_info, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_unit_cnt,
-        &c->d_unit_p, &c->d_tile_seg, &c->d_stage, &c->d_stage_p, &c->d_cnt, &c->d_cnt_off, &c->d_p_off, &c->d_ar, &c->d_P, &c->d_summary,
+    DevBuf* all[] = {&c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_ticket,
+        &c->d_tile_status, &c->d_tile_agg, &c->d_tile_inc, &c->d_tile_bams, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
         &c->d_edge_key, &c->d_edge_start, &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
@@ -313,21 +337,40 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) { CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)); CUC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming)); }
     for (int t = 0; t < T_N; ++t) { c->timers[t].name = kTimerNames[t]; CUC(cudaEventCreate(&c->timers[t].e0)); CUC(cudaEventCreate(&c->timers[t].e1)); }
-    // constant tables
+    // constant tables: per-read-group constants with the ids a record maps to
     std::vector<LibDev> ld = make_libdev(c->P);
     std::vector<float> lm = make_lib_mean(c->P);
-    std::vector<uint32_t> rgi(p->nrg);
-    for (int i = 0; i < p->nrg; ++i)
-        rgi[i] = p->rg_lib[i] < 0 ? RG_INVALID : ((uint32_t)p->rg_lib[i] | ((uint32_t)p->rg_bam[i] << 8));
+    std::vector<RgDev> rgt(p->nrg + 1);
+    std::vector<int32_t> cnt_rg;                       // counter column -> representative read group
+    {
+        std::vector<std::pair<int, int>> pairs;        // distinct (library, bam) pairs, in order of appearance
+        for (int i = 0; i < p->nrg; ++i) {
+            if (p->rg_lib[i] < 0) continue;
+            std::pair<int, int> pr(p->rg_lib[i], p->rg_bam[i]);
+            if (std::find(pairs.begin(), pairs.end(), pr) == pairs.end()) { pairs.push_back(pr); cnt_rg.push_back(i); }
+        }
+        c->ncnt = (int)pairs.size() <= K1_PRIV_CNT ? std::max<int>(1, (int)pairs.size()) : 0;
+        if (!c->ncnt) cnt_rg.clear();
+        if (cnt_rg.empty()) cnt_rg.push_back(0);
+        for (int i = p->nrg - 1; i >= 0; --i) if (p->rg_lib[i] >= 0) c->pad_rg = i;
+        for (int i = 0; i <= p->nrg; ++i) {
+            RgDev& r = rgt[i];
+            if (i == p->nrg || p->rg_lib[i] < 0) { r.upper = 0; r.lower = 0; r.min_mapq = 0x7fffffff; r.info = RGI_INVALID; continue; }
+            const int lib = p->rg_lib[i], bam = p->rg_bam[i];
+            const int col = c->ncnt ? (int)(std::find(pairs.begin(), pairs.end(), std::make_pair(lib, bam)) - pairs.begin()) : (int)RGI_CNT_NONE;
+            r.upper = ld[lib].upper; r.lower = ld[lib].lower; r.min_mapq = ld[lib].min_mapq;
+            r.info = (uint32_t)lib | ((uint32_t)ld[lib].key << RGI_KEY_SHIFT) | ((uint32_t)bam << RGI_BAM_SHIFT) | ((uint32_t)col << RGI_CNT_SHIFT);
+        }
+    }
     auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e1 = cudaMalloc(&b.p, std::max<size_t>(bytes, 16));
         if (e1 != cudaSuccess) return e1;
         b.cap = bytes;
         return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
     };
-    CUC(up(c->d_libdev, ld.data(), ld.size() * sizeof(LibDev)));
+    CUC(up(c->d_rgtab, rgt.data(), rgt.size() * sizeof(RgDev)));
+    CUC(up(c->d_cnt_rg, cnt_rg.data(), cnt_rg.size() * 4));
     CUC(up(c->d_lib_mean, lm.data(), lm.size() * 4));
-    CUC(up(c->d_rg_info, rgi.data(), rgi.size() * 4));
     CUC(up(c->d_blibs, c->libs.data(), c->libs.size() * sizeof(bdk_lib)));
     CUC(up(c->d_rg_lib, c->rg_lib.data(), c->rg_lib.size() * 4));
     CUC(up(c->d_rg_bam, c->rg_bam.data(), c->rg_bam.size() * 4));
@@ -338,8 +381,8 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     c->off_hist = c->off_last + nbt * 8;
     c->off_err = c->off_hist + (size_t)p->nlib * BDK_NUM_FLAGS * 4;
     c->off_err = (c->off_err + 7) & ~size_t(7);
-    c->off_cursor = c->off_err + 4;
-    c->acc_bytes = c->off_cursor + 4;
+    c->off_cursor = c->off_err + 4;                       // carry: anomalous reads, then kept proper pairs per key
+    c->acc_bytes = c->off_cursor + 4 * (1 + (size_t)c->nkey);
     CUC(cudaMalloc(&c->d_acc.p, c->acc_bytes)); c->d_acc.cap = c->acc_bytes;
     CUC(cudaMalloc(&c->d_acc_bak.p, c->acc_bytes)); c->d_acc_bak.cap = c->acc_bytes;
     CUC(cudaMalloc(&c->d_cnt.p, CNT_N * 4)); c->d_cnt.cap = CNT_N * 4;
@@ -347,8 +390,17 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     CUC(cudaMalloc(&c->d_density.p, (size_t)std::max(1, c->nkey) * 4)); c->d_density.cap = (size_t)std::max(1, c->nkey) * 4;
     CUC(cudaMalloc(&c->d_scan_sums.p, SS_GRID * 4)); c->d_scan_sums.cap = SS_GRID * 4;
     CUC(cudaMalloc(&c->d_sort_hist.p, 256 * SS_GRID * 4)); c->d_sort_hist.cap = 256 * SS_GRID * 4;
-    CUC(cudaFuncSetAttribute(k1_classify_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
-    CUC(cudaFuncSetAttribute(k1_classify_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    CUC(cudaMalloc(&c->d_ticket.p, 16)); c->d_ticket.cap = 16;
+    {   // K1 launch shape: dynamic shared memory and resident CTAs per SM
+        const size_t ncomp = 1 + (size_t)c->nkey;
+        c->k1_smem = (p->nrg <= K1_RG_SMEM ? (size_t)(p->nrg + 1) * sizeof(RgDev) : 0) + (size_t)p->nlib * BDK_NUM_FLAGS * 4 +
+                     (size_t)(c->ncnt > 1 ? c->ncnt : 0) * K1_THREADS * 4 + (c->nkey > 1 ? (size_t)c->nkey * (K1_THREADS + K1_WARPS) * 4 : 0) +
+                     ncomp * K1_WARPS * 4 + ncomp * 4;
+        int bps = 0;
+        CUC(cudaFuncSetAttribute(k1_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_fn(c), K1_THREADS, c->k1_smem));
+        c->k1_blocks_per_sm = std::max(1, bps);
+    }
     int rc = reset_job(c);
     if (rc) { g_create_error = c->err; bdk_destroy(c); return rc; }
     CUC(cudaStreamSynchronize(c->stream));
@@ -379,12 +431,7 @@ int bdk_push_device(bdk_ctx* c, const bdk_soa* cols, uint64_t n) {
         if (!ptrs[i] && n) return fail(c, BDK_ERR_ARG, "null column %d", i);
         if ((uintptr_t)ptrs[i] & 15) return fail(c, BDK_ERR_ARG, "device column %d is not 16-byte aligned", i);
     }
-    return push_common(c, n, [&]() -> int {
-        tstart(c, T_K1);
-        int rc = launch_k1(c, *cols, n, (uint32_t)c->n_records, c->n_units, c->n_tiles);
-        tstop(c, T_K1);
-        return rc;
-    });
+    return push_common(c, n, n, [&]() -> int { return launch_k1(c, *cols, n, (uint32_t)c->n_records, true); });
 }
 
 int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
@@ -397,13 +444,12 @@ int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
     const uint64_t chunk_cap = std::min<uint64_t>(CH, div_up<uint64_t>(std::max<uint64_t>(n, 1), K1_TILE) * K1_TILE);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 10; ++k) ENS(c->d_chunk[b][k], chunk_cap * width[k]);
-    return push_common(c, n, [&]() -> int {
+    return push_common(c, n, CH, [&]() -> int {
         // double-buffered: the copy stream fills chunk i+1 while K1 runs on chunk i
         CU(cudaEventRecord(c->ev_done[0], c->stream));
         CU(cudaEventRecord(c->ev_done[1], c->stream));
         tstart(c, T_H2D);   // spans copies + kernels of this push on the compute stream
         uint64_t off = 0; int i = 0;
-        uint64_t unit_base = c->n_units, tile_base = c->n_tiles;
         while (off < n) {
             const uint64_t m = std::min<uint64_t>(CH, n - off);
             const int b = i & 1;
@@ -417,11 +463,9 @@ int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
             d.mtid = c->d_chunk[b][3].as<int32_t>(); d.isize = c->d_chunk[b][4].as<int32_t>(); d.flag = c->d_chunk[b][5].as<uint16_t>();
             d.mapq = c->d_chunk[b][6].as<uint8_t>(); d.rgid = c->d_chunk[b][7].as<uint16_t>(); d.qlen = c->d_chunk[b][8].as<int32_t>();
             d.qid = c->d_chunk[b][9].as<uint64_t>();
-            int rc = launch_k1(c, d, m, (uint32_t)(c->n_records + off), unit_base, tile_base);
+            int rc = launch_k1(c, d, m, (uint32_t)(c->n_records + off), false);
             if (rc) return rc;
             CU(cudaEventRecord(c->ev_done[b], c->stream));
-            const uint64_t tiles = div_up<uint64_t>(m, K1_TILE);
-            unit_base += tiles * K1_WARPS; tile_base += tiles;
             off += m; ++i;
         }
         tstop(c, T_H2D);
@@ -481,8 +525,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         return 0;
     }
     const size_t A1 = (size_t)A + 2;
-    ENS(c->d_cnt_off, c->n_units * 4 + 4); ENS(c->d_p_off, c->n_units * 4 * nkey + 4);
-    ENS(c->d_ar, A1 * sizeof(bdk_aread)); ENS(c->d_P, A1 * 4 * nkey);
+    { int rc2 = grow_out(c, A1); if (rc2) return rc2; }
     ENS(c->d_read_cand, A1 * 4); ENS(c->d_read_region, A1 * 4); ENS(c->d_alive, A1); ENS(c->d_freed, A1);
     ENS(c->d_mate, A1 * 4); ENS(c->d_sv_of_read, A1 * 4); ENS(c->d_cand_first, A1 * 4); ENS(c->d_cand_maxlen, A1 * 4);
     ENS(c->d_cand_info, A1 * sizeof(CandInfo)); ENS(c->d_reg, A1 * sizeof(RegionRec));
@@ -493,17 +536,6 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
     ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
-
-    // ---- K1 tail: unit offsets, stream order ---------------------------------------------------
-    tstart(c, T_SCAN_REORDER);
-    k1_scan_units_kernel<<<1, SCAN_THREADS, 0, st>>>(c->d_unit_cnt.as<uint32_t>(), c->d_unit_p.as<uint32_t>(), c->n_units, nkey,
-                                                     c->d_cnt_off.as<uint32_t>(), c->d_p_off.as<uint32_t>(), d_cnt + CNT_A);
-    k1_reorder_kernel<<<GS_GRID, 256, 0, st>>>(c->d_stage.as<bdk_aread>(), c->d_stage_p.as<uint32_t>(), c->d_cnt_off.as<uint32_t>(),
-                                               c->d_p_off.as<uint32_t>(), c->d_tile_seg.as<uint32_t>(), c->n_units, d_cnt + CNT_A, nkey,
-                                               c->d_ar.as<bdk_aread>(), c->d_P.as<uint32_t>());
-    c->launches += 2;
-    tstop(c, T_SCAN_REORDER);
-    CU(cudaGetLastError());
 
     // ---- K2 ----------------------------------------------------------------------------------
     const int dummy = dummy_region_of(c->P);

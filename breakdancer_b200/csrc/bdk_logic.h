@@ -88,10 +88,10 @@ struct ClassifyOpts {
 // NA (dup || !paired), UNMAPPED and MATE_UNMAPPED reads are dropped by both passes
 // (BamSummary.cpp:89-94, BreakDancer.cpp:159), so only the mapped-pair classes are materialised.
 BDK_HD uint32_t classify_record(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
-                                uint32_t bdqual, const LibDev& L, const ClassifyOpts& o) {
+                                uint32_t bdqual, float upper, float lower, int32_t min_mapq, const ClassifyOpts& o) {
     const int32_t a = isize < 0 ? -isize : isize;   // abs(core.isize)
     const float af = (float)a;                      // the reference compares int against float cut-offs
-    const bool gt_upper = af > L.upper, lt_lower = af < L.lower;
+    const bool gt_upper = af > upper, lt_lower = af < lower;
     const bool inter = tid != mtid;
     const bool rr = (flag & 0x10u) != 0, mr = (flag & 0x20u) != 0;
     int cls = gt_upper ? BDK_ARP_LARGE_INSERT : (lt_lower ? BDK_ARP_SMALL_INSERT : BDK_NORMAL_FR);
@@ -101,9 +101,9 @@ BDK_HD uint32_t classify_record(int32_t pos, int32_t mpos, int32_t tid, int32_t 
     const bool proper = (flag & 0x40Fu) == 0x3u;                 // paired, proper, both mapped, not dup
     const bool base_ok = (flag & 0x40Du) == 0x1u                 // paired, not dup, neither mate unmapped
                          && !(o.transchr && !inter);
-    const bool mapq_ok = (int32_t)bdqual > L.min_mapq;
+    const bool mapq_ok = (int32_t)bdqual > min_mapq;
     int cls2 = cls;
-    if (o.long_insert) cls2 = long_insert_reflag(cls, gt_upper, af < L.upper, lt_lower);
+    if (o.long_insert) cls2 = long_insert_reflag(cls, gt_upper, af < upper, lt_lower);
     const bool normal2 = cls2 == BDK_NORMAL_FR || cls2 == BDK_NORMAL_RF;
     const int cls3 = cls2 == BDK_ARP_RR ? BDK_ARP_FF : cls2;
     const bool kept = mapq_ok && base_ok && !(cls != BDK_ARP_CTX && a > o.max_sd);
@@ -114,6 +114,36 @@ BDK_HD uint32_t classify_record(int32_t pos, int32_t mpos, int32_t tid, int32_t 
     r |= (kept && proper) ? CR_MPROPER : 0u;
     r |= (kept && !normal2) ? CR_ANOM : 0u;
     return r;
+}
+BDK_HD uint32_t classify_record(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
+                                uint32_t bdqual, const LibDev& L, const ClassifyOpts& o) {
+    return classify_record(pos, mpos, tid, mtid, isize, flag, bdqual, L.upper, L.lower, L.min_mapq, o);
+}
+
+// The four decisions the streaming pass needs from every record, without materialising the class:
+//   CH_ANOM = CR_ANOM, CH_MPROPER = CR_MPROPER, CH_HIST = (pass-1 histogram nibble != 0), CH_SPROPER = CR_SPROPER.
+// Records with CH_HIST set (a superset of CH_ANOM, ~1-3 % of the stream) are classified in full
+// by classify_record() afterwards. Equivalence is checked exhaustively in tests (hostsim_classify_hot_check).
+enum : uint32_t { CH_ANOM = 1u, CH_MPROPER = 2u, CH_HIST = 4u, CH_SPROPER = 8u };
+BDK_HD uint32_t classify_hot(int32_t pos, int32_t mpos, int32_t tid, int32_t mtid, int32_t isize, uint32_t flag,
+                             uint32_t bdqual, float upper, float lower, int32_t min_mapq, const ClassifyOpts& o) {
+    const int32_t a = isize < 0 ? -isize : isize;
+    const float af = (float)a;
+    const bool inter = tid != mtid;
+    const bool rr = (flag & 0x10u) != 0;
+    const bool opposite = (((flag >> 4) ^ (flag >> 5)) & 1u) != 0;          // read and mate on different strands
+    const bool rf = (pos < mpos) == rr;                                      // reverse read leftmost
+    const bool lt_lower = af < lower;
+    const bool fr_pair = !inter && opposite;
+    bool normal2 = fr_pair && !rf && !(af > upper) && !lt_lower;             // NORMAL_FR
+    if (o.long_insert) normal2 = normal2 || (fr_pair && rf && af < upper && !lt_lower);   // ARP_RF re-flagged NORMAL_RF
+    const bool proper = (flag & 0x40Fu) == 0x3u;
+    const bool base_ok = (flag & 0x40Du) == 0x1u && !(o.transchr && !inter);
+    const bool mapq_ok = (int32_t)bdqual > min_mapq;
+    const bool pre = mapq_ok && base_ok;
+    const bool kept = pre && (inter || a <= o.max_sd);
+    return (kept && !normal2 ? CH_ANOM : 0u) | (kept && proper ? CH_MPROPER : 0u) | (pre && !normal2 ? CH_HIST : 0u) |
+           (mapq_ok && proper ? CH_SPROPER : 0u);
 }
 
 // meta word of bdk_aread
@@ -217,7 +247,7 @@ struct K4Static {
     const int32_t* read_cand;     // candidate index
     const int32_t* mate;          // mate read index or -1
     const RegionRec* reg;
-    const uint32_t* P;            // [nkey][A] inclusive proper-pair prefix counts per key
+    const uint32_t* P;            // [A][nkey] inclusive proper-pair prefix counts per key
     const int32_t* cand_maxlen;   // [ncand] _max_readlen when the candidate was closed
     const float* lib_mean;        // [nlib] LibraryConfig::mean_insertsize
     const uint32_t* hist;         // [nlib][BDK_NUM_FLAGS] pass-1 read_counts_by_flag
@@ -370,7 +400,7 @@ BDK_HD bool k4_process_sv(const K4Static& S, K4Mut& M, int s0, int s1, int w, in
         uint32_t c = 0;
         if (n == 2) {
             const RegionRec& R1 = S.reg[s1];
-            c = S.P[(uint64_t)k * S.A + R1.first_read] - S.P[(uint64_t)k * S.A + (R0.first_read + R0.n_reads - 1)];
+            c = S.P[(uint64_t)R1.first_read * S.nkey + k] - S.P[(uint64_t)(R0.first_read + R0.n_reads - 1) * S.nkey + k];
         }
         cnc[k] = c;
         float v = 0.0f;

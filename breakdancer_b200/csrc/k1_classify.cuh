@@ -3,19 +3,23 @@
 // Per record (reference: IlluminaPEReadClassifier::classify, BamSummary::_analyze_bam,
 // BreakDancer::push_read up to the point a read is found anomalous):
 //   * classify against the library's cut-offs                          -> bdk::classify_record
-//   * pass-1 statistics: proper-pair counts per read group, flag histogram per library,
-//     first/last record of every (bam, tid) for the covered reference length
+//   * pass-1 statistics: proper-pair counts per (library, bam), flag histogram per library
 //   * pass-2 filter; kept proper pairs feed the per-key running counts (nread_ROI / nread_FR),
-//     anomalous reads are compacted, in stream order, with their inclusive per-key counts.
+//     anomalous reads are compacted IN STREAM ORDER together with their inclusive per-key counts.
 //
 // Layout of the work: a tile is 4096 consecutive records; each of the 8 warps of a CTA owns a
-// contiguous 512-record span ("unit") and walks it in 4 iterations of 128 records, every lane
-// loading 4 consecutive records with 16-byte (int32 columns), 8-byte (u16) and 4-byte (u8)
-// streaming loads -> 100 bytes in flight per lane and iteration, fully coalesced.
-// Phase 1 classifies and keeps only bit masks in registers; one block-wide exchange reserves
-// the tile's segment in the staging array (one global atomic per tile); phase 2 turns the masks
-// into ranks with warp ballots and writes the anomalous reads. Tiles are handed out round-robin
-// to a persistent grid (a multiple of the 148 SMs).
+// contiguous 512-record span and walks it in 4 iterations of 128 records, every lane loading 4
+// consecutive records with 16-byte (int32 columns), 8-byte (u16) and 4-byte (u8) streaming loads
+// -> 100 bytes in flight per lane and iteration, fully coalesced. The per-read-group constants
+// (cut-offs, mapping-quality threshold, library / bam / key ids) are one 16-byte shared-memory
+// load; the pass-1 proper-pair counters are thread-private shared-memory columns (no conflicts,
+// no warp votes). Phase 1 keeps only two 16-bit masks per thread (anomalous, kept-proper).
+// Tiles are handed out by a ticket counter to a persistent grid (a multiple of the 148 SMs) and
+// chained by a decoupled look-back over (anomalous count, kept-proper count per key): every
+// anomalous read gets its final position in the stream-ordered output and its global inclusive
+// proper-pair counts in the same pass -- no staging, no second pass over the records.
+// The covered-reference-length statistic (first / last record of every (bam, chromosome)) needs
+// only the run boundaries of the sorted tid column: k1_span_kernel finds them by search.
 #pragma once
 #include "common.cuh"
 
@@ -29,30 +33,46 @@ constexpr int K1_UNIT = 32 * K1_IPT * K1_ITERS;             // 512 records per w
 constexpr int K1_TILE = K1_UNIT * K1_WARPS;                 // 4096
 constexpr int K1_MAXK = 64;                                 // copy-number keys (bams, or libraries with -a)
 constexpr int K1_MAXB = BDK_MAX_BAMS;
+constexpr int K1_MAXCOMP = K1_MAXK + 1;                     // look-back vector: anomalous count + one per key
+constexpr int K1_PRIV_CNT = 32;                             // (library, bam) pairs counted in private columns
+constexpr int K1_RG_SMEM = 1023;                            // read groups whose constants live in shared memory
 constexpr uint32_t K1_ERR_RG = 1u, K1_ERR_OVERFLOW = 2u;
-constexpr uint32_t RG_INVALID = 0x80000000u;                // rg_info: lib | srcbam << 8 | invalid << 31
+
+// Per-read-group constants: the library's cut-offs and the ids the record maps to.
+struct alignas(16) RgDev {
+    float upper, lower;
+    int32_t min_mapq;      // effective: library override or -q
+    uint32_t info;         // RGI_* fields
+};
+constexpr uint32_t RGI_LIB_MASK = 0xffu;                    // bits 0-7   library index
+constexpr int RGI_KEY_SHIFT = 8;                            // bits 8-13  copy-number key
+constexpr int RGI_BAM_SHIFT = 14;                           // bits 14-19 source bam
+constexpr int RGI_CNT_SHIFT = 20;                           // bits 20-24 private counter column (31: none)
+constexpr uint32_t RGI_CNT_NONE = 31u;
+constexpr uint32_t RGI_INVALID = 0x80000000u;               // read group without a library
 
 struct K1Args {
-    bdk_soa c;                 // device columns of this push (16-byte aligned)
+    bdk_soa c;                 // device columns of this push (16-byte aligned); qlen / qid may be mapped host memory
     uint64_t n;                // records in this push
     uint32_t base_index;       // stream index of record 0 of this push
-    const LibDev* libs;
-    const uint32_t* rg_info;
-    int32_t nrg, nlib, nbam, nkey, ntid;
-    int32_t nrg_smem;          // read groups counted in shared memory (0: global atomics)
+    const RgDev* rgtab;        // [nrg + 1]: entry nrg = invalid read group
+    int32_t nrg, nlib, nbam, nkey;
+    int32_t pad_rg;            // a read group with a library, used by padding records
+    int32_t ncnt;              // private counter columns in use (0: count with warp votes + global atomics)
+    const int32_t* cnt_rg;     // [ncnt] read group that receives the column's total
     ClassifyOpts co;
-    bdk_aread* stage;          // anomalous reads, tile segments in arrival order
-    uint32_t* stage_p;         // [stage_cap][nkey] unit-relative inclusive proper-pair counts
-    uint32_t stage_cap;
-    uint32_t* cursor;          // staging cursor
-    uint32_t* unit_cnt;        // [units] anomalous reads per unit           (this push: + unit_base)
-    uint32_t* unit_p;          // [units][nkey] kept proper pairs per unit
-    uint32_t* tile_seg;        // [tiles] staging offset of the tile's segment (this push: + tile_base)
-    uint64_t unit_base, tile_base;
+    bdk_aread* ar;             // [cap] anomalous reads in stream order
+    uint32_t* P;               // [cap][nkey] inclusive kept-proper-pair counts per key at each anomalous read
+    uint32_t cap;
+    uint32_t* carry;           // [1 + nkey] anomalous reads / kept proper pairs per key before this push (updated)
+    uint32_t* ticket;          // tile ticket counter (zero at launch)
+    uint32_t* tile_status;     // [tiles] epoch << 2 | state
+    uint32_t* tile_agg;        // [tiles][1 + nkey]
+    uint32_t* tile_inc;        // [tiles][1 + nkey]
+    unsigned long long* tile_bams;   // [tiles] source bams present in the tile (nbam > 1 only)
+    uint32_t epoch;
     unsigned long long* rg_sproper;   // [nrg]
     uint32_t* hist;                   // [nlib][BDK_NUM_FLAGS]
-    unsigned long long* first;        // [nbam][ntid]
-    unsigned long long* last;
     uint32_t* err;
 };
 
@@ -61,7 +81,7 @@ struct K1Rec4 {
     uint32_t flag[4], mapq[4], rg[4];
 };
 
-__device__ __forceinline__ void k1_load4(const bdk_soa& c, uint64_t g, int nv, K1Rec4& r) {
+__device__ __forceinline__ void k1_load4(const bdk_soa& c, uint64_t g, int nv, uint32_t pad_rg, K1Rec4& r) {
     if (nv == 4) {
         int4 a = ld_stream_v4(c.pos + g);   r.pos[0] = a.x; r.pos[1] = a.y; r.pos[2] = a.z; r.pos[3] = a.w;
         int4 b = ld_stream_v4(c.mpos + g);  r.mpos[0] = b.x; r.mpos[1] = b.y; r.mpos[2] = b.z; r.mpos[3] = b.w;
@@ -77,341 +97,390 @@ __device__ __forceinline__ void k1_load4(const bdk_soa& c, uint64_t g, int nv, K
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            bool v = j < nv;
+            bool v = j < nv;    // padding records: flag 0 (unpaired -> dropped by every filter), a valid read group
             r.pos[j] = v ? c.pos[g + j] : 0; r.mpos[j] = v ? c.mpos[g + j] : 0;
             r.tid[j] = v ? c.tid[g + j] : 0; r.mtid[j] = v ? c.mtid[g + j] : 0;
             r.isz[j] = v ? c.isize[g + j] : 0; r.flag[j] = v ? c.flag[g + j] : 0;
-            r.mapq[j] = v ? c.mapq[g + j] : 0; r.rg[j] = v ? c.rgid[g + j] : 0;
+            r.mapq[j] = v ? c.mapq[g + j] : 0; r.rg[j] = v ? c.rgid[g + j] : pad_rg;
         }
     }
 }
 
-// SINGLE_KEY: one copy-number key (the common single-bam run): the running count lives in a register.
-template <bool SINGLE_KEY>
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, v, d); if (lane >= d) v += t; }
+    return v;
+}
+// population count of each nibble of a 16-bit mask, one count per byte of the result
+__device__ __forceinline__ uint32_t nibble_counts(uint32_t m) {
+    m = m - ((m >> 1) & 0x5555u);
+    m = (m & 0x3333u) + ((m >> 2) & 0x3333u);
+    return (m & 0xFu) | ((m & 0xF0u) << 4) | ((m & 0xF00u) << 8) | ((m & 0xF000u) << 12);
+}
+__device__ __forceinline__ uint32_t byte_sum(uint32_t v) { return __dp4a(v, 0x01010101u, 0u); }
+// sum of the bytes below byte `it`
+__device__ __forceinline__ uint32_t bytes_before(uint32_t v, int it) { return byte_sum(v & ((1u << (8 * it)) - 1u)); }
+__device__ __forceinline__ uint32_t byte_of(uint32_t v, int it) { return (v >> (8 * it)) & 0xffu; }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+
+enum : uint32_t { TS_AGG = 1u, TS_INC = 2u };
+
+// SINGLE_KEY: one copy-number key (the common single-bam run): its counts live in registers.
+// RG_SMEM: the read-group table fits in shared memory (nrg <= K1_RG_SMEM).
+template <bool SINGLE_KEY, bool RG_SMEM>
 __global__ void __launch_bounds__(K1_THREADS, 4) k1_classify_kernel(const K1Args a) {
-    extern __shared__ uint32_t s_dyn[];              // [nlib * 11] flag histogram, [nrg_smem] proper counts
-    uint32_t* s_hist = s_dyn;
-    uint32_t* s_rg = s_dyn + a.nlib * BDK_NUM_FLAGS;
-    __shared__ unsigned long long s_wfirst[K1_WARPS][K1_MAXB], s_wlast[K1_WARPS][K1_MAXB];
-    __shared__ unsigned long long s_whas[K1_WARPS];
-    __shared__ unsigned long long s_rfirst[K1_MAXB], s_rlast[K1_MAXB];   // CTA-running first/last of s_cur_tid
-    __shared__ unsigned long long s_rhas;
-    __shared__ int s_cur_tid;
-    __shared__ uint32_t s_wcnt[K1_WARPS], s_woff[K1_WARPS], s_seg;
-    __shared__ uint32_t s_run[SINGLE_KEY ? 1 : K1_WARPS][SINGLE_KEY ? 1 : K1_MAXK];
+    extern __shared__ int4 s_dyn4[];
+    const int ncomp = 1 + a.nkey;
+    const int nhist = a.nlib * BDK_NUM_FLAGS;
+    const int ncol = a.ncnt > 1 ? a.ncnt : 0;                                      // one column: a register does it
+    RgDev* s_rg = reinterpret_cast<RgDev*>(s_dyn4);                                // RG_SMEM: [nrg + 1]
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_rg + (RG_SMEM ? a.nrg + 1 : 0));   // [nlib * 11]
+    uint32_t* s_cnt = s_hist + nhist;                                              // [ncol][K1_THREADS]
+    uint32_t* s_px = s_cnt + ncol * K1_THREADS;                                    // !SINGLE_KEY: [nkey][K1_THREADS]
+    uint32_t* s_pt = s_px + (SINGLE_KEY ? 0 : a.nkey * K1_THREADS);                // !SINGLE_KEY: [nkey][K1_WARPS]
+    uint32_t* s_woff = s_pt + (SINGLE_KEY ? 0 : a.nkey * K1_WARPS);                // [ncomp][K1_WARPS]
+    uint32_t* s_base = s_woff + ncomp * K1_WARPS;                                  // [ncomp]
+    __shared__ uint32_t s_wa[K1_WARPS], s_wp[K1_WARPS];
+    __shared__ unsigned long long s_wb[K1_WARPS];
+    __shared__ uint32_t s_tile[2];
 
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const int nhist = a.nlib * BDK_NUM_FLAGS;
-    for (int i = threadIdx.x; i < nhist + a.nrg_smem; i += K1_THREADS) s_dyn[i] = 0;
-    if (threadIdx.x == 0) { s_rhas = 0; s_cur_tid = -1; }
+    for (int i = threadIdx.x; i < nhist + ncol * K1_THREADS; i += K1_THREADS) s_hist[i] = 0;
+    if (RG_SMEM) for (int i = threadIdx.x; i < a.nrg + 1; i += K1_THREADS) s_rg[i] = a.rgtab[i];
+    uint32_t* my_cnt = s_cnt + threadIdx.x;                                        // this thread's private counter column
+    uint32_t spcnt = 0;                                                            // ncnt == 1: pass-1 proper pairs seen by this thread
+    uint32_t bad = 0;                                                              // OR of the info words (bit 31: invalid read group)
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(a.ticket, 1u);
     __syncthreads();
 
-    const uint64_t ntiles = div_up<uint64_t>(a.n, K1_TILE);
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t span = tile * K1_TILE + (uint64_t)warp * K1_UNIT;   // first record of this warp's unit
-        const int32_t t0 = a.c.tid[tile * K1_TILE];                        // tid of the tile's first record
-        // ---------------- phase 1: classify, statistics, masks -----------------------------------
-        uint32_t amask = 0, pmask = 0, keys[K1_ITERS] = {0, 0, 0, 0};
-        unsigned long long flags4 = 0;      // 16 x 4-bit final ReadFlag
-        unsigned long long whas = 0;        // bams for which this warp recorded a first/last key
-#pragma unroll
+    const uint32_t ntiles = (uint32_t)div_up<uint64_t>(a.n, K1_TILE);
+    int par = 0;
+    for (;;) {
+        const uint32_t tile = s_tile[par];
+        if (tile >= ntiles) break;
+        if (threadIdx.x == 0) s_tile[par ^ 1] = atomicAdd(a.ticket, 1u);   // read after the next barrier
+        par ^= 1;
+        const uint64_t span = (uint64_t)tile * K1_TILE + (uint64_t)warp * K1_UNIT;   // first record of this warp's span
+        // ---------------- phase 1: four decisions per record, kept as bit masks ------------------------
+        uint32_t amask = 0, pmask = 0, hmask = 0, keys[K1_ITERS] = {0, 0, 0, 0};
+        unsigned long long bams = 0;
+#pragma unroll (SINGLE_KEY ? 1 : K1_ITERS)
         for (int it = 0; it < K1_ITERS; ++it) {
             const uint64_t g = span + (uint64_t)it * 128 + (uint64_t)lane * 4;
             const int nv = g + 4 <= a.n ? 4 : (g < a.n ? (int)(a.n - g) : 0);
             K1Rec4 r;
-            k1_load4(a.c, g, nv, r);
-            uint32_t bam_item[4];
-            uint32_t samebits = 0;          // items with tid == t0 (candidates for the tile-level first/last)
+            k1_load4(a.c, g, nv, (uint32_t)a.pad_rg, r);
+            uint32_t kk = 0, a4 = 0, p4 = 0, h4 = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool v = j < nv;
-                uint32_t info = 0;
-                if (v) {
-                    if (r.rg[j] < (uint32_t)a.nrg) info = __ldg(a.rg_info + r.rg[j]); else info = RG_INVALID;
-                    if (info & RG_INVALID) { atomicOr(a.err, K1_ERR_RG); info = 0; }
-                }
-                const int lib = info & 0xffu;
-                bam_item[j] = (info >> 8) & 0xffu;
-                uint32_t cr = 0;
-                LibDev L;
-                if (v) {
-                    L = a.libs[lib];
-                    cr = classify_record(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j], L, a.co);
-                }
-                const int bit = it * 4 + j;
-                if (cr & CR_ANOM) { amask |= 1u << bit; flags4 |= (unsigned long long)(cr & CR_FLAG_MASK) << (4 * bit); }
-                if (cr & CR_MPROPER) { pmask |= 1u << bit; if (!SINGLE_KEY) keys[it] |= (uint32_t)L.key << (8 * j); }
-                // pass-1 proper-pair count per read group: one atomic per distinct read group and warp
-                const bool sp = (cr & CR_SPROPER) != 0;
-                const unsigned spm = __ballot_sync(FULL, sp);
-                if (sp) {
-                    const unsigned peers = __match_any_sync(spm, r.rg[j]);
-                    if (lane == __ffs(peers) - 1) {
-                        if (a.nrg_smem) atomicAdd(&s_rg[r.rg[j]], (uint32_t)__popc(peers));
-                        else atomicAdd(&a.rg_sproper[r.rg[j]], (unsigned long long)__popc(peers));
-                    }
-                }
-                const int hf = (cr >> CR_HIST_SHIFT) & 0xF;
-                if (hf) atomicAdd(&s_hist[lib * BDK_NUM_FLAGS + hf], 1u);
-                if (v) {
-                    if (r.tid[j] == t0) samebits |= 1u << j;
-                    else {   // tile straddles a chromosome boundary: rare, go straight to memory
-                        const unsigned long long key = ((unsigned long long)(a.base_index + (uint32_t)(g + j)) << 32) | (uint32_t)r.pos[j];
-                        const size_t bt = (size_t)bam_item[j] * a.ntid + r.tid[j];
-                        if ((uint32_t)r.tid[j] < (uint32_t)a.ntid) { atomicMin(a.first + bt, key); atomicMax(a.last + bt, key); }
+                const uint32_t ri = min(r.rg[j], (uint32_t)a.nrg);
+                RgDev L;
+                if (RG_SMEM) L = s_rg[ri];
+                else { const int4 q = __ldg(reinterpret_cast<const int4*>(a.rgtab) + ri); L.upper = __int_as_float(q.x); L.lower = __int_as_float(q.y); L.min_mapq = q.z; L.info = (uint32_t)q.w; }
+                const uint32_t ch = classify_hot(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
+                                                 L.upper, L.lower, L.min_mapq, a.co);
+                bad |= L.info;
+                if (ch & CH_ANOM) a4 |= 1u << j;
+                if (ch & CH_MPROPER) p4 |= 1u << j;
+                if (ch & CH_HIST) h4 |= 1u << j;
+                if (!SINGLE_KEY) kk |= ((L.info >> RGI_KEY_SHIFT) & 0x3fu) << (8 * j);
+                if (a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
+                // pass-1 proper-pair count per (library, bam)
+                const uint32_t sp = (ch >> 3) & 1u;          // CH_SPROPER
+                if (a.ncnt == 1) spcnt += sp;
+                else if (a.ncnt) atomicAdd(my_cnt + ((L.info >> RGI_CNT_SHIFT) & 31u) * K1_THREADS, sp);   // private column: no conflicts
+                else {                                       // many (library, bam) pairs: one atomic per distinct read group and warp
+                    const unsigned spm = __ballot_sync(FULL, sp && r.rg[j] < (uint32_t)a.nrg);
+                    if ((spm >> lane) & 1u) {
+                        const unsigned peers = __match_any_sync(spm, r.rg[j]);
+                        if (lane == __ffs(peers) - 1) atomicAdd(&a.rg_sproper[r.rg[j]], (unsigned long long)__popc(peers));
                     }
                 }
             }
-            // first / last record per source bam inside this warp's unit (index-major keys, so the
-            // first hit of the lowest lane in the earliest iteration is the minimum)
-            for (int b = 0; b < a.nbam; ++b) {
-                uint32_t mb = 0;
+            amask |= a4 << (4 * it); pmask |= p4 << (4 * it); hmask |= h4 << (4 * it);
+            if (!SINGLE_KEY) keys[it] = kk;
+        }
+        // ---------------- warp level: ranks inside the 512-record span -----------------------------
+        const uint32_t ca = nibble_counts(amask);
+        const uint32_t ainc = warp_incl_scan(ca);
+        const uint32_t aex = ainc - ca;                                   // per iteration: anomalous reads in lower lanes
+        const uint32_t atot = __shfl_sync(FULL, ainc, 31);                // per iteration: anomalous reads of the warp
+        uint32_t pex = 0, ptot = 0;
+        if (SINGLE_KEY) {
+            const uint32_t cp = nibble_counts(pmask);
+            const uint32_t pinc = warp_incl_scan(cp);
+            pex = pinc - cp;
+            ptot = __shfl_sync(FULL, pinc, 31);
+            if (lane == 0) { s_wa[warp] = byte_sum(atot); s_wp[warp] = byte_sum(ptot); }
+        } else {
+            if (lane == 0) s_wa[warp] = byte_sum(atot);
+            for (int k = lane; k < a.nkey; k += 32) s_pt[k * K1_WARPS + warp] = 0;
+            unsigned long long present = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (((samebits >> j) & 1u) && bam_item[j] == (uint32_t)b) mb |= 1u << j;
-                const unsigned has = __ballot_sync(FULL, mb != 0);
-                if (!has) continue;
-                const int lo = __ffs(has) - 1, hi = 31 - __clz(has);
-                if (!((whas >> b) & 1ull) && lane == lo) {
-                    const int j = __ffs(mb) - 1;
-                    s_wfirst[warp][b] = ((unsigned long long)(a.base_index + (uint32_t)(g + j)) << 32) | (uint32_t)r.pos[j];
-                }
-                if (lane == hi) {
-                    const int j = 31 - __clz(mb);
-                    s_wlast[warp][b] = ((unsigned long long)(a.base_index + (uint32_t)(g + j)) << 32) | (uint32_t)r.pos[j];
-                }
-                whas |= 1ull << b;
+            for (int it = 0; it < K1_ITERS; ++it)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((pmask >> (it * 4 + j)) & 1u) present |= 1ull << ((keys[it] >> (8 * j)) & 0x3fu);
+            present = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)present) |
+                      ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(present >> 32)) << 32);
+            __syncwarp();
+            while (present) {                                             // warp-uniform loop over the keys present
+                const int k = __ffsll((long long)present) - 1;
+                present &= present - 1;
+                uint32_t c = 0;
+#pragma unroll
+                for (int it = 0; it < K1_ITERS; ++it)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (((pmask >> (it * 4 + j)) & 1u) && ((keys[it] >> (8 * j)) & 0x3fu) == (uint32_t)k) c += 1u << (8 * it);
+                const uint32_t inc = warp_incl_scan(c);
+                s_px[k * K1_THREADS + threadIdx.x] = inc - c;
+                if (lane == 31) s_pt[k * K1_WARPS + warp] = inc;
             }
         }
-        const uint32_t wcnt = __reduce_add_sync(FULL, (uint32_t)__popc(amask));
-        if (lane == 0) { s_wcnt[warp] = wcnt; s_whas[warp] = whas; }
+        if (a.nbam > 1) {
+            bams = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)bams) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(bams >> 32)) << 32);
+            if (lane == 0) s_wb[warp] = bams;
+        }
         __syncthreads();                                                     // S1
-        // ---------------- block exchange: reserve the tile's staging segment ----------------------
+        // ---------------- warp 0: tile totals, look-back --------------------------------------------
         if (warp == 0) {
-            uint32_t c = lane < K1_WARPS ? s_wcnt[lane] : 0, inc = c;
+            if (a.nbam > 1 && lane == 0) {
+                unsigned long long b = 0;
+                for (int w = 0; w < K1_WARPS; ++w) b |= s_wb[w];
+                a.tile_bams[tile] = b;
+            }
+            // lane owns components lane, lane + 32, lane + 64 (component 0: anomalous, 1 + k: key k)
+            uint32_t agg[3] = {0, 0, 0}, exc[3] = {0, 0, 0};
 #pragma unroll
-            for (int d = 1; d < K1_WARPS; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-            if (lane < K1_WARPS) s_woff[lane] = inc - c;
-            if (lane == K1_WARPS - 1) {
-                uint32_t seg = inc ? atomicAdd(a.cursor, inc) : 0;
-                s_seg = seg;
-                a.tile_seg[a.tile_base + tile] = seg;
-                if (inc && seg + inc > a.stage_cap) atomicOr(a.err, K1_ERR_OVERFLOW);
-            }
-        } else if (threadIdx.x == 32) {
-            // merge this tile's per-warp first/last into the CTA-running values of chromosome t0
-            if (t0 != s_cur_tid) {
-                unsigned long long h = s_rhas;
-                if ((uint32_t)s_cur_tid < (uint32_t)a.ntid)
-                    for (int b = 0; b < a.nbam; ++b)
-                        if ((h >> b) & 1ull) {
-                            atomicMin(a.first + (size_t)b * a.ntid + s_cur_tid, s_rfirst[b]);
-                            atomicMax(a.last + (size_t)b * a.ntid + s_cur_tid, s_rlast[b]);
-                        }
-                s_rhas = 0; s_cur_tid = t0;
-            }
-            unsigned long long h = s_rhas;
-            for (int w = 0; w < K1_WARPS; ++w) {
-                unsigned long long wh = s_whas[w];
-                for (int b = 0; b < a.nbam; ++b) {
-                    if (!((wh >> b) & 1ull)) continue;
-                    unsigned long long f = s_wfirst[w][b], l = s_wlast[w][b];
-                    if (!((h >> b) & 1ull)) { s_rfirst[b] = f; s_rlast[b] = l; h |= 1ull << b; }
-                    else { if (f < s_rfirst[b]) s_rfirst[b] = f; if (l > s_rlast[b]) s_rlast[b] = l; }
+            for (int q = 0; q < 3; ++q) {
+                const int comp = lane + 32 * q;
+                if (comp < ncomp) {
+                    uint32_t run = 0;
+                    for (int w = 0; w < K1_WARPS; ++w) {
+                        uint32_t v;
+                        if (comp == 0) v = s_wa[w];
+                        else if (SINGLE_KEY) v = s_wp[w];
+                        else v = byte_sum(s_pt[(comp - 1) * K1_WARPS + w]);
+                        s_woff[comp * K1_WARPS + w] = run;
+                        run += v;
+                    }
+                    agg[q] = run;
                 }
+                if (SINGLE_KEY && q == 0) break;
             }
-            s_rhas = h;
+            if (tile == 0) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int comp = lane + 32 * q;
+                    if (comp < ncomp) { exc[q] = a.carry[comp]; a.tile_inc[(size_t)tile * ncomp + comp] = exc[q] + agg[q]; }
+                    if (SINGLE_KEY && q == 0) break;
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_release_u32(a.tile_status + tile, (a.epoch << 2) | TS_INC);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int comp = lane + 32 * q;
+                    if (comp < ncomp) a.tile_agg[(size_t)tile * ncomp + comp] = agg[q];
+                    if (SINGLE_KEY && q == 0) break;
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_release_u32(a.tile_status + tile, (a.epoch << 2) | TS_AGG);
+                // look back over windows of 32 predecessor tiles (lane l inspects tile p - l)
+                int p = (int)tile - 1;
+                for (;;) {
+                    const int q_tile = p - lane;
+                    uint32_t st = TS_AGG;                                    // tiles before 0 contribute nothing
+                    if (q_tile >= 0) {
+                        do { st = ld_acquire_u32(a.tile_status + q_tile); } while ((st >> 2) != a.epoch);
+                        st &= 3u;
+                    }
+                    const unsigned incm = __ballot_sync(FULL, st == TS_INC);
+                    const int cut = incm ? __ffs(incm) - 1 : 31;            // nearest tile with an inclusive prefix
+                    const bool use = lane <= cut && q_tile >= 0;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        for (int cl = 0; cl < 32 && 32 * q + cl < ncomp; ++cl) {
+                            uint32_t v = 0;
+                            if (use) v = ld_cg_u32((st == TS_INC ? a.tile_inc : a.tile_agg) + (size_t)q_tile * ncomp + 32 * q + cl);
+                            v = __reduce_add_sync(FULL, v);
+                            if (cl == lane) exc[q] += v;
+                        }
+                        if (SINGLE_KEY && q == 0) break;
+                    }
+                    if (incm) break;
+                    p -= 32;
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int comp = lane + 32 * q;
+                    if (comp < ncomp) a.tile_inc[(size_t)tile * ncomp + comp] = exc[q] + agg[q];
+                    if (SINGLE_KEY && q == 0) break;
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_release_u32(a.tile_status + tile, (a.epoch << 2) | TS_INC);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int comp = lane + 32 * q;
+                if (comp < ncomp) {
+                    s_base[comp] = exc[q];
+                    if (tile == ntiles - 1) a.carry[comp] = exc[q] + agg[q];   // prefix for the next push
+                }
+                if (SINGLE_KEY && q == 0) break;
+            }
+            if (lane == 0 && exc[0] + agg[0] > a.cap) atomicOr(a.err, K1_ERR_OVERFLOW);
         }
         __syncthreads();                                                     // S2
-        // ---------------- phase 2: ranks from ballots, write the anomalous reads --------------------
-        {
-            const uint32_t out0 = s_seg + s_woff[warp];
-            uint32_t arun = 0;            // anomalous reads of this unit before the current iteration
-            uint32_t prun = 0;            // SINGLE_KEY: kept proper pairs before the current iteration
-            if (!SINGLE_KEY) { for (int k = lane; k < a.nkey; k += 32) s_run[warp][k] = 0; __syncwarp(); }
-            const unsigned lt = lanemask_lt();
-#pragma unroll
-            for (int it = 0; it < K1_ITERS; ++it) {
+        // ---------------- phase 2: full classification of the flagged records (~1-3 %) ----------------
+        // hmask (pass-1 histogram) is a superset of amask (anomalous reads to write out)
+        if (hmask) {
+            const uint32_t out0 = s_base[0] + s_woff[warp];                  // rank of the span's first anomalous read
+            uint32_t m = hmask;
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int it = bit >> 2, j = bit & 3;
+                const uint64_t i = span + (uint64_t)it * 128 + (uint64_t)lane * 4 + j;
+                const uint32_t ri = min((uint32_t)a.c.rgid[i], (uint32_t)a.nrg);
+                const RgDev L = RG_SMEM ? s_rg[ri] : a.rgtab[ri];
+                const uint32_t mq = a.c.mapq[i];
+                const int32_t pos = a.c.pos[i], tid = a.c.tid[i], isz = a.c.isize[i];
+                const uint32_t cr = classify_record(pos, a.c.mpos[i], tid, a.c.mtid[i], isz, a.c.flag[i], mq, L.upper, L.lower, L.min_mapq, a.co);
+                const uint32_t hf = (cr >> CR_HIST_SHIFT) & 0xFu;
+                if (hf) atomicAdd(&s_hist[(L.info & RGI_LIB_MASK) * BDK_NUM_FLAGS + hf], 1u);
+                if (!((amask >> bit) & 1u)) continue;
                 const uint32_t a4 = (amask >> (4 * it)) & 0xFu, p4 = (pmask >> (4 * it)) & 0xFu;
-                unsigned ab[4], pb[4];
-                uint32_t abefore = 0, atotal = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ab[j] = __ballot_sync(FULL, (a4 >> j) & 1u);
-                    abefore += __popc(ab[j] & lt);
-                    atotal += __popc(ab[j]);
-                }
+                const uint32_t below = (2u << j) - 1u;                       // items 0..j of the iteration
+                const uint32_t o = out0 + bytes_before(atot, it) + byte_of(aex, it) + __popc(a4 & (below >> 1));
+                if (o >= a.cap) continue;
+                bdk_aread rec;
+                rec.pos = pos; rec.tid = tid; rec.qlen = a.c.qlen[i];
+                rec.abs_isize = isz < 0 ? -isz : isz;
+                rec.meta = make_meta(cr, (int)(L.info & RGI_LIB_MASK), mq);
+                rec.record = a.base_index + (uint32_t)i;
+                rec.qid = a.c.qid[i];
+                int4* dst = reinterpret_cast<int4*>(a.ar + o);
+                const int4* src = reinterpret_cast<const int4*>(&rec);
+                dst[0] = src[0]; dst[1] = src[1];
                 if (SINGLE_KEY) {
-                    uint32_t pbefore = 0, ptotal = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        pb[j] = __ballot_sync(FULL, (p4 >> j) & 1u);
-                        pbefore += __popc(pb[j] & lt);
-                        ptotal += __popc(pb[j]);
-                    }
-                    if (a4) {
-                        uint32_t rank = abefore, pin = prun + pbefore;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            pin += (p4 >> j) & 1u;                       // inclusive of the read itself
-                            if ((a4 >> j) & 1u) {
-                                const uint32_t o = out0 + arun + rank++;
-                                if (o < a.stage_cap) {
-                                    const uint64_t i = span + (uint64_t)it * 128 + (uint64_t)lane * 4 + j;
-                                    const uint32_t rg = a.c.rgid[i];
-                                    const uint32_t info = __ldg(a.rg_info + rg);
-                                    const uint32_t fl = a.c.flag[i];
-                                    const int32_t isz = a.c.isize[i];
-                                    bdk_aread rec;
-                                    rec.pos = a.c.pos[i]; rec.tid = a.c.tid[i]; rec.qlen = a.c.qlen[i];
-                                    rec.abs_isize = isz < 0 ? -isz : isz;
-                                    const uint32_t fnib = (uint32_t)(flags4 >> (4 * (it * 4 + j))) & 0xFu;
-                                    rec.meta = fnib | ((fl & 0x10u) ? 16u : 0u) | ((info & 0xffu) << 8) | ((uint32_t)a.c.mapq[i] << 16);
-                                    rec.record = a.base_index + (uint32_t)i;
-                                    rec.qid = a.c.qid[i];
-                                    int4* dst = reinterpret_cast<int4*>(a.stage + o);
-                                    const int4* src = reinterpret_cast<const int4*>(&rec);
-                                    dst[0] = src[0]; dst[1] = src[1];
-                                    a.stage_p[o] = pin;
-                                }
-                            }
-                        }
-                    }
-                    prun += ptotal;
+                    a.P[o] = s_base[1] + s_woff[K1_WARPS + warp] + bytes_before(ptot, it) + byte_of(pex, it) + __popc(p4 & below);
                 } else {
-                    // general case: one round of ballots per key present in this iteration
-                    unsigned long long present = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if ((p4 >> j) & 1u) present |= 1ull << ((keys[it] >> (8 * j)) & 0xffu);
-                    present |= __shfl_xor_sync(FULL, present, 16); present |= __shfl_xor_sync(FULL, present, 8);
-                    present |= __shfl_xor_sync(FULL, present, 4); present |= __shfl_xor_sync(FULL, present, 2);
-                    present |= __shfl_xor_sync(FULL, present, 1);
-                    const uint32_t obase = out0 + arun + abefore;
                     for (int k = 0; k < a.nkey; ++k) {
-                        uint32_t pbefore = 0, ptotal = 0;
-                        uint32_t mine = 0;
-                        if ((present >> k) & 1ull) {
+                        uint32_t v = s_base[1 + k] + s_woff[(1 + k) * K1_WARPS + warp];
+                        const uint32_t pt = s_pt[k * K1_WARPS + warp];
+                        if (pt) {                                            // key k occurs in this warp's span
+                            uint32_t mine = 0;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const bool m = ((p4 >> j) & 1u) && ((keys[it] >> (8 * j)) & 0xffu) == (uint32_t)k;
-                                const unsigned b = __ballot_sync(FULL, m);
-                                pbefore += __popc(b & lt); ptotal += __popc(b);
-                                mine |= (uint32_t)m << j;
-                            }
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (((p4 & below) >> jj) & 1u) mine += ((keys[it] >> (8 * jj)) & 0x3fu) == (uint32_t)k;
+                            v += bytes_before(pt, it) + byte_of(s_px[k * K1_THREADS + threadIdx.x], it) + mine;
                         }
-                        const uint32_t base = s_run[warp][k];
-                        if (a4) {
-                            uint32_t rank = 0, pin = base + pbefore;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                pin += (mine >> j) & 1u;
-                                if ((a4 >> j) & 1u) {
-                                    const uint32_t o = obase + rank++;
-                                    if (o < a.stage_cap) a.stage_p[(size_t)o * a.nkey + k] = pin;
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0 && ptotal) s_run[warp][k] = base + ptotal;
-                        __syncwarp();
-                    }
-                    if (a4) {
-                        uint32_t rank = abefore;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if ((a4 >> j) & 1u) {
-                                const uint32_t o = out0 + arun + rank++;
-                                if (o < a.stage_cap) {
-                                    const uint64_t i = span + (uint64_t)it * 128 + (uint64_t)lane * 4 + j;
-                                    const uint32_t rg = a.c.rgid[i];
-                                    const uint32_t info = __ldg(a.rg_info + rg);
-                                    const uint32_t fl = a.c.flag[i];
-                                    const int32_t isz = a.c.isize[i];
-                                    bdk_aread rec;
-                                    rec.pos = a.c.pos[i]; rec.tid = a.c.tid[i]; rec.qlen = a.c.qlen[i];
-                                    rec.abs_isize = isz < 0 ? -isz : isz;
-                                    const uint32_t fnib = (uint32_t)(flags4 >> (4 * (it * 4 + j))) & 0xFu;
-                                    rec.meta = fnib | ((fl & 0x10u) ? 16u : 0u) | ((info & 0xffu) << 8) | ((uint32_t)a.c.mapq[i] << 16);
-                                    rec.record = a.base_index + (uint32_t)i;
-                                    rec.qid = a.c.qid[i];
-                                    int4* dst = reinterpret_cast<int4*>(a.stage + o);
-                                    const int4* src = reinterpret_cast<const int4*>(&rec);
-                                    dst[0] = src[0]; dst[1] = src[1];
-                                }
-                            }
-                        }
+                        a.P[(size_t)o * a.nkey + k] = v;
                     }
                 }
-                arun += atotal;
             }
-            // unit table: anomalous and per-key proper-pair totals of this warp's 512 records
-            const uint64_t unit = a.unit_base + tile * K1_WARPS + warp;
-            if (lane == 0) a.unit_cnt[unit] = arun;
-            if (SINGLE_KEY) { if (lane == 0) a.unit_p[unit] = prun; }
-            else { __syncwarp(); for (int k = lane; k < a.nkey; k += 32) a.unit_p[unit * a.nkey + k] = s_run[warp][k]; }
         }
+        // no barrier here: s_woff / s_base are rewritten by warp 0 only after S1 of the next tile, which every
+        // warp reaches after its phase 2; s_pt / s_px rows are rewritten by the warp that alone reads them in phase 2.
     }
-    // ---------------- CTA epilogue: flush the shared accumulators -----------------------------------
+    // ---------------- CTA epilogue: flush the accumulators ---------------------------------------------
+    if (__any_sync(FULL, (bad & RGI_INVALID) != 0) && lane == 0) atomicOr(a.err, K1_ERR_RG);
+    if (a.ncnt == 1) {
+        spcnt = __reduce_add_sync(FULL, spcnt);
+        if (lane == 0 && spcnt) atomicAdd(a.rg_sproper + a.cnt_rg[0], (unsigned long long)spcnt);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < nhist; i += K1_THREADS) if (s_hist[i]) atomicAdd(a.hist + i, s_hist[i]);
-    for (int i = threadIdx.x; i < a.nrg_smem; i += K1_THREADS) if (s_rg[i]) atomicAdd(a.rg_sproper + i, (unsigned long long)s_rg[i]);
-    if (threadIdx.x == 0 && (uint32_t)s_cur_tid < (uint32_t)a.ntid) {
-        unsigned long long h = s_rhas;
-        for (int b = 0; b < a.nbam; ++b)
-            if ((h >> b) & 1ull) {
-                atomicMin(a.first + (size_t)b * a.ntid + s_cur_tid, s_rfirst[b]);
-                atomicMax(a.last + (size_t)b * a.ntid + s_cur_tid, s_rlast[b]);
-            }
-    }
-}
-
-// ---- exclusive scan of the unit table (one CTA; the table is a few hundred KB) -----------------
-// cnt_off[u] = sum of unit_cnt[0..u), p_off[u][k] = sum of unit_p[0..u)[k]; totals[0] = A.
-constexpr int SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(SCAN_THREADS, 1) k1_scan_units_kernel(const uint32_t* __restrict__ unit_cnt,
-        const uint32_t* __restrict__ unit_p, uint64_t nunits, int nkey, uint32_t* __restrict__ cnt_off,
-        uint32_t* __restrict__ p_off, uint32_t* __restrict__ totals) {
-    __shared__ uint32_t s_part[SCAN_THREADS];
-    const int t = threadIdx.x;
-    const uint64_t per = div_up<uint64_t>(nunits, SCAN_THREADS);
-    const uint64_t lo = min(nunits, per * t), hi = min(nunits, lo + per);
-    for (int q = 0; q <= nkey; ++q) {            // q == 0: anomalous counts, q >= 1: key q - 1
-        const uint32_t* src = q == 0 ? unit_cnt : unit_p + (q - 1);
-        const int stride = q == 0 ? 1 : nkey;
-        uint32_t* dst = q == 0 ? cnt_off : p_off + (q - 1);
+    for (int col = warp; col < ncol; col += K1_WARPS) {
         uint32_t s = 0;
-        for (uint64_t u = lo; u < hi; ++u) s += src[u * stride];
-        s_part[t] = s;
-        __syncthreads();
-        for (int d = 1; d < SCAN_THREADS; d <<= 1) {   // Hillis-Steele inclusive scan of the partials
-            uint32_t v = t >= d ? s_part[t - d] : 0;
-            __syncthreads();
-            s_part[t] += v;
-            __syncthreads();
-        }
-        uint32_t run = s_part[t] - s;
-        for (uint64_t u = lo; u < hi; ++u) { uint32_t v = src[u * stride]; dst[u * stride] = run; run += v; }
-        if (q == 0 && t == SCAN_THREADS - 1) totals[0] = s_part[t];
-        __syncthreads();
+        for (int t = lane; t < K1_THREADS; t += 32) s += s_cnt[col * K1_THREADS + t];
+        s = __reduce_add_sync(FULL, s);
+        if (lane == 0 && s) atomicAdd(a.rg_sproper + a.cnt_rg[col], (unsigned long long)s);
     }
 }
 
-// ---- bring the staged reads into stream order and make the proper-pair counts global -----------
-// Final position d of a staged read: cnt_off[unit] + rank inside the unit; the units of a tile are
-// contiguous in the tile's staging segment.
-__global__ void __launch_bounds__(256) k1_reorder_kernel(const bdk_aread* __restrict__ stage, const uint32_t* __restrict__ stage_p,
-        const uint32_t* __restrict__ cnt_off, const uint32_t* __restrict__ p_off, const uint32_t* __restrict__ tile_seg,
-        uint64_t nunits, const uint32_t* __restrict__ totals, int nkey, bdk_aread* __restrict__ ar, uint32_t* __restrict__ P) {
-    const uint32_t A = totals[0];
-    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < A; d += gridDim.x * blockDim.x) {
-        uint64_t lo = 0, hi = nunits;            // last unit with cnt_off[u] <= d
-        while (hi - lo > 1) { uint64_t m = (lo + hi) >> 1; if (cnt_off[m] <= d) lo = m; else hi = m; }
-        const uint64_t u = lo, tile = u / K1_WARPS;
-        const uint32_t src = tile_seg[tile] + (d - cnt_off[tile * K1_WARPS]);
-        const int4* s = reinterpret_cast<const int4*>(stage + src);
-        int4* o = reinterpret_cast<int4*>(ar + d);
-        o[0] = s[0]; o[1] = s[1];
-        for (int k = 0; k < nkey; ++k) P[(size_t)k * A + d] = stage_p[(size_t)src * nkey + k] + p_off[u * nkey + k];
+// ---- first / last record of every (bam, chromosome) of one push -----------------------------------
+// BamSummary::_analyze_bam's ref_len (BamSummary.cpp:70-74) telescopes to last - first position per
+// (bam, tid). The stream is sorted by tid, so chromosome t occupies the run [lower_bound(t),
+// lower_bound(t + 1)); one warp per (bam, t) finds the run by 32-ary search and then the first and
+// the last record of the run that came from that bam (immediately, unless the bam is sparse there:
+// then it skips 4096-record tiles using the per-tile bam masks K1 wrote).
+__device__ __forceinline__ uint64_t warp_lower_bound_tid(const int32_t* __restrict__ tid, uint64_t n, int32_t t, int lane) {
+    uint64_t lo = 0, hi = n;   // answer in [lo, hi]
+    while (hi - lo > 0) {
+        const uint64_t len = hi - lo;
+        const uint64_t step = div_up<uint64_t>(len, 33);
+        const uint64_t probe = lo + step * (lane + 1) - 1;          // 32 probes splitting the range into 33 parts
+        const bool lt = probe < hi ? tid[probe] < t : false;
+        const unsigned m = __ballot_sync(0xffffffffu, lt);          // monotone: a prefix of lanes
+        const int c = __popc(m);
+        const uint64_t nlo = c ? lo + step * c : lo;                // probes below are < t -> answer after the last of them
+        const uint64_t nhi = c < 32 ? min(hi, lo + step * (c + 1) - 1) : hi;
+        lo = nlo; hi = nhi;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) k1_span_kernel(const int32_t* __restrict__ tid, const int32_t* __restrict__ pos, const uint16_t* __restrict__ rgid,
+        uint64_t n, uint32_t base_index, const RgDev* __restrict__ rgtab, int32_t nrg, int32_t nbam, int32_t ntid,
+        const unsigned long long* __restrict__ tile_bams, unsigned long long* __restrict__ first, unsigned long long* __restrict__ last) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = lane_id();
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (n == 0) return;
+    const int32_t t_lo = max(tid[0], 0), t_hi = min(tid[n - 1], ntid - 1);
+    const int64_t nitems = (int64_t)(t_hi - t_lo + 1) * nbam;
+    for (int64_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += nwarps) {
+        const int32_t t = t_lo + (int32_t)(item / nbam);
+        const uint32_t b = (uint32_t)(item % nbam);
+        const uint64_t s = warp_lower_bound_tid(tid, n, t, lane), e = warp_lower_bound_tid(tid, n, t + 1, lane);
+        if (s >= e) continue;
+        auto from_bam = [&](uint64_t i) -> bool {
+            const uint32_t rg = rgid[i];
+            return rg < (uint32_t)nrg && ((rgtab[rg].info >> RGI_BAM_SHIFT) & 0x3fu) == b;
+        };
+        // forward
+        uint64_t i0 = s, f = 0; bool found = false;
+        while (i0 < e) {
+            if (nbam > 1 && !((tile_bams[i0 / K1_TILE] >> b) & 1ull)) { i0 = (i0 / K1_TILE + 1) * K1_TILE; continue; }
+            const uint64_t i = i0 + lane;
+            const unsigned m = __ballot_sync(FULL, i < e && from_bam(i));
+            if (m) { f = i0 + (__ffs(m) - 1); found = true; break; }
+            i0 += 32;
+        }
+        if (!found) continue;
+        // backward (stops at f at the latest)
+        uint64_t l = f, i1 = e;
+        while (i1 > f + 1) {
+            if (nbam > 1 && !((tile_bams[(i1 - 1) / K1_TILE] >> b) & 1ull)) { i1 = (i1 - 1) / K1_TILE * K1_TILE; continue; }
+            const int64_t i = (int64_t)i1 - 1 - lane;
+            const unsigned m = __ballot_sync(FULL, i > (int64_t)f && from_bam((uint64_t)i));
+            if (m) { l = i1 - 1 - (__ffs(m) - 1); break; }
+            i1 = i1 > 32 ? i1 - 32 : 0;
+        }
+        if (lane == 0) {
+            const unsigned long long kf = ((unsigned long long)(base_index + (uint32_t)f) << 32) | (uint32_t)pos[f];
+            const unsigned long long kl = ((unsigned long long)(base_index + (uint32_t)l) << 32) | (uint32_t)pos[l];
+            atomicMin(first + (size_t)b * ntid + t, kf);
+            atomicMax(last + (size_t)b * ntid + t, kl);
+        }
     }
 }
 

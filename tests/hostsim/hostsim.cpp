@@ -143,7 +143,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
 
     // ---- K4 -----------------------------------------------------------------------------------
     std::vector<uint32_t> Pflat((size_t)nkey * std::max<int64_t>(A, 1));
-    for (int k = 0; k < nkey; ++k) std::copy(P[k].begin(), P[k].end(), Pflat.begin() + (size_t)k * A);
+    for (int k = 0; k < nkey; ++k) for (int64_t d = 0; d < A; ++d) Pflat[(size_t)d * nkey + k] = P[k][d];   // [A][nkey] like the device
     std::vector<uint8_t> freed(A, 0), deleted(nreg, 0), row_emit(nrow_cap + 1, 0);
     std::vector<int32_t> sv_of_read(A, -1), row_lib_count((size_t)(nrow_cap + 1) * nlib), row_lib_span((size_t)(nrow_cap + 1) * nlib);
     std::vector<uint32_t> row_cn_count((size_t)(nrow_cap + 1) * nkey);
@@ -223,4 +223,33 @@ extern "C" uint32_t hostsim_classify(int32_t pos, int32_t mpos, int32_t tid, int
     LibDev L{upper, lower, min_mapq, 0};
     ClassifyOpts o{max_sd, transchr, long_insert};
     return classify_record(pos, mpos, tid, mtid, isize, flag, bdqual, L, o);
+}
+
+// Exhaustive equivalence of the streaming pass's classify_hot() with classify_record() over every
+// flag word, tid/pos/isize relation, mapq relation and option combination. Returns the number of
+// mismatches (0 expected) and the number of cases through *ncases.
+extern "C" long hostsim_classify_hot_check(long* ncases) {
+    long bad = 0, n = 0;
+    const float upper = 400.5f, lower = 200.25f;
+    const int32_t isz[] = {0, 1, 100, 200, 201, 300, 400, 401, -1, -200, -201, -400, -401, 999, 1000, 1001, -1001, 2147483647, -2147483647};
+    const int32_t posp[][2] = {{100, 500}, {500, 100}, {100, 100}, {0, 0}, {-1, 5}};
+    const int32_t tidp[][2] = {{1, 1}, {1, 2}, {0, 0}, {3, -1}};
+    for (int long_insert = 0; long_insert < 2; ++long_insert)
+        for (int transchr = 0; transchr < 2; ++transchr)
+            for (int max_sd : {1000, 1000000000, 0})
+                for (uint32_t flag = 0; flag < 0x1000; ++flag)
+                    for (auto& tp : tidp)
+                        for (auto& pp : posp)
+                            for (int32_t is : isz)
+                                for (uint32_t mq : {0u, 35u, 36u, 255u}) {
+                                    ClassifyOpts o{max_sd, transchr, long_insert};
+                                    uint32_t cr = classify_record(pp[0], pp[1], tp[0], tp[1], is, flag, mq, upper, lower, 35, o);
+                                    uint32_t ch = classify_hot(pp[0], pp[1], tp[0], tp[1], is, flag, mq, upper, lower, 35, o);
+                                    uint32_t want = ((cr & CR_ANOM) ? CH_ANOM : 0u) | ((cr & CR_MPROPER) ? CH_MPROPER : 0u) |
+                                                    (((cr >> CR_HIST_SHIFT) & 0xFu) ? CH_HIST : 0u) | ((cr & CR_SPROPER) ? CH_SPROPER : 0u);
+                                    ++n;
+                                    if (ch != want) ++bad;
+                                }
+    if (ncases) *ncases = n;
+    return bad;
 }

@@ -42,6 +42,18 @@ def test_all_anomalous_dense_cluster():
         util.assert_result_matches_oracle(ro, rh.table, rh.summary, rh.regions, rh.areads, rh.aread_region, rh.sv_of_read, str(od))
 
 
+def test_classify_hot_equals_classify_record():
+    """The streaming kernel's 4-decision classifier equals the full classifier on every flag word x
+    tid/pos/isize/mapq relation x option combination (about 1.1e8 cases, in C)."""
+    import ctypes as C
+    hs = util.hostsim_lib()
+    hs.hostsim_classify_hot_check.restype = C.c_long
+    hs.hostsim_classify_hot_check.argtypes = [C.POINTER(C.c_long)]
+    n = C.c_long(0)
+    assert hs.hostsim_classify_hot_check(C.byref(n)) == 0
+    assert n.value > 10 ** 7
+
+
 def test_classifier_truth_table():
     """pe_classify truth table (reference TestIlluminaPEReadClassifier.cpp only prints it; asserted here
     against IlluminaPEReadClassifier.cpp:13-101 by enumeration through the oracle's classifier)."""
