@@ -277,6 +277,7 @@ def ours(args):
     esteps = max(1, min(args.steps, 5))
     for _ in range(esteps):
         res = step_host()
+    h2d = ctx.h2d_bytes()
     e1.record()
     barrier()
     e_ms_wall = 1e3 * (time.perf_counter() - w0) / esteps
@@ -315,7 +316,8 @@ def ours(args):
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * BYTES_PER_RECORD, "kernel_ms": k1_ms},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in ktimes.items()},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_ms, "h2d_bytes_per_step": n * HOST_BYTES_PER_RECORD,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_ms, "h2d_bytes_per_step": h2d,
+                    "zero_copy_side_columns": h2d < n * HOST_BYTES_PER_RECORD,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches,
             "clocks": clocks,

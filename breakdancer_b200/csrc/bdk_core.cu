@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -82,6 +83,7 @@ struct bdk_ctx {
     int k1_blocks_per_sm = 0;
     size_t k1_smem = 0;
     uint64_t launches = 0;       // kernels launched since the last bdk_reset
+    uint64_t h2d_bytes = 0;      // bytes the last bdk_push copied host -> device
     // host results
     bdk_summary_t h_summary;
     std::vector<bdk_sv> h_sv;
@@ -442,27 +444,44 @@ int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
     for (int i = 0; i < 10; ++i) if (!src[i] && n) return fail(c, BDK_ERR_ARG, "null column %d", i);
     const uint64_t CH = (uint64_t)K1_TILE * 2048;   // 8 Mi records per chunk (multiple of the tile size)
     const uint64_t chunk_cap = std::min<uint64_t>(CH, div_up<uint64_t>(std::max<uint64_t>(n, 1), K1_TILE) * K1_TILE);
+    // qlen / qid are read only for the anomalous 1-3 % of the records: when the caller's columns are pinned
+    // (mapped) host memory the kernel reads those few values in place instead of copying 12 bytes per record.
+    const void* side_dev[2] = {nullptr, nullptr};
+    bool zero_copy = n > 0 && !getenv("BDK_NO_ZEROCOPY");
+    for (int k = 0; k < 2 && zero_copy; ++k) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src[8 + k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            cudaGetLastError();
+            zero_copy = false;
+        } else side_dev[k] = at.devicePointer;
+    }
+    const int ncopy = zero_copy ? 8 : 10;
     for (int b = 0; b < 2; ++b)
-        for (int k = 0; k < 10; ++k) ENS(c->d_chunk[b][k], chunk_cap * width[k]);
+        for (int k = 0; k < ncopy; ++k) ENS(c->d_chunk[b][k], chunk_cap * width[k]);
+    c->h2d_bytes = 0;
     return push_common(c, n, CH, [&]() -> int {
         // double-buffered: the copy stream fills chunk i+1 while K1 runs on chunk i
         CU(cudaEventRecord(c->ev_done[0], c->stream));
         CU(cudaEventRecord(c->ev_done[1], c->stream));
         tstart(c, T_H2D);   // spans copies + kernels of this push on the compute stream
         uint64_t off = 0; int i = 0;
+        c->h2d_bytes = 0;
         while (off < n) {
             const uint64_t m = std::min<uint64_t>(CH, n - off);
             const int b = i & 1;
             CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
-            for (int k = 0; k < 10; ++k)
+            for (int k = 0; k < ncopy; ++k) {
                 CU(cudaMemcpyAsync(c->d_chunk[b][k].p, (const char*)src[k] + off * width[k], m * width[k], cudaMemcpyHostToDevice, c->copy_stream));
+                c->h2d_bytes += m * width[k];
+            }
             CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
             CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
             bdk_soa d;
             d.pos = c->d_chunk[b][0].as<int32_t>(); d.mpos = c->d_chunk[b][1].as<int32_t>(); d.tid = c->d_chunk[b][2].as<int32_t>();
             d.mtid = c->d_chunk[b][3].as<int32_t>(); d.isize = c->d_chunk[b][4].as<int32_t>(); d.flag = c->d_chunk[b][5].as<uint16_t>();
-            d.mapq = c->d_chunk[b][6].as<uint8_t>(); d.rgid = c->d_chunk[b][7].as<uint16_t>(); d.qlen = c->d_chunk[b][8].as<int32_t>();
-            d.qid = c->d_chunk[b][9].as<uint64_t>();
+            d.mapq = c->d_chunk[b][6].as<uint8_t>(); d.rgid = c->d_chunk[b][7].as<uint16_t>();
+            if (zero_copy) { d.qlen = (const int32_t*)side_dev[0] + off; d.qid = (const uint64_t*)side_dev[1] + off; }
+            else { d.qlen = c->d_chunk[b][8].as<int32_t>(); d.qid = c->d_chunk[b][9].as<uint64_t>(); }
             int rc = launch_k1(c, d, m, (uint32_t)(c->n_records + off), false);
             if (rc) return rc;
             CU(cudaEventRecord(c->ev_done[b], c->stream));
@@ -607,8 +626,8 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     M.row_emit = c->d_row_emit.as<uint8_t>(); M.row_key = c->d_row_key.as<uint64_t>();
     tstart(c, T_K4);
     if (nrow || c->h_cnt[CNT_NDE]) {
-        const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(nreg, 128), (uint64_t)kNumSMs * 8);
-        k4_components_kernel<<<std::max(1u, grid), 128, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
+        const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(nreg, 32 * (K4_THREADS / 32)), (uint64_t)kNumSMs * 16);
+        k4_components_kernel<<<std::max(1u, grid), K4_THREADS, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
                                                                   c->d_de.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt);
     }
     if (nrow || c->h_cnt[CNT_NDE]) c->launches += 1;
@@ -712,6 +731,8 @@ int bdk_kernel_times(bdk_ctx* c, const char** names, float* ms, int* launches, i
 }
 
 uint64_t bdk_kernel_launches(bdk_ctx* c) { return c ? c->launches : 0; }
+
+uint64_t bdk_h2d_bytes(bdk_ctx* c) { return c ? c->h2d_bytes : 0; }
 
 int bdk_set_comm(bdk_ctx* c, void*, int, int) {
     if (!c) return BDK_ERR_ARG;

@@ -310,57 +310,96 @@ BDK_HD bool k4_size2(const K4Static& S, const K4Mut& M, int j, int cF) {
     return true;
 }
 
-BDK_HD bool k4_region_final(const K4Static& S, const K4Mut& M, int v, const WindowInfo& wi) {
+// ---- execution policy of the connection walk --------------------------------------------------
+// The walk over one connected component is sequential (it reproduces build_connection's order), but
+// the loops over the reads of a region are independent per read: a "team" spreads them over its
+// lanes. SoloTeam = one thread (host simulation, tests); WarpTeam = the 32 lanes of a warp (K4).
+// Every lane of a team runs the same control flow on the same values; writes to shared state are
+// done by lane 0 between two sync()s.
+struct SoloTeam {
+    BDK_HD int lane() const { return 0; }
+    BDK_HD int width() const { return 1; }
+    BDK_HD int sum(int v) const { return v; }
+    BDK_HD bool any(bool p) const { return p; }
+    BDK_HD void sync() const {}
+    BDK_HD void add(int32_t* p, int v) const { *p += v; }
+};
+#if defined(__CUDACC__)
+struct WarpTeam {
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    __device__ __forceinline__ int width() const { return 32; }
+    __device__ __forceinline__ int sum(int v) const { return (int)__reduce_add_sync(0xffffffffu, v); }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ void add(int32_t* p, int v) const { atomicAdd(p, v); }
+};
+#endif
+
+template <class Team>
+BDK_HD bool k4_region_final(const Team& T, const K4Static& S, const K4Mut& M, int v, const WindowInfo& wi) {
     if (M.deleted[v] || v == wi.last_region) return false;
     const RegionRec& R = S.reg[v];
-    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) {
+    bool bad = false;
+    for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
         if (!M.alive[j]) continue;
         if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
-        if (!k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF)) return false;
+        if (!k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF)) bad = true;
     }
-    return true;
+    return !T.any(bad);
+}
+
+// read y is the later mate of a pair (x, y) whose both reads are still held by regions s0 / s1
+BDK_HD int k4_pair_of(const K4Static& S, const K4Mut& M, int y, int s0, int s1, int cF) {
+    int x = S.mate[y];
+    if (x < 0 || x >= y) return -1;
+    int rx = S.read_region[x];
+    if ((rx != s0 && rx != s1) || rx < 0) return -1;
+    // x comes earlier in the reference's scan order, so by the time y is looked at x has already been
+    // dropped if its name no longer exists (BreakDancer.cpp:367-375 via SvBuilder's observe loop)
+    if (!M.alive[x] || !k4_exists(S, M, x, cF)) return -1;
+    return x;
 }
 
 // process_sv for snodes = {s0, s1} (s1 < 0: single region). Returns true if a row was emitted
-// into slot `row`.
-BDK_HD bool k4_process_sv(const K4Static& S, K4Mut& M, int s0, int s1, int w, int v0, const WindowInfo& wi, int row) {
+// into slot `row` (valid on lane 0).
+template <class Team>
+BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, int s1, int w, int v0, const WindowInfo& wi, int row) {
     int n = s1 >= 0 ? 2 : 1;
     int sn[2] = {s0, s1};
-    int flag_counts[BDK_NUM_FLAGS];
-    for (int i = 0; i < BDK_NUM_FLAGS; ++i) flag_counts[i] = 0;
-    int num_pairs = 0;
+    T.sync();
     // pass 1: count pairs per flag (flag of the second-seen mate, SvBuilder.cpp:101-118)
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0, c9 = 0, c10 = 0;
     for (int i = 0; i < n; ++i) {
         const RegionRec& R = S.reg[sn[i]];
-        for (int y = R.first_read; y < R.first_read + R.n_reads; ++y) {
+        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width()) {
             if (!M.alive[y] || !k4_exists(S, M, y, wi.cF)) continue;
-            int x = S.mate[y];
-            if (x < 0 || x >= y) continue;
-            int rx = S.read_region[x];
-            if ((rx != s0 && rx != s1) || rx < 0) continue;
-            if (!M.alive[x] || !k4_exists(S, M, x, wi.cF)) continue;
-            ++flag_counts[meta_flag(S.ar[y].meta)];
-            ++num_pairs;
+            if (k4_pair_of(S, M, y, s0, s1, wi.cF) < 0) continue;
+            int f = meta_flag(S.ar[y].meta);
+            c0 += f == 0; c1 += f == 1; c2 += f == 2; c3 += f == 3; c4 += f == 4; c5 += f == 5;
+            c6 += f == 6; c7 += f == 7; c8 += f == 8; c9 += f == 9; c10 += f == 10;
         }
     }
+    int flag_counts[BDK_NUM_FLAGS] = {T.sum(c0), T.sum(c1), T.sum(c2), T.sum(c3), T.sum(c4), T.sum(c5),
+                                      T.sum(c6), T.sum(c7), T.sum(c8), T.sum(c9), T.sum(c10)};
+    int num_pairs = 0;
+    for (int i = 0; i < BDK_NUM_FLAGS; ++i) num_pairs += flag_counts[i];
     int flag = BDK_NA, best = 0;
     for (int i = 0; i < BDK_NUM_FLAGS; ++i)
         if (flag_counts[i] > best) { best = flag_counts[i]; flag = i; }  // first maximum in enum order
     bool early = num_pairs < S.min_read_pair || flag_counts[flag] < S.min_read_pair;
     int32_t* lib_count = M.row_lib_count + (int64_t)row * S.nlib;
     int32_t* lib_span = M.row_lib_span + (int64_t)row * S.nlib;
-    if (!early) for (int l = 0; l < S.nlib; ++l) { lib_count[l] = 0; lib_span[l] = 0; }
-    // pass 2: consume the pairs, drop reads whose name no longer exists
+    if (!early) for (int l = T.lane(); l < S.nlib; l += T.width()) { lib_count[l] = 0; lib_span[l] = 0; }
+    T.sync();
+    // pass 2: consume the pairs, drop reads whose name no longer exists. A read is touched only by its own
+    // lane and by the lane of its (later) mate, and both write the same values, so the lanes do not interfere.
     for (int i = 0; i < n; ++i) {
         const RegionRec& R = S.reg[sn[i]];
-        for (int y = R.first_read; y < R.first_read + R.n_reads; ++y) {
+        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width()) {
             if (!M.alive[y]) continue;
             if (!k4_exists(S, M, y, wi.cF)) { M.alive[y] = 0; continue; }
-            int x = S.mate[y];
-            if (x < 0 || x >= y) continue;
-            int rx = S.read_region[x];
-            if ((rx != s0 && rx != s1) || rx < 0) continue;
-            if (!M.alive[x]) continue;
+            int x = k4_pair_of(S, M, y, s0, s1, wi.cF);
+            if (x < 0) continue;
             // pair (x, y): remove_reads_in_region_if(is_supportive) (BreakDancer.cpp:367-368)
             M.alive[x] = 0; M.alive[y] = 0;
             M.sv_of_read[x] = row; M.sv_of_read[y] = row;
@@ -369,12 +408,14 @@ BDK_HD bool k4_process_sv(const K4Static& S, K4Mut& M, int s0, int s1, int w, in
                 uint32_t my = S.ar[y].meta;
                 if (meta_flag(my) == flag) {
                     int l = meta_lib(my);
-                    ++lib_count[l];
-                    lib_span[l] += S.ar[y].abs_isize;
+                    T.add(lib_count + l, 1);
+                    T.add(lib_span + l, S.ar[y].abs_isize);
                 }
             }
         }
     }
+    T.sync();
+    if (T.lane() != 0) return false;
     M.row_emit[row] = 0;
     if (early) return false;
 
@@ -491,8 +532,14 @@ BDK_HD int de_find_src(const DEdge* e, int lo, int hi, int src) {
 // e[0..ne) (unsorted on entry), a queue scratch of ne + 2 ints, and row slots [row0, ...).
 // Walks the windows in order, doing for each what build_connection does for the part of the
 // graph that belongs to this component. Returns the number of row slots used.
-BDK_HD int k4_component(const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* queue, int row0) {
-    de_sort(e, ne);
+// All lanes of the team follow the same path; lane 0 alone writes the walk's state (edge flags,
+// queue, deleted[]), bracketed by sync() so that every lane reads the same values.
+template <class Team>
+BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* queue, int row0) {
+    const bool lead = T.lane() == 0;
+    T.sync();
+    if (lead) de_sort(e, ne);
+    T.sync();
     int row = row0;
     int i = 0;
     while (i < ne) {
@@ -509,7 +556,10 @@ BDK_HD int k4_component(const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* 
             if (!(e[vi].flags & DE_VERASED)) {
                 // BFS from v; tails live in queue[qa..qb), newtails appended after
                 int qa = 0, qb = 0, qn;
-                queue[qb++] = v;
+                T.sync();
+                if (lead) queue[0] = v;
+                T.sync();
+                qb = 1;
                 while (qa < qb) {
                     qn = qb;
                     for (int t = qa; t < qb; ++t) {
@@ -519,21 +569,31 @@ BDK_HD int k4_component(const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* 
                         if (ts < 0 || (e[ts].flags & DE_VERASED)) continue; // graph.find(tail) == end
                         for (int k = ts; k < j && e[k].src == tail; ++k) {
                             if (e[k].flags & DE_ERASED) continue;
-                            e[k].flags |= DE_ERASED;
                             int s1 = e[k].dst, nlinks = e[k].w;
-                            if (nlinks < S.min_read_pair || M.deleted[s1]) continue;
-                            if (tail != s1) {                               // erase_edge(s1, tail)
+                            const bool go = !(nlinks < S.min_read_pair || M.deleted[s1]);
+                            int rq = -1;
+                            if (go && tail != s1) {                         // erase_edge(s1, tail)
                                 int rs = de_find_src(e, i, j, s1);
                                 if (rs >= 0)
                                     for (int q = rs; q < j && e[q].src == s1; ++q)
-                                        if (e[q].dst == tail) { e[q].flags |= DE_ERASED; break; }
+                                        if (e[q].dst == tail) { rq = q; break; }
                             }
-                            queue[qn++] = s1;                               // newtails.push_back(s1)
+                            T.sync();
+                            if (lead) {
+                                e[k].flags |= DE_ERASED;
+                                if (rq >= 0) e[rq].flags |= DE_ERASED;
+                                if (go) queue[qn] = s1;                     // newtails.push_back(s1)
+                            }
+                            T.sync();
+                            if (!go) continue;
+                            ++qn;
                             int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
-                            k4_process_sv(S, M, a, tail != s1 ? b : -1, w, v, wi, row);
+                            k4_process_sv(T, S, M, a, tail != s1 ? b : -1, w, v, wi, row);
                             ++row;
                         }
-                        e[ts].flags |= DE_VERASED;                          // graph.erase(tail)
+                        T.sync();
+                        if (lead) e[ts].flags |= DE_VERASED;                // graph.erase(tail)
+                        T.sync();
                     }
                     qa = qb; qb = qn;
                 }
@@ -543,7 +603,10 @@ BDK_HD int k4_component(const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* 
         // is_region_final / clear_region over the active nodes, ascending
         for (vi = i; vi < j;) {
             int v = e[vi].src;
-            if (k4_region_final(S, M, v, wi)) M.deleted[v] = 1;
+            const bool fin = k4_region_final(T, S, M, v, wi);
+            T.sync();
+            if (fin && lead) M.deleted[v] = 1;
+            T.sync();
             while (vi < j && e[vi].src == v) ++vi;
         }
         i = j;

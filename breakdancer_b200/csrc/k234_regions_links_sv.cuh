@@ -230,16 +230,30 @@ __global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsi
     }
 }
 
-// ---- K4: one thread walks one connected component ------------------------------------------------
-__global__ void __launch_bounds__(128) k4_components_kernel(K4Static S, K4Mut M, const uint32_t* __restrict__ comp_ne, const uint32_t* __restrict__ de_off,
+// ---- K4: one warp walks one connected component ------------------------------------------------------
+// Components are found 32 regions at a time (a region with edges is the root of its component); the warp
+// then walks them one after the other, its lanes sharing the loops over the reads of the regions involved.
+constexpr int K4_THREADS = 128;
+__global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K4Mut M, const uint32_t* __restrict__ comp_ne, const uint32_t* __restrict__ de_off,
         const uint32_t* __restrict__ row_off, DEdge* __restrict__ de, int32_t* __restrict__ queue, const bdk_summary_t* __restrict__ summary,
         const uint32_t* __restrict__ d_cnt) {
+    const unsigned FULL = 0xffffffffu;
     S.nreg = (int32_t)d_cnt[CNT_NREG]; S.ncand = (int32_t)d_cnt[CNT_NCAND];
     S.covered_ref_len = summary->covered_ref_len;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < (uint32_t)S.nreg; r += gridDim.x * blockDim.x) {
-        const uint32_t ne = comp_ne[r];
-        if (!ne) continue;
-        k4_component(S, M, de + de_off[r], (int)ne, queue + de_off[r] + 2 * (size_t)r, (int)row_off[r]);
+    const WarpTeam T;
+    const uint32_t lane = lane_id();
+    const uint32_t nwarps = gridDim.x * (K4_THREADS / 32), wid = blockIdx.x * (K4_THREADS / 32) + (threadIdx.x >> 5);
+    for (uint32_t base = wid * 32; base < (uint32_t)S.nreg; base += nwarps * 32) {
+        const uint32_t r = base + lane;
+        const uint32_t ne = r < (uint32_t)S.nreg ? comp_ne[r] : 0;
+        unsigned m = __ballot_sync(FULL, ne != 0);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t rr = base + src;
+            const int n = (int)__shfl_sync(FULL, ne, src);
+            k4_component(T, S, M, de + de_off[rr], n, queue + de_off[rr] + 2 * (size_t)rr, (int)row_off[rr]);
+        }
     }
 }
 

@@ -178,7 +178,8 @@ int bdk_set_stream(bdk_ctx* ctx, void* cuda_stream);
 int bdk_reset(bdk_ctx* ctx);
 
 /* Feed n position-sorted records from HOST memory (pinned memory makes the copies asynchronous
- * and overlapped with the classify kernel). Replaces the per-record loops
+ * and overlapped with the classify kernel; pinned qlen / qid columns are not copied at all -- the
+ * kernel reads the few values it needs, those of anomalous reads, in place over PCIe). Replaces the per-record loops
  * BamSummary::_analyze_bam (BamSummary.cpp:69-114) and BreakDancer::run/push_read up to the
  * point where a read is found anomalous (BreakDancer.cpp:139-207). May be called repeatedly. */
 int bdk_push(bdk_ctx* ctx, const bdk_soa* host_cols, uint64_t n);
@@ -206,6 +207,8 @@ int bdk_kernel_times(bdk_ctx* ctx, const char** names, float* ms, int* launches,
 
 /* Number of kernels this context has launched since the last bdk_reset / bdk_create. */
 uint64_t bdk_kernel_launches(bdk_ctx* ctx);
+/* Bytes the last bdk_push copied host -> device with the copy engine. */
+uint64_t bdk_h2d_bytes(bdk_ctx* ctx);
 
 /* Pinned host memory helpers for callers without their own CUDA binding. */
 void* bdk_host_alloc(uint64_t bytes);

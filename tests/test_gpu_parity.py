@@ -79,6 +79,22 @@ def test_gpu_chunked_pushes_and_device_push():
     _check(b, cols, "3 chunks", chunks=3)
     _check(b, cols, "17 chunks", chunks=17)
     _check(b, cols, "device push", device_push=True)
+    _check(b, cols, "pinned host columns, qlen/qid zero-copy", pinned=True)
+
+
+def test_gpu_many_read_groups_and_library_bam_pairs():
+    """More (library, bam) pairs than private counter columns (warp-vote fallback) and more read groups than fit
+    the shared-memory table: same results as the oracle."""
+    libs = [synth.LibSpec(f"lib{i:02d}", f"b{i % 3}.bam", 300 + i, 30, 75, [f"rg{i:02d}_{j}" for j in range(2)]) for i in range(40)]
+    w = synth.generate(util.GENOME3, libs, 120000, seed=11, anomaly_frac=0.05)
+    for od in (dict(), dict(CN_lib=True)):
+        b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+        _check(b, cols, f"40 libraries / 80 read groups {od}")
+    libs = [synth.LibSpec(f"L{i}", "one.bam", 300 + 10 * i, 30, 75, [f"g{i}_{j}" for j in range(600)]) for i in range(2)]
+    w = synth.generate(util.GENOME3, libs, 60000, seed=12, anomaly_frac=0.05)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    assert len(b.rg_lib) > 1023
+    _check(b, cols, "1200 read groups")
 
 
 def test_gpu_single_bam_single_key_path():

@@ -148,11 +148,19 @@ def have_gpu() -> bool:
         return False
 
 
-def run_gpu(bundle: api.ParamBundle, cols: Dict[str, np.ndarray], chunks: Optional[int] = None, device_push: bool = False):
+def run_gpu(bundle: api.ParamBundle, cols: Dict[str, np.ndarray], chunks: Optional[int] = None, device_push: bool = False,
+            pinned: bool = False):
     """Run the CUDA path through the C ABI; returns (table, summary, regions, areads, read_region, support, ctx)."""
     ctx = api.Context(bundle, 0)
     n = len(cols["pos"])
-    if device_push:
+    if pinned:   # pinned host columns: qlen / qid are read in place (zero copy), the rest goes through the copy engine
+        import torch
+        pin = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else (v.view(np.int16) if v.dtype == np.uint16 else v)).pin_memory()
+               for k, v in cols.items()}
+        soa = api.soa_from_pointers({k: t.data_ptr() for k, t in pin.items()})
+        ctx.push_soa(soa, n, device=False)
+        assert n == 0 or ctx.h2d_bytes() == 25 * n, (ctx.h2d_bytes(), n)
+    elif device_push:
         import torch
         dev = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else (v.view(np.int16) if v.dtype == np.uint16 else v)).cuda()
                for k, v in cols.items()}
