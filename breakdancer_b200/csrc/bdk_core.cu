@@ -77,8 +77,9 @@ struct bdk_ctx {
     DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
         d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_links, d_links_tmp,
         d_sort_hist, d_edge_key, d_edge_start, d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
-        d_deleted, d_de, d_queue, d_rows, d_row_lib_count, d_row_lib_span, d_row_cn_count, d_row_cn, d_row_emit, d_row_key,
-        d_pois_l, d_pois_k, d_pois_o;
+        d_deleted, d_de, d_de2, d_queue, d_rowpack, d_pois_l, d_pois_k, d_pois_o;
+    void* h_pack = nullptr;       // pinned host block the row outputs + summary are copied into
+    size_t h_pack_cap = 0;
     bool finished = false, summary_ready = false;
     int k1_blocks_per_sm = 0;
     size_t k1_smem = 0;
@@ -280,8 +281,7 @@ void bdk_destroy(bdk_ctx* c) {
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
         &c->d_edge_key, &c->d_edge_start, &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
-        &c->d_deleted, &c->d_de, &c->d_queue, &c->d_rows, &c->d_row_lib_count, &c->d_row_lib_span, &c->d_row_cn_count, &c->d_row_cn,
-        &c->d_row_emit, &c->d_row_key, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
+        &c->d_deleted, &c->d_de, &c->d_de2, &c->d_queue, &c->d_rowpack, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
@@ -289,6 +289,7 @@ void bdk_destroy(bdk_ctx* c) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
     for (int t = 0; t < T_N; ++t) { if (c->timers[t].e0) cudaEventDestroy(c->timers[t].e0); if (c->timers[t].e1) cudaEventDestroy(c->timers[t].e1); }
+    if (c->h_pack) cudaFreeHost(c->h_pack);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -554,7 +555,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     ENS(c->d_links, L1 * 8); ENS(c->d_links_tmp, L1 * 8); ENS(c->d_edge_key, L1 * 8); ENS(c->d_edge_start, L1 * 4);
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
-    ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
+    ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
     const int dummy = dummy_region_of(c->P);
@@ -606,10 +607,21 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     const uint32_t nrow = c->h_cnt[CNT_NROW], nreg = c->h_cnt[CNT_NREG];
 
     // ---- K4 ----------------------------------------------------------------------------------
+    // all per-row outputs live in one device block so that a single copy brings them to a pinned host block
     const size_t R1 = (size_t)nrow + 1;
-    ENS(c->d_rows, R1 * sizeof(bdk_sv)); ENS(c->d_row_lib_count, R1 * 4 * nlib); ENS(c->d_row_lib_span, R1 * 4 * nlib);
-    ENS(c->d_row_cn_count, R1 * 4 * nkey); ENS(c->d_row_cn, R1 * 4 * nkey); ENS(c->d_row_emit, R1); ENS(c->d_row_key, R1 * 8);
-    CU(cudaMemsetAsync(c->d_row_emit.p, 0, R1, st));
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_rows = 0, o_lc = al(o_rows + R1 * sizeof(bdk_sv)), o_cc = al(o_lc + R1 * 4 * nlib), o_cn = al(o_cc + R1 * 4 * nkey),
+                 o_emit = al(o_cn + R1 * 4 * nkey), o_key = al(o_emit + R1), o_span = al(o_key + R1 * 8), pack_bytes = o_span + R1 * 4 * nlib;
+    ENS(c->d_rowpack, pack_bytes);
+    if (c->h_pack_cap < o_span + sizeof(bdk_summary_t)) {
+        if (c->h_pack) cudaFreeHost(c->h_pack);
+        c->h_pack = nullptr; c->h_pack_cap = 0;
+        const size_t want = (o_span + sizeof(bdk_summary_t)) * 5 / 4 + 4096;
+        CU(cudaHostAlloc(&c->h_pack, want, cudaHostAllocDefault));
+        c->h_pack_cap = want;
+    }
+    char* dp = (char*)c->d_rowpack.p;
+    CU(cudaMemsetAsync(dp + o_emit, 0, R1, st));
     K4Static S;
     S.ar = c->d_ar.as<bdk_aread>(); S.read_region = c->d_read_region.as<int32_t>(); S.read_cand = c->d_read_cand.as<int32_t>();
     S.mate = c->d_mate.as<int32_t>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
@@ -620,15 +632,15 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     S.fisher = c->P.fisher; S.covered_ref_len = 0;
     K4Mut M;
     M.alive = c->d_alive.as<uint8_t>(); M.freed = c->d_freed.as<uint8_t>(); M.deleted = c->d_deleted.as<uint8_t>();
-    M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = c->d_rows.as<bdk_sv>();
-    M.row_lib_count = c->d_row_lib_count.as<int32_t>(); M.row_lib_span = c->d_row_lib_span.as<int32_t>();
-    M.row_cn_count = c->d_row_cn_count.as<uint32_t>(); M.row_cn = c->d_row_cn.as<float>();
-    M.row_emit = c->d_row_emit.as<uint8_t>(); M.row_key = c->d_row_key.as<uint64_t>();
+    M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = (bdk_sv*)(dp + o_rows);
+    M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + o_span);
+    M.row_cn_count = (uint32_t*)(dp + o_cc); M.row_cn = (float*)(dp + o_cn);
+    M.row_emit = (uint8_t*)(dp + o_emit); M.row_key = (uint64_t*)(dp + o_key);
     tstart(c, T_K4);
     if (nrow || c->h_cnt[CNT_NDE]) {
         const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(nreg, 32 * (K4_THREADS / 32)), (uint64_t)kNumSMs * 16);
         k4_components_kernel<<<std::max(1u, grid), K4_THREADS, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
-                                                                  c->d_de.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt);
+                                                                  c->d_de.as<DEdge>(), c->d_de2.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt);
     }
     if (nrow || c->h_cnt[CNT_NDE]) c->launches += 1;
     tstop(c, T_K4);
@@ -636,24 +648,19 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
 
     // ---- results to the host, final order ---------------------------------------------------------
     tstart(c, T_D2H);
-    std::vector<bdk_sv> rows(nrow);
-    std::vector<int32_t> rlc((size_t)nrow * nlib);
-    std::vector<uint32_t> rcc((size_t)nrow * nkey);
-    std::vector<float> rcn((size_t)nrow * nkey);
-    std::vector<uint8_t> remit(nrow);
-    std::vector<uint64_t> rkey(nrow);
-    CU(cudaMemcpyAsync(&c->h_summary, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, st));
-    if (nrow) {
-        CU(cudaMemcpyAsync(rows.data(), c->d_rows.p, (size_t)nrow * sizeof(bdk_sv), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(rlc.data(), c->d_row_lib_count.p, rlc.size() * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(rcc.data(), c->d_row_cn_count.p, rcc.size() * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(rcn.data(), c->d_row_cn.p, rcn.size() * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(remit.data(), c->d_row_emit.p, nrow, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(rkey.data(), c->d_row_key.p, (size_t)nrow * 8, cudaMemcpyDeviceToHost, st));
-    }
+    char* hp = (char*)c->h_pack;
+    if (nrow) CU(cudaMemcpyAsync(hp, dp, o_span, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hp + o_span, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, st));
     tstop(c, T_D2H);
     CU(cudaStreamSynchronize(st));
     tcollect(c);
+    memcpy(&c->h_summary, hp + o_span, sizeof(bdk_summary_t));
+    const bdk_sv* rows = (const bdk_sv*)(hp + o_rows);
+    const int32_t* rlc = (const int32_t*)(hp + o_lc);
+    const uint32_t* rcc = (const uint32_t*)(hp + o_cc);
+    const float* rcn = (const float*)(hp + o_cn);
+    const uint8_t* remit = (const uint8_t*)(hp + o_emit);
+    const uint64_t* rkey = (const uint64_t*)(hp + o_key);
     // the reference prints window by window, BFS by BFS (key), calls of one BFS in slot order
     std::vector<uint32_t> order;
     for (uint32_t r = 0; r < nrow; ++r) if (remit[r]) order.push_back(r);
@@ -663,9 +670,9 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     for (size_t i = 0; i < ns; ++i) {
         const uint32_t r = order[i];
         c->h_sv[i] = rows[r]; c->h_sv[i].order = (int32_t)i;
-        std::copy(rlc.begin() + (size_t)r * nlib, rlc.begin() + (size_t)(r + 1) * nlib, c->h_lib_count.begin() + i * nlib);
-        std::copy(rcc.begin() + (size_t)r * nkey, rcc.begin() + (size_t)(r + 1) * nkey, c->h_cn_count.begin() + i * nkey);
-        std::copy(rcn.begin() + (size_t)r * nkey, rcn.begin() + (size_t)(r + 1) * nkey, c->h_copy_number.begin() + i * nkey);
+        std::copy(rlc + (size_t)r * nlib, rlc + (size_t)(r + 1) * nlib, c->h_lib_count.begin() + i * nlib);
+        std::copy(rcc + (size_t)r * nkey, rcc + (size_t)(r + 1) * nkey, c->h_cn_count.begin() + i * nkey);
+        std::copy(rcn + (size_t)r * nkey, rcn + (size_t)(r + 1) * nkey, c->h_copy_number.begin() + i * nkey);
     }
     // slot -> output order, for bdk_get_support
     c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet

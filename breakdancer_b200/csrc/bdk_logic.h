@@ -534,12 +534,33 @@ BDK_HD int de_find_src(const DEdge* e, int lo, int hi, int src) {
 // graph that belongs to this component. Returns the number of row slots used.
 // All lanes of the team follow the same path; lane 0 alone writes the walk's state (edge flags,
 // queue, deleted[]), bracketed by sync() so that every lane reads the same values.
+// Sort a component's directed edges by (win, src, dst). Up to DE_RANK_SORT_MAX edges: rank sort spread over the
+// team (the keys are unique, so the rank of an edge is its final position) into `scratch`; beyond that the leader
+// heap-sorts in place. Returns the array that holds the sorted edges.
+constexpr int DE_RANK_SORT_MAX = 2048;
 template <class Team>
-BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* queue, int row0) {
+BDK_HD DEdge* de_sort_team(const Team& T, DEdge* e, int ne, DEdge* scratch) {
+    T.sync();
+    if (ne <= 1) return e;
+    if (ne > DE_RANK_SORT_MAX || !scratch) {
+        if (T.lane() == 0) de_sort(e, ne);
+        T.sync();
+        return e;
+    }
+    for (int i = T.lane(); i < ne; i += T.width()) {
+        const DEdge x = e[i];
+        int r = 0;
+        for (int j = 0; j < ne; ++j) r += de_less(e[j], x) ? 1 : 0;
+        scratch[r] = x;
+    }
+    T.sync();
+    return scratch;
+}
+
+template <class Team>
+BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e_in, DEdge* e_scratch, int ne, int32_t* queue, int row0) {
     const bool lead = T.lane() == 0;
-    T.sync();
-    if (lead) de_sort(e, ne);
-    T.sync();
+    DEdge* e = de_sort_team(T, e_in, ne, e_scratch);
     int row = row0;
     int i = 0;
     while (i < ne) {

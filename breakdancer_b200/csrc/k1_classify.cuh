@@ -2,22 +2,26 @@
 //
 // Per record (reference: IlluminaPEReadClassifier::classify, BamSummary::_analyze_bam,
 // BreakDancer::push_read up to the point a read is found anomalous):
-//   * classify against the library's cut-offs                          -> bdk::classify_record
+//   * classify against the library's cut-offs                          -> bdk::classify_hot / classify_record
 //   * pass-1 statistics: proper-pair counts per (library, bam), flag histogram per library
 //   * pass-2 filter; kept proper pairs feed the per-key running counts (nread_ROI / nread_FR),
 //     anomalous reads are compacted IN STREAM ORDER together with their inclusive per-key counts.
 //
-// Layout of the work: a tile is 4096 consecutive records; each of the 8 warps of a CTA owns a
-// contiguous 512-record span and walks it in 4 iterations of 128 records, every lane loading 4
-// consecutive records with 16-byte (int32 columns), 8-byte (u16) and 4-byte (u8) streaming loads
-// -> 100 bytes in flight per lane and iteration, fully coalesced. The per-read-group constants
-// (cut-offs, mapping-quality threshold, library / bam / key ids) are one 16-byte shared-memory
-// load; the pass-1 proper-pair counters are thread-private shared-memory columns (no conflicts,
-// no warp votes). Phase 1 keeps only two 16-bit masks per thread (anomalous, kept-proper).
-// Tiles are handed out by a ticket counter to a persistent grid (a multiple of the 148 SMs) and
-// chained by a decoupled look-back over (anomalous count, kept-proper count per key): every
-// anomalous read gets its final position in the stream-ordered output and its global inclusive
-// proper-pair counts in the same pass -- no staging, no second pass over the records.
+// Shape of the kernel (persistent, two CTAs per SM, warp-specialised):
+//   * producer warp: takes 8192-record tiles from a ticket counter and streams them through a
+//     3-stage shared-memory ring, 1024 records (25 600 B, eight column slices) per stage, with TMA
+//     bulk copies (cp.async.bulk ... mbarrier::complete_tx) -- no registers, ~150 KB in flight per SM;
+//   * 8 consumer warps: wait on a stage's "full" mbarrier, read 4 consecutive records per lane with
+//     conflict-free 16/8/4-byte shared loads, make the four decisions of classify_hot() per record
+//     and keep them as bit masks (32 records per thread and tile); the per-read-group constants are
+//     one 16-byte shared load, the pass-1 proper-pair counters a register (one (library, bam) pair)
+//     or thread-private shared-memory columns; the 1-3 % flagged records are classified in full on
+//     the spot (histogram) and, if anomalous, parked in a thread-private stash slot;
+//   * scan warp: chains the tiles by a decoupled look-back over (anomalous count, kept-proper count
+//     per key), 32 predecessor tiles per step. The consumers do not wait for it: they classify the
+//     next tile first and only then write out the previous tile's anomalous reads at their final,
+//     stream-ordered positions with their global inclusive proper-pair counts.
+// So every record is read from HBM exactly once and nothing but the anomalous reads is written.
 // The covered-reference-length statistic (first / last record of every (bam, chromosome)) needs
 // only the run boundaries of the sorted tid column: k1_span_kernel finds them by search.
 #pragma once
@@ -25,18 +29,25 @@
 
 namespace bdk {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_IPT = 4;                                   // consecutive records per lane per iteration
-constexpr int K1_ITERS = 4;
-constexpr int K1_UNIT = 32 * K1_IPT * K1_ITERS;             // 512 records per warp and tile
-constexpr int K1_TILE = K1_UNIT * K1_WARPS;                 // 4096
+constexpr int K1_CWARPS = 8;                                // consumer warps
+constexpr int K1_CTHREADS = K1_CWARPS * 32;                 // 256
+constexpr int K1_THREADS = K1_CTHREADS + 64;                // + producer warp + scan warp
+constexpr int K1_SUB = 1024;                                // records per ring stage (128 per consumer warp)
+constexpr int K1_SUBS = 8;                                  // stages per look-back tile
+constexpr int K1_TILE = K1_SUB * K1_SUBS;                   // 8192
+constexpr int K1_STAGES = 3;                                // ring depth
+constexpr int K1_STAGE_BYTES = K1_SUB * 25;                 // 25 600
+constexpr int K1_STASH = 32;                                // stash slots per thread and tile (= records per thread)
 constexpr int K1_MAXK = 64;                                 // copy-number keys (bams, or libraries with -a)
 constexpr int K1_MAXB = BDK_MAX_BAMS;
-constexpr int K1_MAXCOMP = K1_MAXK + 1;                     // look-back vector: anomalous count + one per key
 constexpr int K1_PRIV_CNT = 32;                             // (library, bam) pairs counted in private columns
-constexpr int K1_RG_SMEM = 1023;                            // read groups whose constants live in shared memory
+constexpr int K1_RG_SMEM = 255;                             // read groups whose constants live in shared memory
 constexpr uint32_t K1_ERR_RG = 1u, K1_ERR_OVERFLOW = 2u;
+// byte offsets of the column slices inside a ring stage
+constexpr int K1_OFF_POS = 0, K1_OFF_MPOS = 4 * K1_SUB, K1_OFF_TID = 8 * K1_SUB, K1_OFF_MTID = 12 * K1_SUB, K1_OFF_ISZ = 16 * K1_SUB,
+              K1_OFF_FLAG = 20 * K1_SUB, K1_OFF_RG = 22 * K1_SUB, K1_OFF_MAPQ = 24 * K1_SUB;
+// named barriers (0 is __syncthreads)
+constexpr int K1_BAR_A = 1, K1_BAR_B = 3, K1_BAR_C = 5;     // A[2]: totals ready, B[2]: prefix ready, C: consumers only
 
 // Per-read-group constants: the library's cut-offs and the ids the record maps to.
 struct alignas(16) RgDev {
@@ -51,6 +62,8 @@ constexpr int RGI_CNT_SHIFT = 20;                           // bits 20-24 privat
 constexpr uint32_t RGI_CNT_NONE = 31u;
 constexpr uint32_t RGI_INVALID = 0x80000000u;               // read group without a library
 
+struct alignas(16) K1Stash { int32_t pos, tid, abs_isize; uint32_t meta; };
+
 struct K1Args {
     bdk_soa c;                 // device columns of this push (16-byte aligned); qlen / qid may be mapped host memory
     uint64_t n;                // records in this push
@@ -64,6 +77,7 @@ struct K1Args {
     bdk_aread* ar;             // [cap] anomalous reads in stream order
     uint32_t* P;               // [cap][nkey] inclusive kept-proper-pair counts per key at each anomalous read
     uint32_t cap;
+    K1Stash* stash;            // [grid][2][K1_CTHREADS][K1_STASH]
     uint32_t* carry;           // [1 + nkey] anomalous reads / kept proper pairs per key before this push (updated)
     uint32_t* ticket;          // tile ticket counter (zero at launch)
     uint32_t* tile_status;     // [tiles] epoch << 2 | state
@@ -81,19 +95,36 @@ struct K1Rec4 {
     uint32_t flag[4], mapq[4], rg[4];
 };
 
-__device__ __forceinline__ void k1_load4(const bdk_soa& c, uint64_t g, int nv, uint32_t pad_rg, K1Rec4& r) {
+__device__ __forceinline__ void k1_unpack(const int4 a, const int4 b, const int4 d, const int4 e, const int4 f, const uint2 fl, const uint32_t mq,
+                                          const uint2 rg, K1Rec4& r) {
+    r.pos[0] = a.x; r.pos[1] = a.y; r.pos[2] = a.z; r.pos[3] = a.w;
+    r.mpos[0] = b.x; r.mpos[1] = b.y; r.mpos[2] = b.z; r.mpos[3] = b.w;
+    r.tid[0] = d.x; r.tid[1] = d.y; r.tid[2] = d.z; r.tid[3] = d.w;
+    r.mtid[0] = e.x; r.mtid[1] = e.y; r.mtid[2] = e.z; r.mtid[3] = e.w;
+    r.isz[0] = f.x; r.isz[1] = f.y; r.isz[2] = f.z; r.isz[3] = f.w;
+    r.flag[0] = fl.x & 0xffffu; r.flag[1] = fl.x >> 16; r.flag[2] = fl.y & 0xffffu; r.flag[3] = fl.y >> 16;
+    r.mapq[0] = mq & 0xffu; r.mapq[1] = (mq >> 8) & 0xffu; r.mapq[2] = (mq >> 16) & 0xffu; r.mapq[3] = mq >> 24;
+    r.rg[0] = rg.x & 0xffffu; r.rg[1] = rg.x >> 16; r.rg[2] = rg.y & 0xffffu; r.rg[3] = rg.y >> 16;
+}
+
+// 4 consecutive records of this lane from a ring stage
+__device__ __forceinline__ void k1_load4_smem(const unsigned char* st, int idx, K1Rec4& r) {
+    const int4 a = *reinterpret_cast<const int4*>(st + K1_OFF_POS + idx * 4);
+    const int4 b = *reinterpret_cast<const int4*>(st + K1_OFF_MPOS + idx * 4);
+    const int4 d = *reinterpret_cast<const int4*>(st + K1_OFF_TID + idx * 4);
+    const int4 e = *reinterpret_cast<const int4*>(st + K1_OFF_MTID + idx * 4);
+    const int4 f = *reinterpret_cast<const int4*>(st + K1_OFF_ISZ + idx * 4);
+    const uint2 fl = *reinterpret_cast<const uint2*>(st + K1_OFF_FLAG + idx * 2);
+    const uint2 rg = *reinterpret_cast<const uint2*>(st + K1_OFF_RG + idx * 2);
+    const uint32_t mq = *reinterpret_cast<const uint32_t*>(st + K1_OFF_MAPQ + idx);
+    k1_unpack(a, b, d, e, f, fl, mq, rg, r);
+}
+
+// the same straight from global memory, with a ragged end (last, partial stage of a push)
+__device__ __forceinline__ void k1_load4_global(const bdk_soa& c, uint64_t g, int nv, uint32_t pad_rg, K1Rec4& r) {
     if (nv == 4) {
-        int4 a = ld_stream_v4(c.pos + g);   r.pos[0] = a.x; r.pos[1] = a.y; r.pos[2] = a.z; r.pos[3] = a.w;
-        int4 b = ld_stream_v4(c.mpos + g);  r.mpos[0] = b.x; r.mpos[1] = b.y; r.mpos[2] = b.z; r.mpos[3] = b.w;
-        int4 d = ld_stream_v4(c.tid + g);   r.tid[0] = d.x; r.tid[1] = d.y; r.tid[2] = d.z; r.tid[3] = d.w;
-        int4 e = ld_stream_v4(c.mtid + g);  r.mtid[0] = e.x; r.mtid[1] = e.y; r.mtid[2] = e.z; r.mtid[3] = e.w;
-        int4 f = ld_stream_v4(c.isize + g); r.isz[0] = f.x; r.isz[1] = f.y; r.isz[2] = f.z; r.isz[3] = f.w;
-        uint2 fl = ld_stream_v2(c.flag + g);
-        r.flag[0] = fl.x & 0xffffu; r.flag[1] = fl.x >> 16; r.flag[2] = fl.y & 0xffffu; r.flag[3] = fl.y >> 16;
-        uint32_t mq = ld_stream_u32(c.mapq + g);
-        r.mapq[0] = mq & 0xffu; r.mapq[1] = (mq >> 8) & 0xffu; r.mapq[2] = (mq >> 16) & 0xffu; r.mapq[3] = mq >> 24;
-        uint2 rg = ld_stream_v2(c.rgid + g);
-        r.rg[0] = rg.x & 0xffffu; r.rg[1] = rg.x >> 16; r.rg[2] = rg.y & 0xffffu; r.rg[3] = rg.y >> 16;
+        k1_unpack(ld_stream_v4(c.pos + g), ld_stream_v4(c.mpos + g), ld_stream_v4(c.tid + g), ld_stream_v4(c.mtid + g), ld_stream_v4(c.isize + g),
+                  ld_stream_v2(c.flag + g), ld_stream_u32(c.mapq + g), ld_stream_v2(c.rgid + g), r);
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -120,9 +151,8 @@ __device__ __forceinline__ uint32_t nibble_counts(uint32_t m) {
     return (m & 0xFu) | ((m & 0xF0u) << 4) | ((m & 0xF00u) << 8) | ((m & 0xF000u) << 12);
 }
 __device__ __forceinline__ uint32_t byte_sum(uint32_t v) { return __dp4a(v, 0x01010101u, 0u); }
-// sum of the bytes below byte `it`
-__device__ __forceinline__ uint32_t bytes_before(uint32_t v, int it) { return byte_sum(v & ((1u << (8 * it)) - 1u)); }
-__device__ __forceinline__ uint32_t byte_of(uint32_t v, int it) { return (v >> (8 * it)) & 0xffu; }
+// byte `it` (0..7) of the pair (lo, hi)
+__device__ __forceinline__ uint32_t byte_of2(uint32_t lo, uint32_t hi, int it) { return ((it < 4 ? lo : hi) >> (8 * (it & 3))) & 0xffu; }
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -134,159 +164,144 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
     uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
+// ---- mbarrier / TMA bulk copy / named barrier wrappers ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
 enum : uint32_t { TS_AGG = 1u, TS_INC = 2u };
 
-// SINGLE_KEY: one copy-number key (the common single-bam run): its counts live in registers.
-// RG_SMEM: the read-group table fits in shared memory (nrg <= K1_RG_SMEM).
+// dynamic shared memory of k1_classify_kernel (bytes), host and device agree through this one function
+__host__ __device__ inline size_t k1_smem_bytes(int nrg, int nlib, int ncnt, int nkey, bool single_key, bool rg_smem) {
+    const size_t ncomp = 1 + (size_t)nkey, ncol = ncnt > 1 ? ncnt : 0;
+    size_t b = (size_t)K1_STAGES * K1_STAGE_BYTES;
+    b += rg_smem ? (size_t)(nrg + 1) * sizeof(RgDev) : 0;
+    b += ((size_t)nlib * BDK_NUM_FLAGS + ncol * K1_CTHREADS) * 4;
+    b += 2 * ncomp * K1_CWARPS * 8;                       // s_tot [2][ncomp][warps] packed per-stage totals (2 words)
+    b += 2 * ncomp * 64 * 2;                              // s_off [2][ncomp][64] u16
+    b += 2 * ncomp * 4;                                   // s_base [2][ncomp]
+    (void)single_key;
+    return b + 128;
+}
+
+// SINGLE_KEY: one copy-number key (the common single-bam run). RG_SMEM: the read-group table fits in shared memory.
 template <bool SINGLE_KEY, bool RG_SMEM>
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_classify_kernel(const K1Args a) {
-    extern __shared__ int4 s_dyn4[];
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args a) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     const int ncomp = 1 + a.nkey;
     const int nhist = a.nlib * BDK_NUM_FLAGS;
     const int ncol = a.ncnt > 1 ? a.ncnt : 0;                                      // one column: a register does it
-    RgDev* s_rg = reinterpret_cast<RgDev*>(s_dyn4);                                // RG_SMEM: [nrg + 1]
+    unsigned char* s_ring = s_dyn;                                                 // [K1_STAGES][K1_STAGE_BYTES]
+    RgDev* s_rg = reinterpret_cast<RgDev*>(s_ring + K1_STAGES * K1_STAGE_BYTES);   // RG_SMEM: [nrg + 1]
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_rg + (RG_SMEM ? a.nrg + 1 : 0));   // [nlib * 11]
-    uint32_t* s_cnt = s_hist + nhist;                                              // [ncol][K1_THREADS]
-    uint32_t* s_px = s_cnt + ncol * K1_THREADS;                                    // !SINGLE_KEY: [nkey][K1_THREADS]
-    uint32_t* s_pt = s_px + (SINGLE_KEY ? 0 : a.nkey * K1_THREADS);                // !SINGLE_KEY: [nkey][K1_WARPS]
-    uint32_t* s_woff = s_pt + (SINGLE_KEY ? 0 : a.nkey * K1_WARPS);                // [ncomp][K1_WARPS]
-    uint32_t* s_base = s_woff + ncomp * K1_WARPS;                                  // [ncomp]
-    __shared__ uint32_t s_wa[K1_WARPS], s_wp[K1_WARPS];
-    __shared__ unsigned long long s_wb[K1_WARPS];
-    __shared__ uint32_t s_tile[2];
+    uint32_t* s_cnt = s_hist + nhist;                                              // [ncol][K1_CTHREADS]
+    uint2* s_tot = reinterpret_cast<uint2*>(s_cnt + ncol * K1_CTHREADS);           // [2][ncomp][K1_CWARPS] per-stage totals, a byte each
+    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_tot + 2 * ncomp * K1_CWARPS);  // [2][ncomp][64] exclusive offset of (stage, warp) in the tile
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(s_off + 2 * ncomp * 64);        // [2][ncomp] exclusive prefix of the tile
+    __shared__ __align__(8) uint64_t s_full[K1_STAGES], s_empty[K1_STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tile_ring[2];
+    __shared__ unsigned long long s_wb[2][K1_CWARPS];
 
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < nhist + ncol * K1_THREADS; i += K1_THREADS) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < nhist + ncol * K1_CTHREADS; i += K1_THREADS) s_hist[i] = 0;
     if (RG_SMEM) for (int i = threadIdx.x; i < a.nrg + 1; i += K1_THREADS) s_rg[i] = a.rgtab[i];
-    uint32_t* my_cnt = s_cnt + threadIdx.x;                                        // this thread's private counter column
-    uint32_t spcnt = 0;                                                            // ncnt == 1: pass-1 proper pairs seen by this thread
-    uint32_t bad = 0;                                                              // OR of the info words (bit 31: invalid read group)
-    if (threadIdx.x == 0) s_tile[0] = atomicAdd(a.ticket, 1u);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], K1_CWARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], K1_CWARPS + 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-
     const uint32_t ntiles = (uint32_t)div_up<uint64_t>(a.n, K1_TILE);
-    int par = 0;
-    for (;;) {
-        const uint32_t tile = s_tile[par];
-        if (tile >= ntiles) break;
-        if (threadIdx.x == 0) s_tile[par ^ 1] = atomicAdd(a.ticket, 1u);   // read after the next barrier
-        par ^= 1;
-        const uint64_t span = (uint64_t)tile * K1_TILE + (uint64_t)warp * K1_UNIT;   // first record of this warp's span
-        // ---------------- phase 1: four decisions per record, kept as bit masks ------------------------
-        uint32_t amask = 0, pmask = 0, hmask = 0, keys[K1_ITERS] = {0, 0, 0, 0};
-        unsigned long long bams = 0;
-#pragma unroll (SINGLE_KEY ? 1 : K1_ITERS)
-        for (int it = 0; it < K1_ITERS; ++it) {
-            const uint64_t g = span + (uint64_t)it * 128 + (uint64_t)lane * 4;
-            const int nv = g + 4 <= a.n ? 4 : (g < a.n ? (int)(a.n - g) : 0);
-            K1Rec4 r;
-            k1_load4(a.c, g, nv, (uint32_t)a.pad_rg, r);
-            uint32_t kk = 0, a4 = 0, p4 = 0, h4 = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t ri = min(r.rg[j], (uint32_t)a.nrg);
-                RgDev L;
-                if (RG_SMEM) L = s_rg[ri];
-                else { const int4 q = __ldg(reinterpret_cast<const int4*>(a.rgtab) + ri); L.upper = __int_as_float(q.x); L.lower = __int_as_float(q.y); L.min_mapq = q.z; L.info = (uint32_t)q.w; }
-                const uint32_t ch = classify_hot(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
-                                                 L.upper, L.lower, L.min_mapq, a.co);
-                bad |= L.info;
-                if (ch & CH_ANOM) a4 |= 1u << j;
-                if (ch & CH_MPROPER) p4 |= 1u << j;
-                if (ch & CH_HIST) h4 |= 1u << j;
-                if (!SINGLE_KEY) kk |= ((L.info >> RGI_KEY_SHIFT) & 0x3fu) << (8 * j);
-                if (a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
-                // pass-1 proper-pair count per (library, bam)
-                const uint32_t sp = (ch >> 3) & 1u;          // CH_SPROPER
-                if (a.ncnt == 1) spcnt += sp;
-                else if (a.ncnt) atomicAdd(my_cnt + ((L.info >> RGI_CNT_SHIFT) & 31u) * K1_THREADS, sp);   // private column: no conflicts
-                else {                                       // many (library, bam) pairs: one atomic per distinct read group and warp
-                    const unsigned spm = __ballot_sync(FULL, sp && r.rg[j] < (uint32_t)a.nrg);
-                    if ((spm >> lane) & 1u) {
-                        const unsigned peers = __match_any_sync(spm, r.rg[j]);
-                        if (lane == __ffs(peers) - 1) atomicAdd(&a.rg_sproper[r.rg[j]], (unsigned long long)__popc(peers));
-                    }
-                }
+
+    // =============================== producer warp ===================================================
+    if (warp == K1_CWARPS) {
+        if (lane != 0) return;
+        uint32_t g = 0;                                       // ring uses so far
+        for (uint32_t i = 0;; ++i) {
+            const int slot = i & 1;
+            if (i >= 2) mbar_wait(&s_tempty[slot], ((i >> 1) - 1) & 1);
+            const uint32_t tile = atomicAdd(a.ticket, 1u);
+            s_tile_ring[slot] = tile;
+            mbar_arrive(&s_tfull[slot]);
+            if (tile >= ntiles) break;
+            for (int s = 0; s < K1_SUBS; ++s) {
+                const uint64_t rec0 = (uint64_t)tile * K1_TILE + (uint64_t)s * K1_SUB;
+                if (rec0 + K1_SUB > a.n) break;               // ragged stage: the consumers read it straight from global memory
+                const int stage = g % K1_STAGES;
+                const uint32_t use = g / K1_STAGES;
+                if (use) mbar_wait(&s_empty[stage], (use - 1) & 1);
+                unsigned char* st = s_ring + stage * K1_STAGE_BYTES;
+                mbar_arrive_expect_tx(&s_full[stage], K1_STAGE_BYTES);
+                tma_load_1d(st + K1_OFF_POS, a.c.pos + rec0, 4 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_MPOS, a.c.mpos + rec0, 4 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_TID, a.c.tid + rec0, 4 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_MTID, a.c.mtid + rec0, 4 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_ISZ, a.c.isize + rec0, 4 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_FLAG, a.c.flag + rec0, 2 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_RG, a.c.rgid + rec0, 2 * K1_SUB, &s_full[stage]);
+                tma_load_1d(st + K1_OFF_MAPQ, a.c.mapq + rec0, K1_SUB, &s_full[stage]);
+                ++g;
             }
-            amask |= a4 << (4 * it); pmask |= p4 << (4 * it); hmask |= h4 << (4 * it);
-            if (!SINGLE_KEY) keys[it] = kk;
         }
-        // ---------------- warp level: ranks inside the 512-record span -----------------------------
-        const uint32_t ca = nibble_counts(amask);
-        const uint32_t ainc = warp_incl_scan(ca);
-        const uint32_t aex = ainc - ca;                                   // per iteration: anomalous reads in lower lanes
-        const uint32_t atot = __shfl_sync(FULL, ainc, 31);                // per iteration: anomalous reads of the warp
-        uint32_t pex = 0, ptot = 0;
-        if (SINGLE_KEY) {
-            const uint32_t cp = nibble_counts(pmask);
-            const uint32_t pinc = warp_incl_scan(cp);
-            pex = pinc - cp;
-            ptot = __shfl_sync(FULL, pinc, 31);
-            if (lane == 0) { s_wa[warp] = byte_sum(atot); s_wp[warp] = byte_sum(ptot); }
-        } else {
-            if (lane == 0) s_wa[warp] = byte_sum(atot);
-            for (int k = lane; k < a.nkey; k += 32) s_pt[k * K1_WARPS + warp] = 0;
-            unsigned long long present = 0;
-#pragma unroll
-            for (int it = 0; it < K1_ITERS; ++it)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((pmask >> (it * 4 + j)) & 1u) present |= 1ull << ((keys[it] >> (8 * j)) & 0x3fu);
-            present = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)present) |
-                      ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(present >> 32)) << 32);
+        return;
+    }
+
+    // =============================== scan warp =======================================================
+    if (warp == K1_CWARPS + 1) {
+        for (uint32_t i = 0;; ++i) {
+            const int slot = i & 1, tb = i & 1;
+            mbar_wait(&s_tfull[slot], (i >> 1) & 1);
+            const uint32_t tile = s_tile_ring[slot];
             __syncwarp();
-            while (present) {                                             // warp-uniform loop over the keys present
-                const int k = __ffsll((long long)present) - 1;
-                present &= present - 1;
-                uint32_t c = 0;
-#pragma unroll
-                for (int it = 0; it < K1_ITERS; ++it)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (((pmask >> (it * 4 + j)) & 1u) && ((keys[it] >> (8 * j)) & 0x3fu) == (uint32_t)k) c += 1u << (8 * it);
-                const uint32_t inc = warp_incl_scan(c);
-                s_px[k * K1_THREADS + threadIdx.x] = inc - c;
-                if (lane == 31) s_pt[k * K1_WARPS + warp] = inc;
-            }
-        }
-        if (a.nbam > 1) {
-            bams = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)bams) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(bams >> 32)) << 32);
-            if (lane == 0) s_wb[warp] = bams;
-        }
-        __syncthreads();                                                     // S1
-        // ---------------- warp 0: tile totals, look-back --------------------------------------------
-        if (warp == 0) {
+            if (lane == 0) mbar_arrive(&s_tempty[slot]);
+            if (tile >= ntiles) break;
+            named_bar_sync(K1_BAR_A + tb, K1_CTHREADS + 32);                 // the consumers' totals of this tile are in s_tot
             if (a.nbam > 1 && lane == 0) {
                 unsigned long long b = 0;
-                for (int w = 0; w < K1_WARPS; ++w) b |= s_wb[w];
+                for (int w = 0; w < K1_CWARPS; ++w) b |= s_wb[tb][w];
                 a.tile_bams[tile] = b;
             }
-            // lane owns components lane, lane + 32, lane + 64 (component 0: anomalous, 1 + k: key k)
-            uint32_t agg[3] = {0, 0, 0}, exc[3] = {0, 0, 0};
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int comp = lane + 32 * q;
-                if (comp < ncomp) {
-                    uint32_t run = 0;
-                    for (int w = 0; w < K1_WARPS; ++w) {
-                        uint32_t v;
-                        if (comp == 0) v = s_wa[w];
-                        else if (SINGLE_KEY) v = s_wp[w];
-                        else v = byte_sum(s_pt[(comp - 1) * K1_WARPS + w]);
-                        s_woff[comp * K1_WARPS + w] = run;
-                        run += v;
-                    }
-                    agg[q] = run;
-                }
-                if (SINGLE_KEY && q == 0) break;
+            // per component: exclusive offsets of the 64 (stage, warp) cells in stream order, and the tile total
+            uint32_t agg[3] = {0, 0, 0}, exc[3] = {0, 0, 0};                 // lane owns components lane, lane + 32, lane + 64
+            for (int comp = 0; comp < ncomp; ++comp) {
+                const uint2* tot = s_tot + ((size_t)tb * ncomp + comp) * K1_CWARPS;
+                // cell q = stage * 8 + warp; this lane scans cells 2 * lane and 2 * lane + 1
+                const int q0 = 2 * lane, st0 = q0 >> 3, w0 = q0 & 7;
+                const uint2 t0 = tot[w0], t1 = tot[w0 + 1];
+                const uint32_t v0 = byte_of2(t0.x, t0.y, st0), v1 = byte_of2(t1.x, t1.y, st0);
+                const uint32_t inc = warp_incl_scan(v0 + v1);
+                uint16_t* off = s_off + ((size_t)tb * ncomp + comp) * 64;
+                off[q0] = (uint16_t)(inc - v0 - v1); off[q0 + 1] = (uint16_t)(inc - v1);
+                const uint32_t total = __shfl_sync(FULL, inc, 31);
+                if ((comp & 31) == lane) { if (comp < 32) agg[0] = total; else if (comp < 64) agg[1] = total; else agg[2] = total; }
             }
             if (tile == 0) {
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const int comp = lane + 32 * q;
                     if (comp < ncomp) { exc[q] = a.carry[comp]; a.tile_inc[(size_t)tile * ncomp + comp] = exc[q] + agg[q]; }
-                    if (SINGLE_KEY && q == 0) break;
                 }
                 __threadfence();
                 __syncwarp();
@@ -296,7 +311,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_classify_kernel(const K1Args
                 for (int q = 0; q < 3; ++q) {
                     const int comp = lane + 32 * q;
                     if (comp < ncomp) a.tile_agg[(size_t)tile * ncomp + comp] = agg[q];
-                    if (SINGLE_KEY && q == 0) break;
                 }
                 __threadfence();
                 __syncwarp();
@@ -321,7 +335,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_classify_kernel(const K1Args
                             v = __reduce_add_sync(FULL, v);
                             if (cl == lane) exc[q] += v;
                         }
-                        if (SINGLE_KEY && q == 0) break;
                     }
                     if (incm) break;
                     p -= 32;
@@ -330,7 +343,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_classify_kernel(const K1Args
                 for (int q = 0; q < 3; ++q) {
                     const int comp = lane + 32 * q;
                     if (comp < ncomp) a.tile_inc[(size_t)tile * ncomp + comp] = exc[q] + agg[q];
-                    if (SINGLE_KEY && q == 0) break;
                 }
                 __threadfence();
                 __syncwarp();
@@ -340,79 +352,232 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_classify_kernel(const K1Args
             for (int q = 0; q < 3; ++q) {
                 const int comp = lane + 32 * q;
                 if (comp < ncomp) {
-                    s_base[comp] = exc[q];
+                    s_base[tb * ncomp + comp] = exc[q];
                     if (tile == ntiles - 1) a.carry[comp] = exc[q] + agg[q];   // prefix for the next push
                 }
-                if (SINGLE_KEY && q == 0) break;
             }
             if (lane == 0 && exc[0] + agg[0] > a.cap) atomicOr(a.err, K1_ERR_OVERFLOW);
+            __syncwarp();
+            named_bar_arrive(K1_BAR_B + tb, K1_CTHREADS + 32);               // s_off / s_base of this tile are ready
         }
-        __syncthreads();                                                     // S2
-        // ---------------- phase 2: full classification of the flagged records (~1-3 %) ----------------
-        // hmask (pass-1 histogram) is a superset of amask (anomalous reads to write out)
-        if (hmask) {
-            const uint32_t out0 = s_base[0] + s_woff[warp];                  // rank of the span's first anomalous read
-            uint32_t m = hmask;
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int it = bit >> 2, j = bit & 3;
-                const uint64_t i = span + (uint64_t)it * 128 + (uint64_t)lane * 4 + j;
-                const uint32_t ri = min((uint32_t)a.c.rgid[i], (uint32_t)a.nrg);
-                const RgDev L = RG_SMEM ? s_rg[ri] : a.rgtab[ri];
-                const uint32_t mq = a.c.mapq[i];
-                const int32_t pos = a.c.pos[i], tid = a.c.tid[i], isz = a.c.isize[i];
-                const uint32_t cr = classify_record(pos, a.c.mpos[i], tid, a.c.mtid[i], isz, a.c.flag[i], mq, L.upper, L.lower, L.min_mapq, a.co);
-                const uint32_t hf = (cr >> CR_HIST_SHIFT) & 0xFu;
-                if (hf) atomicAdd(&s_hist[(L.info & RGI_LIB_MASK) * BDK_NUM_FLAGS + hf], 1u);
-                if (!((amask >> bit) & 1u)) continue;
-                const uint32_t a4 = (amask >> (4 * it)) & 0xFu, p4 = (pmask >> (4 * it)) & 0xFu;
-                const uint32_t below = (2u << j) - 1u;                       // items 0..j of the iteration
-                const uint32_t o = out0 + bytes_before(atot, it) + byte_of(aex, it) + __popc(a4 & (below >> 1));
-                if (o >= a.cap) continue;
-                bdk_aread rec;
-                rec.pos = pos; rec.tid = tid; rec.qlen = a.c.qlen[i];
-                rec.abs_isize = isz < 0 ? -isz : isz;
-                rec.meta = make_meta(cr, (int)(L.info & RGI_LIB_MASK), mq);
-                rec.record = a.base_index + (uint32_t)i;
-                rec.qid = a.c.qid[i];
-                int4* dst = reinterpret_cast<int4*>(a.ar + o);
-                const int4* src = reinterpret_cast<const int4*>(&rec);
-                dst[0] = src[0]; dst[1] = src[1];
-                if (SINGLE_KEY) {
-                    a.P[o] = s_base[1] + s_woff[K1_WARPS + warp] + bytes_before(ptot, it) + byte_of(pex, it) + __popc(p4 & below);
-                } else {
-                    for (int k = 0; k < a.nkey; ++k) {
-                        uint32_t v = s_base[1 + k] + s_woff[(1 + k) * K1_WARPS + warp];
-                        const uint32_t pt = s_pt[k * K1_WARPS + warp];
-                        if (pt) {                                            // key k occurs in this warp's span
-                            uint32_t mine = 0;
+        return;
+    }
+
+    // =============================== consumer warps ==================================================
+    uint32_t* my_cnt = s_cnt + threadIdx.x;                                        // this thread's private counter column
+    uint32_t spcnt = 0;                                                            // ncnt == 1: pass-1 proper pairs seen by this thread
+    uint32_t bad = 0;                                                              // OR of the info words (bit 31: invalid read group)
+    K1Stash* my_stash = a.stash + ((size_t)blockIdx.x * 2 * K1_CTHREADS + threadIdx.x) * K1_STASH;   // + tb * K1_CTHREADS * K1_STASH
+    uint32_t g = 0;                                                                // ring uses so far (same sequence as the producer)
+    // state of the previous tile, whose anomalous reads are written out after the current tile is classified
+    bool prev_have = false;
+    uint32_t prev_tile = 0, prev_amask = 0, prev_pmask = 0, prev_aex0 = 0, prev_aex1 = 0, prev_pex0 = 0, prev_pex1 = 0;
+    uint32_t prev_keys[K1_SUBS];
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-                                if (((p4 & below) >> jj) & 1u) mine += ((keys[it] >> (8 * jj)) & 0x3fu) == (uint32_t)k;
-                            v += bytes_before(pt, it) + byte_of(s_px[k * K1_THREADS + threadIdx.x], it) + mine;
+    for (int s = 0; s < K1_SUBS; ++s) prev_keys[s] = 0;
+
+    for (uint32_t i = 0;; ++i) {
+        const int slot = i & 1, tb = i & 1;
+        mbar_wait(&s_tfull[slot], (i >> 1) & 1);
+        const uint32_t tile = s_tile_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_tempty[slot]);
+        const bool have = tile < ntiles;
+        uint32_t amask = 0, pmask = 0, aex0 = 0, aex1 = 0, pex0 = 0, pex1 = 0, keys[K1_SUBS];
+#pragma unroll
+        for (int s = 0; s < K1_SUBS; ++s) keys[s] = 0;
+        if (have) {
+            // ---------------- phase 1: four decisions per record, kept as bit masks ----------------------
+            unsigned long long bams = 0;
+            uint32_t nst = 0;                                                  // stash slots used by this thread
+            K1Stash* stash = my_stash + (size_t)tb * K1_CTHREADS * K1_STASH;
+#pragma unroll (SINGLE_KEY ? 1 : K1_SUBS)
+            for (int s = 0; s < K1_SUBS; ++s) {
+                const uint64_t rec0 = (uint64_t)tile * K1_TILE + (uint64_t)s * K1_SUB;
+                if (rec0 >= a.n) break;
+                const int idx = (warp << 7) + (lane << 2);                     // first of this lane's 4 records inside the stage
+                K1Rec4 r;
+                const bool staged = rec0 + K1_SUB <= a.n;
+                int stage = 0;
+                if (staged) {
+                    stage = g % K1_STAGES;
+                    mbar_wait(&s_full[stage], (g / K1_STAGES) & 1);
+                    k1_load4_smem(s_ring + stage * K1_STAGE_BYTES, idx, r);
+                } else {
+                    const uint64_t gi = rec0 + idx;
+                    const int nv = gi + 4 <= a.n ? 4 : (gi < a.n ? (int)(a.n - gi) : 0);
+                    k1_load4_global(a.c, gi, nv, (uint32_t)a.pad_rg, r);
+                }
+                uint32_t kk = 0, a4 = 0, p4 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t ri = min(r.rg[j], (uint32_t)a.nrg);
+                    RgDev L;
+                    if (RG_SMEM) L = s_rg[ri];
+                    else { const int4 q = __ldg(reinterpret_cast<const int4*>(a.rgtab) + ri); L.upper = __int_as_float(q.x); L.lower = __int_as_float(q.y); L.min_mapq = q.z; L.info = (uint32_t)q.w; }
+                    const uint32_t ch = classify_hot(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
+                                                     L.upper, L.lower, L.min_mapq, a.co);
+                    bad |= L.info;
+                    if (ch & CH_ANOM) a4 |= 1u << j;
+                    if (ch & CH_MPROPER) p4 |= 1u << j;
+                    if (!SINGLE_KEY) kk |= ((L.info >> RGI_KEY_SHIFT) & 0x3fu) << (8 * j);
+                    if (a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
+                    // pass-1 proper-pair count per (library, bam)
+                    const uint32_t sp = (ch >> 3) & 1u;          // CH_SPROPER
+                    if (a.ncnt == 1) spcnt += sp;
+                    else if (a.ncnt) atomicAdd(my_cnt + ((L.info >> RGI_CNT_SHIFT) & 31u) * K1_CTHREADS, sp);   // private column: no conflicts
+                    else {                                       // many (library, bam) pairs: one atomic per distinct read group and warp
+                        const unsigned spm = __ballot_sync(FULL, sp && r.rg[j] < (uint32_t)a.nrg);
+                        if ((spm >> lane) & 1u) {
+                            const unsigned peers = __match_any_sync(spm, r.rg[j]);
+                            if (lane == __ffs(peers) - 1) atomicAdd(&a.rg_sproper[r.rg[j]], (unsigned long long)__popc(peers));
                         }
-                        a.P[(size_t)o * a.nkey + k] = v;
+                    }
+                    if (ch & CH_HIST) {                          // ~1-3 % of the records: full classification, histogram, stash
+                        const uint32_t cr = classify_record(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
+                                                            L.upper, L.lower, L.min_mapq, a.co);
+                        const uint32_t hf = (cr >> CR_HIST_SHIFT) & 0xFu;
+                        if (hf) atomicAdd(&s_hist[(L.info & RGI_LIB_MASK) * BDK_NUM_FLAGS + hf], 1u);
+                        if (cr & CR_ANOM) {
+                            K1Stash e;
+                            e.pos = r.pos[j]; e.tid = r.tid[j]; e.abs_isize = r.isz[j] < 0 ? -r.isz[j] : r.isz[j];
+                            e.meta = make_meta(cr, (int)(L.info & RGI_LIB_MASK), r.mapq[j]);
+                            *reinterpret_cast<int4*>(stash + nst) = *reinterpret_cast<const int4*>(&e);
+                            ++nst;
+                        }
+                    }
+                }
+                if (staged) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[stage]);
+                    ++g;
+                }
+                amask |= a4 << (4 * s); pmask |= p4 << (4 * s);
+                if (!SINGLE_KEY) keys[s] = kk;
+            }
+            // ---------------- warp level: ranks inside the warp's 8 x 128 records ------------------------
+            {
+                const uint32_t c0 = nibble_counts(amask & 0xffffu), c1 = nibble_counts(amask >> 16);
+                const uint32_t i0 = warp_incl_scan(c0), i1 = warp_incl_scan(c1);
+                aex0 = i0 - c0; aex1 = i1 - c1;
+                if (lane == 31) s_tot[((size_t)tb * ncomp + 0) * K1_CWARPS + warp] = make_uint2(i0, i1);
+            }
+            if (SINGLE_KEY) {
+                const uint32_t c0 = nibble_counts(pmask & 0xffffu), c1 = nibble_counts(pmask >> 16);
+                const uint32_t i0 = warp_incl_scan(c0), i1 = warp_incl_scan(c1);
+                pex0 = i0 - c0; pex1 = i1 - c1;
+                if (lane == 31) s_tot[((size_t)tb * ncomp + 1) * K1_CWARPS + warp] = make_uint2(i0, i1);
+            } else {
+                for (int k = 0; k < a.nkey; ++k) {                            // per key: per-stage totals of the warp
+                    uint32_t c0 = 0, c1 = 0;
+#pragma unroll
+                    for (int s = 0; s < K1_SUBS; ++s)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (((pmask >> (s * 4 + j)) & 1u) && ((keys[s] >> (8 * j)) & 0x3fu) == (uint32_t)k) { if (s < 4) c0 += 1u << (8 * s); else c1 += 1u << (8 * (s - 4)); }
+                    c0 = __reduce_add_sync(FULL, c0); c1 = __reduce_add_sync(FULL, c1);
+                    if (lane == 0) s_tot[((size_t)tb * ncomp + 1 + k) * K1_CWARPS + warp] = make_uint2(c0, c1);
+                }
+            }
+            if (a.nbam > 1) {
+                bams = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)bams) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(bams >> 32)) << 32);
+                if (lane == 0) s_wb[tb][warp] = bams;
+            }
+            __syncwarp();
+            named_bar_arrive(K1_BAR_A + tb, K1_CTHREADS + 32);               // hand the totals to the scan warp, do not wait
+        }
+        // ---------------- phase 2 of the PREVIOUS tile: write its anomalous reads -------------------------
+        if (prev_have) {
+            const int pb = tb ^ 1;
+            named_bar_sync(K1_BAR_B + pb, K1_CTHREADS + 32);                 // its look-back is done (it had a whole tile of time)
+            if (prev_amask) {
+                const uint32_t base_a = s_base[pb * ncomp];
+                const uint16_t* off_a = s_off + ((size_t)pb * ncomp) * 64;
+                const K1Stash* stash = my_stash + (size_t)pb * K1_CTHREADS * K1_STASH;
+                uint32_t m = prev_amask, k = 0;
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int s = bit >> 2, j = bit & 3;
+                    const uint32_t a4 = (prev_amask >> (4 * s)) & 0xFu, p4 = (prev_pmask >> (4 * s)) & 0xFu;
+                    const uint32_t below = (2u << j) - 1u;                   // items 0..j of the stage
+                    const uint32_t o = base_a + off_a[s * 8 + warp] + byte_of2(prev_aex0, prev_aex1, s) + __popc(a4 & (below >> 1));
+                    const K1Stash e = stash[k++];
+                    if (o >= a.cap) continue;
+                    const uint64_t idx = (uint64_t)prev_tile * K1_TILE + (uint64_t)s * K1_SUB + (warp << 7) + (lane << 2) + j;
+                    bdk_aread rec;
+                    rec.pos = e.pos; rec.tid = e.tid; rec.qlen = a.c.qlen[idx];
+                    rec.abs_isize = e.abs_isize; rec.meta = e.meta;
+                    rec.record = a.base_index + (uint32_t)idx;
+                    rec.qid = a.c.qid[idx];
+                    int4* dst = reinterpret_cast<int4*>(a.ar + o);
+                    const int4* src = reinterpret_cast<const int4*>(&rec);
+                    dst[0] = src[0]; dst[1] = src[1];
+                    if (SINGLE_KEY) {
+                        a.P[o] = s_base[pb * ncomp + 1] + s_off[((size_t)pb * ncomp + 1) * 64 + s * 8 + warp] + byte_of2(prev_pex0, prev_pex1, s) + __popc(p4 & below);
+                    }
+                }
+            }
+            if (!SINGLE_KEY) {
+                // per key: proper pairs of lower lanes in the same stage come from warp votes (all lanes take part)
+                const uint32_t base_a = s_base[pb * ncomp];
+                const uint16_t* off_a = s_off + ((size_t)pb * ncomp) * 64;
+                const unsigned lt = lanemask_lt();
+#pragma unroll
+                for (int s = 0; s < K1_SUBS; ++s) {
+                    const uint32_t a4 = (prev_amask >> (4 * s)) & 0xFu, p4 = (prev_pmask >> (4 * s)) & 0xFu;
+                    if (!__any_sync(FULL, a4 != 0)) continue;
+                    unsigned long long present = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if ((p4 >> j) & 1u) present |= 1ull << ((prev_keys[s] >> (8 * j)) & 0x3fu);
+                    present = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)present) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(present >> 32)) << 32);
+                    const uint32_t o0 = base_a + off_a[s * 8 + warp] + byte_of2(prev_aex0, prev_aex1, s);
+                    for (int k = 0; k < a.nkey; ++k) {
+                        uint32_t before = 0, mine = 0;
+                        if ((present >> k) & 1ull) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const bool mk = ((p4 >> j) & 1u) && ((prev_keys[s] >> (8 * j)) & 0x3fu) == (uint32_t)k;
+                                before += __popc(__ballot_sync(FULL, mk) & lt);
+                                mine |= (uint32_t)mk << j;
+                            }
+                        }
+                        if (a4) {
+                            const uint32_t v0 = s_base[pb * ncomp + 1 + k] + s_off[((size_t)pb * ncomp + 1 + k) * 64 + s * 8 + warp] + before;
+                            uint32_t rank = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if ((a4 >> j) & 1u) {
+                                    const uint32_t o = o0 + rank++;
+                                    if (o < a.cap) a.P[(size_t)o * a.nkey + k] = v0 + __popc(mine & ((2u << j) - 1u));
+                                }
+                            }
+                        }
                     }
                 }
             }
         }
-        // no barrier here: s_woff / s_base are rewritten by warp 0 only after S1 of the next tile, which every
-        // warp reaches after its phase 2; s_pt / s_px rows are rewritten by the warp that alone reads them in phase 2.
+        if (!have) break;
+        prev_have = true; prev_tile = tile; prev_amask = amask; prev_pmask = pmask;
+        prev_aex0 = aex0; prev_aex1 = aex1; prev_pex0 = pex0; prev_pex1 = pex1;
+        if (!SINGLE_KEY) {
+#pragma unroll
+            for (int s = 0; s < K1_SUBS; ++s) prev_keys[s] = keys[s];
+        }
     }
-    // ---------------- CTA epilogue: flush the accumulators ---------------------------------------------
+    // ---------------- epilogue of the consumers: flush the accumulators --------------------------------------
     if (__any_sync(FULL, (bad & RGI_INVALID) != 0) && lane == 0) atomicOr(a.err, K1_ERR_RG);
     if (a.ncnt == 1) {
         spcnt = __reduce_add_sync(FULL, spcnt);
         if (lane == 0 && spcnt) atomicAdd(a.rg_sproper + a.cnt_rg[0], (unsigned long long)spcnt);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nhist; i += K1_THREADS) if (s_hist[i]) atomicAdd(a.hist + i, s_hist[i]);
-    for (int col = warp; col < ncol; col += K1_WARPS) {
-        uint32_t s = 0;
-        for (int t = lane; t < K1_THREADS; t += 32) s += s_cnt[col * K1_THREADS + t];
-        s = __reduce_add_sync(FULL, s);
-        if (lane == 0 && s) atomicAdd(a.rg_sproper + a.cnt_rg[col], (unsigned long long)s);
+    named_bar_sync(K1_BAR_C, K1_CTHREADS);
+    for (int i = threadIdx.x; i < nhist; i += K1_CTHREADS) if (s_hist[i]) atomicAdd(a.hist + i, s_hist[i]);
+    for (int col = warp; col < ncol; col += K1_CWARPS) {
+        uint32_t sum = 0;
+        for (int t = lane; t < K1_CTHREADS; t += 32) sum += s_cnt[col * K1_CTHREADS + t];
+        sum = __reduce_add_sync(FULL, sum);
+        if (lane == 0 && sum) atomicAdd(a.rg_sproper + a.cnt_rg[col], (unsigned long long)sum);
     }
 }
 

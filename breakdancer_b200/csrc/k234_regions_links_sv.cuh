@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsi
 // then walks them one after the other, its lanes sharing the loops over the reads of the regions involved.
 constexpr int K4_THREADS = 128;
 __global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K4Mut M, const uint32_t* __restrict__ comp_ne, const uint32_t* __restrict__ de_off,
-        const uint32_t* __restrict__ row_off, DEdge* __restrict__ de, int32_t* __restrict__ queue, const bdk_summary_t* __restrict__ summary,
-        const uint32_t* __restrict__ d_cnt) {
+        const uint32_t* __restrict__ row_off, DEdge* __restrict__ de, DEdge* __restrict__ de_sorted, int32_t* __restrict__ queue,
+        const bdk_summary_t* __restrict__ summary, const uint32_t* __restrict__ d_cnt) {
     const unsigned FULL = 0xffffffffu;
     S.nreg = (int32_t)d_cnt[CNT_NREG]; S.ncand = (int32_t)d_cnt[CNT_NCAND];
     S.covered_ref_len = summary->covered_ref_len;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K
             m &= m - 1;
             const uint32_t rr = base + src;
             const int n = (int)__shfl_sync(FULL, ne, src);
-            k4_component(T, S, M, de + de_off[rr], n, queue + de_off[rr] + 2 * (size_t)rr, (int)row_off[rr]);
+            k4_component(T, S, M, de + de_off[rr], de_sorted + de_off[rr], n, queue + de_off[rr] + 2 * (size_t)rr, (int)row_off[rr]);
         }
     }
 }

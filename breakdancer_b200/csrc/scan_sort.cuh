@@ -107,25 +107,49 @@ __global__ void __launch_bounds__(SS_THREADS) sort_hist_kernel(const unsigned lo
     hist[threadIdx.x * SS_GRID + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan over the digit-major [256][SS_GRID] table, in place (one block)
+// exclusive scan over the digit-major [256][SS_GRID] table, in place (one block of 32 warps).
+// Each warp owns 8 digit rows: coalesced row sums, a 256-entry scan of the row totals, then a
+// warp-scan of every row seeded with its base.
 __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s[1024];
-    const int t = threadIdx.x;
-    constexpr int TOTAL = 256 * SS_GRID;
-    constexpr int PER = (TOTAL + 1023) / 1024;
-    const int lo = min(TOTAL, t * PER), hi = min(TOTAL, lo + PER);
-    uint32_t sum = 0;
-    for (int i = lo; i < hi; ++i) sum += hist[i];
-    s[t] = sum;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t x = t >= d ? s[t - d] : 0;
-        __syncthreads();
-        s[t] += x;
-        __syncthreads();
+    __shared__ uint32_t s_row[256];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int CH = (SS_GRID + 31) / 32;
+    for (int d = warp * 8; d < warp * 8 + 8; ++d) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { const int i = c * 32 + lane; if (i < SS_GRID) s += hist[d * SS_GRID + i]; }
+        s = __reduce_add_sync(FULL, s);
+        if (lane == 0) s_row[d] = s;
     }
-    uint32_t run = s[t] - sum;
-    for (int i = lo; i < hi; ++i) { uint32_t v = hist[i]; hist[i] = run; run += v; }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 256 row totals: 8 per lane
+        uint32_t v[8], t = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = s_row[lane * 8 + k]; t += v[k]; }
+        uint32_t inc = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += x; }
+        uint32_t run = inc - t;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_row[lane * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    for (int d = warp * 8; d < warp * 8 + 8; ++d) {
+        uint32_t v[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { const int i = c * 32 + lane; v[c] = i < SS_GRID ? hist[d * SS_GRID + i] : 0; }
+        uint32_t base = s_row[d];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            uint32_t inc = v[c];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) { uint32_t x = __shfl_up_sync(FULL, inc, k); if (lane >= k) inc += x; }
+            const int i = c * 32 + lane;
+            if (i < SS_GRID) hist[d * SS_GRID + i] = base + inc - v[c];
+            base += __shfl_sync(FULL, inc, 31);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(SS_THREADS) sort_scatter_kernel(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,

@@ -165,7 +165,8 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     for (int r = 0; r < nreg; ++r) {
         if (!comp_ne[r]) continue;
         queue.assign(comp_ne[r] + 2, 0);
-        int used = k4_component(SoloTeam(), KS, KM, de.data() + de_off[r], comp_ne[r], queue.data(), row_off[r]);
+        std::vector<DEdge> scratch(comp_ne[r]);
+        int used = k4_component(SoloTeam(), KS, KM, de.data() + de_off[r], scratch.data(), comp_ne[r], queue.data(), row_off[r]);
         if (used > comp_strong[r]) return -100;
     }
     // final order: stable by (window, BFS start vertex), slot order inside
