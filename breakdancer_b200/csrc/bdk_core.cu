@@ -67,7 +67,7 @@ struct bdk_ctx {
     uint32_t A = 0;               // anomalous reads compacted so far
     uint32_t out_cap = 0;         // capacity of d_ar / d_P in reads
     // K1 tile chaining (look-back) state, reused by every launch
-    DevBuf d_ticket, d_tile_status, d_tile_agg, d_tile_inc, d_tile_bams;
+    DevBuf d_ticket, d_tile_status, d_tile_agg, d_tile_inc, d_tile_bams, d_stash;
     uint64_t tile_cap = 0;
     uint32_t epoch = 0;
     // chunk buffers for host pushes
@@ -169,6 +169,7 @@ int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, 
     a.ncnt = c->ncnt; a.cnt_rg = c->d_cnt_rg.as<int32_t>();
     a.co.max_sd = c->P.max_sd; a.co.transchr = c->P.transchr_rearrange; a.co.long_insert = c->P.illumina_long_insert;
     a.ar = c->d_ar.as<bdk_aread>(); a.P = c->d_P.as<uint32_t>(); a.cap = c->out_cap;
+    a.stash = c->d_stash.as<K1Stash>();
     char* acc = (char*)c->d_acc.p;
     a.carry = (uint32_t*)(acc + c->off_cursor);
     a.ticket = c->d_ticket.as<uint32_t>();
@@ -277,7 +278,7 @@ void bdk_destroy(bdk_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* all[] = {&c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_ticket,
-        &c->d_tile_status, &c->d_tile_agg, &c->d_tile_inc, &c->d_tile_bams, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
+        &c->d_tile_status, &c->d_tile_agg, &c->d_tile_inc, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
         &c->d_edge_key, &c->d_edge_start, &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
@@ -395,14 +396,14 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     CUC(cudaMalloc(&c->d_sort_hist.p, 256 * SS_GRID * 4)); c->d_sort_hist.cap = 256 * SS_GRID * 4;
     CUC(cudaMalloc(&c->d_ticket.p, 16)); c->d_ticket.cap = 16;
     {   // K1 launch shape: dynamic shared memory and resident CTAs per SM
-        const size_t ncomp = 1 + (size_t)c->nkey;
-        c->k1_smem = (p->nrg <= K1_RG_SMEM ? (size_t)(p->nrg + 1) * sizeof(RgDev) : 0) + (size_t)p->nlib * BDK_NUM_FLAGS * 4 +
-                     (size_t)(c->ncnt > 1 ? c->ncnt : 0) * K1_THREADS * 4 + (c->nkey > 1 ? (size_t)c->nkey * (K1_THREADS + K1_WARPS) * 4 : 0) +
-                     ncomp * K1_WARPS * 4 + ncomp * 4;
+        c->k1_smem = k1_smem_bytes(p->nrg, p->nlib, c->ncnt, c->nkey, c->nkey == 1, p->nrg <= K1_RG_SMEM);
         int bps = 0;
         CUC(cudaFuncSetAttribute(k1_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem));
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_fn(c), K1_THREADS, c->k1_smem));
-        c->k1_blocks_per_sm = std::max(1, bps);
+        c->k1_blocks_per_sm = std::max(1, std::min(bps, 2));
+        // thread-private stash of the anomalous reads of a tile, two tiles deep, for the largest grid
+        const size_t stash_bytes = (size_t)kNumSMs * c->k1_blocks_per_sm * 2 * K1_CTHREADS * K1_STASH * sizeof(K1Stash);
+        CUC(cudaMalloc(&c->d_stash.p, stash_bytes)); c->d_stash.cap = stash_bytes;
     }
     int rc = reset_job(c);
     if (rc) { g_create_error = c->err; bdk_destroy(c); return rc; }
@@ -443,7 +444,7 @@ int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
     const void* src[10] = {h->pos, h->mpos, h->tid, h->mtid, h->isize, h->flag, h->mapq, h->rgid, h->qlen, h->qid};
     static const size_t width[10] = {4, 4, 4, 4, 4, 2, 1, 2, 4, 8};
     for (int i = 0; i < 10; ++i) if (!src[i] && n) return fail(c, BDK_ERR_ARG, "null column %d", i);
-    const uint64_t CH = (uint64_t)K1_TILE * 2048;   // 8 Mi records per chunk (multiple of the tile size)
+    const uint64_t CH = (uint64_t)K1_TILE * 1024;   // 8 Mi records per chunk (multiple of the tile size)
     const uint64_t chunk_cap = std::min<uint64_t>(CH, div_up<uint64_t>(std::max<uint64_t>(n, 1), K1_TILE) * K1_TILE);
     // qlen / qid are read only for the anomalous 1-3 % of the records: when the caller's columns are pinned
     // (mapped) host memory the kernel reads those few values in place instead of copying 12 bytes per record.

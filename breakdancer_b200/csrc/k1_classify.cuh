@@ -197,7 +197,7 @@ __host__ __device__ inline size_t k1_smem_bytes(int nrg, int nlib, int ncnt, int
     const size_t ncomp = 1 + (size_t)nkey, ncol = ncnt > 1 ? ncnt : 0;
     size_t b = (size_t)K1_STAGES * K1_STAGE_BYTES;
     b += rg_smem ? (size_t)(nrg + 1) * sizeof(RgDev) : 0;
-    b += ((size_t)nlib * BDK_NUM_FLAGS + ncol * K1_CTHREADS) * 4;
+    b += ((((size_t)nlib * BDK_NUM_FLAGS + 3) & ~size_t(3)) + ncol * K1_CTHREADS) * 4;   // histogram padded to 16 bytes
     b += 2 * ncomp * K1_CWARPS * 8;                       // s_tot [2][ncomp][warps] packed per-stage totals (2 words)
     b += 2 * ncomp * 64 * 2;                              // s_off [2][ncomp][64] u16
     b += 2 * ncomp * 4;                                   // s_base [2][ncomp]
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     unsigned char* s_ring = s_dyn;                                                 // [K1_STAGES][K1_STAGE_BYTES]
     RgDev* s_rg = reinterpret_cast<RgDev*>(s_ring + K1_STAGES * K1_STAGE_BYTES);   // RG_SMEM: [nrg + 1]
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_rg + (RG_SMEM ? a.nrg + 1 : 0));   // [nlib * 11]
-    uint32_t* s_cnt = s_hist + nhist;                                              // [ncol][K1_CTHREADS]
+    uint32_t* s_cnt = s_hist + ((nhist + 3) & ~3);                                 // [ncol][K1_CTHREADS], 16-byte aligned
     uint2* s_tot = reinterpret_cast<uint2*>(s_cnt + ncol * K1_CTHREADS);           // [2][ncomp][K1_CWARPS] per-stage totals, a byte each
     uint16_t* s_off = reinterpret_cast<uint16_t*>(s_tot + 2 * ncomp * K1_CWARPS);  // [2][ncomp][64] exclusive offset of (stage, warp) in the tile
     uint32_t* s_base = reinterpret_cast<uint32_t*>(s_off + 2 * ncomp * 64);        // [2][ncomp] exclusive prefix of the tile
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
 
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < nhist + ncol * K1_CTHREADS; i += K1_THREADS) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < ((nhist + 3) & ~3) + ncol * K1_CTHREADS; i += K1_THREADS) s_hist[i] = 0;
     if (RG_SMEM) for (int i = threadIdx.x; i < a.nrg + 1; i += K1_THREADS) s_rg[i] = a.rgtab[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < K1_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], K1_CWARPS); }
@@ -468,8 +468,19 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 pex0 = i0 - c0; pex1 = i1 - c1;
                 if (lane == 31) s_tot[((size_t)tb * ncomp + 1) * K1_CWARPS + warp] = make_uint2(i0, i1);
             } else {
+                unsigned long long present = 0;
+#pragma unroll
+                for (int s = 0; s < K1_SUBS; ++s)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((pmask >> (s * 4 + j)) & 1u) present |= 1ull << ((keys[s] >> (8 * j)) & 0x3fu);
+                present = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)present) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(present >> 32)) << 32);
                 for (int k = 0; k < a.nkey; ++k) {                            // per key: per-stage totals of the warp
                     uint32_t c0 = 0, c1 = 0;
+                    if (!((present >> k) & 1ull)) {
+                        if (lane == 0) s_tot[((size_t)tb * ncomp + 1 + k) * K1_CWARPS + warp] = make_uint2(0u, 0u);
+                        continue;
+                    }
 #pragma unroll
                     for (int s = 0; s < K1_SUBS; ++s)
 #pragma unroll

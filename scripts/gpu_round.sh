@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 TAG=${2:-r01}
 K=${1:-k1_classify}
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
 tail -5 gpurun_out/test_$TAG.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
