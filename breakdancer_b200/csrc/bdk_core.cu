@@ -66,10 +66,10 @@ struct bdk_ctx {
     uint64_t n_records = 0;       // records pushed so far
     uint32_t A = 0;               // anomalous reads compacted so far
     uint32_t out_cap = 0;         // capacity of d_ar / d_P in reads
-    // K1 tile chaining (look-back) state, reused by every launch
-    DevBuf d_ticket, d_tile_status, d_tile_agg, d_tile_inc, d_tile_bams, d_stash;
+    // K1 per-CTA output segments (compacted into d_ar / d_P by k1_compact_kernel), reused by every launch
+    DevBuf d_seg_ar, d_seg_P, d_seg_cnt, d_carry_out, d_tile_bams, d_stash;
     uint64_t tile_cap = 0;
-    uint32_t epoch = 0;
+    uint32_t seg_cap = 0, seg_cap_min = 8192;
     // chunk buffers for host pushes
     DevBuf d_chunk[2][10];
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -151,41 +151,40 @@ int reset_job(bdk_ctx* c) {
 
 typedef void (*K1Fn)(const K1Args);
 K1Fn k1_fn(const bdk_ctx* c) {
-    const bool single = c->nkey == 1, smem = c->P.nrg <= K1_RG_SMEM;
+    const bool single = c->nkey == 1 && c->P.nbam == 1 && c->ncnt == 1, smem = c->P.nrg <= K1_RG_SMEM;   // FAST variant
     return single ? (smem ? k1_classify_kernel<true, true> : k1_classify_kernel<true, false>)
                   : (smem ? k1_classify_kernel<false, true> : k1_classify_kernel<false, false>);
 }
 
-// one K1 launch (+ the span search) over n records whose columns are on the device; qlen / qid may be
-// mapped host memory (only anomalous records touch them)
+int grow_segments(bdk_ctx* c, uint64_t want);
+
+// one K1 launch (+ segment compaction + the span search) over n records whose columns are on the device;
+// qlen / qid may be mapped host memory (only anomalous records touch them)
 int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, bool timed) {
     const uint64_t ntiles = div_up<uint64_t>(n, K1_TILE);
     if (!ntiles) return 0;
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)kNumSMs * c->k1_blocks_per_sm);
     K1Args a;
     a.c = cols; a.n = n; a.base_index = base_index;
+    a.tiles_per_cta = (uint32_t)div_up<uint64_t>(ntiles, grid);
     a.rgtab = c->d_rgtab.as<RgDev>();
     a.nrg = c->P.nrg; a.nlib = c->P.nlib; a.nbam = c->P.nbam; a.nkey = c->nkey;
     a.pad_rg = c->pad_rg;
     a.ncnt = c->ncnt; a.cnt_rg = c->d_cnt_rg.as<int32_t>();
     a.co.max_sd = c->P.max_sd; a.co.transchr = c->P.transchr_rearrange; a.co.long_insert = c->P.illumina_long_insert;
-    a.ar = c->d_ar.as<bdk_aread>(); a.P = c->d_P.as<uint32_t>(); a.cap = c->out_cap;
+    a.seg_ar = c->d_seg_ar.as<bdk_aread>(); a.seg_P = c->d_seg_P.as<uint32_t>(); a.seg_cap = c->seg_cap;
+    a.seg_cnt = c->d_seg_cnt.as<uint32_t>();
     a.stash = c->d_stash.as<K1Stash>();
-    char* acc = (char*)c->d_acc.p;
-    a.carry = (uint32_t*)(acc + c->off_cursor);
-    a.ticket = c->d_ticket.as<uint32_t>();
-    a.tile_status = c->d_tile_status.as<uint32_t>(); a.tile_agg = c->d_tile_agg.as<uint32_t>(); a.tile_inc = c->d_tile_inc.as<uint32_t>();
     a.tile_bams = c->d_tile_bams.as<unsigned long long>();
-    a.epoch = ++c->epoch;
-    if (c->epoch >= 0x3fffffffu) {   // epoch space exhausted: start over with clean status words
-        CU(cudaMemsetAsync(c->d_tile_status.p, 0, c->d_tile_status.cap, c->stream));
-        c->epoch = 1; a.epoch = 1;
-    }
+    char* acc = (char*)c->d_acc.p;
     a.rg_sproper = (unsigned long long*)acc;
     a.hist = (uint32_t*)(acc + c->off_hist); a.err = (uint32_t*)(acc + c->off_err);
-    CU(cudaMemsetAsync(c->d_ticket.p, 0, 4, c->stream));
-    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)kNumSMs * c->k1_blocks_per_sm);
+    uint32_t* carry = (uint32_t*)(acc + c->off_cursor);
     if (timed) tstart(c, T_K1);
     k1_fn(c)<<<grid, K1_THREADS, c->k1_smem, c->stream>>>(a);
+    k1_compact_kernel<<<grid, 256, 0, c->stream>>>(a.seg_ar, a.seg_P, a.seg_cap, a.seg_cnt, c->nkey, carry, c->d_carry_out.as<uint32_t>(),
+                                                   c->d_ar.as<bdk_aread>(), c->d_P.as<uint32_t>(), c->out_cap, a.err);
+    CU(cudaMemcpyAsync(carry, c->d_carry_out.p, 4 * (1 + (size_t)c->nkey), cudaMemcpyDeviceToDevice, c->stream));
     if (timed) tstop(c, T_K1);
     CU(cudaGetLastError());
     if (timed) tstart(c, T_SPAN);
@@ -195,19 +194,18 @@ int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, 
                                                  c->d_tile_bams.as<unsigned long long>(), (unsigned long long*)(acc + c->off_first),
                                                  (unsigned long long*)(acc + c->off_last));
     if (timed) tstop(c, T_SPAN);
-    c->launches += 2;
+    c->launches += 3;
     CU(cudaGetLastError());
     return 0;
 }
 
-// look-back tables for launches of up to `tiles` tiles
-int grow_tiles(bdk_ctx* c, uint64_t tiles) {
-    if (tiles <= c->tile_cap) return 0;
-    const size_t ncomp = 1 + (size_t)c->nkey;
-    ENS(c->d_tile_status, tiles * 4); ENS(c->d_tile_agg, tiles * 4 * ncomp); ENS(c->d_tile_inc, tiles * 4 * ncomp);
-    ENS(c->d_tile_bams, tiles * 8);
-    CU(cudaMemsetAsync(c->d_tile_status.p, 0, c->d_tile_status.cap, c->stream));
-    c->tile_cap = tiles;
+// per-tile tables and per-CTA output segments for launches of up to `n` records
+int grow_tiles(bdk_ctx* c, uint64_t n) {
+    const uint64_t tiles = div_up<uint64_t>(n, K1_TILE);
+    if (tiles > c->tile_cap) { ENS(c->d_tile_bams, tiles * 8); c->tile_cap = tiles; }
+    const uint64_t grid = (uint64_t)kNumSMs * c->k1_blocks_per_sm;
+    const uint64_t want = std::max<uint64_t>(c->seg_cap_min, n / (8 * grid));      // 12.5 % anomalous, evenly spread
+    if (want > c->seg_cap) return grow_segments(c, want);
     return 0;
 }
 
@@ -221,12 +219,21 @@ int grow_out(bdk_ctx* c, uint64_t want) {
 }
 
 // push of one batch whose columns are already device pointers; handles staging overflow by retry
+int grow_segments(bdk_ctx* c, uint64_t want) {
+    const uint64_t grid = (uint64_t)kNumSMs * c->k1_blocks_per_sm;
+    if (want > 0xfffffff0ull) return fail(c, BDK_ERR_NOMEM, "segment too large");
+    ENS(c->d_seg_ar, grid * want * sizeof(bdk_aread));
+    ENS(c->d_seg_P, grid * want * 4 * c->nkey);
+    c->seg_cap = (uint32_t)want;
+    return 0;
+}
+
 template <class RunFn>
 int push_common(bdk_ctx* c, uint64_t n, uint64_t max_launch, RunFn run) {
     if (c->finished) return fail(c, BDK_ERR_STATE, "bdk_push after bdk_finish (call bdk_reset first)");
     if (n == 0) return 0;
     if (c->n_records + n > 0xffffffffull) return fail(c, BDK_ERR_ARG, "more than 2^32 records in one context");
-    int rc = grow_tiles(c, div_up<uint64_t>(std::min(n, max_launch), K1_TILE));
+    int rc = grow_tiles(c, std::min(n, max_launch));
     if (rc) return rc;
     rc = grow_out(c, std::max<uint64_t>((uint64_t)c->A + std::max<uint64_t>(n / 16, 1 << 16), c->out_cap));
     if (rc) return rc;
@@ -234,19 +241,20 @@ int push_common(bdk_ctx* c, uint64_t n, uint64_t max_launch, RunFn run) {
         CU(cudaMemcpyAsync(c->d_acc_bak.p, c->d_acc.p, c->acc_bytes, cudaMemcpyDeviceToDevice, c->stream));
         rc = run();
         if (rc) return rc;
-        uint32_t tail[2];   // err, anomalous reads so far
-        CU(cudaMemcpyAsync(tail, (char*)c->d_acc.p + c->off_err, 8, cudaMemcpyDeviceToHost, c->stream));
+        uint32_t tail[3];   // err, largest per-CTA segment, anomalous reads so far
+        CU(cudaMemcpyAsync(tail, (char*)c->d_acc.p + c->off_err, 12, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         tcollect(c);
         if (tail[0] & K1_ERR_RG)
             return fail(c, BDK_ERR_DATA, "library index out of range (a record's read group has no library)");
-        if (tail[0] & K1_ERR_OVERFLOW) {   // output too small: restore the accumulators, grow, run again
+        if (tail[0] & K1_ERR_OVERFLOW) {   // a segment or the output is too small: restore the accumulators, grow, run again
             CU(cudaMemcpyAsync(c->d_acc.p, c->d_acc_bak.p, c->acc_bytes, cudaMemcpyDeviceToDevice, c->stream));
-            rc = grow_out(c, (uint64_t)tail[1] + (tail[1] - c->A) / 8 + 1024);
+            if (tail[1] > c->seg_cap) { rc = grow_segments(c, (uint64_t)tail[1] + tail[1] / 4 + 64); if (rc) return rc; }
+            rc = grow_out(c, (uint64_t)tail[2] + (tail[2] - c->A) / 8 + 1024);
             if (rc) return rc;
             continue;
         }
-        c->A = tail[1];
+        c->A = tail[2];
         c->summary_ready = false;
         c->n_records += n;
         return 0;
@@ -277,8 +285,8 @@ void bdk_destroy(bdk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_ticket,
-        &c->d_tile_status, &c->d_tile_agg, &c->d_tile_inc, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
+    DevBuf* all[] = {&c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
+        &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
         &c->d_edge_key, &c->d_edge_start, &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
@@ -385,7 +393,7 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     c->off_hist = c->off_last + nbt * 8;
     c->off_err = c->off_hist + (size_t)p->nlib * BDK_NUM_FLAGS * 4;
     c->off_err = (c->off_err + 7) & ~size_t(7);
-    c->off_cursor = c->off_err + 4;                       // carry: anomalous reads, then kept proper pairs per key
+    c->off_cursor = c->off_err + 8;                       // err, max segment; then the carry: anomalous reads, kept proper pairs per key
     c->acc_bytes = c->off_cursor + 4 * (1 + (size_t)c->nkey);
     CUC(cudaMalloc(&c->d_acc.p, c->acc_bytes)); c->d_acc.cap = c->acc_bytes;
     CUC(cudaMalloc(&c->d_acc_bak.p, c->acc_bytes)); c->d_acc_bak.cap = c->acc_bytes;
@@ -394,7 +402,6 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     CUC(cudaMalloc(&c->d_density.p, (size_t)std::max(1, c->nkey) * 4)); c->d_density.cap = (size_t)std::max(1, c->nkey) * 4;
     CUC(cudaMalloc(&c->d_scan_sums.p, SS_GRID * 4)); c->d_scan_sums.cap = SS_GRID * 4;
     CUC(cudaMalloc(&c->d_sort_hist.p, 256 * SS_GRID * 4)); c->d_sort_hist.cap = 256 * SS_GRID * 4;
-    CUC(cudaMalloc(&c->d_ticket.p, 16)); c->d_ticket.cap = 16;
     {   // K1 launch shape: dynamic shared memory and resident CTAs per SM
         c->k1_smem = k1_smem_bytes(p->nrg, p->nlib, c->ncnt, c->nkey, c->nkey == 1, p->nrg <= K1_RG_SMEM);
         int bps = 0;
@@ -404,6 +411,10 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         // thread-private stash of the anomalous reads of a tile, two tiles deep, for the largest grid
         const size_t stash_bytes = (size_t)kNumSMs * c->k1_blocks_per_sm * 2 * K1_CTHREADS * K1_STASH * sizeof(K1Stash);
         CUC(cudaMalloc(&c->d_stash.p, stash_bytes)); c->d_stash.cap = stash_bytes;
+        const size_t ncomp = 1 + (size_t)c->nkey, grid = (size_t)kNumSMs * c->k1_blocks_per_sm;
+        CUC(cudaMalloc(&c->d_seg_cnt.p, grid * ncomp * 4)); c->d_seg_cnt.cap = grid * ncomp * 4;
+        CUC(cudaMalloc(&c->d_carry_out.p, ncomp * 4)); c->d_carry_out.cap = ncomp * 4;
+        if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
     }
     int rc = reset_job(c);
     if (rc) { g_create_error = c->err; bdk_destroy(c); return rc; }

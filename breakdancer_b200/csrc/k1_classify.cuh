@@ -7,21 +7,24 @@
 //   * pass-2 filter; kept proper pairs feed the per-key running counts (nread_ROI / nread_FR),
 //     anomalous reads are compacted IN STREAM ORDER together with their inclusive per-key counts.
 //
-// Shape of the kernel (persistent, two CTAs per SM, warp-specialised):
-//   * producer warp: takes 8192-record tiles from a ticket counter and streams them through a
-//     3-stage shared-memory ring, 1024 records (25 600 B, eight column slices) per stage, with TMA
-//     bulk copies (cp.async.bulk ... mbarrier::complete_tx) -- no registers, ~150 KB in flight per SM;
+// Shape of the kernel (persistent, two CTAs per SM, warp-specialised). Every CTA owns one contiguous
+// range of 8192-record tiles, so its running counts are a local carry and no CTA ever waits for another:
+//   * producer warp: streams the CTA's tiles through a 3-stage shared-memory ring, 1024 records
+//     (25 600 B, eight column slices) per stage, with TMA bulk copies (cp.async.bulk ...
+//     mbarrier::complete_tx) -- no registers, ~150 KB in flight per SM;
 //   * 8 consumer warps: wait on a stage's "full" mbarrier, read 4 consecutive records per lane with
 //     conflict-free 16/8/4-byte shared loads, make the four decisions of classify_hot() per record
 //     and keep them as bit masks (32 records per thread and tile); the per-read-group constants are
 //     one 16-byte shared load, the pass-1 proper-pair counters a register (one (library, bam) pair)
 //     or thread-private shared-memory columns; the 1-3 % flagged records are classified in full on
 //     the spot (histogram) and, if anomalous, parked in a thread-private stash slot;
-//   * scan warp: chains the tiles by a decoupled look-back over (anomalous count, kept-proper count
-//     per key), 32 predecessor tiles per step. The consumers do not wait for it: they classify the
-//     next tile first and only then write out the previous tile's anomalous reads at their final,
-//     stream-ordered positions with their global inclusive proper-pair counts.
-// So every record is read from HBM exactly once and nothing but the anomalous reads is written.
+//   * scan warp: turns the per-(stage, warp) totals of a tile into exclusive offsets and advances the
+//     CTA's running counts. The consumers do not wait for it: they classify the next tile first and
+//     only then write the previous tile's anomalous reads, in stream order, into the CTA's output
+//     segment together with their CTA-relative inclusive proper-pair counts.
+// k1_compact_kernel then moves the segments to their final place (prefix over the per-CTA totals)
+// and makes the counts global. Every record is read from HBM exactly once; only the anomalous
+// 1-3 % are written.
 // The covered-reference-length statistic (first / last record of every (bam, chromosome)) needs
 // only the run boundaries of the sorted tid column: k1_span_kernel finds them by search.
 #pragma once
@@ -47,7 +50,7 @@ constexpr uint32_t K1_ERR_RG = 1u, K1_ERR_OVERFLOW = 2u;
 constexpr int K1_OFF_POS = 0, K1_OFF_MPOS = 4 * K1_SUB, K1_OFF_TID = 8 * K1_SUB, K1_OFF_MTID = 12 * K1_SUB, K1_OFF_ISZ = 16 * K1_SUB,
               K1_OFF_FLAG = 20 * K1_SUB, K1_OFF_RG = 22 * K1_SUB, K1_OFF_MAPQ = 24 * K1_SUB;
 // named barriers (0 is __syncthreads)
-constexpr int K1_BAR_A = 1, K1_BAR_B = 3, K1_BAR_C = 5;     // A[2]: totals ready, B[2]: prefix ready, C: consumers only
+constexpr int K1_BAR_A = 1, K1_BAR_B = 3, K1_BAR_C = 5;     // A[2]: totals ready, B[2]: offsets ready, C: consumers only
 
 // Per-read-group constants: the library's cut-offs and the ids the record maps to.
 struct alignas(16) RgDev {
@@ -68,26 +71,22 @@ struct K1Args {
     bdk_soa c;                 // device columns of this push (16-byte aligned); qlen / qid may be mapped host memory
     uint64_t n;                // records in this push
     uint32_t base_index;       // stream index of record 0 of this push
+    uint32_t tiles_per_cta;    // CTA b owns tiles [b * tiles_per_cta, (b + 1) * tiles_per_cta)
     const RgDev* rgtab;        // [nrg + 1]: entry nrg = invalid read group
     int32_t nrg, nlib, nbam, nkey;
     int32_t pad_rg;            // a read group with a library, used by padding records
     int32_t ncnt;              // private counter columns in use (0: count with warp votes + global atomics)
     const int32_t* cnt_rg;     // [ncnt] read group that receives the column's total
     ClassifyOpts co;
-    bdk_aread* ar;             // [cap] anomalous reads in stream order
-    uint32_t* P;               // [cap][nkey] inclusive kept-proper-pair counts per key at each anomalous read
-    uint32_t cap;
+    bdk_aread* seg_ar;         // [grid][seg_cap] anomalous reads of each CTA's range, in stream order
+    uint32_t* seg_P;           // [grid][seg_cap][nkey] CTA-relative inclusive kept-proper-pair counts per key
+    uint32_t seg_cap;
+    uint32_t* seg_cnt;         // [grid][1 + nkey] totals of each CTA: anomalous reads, kept proper pairs per key
     K1Stash* stash;            // [grid][2][K1_CTHREADS][K1_STASH]
-    uint32_t* carry;           // [1 + nkey] anomalous reads / kept proper pairs per key before this push (updated)
-    uint32_t* ticket;          // tile ticket counter (zero at launch)
-    uint32_t* tile_status;     // [tiles] epoch << 2 | state
-    uint32_t* tile_agg;        // [tiles][1 + nkey]
-    uint32_t* tile_inc;        // [tiles][1 + nkey]
     unsigned long long* tile_bams;   // [tiles] source bams present in the tile (nbam > 1 only)
-    uint32_t epoch;
     unsigned long long* rg_sproper;   // [nrg]
     uint32_t* hist;                   // [nlib][BDK_NUM_FLAGS]
-    uint32_t* err;
+    uint32_t* err;                    // err[0]: K1_ERR_* bits, err[1]: largest per-CTA anomalous count seen
 };
 
 struct K1Rec4 {
@@ -190,8 +189,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 
-enum : uint32_t { TS_AGG = 1u, TS_INC = 2u };
-
 // dynamic shared memory of k1_classify_kernel (bytes), host and device agree through this one function
 __host__ __device__ inline size_t k1_smem_bytes(int nrg, int nlib, int ncnt, int nkey, bool single_key, bool rg_smem) {
     const size_t ncomp = 1 + (size_t)nkey, ncol = ncnt > 1 ? ncnt : 0;
@@ -205,9 +202,12 @@ __host__ __device__ inline size_t k1_smem_bytes(int nrg, int nlib, int ncnt, int
     return b + 128;
 }
 
-// SINGLE_KEY: one copy-number key (the common single-bam run). RG_SMEM: the read-group table fits in shared memory.
-template <bool SINGLE_KEY, bool RG_SMEM>
+// FAST: one copy-number key, one source bam, one (library, bam) pair -- the common single-bam run: the
+// running counts live in registers and the hot loop has no per-record branches.
+// RG_SMEM: the read-group table fits in shared memory.
+template <bool FAST, bool RG_SMEM>
 __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args a) {
+    constexpr bool SINGLE_KEY = FAST;
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int ncomp = 1 + a.nkey;
     const int nhist = a.nlib * BDK_NUM_FLAGS;
@@ -218,9 +218,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     uint32_t* s_cnt = s_hist + ((nhist + 3) & ~3);                                 // [ncol][K1_CTHREADS], 16-byte aligned
     uint2* s_tot = reinterpret_cast<uint2*>(s_cnt + ncol * K1_CTHREADS);           // [2][ncomp][K1_CWARPS] per-stage totals, a byte each
     uint16_t* s_off = reinterpret_cast<uint16_t*>(s_tot + 2 * ncomp * K1_CWARPS);  // [2][ncomp][64] exclusive offset of (stage, warp) in the tile
-    uint32_t* s_base = reinterpret_cast<uint32_t*>(s_off + 2 * ncomp * 64);        // [2][ncomp] exclusive prefix of the tile
-    __shared__ __align__(8) uint64_t s_full[K1_STAGES], s_empty[K1_STAGES], s_tfull[2], s_tempty[2];
-    __shared__ uint32_t s_tile_ring[2];
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(s_off + 2 * ncomp * 64);        // [2][ncomp] CTA-relative exclusive prefix of the tile
+    __shared__ __align__(8) uint64_t s_full[K1_STAGES], s_empty[K1_STAGES];
     __shared__ unsigned long long s_wb[2][K1_CWARPS];
 
     const unsigned FULL = 0xffffffffu;
@@ -229,23 +228,17 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     if (RG_SMEM) for (int i = threadIdx.x; i < a.nrg + 1; i += K1_THREADS) s_rg[i] = a.rgtab[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < K1_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], K1_CWARPS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], K1_CWARPS + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const uint32_t ntiles = (uint32_t)div_up<uint64_t>(a.n, K1_TILE);
+    const uint32_t tile0 = min(ntiles, blockIdx.x * a.tiles_per_cta), tile1 = min(ntiles, tile0 + a.tiles_per_cta);
 
     // =============================== producer warp ===================================================
     if (warp == K1_CWARPS) {
         if (lane != 0) return;
         uint32_t g = 0;                                       // ring uses so far
-        for (uint32_t i = 0;; ++i) {
-            const int slot = i & 1;
-            if (i >= 2) mbar_wait(&s_tempty[slot], ((i >> 1) - 1) & 1);
-            const uint32_t tile = atomicAdd(a.ticket, 1u);
-            s_tile_ring[slot] = tile;
-            mbar_arrive(&s_tfull[slot]);
-            if (tile >= ntiles) break;
+        for (uint32_t tile = tile0; tile < tile1; ++tile) {
             for (int s = 0; s < K1_SUBS; ++s) {
                 const uint64_t rec0 = (uint64_t)tile * K1_TILE + (uint64_t)s * K1_SUB;
                 if (rec0 + K1_SUB > a.n) break;               // ragged stage: the consumers read it straight from global memory
@@ -270,13 +263,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
 
     // =============================== scan warp =======================================================
     if (warp == K1_CWARPS + 1) {
-        for (uint32_t i = 0;; ++i) {
-            const int slot = i & 1, tb = i & 1;
-            mbar_wait(&s_tfull[slot], (i >> 1) & 1);
-            const uint32_t tile = s_tile_ring[slot];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_tempty[slot]);
-            if (tile >= ntiles) break;
+        uint32_t run[3] = {0, 0, 0};                                         // lane owns components lane, lane + 32, lane + 64
+        for (uint32_t tile = tile0; tile < tile1; ++tile) {
+            const int tb = (tile - tile0) & 1;
             named_bar_sync(K1_BAR_A + tb, K1_CTHREADS + 32);                 // the consumers' totals of this tile are in s_tot
             if (a.nbam > 1 && lane == 0) {
                 unsigned long long b = 0;
@@ -284,7 +273,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 a.tile_bams[tile] = b;
             }
             // per component: exclusive offsets of the 64 (stage, warp) cells in stream order, and the tile total
-            uint32_t agg[3] = {0, 0, 0}, exc[3] = {0, 0, 0};                 // lane owns components lane, lane + 32, lane + 64
             for (int comp = 0; comp < ncomp; ++comp) {
                 const uint2* tot = s_tot + ((size_t)tb * ncomp + comp) * K1_CWARPS;
                 // cell q = stage * 8 + warp; this lane scans cells 2 * lane and 2 * lane + 1
@@ -295,70 +283,23 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 uint16_t* off = s_off + ((size_t)tb * ncomp + comp) * 64;
                 off[q0] = (uint16_t)(inc - v0 - v1); off[q0 + 1] = (uint16_t)(inc - v1);
                 const uint32_t total = __shfl_sync(FULL, inc, 31);
-                if ((comp & 31) == lane) { if (comp < 32) agg[0] = total; else if (comp < 64) agg[1] = total; else agg[2] = total; }
-            }
-            if (tile == 0) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int comp = lane + 32 * q;
-                    if (comp < ncomp) { exc[q] = a.carry[comp]; a.tile_inc[(size_t)tile * ncomp + comp] = exc[q] + agg[q]; }
-                }
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) st_release_u32(a.tile_status + tile, (a.epoch << 2) | TS_INC);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int comp = lane + 32 * q;
-                    if (comp < ncomp) a.tile_agg[(size_t)tile * ncomp + comp] = agg[q];
-                }
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) st_release_u32(a.tile_status + tile, (a.epoch << 2) | TS_AGG);
-                // look back over windows of 32 predecessor tiles (lane l inspects tile p - l)
-                int p = (int)tile - 1;
-                for (;;) {
-                    const int q_tile = p - lane;
-                    uint32_t st = TS_AGG;                                    // tiles before 0 contribute nothing
-                    if (q_tile >= 0) {
-                        do { st = ld_acquire_u32(a.tile_status + q_tile); } while ((st >> 2) != a.epoch);
-                        st &= 3u;
-                    }
-                    const unsigned incm = __ballot_sync(FULL, st == TS_INC);
-                    const int cut = incm ? __ffs(incm) - 1 : 31;            // nearest tile with an inclusive prefix
-                    const bool use = lane <= cut && q_tile >= 0;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        for (int cl = 0; cl < 32 && 32 * q + cl < ncomp; ++cl) {
-                            uint32_t v = 0;
-                            if (use) v = ld_cg_u32((st == TS_INC ? a.tile_inc : a.tile_agg) + (size_t)q_tile * ncomp + 32 * q + cl);
-                            v = __reduce_add_sync(FULL, v);
-                            if (cl == lane) exc[q] += v;
-                        }
-                    }
-                    if (incm) break;
-                    p -= 32;
-                }
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int comp = lane + 32 * q;
-                    if (comp < ncomp) a.tile_inc[(size_t)tile * ncomp + comp] = exc[q] + agg[q];
-                }
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) st_release_u32(a.tile_status + tile, (a.epoch << 2) | TS_INC);
-            }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int comp = lane + 32 * q;
-                if (comp < ncomp) {
-                    s_base[tb * ncomp + comp] = exc[q];
-                    if (tile == ntiles - 1) a.carry[comp] = exc[q] + agg[q];   // prefix for the next push
+                if ((comp & 31) == lane) {
+                    uint32_t& r = comp < 32 ? run[0] : (comp < 64 ? run[1] : run[2]);
+                    s_base[tb * ncomp + comp] = r;
+                    r += total;
                 }
             }
-            if (lane == 0 && exc[0] + agg[0] > a.cap) atomicOr(a.err, K1_ERR_OVERFLOW);
             __syncwarp();
             named_bar_arrive(K1_BAR_B + tb, K1_CTHREADS + 32);               // s_off / s_base of this tile are ready
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int comp = lane + 32 * q;
+            if (comp < ncomp) a.seg_cnt[(size_t)blockIdx.x * ncomp + comp] = run[q];
+        }
+        if (lane == 0) {
+            atomicMax(a.err + 1, run[0]);
+            if (run[0] > a.seg_cap) atomicOr(a.err, K1_ERR_OVERFLOW);
         }
         return;
     }
@@ -371,18 +312,16 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     uint32_t g = 0;                                                                // ring uses so far (same sequence as the producer)
     // state of the previous tile, whose anomalous reads are written out after the current tile is classified
     bool prev_have = false;
+    bdk_aread* seg_ar = a.seg_ar + (size_t)blockIdx.x * a.seg_cap;
+    uint32_t* seg_P = a.seg_P + (size_t)blockIdx.x * a.seg_cap * a.nkey;
     uint32_t prev_tile = 0, prev_amask = 0, prev_pmask = 0, prev_aex0 = 0, prev_aex1 = 0, prev_pex0 = 0, prev_pex1 = 0;
     uint32_t prev_keys[K1_SUBS];
 #pragma unroll
     for (int s = 0; s < K1_SUBS; ++s) prev_keys[s] = 0;
 
-    for (uint32_t i = 0;; ++i) {
-        const int slot = i & 1, tb = i & 1;
-        mbar_wait(&s_tfull[slot], (i >> 1) & 1);
-        const uint32_t tile = s_tile_ring[slot];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_tempty[slot]);
-        const bool have = tile < ntiles;
+    for (uint32_t tile = tile0;; ++tile) {
+        const int tb = (tile - tile0) & 1;
+        const bool have = tile < tile1;
         uint32_t amask = 0, pmask = 0, aex0 = 0, aex1 = 0, pex0 = 0, pex1 = 0, keys[K1_SUBS];
 #pragma unroll
         for (int s = 0; s < K1_SUBS; ++s) keys[s] = 0;
@@ -421,10 +360,10 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     if (ch & CH_ANOM) a4 |= 1u << j;
                     if (ch & CH_MPROPER) p4 |= 1u << j;
                     if (!SINGLE_KEY) kk |= ((L.info >> RGI_KEY_SHIFT) & 0x3fu) << (8 * j);
-                    if (a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
+                    if (!FAST && a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
                     // pass-1 proper-pair count per (library, bam)
                     const uint32_t sp = (ch >> 3) & 1u;          // CH_SPROPER
-                    if (a.ncnt == 1) spcnt += sp;
+                    if (FAST || a.ncnt == 1) spcnt += sp;
                     else if (a.ncnt) atomicAdd(my_cnt + ((L.info >> RGI_CNT_SHIFT) & 31u) * K1_CTHREADS, sp);   // private column: no conflicts
                     else {                                       // many (library, bam) pairs: one atomic per distinct read group and warp
                         const unsigned spm = __ballot_sync(FULL, sp && r.rg[j] < (uint32_t)a.nrg);
@@ -490,7 +429,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     if (lane == 0) s_tot[((size_t)tb * ncomp + 1 + k) * K1_CWARPS + warp] = make_uint2(c0, c1);
                 }
             }
-            if (a.nbam > 1) {
+            if (!FAST && a.nbam > 1) {
                 bams = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)bams) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(bams >> 32)) << 32);
                 if (lane == 0) s_wb[tb][warp] = bams;
             }
@@ -514,18 +453,18 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     const uint32_t below = (2u << j) - 1u;                   // items 0..j of the stage
                     const uint32_t o = base_a + off_a[s * 8 + warp] + byte_of2(prev_aex0, prev_aex1, s) + __popc(a4 & (below >> 1));
                     const K1Stash e = stash[k++];
-                    if (o >= a.cap) continue;
+                    if (o >= a.seg_cap) continue;
                     const uint64_t idx = (uint64_t)prev_tile * K1_TILE + (uint64_t)s * K1_SUB + (warp << 7) + (lane << 2) + j;
                     bdk_aread rec;
                     rec.pos = e.pos; rec.tid = e.tid; rec.qlen = a.c.qlen[idx];
                     rec.abs_isize = e.abs_isize; rec.meta = e.meta;
                     rec.record = a.base_index + (uint32_t)idx;
                     rec.qid = a.c.qid[idx];
-                    int4* dst = reinterpret_cast<int4*>(a.ar + o);
+                    int4* dst = reinterpret_cast<int4*>(seg_ar + o);
                     const int4* src = reinterpret_cast<const int4*>(&rec);
                     dst[0] = src[0]; dst[1] = src[1];
                     if (SINGLE_KEY) {
-                        a.P[o] = s_base[pb * ncomp + 1] + s_off[((size_t)pb * ncomp + 1) * 64 + s * 8 + warp] + byte_of2(prev_pex0, prev_pex1, s) + __popc(p4 & below);
+                        seg_P[o] = s_base[pb * ncomp + 1] + s_off[((size_t)pb * ncomp + 1) * 64 + s * 8 + warp] + byte_of2(prev_pex0, prev_pex1, s) + __popc(p4 & below);
                     }
                 }
             }
@@ -560,7 +499,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                             for (int j = 0; j < 4; ++j) {
                                 if ((a4 >> j) & 1u) {
                                     const uint32_t o = o0 + rank++;
-                                    if (o < a.cap) a.P[(size_t)o * a.nkey + k] = v0 + __popc(mine & ((2u << j) - 1u));
+                                    if (o < a.seg_cap) seg_P[(size_t)o * a.nkey + k] = v0 + __popc(mine & ((2u << j) - 1u));
                                 }
                             }
                         }
@@ -578,7 +517,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     }
     // ---------------- epilogue of the consumers: flush the accumulators --------------------------------------
     if (__any_sync(FULL, (bad & RGI_INVALID) != 0) && lane == 0) atomicOr(a.err, K1_ERR_RG);
-    if (a.ncnt == 1) {
+    if (FAST || a.ncnt == 1) {
         spcnt = __reduce_add_sync(FULL, spcnt);
         if (lane == 0 && spcnt) atomicAdd(a.rg_sproper + a.cnt_rg[0], (unsigned long long)spcnt);
     }
@@ -589,6 +528,43 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
         for (int t = lane; t < K1_CTHREADS; t += 32) sum += s_cnt[col * K1_CTHREADS + t];
         sum = __reduce_add_sync(FULL, sum);
         if (lane == 0 && sum) atomicAdd(a.rg_sproper + a.cnt_rg[col], (unsigned long long)sum);
+    }
+}
+
+// ---- move the per-CTA segments to their final place ---------------------------------------------------
+// Block b copies segment b to ar[carry[0] + sum of the anomalous counts of segments < b ...) and adds the
+// matching kept-proper-pair prefixes to its P rows. Launched with the same grid as K1. The last block leaves
+// the totals after this push in carry_out.
+__global__ void __launch_bounds__(256) k1_compact_kernel(const bdk_aread* __restrict__ seg_ar, const uint32_t* __restrict__ seg_P, uint32_t seg_cap,
+        const uint32_t* __restrict__ seg_cnt, int nkey, const uint32_t* __restrict__ carry, uint32_t* __restrict__ carry_out,
+        bdk_aread* __restrict__ ar, uint32_t* __restrict__ P, uint32_t cap, uint32_t* __restrict__ err) {
+    __shared__ uint32_t s_base[K1_MAXK + 1];
+    __shared__ uint32_t s_red[8];
+    const int ncomp = 1 + nkey, b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int comp = 0; comp < ncomp; ++comp) {
+        uint32_t s = 0;
+        for (int i = threadIdx.x; i < b; i += 256) s += seg_cnt[(size_t)i * ncomp + comp];
+        s = __reduce_add_sync(0xffffffffu, s);
+        if (lane == 0) s_red[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = carry[comp];
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            s_base[comp] = t;
+            if (b == (int)gridDim.x - 1) carry_out[comp] = t + seg_cnt[(size_t)b * ncomp + comp];
+        }
+        __syncthreads();
+    }
+    const uint32_t cnt = min(seg_cnt[(size_t)b * ncomp], seg_cap), base = s_base[0];
+    if (threadIdx.x == 0 && base + seg_cnt[(size_t)b * ncomp] > cap) atomicOr(err, K1_ERR_OVERFLOW);
+    const int4* src = reinterpret_cast<const int4*>(seg_ar + (size_t)b * seg_cap);
+    int4* dst = reinterpret_cast<int4*>(ar + base);
+    for (uint32_t i = threadIdx.x; i < 2 * cnt; i += 256) if (base + (i >> 1) < cap) dst[i] = src[i];
+    const uint32_t* sp = seg_P + (size_t)b * seg_cap * nkey;
+    for (uint32_t i = threadIdx.x; i < cnt * (uint32_t)nkey; i += 256) {
+        const uint32_t d = i / nkey, k = i - d * nkey;
+        if (base + d < cap) P[(size_t)(base + d) * nkey + k] = sp[i] + s_base[1 + k];
     }
 }
 

@@ -120,6 +120,18 @@ def test_gpu_all_anomalous_staging_overflow_and_giant_region():
         _check(b, cols, str(od))
 
 
+def test_gpu_segment_overflow_retry(monkeypatch):
+    """Per-CTA output segments far too small (forced): the push detects it, grows them and runs again."""
+    monkeypatch.setenv("BDK_SEG_CAP_MIN", "16")
+    w = synth.generate(util.GENOME3, util.LIBS4, 150000, seed=21, anomaly_frac=0.2)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    _check(b, cols, "tiny segments, one push")
+    _check(b, cols, "tiny segments, 5 pushes", chunks=5)
+    w = synth.config2(400000, seed=3)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    _check(b, cols, "tiny segments, single-key path")
+
+
 def test_gpu_reset_and_reuse_is_idempotent():
     w = synth.generate(util.GENOME3, util.LIBS4, 80000, seed=8, anomaly_frac=0.04)
     b, cols, *_ = util.workload_bundle(w, api.Options())
