@@ -218,10 +218,18 @@ def ours(args):
             e["ms"] += v["ms"]; e["launches"] += v["launches"]
         launches[0] += ctx.kernel_launches()
 
+    host_ms = {"reset": 0.0, "push": 0.0, "finish": 0.0}
+
     def step_device():
+        t0 = time.perf_counter()
         ctx.reset()
+        t1 = time.perf_counter()
         ctx.push_soa(dsoa, n, device=True)
-        return ctx.finish_raw()
+        t2 = time.perf_counter()
+        r = ctx.finish_raw()
+        t3 = time.perf_counter()
+        host_ms["reset"] += 1e3 * (t1 - t0); host_ms["push"] += 1e3 * (t2 - t1); host_ms["finish"] += 1e3 * (t3 - t2)
+        return r
 
     def barrier():
         if world > 1:
@@ -232,6 +240,8 @@ def ours(args):
         res = step_device()
     n_sv = int(res.n_sv) if args.warmup else 0
     sampler = ClockSampler(local) if rank == 0 else None
+    for k in host_ms:
+        host_ms[k] = 0.0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -283,7 +293,7 @@ def ours(args):
     e_ms_wall = 1e3 * (time.perf_counter() - w0) / esteps
     e_ms = max(e0.elapsed_time(e1) / esteps, 0.0)
     e_ms = max(e_ms, e_ms_wall) if world == 1 else e_ms
-    d2h = int(res.n_sv) * (80 + 4 * bundle.params.nlib + 8 * bundle.nkey) + 15072 + 36
+    d2h = ctx.d2h_bytes()
     if world > 1:
         t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -316,6 +326,7 @@ def ours(args):
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * BYTES_PER_RECORD, "kernel_ms": k1_ms},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in ktimes.items()},
+            "host_call_ms_per_step": {k: v / args.steps for k, v in host_ms.items()},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_ms, "h2d_bytes_per_step": h2d,
                     "zero_copy_side_columns": h2d < n * HOST_BYTES_PER_RECORD,
                     "d2h_bytes_per_step": d2h},

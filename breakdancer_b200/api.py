@@ -136,6 +136,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdk_kernel_times": (C.c_int, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
         "bdk_kernel_launches": (u64, [vp]),
         "bdk_h2d_bytes": (u64, [vp]),
+        "bdk_d2h_bytes": (u64, [vp]),
         "bdk_host_alloc": (vp, [u64]),
         "bdk_host_free": (None, [vp]),
         "bdk_set_comm": (C.c_int, [vp, vp, C.c_int, C.c_int]),
@@ -406,6 +407,10 @@ class Context:
     def h2d_bytes(self) -> int:
         """Bytes the last push() copied host -> device."""
         return int(self._L.bdk_h2d_bytes(self._h))
+
+    def d2h_bytes(self) -> int:
+        """Bytes the last finish() copied device -> host."""
+        return int(self._L.bdk_d2h_bytes(self._h))
 
     def poisson_logsf(self, lam: np.ndarray, k: np.ndarray) -> np.ndarray:
         lam = np.ascontiguousarray(lam, np.float64)

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -41,8 +42,9 @@ struct StageTimer {
     bool pending = false;
 };
 
-enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_N };
-const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_span", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results"};
+enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_HOST, T_N };
+const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_span", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results",
+                                "host_order_rows"};   // the last one is host wall time (output ordering), not a device timer
 
 }  // namespace
 
@@ -75,9 +77,12 @@ struct bdk_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // finish() work space
     DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
-        d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_links, d_links_tmp,
-        d_sort_hist, d_edge_key, d_edge_start, d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
-        d_deleted, d_de, d_de2, d_queue, d_rowpack, d_pois_l, d_pois_k, d_pois_o;
+        d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt, d_de_root,
+        d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
+        d_deleted, d_de, d_de2, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_sort_k, d_sort_v, d_pois_l, d_pois_k, d_pois_o;
+    int k5_smem_rows = K5_SMEM_ROWS;   // tables up to this many row slots are ordered by the single-CTA shared-memory sort
+    uint64_t d2h_bytes = 0;
+    uint32_t n_slots = 0;
     void* h_pack = nullptr;       // pinned host block the row outputs + summary are copied into
     size_t h_pack_cap = 0;
     bool finished = false, summary_ready = false;
@@ -93,7 +98,7 @@ struct bdk_ctx {
     std::vector<float> h_copy_number;
     std::vector<bdk_region> h_regions;
     std::vector<bdk_aread> h_areads;
-    std::vector<int32_t> h_read_region, h_sv_of_read, h_slot_order;
+    std::vector<int32_t> h_read_region, h_sv_of_read;
     uint32_t h_cnt[CNT_N] = {0};
     StageTimer timers[T_N];
 };
@@ -288,9 +293,9 @@ void bdk_destroy(bdk_ctx* c) {
     DevBuf* all[] = {&c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
-        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_links, &c->d_links_tmp, &c->d_sort_hist,
-        &c->d_edge_key, &c->d_edge_start, &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
-        &c->d_deleted, &c->d_de, &c->d_de2, &c->d_queue, &c->d_rowpack, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
+        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt, &c->d_de_root,
+        &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
+        &c->d_deleted, &c->d_de, &c->d_de2, &c->d_queue, &c->d_rowpack, &c->d_outpack, &c->d_slot_order, &c->d_sort_hist, &c->d_sort_k, &c->d_sort_v, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
@@ -401,7 +406,6 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     CUC(cudaMalloc(&c->d_summary.p, sizeof(bdk_summary_t))); c->d_summary.cap = sizeof(bdk_summary_t);
     CUC(cudaMalloc(&c->d_density.p, (size_t)std::max(1, c->nkey) * 4)); c->d_density.cap = (size_t)std::max(1, c->nkey) * 4;
     CUC(cudaMalloc(&c->d_scan_sums.p, SS_GRID * 4)); c->d_scan_sums.cap = SS_GRID * 4;
-    CUC(cudaMalloc(&c->d_sort_hist.p, 256 * SS_GRID * 4)); c->d_sort_hist.cap = 256 * SS_GRID * 4;
     {   // K1 launch shape: dynamic shared memory and resident CTAs per SM
         c->k1_smem = k1_smem_bytes(p->nrg, p->nlib, c->ncnt, c->nkey, c->nkey == 1, p->nrg <= K1_RG_SMEM);
         int bps = 0;
@@ -414,6 +418,8 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         const size_t ncomp = 1 + (size_t)c->nkey, grid = (size_t)kNumSMs * c->k1_blocks_per_sm;
         CUC(cudaMalloc(&c->d_seg_cnt.p, grid * ncomp * 4)); c->d_seg_cnt.cap = grid * ncomp * 4;
         CUC(cudaMalloc(&c->d_carry_out.p, ncomp * 4)); c->d_carry_out.cap = ncomp * 4;
+        if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
+        CUC(cudaFuncSetAttribute(k5_order_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM_ROWS * 12));
         if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
     }
     int rc = reset_job(c);
@@ -564,7 +570,6 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     uint32_t tsize = 1024; while (tsize < 2 * (uint64_t)A) tsize <<= 1;
     ENS(c->d_table, (size_t)tsize * 4);
     const size_t L1 = (size_t)A / 2 + 2;
-    ENS(c->d_links, L1 * 8); ENS(c->d_links_tmp, L1 * 8); ENS(c->d_edge_key, L1 * 8); ENS(c->d_edge_start, L1 * 4);
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
     ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
@@ -587,29 +592,30 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
 
     // ---- K3 ----------------------------------------------------------------------------------
     tstart(c, T_K3);
+    uint32_t esize = 1024; while (esize < (uint64_t)A + 2) esize <<= 1;    // edge table: at most A / 2 distinct (region, region) keys
+    ENS(c->d_ekeys, (size_t)esize * 8); ENS(c->d_ecnt, (size_t)esize * 4); ENS(c->d_de_root, (2 * L1 + 2) * 4);
     CU(cudaMemsetAsync(c->d_table.p, 0xff, (size_t)tsize * 4, st));
     CU(cudaMemsetAsync(c->d_mate.p, 0xff, (size_t)A * 4, st));
     CU(cudaMemsetAsync(c->d_sv_of_read.p, 0xff, (size_t)A * 4, st));
     CU(cudaMemsetAsync(c->d_freed.p, 0, A, st));
+    CU(cudaMemsetAsync(c->d_ekeys.p, 0xff, (size_t)esize * 8, st));
+    CU(cudaMemsetAsync(c->d_ecnt.p, 0, (size_t)esize * 4, st));
+    unsigned long long* ekeys = c->d_ekeys.as<unsigned long long>();
+    uint32_t* ecnt = c->d_ecnt.as<uint32_t>();
     k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
-    k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, c->d_links.as<unsigned long long>(), d_cnt);
-    int rbits = 1; while ((1ull << rbits) < (uint64_t)A + 2) ++rbits;      // region indices < A + 1
-    unsigned long long* keys = c->d_links.as<unsigned long long>();
-    SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_links_tmp.as<unsigned long long>(), nullptr};
-    device_radix_sort(st, &keys, nullptr, d_cnt + CNT_NLINK, 0, rbits, sosc);
-    device_radix_sort(st, &keys, nullptr, d_cnt + CNT_NLINK, 32, 32 + rbits, sosc);
-    device_scan(st, HeadFlag{keys}, HeadOut{keys, c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>()},
-                d_cnt + CNT_NLINK, d_cnt + CNT_NEDGE, 0, ssc);
+    k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
     k3_init_regions_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(), c->d_comp_strong.as<uint32_t>(),
                                                            c->d_comp_fill.as<uint32_t>(), c->d_deleted.as<uint8_t>(), d_cnt);
-    k3_union_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_parent.as<int32_t>(), d_cnt);
-    k3_comp_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>(), c->d_parent.as<int32_t>(),
-                                                         c->d_comp_ne.as<uint32_t>(), c->d_comp_strong.as<uint32_t>(), c->P.min_read_pair, d_cnt);
+    k3_union_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, esize, c->d_parent.as<int32_t>());
+    k3_comp_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(),
+                                                         c->d_comp_strong.as<uint32_t>(), c->P.min_read_pair);
     device_scan(st, LoadU32{c->d_comp_ne.as<uint32_t>()}, ExclOut{c->d_de_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NDE, 0, ssc);
     device_scan(st, LoadU32{c->d_comp_strong.as<uint32_t>()}, ExclOut{c->d_row_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NROW, 0, ssc);
-    k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_edge_key.as<unsigned long long>(), c->d_edge_start.as<uint32_t>(), c->d_parent.as<int32_t>(),
-                                                            c->d_de_off.as<uint32_t>(), c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->period, d_cnt);
-    c->launches += 2 + 3 * 2 * (uint64_t)((rbits + 7) / 8) + 3 + 3 + 3 + 3 + 1;   // join, links, sort passes, 3 scans, init/union/count, scatter
+    k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_de_off.as<uint32_t>(),
+                                                            c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->period);
+    k3_rank_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->d_de_off.as<uint32_t>(),
+                                                         c->d_comp_ne.as<uint32_t>(), c->d_de2.as<DEdge>(), d_cnt);
+    c->launches += 2 + 3 + 3 + 3 + 2;   // join, links, init/union/count, 2 scans, scatter, rank
     tstop(c, T_K3);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_cnt, d_cnt, CNT_N * 4, cudaMemcpyDeviceToHost, st));
@@ -619,21 +625,27 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     const uint32_t nrow = c->h_cnt[CNT_NROW], nreg = c->h_cnt[CNT_NREG];
 
     // ---- K4 ----------------------------------------------------------------------------------
-    // all per-row outputs live in one device block so that a single copy brings them to a pinned host block
+    // per-row outputs by slot (K4 writes them) and, after ordering, by output position (one block, one copy to a
+    // pinned host block that the result pointers then refer to: the host never touches the rows)
     const size_t R1 = (size_t)nrow + 1;
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_rows = 0, o_lc = al(o_rows + R1 * sizeof(bdk_sv)), o_cc = al(o_lc + R1 * 4 * nlib), o_cn = al(o_cc + R1 * 4 * nkey),
-                 o_emit = al(o_cn + R1 * 4 * nkey), o_key = al(o_emit + R1), o_span = al(o_key + R1 * 8), pack_bytes = o_span + R1 * 4 * nlib;
-    ENS(c->d_rowpack, pack_bytes);
-    if (c->h_pack_cap < o_span + sizeof(bdk_summary_t)) {
+                 o_n = al(o_cn + R1 * 4 * nkey), o_sum = al(o_n + 16), out_bytes = al(o_sum + sizeof(bdk_summary_t));   // ordered block (device + host)
+    const size_t w_emit = al(out_bytes), w_key = al(w_emit + R1), w_span = al(w_key + R1 * 8), w_ekey = al(w_span + R1 * 4 * nlib),
+                 w_eslot = al(w_ekey + R1 * 8), w_order = al(w_eslot + R1 * 4), w_tmpk = al(w_order + R1 * 4), w_tmpv = al(w_tmpk + R1 * 8),
+                 work_bytes = al(w_tmpv + R1 * 4);                                                                  // slot-indexed block
+    ENS(c->d_rowpack, work_bytes); ENS(c->d_outpack, out_bytes); ENS(c->d_slot_order, R1 * 4);
+    if (c->h_pack_cap < out_bytes) {
         if (c->h_pack) cudaFreeHost(c->h_pack);
         c->h_pack = nullptr; c->h_pack_cap = 0;
-        const size_t want = (o_span + sizeof(bdk_summary_t)) * 5 / 4 + 4096;
+        const size_t want = out_bytes * 5 / 4 + 4096;
         CU(cudaHostAlloc(&c->h_pack, want, cudaHostAllocDefault));
         c->h_pack_cap = want;
     }
     char* dp = (char*)c->d_rowpack.p;
-    CU(cudaMemsetAsync(dp + o_emit, 0, R1, st));
+    char* op = (char*)c->d_outpack.p;
+    CU(cudaMemsetAsync(dp + w_emit, 0, R1, st));
+    CU(cudaMemsetAsync(c->d_slot_order.p, 0xff, R1 * 4, st));
     K4Static S;
     S.ar = c->d_ar.as<bdk_aread>(); S.read_region = c->d_read_region.as<int32_t>(); S.read_cand = c->d_read_cand.as<int32_t>();
     S.mate = c->d_mate.as<int32_t>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
@@ -645,55 +657,66 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     K4Mut M;
     M.alive = c->d_alive.as<uint8_t>(); M.freed = c->d_freed.as<uint8_t>(); M.deleted = c->d_deleted.as<uint8_t>();
     M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = (bdk_sv*)(dp + o_rows);
-    M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + o_span);
+    M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + w_span);
     M.row_cn_count = (uint32_t*)(dp + o_cc); M.row_cn = (float*)(dp + o_cn);
-    M.row_emit = (uint8_t*)(dp + o_emit); M.row_key = (uint64_t*)(dp + o_key);
+    M.row_emit = (uint8_t*)(dp + w_emit); M.row_key = (uint64_t*)(dp + w_key);
+    M.emit_count = d_cnt + CNT_NEMIT; M.emit_key = (uint64_t*)(dp + w_ekey); M.emit_slot = (uint32_t*)(dp + w_eslot);
     tstart(c, T_K4);
     if (nrow || c->h_cnt[CNT_NDE]) {
         const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(nreg, 32 * (K4_THREADS / 32)), (uint64_t)kNumSMs * 16);
         k4_components_kernel<<<std::max(1u, grid), K4_THREADS, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
-                                                                  c->d_de.as<DEdge>(), c->d_de2.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt);
+                                                                  c->d_de.as<DEdge>(), c->d_de2.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt, d_cnt + CNT_K4_TICKET);
+        c->launches += 1;
     }
-    if (nrow || c->h_cnt[CNT_NDE]) c->launches += 1;
     tstop(c, T_K4);
     CU(cudaGetLastError());
 
-    // ---- results to the host, final order ---------------------------------------------------------
+    // ---- output order + results to the host -----------------------------------------------------------
     tstart(c, T_D2H);
+    uint32_t* order_slot = (uint32_t*)(dp + w_order);
+    if (nrow <= (uint32_t)c->k5_smem_rows) {
+        uint32_t m = 1024; while (m < nrow) m <<= 1;
+        k5_order_smem_kernel<<<1, K5_THREADS, (size_t)m * 12, st>>>(M.emit_key, M.emit_slot, d_cnt, order_slot);
+        c->launches += 1;
+    } else {   // large tables: stable LSD radix sort by slot, BFS start vertex, window
+        int sbits = 1; while ((1ull << sbits) < (uint64_t)nrow + 1) ++sbits;
+        int vbits = 1; while ((1ull << vbits) < (uint64_t)nreg + 1) ++vbits;
+        ENS(c->d_sort_hist, 256 * SS_GRID * 4);
+        // pass 1: by slot (as the key), carrying the key as ... the sort moves (u64 key, u32 value) pairs, so sort twice:
+        // first (key = slot, value = index), then (key = row key, value = slot) stably
+        unsigned long long* k1 = (unsigned long long*)(dp + w_tmpk);
+        uint32_t* v1 = (uint32_t*)(dp + w_tmpv);
+        k5_slot_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(M.emit_key, M.emit_slot, d_cnt + CNT_NEMIT, k1, v1);
+        unsigned long long* kk = k1; uint32_t* vv = v1;
+        ENS(c->d_sort_k, R1 * 8); ENS(c->d_sort_v, R1 * 4);
+        SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_sort_k.as<unsigned long long>(), c->d_sort_v.as<uint32_t>()};
+        device_radix_sort(st, &kk, &vv, d_cnt + CNT_NEMIT, 0, sbits, sosc);           // by slot
+        k5_row_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(M.row_key, d_cnt + CNT_NEMIT, kk);   // kk[i] (= slot) -> row key, vv[i] = slot
+        device_radix_sort(st, &kk, &vv, d_cnt + CNT_NEMIT, 0, vbits, sosc);           // by BFS start vertex
+        device_radix_sort(st, &kk, &vv, d_cnt + CNT_NEMIT, 32, 32 + vbits, sosc);     // by window
+        k5_copy_u32_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(vv, order_slot, d_cnt + CNT_NEMIT);
+        c->launches += 3 + 3 * (uint64_t)((sbits + 7) / 8 + 2 * ((vbits + 7) / 8));
+    }
+    RowPack in{M.rows, M.row_lib_count, M.row_cn_count, M.row_cn};
+    RowPack outp{(bdk_sv*)(op + o_rows), (int32_t*)(op + o_lc), (uint32_t*)(op + o_cc), (float*)(op + o_cn)};
+    k5_gather_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(in, outp, order_slot, c->d_slot_order.as<int32_t>(), nlib, nkey, d_cnt, (uint32_t*)(op + o_n));
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(op + o_sum, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToDevice, st));
     char* hp = (char*)c->h_pack;
-    if (nrow) CU(cudaMemcpyAsync(hp, dp, o_span, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(hp + o_span, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hp, op, out_bytes, cudaMemcpyDeviceToHost, st));
+    c->d2h_bytes = out_bytes;
     tstop(c, T_D2H);
     CU(cudaStreamSynchronize(st));
     tcollect(c);
-    memcpy(&c->h_summary, hp + o_span, sizeof(bdk_summary_t));
-    const bdk_sv* rows = (const bdk_sv*)(hp + o_rows);
-    const int32_t* rlc = (const int32_t*)(hp + o_lc);
-    const uint32_t* rcc = (const uint32_t*)(hp + o_cc);
-    const float* rcn = (const float*)(hp + o_cn);
-    const uint8_t* remit = (const uint8_t*)(hp + o_emit);
-    const uint64_t* rkey = (const uint64_t*)(hp + o_key);
-    // the reference prints window by window, BFS by BFS (key), calls of one BFS in slot order
-    std::vector<uint32_t> order;
-    for (uint32_t r = 0; r < nrow; ++r) if (remit[r]) order.push_back(r);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return rkey[x] < rkey[y]; });
-    const size_t ns = order.size();
-    c->h_sv.resize(ns); c->h_lib_count.resize(ns * nlib); c->h_cn_count.resize(ns * nkey); c->h_copy_number.resize(ns * nkey);
-    for (size_t i = 0; i < ns; ++i) {
-        const uint32_t r = order[i];
-        c->h_sv[i] = rows[r]; c->h_sv[i].order = (int32_t)i;
-        std::copy(rlc + (size_t)r * nlib, rlc + (size_t)(r + 1) * nlib, c->h_lib_count.begin() + i * nlib);
-        std::copy(rcc + (size_t)r * nkey, rcc + (size_t)(r + 1) * nkey, c->h_cn_count.begin() + i * nkey);
-        std::copy(rcn + (size_t)r * nkey, rcn + (size_t)(r + 1) * nkey, c->h_copy_number.begin() + i * nkey);
-    }
-    // slot -> output order, for bdk_get_support
+    memcpy(&c->h_summary, hp + o_sum, sizeof(bdk_summary_t));
+    const size_t ns = *(const uint32_t*)(hp + o_n);
     c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet
-    c->h_slot_order.assign(nrow, -1);
-    for (size_t i = 0; i < ns; ++i) c->h_slot_order[order[i]] = (int32_t)i;
+    c->n_slots = nrow;
     c->finished = true;
     out->n_sv = ns;
-    out->sv = c->h_sv.data(); out->lib_count = c->h_lib_count.data(); out->cn_count = c->h_cn_count.data();
-    out->copy_number = c->h_copy_number.data(); out->nkey = nkey;
+    out->sv = (const bdk_sv*)(hp + o_rows); out->lib_count = (const int32_t*)(hp + o_lc); out->cn_count = (const uint32_t*)(hp + o_cc);
+    out->copy_number = (const float*)(hp + o_cn); out->nkey = nkey;
     return 0;
 }
 
@@ -732,9 +755,9 @@ int bdk_get_support(bdk_ctx* c, const int32_t** sv_of_read, uint64_t* n) {
     if (!c->finished) return fail(c, BDK_ERR_STATE, "bdk_get_support before bdk_finish");
     CU(cudaSetDevice(c->device));
     if (c->h_sv_of_read.size() == 1 && c->h_sv_of_read[0] == -2) {
-        std::vector<int32_t> slots(c->A);
+        std::vector<int32_t> slots(c->A), slot_order(c->n_slots);
         if (c->A) CU(cudaMemcpy(slots.data(), c->d_sv_of_read.p, (size_t)c->A * 4, cudaMemcpyDeviceToHost));
-        const std::vector<int32_t>& slot_order = c->h_slot_order;
+        if (c->n_slots) CU(cudaMemcpy(slot_order.data(), c->d_slot_order.p, (size_t)c->n_slots * 4, cudaMemcpyDeviceToHost));
         for (auto& s : slots) s = (s >= 0 && (size_t)s < slot_order.size()) ? slot_order[s] : -1;
         c->h_sv_of_read.swap(slots);
     }
@@ -752,6 +775,7 @@ int bdk_kernel_times(bdk_ctx* c, const char** names, float* ms, int* launches, i
 uint64_t bdk_kernel_launches(bdk_ctx* c) { return c ? c->launches : 0; }
 
 uint64_t bdk_h2d_bytes(bdk_ctx* c) { return c ? c->h2d_bytes : 0; }
+uint64_t bdk_d2h_bytes(bdk_ctx* c) { return c ? c->d2h_bytes : 0; }
 
 int bdk_set_comm(bdk_ctx* c, void*, int, int) {
     if (!c) return BDK_ERR_ARG;

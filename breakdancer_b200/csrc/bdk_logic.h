@@ -270,6 +270,9 @@ struct K4Mut {
     float* row_cn;          // [nrow_cap][nkey]
     uint8_t* row_emit;      // [nrow_cap]
     uint64_t* row_key;      // [nrow_cap] (window << 32 | BFS start vertex)
+    uint32_t* emit_count;   // number of rows emitted so far
+    uint64_t* emit_key;     // [nrow_cap] key of the i-th emitted row (arrival order)
+    uint32_t* emit_slot;    // [nrow_cap] its row slot
 };
 
 struct WindowInfo { int32_t cF; int32_t maxlen; int32_t last_region; };
@@ -323,6 +326,7 @@ struct SoloTeam {
     BDK_HD bool any(bool p) const { return p; }
     BDK_HD void sync() const {}
     BDK_HD void add(int32_t* p, int v) const { *p += v; }
+    BDK_HD uint32_t fetch_inc(uint32_t* p) const { return (*p)++; }
 };
 #if defined(__CUDACC__)
 struct WarpTeam {
@@ -332,6 +336,7 @@ struct WarpTeam {
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void add(int32_t* p, int v) const { atomicAdd(p, v); }
+    __device__ __forceinline__ uint32_t fetch_inc(uint32_t* p) const { return atomicAdd(p, 1u); }
 };
 #endif
 
@@ -491,8 +496,11 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
     o.flag = flag; o.diffspan = diffspan; o.score = phred; o.num_pairs = flag_counts[flag];
     o.logp = logp; o.allele_frequency = af; o.cn_present = 0;
     o.region[0] = s0; o.region[1] = s1; o.window = w; o.order = 0;
-    M.row_key[row] = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;
+    const uint64_t key = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;
+    M.row_key[row] = key;
     M.row_emit[row] = 1;
+    const uint32_t idx = T.fetch_inc(M.emit_count);      // the reference prints by (window, BFS start), calls of one BFS in slot order
+    M.emit_key[idx] = key; M.emit_slot[idx] = (uint32_t)row;
     return true;
 }
 
@@ -529,7 +537,7 @@ BDK_HD int de_find_src(const DEdge* e, int lo, int hi, int src) {
 }
 
 // One connected component (over all windows) of the region graph: its directed edges
-// e[0..ne) (unsorted on entry), a queue scratch of ne + 2 ints, and row slots [row0, ...).
+// e[0..ne) (sorted by (win, src, dst)), a queue scratch of ne + 2 ints, and row slots [row0, ...).
 // Walks the windows in order, doing for each what build_connection does for the part of the
 // graph that belongs to this component. Returns the number of row slots used.
 // All lanes of the team follow the same path; lane 0 alone writes the walk's state (edge flags,
@@ -537,7 +545,7 @@ BDK_HD int de_find_src(const DEdge* e, int lo, int hi, int src) {
 // Sort a component's directed edges by (win, src, dst). Up to DE_RANK_SORT_MAX edges: rank sort spread over the
 // team (the keys are unique, so the rank of an edge is its final position) into `scratch`; beyond that the leader
 // heap-sorts in place. Returns the array that holds the sorted edges.
-constexpr int DE_RANK_SORT_MAX = 2048;
+constexpr int DE_RANK_SORT_MAX = 8192;
 template <class Team>
 BDK_HD DEdge* de_sort_team(const Team& T, DEdge* e, int ne, DEdge* scratch) {
     T.sync();
@@ -558,9 +566,9 @@ BDK_HD DEdge* de_sort_team(const Team& T, DEdge* e, int ne, DEdge* scratch) {
 }
 
 template <class Team>
-BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e_in, DEdge* e_scratch, int ne, int32_t* queue, int row0) {
+BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* sorted by (win, src, dst) */, int ne, int32_t* queue, int row0) {
     const bool lead = T.lane() == 0;
-    DEdge* e = de_sort_team(T, e_in, ne, e_scratch);
+    T.sync();
     int row = row0;
     int i = 0;
     while (i < ne) {

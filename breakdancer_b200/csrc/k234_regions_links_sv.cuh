@@ -14,7 +14,7 @@
 
 namespace bdk {
 
-enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NLINK, CNT_NEDGE, CNT_NDE, CNT_NROW, CNT_ERR, CNT_NREG_REAL, CNT_N };
+enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NLINK, CNT_NEDGE, CNT_NDE, CNT_NROW, CNT_ERR, CNT_NREG_REAL, CNT_K4_TICKET, CNT_NEMIT, CNT_N };
 constexpr uint32_t K3_ERR_DUPNAME = 1u;
 constexpr int GS_THREADS = 256;
 constexpr int GS_GRID = kNumSMs * 4;
@@ -123,42 +123,26 @@ __global__ void __launch_bounds__(GS_THREADS) k3_mate_join_kernel(const bdk_area
     }
 }
 
-// one link per pair whose two reads were both registered: key = (earlier region << 32 | later region)
+// one link per pair whose two reads were both registered: key = (earlier region << 32 | later region).
+// Links are aggregated straight into weighted edges in an open-addressing table (key -> count); the edge list is
+// never sorted -- everything downstream is order-independent until each component's edges are ranked.
+constexpr unsigned long long EDGE_EMPTY = ~0ull;
 __global__ void __launch_bounds__(GS_THREADS) k3_links_kernel(const int32_t* __restrict__ mate, const int32_t* __restrict__ read_region, uint32_t A,
-        unsigned long long* __restrict__ links, uint32_t* __restrict__ d_cnt) {
-    const unsigned FULL = 0xffffffffu;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t y0 = blockIdx.x * blockDim.x; y0 < A; y0 += stride) {   // warp-uniform trip count
-        const uint32_t y = y0 + threadIdx.x;
-        bool has = false; unsigned long long key = 0;
-        if (y < A) {
-            const int32_t x = mate[y];
-            if (x >= 0 && (uint32_t)x < y) {
-                const int32_t rx = read_region[x], ry = read_region[y];
-                if (rx >= 0 && ry >= 0) { has = true; key = ((unsigned long long)(uint32_t)rx << 32) | (uint32_t)ry; }
-            }
-        }
-        const unsigned m = __ballot_sync(FULL, has);
-        if (m) {
-            uint32_t base = 0;
-            const int leader = __ffs(m) - 1;
-            if ((int)lane_id() == leader) base = atomicAdd(d_cnt + CNT_NLINK, (uint32_t)__popc(m));
-            base = __shfl_sync(FULL, base, leader);
-            if (has) links[base + __popc(m & lanemask_lt())] = key;
+        unsigned long long* __restrict__ tkeys, uint32_t* __restrict__ tcnt, uint32_t mask) {
+    for (uint32_t y = blockIdx.x * blockDim.x + threadIdx.x; y < A; y += gridDim.x * blockDim.x) {
+        const int32_t x = mate[y];
+        if (x < 0 || (uint32_t)x >= y) continue;
+        const int32_t rx = read_region[x], ry = read_region[y];
+        if (rx < 0 || ry < 0) continue;
+        const unsigned long long key = ((unsigned long long)(uint32_t)rx << 32) | (uint32_t)ry;
+        uint32_t h = hash64(key) & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(tkeys + h, EDGE_EMPTY, key);
+            if (prev == EDGE_EMPTY || prev == key) { atomicAdd(tcnt + h, 1u); break; }
+            h = (h + 1) & mask;
         }
     }
 }
-
-struct HeadFlag {   // run heads of the sorted link keys
-    const unsigned long long* keys;
-    __device__ uint32_t operator()(uint32_t i, uint32_t) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
-};
-struct HeadOut {
-    const unsigned long long* keys; unsigned long long* edge_key; uint32_t* edge_start;
-    __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const {
-        if (v) { edge_key[inc - 1] = keys[i]; edge_start[inc - 1] = i; }
-    }
-};
 
 __device__ __forceinline__ int uf_find(int32_t* parent, int x) {
     for (;;) {
@@ -186,47 +170,60 @@ __global__ void __launch_bounds__(GS_THREADS) k3_init_regions_kernel(int32_t* __
     }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k3_union_kernel(const unsigned long long* __restrict__ edge_key, int32_t* __restrict__ parent,
-        const uint32_t* __restrict__ d_cnt) {
-    const uint32_t ne = d_cnt[CNT_NEDGE];
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-        const unsigned long long k = edge_key[e];
+__global__ void __launch_bounds__(GS_THREADS) k3_union_kernel(const unsigned long long* __restrict__ tkeys, uint32_t tsize, int32_t* __restrict__ parent) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = tkeys[e];
+        if (k == EDGE_EMPTY) continue;
         const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
         if (r0 != r1) uf_union(parent, r0, r1);
     }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k3_comp_count_kernel(const unsigned long long* __restrict__ edge_key, const uint32_t* __restrict__ edge_start,
-        int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ comp_strong, int32_t min_read_pair,
-        const uint32_t* __restrict__ d_cnt) {
-    const uint32_t ne = d_cnt[CNT_NEDGE], nl = d_cnt[CNT_NLINK];
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-        const unsigned long long k = edge_key[e];
+__global__ void __launch_bounds__(GS_THREADS) k3_comp_count_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
+        int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ comp_strong, int32_t min_read_pair) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = tkeys[e];
+        if (k == EDGE_EMPTY) continue;
         const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
         const int root = uf_find(parent, r0);
-        const uint32_t w = (e + 1 < ne ? edge_start[e + 1] : nl) - edge_start[e];
         atomicAdd(comp_ne + root, r0 == r1 ? 1u : 2u);
-        if ((int32_t)w >= min_read_pair) atomicAdd(comp_strong + root, 1u);
+        if ((int32_t)tcnt[e] >= min_read_pair) atomicAdd(comp_strong + root, 1u);
     }
 }
 
 struct LoadU32 { const uint32_t* p; __device__ uint32_t operator()(uint32_t i, uint32_t) const { return p[i]; } };
 struct ExclOut { uint32_t* o; __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const { o[i] = inc - v; } };
 
-__global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsigned long long* __restrict__ edge_key, const uint32_t* __restrict__ edge_start,
-        int32_t* __restrict__ parent, const uint32_t* __restrict__ de_off, uint32_t* __restrict__ comp_fill, DEdge* __restrict__ de, int32_t period,
-        const uint32_t* __restrict__ d_cnt) {
-    const uint32_t ne = d_cnt[CNT_NEDGE], nl = d_cnt[CNT_NLINK];
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
-        const unsigned long long k = edge_key[e];
+__global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
+        int32_t* __restrict__ parent, const uint32_t* __restrict__ de_off, uint32_t* __restrict__ comp_fill, DEdge* __restrict__ de,
+        int32_t* __restrict__ de_root, int32_t period) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = tkeys[e];
+        if (k == EDGE_EMPTY) continue;
         const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
         const int root = uf_find(parent, r0);
-        const int w = (int)((e + 1 < ne ? edge_start[e + 1] : nl) - edge_start[e]);
         const int win = r1 / period;          // r0 <= r1: the pair is counted when r1 is registered
         const uint32_t slot = de_off[root] + atomicAdd(comp_fill + root, r0 == r1 ? 1u : 2u);
-        DEdge d; d.win = win; d.src = r0; d.dst = r1; d.w = w; d.flags = 0;
-        de[slot] = d;
-        if (r0 != r1) { d.src = r1; d.dst = r0; de[slot + 1] = d; }
+        DEdge d; d.win = win; d.src = r0; d.dst = r1; d.w = (int)tcnt[e]; d.flags = 0;
+        de[slot] = d; de_root[slot] = root;
+        if (r0 != r1) { d.src = r1; d.dst = r0; de[slot + 1] = d; de_root[slot + 1] = root; }
+    }
+}
+
+// Rank sort of every component's directed edges by (win, src, dst), one thread per edge: the keys are unique, so
+// the number of smaller edges in the component is the edge's final position. Components with more than
+// DE_RANK_SORT_MAX edges are left to the walk (in-place heap sort).
+__global__ void __launch_bounds__(GS_THREADS) k3_rank_edges_kernel(const DEdge* __restrict__ de, const int32_t* __restrict__ de_root,
+        const uint32_t* __restrict__ de_off, const uint32_t* __restrict__ comp_ne, DEdge* __restrict__ de_sorted, const uint32_t* __restrict__ d_cnt) {
+    const uint32_t nde = d_cnt[CNT_NDE];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nde; t += gridDim.x * blockDim.x) {
+        const int root = de_root[t];
+        const uint32_t lo = de_off[root], n = comp_ne[root];
+        if (n > (uint32_t)DE_RANK_SORT_MAX) continue;
+        const DEdge x = de[t];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n; ++j) r += de_less(de[lo + j], x) ? 1u : 0u;
+        de_sorted[lo + r] = x;
     }
 }
 
@@ -236,14 +233,19 @@ __global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsi
 constexpr int K4_THREADS = 128;
 __global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K4Mut M, const uint32_t* __restrict__ comp_ne, const uint32_t* __restrict__ de_off,
         const uint32_t* __restrict__ row_off, DEdge* __restrict__ de, DEdge* __restrict__ de_sorted, int32_t* __restrict__ queue,
-        const bdk_summary_t* __restrict__ summary, const uint32_t* __restrict__ d_cnt) {
+        const bdk_summary_t* __restrict__ summary, const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ ticket) {
     const unsigned FULL = 0xffffffffu;
     S.nreg = (int32_t)d_cnt[CNT_NREG]; S.ncand = (int32_t)d_cnt[CNT_NCAND];
     S.covered_ref_len = summary->covered_ref_len;
     const WarpTeam T;
     const uint32_t lane = lane_id();
     const uint32_t nwarps = gridDim.x * (K4_THREADS / 32), wid = blockIdx.x * (K4_THREADS / 32) + (threadIdx.x >> 5);
-    for (uint32_t base = wid * 32; base < (uint32_t)S.nreg; base += nwarps * 32) {
+    (void)nwarps; (void)wid;
+    for (;;) {                                  // 32 regions at a time, handed out dynamically (components differ a lot in size)
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 1u) * 32u;
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= (uint32_t)S.nreg) break;
         const uint32_t r = base + lane;
         const uint32_t ne = r < (uint32_t)S.nreg ? comp_ne[r] : 0;
         unsigned m = __ballot_sync(FULL, ne != 0);
@@ -252,8 +254,79 @@ __global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K
             m &= m - 1;
             const uint32_t rr = base + src;
             const int n = (int)__shfl_sync(FULL, ne, src);
-            k4_component(T, S, M, de + de_off[rr], de_sorted + de_off[rr], n, queue + de_off[rr] + 2 * (size_t)rr, (int)row_off[rr]);
+            DEdge* e = n <= DE_RANK_SORT_MAX ? de_sorted + de_off[rr] : de_sort_team(T, de + de_off[rr], n, (DEdge*)nullptr);
+            k4_component(T, S, M, e, n, queue + de_off[rr] + 2 * (size_t)rr, (int)row_off[rr]);
         }
+    }
+}
+
+// ---- output order --------------------------------------------------------------------------------------
+// The reference prints window by window, BFS by BFS, and the calls of one BFS in the order they were made:
+// sort the emitted rows by (key = window << 32 | BFS start vertex, row slot). One CTA, bitonic sort in
+// shared memory (an SV table has thousands of rows, not millions).
+constexpr int K5_THREADS = 1024;
+constexpr int K5_SMEM_ROWS = 16384;                       // 12 bytes per row -> 192 KB
+__global__ void __launch_bounds__(K5_THREADS, 1) k5_order_smem_kernel(const uint64_t* __restrict__ emit_key, const uint32_t* __restrict__ emit_slot,
+        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ order_slot) {
+    extern __shared__ __align__(16) unsigned char s_k5[];
+    const uint32_t n = d_cnt[CNT_NEMIT];
+    uint32_t m = 1024; while (m < n) m <<= 1;            // n <= K5_SMEM_ROWS (checked by the host against the row-slot count)
+    uint64_t* key = reinterpret_cast<uint64_t*>(s_k5);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(key + m);
+    for (uint32_t i = threadIdx.x; i < m; i += K5_THREADS) {
+        key[i] = i < n ? emit_key[i] : ~0ull;
+        slot[i] = i < n ? emit_slot[i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += K5_THREADS) {
+                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;   // lo has bit j clear
+                const bool up = (lo & k) == 0;
+                const uint64_t ka = key[lo], kb = key[hi];
+                const uint32_t sa = slot[lo], sb = slot[hi];
+                const bool gt = ka > kb || (ka == kb && sa > sb);
+                if (gt == up) { key[lo] = kb; key[hi] = ka; slot[lo] = sb; slot[hi] = sa; }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += K5_THREADS) order_slot[i] = slot[i];
+}
+
+// large tables: order_slot comes from the device radix sort; this just seeds its value array
+__global__ void __launch_bounds__(GS_THREADS) k5_copy_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ n_ptr) {
+    const uint32_t n = *n_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// (key = slot, value = slot) pairs of the emitted rows, and the replacement of those keys by the rows' sort keys
+__global__ void __launch_bounds__(GS_THREADS) k5_slot_keys_kernel(const uint64_t* __restrict__ emit_key, const uint32_t* __restrict__ emit_slot,
+        const uint32_t* __restrict__ n_ptr, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t n = *n_ptr;
+    (void)emit_key;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { keys[i] = emit_slot[i]; vals[i] = emit_slot[i]; }
+}
+__global__ void __launch_bounds__(GS_THREADS) k5_row_keys_kernel(const uint64_t* __restrict__ row_key, const uint32_t* __restrict__ n_ptr,
+        unsigned long long* __restrict__ keys) {
+    const uint32_t n = *n_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) keys[i] = row_key[keys[i]];
+}
+
+struct RowPack {           // per-row arrays, by slot (K4 output) or by output position (what the host receives)
+    bdk_sv* rows; int32_t* lib_count; uint32_t* cn_count; float* cn;
+};
+__global__ void __launch_bounds__(GS_THREADS) k5_gather_kernel(RowPack in, RowPack out, const uint32_t* __restrict__ order_slot, int32_t* __restrict__ slot_order,
+        int nlib, int nkey, const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ n_out) {
+    const uint32_t n = d_cnt[CNT_NEMIT];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = order_slot[i];
+        bdk_sv r = in.rows[s];
+        r.order = (int32_t)i;
+        out.rows[i] = r;
+        slot_order[s] = (int32_t)i;
+        for (int l = 0; l < nlib; ++l) out.lib_count[(size_t)i * nlib + l] = in.lib_count[(size_t)s * nlib + l];
+        for (int k = 0; k < nkey; ++k) { out.cn_count[(size_t)i * nkey + k] = in.cn_count[(size_t)s * nkey + k]; out.cn[(size_t)i * nkey + k] = in.cn[(size_t)s * nkey + k]; }
     }
 }
 

@@ -209,6 +209,8 @@ int bdk_kernel_times(bdk_ctx* ctx, const char** names, float* ms, int* launches,
 uint64_t bdk_kernel_launches(bdk_ctx* ctx);
 /* Bytes the last bdk_push copied host -> device with the copy engine. */
 uint64_t bdk_h2d_bytes(bdk_ctx* ctx);
+/* Bytes the last bdk_finish copied device -> host (ordered SV table + summary). */
+uint64_t bdk_d2h_bytes(bdk_ctx* ctx);
 
 /* Pinned host memory helpers for callers without their own CUDA binding. */
 void* bdk_host_alloc(uint64_t bytes);

@@ -149,7 +149,9 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     std::vector<uint32_t> row_cn_count((size_t)(nrow_cap + 1) * nkey);
     std::vector<float> row_cn((size_t)(nrow_cap + 1) * nkey);
     std::vector<bdk_sv> rows(nrow_cap + 1);
-    std::vector<uint64_t> row_key(nrow_cap + 1, 0);
+    std::vector<uint64_t> row_key(nrow_cap + 1, 0), emit_key(nrow_cap + 1, 0);
+    std::vector<uint32_t> emit_slot(nrow_cap + 1, 0);
+    uint32_t emit_count = 0;
     K4Static KS;
     KS.ar = ar.data(); KS.read_region = read_region.data(); KS.read_cand = read_cand.data(); KS.mate = mate.data();
     KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.lib_mean = lib_mean.data();
@@ -161,12 +163,14 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     KM.alive = alive.data(); KM.freed = freed.data(); KM.deleted = deleted.data(); KM.sv_of_read = sv_of_read.data();
     KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
     KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
+    KM.emit_count = &emit_count; KM.emit_key = emit_key.data(); KM.emit_slot = emit_slot.data();
     std::vector<int32_t> queue;
     for (int r = 0; r < nreg; ++r) {
         if (!comp_ne[r]) continue;
         queue.assign(comp_ne[r] + 2, 0);
         std::vector<DEdge> scratch(comp_ne[r]);
-        int used = k4_component(SoloTeam(), KS, KM, de.data() + de_off[r], scratch.data(), comp_ne[r], queue.data(), row_off[r]);
+        DEdge* es = de_sort_team(SoloTeam(), de.data() + de_off[r], comp_ne[r], scratch.data());
+        int used = k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r]);
         if (used > comp_strong[r]) return -100;
     }
     // final order: stable by (window, BFS start vertex), slot order inside

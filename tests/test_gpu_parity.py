@@ -132,6 +132,15 @@ def test_gpu_segment_overflow_retry(monkeypatch):
     _check(b, cols, "tiny segments, single-key path")
 
 
+def test_gpu_large_table_ordering_path(monkeypatch):
+    """Output ordering of SV tables too large for the single-CTA shared-memory sort (forced): radix path."""
+    monkeypatch.setenv("BDK_K5_SMEM_ROWS", "0")
+    w = synth.generate(util.GENOME3, util.LIBS4, 200000, seed=31, anomaly_frac=0.05, somatic_frac=0.3)
+    b, cols, *_ = util.workload_bundle(w, api.Options(min_read_pair=1, score_threshold=-100))
+    ro = _check(b, cols, "radix ordering")
+    assert len(ro.table.sv) > 500
+
+
 def test_gpu_reset_and_reuse_is_idempotent():
     w = synth.generate(util.GENOME3, util.LIBS4, 80000, seed=8, anomaly_frac=0.04)
     b, cols, *_ = util.workload_bundle(w, api.Options())
