@@ -581,8 +581,12 @@ BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* 
         while (vi < j) {
             int v = e[vi].src;
             int vend = vi;
-            while (vend < j && e[vend].src == v) ++vend;
-            if (!(e[vi].flags & DE_VERASED)) {
+            bool live = false;          // v has an edge the BFS would follow; otherwise a BFS from v changes nothing
+            while (vend < j && e[vend].src == v) {
+                live = live || (!(e[vend].flags & DE_ERASED) && e[vend].w >= S.min_read_pair && !M.deleted[e[vend].dst]);
+                ++vend;
+            }
+            if (live && !(e[vi].flags & DE_VERASED) && !M.deleted[v]) {
                 // BFS from v; tails live in queue[qa..qb), newtails appended after
                 int qa = 0, qb = 0, qn;
                 T.sync();
@@ -599,9 +603,12 @@ BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* 
                         for (int k = ts; k < j && e[k].src == tail; ++k) {
                             if (e[k].flags & DE_ERASED) continue;
                             int s1 = e[k].dst, nlinks = e[k].w;
-                            const bool go = !(nlinks < S.min_read_pair || M.deleted[s1]);
+                            // An edge that is too weak or leads to a deleted region is erased without any other
+                            // effect, and meeting it again (from either side, in this window) would again have no
+                            // effect: it needs no mark. Only edges that are followed are erased both ways.
+                            if (nlinks < S.min_read_pair || M.deleted[s1]) continue;
                             int rq = -1;
-                            if (go && tail != s1) {                         // erase_edge(s1, tail)
+                            if (tail != s1) {                               // erase_edge(s1, tail)
                                 int rs = de_find_src(e, i, j, s1);
                                 if (rs >= 0)
                                     for (int q = rs; q < j && e[q].src == s1; ++q)
@@ -611,10 +618,9 @@ BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* 
                             if (lead) {
                                 e[k].flags |= DE_ERASED;
                                 if (rq >= 0) e[rq].flags |= DE_ERASED;
-                                if (go) queue[qn] = s1;                     // newtails.push_back(s1)
+                                queue[qn] = s1;                             // newtails.push_back(s1)
                             }
                             T.sync();
-                            if (!go) continue;
                             ++qn;
                             int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
                             k4_process_sv(T, S, M, a, tail != s1 ? b : -1, w, v, wi, row);
