@@ -1,0 +1,135 @@
+"""Full-size checks (BASELINE.json configs[1]: 50 M read pairs = 100 M records on one GPU) through the C ABI.
+
+The oracle needs minutes for this size, so the full-size run is pinned by size-independent properties:
+  * an independent vectorised (torch, on the device) evaluation of the classifier's decisions for this
+    workload must reproduce the summary statistics K1 produces (record count, anomalous reads, per-library
+    proper-pair count, flag histogram, covered reference length);
+  * the anomalous-read stream is exactly the set of records the vectorised classifier flags, in stream order;
+  * regions are sorted, disjoint runs of the anomalous stream that respect the window / -s rules;
+  * the SV table is invariant under how the records arrive (device-resident push, host pushes in ragged chunks
+    from pinned memory with zero-copy side columns) and under reset + re-run (idempotence);
+  * every SV row is supported by reads that K4 marked as consumed by exactly that row.
+The bit-exact comparison with the oracle at 2 M pairs of the same distribution is in test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from breakdancer_b200 import api, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+PAIRS = 50_000_000
+
+
+@pytest.fixture(scope="module")
+def big():
+    import torch
+    from breakdancer_b200 import synth_torch
+    dev = torch.device("cuda", 0)
+    cols = synth_torch.config2_device(PAIRS, seed=20260101, device=dev, tid=0)
+    lib = synth.LibSpec("lib1", "syn_chr1.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
+    wl = synth.Workload({}, [("chr1", synth_torch.CHR1_LEN)], [lib], ["rg1"], ["lib1"], ["syn_chr1.bam"])
+    cfg = api.BamConfig(text=wl.config_text())
+    bundle = api.ParamBundle(api.Options(), cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, 1)
+    ctx = api.Context(bundle, 0)
+    n = cols["pos"].numel()
+    ctx.push_soa(synth_torch.soa_of(cols), n, device=True)
+    summary = ctx.summary()
+    table = ctx.finish()
+    out = dict(cols=cols, n=n, bundle=bundle, ctx=ctx, summary=summary, table=table, regions=ctx.regions(), areads=ctx.areads(),
+               support=ctx.support(), lib=cfg.libs[0], opts=api.Options())
+    yield out
+    ctx.close()
+
+
+def test_fullsize_summary_matches_vectorised_classifier(big):
+    import torch
+    c, L, o, S = big["cols"], big["lib"], big["opts"], big["summary"]
+    a = c["isize"].abs()
+    af = a.to(torch.float32)
+    flag = c["flag"].to(torch.int32) & 0xFFFF
+    mapq_ok = c["mapq"].to(torch.int32) > o.min_map_qual
+    proper = (flag & 0x40F) == 0x3
+    base_ok = (flag & 0x40D) == 0x1
+    rr = (flag & 0x10) != 0
+    opposite = (((flag >> 4) ^ (flag >> 5)) & 1) != 0
+    assert bool(opposite.all()) and bool((c["tid"] == c["mtid"]).all())          # this workload: FR-oriented pairs on one chromosome
+    rf = (c["pos"] < c["mpos"]) == rr
+    large, small = af > L.uppercutoff, af < L.lowercutoff
+    cls_normal = ~rf & ~large & ~small
+    hist_large = int((mapq_ok & base_ok & ~rf & large).sum())
+    hist_small = int((mapq_ok & base_ok & ~rf & ~large & small).sum())
+    hist_rf = int((mapq_ok & base_ok & rf).sum())
+    kept = mapq_ok & base_ok & (a <= o.max_sd)
+    anom = kept & ~cls_normal
+    assert int(S.n_records) == big["n"]
+    assert int(S.n_anomalous) == int(anom.sum()) == len(big["areads"][0])
+    assert int(S.lib_read_count[0]) == int((mapq_ok & proper).sum())
+    h = list(S.read_counts_by_flag[0])
+    LARGE, SMALL, RF = (api.FLAG_NAMES.index(x) for x in ("ARP_LARGE_INSERT", "ARP_SMALL_INSERT", "ARP_RF"))
+    assert (h[LARGE], h[SMALL], h[RF]) == (hist_large, hist_small, hist_rf)
+    assert sum(h) == hist_large + hist_small + hist_rf
+    assert int(S.covered_ref_len) == int(c["pos"][-1]) - int(c["pos"][0])
+    # the compacted stream is exactly the flagged records, in stream order
+    idx = torch.nonzero(anom).squeeze(1).cpu().numpy()
+    ar = big["areads"][0]
+    assert np.array_equal(ar["record"], idx.astype(np.uint32))
+    assert np.array_equal(ar["pos"], c["pos"].cpu().numpy()[idx])
+    assert np.array_equal(ar["qid"], c["qid"].cpu().numpy()[idx].view(np.uint64))
+
+
+def test_fullsize_regions_are_sorted_runs_of_the_anomalous_stream(big):
+    ar, rr = big["areads"]
+    reg, S, o = big["regions"], big["summary"], big["opts"]
+    assert len(reg) > 100000
+    assert np.all(np.diff(ar["record"].astype(np.int64)) > 0) and np.all(np.diff(ar["pos"]) >= 0)
+    first, nreads = reg["first_read"], reg["n_reads"]
+    assert np.all(first[1:] >= first[:-1] + nreads[:-1])                       # disjoint, ascending
+    assert np.array_equal(reg["start"], ar["pos"][first]) and np.array_equal(reg["end"], ar["pos"][first + nreads - 1])
+    assert np.all(reg["end"] - reg["start"] > o.min_len)                        # -s rule
+    assert np.all(reg["fwd"] + reg["rev"] == nreads)
+    # reads of one region are never further apart than the window; consecutive regions' reads are (or a candidate in between collapsed)
+    gaps = np.diff(ar["pos"])
+    same = rr[1:] == rr[:-1]
+    assert np.all(gaps[same & (rr[1:] >= 0)] <= S.window)
+    member = np.repeat(np.arange(len(reg)), nreads)
+    assert np.array_equal(rr[np.concatenate([np.arange(f, f + k) for f, k in zip(first[:1000], nreads[:1000])])], member[:nreads[:1000].sum()])
+
+
+def test_fullsize_sv_rows_are_backed_by_consumed_reads(big):
+    t, sup = big["table"], big["support"]
+    ar, _ = big["areads"]
+    assert len(t.sv) > 5000
+    assert np.array_equal(t.sv["order"], np.arange(len(t.sv)))
+    assert np.all((t.sv["score"] > big["opts"].score_threshold) & (t.sv["score"] <= 99))
+    assert np.all(t.sv["num_pairs"] >= big["opts"].min_read_pair)
+    per_row = np.bincount(sup[sup >= 0], minlength=len(t.sv))
+    assert np.all(per_row >= 2 * t.sv["num_pairs"])                             # both reads of every supporting pair are marked
+    assert np.array_equal(t.lib_count[:, 0], t.sv["num_pairs"])                 # one library
+    # keys of the reference's output order: window ascending
+    assert np.all(np.diff(t.sv["window"]) >= 0)
+    # consumed reads come in mate pairs
+    q = ar["qid"][sup >= 0]
+    u, cnt = np.unique(q, return_counts=True)
+    assert np.all(cnt == 2)
+
+
+def test_fullsize_table_is_invariant_under_arrival_and_rerun(big):
+    from breakdancer_b200 import synth_torch
+    ctx, cols, n = big["ctx"], big["cols"], big["n"]
+    ref = big["table"]
+    ctx.reset()
+    ctx.push_soa(synth_torch.soa_of(cols), n, device=True)                      # idempotence: same context, same input
+    t2 = ctx.finish()
+    util.assert_tables_equal(ref, t2, "re-run")
+    hcols = synth_torch.to_pinned(cols)
+    ctx.reset()
+    edges = [0, 1, 4097, 30_000_001, 30_000_002, 77_777_777, n]                 # ragged host pushes, pinned (zero-copy side columns)
+    for a, b in zip(edges[:-1], edges[1:]):
+        soa = api.soa_from_pointers({k: hcols[k][a:b].data_ptr() for k in api.COLUMN_DTYPES})
+        ctx.push_soa(soa, b - a, device=False)
+    s3 = ctx.summary()
+    t3 = ctx.finish()
+    util.assert_tables_equal(ref, t3, "ragged pinned host pushes")
+    util.assert_summary_equal(big["summary"], s3, "ragged pinned host pushes")
