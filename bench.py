@@ -135,47 +135,85 @@ def reference_arm(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread (the timed
+    region of the default run is tens of milliseconds, too short for `nvidia-smi -lms`); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device):
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.stop_flag = False
+        self.nvml = None
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        self.bits = bits
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                r = int(get_reasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, r))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for l in self.proc.stdout:
-            self.lines.append((time.perf_counter(), l.strip()))
-
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, l in self.lines:
-            f = [x.strip() for x in l.split(",")]
+            f = [x.strip() for x in l.strip().split(",")]
             if len(f) < 8:
                 continue
             try:
-                if t0 <= ts <= t1 + 0.2:
-                    sm.append(float(f[1]))
-                mx = float(f[2])
+                r = sum(1 << i for i, v in enumerate(f[4:8]) if v.lower().startswith("active"))
+                self.samples.append((time.perf_counter(), float(f[1]), r))
+                self.max_mhz = float(f[2])
             except ValueError:
                 continue
-            if t0 <= ts <= t1 + 0.2:
-                for name, v in zip(self.NAMES, f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+        elif self.nvml:
+            self.t.join(timeout=1.0)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        inside = [(mhz, r) for ts, mhz, r in self.samples if t0 <= ts <= t1]
+        sm = sorted(m for m, _ in inside)
+        reasons = set()
+        for _, r in inside:
+            if self.nvml:
+                reasons |= {name for name, bit in self.bits.items() if r & bit}
+            else:
+                reasons |= {name for i, name in enumerate(self.NAMES) if r & (1 << i)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -253,6 +291,7 @@ def ours(args):
     barrier()
     t1 = time.perf_counter()
     n_sv = int(res.n_sv)
+    k4_sweeps = ctx.k4_sweeps()
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop(t0, t1) if sampler else None
     summ = ctx.summary()
@@ -300,6 +339,12 @@ def ours(args):
         e_ms = float(t.item())
     e2e_value = total_pairs / (e_ms / 1e3)
 
+    genome = None
+    if world > 1 and not args.no_genome:
+        del cols, hcols, dsoa, hsoa
+        torch.cuda.empty_cache()
+        genome = {"whole_genome": genome_mode(args, rank, world, local, dev, False), "ctx_only_t": genome_mode(args, rank, world, local, dev, True)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -330,9 +375,11 @@ def ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_ms, "h2d_bytes_per_step": h2d,
                     "zero_copy_side_columns": h2d < n * HOST_BYTES_PER_RECORD,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": gpu_launches,
+            "gpu_launches": gpu_launches, "k4_sweeps": k4_sweeps,
             "clocks": clocks,
         }
+        if genome:
+            line["one_job_all_gpus"] = genome
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_baseline(args.cpu_pairs, max(1, min(os.cpu_count() or 1, 32)))
@@ -342,6 +389,68 @@ def ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def genome_mode(args, rank, world, local, dev, transchr):
+    """ONE job over all N GPUs with whole-genome semantics (BASELINE configs[4]; -t: CTX-only): rank r holds
+    chromosome r of an N-chromosome genome (a contiguous slice of the globally sorted stream) in HBM; per step:
+    reset, K1 on the local slice, the NCCL exchanges, replicated K2/K3, component-sharded K4, rows gathered to
+    every rank. Returns the block rank 0 prints (max over ranks of the device time)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from breakdancer_b200 import api, synth, synth_torch
+    pairs = args.pairs
+    ctx_frac = 0.02 if transchr else 0.002
+    cols = synth_torch.genome_shard_device(pairs, 20260104, dev, rank, world, ctx_frac)
+    n = cols["pos"].numel()
+    lib = synth.LibSpec("lib1", "syn_genome.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
+    genome = [(f"chr{i + 1}", synth_torch.CHR1_LEN) for i in range(world)]
+    wl = synth.Workload({}, genome, [lib], ["rg1"], ["lib1"], ["syn_genome.bam"])
+    cfg = api.BamConfig(text=wl.config_text())
+    opts = api.Options(transchr_rearrange=bool(transchr))
+    bundle = api.ParamBundle(opts, cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, world)
+    ctx = api.Context(bundle, local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.comm_init_from_dist()
+    dsoa = synth_torch.soa_of(cols)
+
+    def step():
+        ctx.reset()
+        ctx.push_soa(dsoa, n, device=True)
+        return ctx.finish_raw()
+
+    for _ in range(3):
+        res = step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 5))
+    kt = {}
+    e0.record()
+    for _ in range(steps):
+        res = step()
+        for k, v in ctx.kernel_times().items():
+            kt[k] = kt.get(k, 0.0) + v["ms"] / steps
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    summ = ctx.summary()
+    t = torch.tensor([ms] + [kt.get(k, 0.0) for k in ("k1_classify", "comm_gather_reads", "k2_regions", "k3_links_graph", "k4_sv_score", "comm_gather_rows", "d2h_results")],
+                     device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([n // 2, ctx.comm_bytes()], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    out = {"value": float(tot[0].item()) / (float(t[0].item()) / 1e3), "unit": UNIT, "ms_per_step": float(t[0].item()),
+           "workload": f"one job, {world} chromosomes x {pairs / 1e6:g}M pairs (config-2 records + {ctx_frac * 100:g}% inter-chromosomal pairs)"
+                       + (", -t" if transchr else ", whole-genome semantics"),
+           "k4_sweeps": ctx.k4_sweeps(), "records_total": int(summ.n_records), "anomalous_reads_total": int(summ.n_anomalous), "sv_calls": int(res.n_sv),
+           "nvlink_bytes_received_per_step_all_ranks": float(tot[1].item()),
+           "max_over_ranks_ms": dict(zip(["k1_classify", "comm_gather_reads", "k2_regions", "k3_links_graph", "k4_sv_score", "comm_gather_rows", "d2h_results"],
+                                         [float(x) for x in t[1:].tolist()]))}
+    ctx.close()
+    del cols
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -354,6 +463,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=6_000_000, help="total read pairs of the CPU baseline sample")
     ap.add_argument("--ref-pairs", type=int, default=400_000, help="read pairs per process and step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-genome", action="store_true", help="N > 1: skip the one-job-over-all-GPUs (NCCL exchange) measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -140,6 +140,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdk_host_alloc": (vp, [u64]),
         "bdk_host_free": (None, [vp]),
         "bdk_set_comm": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "bdk_comm_unique_id": (C.c_int, [vp, C.c_int]),
+        "bdk_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "bdk_comm_bytes": (u64, [vp]),
+        "bdk_k4_sweeps": (C.c_uint32, [vp]),
         "bdk_poisson_logsf": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(C.c_double), u64]),
         "bdk_version": (C.c_char_p, []),
         "bdh_config_parse": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
@@ -412,6 +416,27 @@ class Context:
         """Bytes the last finish() copied device -> host."""
         return int(self._L.bdk_d2h_bytes(self._h))
 
+    # ---- multi-GPU whole-genome mode (include/bdk.h: bdk_comm_*) ---------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """Create this context's NCCL communicator from the 128-byte id rank 0 obtained with comm_unique_id()."""
+        _prefer_bundled_nccl()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._L.bdk_comm_init(self._h, C.cast(buf, C.c_void_p), rank, nranks), "bdk_comm_init")
+
+    def comm_init_from_dist(self):
+        """Same, with torch.distributed (any backend) carrying the id from rank 0 to the other ranks."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], rank, world)
+
+    def comm_bytes(self) -> int:
+        return int(self._L.bdk_comm_bytes(self._h))
+
+    def k4_sweeps(self) -> int:
+        return int(self._L.bdk_k4_sweeps(self._h))
+
     def poisson_logsf(self, lam: np.ndarray, k: np.ndarray) -> np.ndarray:
         lam = np.ascontiguousarray(lam, np.float64)
         k = np.ascontiguousarray(k, np.int32)
@@ -428,6 +453,35 @@ class Context:
 
     def __del__(self):
         self.close()
+
+
+def _prefer_bundled_nccl():
+    """libbdk dlopens NCCL by soname at the first communicator call. In a process that will also import torch the
+    library must be the one torch was linked against (an older system libnccl.so.2 loaded first would be picked up by
+    torch's own DT_NEEDED lookup and miss symbols), so point BDK_NCCL_LIB at the wheel's copy when there is one."""
+    if os.environ.get("BDK_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            p = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                os.environ["BDK_NCCL_LIB"] = p
+                return
+    except Exception:
+        pass
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 calls this and distributes it)."""
+    _prefer_bundled_nccl()
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.bdk_comm_unique_id(C.cast(buf, C.c_void_p), 128)
+    if rc != 0:
+        raise BdkError(f"bdk_comm_unique_id failed ({rc}): {L.bdk_last_error(None).decode()}")
+    return buf.raw
 
 
 def _copy_array(ptr: Optional[int], n: int, dtype: np.dtype) -> np.ndarray:

@@ -17,6 +17,7 @@
 
 #include "../../include/bdk.h"
 #include "bdk_finalize.h"
+#include "comm.cuh"
 #include "k1_classify.cuh"
 #include "k234_regions_links_sv.cuh"
 #include "scan_sort.cuh"
@@ -42,9 +43,10 @@ struct StageTimer {
     bool pending = false;
 };
 
-enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_HOST, T_N };
+enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_HOST, T_COMM1, T_COMM2, T_N };
 const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_span", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results",
-                                "host_order_rows"};   // the last one is host wall time (output ordering), not a device timer
+                                "host_order_rows",    // host wall time (output ordering), not a device timer
+                                "comm_gather_reads", "comm_gather_rows"};   // multi-GPU exchanges (NCCL over NVLink)
 
 }  // namespace
 
@@ -101,6 +103,17 @@ struct bdk_ctx {
     std::vector<int32_t> h_read_region, h_sv_of_read;
     uint32_t h_cnt[CNT_N] = {0};
     StageTimer timers[T_N];
+    // multi-GPU whole-genome mode (comm.cuh)
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false, exchanged = false;
+    int rank = 0, nranks = 1;
+    uint32_t A_local = 0;             // anomalous reads of this rank's slice (c->A becomes the global count)
+    uint64_t comm_bytes = 0;          // bytes this rank received in the exchanges of the last job
+    DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff, d_cuts;
+    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
+    uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
+    int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
+    std::vector<uint32_t> h_cuts;     // [2][nranks + 1] vertex / row-slot cuts of the last bdk_finish
 };
 
 namespace {
@@ -144,7 +157,7 @@ void tcollect(bdk_ctx* c) {
 }
 
 int reset_job(bdk_ctx* c) {
-    c->n_records = 0; c->A = 0;
+    c->n_records = 0; c->A = 0; c->A_local = 0; c->exchanged = false; c->comm_bytes = 0;
     c->finished = false; c->summary_ready = false; c->launches = 0;
     // accumulators: counts 0, first = ~0, last = 0
     CU(cudaMemsetAsync(c->d_acc.p, 0, c->acc_bytes, c->stream));
@@ -236,6 +249,7 @@ int grow_segments(bdk_ctx* c, uint64_t want) {
 template <class RunFn>
 int push_common(bdk_ctx* c, uint64_t n, uint64_t max_launch, RunFn run) {
     if (c->finished) return fail(c, BDK_ERR_STATE, "bdk_push after bdk_finish (call bdk_reset first)");
+    if (c->exchanged) return fail(c, BDK_ERR_STATE, "bdk_push after the collective bdk_summary / bdk_finish of a multi-GPU job (call bdk_reset first)");
     if (n == 0) return 0;
     if (c->n_records + n > 0xffffffffull) return fail(c, BDK_ERR_ARG, "more than 2^32 records in one context");
     int rc = grow_tiles(c, std::min(n, max_launch));
@@ -267,6 +281,90 @@ int push_common(bdk_ctx* c, uint64_t n, uint64_t max_launch, RunFn run) {
     return fail(c, BDK_ERR_NOMEM, "output overflow persisted");
 }
 
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) return fail(c, BDK_ERR_NCCL, "%s failed: %s", #call, nc->GetErrorString(r_)); \
+    } while (0)
+
+// in-place all-gather of per-rank ranges of one array: rank p owns elements [cut[p], cut[p + 1]) of `elt` bytes each
+int gather_ranges(bdk_ctx* c, NcclApi* nc, void* base, size_t elt, const uint64_t* cut) {
+    for (int p = 0; p < c->nranks; ++p) {
+        const uint64_t cnt = cut[p + 1] - cut[p];
+        if (!cnt) continue;
+        char* ptr = (char*)base + cut[p] * elt;
+        NC(nc->Broadcast(ptr, ptr, cnt * elt, ncclUint8, p, c->comm, c->stream));
+        if (p != c->rank) c->comm_bytes += cnt * elt;
+    }
+    return 0;
+}
+
+// Exchange 1 (comm.cuh): totals, pass-1 accumulators, and the anomalous-read streams of all ranks. Collective.
+int comm_exchange(bdk_ctx* c) {
+    if (!c->comm || c->exchanged) return 0;
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+    const int nkey = c->nkey, ncomp = 1 + nkey, W = ncomp + 2, N = c->nranks;
+    char* acc = (char*)c->d_acc.p;
+    tstart(c, T_COMM1);
+    // totals of every rank: anomalous reads, kept proper pairs per key, records
+    ENS(c->d_hdr, (size_t)W * 4); ENS(c->d_hdr_all, (size_t)N * W * 4); ENS(c->d_koff, (size_t)nkey * 4);
+    std::vector<uint32_t> hdr(W, 0), all((size_t)N * W, 0);
+    hdr[0] = c->A; hdr[ncomp] = (uint32_t)c->n_records; hdr[ncomp + 1] = (uint32_t)(c->n_records >> 32);
+    CU(cudaMemcpyAsync(c->d_hdr.p, hdr.data(), (size_t)W * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_hdr.as<uint32_t>() + 1, acc + c->off_cursor + 4, (size_t)nkey * 4, cudaMemcpyDeviceToDevice, c->stream));
+    NC(nc->AllGather(c->d_hdr.p, c->d_hdr_all.p, W, ncclUint32, c->comm, c->stream));
+    CU(cudaMemcpyAsync(all.data(), c->d_hdr_all.p, (size_t)N * W * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> a_cut(N + 1, 0);
+    std::vector<uint32_t> koff(nkey, 0);
+    uint64_t rec_off = 0, rec_tot = 0;
+    for (int p = 0; p < N; ++p) {
+        const uint32_t* h = all.data() + (size_t)p * W;
+        a_cut[p + 1] = a_cut[p] + h[0];
+        const uint64_t nrec = (uint64_t)h[ncomp] | ((uint64_t)h[ncomp + 1] << 32);
+        if (p < c->rank) { rec_off += nrec; for (int k = 0; k < nkey; ++k) koff[k] += h[1 + k]; }
+        rec_tot += nrec;
+    }
+    if (rec_tot > 0xffffffffull) return fail(c, BDK_ERR_ARG, "more than 2^32 records in one multi-GPU job");
+    const uint64_t A_tot = a_cut[N];
+    if (A_tot > 0xfffffff0ull) return fail(c, BDK_ERR_NOMEM, "more than 2^32 anomalous reads in one multi-GPU job");
+    // pass-1 accumulators: global record indices in the first / last keys, then sum / min / max over the ranks
+    const uint32_t nbt = (uint32_t)((size_t)c->P.nbam * c->P.ntid);
+    unsigned long long* first = (unsigned long long*)(acc + c->off_first);
+    unsigned long long* last = (unsigned long long*)(acc + c->off_last);
+    comm_rebase_span_kernel<<<std::max(1u, std::min(div_up(nbt, 256u), 1184u)), 256, 0, c->stream>>>(first, last, nbt, (uint32_t)rec_off);
+    NC(nc->GroupStart());
+    NC(nc->AllReduce(acc, acc, (size_t)c->P.nrg, ncclUint64, ncclSum, c->comm, c->stream));
+    NC(nc->AllReduce(first, first, nbt, ncclUint64, ncclMin, c->comm, c->stream));
+    NC(nc->AllReduce(last, last, nbt, ncclUint64, ncclMax, c->comm, c->stream));
+    NC(nc->AllReduce(acc + c->off_hist, acc + c->off_hist, (size_t)c->P.nlib * BDK_NUM_FLAGS, ncclUint32, ncclSum, c->comm, c->stream));
+    NC(nc->GroupEnd());
+    // the global anomalous-read stream: every rank writes its rebased slice into place, the slices are all-gathered
+    ENS(c->d_ar_g, (A_tot + 2) * sizeof(bdk_aread)); ENS(c->d_P_g, (A_tot + 2) * 4 * nkey);
+    CU(cudaMemcpyAsync(c->d_koff.p, koff.data(), (size_t)nkey * 4, cudaMemcpyHostToDevice, c->stream));
+    if (c->A)
+        comm_rebase_stream_kernel<<<GS_GRID, GS_THREADS, 0, c->stream>>>(c->d_ar.as<bdk_aread>(), c->d_P.as<uint32_t>(), c->A, nkey, (uint32_t)rec_off,
+            c->d_koff.as<uint32_t>(), c->d_ar_g.as<bdk_aread>() + a_cut[c->rank], c->d_P_g.as<uint32_t>() + a_cut[c->rank] * nkey);
+    CU(cudaGetLastError());
+    NC(nc->GroupStart());
+    int rc = gather_ranges(c, nc, c->d_ar_g.p, sizeof(bdk_aread), a_cut.data());
+    if (!rc) rc = gather_ranges(c, nc, c->d_P_g.p, (size_t)4 * nkey, a_cut.data());
+    NC(nc->GroupEnd());
+    if (rc) return rc;
+    tstop(c, T_COMM1);
+    c->launches += 2;
+    CU(cudaStreamSynchronize(c->stream));   // koff / hdr are host stack data; also surfaces asynchronous NCCL errors here
+    tcollect(c);
+    std::swap(c->d_ar, c->d_ar_g); std::swap(c->d_P, c->d_P_g);
+    c->out_cap = (uint32_t)std::min<uint64_t>({c->d_ar.cap / sizeof(bdk_aread), c->d_P.cap / ((size_t)4 * nkey), 0xfffffff0ull});
+    c->A_local = c->A; c->A = (uint32_t)A_tot;
+    c->n_records = rec_tot;
+    c->exchanged = true;
+    c->summary_ready = false;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -290,7 +388,9 @@ void bdk_destroy(bdk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
+    if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
+    c->comm = nullptr;
+    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt, &c->d_de_root,
@@ -418,6 +518,13 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         const size_t ncomp = 1 + (size_t)c->nkey, grid = (size_t)kNumSMs * c->k1_blocks_per_sm;
         CUC(cudaMalloc(&c->d_seg_cnt.p, grid * ncomp * 4)); c->d_seg_cnt.cap = grid * ncomp * 4;
         CUC(cudaMalloc(&c->d_carry_out.p, ncomp * 4)); c->d_carry_out.cap = ncomp * 4;
+        {
+            int k4bps = 0, nsm = kNumSMs;
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k4bps, k4_sweeps_kernel, K4_THREADS, 0));
+            CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+            c->k4_grid_max = std::max(1, k4bps) * nsm;
+            CUC(cudaMalloc(&c->d_k4sync.p, 64)); c->d_k4sync.cap = 64;
+        }
         if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
         CUC(cudaFuncSetAttribute(k5_order_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM_ROWS * 12));
         if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
@@ -512,6 +619,7 @@ int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
 }
 
 static int run_finalize(bdk_ctx* c) {
+    if (c->comm && !c->exchanged) { int rc = comm_exchange(c); if (rc) return rc; }
     if (c->summary_ready) return 0;
     CU(cudaMemsetAsync(c->d_cnt.p, 0, CNT_N * 4, c->stream));
     CU(cudaMemcpyAsync(c->d_cnt.as<uint32_t>() + CNT_A, &c->A, 4, cudaMemcpyHostToDevice, c->stream));
@@ -545,12 +653,14 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     CU(cudaSetDevice(c->device));
     memset(out, 0, sizeof(*out));
     out->nkey = c->nkey;
-    const uint32_t A = c->A;
     const int nkey = c->nkey, nlib = c->P.nlib;
     cudaStream_t st = c->stream;
     uint32_t* d_cnt = c->d_cnt.as<uint32_t>();
-    int rc = run_finalize(c);
+    int rc = run_finalize(c);     // multi-GPU: exchange 1 happens here, c->A becomes the global count
     if (rc) return rc;
+    const uint32_t A = c->A;
+    NcclApi* nc = c->comm ? nccl_api() : nullptr;
+    const int N = c->nranks;
     c->h_sv.clear(); c->h_lib_count.clear(); c->h_cn_count.clear(); c->h_copy_number.clear();
     c->h_regions.clear(); c->h_areads.clear(); c->h_read_region.clear(); c->h_sv_of_read.clear();
     memset(c->h_cnt, 0, sizeof(c->h_cnt));
@@ -572,6 +682,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     const size_t L1 = (size_t)A / 2 + 2;
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
+    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8);
     ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
@@ -605,21 +716,30 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
     k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
     k3_init_regions_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(), c->d_comp_strong.as<uint32_t>(),
-                                                           c->d_comp_fill.as<uint32_t>(), c->d_deleted.as<uint8_t>(), d_cnt);
-    k3_union_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, esize, c->d_parent.as<int32_t>());
+                                                           c->d_comp_fill.as<uint32_t>(), c->d_deleted.as<uint8_t>(), c->d_win_range.as<int2>(), d_cnt);
+    k3_union_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->P.min_read_pair);
+    k3_flatten_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_parent.as<int32_t>(), d_cnt);
     k3_comp_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(),
                                                          c->d_comp_strong.as<uint32_t>(), c->P.min_read_pair);
     device_scan(st, LoadU32{c->d_comp_ne.as<uint32_t>()}, ExclOut{c->d_de_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NDE, 0, ssc);
     device_scan(st, LoadU32{c->d_comp_strong.as<uint32_t>()}, ExclOut{c->d_row_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NROW, 0, ssc);
     k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_de_off.as<uint32_t>(),
-                                                            c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->period);
+                                                            c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->period, c->d_win_range.as<int2>());
     k3_rank_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->d_de_off.as<uint32_t>(),
                                                          c->d_comp_ne.as<uint32_t>(), c->d_de2.as<DEdge>(), d_cnt);
-    c->launches += 2 + 3 + 3 + 3 + 2;   // join, links, init/union/count, 2 scans, scatter, rank
+    c->launches += 2 + 4 + 3 + 3 + 2;   // join, links, init/union/flatten/count, 2 scans, scatter, rank
     tstop(c, T_K3);
     CU(cudaGetLastError());
+    c->h_cuts.assign(2 * (size_t)(N + 1), 0);
+    if (c->comm) {   // which components this GPU walks, and which row slots they fill
+        ENS(c->d_cuts, 2 * (size_t)(N + 1) * 4);
+        comm_cuts_kernel<<<1, std::max(32, N + 1), 0, st>>>(c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(), d_cnt, N, c->d_cuts.as<uint32_t>());
+        c->launches += 1;
+        CU(cudaMemcpyAsync(c->h_cuts.data(), c->d_cuts.p, 2 * (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaMemcpyAsync(c->h_cnt, d_cnt, CNT_N * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    tcollect(c);
     if (c->h_cnt[CNT_ERR] & K3_ERR_DUPNAME)
         return fail(c, BDK_ERR_DATA, "a read-name key occurs more than twice among the anomalous reads");
     const uint32_t nrow = c->h_cnt[CNT_NROW], nreg = c->h_cnt[CNT_NREG];
@@ -654,29 +774,90 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     S.A = A; S.nreg = 0; S.ncand = 0; S.period = c->period; S.nkey = nkey; S.nlib = nlib;
     S.chr_restricted = c->P.chr_restricted; S.min_read_pair = c->P.min_read_pair; S.score_threshold = c->P.score_threshold;
     S.fisher = c->P.fisher; S.covered_ref_len = 0;
+    S.root_of = c->d_parent.as<int32_t>(); S.del_prev = c->d_del_prev.as<int32_t>(); S.rerun = 0;
     K4Mut M;
     M.alive = c->d_alive.as<uint8_t>(); M.freed = c->d_freed.as<uint8_t>(); M.deleted = c->d_deleted.as<uint8_t>();
-    M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = (bdk_sv*)(dp + o_rows);
+    M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = (bdk_sv*)(dp + o_rows); M.del_cur = c->d_del_cur.as<int32_t>();
     M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + w_span);
     M.row_cn_count = (uint32_t*)(dp + o_cc); M.row_cn = (float*)(dp + o_cn);
     M.row_emit = (uint8_t*)(dp + w_emit); M.row_key = (uint64_t*)(dp + w_key);
-    M.emit_count = d_cnt + CNT_NEMIT; M.emit_key = (uint64_t*)(dp + w_ekey); M.emit_slot = (uint32_t*)(dp + w_eslot);
+    uint64_t* emit_key = (uint64_t*)(dp + w_ekey); uint32_t* emit_slot = (uint32_t*)(dp + w_eslot);
     tstart(c, T_K4);
+    const uint32_t v_lo = c->comm ? c->h_cuts[c->rank] : 0u, v_hi = c->comm ? c->h_cuts[c->rank + 1] : 0xffffffffu;
+    c->k4_sweeps = 0;
+    bool sweeps_on_device = false;
     if (nrow || c->h_cnt[CNT_NDE]) {
-        const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(nreg, 32 * (K4_THREADS / 32)), (uint64_t)kNumSMs * 16);
-        k4_components_kernel<<<std::max(1u, grid), K4_THREADS, 0, st>>>(S, M, c->d_comp_ne.as<uint32_t>(), c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(),
-                                                                  c->d_de.as<DEdge>(), c->d_de2.as<DEdge>(), c->d_queue.as<int32_t>(), c->d_summary.as<bdk_summary_t>(), d_cnt, d_cnt + CNT_K4_TICKET);
-        c->launches += 1;
+        // Sweeps over the components (bdk_logic.h, K4Static): the first walks all of them against an empty table of
+        // deletion times; each later one walks again the components that looked, across an edge that is never followed, at a
+        // region whose deletion time changed. Stable table = the reference's sequential result.
+        CU(cudaMemsetAsync(c->d_del_prev.p, 0x7f, (size_t)nreg * 4, st));
+        CU(cudaMemsetAsync(c->d_del_cur.p, 0x7f, (size_t)nreg * 4, st));
+        CU(cudaMemsetAsync(c->d_dirty.p, 0, (size_t)nreg * 4, st));
+        K4Graph G;
+        G.comp_ne = c->d_comp_ne.as<uint32_t>(); G.comp_strong = c->d_comp_strong.as<uint32_t>(); G.de_off = c->d_de_off.as<uint32_t>();
+        G.row_off = c->d_row_off.as<uint32_t>(); G.de = c->d_de.as<DEdge>(); G.de_sorted = c->d_de2.as<DEdge>(); G.de_root = c->d_de_root.as<int32_t>();
+        G.queue = c->d_queue.as<int32_t>(); G.stamp = c->d_dirty.as<uint32_t>(); G.del_prev = c->d_del_prev.as<int32_t>(); G.win_range = c->d_win_range.as<int2>();
+        G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi;
+        const bool mine = v_lo < std::min(v_hi, nreg);
+        const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
+        if (!c->comm || N == 1) {   // one persistent cooperative kernel, grid-wide barriers between the phases
+            uint32_t* sync = c->d_k4sync.as<uint32_t>();
+            CU(cudaMemsetAsync(sync, 0, 32, st));
+            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->k4_grid_max));
+            void* args[] = {&S, &M, &G, &sync};
+            CU(cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, 0, st));
+            c->launches += 1;
+            sweeps_on_device = true;
+        } else {                    // one launch per phase; the owners' deletion times go to every rank in between
+            if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)kNumSMs * 16));
+            for (uint32_t sweep = 0;; ++sweep) {
+                if (sweep > 100000) return fail(c, BDK_ERR_STATE, "connection walk did not reach a fixed point");
+                if (sweep) CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 4, st));
+                if (mine) { k4_components_kernel<<<grid, K4_THREADS, 0, st>>>(S, M, G, sweep, d_cnt + CNT_K4_TICKET); c->launches += 1; }
+                NC(nc->AllReduce(c->d_del_cur.p, c->d_del_cur.p, nreg, ncclInt32, ncclMin, c->comm, st));   // K4_NEVER where not the owner
+                c->comm_bytes += (uint64_t)nreg * 4;
+                CU(cudaMemsetAsync(d_cnt + CNT_NDIRTY, 0, 4, st));
+                k4_mark_dirty_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G, sweep, d_cnt + CNT_NDIRTY);
+                k4_next_sweep_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G, sweep);
+                c->launches += 2;
+                uint32_t ndirty = 0;
+                CU(cudaMemcpyAsync(&ndirty, d_cnt + CNT_NDIRTY, 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                c->k4_sweeps = sweep + 1;
+                if (!ndirty) break;
+            }
+        }
     }
     tstop(c, T_K4);
     CU(cudaGetLastError());
+    if (c->comm && nrow) {   // exchange 2: every rank's row slots (contiguous per rank) to every rank
+        if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+        tstart(c, T_COMM2);
+        std::vector<uint64_t> s_cut(N + 1);
+        for (int p = 0; p <= N; ++p) s_cut[p] = c->h_cuts[(size_t)N + 1 + p];
+        NC(nc->GroupStart());
+        int rc2 = gather_ranges(c, nc, M.rows, sizeof(bdk_sv), s_cut.data());
+        if (!rc2) rc2 = gather_ranges(c, nc, M.row_lib_count, (size_t)4 * nlib, s_cut.data());
+        if (!rc2) rc2 = gather_ranges(c, nc, M.row_cn_count, (size_t)4 * nkey, s_cut.data());
+        if (!rc2) rc2 = gather_ranges(c, nc, M.row_cn, (size_t)4 * nkey, s_cut.data());
+        if (!rc2) rc2 = gather_ranges(c, nc, M.row_emit, 1, s_cut.data());
+        if (!rc2) rc2 = gather_ranges(c, nc, M.row_key, 8, s_cut.data());
+        NC(nc->GroupEnd());
+        if (rc2) return rc2;
+        tstop(c, T_COMM2);
+    }
 
     // ---- output order + results to the host -----------------------------------------------------------
     tstart(c, T_D2H);
+    // the emitted rows of the whole table, from the per-slot flags (arrival order does not matter: the ordering sorts by
+    // (window, BFS start vertex, slot))
+    comm_emit_list_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(M.row_emit, M.row_key, d_cnt, d_cnt + CNT_NEMIT, emit_key, emit_slot);
+    c->launches += 1;
     uint32_t* order_slot = (uint32_t*)(dp + w_order);
     if (nrow <= (uint32_t)c->k5_smem_rows) {
         uint32_t m = 1024; while (m < nrow) m <<= 1;
-        k5_order_smem_kernel<<<1, K5_THREADS, (size_t)m * 12, st>>>(M.emit_key, M.emit_slot, d_cnt, order_slot);
+        k5_order_smem_kernel<<<1, K5_THREADS, (size_t)m * 12, st>>>(emit_key, emit_slot, d_cnt, order_slot);
         c->launches += 1;
     } else {   // large tables: stable LSD radix sort by slot, BFS start vertex, window
         int sbits = 1; while ((1ull << sbits) < (uint64_t)nrow + 1) ++sbits;
@@ -686,7 +867,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         // first (key = slot, value = index), then (key = row key, value = slot) stably
         unsigned long long* k1 = (unsigned long long*)(dp + w_tmpk);
         uint32_t* v1 = (uint32_t*)(dp + w_tmpv);
-        k5_slot_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(M.emit_key, M.emit_slot, d_cnt + CNT_NEMIT, k1, v1);
+        k5_slot_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(emit_key, emit_slot, d_cnt + CNT_NEMIT, k1, v1);
         unsigned long long* kk = k1; uint32_t* vv = v1;
         ENS(c->d_sort_k, R1 * 8); ENS(c->d_sort_v, R1 * 4);
         SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_sort_k.as<unsigned long long>(), c->d_sort_v.as<uint32_t>()};
@@ -703,6 +884,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     c->launches += 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(op + o_sum, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToDevice, st));
+    if (sweeps_on_device) CU(cudaMemcpyAsync(op + o_n + 4, c->d_k4sync.as<uint32_t>() + 5, 4, cudaMemcpyDeviceToDevice, st));
     char* hp = (char*)c->h_pack;
     CU(cudaMemcpyAsync(hp, op, out_bytes, cudaMemcpyDeviceToHost, st));
     c->d2h_bytes = out_bytes;
@@ -711,6 +893,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     tcollect(c);
     memcpy(&c->h_summary, hp + o_sum, sizeof(bdk_summary_t));
     const size_t ns = *(const uint32_t*)(hp + o_n);
+    if (sweeps_on_device) c->k4_sweeps = *(const uint32_t*)(hp + o_n + 4);
     c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet
     c->n_slots = nrow;
     c->finished = true;
@@ -756,6 +939,12 @@ int bdk_get_support(bdk_ctx* c, const int32_t** sv_of_read, uint64_t* n) {
     CU(cudaSetDevice(c->device));
     if (c->h_sv_of_read.size() == 1 && c->h_sv_of_read[0] == -2) {
         std::vector<int32_t> slots(c->A), slot_order(c->n_slots);
+        if (c->comm && c->A) {   // every read was consumed on the rank that walked its component (-1 elsewhere). Collective.
+            NcclApi* nc = nccl_api();
+            if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+            NC(nc->AllReduce(c->d_sv_of_read.p, c->d_sv_of_read.p, c->A, ncclInt32, ncclMax, c->comm, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
         if (c->A) CU(cudaMemcpy(slots.data(), c->d_sv_of_read.p, (size_t)c->A * 4, cudaMemcpyDeviceToHost));
         if (c->n_slots) CU(cudaMemcpy(slot_order.data(), c->d_slot_order.p, (size_t)c->n_slots * 4, cudaMemcpyDeviceToHost));
         for (auto& s : slots) s = (s >= 0 && (size_t)s < slot_order.size()) ? slot_order[s] : -1;
@@ -777,10 +966,46 @@ uint64_t bdk_kernel_launches(bdk_ctx* c) { return c ? c->launches : 0; }
 uint64_t bdk_h2d_bytes(bdk_ctx* c) { return c ? c->h2d_bytes : 0; }
 uint64_t bdk_d2h_bytes(bdk_ctx* c) { return c ? c->d2h_bytes : 0; }
 
-int bdk_set_comm(bdk_ctx* c, void*, int, int) {
-    if (!c) return BDK_ERR_ARG;
-    return fail(c, BDK_ERR_ARG, "inter-chromosomal mate-link exchange across GPUs is not implemented yet; shard by chromosome (one context per chromosome set)");
+static int attach_comm(bdk_ctx* c, ncclComm_t comm, int rank, int nranks, bool owned) {
+    if (c->n_records || c->exchanged) return fail(c, BDK_ERR_STATE, "attach the communicator before the first bdk_push of a job");
+    if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
+    c->comm = comm; c->comm_owned = owned; c->rank = comm ? rank : 0; c->nranks = comm ? nranks : 1;
+    return 0;
 }
+
+int bdk_set_comm(bdk_ctx* c, void* nccl_comm, int rank, int nranks) {
+    if (!c) return BDK_ERR_ARG;
+    if (nccl_comm && (nranks < 1 || rank < 0 || rank >= nranks || nranks > 1024)) return fail(c, BDK_ERR_ARG, "bad rank %d / nranks %d", rank, nranks);
+    if (nccl_comm && !nccl_api()) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+    return attach_comm(c, (ncclComm_t)nccl_comm, rank, nranks, false);
+}
+
+int bdk_comm_unique_id(void* out, int cap) {
+    bdk_ctx* c = nullptr;
+    if (!out || cap < (int)sizeof(ncclUniqueId)) return fail(c, BDK_ERR_ARG, "bdk_comm_unique_id needs a %d-byte buffer", (int)sizeof(ncclUniqueId));
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+    ncclUniqueId id;
+    NC(nc->GetUniqueId(&id));
+    memcpy(out, &id, sizeof id);
+    return 0;
+}
+
+int bdk_comm_init(bdk_ctx* c, const void* unique_id, int rank, int nranks) {
+    if (!c || !unique_id) return BDK_ERR_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks || nranks > 1024) return fail(c, BDK_ERR_ARG, "bad rank %d / nranks %d", rank, nranks);
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclComm_t comm = nullptr;
+    NC(nc->CommInitRank(&comm, nranks, id, rank));
+    return attach_comm(c, comm, rank, nranks, true);
+}
+
+uint64_t bdk_comm_bytes(bdk_ctx* c) { return c ? c->comm_bytes : 0; }
+uint32_t bdk_k4_sweeps(bdk_ctx* c) { return c ? c->k4_sweeps : 0; }
 
 int bdk_poisson_logsf(bdk_ctx* c, const double* lambda, const int32_t* k, double* out, uint64_t n) {
     if (!c || !lambda || !k || !out) return BDK_ERR_ARG;

@@ -256,12 +256,23 @@ struct K4Static {
     int32_t nreg, ncand, period, nkey, nlib;
     int32_t chr_restricted, min_read_pair, score_threshold, fisher;
     uint32_t covered_ref_len;
+    // Components are the connected components over the edges the walk can FOLLOW (weight >= -r). A weaker edge
+    // couples two components only through is_region_final(): "has the mate's region been cleared by now?". That
+    // one bit per region is read from a table of deletion times (the flush window in which the region was
+    // cleared) left by the previous sweep over the components; sweeps are repeated for the components whose
+    // inputs changed until the table is stable (a fixed point is the sequential result, because every event
+    // depends only on strictly earlier events).
+    const int32_t* root_of;       // [nreg] component root of a region
+    const int32_t* del_prev;      // [nreg] window in which the region was cleared according to the previous sweep (K4_NEVER: not)
+    int32_t rerun;                // 0: first sweep (state initialised by the caller); 1: the walk first resets its component
 };
+constexpr int32_t K4_NEVER = 0x7f7f7f7f;   // byte pattern 0x7f: tables are initialised with memset
 
 struct K4Mut {
     uint8_t* alive;         // [A] read still in its region's vector
     uint8_t* freed;         // [A] name erased by erase_read (set on both mates)
     uint8_t* deleted;       // [nreg] clear_region() happened
+    int32_t* del_cur;       // [nreg] window in which it happened (K4_NEVER: not), written by the region's own component
     int32_t* sv_of_read;    // [A] row slot of the process_sv call that consumed the read, or -1
     bdk_sv* rows;           // [nrow_cap]
     int32_t* row_lib_count; // [nrow_cap][nlib]
@@ -270,15 +281,13 @@ struct K4Mut {
     float* row_cn;          // [nrow_cap][nkey]
     uint8_t* row_emit;      // [nrow_cap]
     uint64_t* row_key;      // [nrow_cap] (window << 32 | BFS start vertex)
-    uint32_t* emit_count;   // number of rows emitted so far
-    uint64_t* emit_key;     // [nrow_cap] key of the i-th emitted row (arrival order)
-    uint32_t* emit_slot;    // [nrow_cap] its row slot
 };
 
-struct WindowInfo { int32_t cF; int32_t maxlen; int32_t last_region; };
+struct WindowInfo { int32_t cF; int32_t maxlen; int32_t last_region; int32_t w; };
 
 BDK_HD WindowInfo k4_window_info(const K4Static& S, int w) {
     WindowInfo wi;
+    wi.w = w;
     int64_t trigger = ((int64_t)w + 1) * S.period - 1;
     if (trigger < S.nreg) {          // flush triggered by the registration of region `trigger`
         wi.cF = S.reg[trigger].cand;
@@ -301,16 +310,37 @@ BDK_HD bool k4_exists(const K4Static& S, const K4Mut& M, int j, int cF) {
     return !M.freed[j];
 }
 
-// _read_regions[name].size() == 2
-BDK_HD bool k4_size2(const K4Static& S, const K4Mut& M, int j, int cF) {
+// _read_regions[name].size() == 2, asked while region v = read_region[j] is checked at the end of window w
+BDK_HD bool k4_size2(const K4Static& S, const K4Mut& M, int j, int cF, int w) {
     int m = S.mate[j];
     if (m < 0) return false;
     int rm = S.read_region[m];
     if (rm < 0) return false;
     if (S.read_cand[m] > cF) return false;      // mate's region not registered yet
     if (M.freed[j]) return false;
-    if (M.deleted[rm] && M.alive[m]) return false;  // clear_region(rm) dropped rm from the entry
+    const int v = S.read_region[j];
+    bool rm_deleted;
+    if (S.root_of[rm] == S.root_of[v]) rm_deleted = M.deleted[rm] != 0;      // same component: the walk's own state
+    else {                                        // other component: cleared before (w, v) in the reference's order?
+        const int dw = S.del_prev[rm];            // (windows in order; inside a window the active nodes ascending)
+        rm_deleted = dw < w || (dw == w && rm < v);
+    }
+    // M.alive[m] of another component's read never changes: the pair hangs on an edge that is never followed
+    if (rm_deleted && M.alive[m]) return false;  // clear_region(rm) dropped rm from the entry
     return true;
+}
+
+// Does it matter to region v (checked by is_region_final in its active windows [wf, wl], wl already capped by v's own
+// deletion) that region rm's deletion window moved from `a` to `b`? k4_size2 asks "rm cleared before (w, v)", i.e.
+// d < w || (d == w && rm < v), which is monotone in w: the answers for a and b differ exactly for the windows between the
+// first one that sees the earlier deletion and the last one that does not see the later.
+BDK_HD bool k4_change_matters(int v, int rm, int wf, int wl, int a, int b) {
+    if (a == b) return false;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    const int tie = rm < v ? 0 : 1;
+    const int w0 = lo + tie, w1 = hi + tie - 1;        // windows w with before(lo, w) && !before(hi, w)
+    const int f = wf > w0 ? wf : w0, l = wl < w1 ? wl : w1;
+    return f <= l;
 }
 
 // ---- execution policy of the connection walk --------------------------------------------------
@@ -348,7 +378,7 @@ BDK_HD bool k4_region_final(const Team& T, const K4Static& S, const K4Mut& M, in
     for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
         if (!M.alive[j]) continue;
         if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
-        if (!k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF)) bad = true;
+        if (!k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF, wi.w)) bad = true;
     }
     return !T.any(bad);
 }
@@ -497,10 +527,8 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
     o.logp = logp; o.allele_frequency = af; o.cn_present = 0;
     o.region[0] = s0; o.region[1] = s1; o.window = w; o.order = 0;
     const uint64_t key = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;
-    M.row_key[row] = key;
+    M.row_key[row] = key;       // the reference prints by (window, BFS start), calls of one BFS in slot order
     M.row_emit[row] = 1;
-    const uint32_t idx = T.fetch_inc(M.emit_count);      // the reference prints by (window, BFS start), calls of one BFS in slot order
-    M.emit_key[idx] = key; M.emit_slot[idx] = (uint32_t)row;
     return true;
 }
 
@@ -566,9 +594,21 @@ BDK_HD DEdge* de_sort_team(const Team& T, DEdge* e, int ne, DEdge* scratch) {
 }
 
 template <class Team>
-BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* sorted by (win, src, dst) */, int ne, int32_t* queue, int row0) {
+BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* sorted by (win, src, dst) */, int ne, int32_t* queue, int row0, int nrows) {
     const bool lead = T.lane() == 0;
     T.sync();
+    if (S.rerun) {      // a later sweep: back to the state before the first one (edges, regions, their reads, row slots)
+        for (int q = T.lane(); q < ne; q += T.width()) {
+            e[q].flags = 0;
+            const int v = e[q].src;
+            if (q > 0 && e[q - 1].src == v) continue;          // once per run of a source (a region may have a run in several windows)
+            M.deleted[v] = 0; M.del_cur[v] = K4_NEVER;
+            const RegionRec& R = S.reg[v];
+            for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) { M.alive[j] = (uint8_t)R.stored; M.freed[j] = 0; M.sv_of_read[j] = -1; }
+        }
+        for (int r = T.lane(); r < nrows; r += T.width()) M.row_emit[row0 + r] = 0;
+        T.sync();
+    }
     int row = row0;
     int i = 0;
     while (i < ne) {
@@ -640,7 +680,7 @@ BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* 
             int v = e[vi].src;
             const bool fin = k4_region_final(T, S, M, v, wi);
             T.sync();
-            if (fin && lead) M.deleted[v] = 1;
+            if (fin && lead) { M.deleted[v] = 1; M.del_cur[v] = w; }
             T.sync();
             while (vi < j && e[vi].src == v) ++vi;
         }

@@ -30,6 +30,16 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+
 template <typename T>
 __host__ __device__ __forceinline__ T div_up(T a, T b) { return (a + b - 1) / b; }
 

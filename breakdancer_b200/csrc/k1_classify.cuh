@@ -153,15 +153,6 @@ __device__ __forceinline__ uint32_t byte_sum(uint32_t v) { return __dp4a(v, 0x01
 // byte `it` (0..7) of the pair (lo, hi)
 __device__ __forceinline__ uint32_t byte_of2(uint32_t lo, uint32_t hi, int it) { return ((it < 4 ? lo : hi) >> (8 * (it & 3))) & 0xffu; }
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
-    uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
-}
 
 // ---- mbarrier / TMA bulk copy / named barrier wrappers ---------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

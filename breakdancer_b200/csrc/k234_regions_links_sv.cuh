@@ -14,7 +14,7 @@
 
 namespace bdk {
 
-enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NLINK, CNT_NEDGE, CNT_NDE, CNT_NROW, CNT_ERR, CNT_NREG_REAL, CNT_K4_TICKET, CNT_NEMIT, CNT_N };
+enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NLINK, CNT_NEDGE, CNT_NDE, CNT_NROW, CNT_ERR, CNT_NREG_REAL, CNT_K4_TICKET, CNT_NEMIT, CNT_NDIRTY, CNT_N };
 constexpr uint32_t K3_ERR_DUPNAME = 1u;
 constexpr int GS_THREADS = 256;
 constexpr int GS_GRID = kNumSMs * 4;
@@ -163,31 +163,48 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
 }
 
 __global__ void __launch_bounds__(GS_THREADS) k3_init_regions_kernel(int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne,
-        uint32_t* __restrict__ comp_strong, uint32_t* __restrict__ comp_fill, uint8_t* __restrict__ deleted, const uint32_t* __restrict__ d_cnt) {
+        uint32_t* __restrict__ comp_strong, uint32_t* __restrict__ comp_fill, uint8_t* __restrict__ deleted, int2* __restrict__ win_range,
+        const uint32_t* __restrict__ d_cnt) {
     const uint32_t nreg = d_cnt[CNT_NREG];
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nreg; r += gridDim.x * blockDim.x) {
         parent[r] = (int32_t)r; comp_ne[r] = 0; comp_strong[r] = 0; comp_fill[r] = 0; deleted[r] = 0;
+        win_range[r] = make_int2(0x7fffffff, -1);      // first / last flush window in which the region has an edge
     }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k3_union_kernel(const unsigned long long* __restrict__ tkeys, uint32_t tsize, int32_t* __restrict__ parent) {
+// Components = connected components over the edges the connection walk can follow (weight >= -r): only those
+// couple two regions through shared reads. A weaker edge still makes both its ends "active" in its flush window
+// (is_region_final is asked for them) and is kept, as a directed copy, in the edge list of each end's component.
+__global__ void __launch_bounds__(GS_THREADS) k3_union_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
+                                                              int32_t* __restrict__ parent, int32_t min_read_pair) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
         const unsigned long long k = tkeys[e];
-        if (k == EDGE_EMPTY) continue;
+        if (k == EDGE_EMPTY || (int32_t)tcnt[e] < min_read_pair) continue;
         const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
         if (r0 != r1) uf_union(parent, r0, r1);
     }
 }
 
+// parent[] -> root table (no unions after this)
+__global__ void __launch_bounds__(GS_THREADS) k3_flatten_kernel(int32_t* __restrict__ parent, const uint32_t* __restrict__ d_cnt) {
+    const uint32_t nreg = d_cnt[CNT_NREG];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nreg; r += gridDim.x * blockDim.x) {
+        int x = (int)r;
+        for (int p = parent[x]; p != x; p = parent[x]) x = p;      // roots never change any more; concurrent writers store roots
+        parent[r] = x;
+    }
+}
+
 __global__ void __launch_bounds__(GS_THREADS) k3_comp_count_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
-        int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ comp_strong, int32_t min_read_pair) {
+        const int32_t* __restrict__ root_of, uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ comp_strong, int32_t min_read_pair) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
         const unsigned long long k = tkeys[e];
         if (k == EDGE_EMPTY) continue;
         const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
-        const int root = uf_find(parent, r0);
-        atomicAdd(comp_ne + root, r0 == r1 ? 1u : 2u);
-        if ((int32_t)tcnt[e] >= min_read_pair) atomicAdd(comp_strong + root, 1u);
+        const int root0 = root_of[r0];
+        atomicAdd(comp_ne + root0, 1u);
+        if (r0 != r1) atomicAdd(comp_ne + root_of[r1], 1u);
+        if ((int32_t)tcnt[e] >= min_read_pair) atomicAdd(comp_strong + root0, 1u);   // a followed edge: both ends in one component
     }
 }
 
@@ -195,18 +212,24 @@ struct LoadU32 { const uint32_t* p; __device__ uint32_t operator()(uint32_t i, u
 struct ExclOut { uint32_t* o; __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const { o[i] = inc - v; } };
 
 __global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
-        int32_t* __restrict__ parent, const uint32_t* __restrict__ de_off, uint32_t* __restrict__ comp_fill, DEdge* __restrict__ de,
-        int32_t* __restrict__ de_root, int32_t period) {
+        const int32_t* __restrict__ root_of, const uint32_t* __restrict__ de_off, uint32_t* __restrict__ comp_fill, DEdge* __restrict__ de,
+        int32_t* __restrict__ de_root, int32_t period, int2* __restrict__ win_range) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
         const unsigned long long k = tkeys[e];
         if (k == EDGE_EMPTY) continue;
         const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
-        const int root = uf_find(parent, r0);
         const int win = r1 / period;          // r0 <= r1: the pair is counted when r1 is registered
-        const uint32_t slot = de_off[root] + atomicAdd(comp_fill + root, r0 == r1 ? 1u : 2u);
         DEdge d; d.win = win; d.src = r0; d.dst = r1; d.w = (int)tcnt[e]; d.flags = 0;
-        de[slot] = d; de_root[slot] = root;
-        if (r0 != r1) { d.src = r1; d.dst = r0; de[slot + 1] = d; de_root[slot + 1] = root; }
+        atomicMin(&win_range[r0].x, win); atomicMax(&win_range[r0].y, win);
+        if (r0 != r1) { atomicMin(&win_range[r1].x, win); atomicMax(&win_range[r1].y, win); }
+        const int root0 = root_of[r0];
+        const uint32_t s0 = de_off[root0] + atomicAdd(comp_fill + root0, 1u);
+        de[s0] = d; de_root[s0] = root0;
+        if (r0 != r1) {                       // the copy seen from r1 goes to r1's component (the same one iff the edge is followed)
+            const int root1 = root_of[r1];
+            const uint32_t s1 = de_off[root1] + atomicAdd(comp_fill + root1, 1u);
+            d.src = r1; d.dst = r0; de[s1] = d; de_root[s1] = root1;
+        }
     }
 }
 
@@ -230,34 +253,124 @@ __global__ void __launch_bounds__(GS_THREADS) k3_rank_edges_kernel(const DEdge* 
 // ---- K4: one warp walks one connected component ------------------------------------------------------
 // Components are found 32 regions at a time (a region with edges is the root of its component); the warp
 // then walks them one after the other, its lanes sharing the loops over the reads of the regions involved.
+// The walks are repeated in sweeps (bdk_logic.h, K4Static) until the table of deletion times is stable:
+//   walk phase   sweep 0: every component; sweep s > 0: the components stamped s
+//   mark phase   one thread per directed edge: a component that looks across a never-followed edge at a region
+//                whose deletion time differs from the table it used is stamped s + 1
+//   next phase   del_prev <- del_cur; the regions of the stamped components start again from "never cleared"
+// Single GPU: one persistent cooperative kernel runs all sweeps with grid-wide barriers in between
+// (k4_sweeps_kernel). Multi-GPU: one launch per phase, the deletion times are all-reduced between walk and mark.
 constexpr int K4_THREADS = 128;
-__global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K4Mut M, const uint32_t* __restrict__ comp_ne, const uint32_t* __restrict__ de_off,
-        const uint32_t* __restrict__ row_off, DEdge* __restrict__ de, DEdge* __restrict__ de_sorted, int32_t* __restrict__ queue,
-        const bdk_summary_t* __restrict__ summary, const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ ticket) {
+struct K4Graph {
+    const uint32_t* comp_ne; const uint32_t* comp_strong; const uint32_t* de_off; const uint32_t* row_off;
+    DEdge* de; DEdge* de_sorted; const int32_t* de_root; int32_t* queue;
+    uint32_t* stamp;                 // [nreg] by root: sweep in which the component is walked again
+    int32_t* del_prev;               // = S.del_prev, writable for the next phase
+    const int2* win_range;           // [nreg] first / last flush window in which the region is active
+    const bdk_summary_t* summary; uint32_t* d_cnt;
+    uint32_t v_lo, v_hi;             // this GPU walks the components whose root region is in [v_lo, v_hi); single GPU: [0, ~0)
+};
+
+__device__ __forceinline__ void k4_walk_phase(K4Static& S, K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* ticket) {
     const unsigned FULL = 0xffffffffu;
-    S.nreg = (int32_t)d_cnt[CNT_NREG]; S.ncand = (int32_t)d_cnt[CNT_NCAND];
-    S.covered_ref_len = summary->covered_ref_len;
     const WarpTeam T;
     const uint32_t lane = lane_id();
-    const uint32_t nwarps = gridDim.x * (K4_THREADS / 32), wid = blockIdx.x * (K4_THREADS / 32) + (threadIdx.x >> 5);
-    (void)nwarps; (void)wid;
+    S.rerun = sweep ? 1 : 0;
+    const uint32_t v_end = min(G.v_hi, (uint32_t)S.nreg);
     for (;;) {                                  // 32 regions at a time, handed out dynamically (components differ a lot in size)
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 1u) * 32u;
+        if (lane == 0) base = G.v_lo + atomicAdd(ticket, 1u) * 32u;
         base = __shfl_sync(FULL, base, 0);
-        if (base >= (uint32_t)S.nreg) break;
+        if (base >= v_end) break;
         const uint32_t r = base + lane;
-        const uint32_t ne = r < (uint32_t)S.nreg ? comp_ne[r] : 0;
+        const uint32_t ne = (r < v_end && (!sweep || G.stamp[r] == sweep)) ? G.comp_ne[r] : 0;
         unsigned m = __ballot_sync(FULL, ne != 0);
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
             const uint32_t rr = base + src;
             const int n = (int)__shfl_sync(FULL, ne, src);
-            DEdge* e = n <= DE_RANK_SORT_MAX ? de_sorted + de_off[rr] : de_sort_team(T, de + de_off[rr], n, (DEdge*)nullptr);
-            k4_component(T, S, M, e, n, queue + de_off[rr] + 2 * (size_t)rr, (int)row_off[rr]);
+            DEdge* e = n <= DE_RANK_SORT_MAX ? G.de_sorted + G.de_off[rr] : de_sort_team(T, G.de + G.de_off[rr], n, (DEdge*)nullptr);
+            k4_component(T, S, M, e, n, G.queue + G.de_off[rr] + 2 * (size_t)rr, (int)G.row_off[rr], (int)G.comp_strong[rr]);
         }
     }
+}
+
+__device__ __forceinline__ void k4_mark_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* n_dirty) {
+    const uint32_t nde = G.d_cnt[CNT_NDE];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nde; t += gridDim.x * blockDim.x) {
+        const int root = G.de_root[t];
+        const DEdge x = G.de[t];                               // de[]: the component's edges as a set (sorted or not)
+        if (S.root_of[x.dst] == root) continue;
+        const int a = S.del_prev[x.dst], b = M.del_cur[x.dst];
+        if (a == b || G.stamp[root] == sweep + 1) continue;
+        const int2 wr = G.win_range[x.src];
+        if (k4_change_matters(x.src, x.dst, wr.x, min(wr.y, M.del_cur[x.src]), a, b)) { G.stamp[root] = sweep + 1; atomicAdd(n_dirty, 1u); }
+    }
+}
+
+__device__ __forceinline__ void k4_next_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep) {
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < (uint32_t)S.nreg; v += gridDim.x * blockDim.x) {
+        G.del_prev[v] = M.del_cur[v];
+        if (G.stamp[S.root_of[v]] == sweep + 1) M.del_cur[v] = K4_NEVER;
+    }
+}
+
+__device__ __forceinline__ void k4_load_counts(K4Static& S, const K4Graph& G) {
+    S.nreg = (int32_t)G.d_cnt[CNT_NREG]; S.ncand = (int32_t)G.d_cnt[CNT_NCAND];
+    S.covered_ref_len = G.summary->covered_ref_len;
+}
+
+// grid-wide barrier of a cooperative launch (all CTAs resident): monotone arrival counter. The spin uses relaxed loads
+// (an acquire load per iteration would invalidate L1 every time); the fences on both sides order the data.
+__device__ __forceinline__ void k4_grid_barrier(uint32_t* counter, uint32_t& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const uint32_t target = epoch * gridDim.x;
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// single GPU: all sweeps in one persistent kernel. sync[0]: barrier counter, sync[1..2]: walk tickets (alternating),
+// sync[3..4]: stamped-component counts (alternating), sync[5]: number of sweeps done (result)
+__global__ void __launch_bounds__(K4_THREADS) k4_sweeps_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t* __restrict__ sync) {
+    k4_load_counts(S, G);
+    uint32_t epoch = 0;
+    for (uint32_t sweep = 0;; ++sweep) {
+        k4_walk_phase(S, M, G, sweep, sync + 1 + (sweep & 1));
+        k4_grid_barrier(sync, epoch);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sync[1 + ((sweep + 1) & 1)] = 0; sync[3 + ((sweep + 1) & 1)] = 0; }   // last used before the barrier two phases back
+        k4_mark_phase(S, M, G, sweep, sync + 3 + (sweep & 1));
+        k4_grid_barrier(sync, epoch);
+        const uint32_t ndirty = ld_acquire_u32(sync + 3 + (sweep & 1));
+        k4_next_phase(S, M, G, sweep);
+        k4_grid_barrier(sync, epoch);
+        if (!ndirty) { if (blockIdx.x == 0 && threadIdx.x == 0) sync[5] = sweep + 1; break; }
+    }
+}
+
+// multi-GPU: one launch per phase
+__global__ void __launch_bounds__(K4_THREADS) k4_components_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep, uint32_t* __restrict__ ticket) {
+    k4_load_counts(S, G);
+    k4_walk_phase(S, M, G, sweep, ticket);
+}
+__global__ void __launch_bounds__(GS_THREADS) k4_mark_dirty_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep, uint32_t* __restrict__ n_dirty) {
+    k4_load_counts(S, G);
+    k4_mark_phase(S, M, G, sweep, n_dirty);
+}
+__global__ void __launch_bounds__(GS_THREADS) k4_next_sweep_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep) {
+    k4_load_counts(S, G);
+    k4_next_phase(S, M, G, sweep);
 }
 
 // ---- output order --------------------------------------------------------------------------------------

@@ -96,6 +96,68 @@ def config2_device(n_pairs: int, seed: int, device, chrom_len: int = CHR1_LEN, t
     return cols
 
 
+def genome_shard_device(n_pairs: int, seed: int, device, tid: int, ntid: int, ctx_frac: float, clustered: float = 0.3,
+                        chrom_len: int = CHR1_LEN) -> Dict[str, torch.Tensor]:
+    """Chromosome `tid` of an `ntid`-chromosome genome (BASELINE.json configs[3]/[4] shape): the config-2 records of
+    the chromosome plus its side of the inter-chromosomal pairs (ctx_frac of the pairs; `clustered` of them in planted
+    translocation clusters of Poisson(10) pairs, the rest uniform). The pairs between chromosomes i < j come from a
+    generator seeded by (seed, i, j), so the ranks that own i and j produce matching mates without talking."""
+    dev = torch.device(device)
+    cols = config2_device(n_pairs, seed * 1000 + tid, dev, chrom_len, tid)
+    cols["qid"] += (tid + 1) << 40                                 # read names unique across chromosomes
+    L = chrom_len if n_pairs >= 50_000_000 else max(200000, int(chrom_len * n_pairs / 50_000_000))
+    n_ctx = int(round(n_pairs * ctx_frac))
+    if ntid < 2 or n_ctx == 0:
+        return cols
+    per = max(1, n_ctx // (ntid - 1))
+    extra = {k: [] for k in ("pos", "mpos", "mtid", "flag", "qid")}
+    for other in range(ntid):
+        if other == tid:
+            continue
+        i, j = min(tid, other), max(tid, other)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed((seed * 1_000_003 + i) * 1009 + j)
+        ncl = max(1, int(per * clustered / 10))
+        sizes = torch.poisson(torch.full((ncl,), 10.0, device=dev), generator=gen).to(torch.int64)
+        n_cl = int(sizes.sum().item())
+        n_un = max(0, per - n_cl)
+
+        def uni(n, lo, hi):
+            return (lo + torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * (hi - lo)).to(torch.int64)
+
+        ci, cj = uni(ncl, 1000, L - 1000), uni(ncl, 1000, L - 1000)
+        rep = torch.repeat_interleave(torch.arange(ncl, device=dev), sizes)
+        pi = torch.cat([ci[rep] - uni(n_cl, 0, 240), uni(n_un, 1000, L - 1000)])
+        pj = torch.cat([cj[rep] + uni(n_cl, 0, 240), uni(n_un, 1000, L - 1000)])
+        ri = torch.cat([torch.zeros(n_cl, dtype=torch.int64, device=dev), uni(n_un, 0, 2)])      # clusters: + on i, - on j
+        rj = torch.cat([torch.ones(n_cl, dtype=torch.int64, device=dev), uni(n_un, 0, 2)])
+        k = torch.arange(n_cl + n_un, device=dev, dtype=torch.int64)
+        qid = (1 << 62) | ((i * ntid + j) << 36) | k
+        if tid == i:
+            extra["pos"].append(pi); extra["mpos"].append(pj)
+            extra["flag"].append(0x1 | 0x40 | (ri << 4) | (rj << 5))
+        else:
+            extra["pos"].append(pj); extra["mpos"].append(pi)
+            extra["flag"].append(0x1 | 0x80 | (rj << 4) | (ri << 5))
+        extra["mtid"].append(torch.full_like(k, other))
+        extra["qid"].append(qid)
+    ne = sum(int(x.numel()) for x in extra["pos"])
+    add = {
+        "pos": torch.cat(extra["pos"]).to(torch.int32), "mpos": torch.cat(extra["mpos"]).to(torch.int32),
+        "mtid": torch.cat(extra["mtid"]).to(torch.int32), "flag": torch.cat(extra["flag"]).to(torch.int16),
+        "qid": torch.cat(extra["qid"]),
+        "tid": torch.full((ne,), tid, dtype=torch.int32, device=dev), "isize": torch.zeros(ne, dtype=torch.int32, device=dev),
+        "mapq": torch.full((ne,), 60, dtype=torch.uint8, device=dev), "rgid": torch.zeros(ne, dtype=torch.int16, device=dev),
+        "qlen": torch.full((ne,), READLEN, dtype=torch.int32, device=dev),
+    }
+    order = torch.sort(torch.cat([cols["pos"], add["pos"]]).to(torch.int64), stable=True).indices
+    out = {}
+    for name in list(cols):
+        out[name] = torch.cat([cols[name], add[name]])[order].contiguous()
+        del cols[name]
+    return out
+
+
 def soa_of(cols: Dict[str, torch.Tensor]) -> api.Soa:
     return api.soa_from_pointers({k: cols[k].data_ptr() for k in api.COLUMN_DTYPES})
 

@@ -207,6 +207,9 @@ int bdk_kernel_times(bdk_ctx* ctx, const char** names, float* ms, int* launches,
 
 /* Number of kernels this context has launched since the last bdk_reset / bdk_create. */
 uint64_t bdk_kernel_launches(bdk_ctx* ctx);
+/* Sweeps over the connected components the last bdk_finish needed until the connection walk was stable
+ * (csrc/bdk_logic.h, K4Static: 1 = no component depends on another one). */
+uint32_t bdk_k4_sweeps(bdk_ctx* ctx);
 /* Bytes the last bdk_push copied host -> device with the copy engine. */
 uint64_t bdk_h2d_bytes(bdk_ctx* ctx);
 /* Bytes the last bdk_finish copied device -> host (ordered SV table + summary). */
@@ -216,9 +219,28 @@ uint64_t bdk_d2h_bytes(bdk_ctx* ctx);
 void* bdk_host_alloc(uint64_t bytes);
 void bdk_host_free(void* p);
 
-/* Multi-GPU: attach an NCCL communicator (ncclComm_t) for the inter-chromosomal mate-link
- * exchange of whole-genome / -t runs. Per-chromosome sharding needs no communicator. */
+/* Multi-GPU, whole-genome semantics (one job over several GPUs; the reference's non-"-o" run, where regions on
+ * different chromosomes are linked: BreakDancer.cpp:161,254-259, ReadRegionData.cpp:109-113). Per-chromosome
+ * sharding ("-o chr" runs, README:31) needs no communicator: use one independent context per chromosome set.
+ *
+ * With a communicator attached, rank r pushes the r-th CONTIGUOUS SLICE of the globally (tid, pos)-sorted
+ * record stream (rank order = stream order; a cut may fall anywhere). bdk_push / bdk_push_device stay local.
+ * bdk_summary, bdk_finish and bdk_get_support become COLLECTIVE: every rank must call them, in the same order,
+ * and every rank receives the same complete result (summary of the whole stream, the whole SV table, region and
+ * read indices global). The exchanges run over NCCL on the context's stream: an all-gather of the compacted
+ * anomalous reads (1-3 % of the records), a few-KB all-reduce of the pass-1 statistics, and an all-gather of
+ * the SV rows each GPU produced for the connected components it walked (csrc/comm.cuh).
+ * Attach before the first push of a job; a caller that saw a push fail on one rank must not enter the
+ * collectives on the others.
+ *
+ * bdk_set_comm adopts the caller's ncclComm_t (not destroyed by bdk_destroy); nccl_comm = NULL detaches.
+ * bdk_comm_unique_id + bdk_comm_init create one inside the library for callers without an NCCL binding
+ * (rank 0 obtains the 128-byte id, hands it to the other ranks by any means, all call bdk_comm_init). */
 int bdk_set_comm(bdk_ctx* ctx, void* nccl_comm, int rank, int nranks);
+int bdk_comm_unique_id(void* out128, int cap);
+int bdk_comm_init(bdk_ctx* ctx, const void* unique_id128, int rank, int nranks);
+/* Bytes this rank received over NVLink in the exchanges of the last job. */
+uint64_t bdk_comm_bytes(bdk_ctx* ctx);
 
 /* Poisson tail used by ComputeProbScore (BreakDancer.cpp:62-68): log P[Pois(lambda) > k],
  * evaluated on the device (for known-answer tests). */

@@ -12,6 +12,7 @@
 #include "../../oracle/bdo_api.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -126,18 +127,27 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     std::vector<int> parent(nreg);
     std::iota(parent.begin(), parent.end(), 0);
     auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    for (auto const& e : ue) { int a = find(e.r0), b = find(e.r1); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } }
+    // components over the edges the walk can follow (weight >= -r); a weaker edge is kept as a directed copy in each end's component
+    for (auto const& e : ue) { if (e.w < p.min_read_pair) continue; int a = find(e.r0), b = find(e.r1); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } }
+    std::vector<int32_t> root_of(nreg);
+    for (int r = 0; r < nreg; ++r) root_of[r] = find(r);
     std::vector<int> comp_ne(nreg, 0), comp_strong(nreg, 0);
-    for (auto const& e : ue) { int r = find(e.r0); comp_ne[r] += e.r0 == e.r1 ? 1 : 2; if (e.w >= p.min_read_pair) ++comp_strong[r]; }
+    for (auto const& e : ue) {
+        ++comp_ne[root_of[e.r0]];
+        if (e.r0 != e.r1) ++comp_ne[root_of[e.r1]];
+        if (e.w >= p.min_read_pair) ++comp_strong[root_of[e.r0]];
+    }
     std::vector<int> de_off(nreg + 1, 0), row_off(nreg + 1, 0);
     for (int r = 0; r < nreg; ++r) { de_off[r + 1] = de_off[r] + comp_ne[r]; row_off[r + 1] = row_off[r] + comp_strong[r]; }
     std::vector<DEdge> de(de_off[nreg] + 1);
     std::vector<int> fill(nreg, 0);
+    std::vector<int> win_first(nreg + 1, 0x7fffffff), win_last(nreg + 1, -1);
     for (auto const& e : ue) {
-        int r = find(e.r0);
         int win = e.r1 / period;  // r0 <= r1: the edge is counted when r1 is registered
+        for (int v : {e.r0, e.r1}) { win_first[v] = std::min(win_first[v], win); win_last[v] = std::max(win_last[v], win); }
+        int r = root_of[e.r0];
         de[de_off[r] + fill[r]++] = DEdge{win, e.r0, e.r1, e.w, 0};
-        if (e.r0 != e.r1) de[de_off[r] + fill[r]++] = DEdge{win, e.r1, e.r0, e.w, 0};
+        if (e.r0 != e.r1) { r = root_of[e.r1]; de[de_off[r] + fill[r]++] = DEdge{win, e.r1, e.r0, e.w, 0}; }
     }
     int nrow_cap = row_off[nreg];
 
@@ -149,9 +159,9 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     std::vector<uint32_t> row_cn_count((size_t)(nrow_cap + 1) * nkey);
     std::vector<float> row_cn((size_t)(nrow_cap + 1) * nkey);
     std::vector<bdk_sv> rows(nrow_cap + 1);
-    std::vector<uint64_t> row_key(nrow_cap + 1, 0), emit_key(nrow_cap + 1, 0);
-    std::vector<uint32_t> emit_slot(nrow_cap + 1, 0);
-    uint32_t emit_count = 0;
+    std::vector<uint64_t> row_key(nrow_cap + 1, 0);
+    std::vector<int32_t> del_prev(nreg + 1, K4_NEVER), del_cur(nreg + 1, K4_NEVER);
+    std::vector<uint8_t> dirty(nreg + 1, 0);
     K4Static KS;
     KS.ar = ar.data(); KS.read_region = read_region.data(); KS.read_cand = read_cand.data(); KS.mate = mate.data();
     KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.lib_mean = lib_mean.data();
@@ -159,20 +169,40 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     KS.period = period; KS.nkey = nkey; KS.nlib = nlib; KS.chr_restricted = p.chr_restricted;
     KS.min_read_pair = p.min_read_pair; KS.score_threshold = p.score_threshold; KS.fisher = p.fisher;
     KS.covered_ref_len = S.covered_ref_len;
+    KS.root_of = root_of.data(); KS.del_prev = del_prev.data(); KS.rerun = 0;
     K4Mut KM;
     KM.alive = alive.data(); KM.freed = freed.data(); KM.deleted = deleted.data(); KM.sv_of_read = sv_of_read.data();
     KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
     KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
-    KM.emit_count = &emit_count; KM.emit_key = emit_key.data(); KM.emit_slot = emit_slot.data();
+    KM.del_cur = del_cur.data();
     std::vector<int32_t> queue;
-    for (int r = 0; r < nreg; ++r) {
-        if (!comp_ne[r]) continue;
-        queue.assign(comp_ne[r] + 2, 0);
-        std::vector<DEdge> scratch(comp_ne[r]);
-        DEdge* es = de_sort_team(SoloTeam(), de.data() + de_off[r], comp_ne[r], scratch.data());
-        int used = k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r]);
-        if (used > comp_strong[r]) return -100;
+    // sweeps over the components until the table of deletion times is stable (same driver as bdk_finish). The components are
+    // walked in DESCENDING root order on purpose: nothing may depend on the order inside a sweep.
+    int sweeps = 0;
+    for (;; ++sweeps) {
+        if (sweeps > 100000) return -101;
+        KS.rerun = sweeps ? 1 : 0;
+        for (int r = nreg - 1; r >= 0; --r) {
+            if (!comp_ne[r] || (sweeps && !dirty[r])) continue;
+            queue.assign(comp_ne[r] + 2, 0);
+            DEdge* es = de.data() + de_off[r];
+            if (!sweeps) de_sort(es, comp_ne[r]);
+            int used = k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r], comp_strong[r]);
+            if (used > comp_strong[r]) return -100;
+        }
+        std::fill(dirty.begin(), dirty.end(), 0);
+        int ndirty = 0;
+        for (int r = 0; r < nreg; ++r)
+            for (int t = de_off[r]; t < de_off[r + 1]; ++t) {
+                const DEdge& x = de[t];
+                if (root_of[x.dst] == r) continue;
+                if (!dirty[r] && k4_change_matters(x.src, x.dst, win_first[x.src], std::min(win_last[x.src], del_cur[x.src]), del_prev[x.dst], del_cur[x.dst])) { dirty[r] = 1; ++ndirty; }
+            }
+        for (int v = 0; v < nreg; ++v) { del_prev[v] = del_cur[v]; if (dirty[root_of[v]]) del_cur[v] = K4_NEVER; }
+        if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: sweep %d -> %d components to walk again\n", sweeps, ndirty);
+        if (!ndirty) break;
     }
+    if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: %d regions, %zu edges, %d sweeps\n", nreg, ue.size(), sweeps + 1);
     // final order: stable by (window, BFS start vertex), slot order inside
     std::vector<int> order;
     for (int r = 0; r < nrow_cap; ++r) if (row_emit[r]) order.push_back(r);
