@@ -39,7 +39,9 @@ BYTES_PER_RECORD = 25          # pos,mpos,tid,mtid,isize int32 + flag u16 + mapq
 HOST_BYTES_PER_RECORD = 37     # + qlen int32 + qid u64 side columns copied by bdk_push
 
 
-def workload_name(pairs):
+def workload_name(pairs, config=2):
+    if config == 3:
+        return f"synthetic 4-library tumor/normal chr1-3, all 5 SV types (-c 3 -q 35), {pairs / 1e6:g}M read pairs per GPU (BASELINE configs[2])"
     return f"synthetic single-library 30x chr1-shaped, DEL-only, {pairs / 1e6:g}M read pairs per GPU (BASELINE configs[1])"
 
 
@@ -236,13 +238,17 @@ def ours(args):
     dev = torch.device("cuda", local)
 
     pairs = args.pairs
-    cols = synth_torch.config2_device(pairs, seed=20260101 + rank, device=dev, tid=0)
+    if args.config == 3:
+        cols = synth_torch.config3_device(pairs, seed=20260102 + rank, device=dev)
+        bundle, cfg = synth_torch.config3_bundle()
+    else:
+        cols = synth_torch.config2_device(pairs, seed=20260101 + rank, device=dev, tid=0)
+        lib = synth.LibSpec("lib1", "syn_chr1.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
+        wl = synth.Workload({}, [("chr1", synth_torch.CHR1_LEN)], [lib], ["rg1"], ["lib1"], ["syn_chr1.bam"])
+        cfg = api.BamConfig(text=wl.config_text())
+        bundle = api.ParamBundle(api.Options(), cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, 1)
     n = cols["pos"].numel()
     npairs = n // 2
-    lib = synth.LibSpec("lib1", "syn_chr1.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
-    wl = synth.Workload({}, [("chr1", synth_torch.CHR1_LEN)], [lib], ["rg1"], ["lib1"], ["syn_chr1.bam"])
-    cfg = api.BamConfig(text=wl.config_text())
-    bundle = api.ParamBundle(api.Options(), cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, 1)
     ctx = api.Context(bundle, local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     dsoa = synth_torch.soa_of(cols)
@@ -340,7 +346,7 @@ def ours(args):
     e2e_value = total_pairs / (e_ms / 1e3)
 
     genome = None
-    if world > 1 and not args.no_genome:
+    if world > 1 and not args.no_genome and args.config == 2:
         del cols, hcols, dsoa, hsoa
         torch.cuda.empty_cache()
         genome = {"whole_genome": genome_mode(args, rank, world, local, dev, False), "ctx_only_t": genome_mode(args, rank, world, local, dev, True)}
@@ -364,9 +370,9 @@ def ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(pairs), "records_per_gpu": n, "anomalous_reads_per_gpu": n_anom, "sv_calls_per_gpu": n_sv,
+            "config": {"workload": workload_name(pairs, args.config), "records_per_gpu": n, "anomalous_reads_per_gpu": n_anom, "sv_calls_per_gpu": n_sv,
                        "sharding": "one chromosome-shaped shard per GPU, no data-path collective" if world > 1 else "single GPU",
-                       "l2": "inputs (3.7 GB) are larger than L2, no flush needed", "options": "defaults (-c 3 -q 35 -r 2 -y 30)"},
+                       "l2": f"inputs ({n * HOST_BYTES_PER_RECORD / 1e9:.1f} GB) are larger than L2, no flush needed", "options": "defaults (-c 3 -q 35 -r 2 -y 30)"},
             "roofline": {"bound": "hbm", "kernel": "k1_classify_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * BYTES_PER_RECORD, "kernel_ms": k1_ms},
@@ -458,13 +464,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=50_000_000, help="read pairs per GPU (BASELINE configs[1]: 50 M)")
+    ap.add_argument("--pairs", type=int, default=None, help="read pairs per GPU (BASELINE configs[1]: 50 M; configs[2]: 300 M)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="2: BASELINE configs[1] (the bench line); 3: configs[2], 4 libraries / all SV types")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=6_000_000, help="total read pairs of the CPU baseline sample")
     ap.add_argument("--ref-pairs", type=int, default=400_000, help="read pairs per process and step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-genome", action="store_true", help="N > 1: skip the one-job-over-all-GPUs (NCCL exchange) measurements")
     args = ap.parse_args()
+    if args.pairs is None:
+        args.pairs = 300_000_000 if args.config == 3 else 50_000_000
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         reference_arm(args)

@@ -523,7 +523,7 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k4bps, k4_sweeps_kernel, K4_THREADS, 0));
             CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
             c->k4_grid_max = std::max(1, k4bps) * nsm;
-            CUC(cudaMalloc(&c->d_k4sync.p, 64)); c->d_k4sync.cap = 64;
+            CUC(cudaMalloc(&c->d_k4sync.p, 64 + sizeof(K4Trace))); c->d_k4sync.cap = 64 + sizeof(K4Trace);
         }
         if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
         CUC(cudaFuncSetAttribute(k5_order_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM_ROWS * 12));
@@ -790,21 +790,21 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         // Sweeps over the components (bdk_logic.h, K4Static): the first walks all of them against an empty table of
         // deletion times; each later one walks again the components that looked, across an edge that is never followed, at a
         // region whose deletion time changed. Stable table = the reference's sequential result.
-        CU(cudaMemsetAsync(c->d_del_prev.p, 0x7f, (size_t)nreg * 4, st));
-        CU(cudaMemsetAsync(c->d_del_cur.p, 0x7f, (size_t)nreg * 4, st));
-        CU(cudaMemsetAsync(c->d_dirty.p, 0, (size_t)nreg * 4, st));
         K4Graph G;
         G.comp_ne = c->d_comp_ne.as<uint32_t>(); G.comp_strong = c->d_comp_strong.as<uint32_t>(); G.de_off = c->d_de_off.as<uint32_t>();
         G.row_off = c->d_row_off.as<uint32_t>(); G.de = c->d_de.as<DEdge>(); G.de_sorted = c->d_de2.as<DEdge>(); G.de_root = c->d_de_root.as<int32_t>();
         G.queue = c->d_queue.as<int32_t>(); G.stamp = c->d_dirty.as<uint32_t>(); G.del_prev = c->d_del_prev.as<int32_t>(); G.win_range = c->d_win_range.as<int2>();
         G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi;
+        k4_guess_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G);     // starting table, cleared stamps
+        c->launches += 1;
         const bool mine = v_lo < std::min(v_hi, nreg);
         const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
         if (!c->comm || N == 1) {   // one persistent cooperative kernel, grid-wide barriers between the phases
             uint32_t* sync = c->d_k4sync.as<uint32_t>();
             CU(cudaMemsetAsync(sync, 0, 32, st));
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->k4_grid_max));
-            void* args[] = {&S, &M, &G, &sync};
+            K4Trace* trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
+            void* args[] = {&S, &M, &G, &sync, &trace};
             CU(cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, 0, st));
             c->launches += 1;
             sweeps_on_device = true;
@@ -894,6 +894,14 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     memcpy(&c->h_summary, hp + o_sum, sizeof(bdk_summary_t));
     const size_t ns = *(const uint32_t*)(hp + o_n);
     if (sweeps_on_device) c->k4_sweeps = *(const uint32_t*)(hp + o_n + 4);
+    if (sweeps_on_device && getenv("BDK_K4_TRACE")) {
+        K4Trace tr;
+        CU(cudaMemcpy(&tr, (char*)c->d_k4sync.p + 64, sizeof tr, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "bdk K4 trace: %u regions, %u directed edges, %u row slots, %u sweeps\n", nreg, c->h_cnt[CNT_NDE], nrow, c->k4_sweeps);
+        for (uint32_t sw = 0; sw < std::min<uint32_t>(c->k4_sweeps, K4_TRACE_SWEEPS); ++sw)
+            fprintf(stderr, "  sweep %2u: walk %7.1f us  mark %6.1f us  next %6.1f us  -> %u components to walk again\n", sw,
+                    (tr.t[1 + 3 * sw] - tr.t[3 * sw]) / 1e3, (tr.t[2 + 3 * sw] - tr.t[1 + 3 * sw]) / 1e3, (tr.t[3 + 3 * sw] - tr.t[2 + 3 * sw]) / 1e3, tr.ndirty[sw]);
+    }
     c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet
     c->n_slots = nrow;
     c->finished = true;

@@ -343,6 +343,21 @@ BDK_HD bool k4_change_matters(int v, int rm, int wf, int wl, int a, int b) {
     return f <= l;
 }
 
+// Starting value of the deletion-time table (any table converges to the same fixed point; a good guess saves sweeps): a
+// region whose stored reads all have their mate in a registered region is usually cleared in the last window in which it
+// has an edge (by then every mate is registered); a region holding a read without such a mate is never cleared.
+BDK_HD int k4_guess_deletion(const K4Static& S, const uint8_t* alive, int v, int win_last) {
+    if (win_last < 0 || v == S.nreg - 1) return K4_NEVER;
+    const RegionRec& R = S.reg[v];
+    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) {
+        if (!alive[j]) continue;
+        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
+        const int m = S.mate[j];
+        if (m < 0 || S.read_region[m] < 0) return K4_NEVER;
+    }
+    return win_last;
+}
+
 // ---- execution policy of the connection walk --------------------------------------------------
 // The walk over one connected component is sequential (it reproduces build_connection's order), but
 // the loops over the reads of a region are independent per read: a "team" spreads them over its

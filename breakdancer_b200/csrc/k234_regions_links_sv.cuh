@@ -343,19 +343,38 @@ __device__ __forceinline__ void k4_grid_barrier(uint32_t* counter, uint32_t& epo
 
 // single GPU: all sweeps in one persistent kernel. sync[0]: barrier counter, sync[1..2]: walk tickets (alternating),
 // sync[3..4]: stamped-component counts (alternating), sync[5]: number of sweeps done (result)
-__global__ void __launch_bounds__(K4_THREADS) k4_sweeps_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t* __restrict__ sync) {
+constexpr int K4_TRACE_SWEEPS = 32;
+struct K4Trace { unsigned long long t[1 + 3 * K4_TRACE_SWEEPS]; uint32_t ndirty[K4_TRACE_SWEEPS]; };   // BDK_K4_TRACE=1: phase time stamps (ns)
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__global__ void __launch_bounds__(K4_THREADS) k4_sweeps_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t* __restrict__ sync, K4Trace* __restrict__ trace) {
     k4_load_counts(S, G);
     uint32_t epoch = 0;
+    const bool tr = trace && blockIdx.x == 0 && threadIdx.x == 0;
+    if (tr) trace->t[0] = globaltimer_ns();
     for (uint32_t sweep = 0;; ++sweep) {
         k4_walk_phase(S, M, G, sweep, sync + 1 + (sweep & 1));
         k4_grid_barrier(sync, epoch);
+        if (tr && sweep < K4_TRACE_SWEEPS) trace->t[1 + 3 * sweep] = globaltimer_ns();
         if (blockIdx.x == 0 && threadIdx.x == 0) { sync[1 + ((sweep + 1) & 1)] = 0; sync[3 + ((sweep + 1) & 1)] = 0; }   // last used before the barrier two phases back
         k4_mark_phase(S, M, G, sweep, sync + 3 + (sweep & 1));
         k4_grid_barrier(sync, epoch);
+        if (tr && sweep < K4_TRACE_SWEEPS) trace->t[2 + 3 * sweep] = globaltimer_ns();
         const uint32_t ndirty = ld_acquire_u32(sync + 3 + (sweep & 1));
         k4_next_phase(S, M, G, sweep);
         k4_grid_barrier(sync, epoch);
+        if (tr && sweep < K4_TRACE_SWEEPS) { trace->t[3 + 3 * sweep] = globaltimer_ns(); trace->ndirty[sweep] = ndirty; }
         if (!ndirty) { if (blockIdx.x == 0 && threadIdx.x == 0) sync[5] = sweep + 1; break; }
+    }
+}
+
+// starting table of deletion times (bdk_logic.h: k4_guess_deletion), one thread per region
+__global__ void __launch_bounds__(GS_THREADS) k4_guess_kernel(K4Static S, K4Mut M, K4Graph G) {
+    k4_load_counts(S, G);
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < (uint32_t)S.nreg; v += gridDim.x * blockDim.x) {
+        G.del_prev[v] = k4_guess_deletion(S, M.alive, (int)v, G.win_range[v].y);
+        M.del_cur[v] = K4_NEVER;
+        G.stamp[v] = 0;
     }
 }
 

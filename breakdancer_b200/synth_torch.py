@@ -158,6 +158,162 @@ def genome_shard_device(n_pairs: int, seed: int, device, tid: int, ntid: int, ct
     return out
 
 
+CONFIG3_GENOME = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559)]
+CONFIG3_LIBS = [("normal_a", "normal.bam", 315.0, 44.0), ("normal_b", "normal.bam", 312.0, 43.0),
+                ("tumor_a", "tumor.bam", 467.0, 32.0), ("tumor_b", "tumor.bam", 476.0, 29.0)]     # 2 read groups each
+
+
+def config3_device(n_pairs: int, seed: int, device) -> Dict[str, torch.Tensor]:
+    """BASELINE.json configs[2] on the device: chr1-3, 2 BAMs x 2 libraries x 2 read groups, 2 % anomalous pairs
+    (DEL 50 / INS 15 / INV 15 / ITX 10 / CTX 10 %), half of them in planted clusters of Poisson(12) pairs, half uniform
+    noise. Same construction as synth.generate (host), vectorised with torch; sorted by (tid, pos, strand).
+    Read group id = 2 * library + {0, 1}; library index = rank of the library name (as the config parser assigns it)."""
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    scale = min(1.0, n_pairs / 300_000_000)
+    glen = torch.tensor([max(300000, int(l * scale)) for _, l in CONFIG3_GENOME], device=dev, dtype=torch.int64)
+    gcum = torch.cumsum(glen.to(torch.float64) / float(glen.sum()), 0)
+    means = torch.tensor([l[2] for l in CONFIG3_LIBS], device=dev, dtype=torch.float64)
+    stds = torch.tensor([l[3] for l in CONFIG3_LIBS], device=dev, dtype=torch.float64)
+    RL = READLEN
+
+    def rnd(n):
+        return torch.rand(n, generator=gen, device=dev, dtype=torch.float64)
+
+    def randint(n, lo, hi):
+        return (lo + rnd(n) * (hi - lo)).to(torch.int64)
+
+    def place(n):
+        tid = torch.bucketize(rnd(n), gcum).clamp_(max=2)
+        pos = (rnd(n) * (glen[tid] - 60000).to(torch.float64)).to(torch.int64) + 1000
+        return tid, pos
+
+    def insert(lib):
+        x = torch.round(means[lib] + stds[lib] * torch.randn(lib.numel(), generator=gen, device=dev, dtype=torch.float64)).to(torch.int64)
+        return torch.clamp(x, min=RL + 1)
+
+    parts = []
+    next_id = [1]
+
+    def emit(tid1, p1, tid2, p2, rev1, rev2, proper, isz, lib):
+        n = p1.numel()
+        if n == 0:
+            return
+        same = tid1 == tid2
+        isz1 = torch.where(same, torch.where(p1 <= p2, isz, -isz), torch.zeros_like(isz))
+        fc = 0x1 | torch.where(proper, 0x2, 0)
+        r1, r2 = rev1.to(torch.int64), rev2.to(torch.int64)
+        flag1 = fc | (r1 << 4) | (r2 << 5) | 0x40
+        flag2 = fc | (r2 << 4) | (r1 << 5) | 0x80
+        rg = (2 * lib + randint(n, 0, 2)).to(torch.int16)
+        qid = torch.arange(next_id[0], next_id[0] + n, device=dev, dtype=torch.int64)
+        next_id[0] += n
+        for t, p, mt, mp, i_s, fl in ((tid1, p1, tid2, p2, isz1, flag1), (tid2, p2, tid1, p1, -isz1, flag2)):
+            parts.append(dict(pos=p.clamp(min=0).to(torch.int32), mpos=mp.clamp(min=0).to(torch.int32), tid=t.to(torch.int32), mtid=mt.to(torch.int32),
+                              isize=i_s.to(torch.int32), flag=fl.to(torch.int16), mapq=_mapq(n, gen, dev).to(torch.uint8), rgid=rg, qid=qid))
+
+    n_anom = int(round(n_pairs * 0.02))
+    n_normal = n_pairs - n_anom
+    # normal FR pairs, in slabs to bound the temporaries
+    done = 0
+    while done < n_normal:
+        m = min(100_000_000, n_normal - done)
+        lib = randint(m, 0, 4)
+        tid, pos = place(m)
+        ins = insert(lib)
+        f, t = torch.zeros(m, dtype=torch.bool, device=dev), torch.ones(m, dtype=torch.bool, device=dev)
+        emit(tid, pos, tid, pos + ins - RL, f, t, t, ins, lib)
+        done += m
+        del lib, tid, pos, ins
+
+    kinds = ["DEL", "INS", "INV", "ITX", "CTX"]
+    shares = torch.tensor([0.5, 0.15, 0.15, 0.10, 0.10], device=dev, dtype=torch.float64)
+    kcum = torch.cumsum(shares, 0)
+
+    def anomalous(kind, tid, pos, lib, span):
+        n = pos.numel()
+        if n == 0:
+            return
+        ins = insert(lib)
+        t2 = tid.clone()
+        rev1 = torch.zeros(n, dtype=torch.bool, device=dev)
+        rev2 = torch.ones(n, dtype=torch.bool, device=dev)
+        if kind == "DEL":
+            p1 = pos - randint(n, 0, 240); isz = ins + span; p2 = p1 + isz - RL
+        elif kind == "INS":
+            isz = torch.clamp((means[lib] - 4 * stds[lib]).to(torch.int64) - randint(n, 20, 120), min=RL + 1)
+            p1 = pos + randint(n, 0, 100); p2 = p1 + isz - RL
+        elif kind == "INV":
+            ff = rnd(n) < 0.5
+            rev1 = ~ff; rev2 = ~ff
+            p1 = pos + randint(n, 0, 150); p2 = p1 + (span % 4700 + 300) + randint(n, 0, 150); isz = p2 - p1 + RL
+        elif kind == "ITX":
+            rev1 = torch.ones(n, dtype=torch.bool, device=dev); rev2 = torch.zeros(n, dtype=torch.bool, device=dev)
+            p1 = pos + randint(n, 0, 150); p2 = p1 + (span % 4700 + 300) + randint(n, 0, 150); isz = p2 - p1 + RL
+        else:   # CTX: mate on another chromosome; clusters share the partner locus (span carries it), noise is uniform
+            t2 = (tid + 1 + randint(n, 0, 2)) % 3
+            p2 = (span.to(torch.float64) / 20000.0 * (glen[t2] - 60000).to(torch.float64)).to(torch.int64) + 1000 + randint(n, 0, 150)
+            p1 = pos + randint(n, 0, 150); isz = torch.zeros(n, dtype=torch.int64, device=dev)
+        emit(tid, p1, t2, p2, rev1, rev2, torch.zeros(n, dtype=torch.bool, device=dev), isz, lib)
+
+    n_cl_pairs = n_anom // 2
+    ncl = max(1, n_cl_pairs // 12)
+    sizes = torch.poisson(torch.full((ncl,), 12.0, device=dev), generator=gen).to(torch.int64)
+    ck = torch.bucketize(rnd(ncl), kcum).clamp_(max=4)
+    ctid, cpos = place(ncl)
+    cspan = randint(ncl, 500, 20000)
+    clib_t = randint(ncl, 0, 4)
+    rep = torch.repeat_interleave(torch.arange(ncl, device=dev), sizes)
+    n_noise = n_anom - int(rep.numel())
+    nk = torch.bucketize(rnd(max(n_noise, 0)), kcum).clamp_(max=4)
+    for ki, kn in enumerate(kinds):
+        r = rep[ck[rep] == ki]
+        som = rnd(r.numel()) < 0.3                                   # somatic clusters: tumor libraries only
+        lib = torch.where(som, 2 + randint(r.numel(), 0, 2), randint(r.numel(), 0, 4))
+        if kn == "CTX":                                              # partner chromosome fixed per cluster
+            n = r.numel()
+            if n:
+                ins = insert(lib)
+                t2 = (ctid[r] + 1 + (cspan[r] % 2)) % 3
+                p2 = (cspan[r].to(torch.float64) / 20000.0 * (glen[t2] - 60000).to(torch.float64)).to(torch.int64) + 1000 + randint(n, 0, 150)
+                emit(ctid[r], cpos[r] + randint(n, 0, 150), t2, p2, torch.zeros(n, dtype=torch.bool, device=dev), torch.ones(n, dtype=torch.bool, device=dev),
+                     torch.zeros(n, dtype=torch.bool, device=dev), torch.zeros(n, dtype=torch.int64, device=dev), lib)
+        else:
+            anomalous(kn, ctid[r], cpos[r], lib, cspan[r])
+        m = int((nk == ki).sum().item())
+        t, p = place(m)
+        anomalous(kn, t, p, randint(m, 0, 4), randint(m, 500, 20000))
+    del clib_t
+
+    cols = {}
+    key = torch.cat([(x["tid"].to(torch.int64) << 33) | (x["pos"].to(torch.int64) << 1) | ((x["flag"].to(torch.int64) >> 4) & 1) for x in parts])
+    order = torch.sort(key, stable=True).indices
+    del key
+    for name in ("pos", "mpos", "tid", "mtid", "isize", "flag", "mapq", "rgid", "qid"):
+        cols[name] = torch.cat([x[name] for x in parts])[order].contiguous()
+        for x in parts:
+            del x[name]
+    cols["qlen"] = torch.full((cols["pos"].numel(),), RL, dtype=torch.int32, device=dev)
+    return cols
+
+
+def config3_bundle():
+    """(ParamBundle with `-c 3 -q 35`, config) matching config3_device's read-group numbering."""
+    from . import synth
+    libs = [synth.LibSpec(n, b, m, s, READLEN, [f"{n}.1", f"{n}.2"], tumor=n.startswith("tumor")) for n, b, m, s in CONFIG3_LIBS]
+    rg_names = [r for l in libs for r in l.read_groups]
+    rg_lib = [l.name for l in libs for _ in l.read_groups]
+    rg_bam = [l.bam for l in libs for _ in l.read_groups]
+    wl = synth.Workload({}, list(CONFIG3_GENOME), libs, rg_names, rg_lib, rg_bam)
+    cfg = api.BamConfig(text=wl.config_text())
+    bams = sorted(set(rg_bam))
+    rgl = np.array([cfg.rg_lib(r) for r in rg_names], np.int32)
+    rgb = np.array([bams.index(b) for b in rg_bam], np.int32)
+    opts = api.Options(min_map_qual=35, cut_sd=3)
+    return api.ParamBundle(opts, cfg.libs, cfg.nbam, rgl, rgb, cfg.window, len(CONFIG3_GENOME)), cfg
+
+
 def soa_of(cols: Dict[str, torch.Tensor]) -> api.Soa:
     return api.soa_from_pointers({k: cols[k].data_ptr() for k in api.COLUMN_DTYPES})
 

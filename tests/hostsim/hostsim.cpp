@@ -175,6 +175,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
     KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
     KM.del_cur = del_cur.data();
+    for (int v = 0; v < nreg; ++v) del_prev[v] = getenv("HOSTSIM_NO_GUESS") ? K4_NEVER : k4_guess_deletion(KS, alive.data(), v, win_last[v]);
     std::vector<int32_t> queue;
     // sweeps over the components until the table of deletion times is stable (same driver as bdk_finish). The components are
     // walked in DESCENDING root order on purpose: nothing may depend on the order inside a sweep.

@@ -133,3 +133,59 @@ def test_fullsize_table_is_invariant_under_arrival_and_rerun(big):
     t3 = ctx.finish()
     util.assert_tables_equal(ref, t3, "ragged pinned host pushes")
     util.assert_summary_equal(big["summary"], s3, "ragged pinned host pushes")
+
+
+# ---- BASELINE.json configs[2]: 4 libraries in 2 BAMs, chr1-3, all five SV types, 300 M read pairs (600 M records, 22 GB) -------
+PAIRS3 = 300_000_000
+
+
+@pytest.fixture(scope="module")
+def big3():
+    import torch
+    from breakdancer_b200 import synth_torch
+    torch.cuda.empty_cache()
+    dev = torch.device("cuda", 0)
+    cols = synth_torch.config3_device(PAIRS3, seed=20260102, device=dev)
+    bundle, cfg = synth_torch.config3_bundle()
+    ctx = api.Context(bundle, 0)
+    n = cols["pos"].numel()
+    ctx.push_soa(synth_torch.soa_of(cols), n, device=True)
+    summary = ctx.summary()
+    table = ctx.finish()
+    out = dict(cols=cols, n=n, ctx=ctx, summary=summary, table=table, sweeps=ctx.k4_sweeps(), times=ctx.kernel_times())
+    yield out
+    ctx.close()
+    del cols
+    torch.cuda.empty_cache()
+
+
+def test_config3_fullsize_runs_and_calls_every_sv_type(big3):
+    t, S = big3["table"], big3["summary"]
+    assert int(S.n_records) == big3["n"] == 2 * PAIRS3
+    assert 0.015 * big3["n"] < int(S.n_anomalous) < 0.04 * big3["n"]
+    flags = set(np.unique(t.sv["flag"]).tolist())
+    want = {api.FLAG_NAMES.index(x) for x in ("ARP_FF", "ARP_LARGE_INSERT", "ARP_SMALL_INSERT", "ARP_RF", "ARP_CTX")}
+    assert want <= flags, flags
+    assert len(t.sv) > 100000 and np.array_equal(t.sv["order"], np.arange(len(t.sv)))
+    assert np.all(np.diff(t.sv["window"]) >= 0)
+    ctx_rows = t.sv[t.sv["flag"] == api.FLAG_NAMES.index("ARP_CTX")]
+    assert np.all(ctx_rows["chr"][:, 0] != ctx_rows["chr"][:, 1])
+    assert np.all(t.lib_count.sum(axis=1) == t.sv["num_pairs"])
+    for i in range(4):                                                     # every library saw every anomalous flag
+        h = list(S.read_counts_by_flag[i])
+        assert all(h[f] > 0 for f in want), h
+    print("config 3 full size:", len(t.sv), "SV calls,", big3["sweeps"], "K4 sweeps, kernel ms", {k: round(v["ms"], 3) for k, v in big3["times"].items() if v["ms"]})
+
+
+def test_config3_fullsize_invariant_under_chunked_arrival(big3):
+    from breakdancer_b200 import synth_torch
+    ctx, cols, n = big3["ctx"], big3["cols"], big3["n"]
+    ctx.reset()
+    edges = [0, 16, 8192 * 3 + 16, 200_000_000, 200_000_016, 433_333_328, n]   # device slices must stay 16-byte aligned
+    for a, b in zip(edges[:-1], edges[1:]):
+        soa = api.soa_from_pointers({k: cols[k][a:b].data_ptr() for k in api.COLUMN_DTYPES})
+        ctx.push_soa(soa, b - a, device=True)
+    s2 = ctx.summary()
+    t2 = ctx.finish()
+    util.assert_summary_equal(big3["summary"], s2, "config 3 chunked")
+    util.assert_tables_equal(big3["table"], t2, "config 3 chunked")

@@ -191,3 +191,13 @@ def test_gpu_config3_shape_matches_oracle():
     ro = _check(b, cols, "config3 1.5M pairs")
     flags = set(ro.table.sv["flag"].tolist())
     assert {1, 2, 3, 4, 8} <= flags
+
+
+def test_config3_device_generator_matches_oracle():
+    """The generator of the full-size configs[2] workload (torch, on the device) at a size the oracle handles."""
+    import torch
+    from breakdancer_b200 import synth_torch
+    cols = synth_torch.config3_device(1_500_000, seed=11, device=torch.device("cuda", 0))
+    b, _ = synth_torch.config3_bundle()
+    ro = _check(b, synth_torch.to_numpy(cols), "config3_device 1.5M pairs")
+    assert len(ro.table.sv) > 300 and len(set(ro.table.sv["flag"].tolist())) >= 5
