@@ -110,7 +110,7 @@ struct bdk_ctx {
     uint32_t A_local = 0;             // anomalous reads of this rank's slice (c->A becomes the global count)
     uint64_t comm_bytes = 0;          // bytes this rank received in the exchanges of the last job
     DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff, d_cuts;
-    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
+    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range, d_never_final;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
     uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
     std::vector<uint32_t> h_cuts;     // [2][nranks + 1] vertex / row-slot cuts of the last bdk_finish
@@ -390,7 +390,7 @@ void bdk_destroy(bdk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
     c->comm = nullptr;
-    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
+    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_never_final, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt, &c->d_de_root,
@@ -682,7 +682,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     const size_t L1 = (size_t)A / 2 + 2;
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
-    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8);
+    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8); ENS(c->d_never_final, A1);
     ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
@@ -774,7 +774,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     S.A = A; S.nreg = 0; S.ncand = 0; S.period = c->period; S.nkey = nkey; S.nlib = nlib;
     S.chr_restricted = c->P.chr_restricted; S.min_read_pair = c->P.min_read_pair; S.score_threshold = c->P.score_threshold;
     S.fisher = c->P.fisher; S.covered_ref_len = 0;
-    S.root_of = c->d_parent.as<int32_t>(); S.del_prev = c->d_del_prev.as<int32_t>(); S.rerun = 0;
+    S.root_of = c->d_parent.as<int32_t>(); S.del_prev = c->d_del_prev.as<int32_t>(); S.rerun = 0; S.never_final = c->d_never_final.as<uint8_t>();
     K4Mut M;
     M.alive = c->d_alive.as<uint8_t>(); M.freed = c->d_freed.as<uint8_t>(); M.deleted = c->d_deleted.as<uint8_t>();
     M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = (bdk_sv*)(dp + o_rows); M.del_cur = c->d_del_cur.as<int32_t>();
@@ -793,7 +793,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         K4Graph G;
         G.comp_ne = c->d_comp_ne.as<uint32_t>(); G.comp_strong = c->d_comp_strong.as<uint32_t>(); G.de_off = c->d_de_off.as<uint32_t>();
         G.row_off = c->d_row_off.as<uint32_t>(); G.de = c->d_de.as<DEdge>(); G.de_sorted = c->d_de2.as<DEdge>(); G.de_root = c->d_de_root.as<int32_t>();
-        G.queue = c->d_queue.as<int32_t>(); G.stamp = c->d_dirty.as<uint32_t>(); G.del_prev = c->d_del_prev.as<int32_t>(); G.win_range = c->d_win_range.as<int2>();
+        G.queue = c->d_queue.as<int32_t>(); G.stamp = c->d_dirty.as<uint32_t>(); G.del_prev = c->d_del_prev.as<int32_t>(); G.win_range = c->d_win_range.as<int2>(); G.never_final = c->d_never_final.as<uint8_t>();
         G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi;
         k4_guess_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G);     // starting table, cleared stamps
         c->launches += 1;
@@ -801,7 +801,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
         if (!c->comm || N == 1) {   // one persistent cooperative kernel, grid-wide barriers between the phases
             uint32_t* sync = c->d_k4sync.as<uint32_t>();
-            CU(cudaMemsetAsync(sync, 0, 32, st));
+            CU(cudaMemsetAsync(sync, 0, 64, st));
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->k4_grid_max));
             K4Trace* trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
             void* args[] = {&S, &M, &G, &sync, &trace};

@@ -265,6 +265,7 @@ struct K4Static {
     const int32_t* root_of;       // [nreg] component root of a region
     const int32_t* del_prev;      // [nreg] window in which the region was cleared according to the previous sweep (K4_NEVER: not)
     int32_t rerun;                // 0: first sweep (state initialised by the caller); 1: the walk first resets its component
+    const uint8_t* never_final;   // [nreg] the region holds a read that can never be paired or dropped: is_region_final is false forever
 };
 constexpr int32_t K4_NEVER = 0x7f7f7f7f;   // byte pattern 0x7f: tables are initialised with memset
 
@@ -356,6 +357,20 @@ BDK_HD int k4_guess_deletion(const K4Static& S, const uint8_t* alive, int v, int
         if (m < 0 || S.read_region[m] < 0) return K4_NEVER;
     }
     return win_last;
+}
+
+// A stored read whose mate is not in the anomalous stream at all, or sits EARLIER in a collapsed candidate, keeps its
+// name entry forever with a single region in it (k4_exists stays true, so process_sv never drops it, and it has no
+// partner to be consumed with): is_region_final(v) is false in every window. `alive` = the initial stored flags.
+BDK_HD bool k4_never_final(const K4Static& S, const uint8_t* alive, int v) {
+    const RegionRec& R = S.reg[v];
+    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) {
+        if (!alive[j]) continue;
+        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
+        const int m = S.mate[j];
+        if (m < 0 || (S.read_region[m] < 0 && m < j)) return true;
+    }
+    return false;
 }
 
 // ---- execution policy of the connection walk --------------------------------------------------
@@ -693,7 +708,7 @@ BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* 
         // is_region_final / clear_region over the active nodes, ascending
         for (vi = i; vi < j;) {
             int v = e[vi].src;
-            const bool fin = k4_region_final(T, S, M, v, wi);
+            const bool fin = !S.never_final[v] && k4_region_final(T, S, M, v, wi);
             T.sync();
             if (fin && lead) { M.deleted[v] = 1; M.del_cur[v] = w; }
             T.sync();

@@ -267,11 +267,16 @@ struct K4Graph {
     uint32_t* stamp;                 // [nreg] by root: sweep in which the component is walked again
     int32_t* del_prev;               // = S.del_prev, writable for the next phase
     const int2* win_range;           // [nreg] first / last flush window in which the region is active
+    uint8_t* never_final;            // = S.never_final, written by k4_guess_kernel
     const bdk_summary_t* summary; uint32_t* d_cnt;
     uint32_t v_lo, v_hi;             // this GPU walks the components whose root region is in [v_lo, v_hi); single GPU: [0, ~0)
 };
 
-__device__ __forceinline__ void k4_walk_phase(K4Static& S, K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* ticket) {
+// A component with more than K4_BIG directed edges is walked by its warp for milliseconds to seconds. It waits (keeps its
+// stamp for the next sweep) while smaller components are still changing, so that it is walked as few times as possible.
+constexpr uint32_t K4_BIG = 4096;
+__device__ __forceinline__ void k4_walk_phase(K4Static& S, K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* ticket,
+                                              bool defer_big = false, uint32_t* n_dirty = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const WarpTeam T;
     const uint32_t lane = lane_id();
@@ -283,7 +288,8 @@ __device__ __forceinline__ void k4_walk_phase(K4Static& S, K4Mut& M, const K4Gra
         base = __shfl_sync(FULL, base, 0);
         if (base >= v_end) break;
         const uint32_t r = base + lane;
-        const uint32_t ne = (r < v_end && (!sweep || G.stamp[r] == sweep)) ? G.comp_ne[r] : 0;
+        uint32_t ne = (r < v_end && (!sweep || G.stamp[r] == sweep)) ? G.comp_ne[r] : 0;
+        if (defer_big && ne > K4_BIG) { G.stamp[r] = sweep + 1; atomicAdd(n_dirty, 1u); ne = 0; }
         unsigned m = __ballot_sync(FULL, ne != 0);
         while (m) {
             const int src = __ffs(m) - 1;
@@ -296,7 +302,8 @@ __device__ __forceinline__ void k4_walk_phase(K4Static& S, K4Mut& M, const K4Gra
     }
 }
 
-__device__ __forceinline__ void k4_mark_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* n_dirty) {
+__device__ __forceinline__ void k4_mark_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* n_dirty,
+                                              uint32_t* n_small = nullptr) {
     const uint32_t nde = G.d_cnt[CNT_NDE];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nde; t += gridDim.x * blockDim.x) {
         const int root = G.de_root[t];
@@ -304,15 +311,21 @@ __device__ __forceinline__ void k4_mark_phase(const K4Static& S, const K4Mut& M,
         if (S.root_of[x.dst] == root) continue;
         const int a = S.del_prev[x.dst], b = M.del_cur[x.dst];
         if (a == b || G.stamp[root] == sweep + 1) continue;
+        if (S.never_final[x.src]) continue;                    // x.src is never checked against other regions' state
         const int2 wr = G.win_range[x.src];
-        if (k4_change_matters(x.src, x.dst, wr.x, min(wr.y, M.del_cur[x.src]), a, b)) { G.stamp[root] = sweep + 1; atomicAdd(n_dirty, 1u); }
+        if (k4_change_matters(x.src, x.dst, wr.x, min(wr.y, M.del_cur[x.src]), a, b)) {
+            G.stamp[root] = sweep + 1; atomicAdd(n_dirty, 1u);
+            if (n_small && G.comp_ne[root] <= K4_BIG) atomicAdd(n_small, 1u);
+        }
     }
 }
 
-__device__ __forceinline__ void k4_next_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep) {
+// reset_stamped: multi-GPU only -- every rank forgets the deletion times of the components that will be walked again (their
+// owner rewrites them, the min all-reduce then takes the owner's values); on a single GPU the walk resets its own regions.
+__device__ __forceinline__ void k4_next_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep, bool reset_stamped) {
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < (uint32_t)S.nreg; v += gridDim.x * blockDim.x) {
         G.del_prev[v] = M.del_cur[v];
-        if (G.stamp[S.root_of[v]] == sweep + 1) M.del_cur[v] = K4_NEVER;
+        if (reset_stamped && G.stamp[S.root_of[v]] == sweep + 1) M.del_cur[v] = K4_NEVER;
     }
 }
 
@@ -342,7 +355,8 @@ __device__ __forceinline__ void k4_grid_barrier(uint32_t* counter, uint32_t& epo
 }
 
 // single GPU: all sweeps in one persistent kernel. sync[0]: barrier counter, sync[1..2]: walk tickets (alternating),
-// sync[3..4]: stamped-component counts (alternating), sync[5]: number of sweeps done (result)
+// sync[3..4]: stamped-component counts (alternating), sync[5]: number of sweeps done (result), sync[6..7]: stamped small
+// components (alternating), sync[8]: there are big components
 constexpr int K4_TRACE_SWEEPS = 32;
 struct K4Trace { unsigned long long t[1 + 3 * K4_TRACE_SWEEPS]; uint32_t ndirty[K4_TRACE_SWEEPS]; };   // BDK_K4_TRACE=1: phase time stamps (ns)
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -352,16 +366,19 @@ __global__ void __launch_bounds__(K4_THREADS) k4_sweeps_kernel(K4Static S, K4Mut
     uint32_t epoch = 0;
     const bool tr = trace && blockIdx.x == 0 && threadIdx.x == 0;
     if (tr) trace->t[0] = globaltimer_ns();
+    uint32_t nsmall_prev = 1;                                      // sweep 0: the small components go first
     for (uint32_t sweep = 0;; ++sweep) {
-        k4_walk_phase(S, M, G, sweep, sync + 1 + (sweep & 1));
+        // big components wait while small ones are still being corrected (they are walked at the latest when nothing else is left)
+        k4_walk_phase(S, M, G, sweep, sync + 1 + (sweep & 1), nsmall_prev != 0, sync + 3 + (sweep & 1));
         k4_grid_barrier(sync, epoch);
         if (tr && sweep < K4_TRACE_SWEEPS) trace->t[1 + 3 * sweep] = globaltimer_ns();
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sync[1 + ((sweep + 1) & 1)] = 0; sync[3 + ((sweep + 1) & 1)] = 0; }   // last used before the barrier two phases back
-        k4_mark_phase(S, M, G, sweep, sync + 3 + (sweep & 1));
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sync[1 + ((sweep + 1) & 1)] = 0; sync[3 + ((sweep + 1) & 1)] = 0; sync[6 + ((sweep + 1) & 1)] = 0; }   // last used before the barrier two phases back
+        k4_mark_phase(S, M, G, sweep, sync + 3 + (sweep & 1), sync + 6 + (sweep & 1));
         k4_grid_barrier(sync, epoch);
         if (tr && sweep < K4_TRACE_SWEEPS) trace->t[2 + 3 * sweep] = globaltimer_ns();
         const uint32_t ndirty = ld_acquire_u32(sync + 3 + (sweep & 1));
-        k4_next_phase(S, M, G, sweep);
+        nsmall_prev = ld_acquire_u32(sync + 6 + (sweep & 1));
+        k4_next_phase(S, M, G, sweep, false);
         k4_grid_barrier(sync, epoch);
         if (tr && sweep < K4_TRACE_SWEEPS) { trace->t[3 + 3 * sweep] = globaltimer_ns(); trace->ndirty[sweep] = ndirty; }
         if (!ndirty) { if (blockIdx.x == 0 && threadIdx.x == 0) sync[5] = sweep + 1; break; }
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(GS_THREADS) k4_guess_kernel(K4Static S, K4Mut 
     k4_load_counts(S, G);
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < (uint32_t)S.nreg; v += gridDim.x * blockDim.x) {
         G.del_prev[v] = k4_guess_deletion(S, M.alive, (int)v, G.win_range[v].y);
+        G.never_final[v] = k4_never_final(S, M.alive, (int)v) ? 1 : 0;
         M.del_cur[v] = K4_NEVER;
         G.stamp[v] = 0;
     }
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(GS_THREADS) k4_mark_dirty_kernel(K4Static S, K
 }
 __global__ void __launch_bounds__(GS_THREADS) k4_next_sweep_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep) {
     k4_load_counts(S, G);
-    k4_next_phase(S, M, G, sweep);
+    k4_next_phase(S, M, G, sweep, true);
 }
 
 // ---- output order --------------------------------------------------------------------------------------

@@ -175,7 +175,14 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
     KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
     KM.del_cur = del_cur.data();
-    for (int v = 0; v < nreg; ++v) del_prev[v] = getenv("HOSTSIM_NO_GUESS") ? K4_NEVER : k4_guess_deletion(KS, alive.data(), v, win_last[v]);
+    std::vector<uint8_t> never_final(nreg + 1, 0);
+    KS.never_final = never_final.data();
+    for (int v = 0; v < nreg; ++v) {
+        del_prev[v] = getenv("HOSTSIM_NO_GUESS") ? K4_NEVER : k4_guess_deletion(KS, alive.data(), v, win_last[v]);
+        never_final[v] = k4_never_final(KS, alive.data(), v) ? 1 : 0;
+    }
+    const int big = getenv("HOSTSIM_BIG") ? atoi(getenv("HOSTSIM_BIG")) : 4096;   // tests lower it to exercise the deferral of big components
+    int nsmall_prev = 1;
     std::vector<int32_t> queue;
     // sweeps over the components until the table of deletion times is stable (same driver as bdk_finish). The components are
     // walked in DESCENDING root order on purpose: nothing may depend on the order inside a sweep.
@@ -183,27 +190,38 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     for (;; ++sweeps) {
         if (sweeps > 100000) return -101;
         KS.rerun = sweeps ? 1 : 0;
+        std::vector<int> deferred;
         for (int r = nreg - 1; r >= 0; --r) {
             if (!comp_ne[r] || (sweeps && !dirty[r])) continue;
+            if (nsmall_prev && comp_ne[r] > big) { deferred.push_back(r); continue; }
             queue.assign(comp_ne[r] + 2, 0);
             DEdge* es = de.data() + de_off[r];
-            if (!sweeps) de_sort(es, comp_ne[r]);
+            de_sort(es, comp_ne[r]);
             int used = k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r], comp_strong[r]);
             if (used > comp_strong[r]) return -100;
         }
         std::fill(dirty.begin(), dirty.end(), 0);
-        int ndirty = 0;
+        int ndirty = 0, nsmall = 0;
+        for (int r : deferred) { dirty[r] = 1; ++ndirty; }
         for (int r = 0; r < nreg; ++r)
             for (int t = de_off[r]; t < de_off[r + 1]; ++t) {
                 const DEdge& x = de[t];
                 if (root_of[x.dst] == r) continue;
-                if (!dirty[r] && k4_change_matters(x.src, x.dst, win_first[x.src], std::min(win_last[x.src], del_cur[x.src]), del_prev[x.dst], del_cur[x.dst])) { dirty[r] = 1; ++ndirty; }
+                if (never_final[x.src]) continue;
+                if (!dirty[r] && k4_change_matters(x.src, x.dst, win_first[x.src], std::min(win_last[x.src], del_cur[x.src]), del_prev[x.dst], del_cur[x.dst])) {
+                    dirty[r] = 1; ++ndirty;
+                    if (comp_ne[r] <= big) ++nsmall;
+                }
             }
-        for (int v = 0; v < nreg; ++v) { del_prev[v] = del_cur[v]; if (dirty[root_of[v]]) del_cur[v] = K4_NEVER; }
+        for (int v = 0; v < nreg; ++v) del_prev[v] = del_cur[v];      // (the walk resets the regions of its own component)
+        nsmall_prev = nsmall;
         if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: sweep %d -> %d components to walk again\n", sweeps, ndirty);
         if (!ndirty) break;
     }
-    if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: %d regions, %zu edges, %d sweeps\n", nreg, ue.size(), sweeps + 1);
+    if (getenv("HOSTSIM_VERBOSE")) {
+        int mx = 0, nf = 0; for (int r = 0; r < nreg; ++r) { mx = std::max(mx, comp_ne[r]); nf += never_final[r]; }
+        fprintf(stderr, "hostsim: %d regions (%d never final), %zu edges, largest component %d directed edges, %d sweeps\n", nreg, nf, ue.size(), mx, sweeps + 1);
+    }
     // final order: stable by (window, BFS start vertex), slot order inside
     std::vector<int> order;
     for (int r = 0; r < nrow_cap; ++r) if (row_emit[r]) order.push_back(r);
