@@ -81,7 +81,7 @@ struct bdk_ctx {
     DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
         d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt, d_de_root,
         d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
-        d_deleted, d_de, d_de2, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_sort_k, d_sort_v, d_pois_l, d_pois_k, d_pois_o;
+        d_deleted, d_de, d_de2, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_sort_k, d_sort_v, d_sort_k2, d_sort_v2, d_pois_l, d_pois_k, d_pois_o;
     int k5_smem_rows = K5_SMEM_ROWS;   // tables up to this many row slots are ordered by the single-CTA shared-memory sort
     uint64_t d2h_bytes = 0;
     uint32_t n_slots = 0;
@@ -110,9 +110,11 @@ struct bdk_ctx {
     uint32_t A_local = 0;             // anomalous reads of this rank's slice (c->A becomes the global count)
     uint64_t comm_bytes = 0;          // bytes this rank received in the exchanges of the last job
     DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff, d_cuts;
-    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range, d_never_final;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
+    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range, d_never_final, d_big_list;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
     uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
+    uint32_t k4_cta_min = K4_CTA_MIN, k4_big_min = K4_BIG;   // BDK_K4_CTA_MIN / BDK_K4_BIG (tests)
+    int k4_maxr = K4C_MAXR;                   // BDK_K4_MAXR (tests)
     std::vector<uint32_t> h_cuts;     // [2][nranks + 1] vertex / row-slot cuts of the last bdk_finish
 };
 
@@ -390,12 +392,12 @@ void bdk_destroy(bdk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
     c->comm = nullptr;
-    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_never_final, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
+    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_never_final, &c->d_big_list, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt, &c->d_de_root,
         &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
-        &c->d_deleted, &c->d_de, &c->d_de2, &c->d_queue, &c->d_rowpack, &c->d_outpack, &c->d_slot_order, &c->d_sort_hist, &c->d_sort_k, &c->d_sort_v, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
+        &c->d_deleted, &c->d_de, &c->d_de2, &c->d_queue, &c->d_rowpack, &c->d_outpack, &c->d_slot_order, &c->d_sort_hist, &c->d_sort_k, &c->d_sort_v, &c->d_sort_k2, &c->d_sort_v2, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
@@ -520,11 +522,16 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         CUC(cudaMalloc(&c->d_carry_out.p, ncomp * 4)); c->d_carry_out.cap = ncomp * 4;
         {
             int k4bps = 0, nsm = kNumSMs;
-            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k4bps, k4_sweeps_kernel, K4_THREADS, 0));
+            CUC(cudaFuncSetAttribute(k4_sweeps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4CtaSmem)));
+            CUC(cudaFuncSetAttribute(k4_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4CtaSmem)));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k4bps, k4_sweeps_kernel, K4_THREADS, sizeof(K4CtaSmem)));
             CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
             c->k4_grid_max = std::max(1, k4bps) * nsm;
             CUC(cudaMalloc(&c->d_k4sync.p, 64 + sizeof(K4Trace))); c->d_k4sync.cap = 64 + sizeof(K4Trace);
         }
+        if (const char* e = getenv("BDK_K4_CTA_MIN")) c->k4_cta_min = (uint32_t)std::max(0, atoi(e));
+        if (const char* e = getenv("BDK_K4_BIG")) c->k4_big_min = (uint32_t)std::max(0, atoi(e));
+        if (const char* e = getenv("BDK_K4_MAXR")) c->k4_maxr = std::max(0, std::min(atoi(e), (int)K4C_MAXR));
         if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
         CUC(cudaFuncSetAttribute(k5_order_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM_ROWS * 12));
         if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
@@ -682,8 +689,8 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     const size_t L1 = (size_t)A / 2 + 2;
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
-    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8); ENS(c->d_never_final, A1);
-    ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (2 * L1 + 2 * A1 + 4) * 4);
+    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8); ENS(c->d_never_final, A1); ENS(c->d_big_list, A1 * 4);
+    ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (4 * L1 + 2 * A1 + 8) * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
     const int dummy = dummy_region_of(c->P);
@@ -724,7 +731,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     device_scan(st, LoadU32{c->d_comp_ne.as<uint32_t>()}, ExclOut{c->d_de_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NDE, 0, ssc);
     device_scan(st, LoadU32{c->d_comp_strong.as<uint32_t>()}, ExclOut{c->d_row_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NROW, 0, ssc);
     k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_de_off.as<uint32_t>(),
-                                                            c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->period, c->d_win_range.as<int2>());
+                                                            c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->period, c->d_win_range.as<int2>(), c->d_comp_ne.as<uint32_t>(), d_cnt);
     k3_rank_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->d_de_off.as<uint32_t>(),
                                                          c->d_comp_ne.as<uint32_t>(), c->d_de2.as<DEdge>(), d_cnt);
     c->launches += 2 + 4 + 3 + 3 + 2;   // join, links, init/union/flatten/count, 2 scans, scatter, rank
@@ -743,6 +750,31 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     if (c->h_cnt[CNT_ERR] & K3_ERR_DUPNAME)
         return fail(c, BDK_ERR_DATA, "a read-name key occurs more than twice among the anomalous reads");
     const uint32_t nrow = c->h_cnt[CNT_NROW], nreg = c->h_cnt[CNT_NREG];
+    bool all_sorted = false;
+    if (c->h_cnt[CNT_NBIG]) {   // some component is too large for the rank sort: radix-sort all directed edges (see k3_edge_keys_kernel)
+        const uint32_t nde = c->h_cnt[CNT_NDE];
+        int vbits = 1; while ((1ull << vbits) < (uint64_t)nreg + 1) ++vbits;
+        int wbits = 1; while ((1ull << wbits) < (uint64_t)nreg / c->period + 2) ++wbits;
+        int obits = 1; while ((1ull << obits) < (uint64_t)nde + 1) ++obits;
+        if (2 * vbits + wbits <= 64) {
+            tstart(c, T_K3);
+            ENS(c->d_sort_hist, 256 * SS_GRID * 4);
+            ENS(c->d_sort_k, (size_t)(nde + 1) * 8); ENS(c->d_sort_v, (size_t)(nde + 1) * 4);
+            ENS(c->d_sort_k2, (size_t)(nde + 1) * 8); ENS(c->d_sort_v2, (size_t)(nde + 1) * 4);
+            unsigned long long* kk = c->d_sort_k2.as<unsigned long long>(); uint32_t* vv = c->d_sort_v2.as<uint32_t>();
+            SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_sort_k.as<unsigned long long>(), c->d_sort_v.as<uint32_t>()};
+            k3_edge_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), d_cnt, vbits, kk, vv);
+            device_radix_sort(st, &kk, &vv, d_cnt + CNT_NDE, 0, 2 * vbits + wbits, sosc);
+            k3_edge_segment_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(vv, c->d_de_root.as<int32_t>(), c->d_de_off.as<uint32_t>(), d_cnt, kk);
+            device_radix_sort(st, &kk, &vv, d_cnt + CNT_NDE, 0, obits, sosc);
+            k3_edge_gather_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), vv, d_cnt, c->d_de2.as<DEdge>());
+            c->launches += 3 + 3 * (uint64_t)((2 * vbits + wbits + 7) / 8 + (obits + 7) / 8);
+            tstop(c, T_K3);
+            CU(cudaGetLastError());
+            // the ping-pong may have swapped the scratch pointers: they all stay owned by the same DevBufs (sizes are equal)
+            all_sorted = true;
+        }
+    }
 
     // ---- K4 ----------------------------------------------------------------------------------
     // per-row outputs by slot (K4 writes them) and, after ordering, by output position (one block, one copy to a
@@ -785,8 +817,11 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     tstart(c, T_K4);
     const uint32_t v_lo = c->comm ? c->h_cuts[c->rank] : 0u, v_hi = c->comm ? c->h_cuts[c->rank + 1] : 0xffffffffu;
     c->k4_sweeps = 0;
-    bool sweeps_on_device = false;
+    bool sweeps_on_device = false, k4_ran = false;
+    K4Graph G_score;
+    memset(&G_score, 0, sizeof G_score);
     if (nrow || c->h_cnt[CNT_NDE]) {
+        k4_ran = true;
         // Sweeps over the components (bdk_logic.h, K4Static): the first walks all of them against an empty table of
         // deletion times; each later one walks again the components that looked, across an edge that is never followed, at a
         // region whose deletion time changed. Stable table = the reference's sequential result.
@@ -794,18 +829,24 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         G.comp_ne = c->d_comp_ne.as<uint32_t>(); G.comp_strong = c->d_comp_strong.as<uint32_t>(); G.de_off = c->d_de_off.as<uint32_t>();
         G.row_off = c->d_row_off.as<uint32_t>(); G.de = c->d_de.as<DEdge>(); G.de_sorted = c->d_de2.as<DEdge>(); G.de_root = c->d_de_root.as<int32_t>();
         G.queue = c->d_queue.as<int32_t>(); G.stamp = c->d_dirty.as<uint32_t>(); G.del_prev = c->d_del_prev.as<int32_t>(); G.win_range = c->d_win_range.as<int2>(); G.never_final = c->d_never_final.as<uint8_t>();
-        G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi;
+        G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi; G.all_sorted = all_sorted ? 1 : 0;
+        G.big_list = c->d_big_list.as<uint32_t>(); G.big_count = d_cnt + CNT_K4_NBIGLIST;
+        G.cta_min = c->k4_cta_min; G.big_min = c->k4_big_min; G.maxr = c->k4_maxr;
+        G.trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
+        if (G.trace) CU(cudaMemsetAsync(G.trace, 0, sizeof(K4Trace), st));
+        CU(cudaMemsetAsync(d_cnt + CNT_K4_NBIGLIST, 0, 8, st));   // list length and the multi-GPU walk's cursor
         k4_guess_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G);     // starting table, cleared stamps
         c->launches += 1;
+        G_score = G;
         const bool mine = v_lo < std::min(v_hi, nreg);
         const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
         if (!c->comm || N == 1) {   // one persistent cooperative kernel, grid-wide barriers between the phases
             uint32_t* sync = c->d_k4sync.as<uint32_t>();
             CU(cudaMemsetAsync(sync, 0, 64, st));
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->k4_grid_max));
-            K4Trace* trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
+            K4Trace* trace = G.trace;
             void* args[] = {&S, &M, &G, &sync, &trace};
-            CU(cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, 0, st));
+            CU(cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, sizeof(K4CtaSmem), st));
             c->launches += 1;
             sweeps_on_device = true;
         } else {                    // one launch per phase; the owners' deletion times go to every rank in between
@@ -813,8 +854,8 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)kNumSMs * 16));
             for (uint32_t sweep = 0;; ++sweep) {
                 if (sweep > 100000) return fail(c, BDK_ERR_STATE, "connection walk did not reach a fixed point");
-                if (sweep) CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 4, st));
-                if (mine) { k4_components_kernel<<<grid, K4_THREADS, 0, st>>>(S, M, G, sweep, d_cnt + CNT_K4_TICKET); c->launches += 1; }
+                if (sweep) { CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 4, st)); CU(cudaMemsetAsync(d_cnt + CNT_K4_BIGCUR, 0, 4, st)); }
+                if (mine) { k4_components_kernel<<<grid, K4_THREADS, sizeof(K4CtaSmem), st>>>(S, M, G, sweep, d_cnt + CNT_K4_TICKET, d_cnt + CNT_K4_BIGCUR); c->launches += 1; }
                 NC(nc->AllReduce(c->d_del_cur.p, c->d_del_cur.p, nreg, ncclInt32, ncclMin, c->comm, st));   // K4_NEVER where not the owner
                 c->comm_bytes += (uint64_t)nreg * 4;
                 CU(cudaMemsetAsync(d_cnt + CNT_NDIRTY, 0, 4, st));
@@ -829,6 +870,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
             }
         }
     }
+    if (k4_ran) { k4_score_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G_score); c->launches += 1; }
     tstop(c, T_K4);
     CU(cudaGetLastError());
     if (c->comm && nrow) {   // exchange 2: every rank's row slots (contiguous per rank) to every rank
@@ -901,6 +943,11 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         for (uint32_t sw = 0; sw < std::min<uint32_t>(c->k4_sweeps, K4_TRACE_SWEEPS); ++sw)
             fprintf(stderr, "  sweep %2u: walk %7.1f us  mark %6.1f us  next %6.1f us  -> %u components to walk again\n", sw,
                     (tr.t[1 + 3 * sw] - tr.t[3 * sw]) / 1e3, (tr.t[2 + 3 * sw] - tr.t[1 + 3 * sw]) / 1e3, (tr.t[3 + 3 * sw] - tr.t[2 + 3 * sw]) / 1e3, tr.ndirty[sw]);
+        if (tr.cta_windows)
+            fprintf(stderr, "  CTA walks of big components: %llu candidates passed their last 32 reads, %llu further 32-read chunks scanned, largest such region %llu reads\n",
+                    tr.cta_survivors, tr.cta_chunks, tr.cta_maxreads),
+            fprintf(stderr, "  CTA walks of big components: %llu windows, %llu pieces, %llu candidates, %llu rounds; ms: stage %.2f runs %.2f labels %.2f pieces %.2f walk %.2f final %.2f resolve %.2f\n",
+                    tr.cta_windows, tr.cta_pieces, tr.cta_cands, tr.cta_rounds, tr.cta[0] / 1e6, tr.cta[1] / 1e6, tr.cta[2] / 1e6, tr.cta[3] / 1e6, tr.cta[4] / 1e6, tr.cta[5] / 1e6, tr.cta[6] / 1e6);
     }
     c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet
     c->n_slots = nrow;

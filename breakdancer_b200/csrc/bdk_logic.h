@@ -280,11 +280,12 @@ struct K4Mut {
     int32_t* row_lib_span;  // [nrow_cap][nlib]
     uint32_t* row_cn_count; // [nrow_cap][nkey]
     float* row_cn;          // [nrow_cap][nkey]
-    uint8_t* row_emit;      // [nrow_cap]
+    uint8_t* row_emit;      // [nrow_cap] K4_ROW_*
     uint64_t* row_key;      // [nrow_cap] (window << 32 | BFS start vertex)
 };
 
 struct WindowInfo { int32_t cF; int32_t maxlen; int32_t last_region; int32_t w; };
+enum { K4_ROW_NONE = 0, K4_ROW_EMIT = 1, K4_ROW_PENDING = 2 };   // row_emit[]: no call / call to print / walked, not scored yet
 
 BDK_HD WindowInfo k4_window_info(const K4Static& S, int w) {
     WindowInfo wi;
@@ -400,17 +401,26 @@ struct WarpTeam {
 };
 #endif
 
+// does read j keep its region from being final (is_region_final's per-read test)?
+BDK_HD bool k4_read_blocks_final(const K4Static& S, const K4Mut& M, int j, const WindowInfo& wi) {
+    if (!M.alive[j]) return false;
+    if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) return false;
+    return !k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF, wi.w);
+}
+
 template <class Team>
 BDK_HD bool k4_region_final(const Team& T, const K4Static& S, const K4Mut& M, int v, const WindowInfo& wi) {
     if (M.deleted[v] || v == wi.last_region) return false;
     const RegionRec& R = S.reg[v];
-    bool bad = false;
-    for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
-        if (!M.alive[j]) continue;
-        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
-        if (!k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF, wi.w)) bad = true;
+    // A team-wide chunk of reads at a time, stopping at the first blocking read. From the END of the region: the reads whose
+    // mates lie ahead (in regions that are not registered yet) are its last ones, so a region that is not final is usually
+    // found out in the first chunk.
+    for (int j1 = R.first_read + R.n_reads; j1 > R.first_read; j1 -= T.width()) {
+        const int j = j1 - 1 - T.lane();
+        const bool bad = j >= R.first_read && k4_read_blocks_final(S, M, j, wi);
+        if (T.any(bad)) return false;
     }
-    return !T.any(bad);
+    return true;
 }
 
 // read y is the later mate of a pair (x, y) whose both reads are still held by regions s0 / s1
@@ -432,16 +442,36 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
     int n = s1 >= 0 ? 2 : 1;
     int sn[2] = {s0, s1};
     T.sync();
-    // pass 1: count pairs per flag (flag of the second-seen mate, SvBuilder.cpp:101-118)
+    // pass 1: count pairs per flag (flag of the second-seen mate, SvBuilder.cpp:101-118). What is decided per read here
+    // (nothing / name gone: drop it / pair with x) is exactly what pass 2 acts on -- nothing changes in between, and inside
+    // pass 2 a read is only touched by its own lane and by the lane of its later mate, which write the same values -- so when
+    // every lane has at most K4_DEC reads the decisions are kept and pass 2 issues no dependent loads of its own.
+    constexpr int K4_DEC = 6;
+    int dec[K4_DEC];                 // x >= 0: pair (x, y); -1: nothing; -2: drop y
+    uint32_t dmeta[K4_DEC];
+    int32_t dabs[K4_DEC];
+    int iters = 0;
+    for (int i = 0; i < n; ++i) iters += (S.reg[sn[i]].n_reads + T.width() - 1) / T.width();
+    const bool keep = iters <= K4_DEC;
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0, c9 = 0, c10 = 0;
+    int it = 0;
     for (int i = 0; i < n; ++i) {
         const RegionRec& R = S.reg[sn[i]];
-        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width()) {
-            if (!M.alive[y] || !k4_exists(S, M, y, wi.cF)) continue;
-            if (k4_pair_of(S, M, y, s0, s1, wi.cF) < 0) continue;
-            int f = meta_flag(S.ar[y].meta);
-            c0 += f == 0; c1 += f == 1; c2 += f == 2; c3 += f == 3; c4 += f == 4; c5 += f == 5;
-            c6 += f == 6; c7 += f == 7; c8 += f == 8; c9 += f == 9; c10 += f == 10;
+        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width(), ++it) {
+            int d = -1; uint32_t my = 0; int32_t ab = 0;
+            if (M.alive[y]) {
+                if (!k4_exists(S, M, y, wi.cF)) d = -2;
+                else {
+                    d = k4_pair_of(S, M, y, s0, s1, wi.cF);
+                    if (d >= 0) {
+                        my = S.ar[y].meta; ab = S.ar[y].abs_isize;
+                        int f = meta_flag(my);
+                        c0 += f == 0; c1 += f == 1; c2 += f == 2; c3 += f == 3; c4 += f == 4; c5 += f == 5;
+                        c6 += f == 6; c7 += f == 7; c8 += f == 8; c9 += f == 9; c10 += f == 10;
+                    }
+                }
+            }
+            if (keep) { dec[it] = d; dmeta[it] = my; dabs[it] = ab; }
         }
     }
     int flag_counts[BDK_NUM_FLAGS] = {T.sum(c0), T.sum(c1), T.sum(c2), T.sum(c3), T.sum(c4), T.sum(c5),
@@ -458,31 +488,56 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
     T.sync();
     // pass 2: consume the pairs, drop reads whose name no longer exists. A read is touched only by its own
     // lane and by the lane of its (later) mate, and both write the same values, so the lanes do not interfere.
+    it = 0;
     for (int i = 0; i < n; ++i) {
         const RegionRec& R = S.reg[sn[i]];
-        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width()) {
-            if (!M.alive[y]) continue;
-            if (!k4_exists(S, M, y, wi.cF)) { M.alive[y] = 0; continue; }
-            int x = k4_pair_of(S, M, y, s0, s1, wi.cF);
+        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width(), ++it) {
+            int x; uint32_t my; int32_t ab;
+            if (keep) { x = dec[it]; my = dmeta[it]; ab = dabs[it]; }
+            else {
+                x = -1; my = 0; ab = 0;
+                if (M.alive[y]) {
+                    if (!k4_exists(S, M, y, wi.cF)) x = -2;
+                    else { x = k4_pair_of(S, M, y, s0, s1, wi.cF); if (x >= 0) { my = S.ar[y].meta; ab = S.ar[y].abs_isize; } }
+                }
+            }
+            if (x == -2) { M.alive[y] = 0; continue; }
             if (x < 0) continue;
             // pair (x, y): remove_reads_in_region_if(is_supportive) (BreakDancer.cpp:367-368)
             M.alive[x] = 0; M.alive[y] = 0;
             M.sv_of_read[x] = row; M.sv_of_read[y] = row;
             if (!early) {
                 M.freed[x] = 1; M.freed[y] = 1;     // erase_read at the end (BreakDancer.cpp:510-511)
-                uint32_t my = S.ar[y].meta;
                 if (meta_flag(my) == flag) {
                     int l = meta_lib(my);
                     T.add(lib_count + l, 1);
-                    T.add(lib_span + l, S.ar[y].abs_isize);
+                    T.add(lib_span + l, ab);
                 }
             }
         }
     }
     T.sync();
     if (T.lane() != 0) return false;
-    M.row_emit[row] = 0;
+    // The walk goes on without the call itself: coordinates, copy number, size and the Poisson score do not feed back into
+    // the walk and are computed afterwards for all row slots at once (k4_score_row).
+    M.row_emit[row] = K4_ROW_NONE;
     if (early) return false;
+    bdk_sv& o = M.rows[row];
+    o.region[0] = s0; o.region[1] = s1; o.flag = flag; o.num_pairs = flag_counts[flag]; o.window = w;
+    M.row_key[row] = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;       // the reference prints by (window, BFS start), calls of one BFS in slot order
+    M.row_emit[row] = K4_ROW_PENDING;
+    return true;
+}
+
+// Second half of process_sv for row slot `row` left PENDING by the walk (BreakDancer.cpp:377-497): breakpoint coordinates,
+// copy number, size, ComputeProbScore, the -y cut. One thread per row.
+BDK_HD void k4_score_row(const K4Static& S, K4Mut& M, int row) {
+    bdk_sv& o = M.rows[row];
+    const int s0 = o.region[0], s1 = o.region[1], flag = o.flag, nflag = o.num_pairs, w = o.window;
+    const int n = s1 >= 0 ? 2 : 1;
+    const WindowInfo wi = k4_window_info(S, w);
+    const int32_t* lib_count = M.row_lib_count + (int64_t)row * S.nlib;
+    const int32_t* lib_span = M.row_lib_span + (int64_t)row * S.nlib;
 
     const RegionRec& R0 = S.reg[s0];
     int chr0 = R0.tid, chr1, pos0 = R0.start, pos1 = R0.end;
@@ -526,7 +581,7 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
     for (int l = 0; l < S.nlib; ++l)
         if (lib_count[l])
             diff = f_add(diff, f_sub((float)lib_span[l], f_mul((float)lib_count[l], S.lib_mean[l])));
-    int diffspan = (int)((double)f_div(diff, (float)flag_counts[flag]) + 0.5);
+    int diffspan = (int)((double)f_div(diff, (float)nflag) + 0.5);
 
     int total_region_size = (R0.end - R0.start + 1) + (n == 2 ? (S.reg[s1].end - S.reg[s1].start + 1) : 0);
     double logp = 0.0, err = 0.0;
@@ -549,17 +604,13 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
     double phred_tmp = -10.0 * logp / log(10.0);
     int phred = phred_tmp > 99 ? 99 : (int)(phred_tmp + 0.5);
     ++pos0; ++pos1;
-    if (!(phred > S.score_threshold)) return false;
-    bdk_sv& o = M.rows[row];
+    if (!(phred > S.score_threshold)) { M.row_emit[row] = K4_ROW_NONE; return; }
     o.chr[0] = chr0; o.chr[1] = chr1; o.pos[0] = pos0; o.pos[1] = pos1;
     o.fwd[0] = fwd0; o.fwd[1] = fwd1; o.rev[0] = rev0; o.rev[1] = rev1;
-    o.flag = flag; o.diffspan = diffspan; o.score = phred; o.num_pairs = flag_counts[flag];
+    o.diffspan = diffspan; o.score = phred;
     o.logp = logp; o.allele_frequency = af; o.cn_present = 0;
-    o.region[0] = s0; o.region[1] = s1; o.window = w; o.order = 0;
-    const uint64_t key = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;
-    M.row_key[row] = key;       // the reference prints by (window, BFS start), calls of one BFS in slot order
-    M.row_emit[row] = 1;
-    return true;
+    o.order = 0;
+    M.row_emit[row] = K4_ROW_EMIT;
 }
 
 // ---- in-place heap sort of a component's directed edges by (win, src, dst) --------------------
@@ -623,19 +674,105 @@ BDK_HD DEdge* de_sort_team(const Team& T, DEdge* e, int ne, DEdge* scratch) {
     return scratch;
 }
 
+// One step of build_connection's outer loop: the BFS from vertex v (edge run e[vi..vend) inside the window e[i..j)) if v
+// still has an edge the walk would follow. Uses queue[0 .. edges reached + 1) and row slots row, row + 1, ...; returns the next
+// free row slot. Touches only the regions reachable from v over followable edges.
+template <class Team>
+BDK_HD int k4_bfs_from(const Team& T, const K4Static& S, K4Mut& M, DEdge* e, int i, int j, int w, const WindowInfo& wi, int vi, int vend,
+                       int32_t* queue, int row) {
+    const bool lead = T.lane() == 0;
+    const int v = e[vi].src;
+    bool live = false;          // v has an edge the BFS would follow; otherwise a BFS from v changes nothing
+    for (int k = vi; k < vend; ++k)
+        live = live || (!(e[k].flags & DE_ERASED) && e[k].w >= S.min_read_pair && !M.deleted[e[k].dst]);
+    if (!live || (e[vi].flags & DE_VERASED) || M.deleted[v]) return row;
+    // tails live in queue[qa..qb), newtails appended after
+    int qa = 0, qb = 0, qn;
+    T.sync();
+    if (lead) queue[0] = v;
+    T.sync();
+    qb = 1;
+    while (qa < qb) {
+        qn = qb;
+        for (int t = qa; t < qb; ++t) {
+            int tail = queue[t];
+            if (M.deleted[tail]) continue;                     // !region_exists(tail)
+            int ts = de_find_src(e, i, j, tail);
+            if (ts < 0 || (e[ts].flags & DE_VERASED)) continue; // graph.find(tail) == end
+            for (int k = ts; k < j && e[k].src == tail; ++k) {
+                if (e[k].flags & DE_ERASED) continue;
+                int s1 = e[k].dst, nlinks = e[k].w;
+                // An edge that is too weak or leads to a deleted region is erased without any other
+                // effect, and meeting it again (from either side, in this window) would again have no
+                // effect: it needs no mark. Only edges that are followed are erased both ways.
+                if (nlinks < S.min_read_pair || M.deleted[s1]) continue;
+                int rq = -1;
+                if (tail != s1) {                               // erase_edge(s1, tail)
+                    int rs = de_find_src(e, i, j, s1);
+                    if (rs >= 0)
+                        for (int q = rs; q < j && e[q].src == s1; ++q)
+                            if (e[q].dst == tail) { rq = q; break; }
+                }
+                T.sync();
+                if (lead) {
+                    e[k].flags |= DE_ERASED;
+                    if (rq >= 0) e[rq].flags |= DE_ERASED;
+                    queue[qn] = s1;                             // newtails.push_back(s1)
+                }
+                T.sync();
+                ++qn;
+                int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
+                k4_process_sv(T, S, M, a, tail != s1 ? b : -1, w, v, wi, row);
+                ++row;
+            }
+            T.sync();
+            if (lead) e[ts].flags |= DE_VERASED;                // graph.erase(tail)
+            T.sync();
+        }
+        qa = qb; qb = qn;
+    }
+    return row;
+}
+
+// a later sweep: one edge slot back to the state before the first one (and, once per run of a source, the region and its reads)
+BDK_HD void k4_reset_slot(const K4Static& S, K4Mut& M, DEdge* e, int q) {
+    e[q].flags = 0;
+    const int v = e[q].src;
+    if (q > 0 && e[q - 1].src == v) return;          // a region may have a run in several windows: all write the same values
+    M.deleted[v] = 0; M.del_cur[v] = K4_NEVER;
+    const RegionRec& R = S.reg[v];
+    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) { M.alive[j] = (uint8_t)R.stored; M.freed[j] = 0; M.sv_of_read[j] = -1; }
+}
+
+// build_connection for the part e[i..j) of one flush window that belongs to this component; returns the next free row slot
+template <class Team>
+BDK_HD int k4_window_seq(const Team& T, const K4Static& S, K4Mut& M, DEdge* e, int i, int j, int w, const WindowInfo& wi, int32_t* queue, int row) {
+    const bool lead = T.lane() == 0;
+    // outer loop over vertices ascending (graph.begin() .. end())
+    int vi = i;
+    while (vi < j) {
+        int vend = vi;
+        while (vend < j && e[vend].src == e[vi].src) ++vend;
+        row = k4_bfs_from(T, S, M, e, i, j, w, wi, vi, vend, queue, row);
+        vi = vend;
+    }
+    // is_region_final / clear_region over the active nodes, ascending
+    for (vi = i; vi < j;) {
+        int v = e[vi].src;
+        const bool fin = !S.never_final[v] && k4_region_final(T, S, M, v, wi);
+        T.sync();
+        if (fin && lead) { M.deleted[v] = 1; M.del_cur[v] = w; }
+        T.sync();
+        while (vi < j && e[vi].src == v) ++vi;
+    }
+    return row;
+}
+
 template <class Team>
 BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* sorted by (win, src, dst) */, int ne, int32_t* queue, int row0, int nrows) {
-    const bool lead = T.lane() == 0;
     T.sync();
-    if (S.rerun) {      // a later sweep: back to the state before the first one (edges, regions, their reads, row slots)
-        for (int q = T.lane(); q < ne; q += T.width()) {
-            e[q].flags = 0;
-            const int v = e[q].src;
-            if (q > 0 && e[q - 1].src == v) continue;          // once per run of a source (a region may have a run in several windows)
-            M.deleted[v] = 0; M.del_cur[v] = K4_NEVER;
-            const RegionRec& R = S.reg[v];
-            for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) { M.alive[j] = (uint8_t)R.stored; M.freed[j] = 0; M.sv_of_read[j] = -1; }
-        }
+    if (S.rerun) {
+        for (int q = T.lane(); q < ne; q += T.width()) k4_reset_slot(S, M, e, q);
         for (int r = T.lane(); r < nrows; r += T.width()) M.row_emit[row0 + r] = 0;
         T.sync();
     }
@@ -645,78 +782,42 @@ BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* 
         int w = e[i].win;
         int j = i;
         while (j < ne && e[j].win == w) ++j;
-        WindowInfo wi = k4_window_info(S, w);
-        // outer loop over vertices ascending (graph.begin() .. end())
-        int vi = i;
-        while (vi < j) {
-            int v = e[vi].src;
-            int vend = vi;
-            bool live = false;          // v has an edge the BFS would follow; otherwise a BFS from v changes nothing
-            while (vend < j && e[vend].src == v) {
-                live = live || (!(e[vend].flags & DE_ERASED) && e[vend].w >= S.min_read_pair && !M.deleted[e[vend].dst]);
-                ++vend;
-            }
-            if (live && !(e[vi].flags & DE_VERASED) && !M.deleted[v]) {
-                // BFS from v; tails live in queue[qa..qb), newtails appended after
-                int qa = 0, qb = 0, qn;
-                T.sync();
-                if (lead) queue[0] = v;
-                T.sync();
-                qb = 1;
-                while (qa < qb) {
-                    qn = qb;
-                    for (int t = qa; t < qb; ++t) {
-                        int tail = queue[t];
-                        if (M.deleted[tail]) continue;                     // !region_exists(tail)
-                        int ts = de_find_src(e, i, j, tail);
-                        if (ts < 0 || (e[ts].flags & DE_VERASED)) continue; // graph.find(tail) == end
-                        for (int k = ts; k < j && e[k].src == tail; ++k) {
-                            if (e[k].flags & DE_ERASED) continue;
-                            int s1 = e[k].dst, nlinks = e[k].w;
-                            // An edge that is too weak or leads to a deleted region is erased without any other
-                            // effect, and meeting it again (from either side, in this window) would again have no
-                            // effect: it needs no mark. Only edges that are followed are erased both ways.
-                            if (nlinks < S.min_read_pair || M.deleted[s1]) continue;
-                            int rq = -1;
-                            if (tail != s1) {                               // erase_edge(s1, tail)
-                                int rs = de_find_src(e, i, j, s1);
-                                if (rs >= 0)
-                                    for (int q = rs; q < j && e[q].src == s1; ++q)
-                                        if (e[q].dst == tail) { rq = q; break; }
-                            }
-                            T.sync();
-                            if (lead) {
-                                e[k].flags |= DE_ERASED;
-                                if (rq >= 0) e[rq].flags |= DE_ERASED;
-                                queue[qn] = s1;                             // newtails.push_back(s1)
-                            }
-                            T.sync();
-                            ++qn;
-                            int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
-                            k4_process_sv(T, S, M, a, tail != s1 ? b : -1, w, v, wi, row);
-                            ++row;
-                        }
-                        T.sync();
-                        if (lead) e[ts].flags |= DE_VERASED;                // graph.erase(tail)
-                        T.sync();
-                    }
-                    qa = qb; qb = qn;
-                }
-            }
-            vi = vend;
-        }
-        // is_region_final / clear_region over the active nodes, ascending
-        for (vi = i; vi < j;) {
-            int v = e[vi].src;
-            const bool fin = !S.never_final[v] && k4_region_final(T, S, M, v, wi);
-            T.sync();
-            if (fin && lead) { M.deleted[v] = 1; M.del_cur[v] = w; }
-            T.sync();
-            while (vi < j && e[vi].src == v) ++vi;
-        }
+        row = k4_window_seq(T, S, M, e, i, j, w, k4_window_info(S, w), queue, row);
         i = j;
     }
     return row - row0;
+}
+
+// ---- the same window, split into independent pieces (used for components too large for one sequential walk) --------
+// Inside one flush window the BFS trees that share no region do not interact: the window's graph falls into pieces
+// (connected over the edges the walk follows), each walked on its own, in any order or concurrently, with its own queue and
+// row slots (slot order only matters inside one BFS). The is_region_final pass over the active nodes is then evaluated for
+// all nodes against the state before the pass, and the ascending-order dependency (a node cleared earlier in the same pass
+// takes its reads' name entries along) is resolved afterwards:
+//   node v is cleared  <=>  it is final against the earlier state  and  no still-held read of v has its still-held mate in a
+//                            region rm < v that is cleared in this same pass.
+enum { K4_FIN_NOT = 0, K4_FIN_UNDECIDED = 1, K4_FIN_CLEARED = 2 };
+
+// dependencies of candidate v on the other candidates of this pass (cand[0..ncand) ascending, state[] their current state):
+// bit 0: some dependency is already cleared, bit 1: some dependency is still undecided
+template <class Team>
+BDK_HD int k4_final_deps(const Team& T, const K4Static& S, const K4Mut& M, int v, const int32_t* cand, const uint8_t* state, int ncand) {
+    const RegionRec& R = S.reg[v];
+    bool cleared = false, undecided = false;
+    for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
+        if (!M.alive[j]) continue;
+        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
+        const int m = S.mate[j];
+        if (m < 0 || !M.alive[m]) continue;
+        const int rm = S.read_region[m];
+        if (rm < 0 || rm >= v) continue;
+        int a = 0, b = ncand;                               // rm among the candidates?
+        while (a < b) { int mid = (a + b) >> 1; if (cand[mid] < rm) a = mid + 1; else b = mid; }
+        if (a >= ncand || cand[a] != rm) continue;
+        if (state[a] == K4_FIN_CLEARED) cleared = true;
+        else if (state[a] == K4_FIN_UNDECIDED) undecided = true;
+    }
+    return (T.any(cleared) ? 1 : 0) | (T.any(undecided) ? 2 : 0);
 }
 
 }  // namespace bdk

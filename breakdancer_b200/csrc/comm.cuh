@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(GS_THREADS) comm_emit_list_kernel(const uint8_
         const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ emit_count, uint64_t* __restrict__ emit_key, uint32_t* __restrict__ emit_slot) {
     const uint32_t nrow = d_cnt[CNT_NROW];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nrow; s += gridDim.x * blockDim.x) {
-        if (!row_emit[s]) continue;
+        if (row_emit[s] != K4_ROW_EMIT) continue;
         const uint32_t idx = atomicAdd(emit_count, 1u);
         emit_key[idx] = row_key[s]; emit_slot[idx] = s;
     }

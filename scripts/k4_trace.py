@@ -5,12 +5,13 @@ os.environ["BDK_K4_TRACE"] = "1"
 import numpy as np, torch
 from breakdancer_b200 import api, synth, synth_torch
 config = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+pairs = int(sys.argv[2]) if len(sys.argv) > 2 else (300_000_000 if config == 3 else 50_000_000)
 dev = torch.device("cuda", 0)
 if config == 3:
-    cols = synth_torch.config3_device(300_000_000, 20260102, dev)
+    cols = synth_torch.config3_device(pairs, 20260102, dev)
     bundle, cfg = synth_torch.config3_bundle()
 else:
-    cols = synth_torch.config2_device(50_000_000, 20260101, dev, tid=0)
+    cols = synth_torch.config2_device(pairs, 20260101, dev, tid=0)
     lib = synth.LibSpec("lib1", "syn_chr1.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
     wl = synth.Workload({}, [("chr1", synth_torch.CHR1_LEN)], [lib], ["rg1"], ["lib1"], ["syn_chr1.bam"])
     cfg = api.BamConfig(text=wl.config_text())

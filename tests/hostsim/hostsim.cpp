@@ -21,6 +21,76 @@
 
 using namespace bdk;
 
+// Host rendering of the piece-parallel walk the CUDA path uses for very large components (k4_component_cta): same
+// decomposition, pieces of a window walked in DESCENDING order (nothing may depend on their order), finality pass evaluated
+// against the earlier state and resolved afterwards.
+static int component_by_pieces(const K4Static& S, K4Mut& M, DEdge* e, int ne, int row0, int nrows) {
+    SoloTeam T;
+    if (S.rerun) {
+        for (int q = 0; q < ne; ++q) k4_reset_slot(S, M, e, q);
+        for (int r = 0; r < nrows; ++r) M.row_emit[row0 + r] = 0;
+    }
+    int row_base = row0, i = 0;
+    std::vector<int32_t> queue;
+    while (i < ne) {
+        const int w = e[i].win;
+        int j = i;
+        while (j < ne && e[j].win == w) ++j;
+        WindowInfo wi = k4_window_info(S, w);
+        std::vector<int> vtx, rs;
+        for (int t = i; t < j; ++t) if (t == i || e[t].src != e[t - 1].src) { vtx.push_back(e[t].src); rs.push_back(t); }
+        rs.push_back(j);
+        const int R = (int)vtx.size();
+        auto run_of = [&](int v) { return (int)(std::lower_bound(vtx.begin(), vtx.end(), v) - vtx.begin()); };
+        std::vector<int> label(R);
+        std::iota(label.begin(), label.end(), 0);
+        auto followable = [&](const DEdge& x) { return x.w >= S.min_read_pair && !M.deleted[x.dst] && !M.deleted[x.src]; };
+        for (bool changed = true; changed;) {
+            changed = false;
+            for (int r = 0; r < R; ++r)
+                for (int t = rs[r]; t < rs[r + 1]; ++t) {
+                    if (!followable(e[t])) continue;
+                    int r2 = run_of(e[t].dst);
+                    int m = std::min(label[r], label[r2]);
+                    if (label[r] != m || label[r2] != m) { label[r] = label[r2] = m; changed = true; }
+                }
+        }
+        std::vector<int> prow(R, 0), pq(R, 0);
+        for (int r = 0; r < R; ++r)
+            for (int t = rs[r]; t < rs[r + 1]; ++t)
+                if (followable(e[t])) { ++pq[label[r]]; if (e[t].src <= e[t].dst) ++prow[label[r]]; }
+        std::vector<int> pieces, rowoff;
+        int rows = 0;
+        for (int r = 0; r < R; ++r) if (label[r] == r && prow[r] > 0) { pieces.push_back(r); rowoff.push_back(rows); rows += prow[r]; }
+        for (int p = (int)pieces.size() - 1; p >= 0; --p) {
+            int row = row_base + rowoff[p];
+            queue.assign(pq[pieces[p]] + 2, 0);
+            for (int r = 0; r < R; ++r)
+                if (label[r] == pieces[p]) row = k4_bfs_from(T, S, M, e, i, j, w, wi, rs[r], rs[r + 1], queue.data(), row);
+            if (row - (row_base + rowoff[p]) != prow[pieces[p]]) return -1;      // every followable edge of a piece is followed exactly once
+        }
+        row_base += rows;
+        // finality pass
+        std::vector<int32_t> cand;
+        for (int r = 0; r < R; ++r) if (!S.never_final[vtx[r]] && !M.deleted[vtx[r]] && vtx[r] != wi.last_region) cand.push_back(vtx[r]);
+        std::vector<uint8_t> state(cand.size() + 1, K4_FIN_NOT);
+        for (size_t c = 0; c < cand.size(); ++c) state[c] = k4_region_final(T, S, M, cand[c], wi) ? K4_FIN_UNDECIDED : K4_FIN_NOT;
+        for (bool pending = true; pending;) {
+            pending = false;
+            for (int c = (int)cand.size() - 1; c >= 0; --c) {                    // descending on purpose
+                if (state[c] != K4_FIN_UNDECIDED) continue;
+                int d = k4_final_deps(T, S, M, cand[c], cand.data(), state.data(), (int)cand.size());
+                if (d & 1) state[c] = K4_FIN_NOT;
+                else if (!(d & 2)) state[c] = K4_FIN_CLEARED;
+                else pending = true;
+            }
+        }
+        for (size_t c = 0; c < cand.size(); ++c) if (state[c] == K4_FIN_CLEARED) { M.deleted[cand[c]] = 1; M.del_cur[cand[c]] = w; }
+        i = j;
+    }
+    return row_base - row0;
+}
+
 extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, bdo_output* out) {
     const bdk_params& p = *pp;
     int nkey = nkey_of(p), nlib = p.nlib;
@@ -197,7 +267,10 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
             queue.assign(comp_ne[r] + 2, 0);
             DEdge* es = de.data() + de_off[r];
             de_sort(es, comp_ne[r]);
-            int used = k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r], comp_strong[r]);
+            const int pieces_min = getenv("HOSTSIM_PIECES") ? atoi(getenv("HOSTSIM_PIECES")) : 4096;   // tests lower it
+            int used = comp_ne[r] > pieces_min ? component_by_pieces(KS, KM, es, comp_ne[r], row_off[r], comp_strong[r])
+                                               : k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r], comp_strong[r]);
+            if (used < 0) return -102;
             if (used > comp_strong[r]) return -100;
         }
         std::fill(dirty.begin(), dirty.end(), 0);
@@ -222,9 +295,10 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
         int mx = 0, nf = 0; for (int r = 0; r < nreg; ++r) { mx = std::max(mx, comp_ne[r]); nf += never_final[r]; }
         fprintf(stderr, "hostsim: %d regions (%d never final), %zu edges, largest component %d directed edges, %d sweeps\n", nreg, nf, ue.size(), mx, sweeps + 1);
     }
+    for (int r = 0; r < nrow_cap; ++r) if (row_emit[r] == K4_ROW_PENDING) k4_score_row(KS, KM, r);
     // final order: stable by (window, BFS start vertex), slot order inside
     std::vector<int> order;
-    for (int r = 0; r < nrow_cap; ++r) if (row_emit[r]) order.push_back(r);
+    for (int r = 0; r < nrow_cap; ++r) if (row_emit[r] == K4_ROW_EMIT) order.push_back(r);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_key[a] < row_key[b]; });
 
     // ---- pack outputs ---------------------------------------------------------------------------

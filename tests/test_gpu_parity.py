@@ -201,3 +201,40 @@ def test_config3_device_generator_matches_oracle():
     b, _ = synth_torch.config3_bundle()
     ro = _check(b, synth_torch.to_numpy(cols), "config3_device 1.5M pairs")
     assert len(ro.table.sv) > 300 and len(set(ro.table.sv["flag"].tolist())) >= 5
+
+
+# ---- the paths of the connection walk that only large inputs reach, forced on small ones ------------------------------
+K4_FORCED = {
+    "cta_walker_for_every_component": dict(BDK_K4_CTA_MIN="0"),
+    "cta_walker_sequential_window_fallback": dict(BDK_K4_CTA_MIN="0", BDK_K4_MAXR="3"),
+    "cta_walker_and_deferral": dict(BDK_K4_CTA_MIN="4", BDK_K4_BIG="8"),
+    "deferral_of_warp_walked_components": dict(BDK_K4_BIG="6"),
+}
+
+
+@pytest.mark.parametrize("name", list(K4_FORCED))
+def test_gpu_k4_forced_paths_match_oracle(monkeypatch, name):
+    """A CTA per component (pieces of a window in parallel, finality pass resolved afterwards), its sequential-window
+    fallback, and big components waiting for the small ones: all must give the oracle's result."""
+    for k, v in K4_FORCED[name].items():
+        monkeypatch.setenv(k, v)
+    w = synth.generate(util.GENOME3, util.LIBS4, 120000, seed=41, anomaly_frac=0.08, somatic_frac=0.3)
+    for od in (dict(), dict(min_read_pair=1, score_threshold=-100), dict(buffer_size=3), dict(transchr_rearrange=True), dict(CN_lib=True, chr="chrA")):
+        b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+        ro = _check(b, cols, f"{name} {od}")
+        assert len(ro.table.sv) > 3
+    import torch
+    from breakdancer_b200 import synth_torch
+    cols = synth_torch.config3_device(1_000_000, seed=13, device=torch.device("cuda", 0))     # dense noise: long strong components
+    b, _ = synth_torch.config3_bundle()
+    _check(b, synth_torch.to_numpy(cols), f"{name} config3-shaped")
+
+
+def test_gpu_radix_sorted_edges_for_large_components(monkeypatch):
+    """A component with more directed edges than the rank sort takes (8192) switches the whole edge list to the radix sort."""
+    import torch
+    from breakdancer_b200 import synth_torch
+    cols = synth_torch.config3_device(8_000_000, seed=17, device=torch.device("cuda", 0))
+    b, _ = synth_torch.config3_bundle()
+    ro = _check(b, synth_torch.to_numpy(cols), "config3-shaped 8M pairs")
+    assert len(ro.table.sv) > 1000
