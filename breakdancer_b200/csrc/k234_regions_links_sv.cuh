@@ -365,6 +365,7 @@ __device__ __forceinline__ int k4_block_compact(int n, int32_t* out, int cap, in
         if (p && pos < cap) out[pos] = r;
         running += tot;
     }
+    __syncthreads();          // out[] is complete for every thread
     return running;
 }
 
