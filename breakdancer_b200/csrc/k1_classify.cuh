@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
             unsigned long long bams = 0;
             uint32_t nst = 0;                                                  // stash slots used by this thread
             K1Stash* stash = my_stash + (size_t)tb * K1_CTHREADS * K1_STASH;
-#pragma unroll (SINGLE_KEY ? 1 : K1_SUBS)
+#pragma unroll 1      // (unrolling the stage loop of the multi-key variant made 11 K instructions: instruction-cache misses were its top stall)
             for (int s = 0; s < K1_SUBS; ++s) {
                 const uint64_t rec0 = (uint64_t)tile * K1_TILE + (uint64_t)s * K1_SUB;
                 if (rec0 >= a.n) break;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 const uint32_t base_a = s_base[pb * ncomp];
                 const uint16_t* off_a = s_off + ((size_t)pb * ncomp) * 64;
                 const unsigned lt = lanemask_lt();
-#pragma unroll
+#pragma unroll 1
                 for (int s = 0; s < K1_SUBS; ++s) {
                     const uint32_t a4 = (prev_amask >> (4 * s)) & 0xFu, p4 = (prev_pmask >> (4 * s)) & 0xFu;
                     if (!__any_sync(FULL, a4 != 0)) continue;
