@@ -15,15 +15,16 @@ SRC   := $(PKG)/csrc
 B     := build
 LIB   := $(PKG)/libbdk.so
 CLI   := $(PKG)/bin/breakdancer_max
+B2C   := $(PKG)/bin/bam2cfg
 ORA   := oracle/_build/libbdoracle.so
 
 HOST_SRCS := $(SRC)/host/config.cpp $(SRC)/host/bam_io.cpp $(SRC)/host/format.cpp $(SRC)/host/options.cpp $(SRC)/host/support.cpp
 HOST_OBJS := $(patsubst $(SRC)/host/%.cpp,$(B)/host_%.o,$(HOST_SRCS))
 CU_HDRS   := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/bdk.h
 
-all: $(LIB) $(CLI) $(ORA)
+all: $(LIB) $(CLI) $(B2C) $(ORA)
 
-$(B)/host_%.o: $(SRC)/host/%.cpp $(SRC)/host/host.hpp $(SRC)/host/cli.hpp include/bdk.h include/bdk_host.h
+$(B)/host_%.o: $(SRC)/host/%.cpp $(SRC)/host/host.hpp $(SRC)/host/cli.hpp $(SRC)/host/bam2cfg_impl.hpp include/bdk.h include/bdk_host.h
 	@mkdir -p $(B)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
@@ -38,6 +39,10 @@ $(CLI): $(SRC)/host/main.cpp $(LIB) $(SRC)/host/host.hpp
 	@mkdir -p $(PKG)/bin
 	$(CXX) $(CXXFLAGS) $< -o $@ -L$(PKG) -lbdk -Wl,-rpath,'$$ORIGIN/..' $(LDLIBS)
 
+$(B2C): $(SRC)/host/bam2cfg_main.cpp $(LIB) include/bdk_host.h
+	@mkdir -p $(PKG)/bin
+	$(CXX) $(CXXFLAGS) $< -o $@ -L$(PKG) -lbdk -Wl,-rpath,'$$ORIGIN/..' $(LDLIBS)
+
 $(ORA): oracle/bd_oracle.cpp include/bdk.h
 	@mkdir -p oracle/_build
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -shared $< -o $@
@@ -46,6 +51,6 @@ ref:
 	bash oracle/build_ref.sh
 
 clean:
-	rm -rf $(B) $(LIB) $(CLI) oracle/_build
+	rm -rf $(B) $(LIB) $(CLI) $(B2C) oracle/_build
 
 .PHONY: all ref clean

@@ -172,6 +172,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdh_write_bam": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_int,
                                     C.POINTER(C.c_char_p), C.POINTER(Soa), u64, C.c_char_p, C.c_int, C.c_int,
                                     C.c_int, C.c_char_p, C.c_int]),
+        "bdh_bam2cfg_defaults": (None, [vp]),
+        "bdh_bam2cfg": (C.c_int64, [C.POINTER(C.c_char_p), C.c_int, vp, C.c_char_p, C.c_int64, C.c_char_p, C.c_int]),
         "bdh_format_header": (C.c_int64, [C.POINTER(Params), C.POINTER(SummaryT), vp, C.c_int, C.c_char_p, C.c_int64]),
         "bdh_format_rows": (C.c_int64, [C.POINTER(Params), C.POINTER(Result), vp, vp, C.c_int, C.POINTER(C.c_int),
                                          C.c_char_p, C.c_int64]),
@@ -554,6 +556,29 @@ def format_output(bundle: ParamBundle, summary: SummaryT, table: SvTable, lib_na
         if n < cap:
             return head + buf.value.decode()
         cap = n + 1
+
+
+class Bam2cfgOpts(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("n_obs", C.c_int32), ("cut_sd", C.c_double), ("min_mean", C.c_double), ("max_cv", C.c_double),
+                ("use_mapq", C.c_int32), ("solid", C.c_int32), ("flag_hist", C.c_int32), ("rg_lib_file", C.c_char_p)]
+
+
+def bam2cfg(bams: Sequence[str], **kw) -> str:
+    """perl/bam2cfg.pl in C++ (bdh_bam2cfg): the configuration text for position-sorted BAM files.
+    Keyword options: min_mapq, n_obs, cut_sd, min_mean, max_cv, use_mapq, solid, flag_hist, rg_lib_file."""
+    L = load_library()
+    o = Bam2cfgOpts()
+    L.bdh_bam2cfg_defaults(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v.encode() if isinstance(v, str) else v)
+    arr = (C.c_char_p * len(bams))(*[b.encode() for b in bams])
+    err = C.create_string_buffer(512)
+    n = L.bdh_bam2cfg(arr, len(bams), C.byref(o), None, 0, err, 512)
+    if n < 0:
+        raise BdkError(err.value.decode())
+    buf = C.create_string_buffer(n + 1)
+    L.bdh_bam2cfg(arr, len(bams), C.byref(o), buf, n + 1, err, 512)
+    return buf.value.decode()
 
 
 def write_bam(path: str, tid_names: Sequence[str], tid_lens: Sequence[int], rg_names: Sequence[str],

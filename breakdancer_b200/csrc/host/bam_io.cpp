@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <mutex>
 #include <queue>
 #include <stdexcept>
@@ -679,3 +680,5 @@ int bdh_write_bam(const char* path, int ntid, const char* const* tid_names, cons
 }
 
 }  // extern "C"
+
+#include "bam2cfg_impl.hpp"

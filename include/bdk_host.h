@@ -70,6 +70,27 @@ int bdh_write_bam(const char* path, int ntid, const char* const* tid_names, cons
                   int nrg, const char* const* rg_names, const bdk_soa* cols, uint64_t n,
                   const char* name_prefix, int write_am, int level, int threads, char* err, int errcap);
 
+/* ---- bam2cfg: the configuration file from the BAMs themselves ------------------------------
+ * perl/bam2cfg.pl:48-247 (+ perl/AlnParser.pm:31-124, Shapiro-Wilk figure bam2cfg.pl:284-744): per library the
+ * insert-size mean / s.d. / lower / upper from the first n_obs proper FR pairs with mapping quality > min_mapq,
+ * mean read length; one line per read group in the grammar bdh_config_parse reads. Options are the script's
+ * (-q -n -c -s -v -m -C -g -f); -h (histogram plots) is not carried over. Lines come in @RG header order (the script
+ * prints in Perl hash order). Returns the text length (stored if it fits in cap, with NUL), -1 on error. */
+typedef struct bdh_bam2cfg_opts {
+    int32_t min_mapq;          /* -q 35 */
+    int32_t n_obs;             /* -n 10000 */
+    double cut_sd;             /* -c 4 */
+    double min_mean;           /* -s 50 */
+    double max_cv;             /* -v 1 */
+    int32_t use_mapq;          /* -m: MAPQ instead of the Aq / AM tag */
+    int32_t solid;             /* -C */
+    int32_t flag_hist;         /* -g */
+    const char* rg_lib_file;   /* -f: two-column RG -> LIB table, or NULL */
+} bdh_bam2cfg_opts;
+void bdh_bam2cfg_defaults(bdh_bam2cfg_opts* o);
+int64_t bdh_bam2cfg(const char* const* bam_paths, int nbam, const bdh_bam2cfg_opts* opts, char* buf, int64_t cap,
+                    char* err, int errcap);
+
 /* ---- output --------------------------------------------------------------------------------
  * Text of the reference's stdout: the "#Library Statistics" header block
  * (src/exe/breakdancer-max/BreakDancerMax.cpp:82-153) and the SV rows
