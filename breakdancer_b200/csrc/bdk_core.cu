@@ -115,6 +115,7 @@ struct bdk_ctx {
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
     uint32_t k4_cta_min = K4_CTA_MIN, k4_big_min = K4_BIG;   // BDK_K4_CTA_MIN / BDK_K4_BIG (tests)
     int k4_maxr = K4C_MAXR;                   // BDK_K4_MAXR (tests)
+    bool k4_host_loop = false;                // BDK_K4_HOST_LOOP (tests): the per-phase launches also on a single GPU
     std::vector<uint32_t> h_cuts;     // [2][nranks + 1] vertex / row-slot cuts of the last bdk_finish
 };
 
@@ -531,6 +532,7 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         }
         if (const char* e = getenv("BDK_K4_CTA_MIN")) c->k4_cta_min = (uint32_t)std::max(0, atoi(e));
         if (const char* e = getenv("BDK_K4_BIG")) c->k4_big_min = (uint32_t)std::max(0, atoi(e));
+        if (const char* e = getenv("BDK_K4_HOST_LOOP")) c->k4_host_loop = atoi(e) != 0;
         if (const char* e = getenv("BDK_K4_MAXR")) c->k4_maxr = std::max(0, std::min(atoi(e), (int)K4C_MAXR));
         if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
         CUC(cudaFuncSetAttribute(k5_order_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM_ROWS * 12));
@@ -840,24 +842,32 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         G_score = G;
         const bool mine = v_lo < std::min(v_hi, nreg);
         const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
-        if (!c->comm || N == 1) {   // one persistent cooperative kernel, grid-wide barriers between the phases
+        const bool multi = c->comm && N > 1;
+        bool host_loop = multi || c->k4_host_loop;
+        if (!host_loop) {           // one persistent cooperative kernel, grid-wide barriers between the phases
             uint32_t* sync = c->d_k4sync.as<uint32_t>();
             CU(cudaMemsetAsync(sync, 0, 64, st));
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->k4_grid_max));
             K4Trace* trace = G.trace;
             void* args[] = {&S, &M, &G, &sync, &trace};
-            CU(cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, sizeof(K4CtaSmem), st));
-            c->launches += 1;
-            sweeps_on_device = true;
-        } else {                    // one launch per phase; the owners' deletion times go to every rank in between
-            if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
+            const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, sizeof(K4CtaSmem), st);
+            if (ce == cudaSuccess) { c->launches += 1; sweeps_on_device = true; }
+            else if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorNotSupported || ce == cudaErrorLaunchOutOfResources) {
+                cudaGetLastError();      // the GPU is shared (MPS, another context): the CTAs cannot all be resident. One launch per phase instead.
+                host_loop = true;
+            } else return fail(c, BDK_ERR_CUDA, "cudaLaunchCooperativeKernel(k4_sweeps_kernel) failed: %s", cudaGetErrorString(ce));
+        }
+        if (host_loop) {            // one launch per phase; multi-GPU: the owners' deletion times go to every rank in between
+            if (multi && !nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)kNumSMs * 16));
             for (uint32_t sweep = 0;; ++sweep) {
                 if (sweep > 100000) return fail(c, BDK_ERR_STATE, "connection walk did not reach a fixed point");
                 if (sweep) { CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 4, st)); CU(cudaMemsetAsync(d_cnt + CNT_K4_BIGCUR, 0, 4, st)); }
                 if (mine) { k4_components_kernel<<<grid, K4_THREADS, sizeof(K4CtaSmem), st>>>(S, M, G, sweep, d_cnt + CNT_K4_TICKET, d_cnt + CNT_K4_BIGCUR); c->launches += 1; }
-                NC(nc->AllReduce(c->d_del_cur.p, c->d_del_cur.p, nreg, ncclInt32, ncclMin, c->comm, st));   // K4_NEVER where not the owner
-                c->comm_bytes += (uint64_t)nreg * 4;
+                if (multi) {
+                    NC(nc->AllReduce(c->d_del_cur.p, c->d_del_cur.p, nreg, ncclInt32, ncclMin, c->comm, st));   // K4_NEVER where not the owner
+                    c->comm_bytes += (uint64_t)nreg * 4;
+                }
                 CU(cudaMemsetAsync(d_cnt + CNT_NDIRTY, 0, 4, st));
                 k4_mark_dirty_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G, sweep, d_cnt + CNT_NDIRTY);
                 k4_next_sweep_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G, sweep);

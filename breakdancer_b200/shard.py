@@ -59,3 +59,25 @@ def run_sharded(cols: Dict[str, np.ndarray], ntid: int, rank: int, world: int,
         return None
     merged = [x for part in out for x in part]
     return sorted(merged, key=lambda x: x[0])
+
+
+# ---- one job over several GPUs (whole-genome / -t semantics, include/bdk.h "Multi-GPU") -----------------------------
+def stream_slices(n_records: int, world: int) -> List[slice]:
+    """Contiguous, near-equal slices of the globally (tid, pos)-sorted record stream, one per rank in rank order.
+    Cuts may fall anywhere (also inside a chromosome): pass 1 is per record plus prefix counts, everything that needs
+    neighbours runs on the gathered anomalous reads."""
+    edges = [(n_records * r) // world for r in range(world + 1)]
+    return [slice(edges[r], edges[r + 1]) for r in range(world)]
+
+
+def run_one_job(cols: Dict[str, np.ndarray], rank: int, world: int, make_context: Callable[[], object], unique_id: bytes):
+    """Rank `rank` of a `world`-GPU job: attach the communicator, push this rank's slice, finish collectively.
+    make_context() returns a breakdancer_b200.api.Context on this rank's GPU; unique_id comes from rank 0
+    (api.comm_unique_id(), distributed by the caller). Returns (summary, table): identical on every rank."""
+    ctx = make_context()
+    ctx.comm_init(unique_id, rank, world)
+    sl = stream_slices(len(cols["pos"]), world)[rank]
+    ctx.push({k: np.ascontiguousarray(v[sl]) for k, v in cols.items()})
+    summary = ctx.summary()
+    table = ctx.finish()
+    return summary, table

@@ -209,6 +209,7 @@ K4_FORCED = {
     "cta_walker_sequential_window_fallback": dict(BDK_K4_CTA_MIN="0", BDK_K4_MAXR="3"),
     "cta_walker_and_deferral": dict(BDK_K4_CTA_MIN="4", BDK_K4_BIG="8"),
     "deferral_of_warp_walked_components": dict(BDK_K4_BIG="6"),
+    "one_launch_per_phase_instead_of_the_cooperative_kernel": dict(BDK_K4_HOST_LOOP="1"),
 }
 
 

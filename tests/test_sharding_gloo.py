@@ -62,3 +62,38 @@ def test_two_rank_sharded_run_equals_per_chromosome_runs():
     want = shard.run_sharded(w.cols, len(w.genome), 0, 1, _engine(w, {}))
     assert [t for t, _ in got] == [0, 1, 2] and got == want
     assert sum(len(r[0]) for _, r in got) > 0
+
+
+def _slice_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # what a rank does before the GPU part of a one-job run: rank 0 obtains the NCCL id (no GPU needed), everyone gets it,
+    # and every rank takes its slice of the stream
+    box = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    sl = shard.stream_slices(n, world)[rank]
+    t = torch.tensor([sl.start, sl.stop, sl.stop - sl.start], dtype=torch.int64)
+    out = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(out, t)
+    if rank == 0:
+        q.put((len(box[0]), [o.tolist() for o in out]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_stream_slices_and_communicator_id():
+    assert [(s.start, s.stop) for s in shard.stream_slices(10, 3)] == [(0, 3), (3, 6), (6, 10)]
+    assert [(s.start, s.stop) for s in shard.stream_slices(2, 4)] == [(0, 0), (0, 1), (1, 1), (1, 2)]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slice_worker, args=(r, 2, port, 1001, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    idlen, slices = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert idlen == 128
+    assert slices == [[0, 500, 500], [500, 1001, 501]]
