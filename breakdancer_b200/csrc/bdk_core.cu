@@ -82,7 +82,7 @@ struct bdk_ctx {
         d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt, d_de_root,
         d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
         d_deleted, d_de, d_de2, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_sort_k, d_sort_v, d_sort_k2, d_sort_v2, d_pois_l, d_pois_k, d_pois_o;
-    int k5_smem_rows = K5_SMEM_ROWS;   // tables up to this many row slots are ordered by the single-CTA shared-memory sort
+    int k5_smem_rows = K5_SMEM_ROWS;   // tables up to this many row slots are ordered by the grid-wide rank sort
     uint64_t d2h_bytes = 0;
     uint32_t n_slots = 0;
     void* h_pack = nullptr;       // pinned host block the row outputs + summary are copied into
@@ -110,7 +110,7 @@ struct bdk_ctx {
     uint32_t A_local = 0;             // anomalous reads of this rank's slice (c->A becomes the global count)
     uint64_t comm_bytes = 0;          // bytes this rank received in the exchanges of the last job
     DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff, d_cuts;
-    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range, d_never_final, d_big_list;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
+    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range, d_never_final, d_big_list, d_ri;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
     uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
     uint32_t k4_cta_min = K4_CTA_MIN, k4_big_min = K4_BIG;   // BDK_K4_CTA_MIN / BDK_K4_BIG (tests)
@@ -393,7 +393,7 @@ void bdk_destroy(bdk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
     c->comm = nullptr;
-    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_never_final, &c->d_big_list, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
+    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_never_final, &c->d_big_list, &c->d_ri, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt, &c->d_de_root,
@@ -535,7 +535,6 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         if (const char* e = getenv("BDK_K4_HOST_LOOP")) c->k4_host_loop = atoi(e) != 0;
         if (const char* e = getenv("BDK_K4_MAXR")) c->k4_maxr = std::max(0, std::min(atoi(e), (int)K4C_MAXR));
         if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
-        CUC(cudaFuncSetAttribute(k5_order_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K5_SMEM_ROWS * 12));
         if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
     }
     int rc = reset_job(c);
@@ -691,7 +690,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     const size_t L1 = (size_t)A / 2 + 2;
     ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
     ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
-    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8); ENS(c->d_never_final, A1); ENS(c->d_big_list, A1 * 4);
+    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8); ENS(c->d_never_final, A1); ENS(c->d_big_list, A1 * 4); ENS(c->d_ri, A1 * sizeof(ReadInfo));
     ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (4 * L1 + 2 * A1 + 8) * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
@@ -801,6 +800,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     CU(cudaMemsetAsync(dp + w_emit, 0, R1, st));
     CU(cudaMemsetAsync(c->d_slot_order.p, 0xff, R1 * 4, st));
     K4Static S;
+    S.ri = c->d_ri.as<ReadInfo>();
     S.ar = c->d_ar.as<bdk_aread>(); S.read_region = c->d_read_region.as<int32_t>(); S.read_cand = c->d_read_cand.as<int32_t>();
     S.mate = c->d_mate.as<int32_t>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
     S.cand_maxlen = c->d_cand_maxlen.as<int32_t>(); S.lib_mean = c->d_lib_mean.as<float>();
@@ -837,8 +837,9 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         G.trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
         if (G.trace) CU(cudaMemsetAsync(G.trace, 0, sizeof(K4Trace), st));
         CU(cudaMemsetAsync(d_cnt + CNT_K4_NBIGLIST, 0, 8, st));   // list length and the multi-GPU walk's cursor
+        k4_read_info_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S.ar, S.mate, S.read_region, S.read_cand, A, c->d_ri.as<ReadInfo>());
         k4_guess_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G);     // starting table, cleared stamps
-        c->launches += 1;
+        c->launches += 2;
         G_score = G;
         const bool mine = v_lo < std::min(v_hi, nreg);
         const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
@@ -908,8 +909,12 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     c->launches += 1;
     uint32_t* order_slot = (uint32_t*)(dp + w_order);
     if (nrow <= (uint32_t)c->k5_smem_rows) {
-        uint32_t m = 1024; while (m < nrow) m <<= 1;
-        k5_order_smem_kernel<<<1, K5_THREADS, (size_t)m * 12, st>>>(emit_key, emit_slot, d_cnt, order_slot);
+        const unsigned g5 = (unsigned)std::max<uint32_t>(1, div_up<uint32_t>(nrow, K5_THREADS));      // nrow bounds the emitted rows
+        uint32_t* rank = (uint32_t*)(dp + w_tmpv);
+        CU(cudaMemsetAsync(rank, 0, R1 * 4, st));
+        k5_rank_partial_kernel<<<dim3(g5, g5), K5_THREADS, 0, st>>>(emit_key, emit_slot, d_cnt, rank);
+        k5_rank_scatter_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(emit_slot, rank, d_cnt, order_slot);
+        c->launches += 1;
         c->launches += 1;
     } else {   // large tables: stable LSD radix sort by slot, BFS start vertex, window
         int sbits = 1; while ((1ull << sbits) < (uint64_t)nrow + 1) ++sbits;

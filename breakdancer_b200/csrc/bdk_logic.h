@@ -241,7 +241,25 @@ struct DEdge {                // directed copy of one graph edge inside its flus
 };
 enum { DE_ERASED = 1, DE_VERASED = 2 };
 
+// Everything the walk needs to know about a read that never changes, in one 16-byte load: the walk is a chain of
+// dependent loads, and mate -> mate's region -> mate's candidate were three of its links.
+struct alignas(16) ReadInfo {
+    int32_t mate;          // index of the mate in the anomalous-read stream, or -1
+    int32_t mate_region;   // region of the mate, or -1 (collapsed candidate / no mate)
+    int32_t mate_cand;     // candidate region of the mate
+    uint32_t meta;         // bdk_aread::meta of the read itself
+};
+BDK_HD ReadInfo make_read_info(const bdk_aread* ar, const int32_t* mate, const int32_t* read_region, const int32_t* read_cand, int j) {
+    ReadInfo r;
+    r.mate = mate[j];
+    r.mate_region = r.mate >= 0 ? read_region[r.mate] : -1;
+    r.mate_cand = r.mate >= 0 ? read_cand[r.mate] : 0;
+    r.meta = ar[j].meta;
+    return r;
+}
+
 struct K4Static {
+    const ReadInfo* ri;           // [A]
     const bdk_aread* ar;
     const int32_t* read_region;   // region index or -1 (collapsed)
     const int32_t* read_cand;     // candidate index
@@ -303,24 +321,23 @@ BDK_HD WindowInfo k4_window_info(const K4Static& S, int w) {
     return wi;
 }
 
-// _read_regions.find(name) != end for read j at the flush whose trigger candidate is cF
-BDK_HD bool k4_exists(const K4Static& S, const K4Mut& M, int j, int cF) {
-    int m = S.mate[j];
+// _read_regions.find(name) != end for read j (R = S.ri[j]) at the flush whose trigger candidate is cF
+BDK_HD bool k4_exists(const ReadInfo& R, const K4Mut& M, int j, int cF) {
+    const int m = R.mate;
     if (m < 0) return true;
-    if (S.read_region[m] < 0)       // mate sat in a collapsed candidate: its collapse erased the name
-        return !(m > j && S.read_cand[m] < cF);
+    if (R.mate_region < 0)          // mate sat in a collapsed candidate: its collapse erased the name
+        return !(m > j && R.mate_cand < cF);
     return !M.freed[j];
 }
 
-// _read_regions[name].size() == 2, asked while region v = read_region[j] is checked at the end of window w
-BDK_HD bool k4_size2(const K4Static& S, const K4Mut& M, int j, int cF, int w) {
-    int m = S.mate[j];
+// _read_regions[name].size() == 2, asked while region v (the region of read j) is checked at the end of window w
+BDK_HD bool k4_size2(const K4Static& S, const ReadInfo& R, const K4Mut& M, int j, int v, int cF, int w) {
+    const int m = R.mate;
     if (m < 0) return false;
-    int rm = S.read_region[m];
+    const int rm = R.mate_region;
     if (rm < 0) return false;
-    if (S.read_cand[m] > cF) return false;      // mate's region not registered yet
+    if (R.mate_cand > cF) return false;         // mate's region not registered yet
     if (M.freed[j]) return false;
-    const int v = S.read_region[j];
     bool rm_deleted;
     if (S.root_of[rm] == S.root_of[v]) rm_deleted = M.deleted[rm] != 0;      // same component: the walk's own state
     else {                                        // other component: cleared before (w, v) in the reference's order?
@@ -402,10 +419,11 @@ struct WarpTeam {
 #endif
 
 // does read j keep its region from being final (is_region_final's per-read test)?
-BDK_HD bool k4_read_blocks_final(const K4Static& S, const K4Mut& M, int j, const WindowInfo& wi) {
+BDK_HD bool k4_read_blocks_final(const K4Static& S, const K4Mut& M, int j, int v, const WindowInfo& wi) {
     if (!M.alive[j]) return false;
-    if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) return false;
-    return !k4_exists(S, M, j, wi.cF) || !k4_size2(S, M, j, wi.cF, wi.w);
+    const ReadInfo R = S.ri[j];
+    if (S.chr_restricted && meta_flag(R.meta) == BDK_ARP_CTX) return false;
+    return !k4_exists(R, M, j, wi.cF) || !k4_size2(S, R, M, j, v, wi.cF, wi.w);
 }
 
 template <class Team>
@@ -417,21 +435,22 @@ BDK_HD bool k4_region_final(const Team& T, const K4Static& S, const K4Mut& M, in
     // found out in the first chunk.
     for (int j1 = R.first_read + R.n_reads; j1 > R.first_read; j1 -= T.width()) {
         const int j = j1 - 1 - T.lane();
-        const bool bad = j >= R.first_read && k4_read_blocks_final(S, M, j, wi);
+        const bool bad = j >= R.first_read && k4_read_blocks_final(S, M, j, v, wi);
         if (T.any(bad)) return false;
     }
     return true;
 }
 
-// read y is the later mate of a pair (x, y) whose both reads are still held by regions s0 / s1
-BDK_HD int k4_pair_of(const K4Static& S, const K4Mut& M, int y, int s0, int s1, int cF) {
-    int x = S.mate[y];
+// read y (Ry = S.ri[y]) is the later mate of a pair (x, y) whose both reads are still held by regions s0 / s1
+BDK_HD int k4_pair_of(const ReadInfo& Ry, const K4Mut& M, int y, int s0, int s1) {
+    const int x = Ry.mate;
     if (x < 0 || x >= y) return -1;
-    int rx = S.read_region[x];
+    const int rx = Ry.mate_region;
     if ((rx != s0 && rx != s1) || rx < 0) return -1;
     // x comes earlier in the reference's scan order, so by the time y is looked at x has already been
-    // dropped if its name no longer exists (BreakDancer.cpp:367-375 via SvBuilder's observe loop)
-    if (!M.alive[x] || !k4_exists(S, M, x, cF)) return -1;
+    // dropped if its name no longer exists (BreakDancer.cpp:367-375 via SvBuilder's observe loop). The mate of x is y, which
+    // sits in a registered region, so "the name of x exists" is just "not freed".
+    if (!M.alive[x] || M.freed[x]) return -1;
     return x;
 }
 
@@ -460,11 +479,12 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
         for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width(), ++it) {
             int d = -1; uint32_t my = 0; int32_t ab = 0;
             if (M.alive[y]) {
-                if (!k4_exists(S, M, y, wi.cF)) d = -2;
+                const ReadInfo Ry = S.ri[y];
+                if (!k4_exists(Ry, M, y, wi.cF)) d = -2;
                 else {
-                    d = k4_pair_of(S, M, y, s0, s1, wi.cF);
+                    d = k4_pair_of(Ry, M, y, s0, s1);
                     if (d >= 0) {
-                        my = S.ar[y].meta; ab = S.ar[y].abs_isize;
+                        my = Ry.meta; ab = S.ar[y].abs_isize;
                         int f = meta_flag(my);
                         c0 += f == 0; c1 += f == 1; c2 += f == 2; c3 += f == 3; c4 += f == 4; c5 += f == 5;
                         c6 += f == 6; c7 += f == 7; c8 += f == 8; c9 += f == 9; c10 += f == 10;
@@ -497,8 +517,9 @@ BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, in
             else {
                 x = -1; my = 0; ab = 0;
                 if (M.alive[y]) {
-                    if (!k4_exists(S, M, y, wi.cF)) x = -2;
-                    else { x = k4_pair_of(S, M, y, s0, s1, wi.cF); if (x >= 0) { my = S.ar[y].meta; ab = S.ar[y].abs_isize; } }
+                    const ReadInfo Ry = S.ri[y];
+                    if (!k4_exists(Ry, M, y, wi.cF)) x = -2;
+                    else { x = k4_pair_of(Ry, M, y, s0, s1); if (x >= 0) { my = Ry.meta; ab = S.ar[y].abs_isize; } }
                 }
             }
             if (x == -2) { M.alive[y] = 0; continue; }

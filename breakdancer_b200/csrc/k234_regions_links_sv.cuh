@@ -507,7 +507,7 @@ __device__ void k4_component_cta(const K4Static& S, K4Mut& M, DEdge* e, int ne, 
         for (int c = warp; c < nc; c += NW) {
             const RegionRec& Rg = S.reg[sm.cand[c]];
             const int jr = Rg.first_read + Rg.n_reads - 1 - lane;
-            const bool bad = jr >= Rg.first_read && k4_read_blocks_final(S, M, jr, wi);
+            const bool bad = jr >= Rg.first_read && k4_read_blocks_final(S, M, jr, sm.cand[c], wi);
             const bool refused = __any_sync(FULL, bad) != 0;
             if (lane == 0) sm.state[c] = refused ? K4_FIN_NOT : K4_FIN_UNDECIDED;
         }
@@ -532,7 +532,7 @@ __device__ void k4_component_cta(const K4Static& S, K4Mut& M, DEdge* e, int ne, 
             while (b - a > 1) { const int m = (a + b) >> 1; if (sm.prowoff[m] <= item) a = m; else b = m; }
             const RegionRec& Rg = S.reg[sm.cand[a]];
             const int jr = Rg.first_read + ((item - sm.prowoff[a]) << 5) + lane;
-            const bool bad = jr < Rg.first_read + Rg.n_reads - 32 && k4_read_blocks_final(S, M, jr, wi);
+            const bool bad = jr < Rg.first_read + Rg.n_reads - 32 && k4_read_blocks_final(S, M, jr, sm.cand[a], wi);
             if (__any_sync(FULL, bad) && lane == 0) sm.state[a] = K4_FIN_NOT;
         }
         __syncthreads();
@@ -702,6 +702,12 @@ __global__ void __launch_bounds__(K4_THREADS, 3) k4_sweeps_kernel(K4Static S, K4
     }
 }
 
+// per-read static information packed for the walk (bdk_logic.h: ReadInfo), one thread per anomalous read
+__global__ void __launch_bounds__(GS_THREADS) k4_read_info_kernel(const bdk_aread* __restrict__ ar, const int32_t* __restrict__ mate,
+        const int32_t* __restrict__ read_region, const int32_t* __restrict__ read_cand, uint32_t A, ReadInfo* __restrict__ ri) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A; j += gridDim.x * blockDim.x) ri[j] = make_read_info(ar, mate, read_region, read_cand, (int)j);
+}
+
 // starting table of deletion times (bdk_logic.h: k4_guess_deletion), one thread per region
 __global__ void __launch_bounds__(GS_THREADS) k4_guess_kernel(K4Static S, K4Mut M, K4Graph G) {
     k4_load_counts(S, G);
@@ -743,33 +749,38 @@ __global__ void __launch_bounds__(GS_THREADS) k4_next_sweep_kernel(K4Static S, K
 // The reference prints window by window, BFS by BFS, and the calls of one BFS in the order they were made:
 // sort the emitted rows by (key = window << 32 | BFS start vertex, row slot). One CTA, bitonic sort in
 // shared memory (an SV table has thousands of rows, not millions).
-constexpr int K5_THREADS = 1024;
-constexpr int K5_SMEM_ROWS = 16384;                       // 12 bytes per row -> 192 KB
-__global__ void __launch_bounds__(K5_THREADS, 1) k5_order_smem_kernel(const uint64_t* __restrict__ emit_key, const uint32_t* __restrict__ emit_slot,
-        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ order_slot) {
-    extern __shared__ __align__(16) unsigned char s_k5[];
+constexpr int K5_THREADS = 256;
+constexpr int K5_SMEM_ROWS = 16384;                       // tables up to this many row slots are ordered by the rank sort below
+// Rank sort over the whole grid: (key, slot) pairs are unique, so the number of smaller pairs is a row's final position.
+// CTA (bx, by) compares the 256 rows of block bx with the 256 rows of tile by (staged in shared memory) and adds its partial
+// counts to rank[]; a second kernel scatters. n^2 comparisons (16 K rows = 2.7e8) spread over up to 4096 CTAs: a few
+// microseconds, where a single-CTA bitonic sort of the same table took over 100 us.
+__global__ void __launch_bounds__(K5_THREADS) k5_rank_partial_kernel(const uint64_t* __restrict__ emit_key, const uint32_t* __restrict__ emit_slot,
+        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ rank) {
+    __shared__ uint64_t s_key[K5_THREADS];
+    __shared__ uint32_t s_slot[K5_THREADS];
     const uint32_t n = d_cnt[CNT_NEMIT];
-    uint32_t m = 1024; while (m < n) m <<= 1;            // n <= K5_SMEM_ROWS (checked by the host against the row-slot count)
-    uint64_t* key = reinterpret_cast<uint64_t*>(s_k5);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(key + m);
-    for (uint32_t i = threadIdx.x; i < m; i += K5_THREADS) {
-        key[i] = i < n ? emit_key[i] : ~0ull;
-        slot[i] = i < n ? emit_slot[i] : 0xffffffffu;
-    }
+    const uint32_t i = blockIdx.x * K5_THREADS + threadIdx.x, t0 = blockIdx.y * K5_THREADS;
+    if (blockIdx.x * K5_THREADS >= n || t0 >= n) return;           // uniform per CTA
+    const uint32_t j = t0 + threadIdx.x;
+    s_key[threadIdx.x] = j < n ? emit_key[j] : ~0ull;
+    s_slot[threadIdx.x] = j < n ? emit_slot[j] : 0xffffffffu;
     __syncthreads();
-    for (uint32_t k = 2; k <= m; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = threadIdx.x; t < (m >> 1); t += K5_THREADS) {
-                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;   // lo has bit j clear
-                const bool up = (lo & k) == 0;
-                const uint64_t ka = key[lo], kb = key[hi];
-                const uint32_t sa = slot[lo], sb = slot[hi];
-                const bool gt = ka > kb || (ka == kb && sa > sb);
-                if (gt == up) { key[lo] = kb; key[hi] = ka; slot[lo] = sb; slot[hi] = sa; }
-            }
-            __syncthreads();
-        }
-    for (uint32_t i = threadIdx.x; i < n; i += K5_THREADS) order_slot[i] = slot[i];
+    if (i >= n) return;
+    const uint64_t ki = emit_key[i];
+    const uint32_t si = emit_slot[i];
+    const uint32_t m = min((uint32_t)K5_THREADS, n - t0);
+    uint32_t r = 0;
+    for (uint32_t q = 0; q < m; ++q) {
+        const uint64_t kq = s_key[q];
+        r += (kq < ki || (kq == ki && s_slot[q] < si)) ? 1u : 0u;
+    }
+    if (r) atomicAdd(rank + i, r);
+}
+__global__ void __launch_bounds__(GS_THREADS) k5_rank_scatter_kernel(const uint32_t* __restrict__ emit_slot, const uint32_t* __restrict__ rank,
+        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ order_slot) {
+    const uint32_t n = d_cnt[CNT_NEMIT];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) order_slot[rank[i]] = emit_slot[i];
 }
 
 // large tables: order_slot comes from the device radix sort; this just seeds its value array

@@ -233,6 +233,9 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     std::vector<int32_t> del_prev(nreg + 1, K4_NEVER), del_cur(nreg + 1, K4_NEVER);
     std::vector<uint8_t> dirty(nreg + 1, 0);
     K4Static KS;
+    std::vector<ReadInfo> ri((size_t)std::max<int64_t>(A, 1));
+    for (int64_t j = 0; j < A; ++j) ri[j] = make_read_info(ar.data(), mate.data(), read_region.data(), read_cand.data(), (int)j);
+    KS.ri = ri.data();
     KS.ar = ar.data(); KS.read_region = read_region.data(); KS.read_cand = read_cand.data(); KS.mate = mate.data();
     KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.lib_mean = lib_mean.data();
     KS.hist = acc.hist.data(); KS.density = density.data(); KS.A = (uint64_t)A; KS.nreg = nreg; KS.ncand = ncand;
