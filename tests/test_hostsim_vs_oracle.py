@@ -23,6 +23,35 @@ def test_stage_decomposition_matches_oracle(seed, od):
     assert len(ro.table.sv) > 5
 
 
+WALK_VARIANTS = {
+    "pieces_for_every_component": dict(HOSTSIM_PIECES="0"),                       # the CTA walker's decomposition (k4_component_cta)
+    "pieces_and_deferral_of_big_components": dict(HOSTSIM_PIECES="6", HOSTSIM_BIG="8"),
+    "deferral_only": dict(HOSTSIM_BIG="4"),
+    "no_starting_guess": dict(HOSTSIM_NO_GUESS="1"),                              # any starting table must converge to the same result
+}
+
+
+@pytest.mark.parametrize("variant", list(WALK_VARIANTS))
+def test_connection_walk_variants_match_oracle(monkeypatch, variant):
+    """The decompositions of the connection walk that the CUDA path uses for large inputs, forced on small ones: window
+    pieces walked independently (in descending order) with the finality pass resolved afterwards, big components waiting for
+    the small ones, sweeps from an empty table. Dense config-3-shaped data (long followed-edge components) and sparse data."""
+    import torch
+    from breakdancer_b200 import synth_torch
+    for k, v in WALK_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    cols = synth_torch.to_numpy(synth_torch.config3_device(1_500_000, 23, torch.device("cpu")))
+    b, _ = synth_torch.config3_bundle()
+    ro, rh = oracle.run(b, cols), util.run_hostsim(b, cols)
+    util.assert_result_matches_oracle(ro, rh.table, rh.summary, rh.regions, rh.areads, rh.aread_region, rh.sv_of_read, variant + " config3")
+    assert len(ro.table.sv) > 300
+    w = synth.generate(util.GENOME3, util.LIBS4, 100000, seed=3, anomaly_frac=0.06, somatic_frac=0.3)
+    for od in (dict(), dict(min_read_pair=1, score_threshold=-100), dict(buffer_size=3), dict(transchr_rearrange=True), dict(chr="chrB")):
+        b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+        ro, rh = oracle.run(b, cols), util.run_hostsim(b, cols)
+        util.assert_result_matches_oracle(ro, rh.table, rh.summary, rh.regions, rh.areads, rh.aread_region, rh.sv_of_read, f"{variant} {od}")
+
+
 def test_edge_cases_empty_and_tiny():
     w = synth.generate(util.GENOME3, util.LIBS4, 50, seed=5, anomaly_frac=0.0, odd_frac=0.0)
     b, cols, *_ = util.workload_bundle(w, api.Options())
