@@ -834,6 +834,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi; G.all_sorted = all_sorted ? 1 : 0;
         G.big_list = c->d_big_list.as<uint32_t>(); G.big_count = d_cnt + CNT_K4_NBIGLIST;
         G.cta_min = c->k4_cta_min; G.big_min = c->k4_big_min; G.maxr = c->k4_maxr;
+        G.defer_first = getenv("BDK_K4_DEFER_FIRST") ? atoi(getenv("BDK_K4_DEFER_FIRST")) : 1;
         G.trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
         if (G.trace) CU(cudaMemsetAsync(G.trace, 0, sizeof(K4Trace), st));
         CU(cudaMemsetAsync(d_cnt + CNT_K4_NBIGLIST, 0, 8, st));   // list length and the multi-GPU walk's cursor

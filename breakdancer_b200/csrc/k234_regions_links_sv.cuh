@@ -305,6 +305,7 @@ struct K4Graph {
     uint32_t* big_count;
     uint32_t cta_min, big_min;       // K4_CTA_MIN / K4_BIG (tests lower them to force those paths on small inputs)
     int32_t maxr;                    // <= K4C_MAXR (tests lower it to force the sequential-window fallback)
+    int32_t defer_first;             // big components also sit out the first sweep (else they are walked once with everybody first)
     K4Trace* trace;                  // or null
 };
 
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(K4_THREADS, 3) k4_sweeps_kernel(K4Static S, K4
     uint32_t epoch = 0;
     const bool tr = trace && blockIdx.x == 0 && threadIdx.x == 0;
     if (tr) trace->t[0] = globaltimer_ns();
-    uint32_t nsmall_prev = 1;                                      // sweep 0: the small components go first
+    uint32_t nsmall_prev = G.defer_first ? 1 : 0;                  // sweep 0: the small components go first (or everybody at once)
     for (uint32_t sweep = 0;; ++sweep) {
         // big components wait while small ones are still being corrected (they are walked at the latest when nothing else is left)
         k4_walk_phase(S, M, G, sweep, sync + 1 + (sweep & 1), sync + 9 + (sweep & 1), sm, nsmall_prev != 0, sync + 3 + (sweep & 1));

@@ -10,9 +10,9 @@ cols = synth_torch.config3_device(pairs, 20260102, dev)
 bundle, cfg = synth_torch.config3_bundle()
 n = cols["pos"].numel()
 dsoa = synth_torch.soa_of(cols)
-for env in ({}, {"BDK_K4_CTA_MIN": "128"}, {"BDK_K4_BIG": "1024"}, {"BDK_K4_CTA_MIN": "128", "BDK_K4_BIG": "1024"}, {"BDK_K4_CTA_MIN": "2048"}, {"BDK_K4_BIG": "16384"},
+for env in ({}, {"BDK_K4_DEFER_FIRST": "0"}, {"BDK_K4_DEFER_FIRST": "0", "BDK_K4_BIG": "1024"}) if len(sys.argv) > 2 else ({}, {"BDK_K4_CTA_MIN": "128"}, {"BDK_K4_BIG": "1024"}, {"BDK_K4_CTA_MIN": "128", "BDK_K4_BIG": "1024"}, {"BDK_K4_CTA_MIN": "2048"}, {"BDK_K4_BIG": "16384"},
             {"BDK_K4_CTA_MIN": "128", "BDK_K4_BIG": "512"}):
-    for k in ("BDK_K4_CTA_MIN", "BDK_K4_BIG"):
+    for k in ("BDK_K4_CTA_MIN", "BDK_K4_BIG", "BDK_K4_DEFER_FIRST"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ctx = api.Context(bundle, 0)
