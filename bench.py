@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- read-pairs/sec to SV calls (BASELINE.json metric) on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3] [--pairs P] [--impl ours|reference]
 
 A "step" is one whole job of the hot path over one synthetic batch: BASELINE.json configs[1]
 (single-library 30x chr1, DEL-only, 50 M read pairs = 100 M position-sorted records per GPU):
 classify -> regions -> link graph -> scored SV table.  `value` is measured with the record columns
 already resident in HBM (bdk_push_device); `e2e` is the same job through the C ABI with HOST (pinned)
 columns, so host->device copies and the device->host read of the SV table are inside the timed
-region.  For N > 1 each rank runs its own chromosome-shaped shard (the path shards by chromosome with
+region.  `roofline` is the classify kernel (25 algorithmic bytes per record) against the measured HBM
+peak; `cpu_baseline` is the unmodified reference binary on the host cores on a bounded sample.
+For N > 1 each rank runs its own chromosome-shaped shard (the path shards by chromosome with
 no data-path collective: weak scaling); torch.distributed/NCCL is used only for the barrier and the
-max-over-ranks of the device time.  One JSON line is printed by rank 0.
+max-over-ranks of the device time.  One JSON line is printed by rank 0.  For N > 1 the line also carries
+`one_job_all_gpus`: ONE job spread over all ranks with whole-genome semantics (and a second one with -t),
+i.e. the NCCL exchanges of csrc/comm.cuh inside the timed region.
+--config 3 runs BASELINE configs[2] instead (300 M pairs, 4 libraries in 2 BAMs, all five SV types).
 
 --impl reference times the unmodified reference executable (oracle/_ref/breakdancer-max; the oracle
 port if that is missing) on the host cores: every step runs one single-threaded process per core, each
