@@ -384,3 +384,28 @@ extern "C" long hostsim_classify_hot_check(long* ncases) {
     if (ncases) *ncases = n;
     return bad;
 }
+
+// k4_change_matters against its definition: the answers "rm cleared before (w, v)" for deletion windows a and b differ for some
+// window w in [wf, wl]. Exhaustive over a small range (K4_NEVER included). Returns the number of mismatches.
+extern "C" long hostsim_change_matters_check(long* ncases) {
+    long bad = 0, n = 0;
+    const int vals[] = {0, 1, 2, 3, 4, 5, 6, K4_NEVER};
+    auto before = [](int d, int rm, int w, int v) { return d < w || (d == w && rm < v); };
+    for (int v = 0; v < 3; ++v)
+        for (int rm = 0; rm < 3; ++rm) {
+            if (rm == v) continue;
+            for (int wf = 0; wf <= 6; ++wf)
+                for (int wl : {-1, 0, 1, 2, 3, 4, 5, 6, K4_NEVER})
+                    for (int a : vals)
+                        for (int b : vals) {
+                            bool want = false;
+                            for (int w = wf; w <= 6 && w <= wl; ++w) want = want || (before(a, rm, w, v) != before(b, rm, w, v));
+                            // windows beyond 6 (wl = K4_NEVER): both finite deletions are "before" there; K4_NEVER never is
+                            if (wl == K4_NEVER && ((a == K4_NEVER) != (b == K4_NEVER))) want = true;
+                            ++n;
+                            if (k4_change_matters(v, rm, wf, wl, a, b) != want) ++bad;
+                        }
+        }
+    if (ncases) *ncases = n;
+    return bad;
+}
