@@ -12,6 +12,7 @@
 // blocks are inflated in parallel into one buffer, and fields are extracted by all cores
 // straight into the columns the GPU consumes.
 #include "host.hpp"
+#include "fast_inflate.hpp"
 
 #include <zlib.h>
 #include <fcntl.h>
@@ -26,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <queue>
 #include <stdexcept>
@@ -96,6 +98,7 @@ struct MappedFile {
 };
 
 struct Block { size_t in_off; uint32_t in_len; uint32_t out_len; size_t out_off; };
+std::atomic<uint64_t> g_inflate_fallbacks(0);     // blocks the fast decoder refused or got wrong (then decoded by zlib)
 
 // Inflate a whole BGZF file into `out` with `threads` workers.
 void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads, std::vector<uint8_t>& out) {
@@ -127,20 +130,34 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
     }
     out.resize(total);
     std::atomic<bool> bad(false);
+    // BDK_FAST_INFLATE=1: every block goes through the table-driven decoder of fast_inflate.hpp first; its result is accepted
+    // only if the block's CRC32 (BGZF footer) matches, otherwise zlib decodes the block. Off by default: on real BAM blocks
+    // it is 1.4x zlib's inflate (1.2x with the checksum), but on very compressible files (the synthetic BAMs of the tests and
+    // the CPU baseline: 6.4 : 1, long matches) the checksum costs more than the decoder gains.
+    static const bool use_fast = getenv("BDK_FAST_INFLATE") && atoi(getenv("BDK_FAST_INFLATE")) != 0 && !getenv("BDK_ZLIB_ONLY");
     parallel_for(blocks.size(), 64, threads, [&](uint64_t b0, uint64_t b1) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+        std::unique_ptr<finf::Tables> tables(use_fast ? new finf::Tables : nullptr);
+        uint64_t fell_back = 0;
         for (uint64_t i = b0; i < b1; ++i) {
             Block const& b = blocks[i];
             if (b.out_len == 0) continue;
+            uint8_t* dst = out.data() + b.out_off;
+            if (use_fast && finf::inflate_raw(f.data + b.in_off, b.in_len, dst, b.out_len, *tables)) {
+                const uint32_t want = rd32(f.data + b.in_off + b.in_len);
+                if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b.out_len) == want) continue;
+            }
+            ++fell_back;
             inflateReset(&zs);
             zs.next_in = (Bytef*)(f.data + b.in_off); zs.avail_in = b.in_len;
-            zs.next_out = out.data() + b.out_off; zs.avail_out = b.out_len;
+            zs.next_out = dst; zs.avail_out = b.out_len;
             int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
         }
         inflateEnd(&zs);
+        if (use_fast && fell_back) g_inflate_fallbacks += fell_back;
     });
     if (bad) throw std::runtime_error(path + ": BGZF inflate failed");
 }
