@@ -130,11 +130,10 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
     }
     out.resize(total);
     std::atomic<bool> bad(false);
-    // BDK_FAST_INFLATE=1: every block goes through the table-driven decoder of fast_inflate.hpp first; its result is accepted
-    // only if the block's CRC32 (BGZF footer) matches, otherwise zlib decodes the block. Off by default: on real BAM blocks
-    // it is 1.4x zlib's inflate (1.2x with the checksum), but on very compressible files (the synthetic BAMs of the tests and
-    // the CPU baseline: 6.4 : 1, long matches) the checksum costs more than the decoder gains.
-    static const bool use_fast = getenv("BDK_FAST_INFLATE") && atoi(getenv("BDK_FAST_INFLATE")) != 0 && !getenv("BDK_ZLIB_ONLY");
+    // Every block goes through the table-driven decoder of fast_inflate.hpp first; its result is accepted only if the block's
+    // CRC32 (BGZF footer, checked by carry-less multiplication) matches, otherwise zlib decodes the block. 1.4x zlib's inflate
+    // on real BAM blocks, about even on very compressible files (the synthetic BAMs of the tests). BDK_FAST_INFLATE=0: zlib only.
+    static const bool use_fast = !(getenv("BDK_FAST_INFLATE") && atoi(getenv("BDK_FAST_INFLATE")) == 0) && !getenv("BDK_ZLIB_ONLY");
     parallel_for(blocks.size(), 64, threads, [&](uint64_t b0, uint64_t b1) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
@@ -147,7 +146,7 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
             uint8_t* dst = out.data() + b.out_off;
             if (use_fast && finf::inflate_raw(f.data + b.in_off, b.in_len, dst, b.out_len, *tables)) {
                 const uint32_t want = rd32(f.data + b.in_off + b.in_len);
-                if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b.out_len) == want) continue;
+                if (finf::crc32_block(dst, b.out_len, [](uint32_t c, const uint8_t* p, size_t n) { return (uint32_t)crc32(c, p, (uInt)n); }) == want) continue;
             }
             ++fell_back;
             inflateReset(&zs);

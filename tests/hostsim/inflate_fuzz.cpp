@@ -48,6 +48,8 @@ int main(int argc, char** argv) {
         std::vector<uint8_t> out(n + 1, 0xAB);
         if (!bdh::finf::inflate_raw(comp.data(), comp.size(), out.data(), n, *T)) { ++refused_good; fprintf(stderr, "refused a good stream: n=%zu level=%d strategy=%d\n", n, level, strategy); continue; }
         if ((n && memcmp(out.data(), src.data(), n) != 0) || out[n] != 0xAB) { ++mismatched; fprintf(stderr, "MISMATCH n=%zu level=%d strategy=%d\n", n, level, strategy); continue; }
+        if (bdh::finf::crc32_block(src.data(), n, [](uint32_t c, const uint8_t* p, size_t k) { return (uint32_t)crc32(c, p, (uInt)k); }) !=
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), src.data(), (uInt)n)) { ++mismatched; fprintf(stderr, "CRC MISMATCH n=%zu\n", n); continue; }
         ++ok;
         // corruptions: flipped bits, truncation, wrong output length
         for (int c = 0; c < 6 && !comp.empty(); ++c) {
