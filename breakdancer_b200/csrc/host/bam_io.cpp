@@ -98,10 +98,31 @@ struct MappedFile {
 };
 
 struct Block { size_t in_off; uint32_t in_len; uint32_t out_len; size_t out_off; };
+
+// The inflated file: a plain allocation that is NOT zero-filled (std::vector::resize would memset more than a gigabyte on one
+// thread before the workers start; here every page is first touched by the worker that inflates into it).
+struct RawBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    RawBuf() {}
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    RawBuf(RawBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    RawBuf& operator=(RawBuf&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~RawBuf() { free(p); }
+    void resize(size_t bytes) {
+        free(p); p = nullptr; n = 0;
+        if (bytes) { p = (uint8_t*)malloc(bytes); if (!p) throw std::bad_alloc(); n = bytes; }
+    }
+    void release() { free(p); p = nullptr; n = 0; }
+    uint8_t* data() { return p; }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+};
 std::atomic<uint64_t> g_inflate_fallbacks(0);     // blocks the fast decoder refused or got wrong (then decoded by zlib)
 
 // Inflate a whole BGZF file into `out` with `threads` workers.
-void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads, std::vector<uint8_t>& out) {
+void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads, RawBuf& out) {
     std::vector<Block> blocks;
     size_t off = 0, total = 0;
     while (off < f.size) {
@@ -163,7 +184,7 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
 
 struct BamData {
     std::string path;
-    std::vector<uint8_t> raw;             // whole inflated file
+    RawBuf raw;                           // whole inflated file
     std::string text;
     std::vector<std::string> tid_names;
     std::vector<uint32_t> tid_lens;
@@ -476,7 +497,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             double t2 = now_s();
             s->t_inflate += t1 - t0; s->t_extract += t2 - t1;
             if (rgt.rg_lib.size() > 65536) throw std::runtime_error("more than 65536 (bam, read group) combinations");
-            if (!keep_records) { std::vector<uint8_t>().swap(bd.raw); std::vector<uint64_t>().swap(bd.rec_off); }
+            if (!keep_records) { bd.raw.release(); std::vector<uint64_t>().swap(bd.rec_off); }
         }
         s->tid_names = s->bams[0].tid_names;  // BamMerger uses the first stream's header (BamMerger.cpp:78)
         s->rg_lib = rgt.rg_lib; s->rg_bam = rgt.rg_bam;
