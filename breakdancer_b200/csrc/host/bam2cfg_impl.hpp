@@ -202,6 +202,7 @@ void b2c_one_bam(const std::string& path, const bdh_bam2cfg_opts& o, const std::
     bd.path = path;
     bgzf_inflate_all(mf, path, default_threads(), bd.raw);
     bd.parse_header();
+    bd.find_records(default_threads());
     // @RG lines (perl/bam2cfg.pl:73-87); -f mappings first, header lines override / add
     std::vector<std::string> rg_order;
     std::map<std::string, std::string> rg_lib(rg_lib_file), rg_platform;

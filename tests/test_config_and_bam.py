@@ -101,3 +101,85 @@ def test_bam_write_read_round_trip(tmp_path):
         assert fq[0] == "@" + st.qname(0) and len(fq[1]) == st.cols["qlen"][0] and fq[2] == "+"
     finally:
         os.chdir(cwd)
+
+
+# ---- record boundaries found in parallel (BamData::find_records) ----------------------------------------------------------
+def _bam_record(tid, pos, name, flag, lseq, mtid, mpos, isize, aux=b"", mapq=30):
+    import struct
+    name_b = name.encode() + b"\0"
+    cigar = struct.pack("<I", (lseq << 4) | 0)
+    seq = bytes((lseq + 1) // 2)
+    qual = bytes([30]) * lseq
+    core = struct.pack("<iiBBHHHiiii", tid, pos, len(name_b), mapq, 4680, 1, flag, lseq, mtid, mpos, isize)
+    body = core + name_b + cigar + seq + qual + aux
+    return struct.pack("<I", len(body)) + body
+
+
+def _bgzf(raw: bytes, block=20000) -> bytes:
+    import struct
+    import zlib
+    out = b""
+    for o in list(range(0, len(raw), block)) + [None]:
+        chunk = b"" if o is None else raw[o:o + block]          # the empty last block is the BGZF end-of-file marker
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        data = co.compress(chunk) + co.flush()
+        out += struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(data) + 25) + data
+        out += struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    return out
+
+
+def _handmade_bam(records) -> bytes:
+    import struct
+    text = b"@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:c1\tLN:100000000\n@RG\tID:g\tLB:L\n"
+    head = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1) + struct.pack("<I", 3) + b"c1\0" + struct.pack("<I", 100000000)
+    return _bgzf(head + b"".join(records))
+
+
+def test_record_chain_segments_with_decoys(tmp_path, monkeypatch):
+    """Records whose aux bytes hold perfectly formed records (decoys): the parallel search for record boundaries must still
+    return the serial chain, however the buffer is cut (csrc/host/bam_io.cpp find_records)."""
+    rng = np.random.default_rng(5)
+    recs, want_pos = [], []
+    pos = 100
+    for i in range(3000):
+        pos += int(rng.integers(1, 50))
+        aux = b"RGZg\0"
+        kind = i % 4
+        if kind == 1:      # a run of decoy records ending exactly where the real record ends (the decoy chain joins the real one)
+            decoys = b"".join(_bam_record(0, 7_000_000 + k, "decoy%d" % k, 99, 20, 0, 7_000_100, 120) for k in range(int(rng.integers(3, 8))))
+            aux += b"XDBC" + np.uint32(len(decoys)).tobytes() + decoys
+        elif kind == 2:    # decoys followed by padding: the decoy chain runs off into garbage
+            decoys = b"".join(_bam_record(0, 8_000_000 + k, "d%d" % k, 147, 10, 0, 8_000_100, -90) for k in range(4))
+            pad = bytes(rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8))
+            aux += b"XDBC" + np.uint32(len(decoys) + len(pad)).tobytes() + decoys + pad
+        elif kind == 3:    # a decoy that claims a huge record reaching far past the real one
+            import struct
+            big = bytearray(_bam_record(0, 9_000_000, "big", 99, 30, 0, 9_000_100, 150))
+            big[0:4] = struct.pack("<I", 50_000)
+            rest = b"".join(_bam_record(0, 9_100_000 + k, "e%d" % k, 99, 30, 0, 9_000_100, 150) for k in range(3))
+            aux += b"XDBC" + np.uint32(len(big) + len(rest)).tobytes() + bytes(big) + rest
+        recs.append(_bam_record(0, pos, "r%d" % i, 99 if i % 2 == 0 else 147, 36, 0, pos + 200, 236, aux))
+        want_pos.append(pos)
+    (tmp_path / "h.bam").write_bytes(_handmade_bam(recs))
+    cfg = api.BamConfig(text="map:%s\tlib:L\tmean:300\tstd:30\treadlen:36\n" % (tmp_path / "h.bam"))
+    results = []
+    for nseg in (1, 2, 7, 64, 1000, 20000):
+        monkeypatch.setenv("BDK_CHAIN_SEGMENTS", str(nseg))
+        st = api.BamStream(cfg, threads=4)
+        results.append({k: v.copy() for k, v in st.cols.items()})
+        st.close()
+    assert results[0]["pos"].tolist() == want_pos
+    for r in results[1:]:
+        for k in results[0]:
+            assert np.array_equal(results[0][k], r[k]), k
+    # a file cut in the middle of a record is refused the same way for every cut
+    raw_recs = b"".join(recs)
+    import struct
+    text = b"@SQ\tSN:c1\tLN:100000000\n"
+    head = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1) + struct.pack("<I", 3) + b"c1\0" + struct.pack("<I", 100000000)
+    (tmp_path / "t.bam").write_bytes(_bgzf(head + raw_recs[:len(raw_recs) - 17]))
+    cfg_t = api.BamConfig(text="map:%s\tlib:L\tmean:300\tstd:30\treadlen:36\n" % (tmp_path / "t.bam"))
+    for nseg in (1, 7, 1000):
+        monkeypatch.setenv("BDK_CHAIN_SEGMENTS", str(nseg))
+        with pytest.raises(RuntimeError, match="truncated BAM record"):
+            api.BamStream(cfg_t, threads=4)
