@@ -398,14 +398,50 @@ Region parse_region(const std::string& s, const std::vector<std::string>& names,
     return r;
 }
 
+// Column storage that is not zero-filled (every element is written by the extraction pass; std::vector::resize would fill
+// 45 bytes per record on one thread first) and that can be handed over to the stream as it is: with one bam there is nothing
+// to merge, so the fields are extracted straight into the (pinned, if asked for) arrays the GPU side reads.
+inline void* col_alloc(size_t bytes, int pinned) {
+    if (bytes == 0) bytes = 16;
+    void* p = 0;
+    if (pinned) {
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+            throw std::runtime_error("cudaHostAlloc failed for the record columns");
+    } else {
+        if (posix_memalign(&p, 256, bytes) != 0) throw std::bad_alloc();
+    }
+    return p;
+}
+inline void col_free(void* p, int pinned) { if (!p) return; if (pinned) cudaFreeHost(p); else free(p); }
+
+template <class T> struct ColBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int pinned = 0;
+    ColBuf() {}
+    ColBuf(const ColBuf&) = delete;
+    ColBuf& operator=(const ColBuf&) = delete;
+    ColBuf(ColBuf&& o) noexcept : p(o.p), n(o.n), pinned(o.pinned) { o.p = nullptr; o.n = 0; }
+    ~ColBuf() { col_free(p, pinned); }
+    void resize(size_t m) { col_free(p, pinned); p = nullptr; n = 0; p = (T*)col_alloc(m * sizeof(T), pinned); n = m; }
+    T* take() { T* q = p; p = nullptr; n = 0; return q; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Columns {
-    std::vector<int32_t> pos, mpos, tid, mtid, isize, qlen;
-    std::vector<uint16_t> flag, rgid;
-    std::vector<uint8_t> mapq;
-    std::vector<uint64_t> qid, rec;  // rec = offset of the raw record in its BamData
+    ColBuf<int32_t> pos, mpos, tid, mtid, isize, qlen;
+    ColBuf<uint16_t> flag, rgid;
+    ColBuf<uint8_t> mapq;
+    ColBuf<uint64_t> qid, rec;  // rec = offset of the raw record in its BamData
+    bool want_rec = true;
+    void set_pinned(int on) { pos.pinned = mpos.pinned = tid.pinned = mtid.pinned = isize.pinned = qlen.pinned = flag.pinned = rgid.pinned = mapq.pinned = qid.pinned = on; }
     void resize(size_t n) {
         pos.resize(n); mpos.resize(n); tid.resize(n); mtid.resize(n); isize.resize(n); qlen.resize(n);
-        flag.resize(n); rgid.resize(n); mapq.resize(n); qid.resize(n); rec.resize(n);
+        flag.resize(n); rgid.resize(n); mapq.resize(n); qid.resize(n);
+        if (want_rec) rec.resize(n);
     }
 };
 
@@ -448,18 +484,8 @@ struct bdh_stream {
     double t_inflate = 0, t_extract = 0, t_merge = 0;
     std::string tmp_name;
 
-    void* alloc(size_t bytes) {
-        if (bytes == 0) bytes = 16;
-        void* p = 0;
-        if (pinned) {
-            if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
-                throw std::runtime_error("cudaHostAlloc failed for the record columns");
-        } else {
-            if (posix_memalign(&p, 256, bytes) != 0) throw std::bad_alloc();
-        }
-        return p;
-    }
-    void release(void* p) { if (!p) return; if (pinned) cudaFreeHost(p); else free(p); }
+    void* alloc(size_t bytes) { return bdh::col_alloc(bytes, pinned); }
+    void release(void* p) { bdh::col_free(p, pinned); }
     ~bdh_stream() {
         release(pos); release(mpos); release(tid); release(mtid); release(isize); release(qlen);
         release(flag); release(rgid); release(mapq); release(qid);
@@ -474,8 +500,13 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
     const uint8_t* raw = bd.raw.data();
     // pass 1: filter flags (primary && tid >= 0 [&& region overlap]) -> keep mask + prefix
     std::vector<uint8_t> keep(nrec);
-    parallel_for(nrec, 1 << 16, threads, [&](uint64_t a, uint64_t b) {
-        for (uint64_t i = a; i < b; ++i) {
+    const uint64_t G = 1 << 16;
+    size_t ng = (nrec + G - 1) / G;
+    std::vector<uint64_t> goff(ng + 1, 0);
+    parallel_for(ng, 1, threads, [&](uint64_t g0, uint64_t g1) {
+      for (uint64_t g = g0; g < g1; ++g) {
+        uint64_t kept = 0;
+        for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) {
             const uint8_t* r = raw + bd.rec_off[i];
             Core c = read_core(r);
             bool ok = !(c.flag & (0x100 | 0x800)) && c.tid >= 0;
@@ -485,16 +516,12 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
                 ok = c.tid == region.tid && rend > (uint32_t)region.beg && c.pos < region.end;
             }
             keep[i] = ok;
+            kept += ok;
         }
+        goff[g + 1] = kept;
+      }
     });
-    const uint64_t G = 1 << 16;
-    size_t ng = (nrec + G - 1) / G;
-    std::vector<uint64_t> goff(ng + 1, 0);
-    for (size_t g = 0; g < ng; ++g) {
-        uint64_t c = 0;
-        for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) c += keep[i];
-        goff[g + 1] = goff[g] + c;
-    }
+    for (size_t g = 0; g < ng; ++g) goff[g + 1] += goff[g];
     out.resize(goff[ng]);
     // pass 2: field extraction
     parallel_for(ng, 1, threads, [&](uint64_t g0, uint64_t g1) {
@@ -519,7 +546,7 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
                 out.mapq[o] = q;
                 size_t nl = c.l_qname ? strnlen((const char*)name, c.l_qname) : 0;
                 out.qid[o] = hash_name(name, nl);
-                out.rec[o] = bd.rec_off[i];
+                if (out.want_rec) out.rec[o] = bd.rec_off[i];
                 const char* rgs = ""; size_t rgl = 0;
                 if (aux <= end) {
                     if (const uint8_t* rg = aux_get(aux, end, "RG")) {
@@ -567,6 +594,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
         s->bams.resize(files.size());
         RgTable rgt; rgt.cfg = &cfg;
         std::vector<Columns> cols(files.size());
+        for (auto& c : cols) { c.want_rec = keep_records != 0; if (files.size() == 1) c.set_pinned(pinned); }
         for (size_t b = 0; b < files.size(); ++b) {
             BamData& bd = s->bams[b];
             bd.path = files[b];
@@ -593,12 +621,21 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
         uint64_t n = 0;
         for (auto& c : cols) n += c.pos.size();
         s->n = n;
+        double t3 = now_s();
+        if (files.size() == 1) {
+            // nothing to merge: the extraction wrote the final arrays
+            Columns& c = cols[0];
+            s->pos = c.pos.take(); s->mpos = c.mpos.take(); s->tid = c.tid.take(); s->mtid = c.mtid.take(); s->isize = c.isize.take();
+            s->qlen = c.qlen.take(); s->flag = c.flag.take(); s->rgid = c.rgid.take(); s->mapq = c.mapq.take(); s->qid = c.qid.take();
+            if (keep_records) { s->rec_bam.assign(n, 0); s->rec_off.assign(c.rec.p, c.rec.p + n); }
+            s->t_merge = now_s() - t3;
+            return s;
+        }
         s->pos = (int32_t*)s->alloc(n * 4); s->mpos = (int32_t*)s->alloc(n * 4); s->tid = (int32_t*)s->alloc(n * 4);
         s->mtid = (int32_t*)s->alloc(n * 4); s->isize = (int32_t*)s->alloc(n * 4); s->qlen = (int32_t*)s->alloc(n * 4);
         s->flag = (uint16_t*)s->alloc(n * 2); s->rgid = (uint16_t*)s->alloc(n * 2);
         s->mapq = (uint8_t*)s->alloc(n); s->qid = (uint64_t*)s->alloc(n * 8);
         if (keep_records) { s->rec_bam.resize(n); s->rec_off.resize(n); }
-        double t3 = now_s();
         // merge order: for each output slot o, (bam, i)
         auto put = [&](uint64_t o, int b, uint64_t i) {
             Columns& c = cols[b];
@@ -607,9 +644,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             s->mapq[o] = c.mapq[i]; s->qid[o] = c.qid[i];
             if (keep_records) { s->rec_bam[o] = (uint8_t)b; s->rec_off[o] = c.rec[i]; }
         };
-        if (files.size() == 1) {
-            parallel_for(n, 1 << 18, threads, [&](uint64_t a, uint64_t e) { for (uint64_t i = a; i < e; ++i) put(i, 0, i); });
-        } else {
+        {
             // Same container, comparator and push/pop sequence as the reference's BamMerger, so
             // ties between bams resolve the same way.
             auto greater = [&](const Head& x, const Head& y) {
