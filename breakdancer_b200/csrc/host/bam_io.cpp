@@ -589,6 +589,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
         if (paths) for (int i = 0; i < npaths; ++i) files.push_back(paths[i]);
         else files = cfg.bam_files;
         if (files.empty()) throw std::runtime_error("BamMerger created with no input streams!");
+        if (files.size() > 255) throw std::runtime_error("more than 255 bam files");
         s = new bdh_stream;
         s->pinned = pinned;
         s->bams.resize(files.size());
@@ -604,6 +605,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
                 bgzf_inflate_all(mf, files[b], threads, bd.raw);
             }
             double t1 = now_s();
+            const size_t raw_bytes = bd.raw.size();
             bd.parse_header();
             bd.find_records(threads);
             double t1b = now_s();
@@ -611,7 +613,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             if (region && region[0]) rg = parse_region(region, bd.tid_names, files[b]);
             extract_bam(bd, (int)b, rg, rgt, threads, cols[b]);
             double t2 = now_s();
-            if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] %s: inflate %.3f s, record chain %.3f s, extract %.3f s\n", files[b].c_str(), t1 - t0, t1b - t1, t2 - t1b);
+            if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] %s: %.1f MB inflated in %.3f s, record chain %.3f s, extract %.3f s\n", files[b].c_str(), raw_bytes / 1e6, t1 - t0, t1b - t1, t2 - t1b);
             s->t_inflate += t1 - t0; s->t_extract += t2 - t1;
             if (rgt.rg_lib.size() > 65536) throw std::runtime_error("more than 65536 (bam, read group) combinations");
             if (!keep_records) { bd.raw.release(); std::vector<uint64_t>().swap(bd.rec_off); }
@@ -645,23 +647,92 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             if (keep_records) { s->rec_bam[o] = (uint8_t)b; s->rec_off[o] = c.rec[i]; }
         };
         {
-            // Same container, comparator and push/pop sequence as the reference's BamMerger, so
-            // ties between bams resolve the same way.
-            auto greater = [&](const Head& x, const Head& y) {
-                Columns const& cx = cols[x.bam]; Columns const& cy = cols[y.bam];
-                if (cx.tid[x.i] != cy.tid[y.i]) return cx.tid[x.i] > cy.tid[y.i];
-                if (cx.pos[x.i] != cy.pos[y.i]) return cx.pos[x.i] > cy.pos[y.i];
-                return ((cx.flag[x.i] & 0x10) != 0) > ((cy.flag[y.i] & 0x10) != 0);
-            };
+            // Same container, comparator outcomes and push/pop sequence as the reference's BamMerger, so ties between bams
+            // resolve the same way. Only the ORDER is decided serially, on one packed key per
+            // record ((tid, pos, strand) lexicographic, the reference's comparison); the columns are moved afterwards by all
+            // cores, each output chunk starting from the per-bam cursors noted when the serial pass went by.
+            const size_t nb = files.size();
+            std::vector<std::vector<uint64_t>> keys(nb);
+            std::atomic<bool> sorted(true);            // every bam ordered by (tid, pos)? (the strand bit is not part of a bam's order)
+            for (size_t b = 0; b < nb; ++b) {
+                Columns const& c = cols[b];
+                keys[b].resize(c.pos.size());
+                uint64_t* k = keys[b].data();
+                parallel_for(c.pos.size(), 1 << 18, threads, [&](uint64_t lo, uint64_t hi) {
+                    for (uint64_t i = lo; i < hi; ++i)
+                        k[i] = (uint64_t)(uint32_t)c.tid[i] << 33 | (uint64_t)((uint32_t)c.pos[i] ^ 0x80000000u) << 1 | (uint64_t)((c.flag[i] & 0x10) != 0);
+                    bool ok = true;
+                    for (uint64_t i = std::max<uint64_t>(lo, 1); i < hi; ++i)
+                        ok &= c.tid[i - 1] < c.tid[i] || (c.tid[i - 1] == c.tid[i] && c.pos[i - 1] <= c.pos[i]);
+                    if (!ok) sorted = false;
+                });
+            }
+            if (nb == 2 && sorted && !getenv("BDK_MERGE_HEAP")) {
+                // Two streams: the heap's behaviour has a closed form. After a pop from stream A the heap holds B's head alone;
+                // A's next record is pushed below it and sifts up only if it is STRICTLY smaller, so on a tie the stream that
+                // did not emit last goes first (at the very start: bam 0, pushed first). A history-free rule, so the merge of
+                // two bams that are each ordered by (tid, pos) can be cut at any (tid, pos) that starts in bam 0 and does not
+                // occur in bam 1 (everything before it leaves both streams first, and the heads differ after it): found by a few
+                // probes after each even cut. Unsorted input takes the priority queue below.
+                const uint64_t* K0 = keys[0].data(); const uint64_t* K1 = keys[1].data();
+                const uint64_t n0 = keys[0].size(), n1 = keys[1].size();
+                std::vector<std::pair<uint64_t, uint64_t>> cuts;
+                cuts.push_back({0, 0});
+                const uint64_t parts = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads * 4, n >> 14));
+                for (uint64_t q = 1; q < parts; ++q) {
+                    uint64_t i0 = n0 * q / parts;
+                    if (i0 <= cuts.back().first) continue;
+                    for (int tries = 0; i0 < n0 && tries < 4096; ++tries, ++i0) {
+                        if ((K0[i0] >> 1) == (K0[i0 - 1] >> 1)) continue;
+                        const uint64_t want = K0[i0] >> 1;
+                        const uint64_t i1 = std::lower_bound(K1, K1 + n1, want, [](uint64_t k, uint64_t w) { return (k >> 1) < w; }) - K1;
+                        if (i1 < n1 && (K1[i1] >> 1) == want) continue;
+                        cuts.push_back({i0, i1});
+                        break;
+                    }
+                }
+                cuts.push_back({n0, n1});
+                if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] two-way merge in %zu independent parts\n", cuts.size() - 1);
+                parallel_for(cuts.size() - 1, 1, threads, [&](uint64_t p0, uint64_t p1) {
+                    for (uint64_t q = p0; q < p1; ++q) {
+                        uint64_t i = cuts[q].first, j = cuts[q].second;
+                        const uint64_t e0 = cuts[q + 1].first, e1 = cuts[q + 1].second;
+                        uint64_t o = i + j;
+                        int last = 1;
+                        while (i < e0 && j < e1) {
+                            const bool take0 = last == 0 ? K0[i] < K1[j] : K0[i] <= K1[j];
+                            if (take0) { put(o++, 0, i++); last = 0; } else { put(o++, 1, j++); last = 1; }
+                        }
+                        while (i < e0) put(o++, 0, i++);
+                        while (j < e1) put(o++, 1, j++);
+                    }
+                });
+                s->t_merge = now_s() - t3;
+                return s;
+            }
+            auto greater = [&](const Head& x, const Head& y) { return keys[x.bam][x.i] > keys[y.bam][y.i]; };
             std::priority_queue<Head, std::vector<Head>, decltype(greater)> pq(greater);
-            for (size_t b = 0; b < files.size(); ++b)
+            for (size_t b = 0; b < nb; ++b)
                 if (!cols[b].pos.empty()) pq.push(Head{(int)b, 0});
+            const uint64_t CH = 1 << 16;
+            const uint64_t nch = (n + CH - 1) / CH;
+            std::vector<uint8_t> src(n);
+            std::vector<uint64_t> cursor((nch + 1) * nb, 0), emitted(nb, 0);
             uint64_t o = 0;
             while (!pq.empty()) {
                 Head h = pq.top(); pq.pop();
-                put(o++, h.bam, h.i);
+                if ((o & (CH - 1)) == 0) for (size_t b = 0; b < nb; ++b) cursor[(o / CH) * nb + b] = emitted[b];
+                src[o++] = (uint8_t)h.bam;
+                ++emitted[h.bam];
                 if (h.i + 1 < cols[h.bam].pos.size()) pq.push(Head{h.bam, h.i + 1});
             }
+            parallel_for(nch, 1, threads, [&](uint64_t c0, uint64_t c1) {
+                std::vector<uint64_t> cur(nb);
+                for (uint64_t ch = c0; ch < c1; ++ch) {
+                    for (size_t b = 0; b < nb; ++b) cur[b] = cursor[ch * nb + b];
+                    for (uint64_t q = ch * CH; q < std::min<uint64_t>(n, (ch + 1) * CH); ++q) { const int b = src[q]; put(q, b, cur[b]++); }
+                }
+            });
         }
         s->t_merge = now_s() - t3;
         return s;

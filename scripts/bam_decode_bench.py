@@ -23,9 +23,11 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--dir", default="/tmp/bdk_decode_bench")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"], help="config3: two bams (tumor / normal), merged")
     a = ap.parse_args()
+    a.dir = os.path.join(a.dir, a.workload)
     os.makedirs(a.dir, exist_ok=True)
-    w = synth.config2(a.pairs, seed=11, chrom_len=50_000_000)
+    w = synth.config2(a.pairs, seed=11, chrom_len=50_000_000) if a.workload == "config2" else synth.config3(a.pairs, seed=11)
     cwd = os.getcwd()
     os.chdir(a.dir)
     try:

@@ -183,3 +183,44 @@ def test_record_chain_segments_with_decoys(tmp_path, monkeypatch):
         monkeypatch.setenv("BDK_CHAIN_SEGMENTS", str(nseg))
         with pytest.raises(RuntimeError, match="truncated BAM record"):
             api.BamStream(cfg_t, threads=4)
+
+
+def test_two_bam_merge_in_parallel_equals_the_heap_merge(tmp_path, monkeypatch):
+    """Two bams full of equal (tid, pos, strand) keys: the partitioned two-way merge (closed form of the reference's
+    priority-queue ties, BamMerger.cpp:40-126) against the priority queue itself; also three bams (heap path with packed keys)
+    against the same records split differently, and an empty second bam."""
+    rng = np.random.default_rng(9)
+
+    def bam(path, n, tag, lo=100, hi=40000, sort=True):
+        pos = rng.integers(lo, hi, n)                                       # 1-2 records per position and bam: ties everywhere, gaps too
+        if sort:
+            pos = np.sort(pos)
+        recs = [_bam_record(0, int(p), "%s%d" % (tag, i), 99 if rng.random() < 0.5 else 147, 36, 0, int(p) + 200, 236, b"RGZg\0")
+                for i, p in enumerate(pos)]
+        # records with equal positions must come in the order the comparator gives inside one (sorted) bam: any order is legal
+        path.write_bytes(_handmade_bam(recs))
+
+    bam(tmp_path / "a.bam", 60000, "a")
+    bam(tmp_path / "b.bam", 45000, "b")
+    bam(tmp_path / "c.bam", 20000, "c")
+    bam(tmp_path / "d.bam", 40000, "d", hi=400)                             # every position of d also occurs in a: no place to cut
+    bam(tmp_path / "u.bam", 30000, "u", sort=False)                         # not sorted: the priority queue decides, as in the reference
+    (tmp_path / "e.bam").write_bytes(_handmade_bam([]))
+    line = "map:%s\tlib:L%d\tmean:300\tstd:30\treadlen:36\n"
+    for names in (("a", "b"), ("b", "a"), ("a", "d"), ("d", "a"), ("a", "u"), ("a", "e"), ("e", "a"), ("a", "b", "c")):
+        cfg = api.BamConfig(text="".join(line % (tmp_path / (nm + ".bam"), i) for i, nm in enumerate(names)))
+        paths = [str(tmp_path / (nm + ".bam")) for nm in names]
+        got = {}
+        for mode in ("parallel", "heap"):
+            if mode == "heap":
+                monkeypatch.setenv("BDK_MERGE_HEAP", "1")
+            else:
+                monkeypatch.delenv("BDK_MERGE_HEAP", raising=False)
+            st = api.BamStream(cfg, paths=paths, threads=8, keep_records=True)
+            got[mode] = {k: v.copy() for k, v in st.cols.items()}
+            got[mode]["names"] = [st.qname(i) for i in range(0, st.n, 97)]
+            st.close()
+        for k in got["heap"]:
+            assert np.array_equal(got["heap"][k], got["parallel"][k]) if k != "names" else got["heap"][k] == got["parallel"][k], (names, k)
+        p = got["heap"]["pos"]
+        assert "u" in names or np.all(p[1:] >= p[:-1])
