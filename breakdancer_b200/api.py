@@ -146,6 +146,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdk_k4_sweeps": (C.c_uint32, [vp]),
         "bdk_poisson_logsf": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(C.c_double), u64]),
         "bdk_version": (C.c_char_p, []),
+        "bdk_bgzf_inflate": (C.c_int, [C.c_int, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.POINTER(i32), C.POINTER(C.c_float)]),
         "bdh_config_parse": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
         "bdh_config_load": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
         "bdh_config_free": (None, [vp]),
@@ -168,6 +169,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdh_stream_tid_name": (C.c_char_p, [vp, C.c_int]),
         "bdh_stream_qname": (C.c_char_p, [vp, u64]),
         "bdh_stream_fastq": (C.c_int, [vp, u64, C.c_char_p, C.c_int]),
+        "bdh_inflate_counters": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "bdh_stream_timings": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bdh_write_bam": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_int,
                                     C.POINTER(C.c_char_p), C.POINTER(Soa), u64, C.c_char_p, C.c_int, C.c_int,
@@ -303,6 +305,13 @@ class BamStream:
 
     def __del__(self):
         self.close()
+
+
+def inflate_counters():
+    """(members the host's fast decoder handed to zlib, members the GPU decoder got wrong and the host redid), process-wide."""
+    a, b = C.c_uint64(), C.c_uint64()
+    load_library().bdh_inflate_counters(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 class ParamBundle:

@@ -17,6 +17,7 @@
 
 #include "../../include/bdk.h"
 #include "bdk_finalize.h"
+#include "bgzf_inflate.cuh"
 #include "comm.cuh"
 #include "k1_classify.cuh"
 #include "k234_regions_links_sv.cuh"
@@ -1090,6 +1091,85 @@ int bdk_poisson_logsf(bdk_ctx* c, const double* lambda, const int32_t* k, double
     CU(cudaMemcpyAsync(out, c->d_pois_o.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// ---- BGZF members inflated on the device (opt-in path of the BAM reader, csrc/host/bam_io.cpp) ---------------------------
+static_assert(sizeof(bdk_bgzf_member) == sizeof(bgz::Member), "bdk_bgzf_member and bgz::Member must have one layout");
+int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const bdk_bgzf_member* members, uint64_t n_members,
+                     uint8_t* out, uint64_t out_bytes, int32_t* status, float* kernel_ms) {
+    if (!file || !members || !out || !status) return BDK_ERR_ARG;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (!n_members) return 0;
+    for (uint64_t i = 0; i < n_members; ++i) {
+        const bdk_bgzf_member& m = members[i];
+        if (m.in_off > file_bytes || file_bytes - m.in_off < m.in_len || m.out_off > out_bytes || out_bytes - m.out_off < m.out_len) return BDK_ERR_ARG;
+        if (i && (m.in_off < members[i - 1].in_off || m.out_off < members[i - 1].out_off)) return BDK_ERR_ARG;     // file order
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BDK_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return BDK_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BDK_ERR_CUDA;
+    const size_t smem = (size_t)bgz::CTA_THREADS * bgz::LUT_PER_THREAD * sizeof(uint16_t);
+    if (cudaFuncSetAttribute(bgz::bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BDK_ERR_CUDA;
+    const unsigned grid = (unsigned)prop.multiProcessorCount;
+    // batches of members: at most 256 MiB of input and 1 GiB of output on the device at a time
+    const uint64_t IN_CAP = 256ull << 20, OUT_CAP = 1ull << 30;
+    uint8_t *d_in = 0, *d_out = 0; bgz::Member* d_mem = 0; bgz::Scratch* d_scr = 0; int32_t* d_st = 0;
+    cudaEvent_t e0 = 0, e1 = 0;
+    cudaStream_t st = 0;
+    std::vector<bgz::Member> batch;
+    int rc = 0;
+    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && !rc) rc = BDK_ERR_CUDA; return e == cudaSuccess; };
+    uint64_t max_members = 0;
+    {   // size the buffers for the largest batch
+        uint64_t i = 0;
+        while (i < n_members) {
+            uint64_t j = i, in_b = 0, out_b = 0;
+            while (j < n_members && (j == i || (members[j].in_off + members[j].in_len - members[i].in_off <= IN_CAP && out_b + members[j].out_len <= OUT_CAP))) {
+                in_b = members[j].in_off + members[j].in_len - members[i].in_off; out_b += members[j].out_len; ++j;
+            }
+            max_members = std::max(max_members, j - i);
+            i = j;
+        }
+    }
+    ck(cudaStreamCreate(&st)); ck(cudaEventCreate(&e0)); ck(cudaEventCreate(&e1));
+    ck(cudaMalloc(&d_in, IN_CAP + (1 << 17))); ck(cudaMalloc(&d_out, OUT_CAP + (1 << 17)));
+    ck(cudaMalloc(&d_mem, max_members * sizeof(bgz::Member))); ck(cudaMalloc(&d_st, max_members * sizeof(int32_t)));
+    ck(cudaMalloc(&d_scr, (size_t)grid * bgz::CTA_THREADS * sizeof(bgz::Scratch)));
+    uint64_t i = 0;
+    while (!rc && i < n_members) {
+        uint64_t j = i, in_b = 0, out_b = 0;
+        batch.clear();
+        while (j < n_members && (j == i || (members[j].in_off + members[j].in_len - members[i].in_off <= IN_CAP && out_b + members[j].out_len <= OUT_CAP))) {
+            bgz::Member m;
+            m.in_off = members[j].in_off - members[i].in_off; m.out_off = out_b; m.in_len = members[j].in_len; m.out_len = members[j].out_len;
+            batch.push_back(m);
+            in_b = members[j].in_off + members[j].in_len - members[i].in_off; out_b += members[j].out_len; ++j;
+        }
+        if (in_b > IN_CAP + (1 << 17) || out_b > OUT_CAP + (1 << 17)) { rc = BDK_ERR_ARG; break; }      // a member larger than BGZF allows
+        // members are in file order but need not be contiguous in `out`: copy back member by member only if they are not
+        bool contiguous = true;
+        for (uint64_t k = i + 1; k < j; ++k) contiguous &= members[k].out_off == members[k - 1].out_off + members[k - 1].out_len;
+        if (!ck(cudaMemcpyAsync(d_in, file + members[i].in_off, in_b, cudaMemcpyHostToDevice, st))) break;
+        if (!ck(cudaMemcpyAsync(d_mem, batch.data(), batch.size() * sizeof(bgz::Member), cudaMemcpyHostToDevice, st))) break;
+        ck(cudaEventRecord(e0, st));
+        bgz::bgzf_inflate_kernel<<<grid, bgz::CTA_THREADS, smem, st>>>(d_in, d_mem, batch.size(), d_out, d_scr, d_st);
+        ck(cudaGetLastError());
+        ck(cudaEventRecord(e1, st));
+        if (contiguous) ck(cudaMemcpyAsync(out + members[i].out_off, d_out, out_b, cudaMemcpyDeviceToHost, st));
+        else for (uint64_t k = i; k < j && !rc; ++k) ck(cudaMemcpyAsync(out + members[k].out_off, d_out + batch[k - i].out_off, members[k].out_len, cudaMemcpyDeviceToHost, st));
+        ck(cudaMemcpyAsync(status + i, d_st, batch.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (!ck(cudaStreamSynchronize(st))) break;
+        float ms = 0.f;
+        if (ck(cudaEventElapsedTime(&ms, e0, e1)) && kernel_ms) *kernel_ms += ms;
+        i = j;
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_mem); cudaFree(d_st); cudaFree(d_scr);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
 }
 
 }  // extern "C"

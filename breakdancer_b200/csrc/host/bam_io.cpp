@@ -119,6 +119,7 @@ struct RawBuf {
     const uint8_t* data() const { return p; }
     size_t size() const { return n; }
 };
+std::atomic<uint64_t> g_gpu_inflate_redone(0);    // members the GPU decoder refused or got wrong (then decoded on the host)
 std::atomic<uint64_t> g_inflate_fallbacks(0);     // blocks the fast decoder refused or got wrong (then decoded by zlib)
 
 // Inflate a whole BGZF file into `out` with `threads` workers.
@@ -155,6 +156,26 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
     // CRC32 (BGZF footer, checked by carry-less multiplication) matches, otherwise zlib decodes the block. 1.4x zlib's inflate
     // on real BAM blocks, about even on very compressible files (the synthetic BAMs of the tests). BDK_FAST_INFLATE=0: zlib only.
     static const bool use_fast = !(getenv("BDK_FAST_INFLATE") && atoi(getenv("BDK_FAST_INFLATE")) == 0) && !getenv("BDK_ZLIB_ONLY");
+    // BDK_GPU_INFLATE=1: all members are inflated by the GPU first (csrc/bgzf_inflate.cuh through bdk_bgzf_inflate); the workers
+    // below then only check the CRC32 of every member and re-inflate on the host whatever the device refused or got wrong.
+    std::vector<int32_t> gpu_status;
+    if (getenv("BDK_GPU_INFLATE") && atoi(getenv("BDK_GPU_INFLATE")) > 0 && !blocks.empty()) {
+        std::vector<bdk_bgzf_member> mem(blocks.size());
+        for (size_t i = 0; i < blocks.size(); ++i) { mem[i].in_off = blocks[i].in_off; mem[i].out_off = blocks[i].out_off; mem[i].in_len = blocks[i].in_len; mem[i].out_len = blocks[i].out_len; }
+        gpu_status.assign(blocks.size(), -1);
+        float kms = 0.f;
+        const double t0 = now_s();
+        const int dev = getenv("BDK_GPU_INFLATE_DEVICE") ? atoi(getenv("BDK_GPU_INFLATE_DEVICE")) : 0;
+        const int rc = bdk_bgzf_inflate(dev, f.data, f.size, mem.data(), mem.size(), out.data(), out.size(), gpu_status.data(), &kms);
+        if (rc != 0) throw std::runtime_error(path + ": BDK_GPU_INFLATE is set but the device inflate failed (error " + std::to_string(rc) + "); there is no silent fallback");
+        if (getenv("BDK_DECODE_TRACE")) {
+            size_t refused = 0;
+            for (int32_t v : gpu_status) refused += v != 0;
+            fprintf(stderr, "[decode] %s: %zu BGZF members, %.1f MB -> %.1f MB on the GPU: kernel %.3f ms (%.1f GB/s of output), with copies %.3f s, %zu members refused\n",
+                    path.c_str(), blocks.size(), f.size / 1e6, total / 1e6, kms, kms > 0 ? total / 1e6 / kms : 0.0, now_s() - t0, refused);
+        }
+    }
+    std::atomic<uint64_t> gpu_wrong(0);
     parallel_for(blocks.size(), 64, threads, [&](uint64_t b0, uint64_t b1) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
@@ -165,6 +186,13 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
             Block const& b = blocks[i];
             if (b.out_len == 0) continue;
             uint8_t* dst = out.data() + b.out_off;
+            if (!gpu_status.empty()) {
+                if (gpu_status[i] == 0) {
+                    const uint32_t want = rd32(f.data + b.in_off + b.in_len);
+                    if (finf::crc32_block(dst, b.out_len, [](uint32_t c, const uint8_t* p, size_t n) { return (uint32_t)crc32(c, p, (uInt)n); }) == want) continue;
+                }
+                ++gpu_wrong;
+            }
             if (use_fast && finf::inflate_raw(f.data + b.in_off, b.in_len, dst, b.out_len, *tables)) {
                 const uint32_t want = rd32(f.data + b.in_off + b.in_len);
                 if (finf::crc32_block(dst, b.out_len, [](uint32_t c, const uint8_t* p, size_t n) { return (uint32_t)crc32(c, p, (uInt)n); }) == want) continue;
@@ -179,6 +207,7 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
         inflateEnd(&zs);
         if (use_fast && fell_back) g_inflate_fallbacks += fell_back;
     });
+    if (gpu_wrong) g_gpu_inflate_redone += gpu_wrong;
     if (bad) throw std::runtime_error(path + ": BGZF inflate failed");
 }
 
@@ -755,6 +784,10 @@ const int32_t* bdh_stream_rg_bam(const bdh_stream* s) { return s->rg_bam.data();
 int bdh_stream_ntid(const bdh_stream* s) { return (int)s->tid_names.size(); }
 const char* bdh_stream_tid_name(const bdh_stream* s, int tid) {
     return tid >= 0 && tid < (int)s->tid_names.size() ? s->tid_names[tid].c_str() : "";
+}
+void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone) {
+    if (host_fallbacks) *host_fallbacks = bdh::g_inflate_fallbacks.load();
+    if (gpu_redone) *gpu_redone = bdh::g_gpu_inflate_redone.load();
 }
 void bdh_stream_timings(const bdh_stream* s, double* a, double* b, double* c) {
     if (a) *a = s->t_inflate; if (b) *b = s->t_extract; if (c) *c = s->t_merge;

@@ -246,6 +246,21 @@ uint64_t bdk_comm_bytes(bdk_ctx* ctx);
  * evaluated on the device (for known-answer tests). */
 int bdk_poisson_logsf(bdk_ctx* ctx, const double* lambda, const int32_t* k, double* out, uint64_t n);
 
+/* BGZF members inflated on the GPU (csrc/bgzf_inflate.cuh; replaces the zlib calls under the reference's samtools reader,
+ * vendor/samtools0.1.19/bgzf.c inflate_block, for whole files at once). `file` is the host image of the BGZF file, `members`
+ * its DEFLATE streams (offsets into `file` and into `out`; out_len from the member's ISIZE footer), `out` a host buffer of
+ * out_bytes. status[i] = 0 if member i decoded to exactly out_len bytes, else a positive error code: the caller checks the
+ * members' CRC32 and re-inflates whatever failed. Needs no context; returns 0 or BDK_ERR_*. kernel_ms (may be NULL) receives
+ * the summed duration of the inflate kernel launches. */
+typedef struct bdk_bgzf_member {
+    uint64_t in_off;
+    uint64_t out_off;
+    uint32_t in_len;
+    uint32_t out_len;
+} bdk_bgzf_member;
+int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const bdk_bgzf_member* members, uint64_t n_members,
+                     uint8_t* out, uint64_t out_bytes, int32_t* status, float* kernel_ms);
+
 const char* bdk_version(void);
 
 #ifdef __cplusplus

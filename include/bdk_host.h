@@ -61,6 +61,9 @@ const char* bdh_stream_qname(const bdh_stream* s, uint64_t i);
 int bdh_stream_fastq(const bdh_stream* s, uint64_t i, char* buf, int cap);
 /* seconds spent in (inflate, parse+extract, merge) by the last open */
 void bdh_stream_timings(const bdh_stream* s, double* inflate_s, double* extract_s, double* merge_s);
+/* Process-wide counters of the BGZF stage: members the host's table-driven decoder handed to zlib, and (BDK_GPU_INFLATE=1)
+ * members the GPU decoder refused or got wrong and the host decoded again. */
+void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone);
 
 /* ---- BAM writer for synthetic inputs (stands in for samtools' bam_write1) ------------------
  * Writes n records from struct-of-arrays columns as a BGZF-compressed BAM with query names

@@ -1,0 +1,139 @@
+"""BGZF members inflated on the GPU (csrc/bgzf_inflate.cuh, C ABI bdk_bgzf_inflate, BDK_GPU_INFLATE=1 in the BAM reader).
+
+CPU: the member decoder every GPU thread runs, compiled for the host, differential- and corruption-fuzzed against zlib under
+AddressSanitizer / UBSan (tests/hostsim/gpu_inflate_host.cpp). GPU: the kernel against zlib on the members of generated BAM
+files and on damaged members, then the reader itself with the device path switched on: same columns as the host path and
+not one member redone by the host. (The file sorts last on purpose: it covers an opt-in path.)"""
+import ctypes as C
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from breakdancer_b200 import api, synth
+from tests import util
+
+
+def test_member_decoder_differential_and_corruption_fuzz_on_the_host():
+    src = os.path.join(util.ROOT, "tests", "hostsim", "gpu_inflate_host.cpp")
+    exe = os.path.join(util.ROOT, "tests", "_build", "gpu_inflate_host")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer",
+                           src, "-o", exe, "-lz"])
+    p = subprocess.run([exe, "500"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "refused_good=0 mismatched=0" in p.stdout, p.stdout
+
+
+def _members(data: bytes):
+    """(in_off, in_len, out_len) of every BGZF member of a file image."""
+    out, off = [], 0
+    while off + 18 <= len(data):
+        xlen = struct.unpack_from("<H", data, off + 10)[0]
+        bsize = struct.unpack_from("<H", data, off + 16)[0] + 1
+        isize = struct.unpack_from("<I", data, off + bsize - 4)[0]
+        out.append((off + 12 + xlen, bsize - 12 - xlen - 8, isize))
+        off += bsize
+    return out
+
+
+def _gpu_inflate(data: bytes, members):
+    L = api.load_library()
+    arr = np.zeros(len(members), dtype=np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4")]))
+    o = 0
+    for i, (in_off, in_len, out_len) in enumerate(members):
+        arr[i] = (in_off, o, in_len, out_len)
+        o += out_len
+    out = np.full(o + 64, 0xEE, dtype=np.uint8)
+    status = np.full(len(members), -1, dtype=np.int32)
+    ms = C.c_float()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    rc = L.bdk_bgzf_inflate(0, buf.ctypes.data, len(data), arr.ctypes.data, len(members), out.ctypes.data, o,
+                            status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
+    assert rc == 0, rc
+    assert np.all(out[o:] == 0xEE)
+    return out[:o], status, arr, ms.value
+
+
+def _synthetic_bam(tmp_path, n_pairs, level):
+    w = synth.generate(util.GENOME3, util.LIBS4, n_pairs, seed=21, anomaly_frac=0.05)
+    d = tmp_path / ("l%d" % level)
+    d.mkdir()
+    for bam, cols in synth.split_by_bam(w).items():
+        api.write_bam(str(d / bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=level)
+    (d / "cfg").write_text(w.config_text())
+    return w, d
+
+
+@pytest.mark.gpu
+def test_kernel_against_zlib_on_bam_members(tmp_path):
+    for level in (1, 6, 9, 0):
+        w, d = _synthetic_bam(tmp_path, 60000, level)
+        for bam in sorted(synth.split_by_bam(w)):
+            data = (d / bam).read_bytes()
+            members = _members(data)
+            got, status, arr, ms = _gpu_inflate(data, members)
+            assert np.all(status == 0), (level, bam, status[status != 0][:10])
+            want = b"".join(zlib.decompress(data[a:a + n], -15) for a, n, _ in members)
+            assert got.tobytes() == want, (level, bam)
+    # the bundled real BAMs (samtools-written members)
+    for name in ("NA19238_chr21_del_inv.bam", "NA19240_chr21_del_inv.bam"):
+        data = open(os.path.join(util.CHR21, name), "rb").read()
+        members = _members(data)
+        got, status, _, _ = _gpu_inflate(data, members)
+        assert np.all(status == 0)
+        assert got.tobytes() == b"".join(zlib.decompress(data[a:a + n], -15) for a, n, _ in members)
+
+
+@pytest.mark.gpu
+def test_kernel_refuses_damaged_members_without_touching_their_neighbours(tmp_path):
+    w, d = _synthetic_bam(tmp_path, 30000, 6)
+    bam = sorted(synth.split_by_bam(w))[0]
+    data = bytearray((d / bam).read_bytes())
+    members = _members(bytes(data))
+    good = [zlib.decompress(bytes(data[a:a + n]), -15) for a, n, _ in members]
+    rng = np.random.default_rng(3)
+    damaged = sorted(rng.choice(len(members) - 1, size=min(12, len(members) - 1), replace=False).tolist())
+    for k, m in enumerate(damaged):
+        a, n, _ = members[m]
+        if k % 3 == 0:
+            data[a + int(rng.integers(0, n))] ^= 1 << int(rng.integers(0, 8))        # a flipped bit
+        elif k % 3 == 1:
+            members[m] = (a, max(1, n // 2), members[m][2])                          # truncated input
+        else:
+            members[m] = (a, n, members[m][2] + 1)                                   # wrong output length
+    got, status, arr, _ = _gpu_inflate(bytes(data), members)
+    for i, (a, n, olen) in enumerate(members):
+        o = int(arr[i]["out_off"])
+        if i not in damaged:
+            assert status[i] == 0 and got[o:o + olen].tobytes() == good[i], i
+        elif status[i] == 0:                        # a flipped bit may still give a well-formed stream of the right length: the CRC catches it
+            assert olen == len(good[i])
+    assert any(status[m] != 0 for m in damaged)
+
+
+@pytest.mark.gpu
+def test_reader_with_the_device_inflate_gives_the_same_columns(tmp_path, monkeypatch):
+    w, d = _synthetic_bam(tmp_path, 80000, 6)
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        cfg = api.BamConfig(text=w.config_text())
+        monkeypatch.delenv("BDK_GPU_INFLATE", raising=False)
+        host = api.BamStream(cfg, threads=4)
+        want = {k: v.copy() for k, v in host.cols.items()}
+        host.close()
+        redone_before = api.inflate_counters()[1]
+        monkeypatch.setenv("BDK_GPU_INFLATE", "1")
+        dev = api.BamStream(cfg, threads=4)
+        assert dev.n == w.n
+        for k, v in want.items():
+            assert np.array_equal(v, dev.cols[k]), k
+        dev.close()
+        assert api.inflate_counters()[1] == redone_before          # the GPU decoded every member itself
+    finally:
+        os.chdir(cwd)
