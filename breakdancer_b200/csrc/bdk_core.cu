@@ -1134,7 +1134,7 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
         }
     }
     ck(cudaStreamCreate(&st)); ck(cudaEventCreate(&e0)); ck(cudaEventCreate(&e1));
-    ck(cudaMalloc(&d_in, IN_CAP + (1 << 17))); ck(cudaMalloc(&d_out, OUT_CAP + (1 << 17)));
+    ck(cudaMalloc(&d_in, std::min<uint64_t>(IN_CAP, file_bytes) + (1 << 17))); ck(cudaMalloc(&d_out, std::min<uint64_t>(OUT_CAP, out_bytes) + (1 << 17)));
     ck(cudaMalloc(&d_mem, max_members * sizeof(bgz::Member))); ck(cudaMalloc(&d_st, max_members * sizeof(int32_t)));
     ck(cudaMalloc(&d_scr, (size_t)grid * bgz::CTA_THREADS * sizeof(bgz::Scratch)));
     uint64_t i = 0;

@@ -15,7 +15,7 @@
 // the caller checks each member's CRC32 on the host and re-inflates with zlib whatever failed, so a defect here costs time,
 // never correctness -- the same contract as the host's table-driven decoder (csrc/host/fast_inflate.hpp).
 //
-// Written from RFC 1951. Not measured on a B200 yet when this was committed.
+// Written from RFC 1951. First measurement: DESIGN.md section 8.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -53,16 +53,21 @@ struct Bits {
     uint32_t n, pos;
     uint64_t buf;
     int cnt;
+    uint32_t ahead;             // the aligned word at `pos`, loaded when the previous one was consumed (its latency hides behind
+    bool has_ahead;             // the decoding of the bits in between)
 };
 
 // at least 33 valid bits afterwards (bytes past the end read as zero; running past the end is detected when the member ends)
 BGZ_HD void refill(Bits& b) {
     while (b.cnt <= 32) {
         if (b.pos + 4 <= b.n && (((uintptr_t)(b.in + b.pos)) & 3) == 0) {
-            const uint32_t w = *(const uint32_t*)(b.in + b.pos);
+            const uint32_t w = b.has_ahead ? b.ahead : *(const uint32_t*)(b.in + b.pos);
             b.buf |= (uint64_t)w << b.cnt;
             b.cnt += 32; b.pos += 4;
+            b.has_ahead = b.pos + 4 <= b.n;
+            if (b.has_ahead) b.ahead = *(const uint32_t*)(b.in + b.pos);
         } else {
+            b.has_ahead = false;
             const uint64_t v = b.pos < b.n ? b.in[b.pos] : 0;
             b.buf |= v << b.cnt;
             b.cnt += 8; b.pos += 1;
@@ -134,7 +139,7 @@ BGZ_HD int decode(Bits& b, const uint16_t* lut, int lut_stride, int lut_bits, co
 // D_LUT entries for distance codes, entry i at lut[i * lut_stride].
 BGZ_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, Scratch& sc, uint16_t* lut, int lut_stride) {
     Bits b;
-    b.in = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0;
+    b.in = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0; b.ahead = 0; b.has_ahead = false;
     uint16_t* lut_ll = lut;
     uint16_t* lut_d = lut + (size_t)LL_LUT * lut_stride;
     uint32_t op = 0;
@@ -158,7 +163,7 @@ BGZ_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
             if (src > in_len || in_len - src < len) return ERR_INPUT;
             if (out_len - op < len) return ERR_OUTPUT;
             for (uint32_t i = 0; i < len; ++i) out[op + i] = in[src + i];
-            op += len; b.pos = src + len;
+            op += len; b.pos = src + len; b.has_ahead = false;
             continue;
         }
         if (type == 1) {                                             // fixed codes
@@ -222,10 +227,21 @@ BGZ_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
             if (dist > op) return ERR_DISTANCE;
             if (len > out_len - op) return ERR_OUTPUT;
             if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return ERR_INPUT;       // ran past the end of the input a while ago
+            // up to eight bytes are loaded before the first of them is stored (never more than `dist`, so no load needs a byte
+            // of the same group): the loads are independent and their latencies overlap, instead of one round trip per byte
             const uint8_t* src = out + op - dist;
             uint8_t* dst = out + op;
-            for (uint32_t i = 0; i < len; ++i) dst[i] = src[i];
             op += len;
+            const uint32_t group = dist < 8 ? dist : 8;
+            while (len) {
+                const uint32_t k = len < group ? len : group;
+                uint8_t v[8];
+#pragma unroll
+                for (uint32_t i = 0; i < 8; ++i) if (i < k) v[i] = src[i];
+#pragma unroll
+                for (uint32_t i = 0; i < 8; ++i) if (i < k) dst[i] = v[i];
+                src += k; dst += k; len -= k;
+            }
         }
     }
     if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return ERR_INPUT;
@@ -233,15 +249,15 @@ BGZ_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
 }
 
 #ifdef __CUDACC__
-// One thread per member, members dealt round-robin over the grid. Dynamic shared memory: CTA_THREADS * LUT_PER_THREAD * 2 bytes.
+// One thread per member. Consecutive members go to different CTAs (member m of a round to CTA m % grid, thread m / grid), so a
+// file with fewer members than thread slots still spreads over all SMs. Dynamic shared memory: CTA_THREADS * LUT_PER_THREAD * 2 bytes.
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 bgzf_inflate_kernel(const uint8_t* __restrict__ file, const Member* __restrict__ members, uint64_t n_members, uint8_t* __restrict__ out,
                     Scratch* __restrict__ scratch, int32_t* __restrict__ status) {
     extern __shared__ uint16_t bgz_lut[];
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-    Scratch& sc = scratch[tid];
-    for (uint64_t m = tid; m < n_members; m += nthreads) {
+    Scratch& sc = scratch[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x];
+    for (uint64_t m = (uint64_t)threadIdx.x * gridDim.x + blockIdx.x; m < n_members; m += nthreads) {
         const Member mb = members[m];
         status[m] = mb.out_len == 0 ? (int32_t)OK
                                     : inflate_member(file + mb.in_off, mb.in_len, out + mb.out_off, mb.out_len, sc, bgz_lut + threadIdx.x, (int)blockDim.x);

@@ -8,6 +8,7 @@ tail -15 gpurun_out/test_inflate_$TAG.log
 timeout 90 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k cli > gpurun_out/test_cli_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_cli_$TAG.log
 tail -3 gpurun_out/test_cli_$TAG.log
 nproc > gpurun_out/decode_$TAG.txt
-timeout 90 env BDK_DECODE_TRACE=1 python scripts/bam_decode_bench.py --pairs 1000000 --reps 3 >> gpurun_out/decode_$TAG.txt 2>&1
-timeout 60 env BDK_DECODE_TRACE=1 BDK_GPU_INFLATE=1 python scripts/bam_decode_bench.py --pairs 1000000 --reps 3 >> gpurun_out/decode_$TAG.txt 2>&1
+PAIRS=${2:-1000000}
+timeout 120 env BDK_DECODE_TRACE=1 python scripts/bam_decode_bench.py --pairs $PAIRS --reps 3 >> gpurun_out/decode_$TAG.txt 2>&1
+timeout 60 env BDK_DECODE_TRACE=1 BDK_GPU_INFLATE=1 python scripts/bam_decode_bench.py --pairs $PAIRS --reps 3 >> gpurun_out/decode_$TAG.txt 2>&1
 grep -v "record chain:" gpurun_out/decode_$TAG.txt | tail -12
