@@ -247,7 +247,8 @@ uint64_t bdk_comm_bytes(bdk_ctx* ctx);
 int bdk_poisson_logsf(bdk_ctx* ctx, const double* lambda, const int32_t* k, double* out, uint64_t n);
 
 /* BGZF members inflated on the GPU (csrc/bgzf_inflate.cuh; replaces the zlib calls under the reference's samtools reader,
- * vendor/samtools0.1.19/bgzf.c inflate_block, for whole files at once). `file` is the host image of the BGZF file, `members`
+ * `inflate_block` in bgzf.c of vendor/samtools-0.1.19.tar.gz, reached through `samread` in src/lib/io/BamReader.hpp:65,
+ * for whole files at once). `file` is the host image of the BGZF file, `members`
  * its DEFLATE streams (offsets into `file` and into `out`; out_len from the member's ISIZE footer), `out` a host buffer of
  * out_bytes. status[i] = 0 if member i decoded to exactly out_len bytes, else a positive error code: the caller checks the
  * members' CRC32 and re-inflates whatever failed. Needs no context; returns 0 or BDK_ERR_*. kernel_ms (may be NULL) receives
