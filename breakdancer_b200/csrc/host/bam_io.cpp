@@ -73,6 +73,7 @@ double now_s() {
 inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline int32_t rdi32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
+inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
 struct MappedFile {
     const uint8_t* data = 0;
@@ -97,7 +98,7 @@ struct MappedFile {
     }
 };
 
-struct Block { size_t in_off; uint32_t in_len; uint32_t out_len; size_t out_off; };
+struct Block { size_t in_off; uint32_t in_len; uint32_t out_len; size_t out_off; size_t file_off; };
 
 // The inflated file: a plain allocation that is NOT zero-filled (std::vector::resize would memset more than a gigabyte on one
 // thread before the workers start; here every page is first touched by the worker that inflates into it).
@@ -122,11 +123,10 @@ struct RawBuf {
 std::atomic<uint64_t> g_gpu_inflate_redone(0);    // members the GPU decoder refused or got wrong (then decoded on the host)
 std::atomic<uint64_t> g_inflate_fallbacks(0);     // blocks the fast decoder refused or got wrong (then decoded by zlib)
 
-// Inflate a whole BGZF file into `out` with `threads` workers.
-void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads, RawBuf& out) {
-    std::vector<Block> blocks;
-    size_t off = 0, total = 0;
-    while (off < f.size) {
+// BGZF members from file offset `off` on: up to the end of the file, or up to and including the member that starts at
+// `last_member_off`. Output offsets continue from `total`.
+void scan_members(const MappedFile& f, const std::string& path, size_t off, size_t last_member_off, std::vector<Block>& blocks, size_t& total) {
+    while (off < f.size && off <= last_member_off) {
         if (off + 18 > f.size) throw std::runtime_error(path + " is not a valid bam file");
         const uint8_t* h = f.data + off;
         if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) throw std::runtime_error(path + " is not a valid bam file");
@@ -142,6 +142,7 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
         size_t blen = (size_t)bsize + 1;
         if (off + blen > f.size || blen < 12 + xlen + 8) throw std::runtime_error(path + " is truncated");
         Block b;
+        b.file_off = off;
         b.in_off = off + 12 + xlen;
         b.in_len = (uint32_t)(blen - 12 - xlen - 8);
         b.out_len = rd32(f.data + off + blen - 4);
@@ -150,7 +151,12 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
         blocks.push_back(b);
         off += blen;
     }
-    out.resize(total);
+}
+
+// Inflate `blocks` into `out` (already sized; the blocks' out_off are offsets into it) with `threads` workers.
+void inflate_members(const MappedFile& f, const std::string& path, int threads, const std::vector<Block>& blocks, RawBuf& out) {
+    size_t total = 0;
+    for (auto const& b : blocks) total += b.out_len;
     std::atomic<bool> bad(false);
     // Every block goes through the table-driven decoder of fast_inflate.hpp first; its result is accepted only if the block's
     // CRC32 (BGZF footer, checked by carry-less multiplication) matches, otherwise zlib decodes the block. 1.4x zlib's inflate
@@ -211,6 +217,15 @@ void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads,
     if (bad) throw std::runtime_error(path + ": BGZF inflate failed");
 }
 
+// Inflate a whole BGZF file into `out`.
+void bgzf_inflate_all(const MappedFile& f, const std::string& path, int threads, RawBuf& out) {
+    std::vector<Block> blocks;
+    size_t total = 0;
+    scan_members(f, path, 0, (size_t)-1, blocks, total);
+    out.resize(total);
+    inflate_members(f, path, threads, blocks, out);
+}
+
 struct BamData {
     std::string path;
     RawBuf raw;                           // whole inflated file
@@ -219,9 +234,24 @@ struct BamData {
     std::vector<uint32_t> tid_lens;
     std::vector<uint64_t> rec_off;        // offset of each record's core (after block_size)
     size_t first_rec = 0;                 // offset of the first record's block_size field
+    size_t rec_end = 0;                   // where the records to look at end (raw.size(), or the end of the indexed range)
+    // Is the BAM header (text, reference names) complete in p[0 .. n)? (the index-driven reader inflates members until it is)
+    static bool header_complete(const uint8_t* p, size_t n) {
+        if (n < 12) return false;
+        size_t o = 8 + (size_t)rd32(p + 4);
+        if (o + 4 > n) return false;
+        const uint32_t n_ref = rd32(p + o); o += 4;
+        for (uint32_t i = 0; i < n_ref; ++i) {
+            if (o + 4 > n) return false;
+            o += 4 + (size_t)rd32(p + o) + 4;
+            if (o > n) return false;
+        }
+        return true;
+    }
     void parse_header() {
         const uint8_t* p = raw.data();
         size_t n = raw.size();
+        tid_names.clear(); tid_lens.clear();
         if (n < 12 || memcmp(p, "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a valid bam file");
         uint32_t l_text = rd32(p + 4);
         if (8 + (size_t)l_text + 4 > n) throw std::runtime_error(path + " is not a valid bam file");
@@ -236,12 +266,13 @@ struct BamData {
             tid_lens.push_back(rd32(p + o)); o += 4;
         }
         first_rec = o;
+        rec_end = n;
     }
 
     // Does a record that could be real start at o (its block_size field)? Only a guess: see find_records.
     bool plausible(size_t o) const {
         const uint8_t* p = raw.data();
-        const size_t n = raw.size();
+        const size_t n = rec_end;
         if (o + 36 > n) return false;
         const uint32_t bs = rd32(p + o);
         if (bs < 32 || bs > (1u << 26) || o + 4 + bs > n) return false;
@@ -262,7 +293,7 @@ struct BamData {
     // is exactly the serial chain whatever the guesses were.
     void find_records(int threads) {
         const uint8_t* p = raw.data();
-        const size_t n = raw.size();
+        const size_t n = rec_end;
         auto broken = [&]() { return std::runtime_error(path + ": truncated BAM record"); };
         size_t nseg = 1;
         if (threads > 1) nseg = std::min<size_t>((size_t)threads * 4, std::max<size_t>(1, (n - first_rec) >> 20));
@@ -596,6 +627,122 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
     });
 }
 
+// ---- -o with a .bai: only the members that hold the reference sequence's records are inflated -----------------------------
+// The reference reads `-o` regions through samtools' index (RegionLimitedBamReader.hpp:40-66: bam_index_load, bam_parse_region,
+// bam_iter_query); without this every per-chromosome process (the reference's way to use many cores, and our per-GPU shards of
+// a whole-genome bam) would inflate the whole file. Written from the SAM specification, section 5.2: per reference sequence a
+// list of bins, each a list of chunks (begin, end) of virtual offsets (file offset of a member << 16 | offset inside its
+// output). All records with this tid lie between the smallest chunk begin and the largest chunk end (the file is sorted);
+// whatever else the range holds is removed by the same overlap test as without an index.
+struct BaiRange { bool found = false, any = false; uint64_t beg = ~0ull, end = 0; };
+
+BaiRange bai_reference_range(const std::string& bam_path, int tid) {
+    BaiRange r;
+    std::vector<std::string> cand{bam_path + ".bai"};
+    if (bam_path.size() > 4 && bam_path.compare(bam_path.size() - 4, 4, ".bam") == 0) cand.push_back(bam_path.substr(0, bam_path.size() - 4) + ".bai");
+    std::vector<uint8_t> d;
+    for (auto const& c : cand) {
+        std::ifstream in(c, std::ios::binary);
+        if (!in) continue;
+        d.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+        break;
+    }
+    if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return r;
+    size_t o = 4;
+    auto need = [&](size_t k) { if (o + k > d.size()) throw std::runtime_error(bam_path + ": truncated bam index"); };
+    need(4);
+    const int32_t n_ref = rdi32(&d[o]); o += 4;
+    if (tid < 0 || tid >= n_ref) return r;
+    for (int t = 0; t <= tid; ++t) {
+        need(4);
+        const int32_t n_bin = rdi32(&d[o]); o += 4;
+        for (int32_t b = 0; b < n_bin; ++b) {
+            need(8);
+            const uint32_t bin = rd32(&d[o]);
+            const int32_t n_chunk = rdi32(&d[o + 4]); o += 8;
+            if (n_chunk < 0) throw std::runtime_error(bam_path + ": truncated bam index");
+            need(16 * (size_t)n_chunk);
+            if (t == tid && bin < 37450)                                  // 37450: samtools' pseudo-bin with counts, not chunks
+                for (int32_t c = 0; c < n_chunk; ++c) {
+                    r.beg = std::min(r.beg, rd64(&d[o + 16 * (size_t)c]));
+                    r.end = std::max(r.end, rd64(&d[o + 16 * (size_t)c + 8]));
+                    r.any = true;
+                }
+            o += 16 * (size_t)n_chunk;
+        }
+        need(4);
+        const int32_t n_intv = rdi32(&d[o]); o += 4;
+        if (n_intv < 0) throw std::runtime_error(bam_path + ": truncated bam index");
+        need(8 * (size_t)n_intv);
+        o += 8 * (size_t)n_intv;
+    }
+    r.found = true;
+    return r;
+}
+
+// Returns false when there is no index to use (the caller then reads the whole file).
+bool inflate_region_with_index(const MappedFile& mf, const std::string& path, const char* region, int threads, BamData& bd, Region& rg) {
+    {
+        std::ifstream probe(path + ".bai", std::ios::binary);
+        std::ifstream probe2(path.size() > 4 ? path.substr(0, path.size() - 4) + ".bai" : std::string(), std::ios::binary);
+        if (!probe && !probe2) return false;
+    }
+    // the header: members from the start of the file, one at a time, until it is complete
+    std::vector<Block> blocks;
+    size_t total = 0, off = 0;
+    std::vector<uint8_t> hraw;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error(path + ": BGZF inflate failed");
+    for (;;) {
+        const size_t before = blocks.size();
+        scan_members(mf, path, off, off, blocks, total);
+        if (blocks.size() == before) { inflateEnd(&zs); throw std::runtime_error(path + " is not a valid bam file"); }
+        Block const& b = blocks.back();
+        hraw.resize(total);
+        if (b.out_len) {
+            inflateReset(&zs);
+            zs.next_in = (Bytef*)(mf.data + b.in_off); zs.avail_in = b.in_len;
+            zs.next_out = hraw.data() + b.out_off; zs.avail_out = b.out_len;
+            if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.avail_out != 0) { inflateEnd(&zs); throw std::runtime_error(path + ": BGZF inflate failed"); }
+        }
+        off = b.in_off + b.in_len + 8;
+        if (hraw.size() >= 4 && memcmp(hraw.data(), "BAM\1", 4) != 0) { inflateEnd(&zs); throw std::runtime_error(path + " is not a valid bam file"); }
+        if (BamData::header_complete(hraw.data(), hraw.size())) break;
+    }
+    inflateEnd(&zs);
+    const size_t hdr_end_off = off;
+    bd.raw.resize(hraw.size());
+    if (!hraw.empty()) memcpy(bd.raw.data(), hraw.data(), hraw.size());
+    bd.parse_header();
+    rg = parse_region(region, bd.tid_names, path);
+    const BaiRange br = bai_reference_range(path, rg.tid);
+    if (!br.found) return false;
+    if (!br.any) {                                                        // no record of this reference sequence
+        bd.rec_end = bd.first_rec;
+        if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] %s: region %s through the index: no records, header members only\n", path.c_str(), region);
+        return true;
+    }
+    const uint64_t cb = br.beg >> 16, ub = br.beg & 0xffff, ce = br.end >> 16, ue = br.end & 0xffff;
+    auto mismatch = [&]() { return std::runtime_error(path + ": the bam index does not match the file"); };
+    if (br.beg > br.end || cb >= mf.size || ce > mf.size) throw mismatch();
+    if (ue > 0 || ce > 0) scan_members(mf, path, std::max<size_t>(cb, hdr_end_off), ue ? (size_t)ce : (size_t)ce - 1, blocks, total);
+    bd.raw.resize(total);
+    inflate_members(mf, path, threads, blocks, bd.raw);
+    bd.parse_header();
+    auto locate = [&](uint64_t coff, uint64_t uoff) -> size_t {
+        auto it = std::lower_bound(blocks.begin(), blocks.end(), coff, [](Block const& b, uint64_t c) { return b.file_off < c; });
+        if (it == blocks.end() || it->file_off != coff || uoff > it->out_len) throw mismatch();
+        return it->out_off + uoff;
+    };
+    bd.first_rec = std::max(bd.first_rec, locate(cb, ub));
+    bd.rec_end = ue ? locate(ce, ue) : total;
+    if (bd.first_rec > bd.rec_end) throw mismatch();
+    if (getenv("BDK_DECODE_TRACE"))
+        fprintf(stderr, "[decode] %s: region %s through the index: %zu of the file's members inflated (%.1f MB)\n", path.c_str(), region, blocks.size(), total / 1e6);
+    return true;
+}
+
 struct Head { int bam; uint64_t i; };
 
 }  // namespace
@@ -629,17 +776,20 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             BamData& bd = s->bams[b];
             bd.path = files[b];
             double t0 = now_s();
+            Region rg;
             {
                 MappedFile mf; mf.open(files[b]);
-                bgzf_inflate_all(mf, files[b], threads, bd.raw);
+                const bool ranged = region && region[0] && !getenv("BDK_NO_BAI") && inflate_region_with_index(mf, files[b], region, threads, bd, rg);
+                if (!ranged) {
+                    bgzf_inflate_all(mf, files[b], threads, bd.raw);
+                    bd.parse_header();
+                    if (region && region[0]) rg = parse_region(region, bd.tid_names, files[b]);
+                }
             }
             double t1 = now_s();
             const size_t raw_bytes = bd.raw.size();
-            bd.parse_header();
             bd.find_records(threads);
             double t1b = now_s();
-            Region rg;
-            if (region && region[0]) rg = parse_region(region, bd.tid_names, files[b]);
             extract_bam(bd, (int)b, rg, rgt, threads, cols[b]);
             double t2 = now_s();
             if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] %s: %.1f MB inflated in %.3f s, record chain %.3f s, extract %.3f s\n", files[b].c_str(), raw_bytes / 1e6, t1 - t0, t1b - t1, t2 - t1b);

@@ -224,3 +224,48 @@ def test_two_bam_merge_in_parallel_equals_the_heap_merge(tmp_path, monkeypatch):
             assert np.array_equal(got["heap"][k], got["parallel"][k]) if k != "names" else got["heap"][k] == got["parallel"][k], (names, k)
         p = got["heap"]["pos"]
         assert "u" in names or np.all(p[1:] >= p[:-1])
+
+
+def test_region_through_the_bam_index_equals_the_full_scan(tmp_path, monkeypatch, capfd):
+    """-o with a .bai next to the bam: only the members holding that reference sequence are inflated (RegionLimitedBamReader.hpp:40-66
+    reads through samtools' index); same records as the scan of the whole file. The index is written by the reference's own
+    vendored samtools (oracle/_ref, test infrastructure)."""
+    samtools = os.path.join(util.ROOT, "oracle", "_ref", "samtools")
+    if not os.path.exists(samtools):
+        pytest.skip("oracle/_ref/samtools not built")
+    import subprocess
+    genome = [("chrA", 400000), ("chrB", 300000), ("chrEmpty", 50000), ("chrC", 350000)]
+    w = synth.generate([g for g in genome if g[0] != "chrEmpty"], util.LIBS4, 60000, seed=17, anomaly_frac=0.05)
+    # the header names a sequence without any record between chrB and chrC
+    names = [g[0] for g in genome]
+    remap = np.array([0, 1, 3], dtype=np.int32)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for bam, cols in synth.split_by_bam(w).items():
+            cols = dict(cols)
+            cols["tid"] = remap[cols["tid"]]
+            cols["mtid"] = np.where(cols["mtid"] >= 0, remap[np.maximum(cols["mtid"], 0)], cols["mtid"]).astype(np.int32)
+            api.write_bam(bam, names, [g[1] for g in genome], w.rg_names, cols, level=6)
+            subprocess.check_call([samtools, "index", bam])
+            assert os.path.exists(bam + ".bai")
+        cfg = api.BamConfig(text=w.config_text())
+        monkeypatch.setenv("BDK_DECODE_TRACE", "1")
+        for region in ("chrA", "chrB", "chrC", "chrEmpty", "chrB:1000-90000", "chrC:200,000", "chrA:399000-400000"):
+            monkeypatch.setenv("BDK_NO_BAI", "1")
+            full = api.BamStream(cfg, region=region, threads=4, keep_records=True)
+            capfd.readouterr()
+            monkeypatch.delenv("BDK_NO_BAI")
+            idx = api.BamStream(cfg, region=region, threads=4, keep_records=True)
+            assert "through the index" in capfd.readouterr().err, region
+            assert idx.n == full.n, region
+            assert idx.n == 0 if region == "chrEmpty" else (idx.n > 0 or ":" in region)
+            for k in full.cols:
+                assert np.array_equal(full.cols[k], idx.cols[k]), (region, k)
+            for i in range(0, idx.n, 501):
+                assert idx.qname(i) == full.qname(i) and idx.fastq(i) == full.fastq(i)
+            full.close(); idx.close()
+        with pytest.raises(RuntimeError, match="Failed to parse bam region"):
+            api.BamStream(cfg, region="chrZ", threads=2)
+    finally:
+        os.chdir(cwd)
