@@ -169,6 +169,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdh_stream_tid_name": (C.c_char_p, [vp, C.c_int]),
         "bdh_stream_qname": (C.c_char_p, [vp, u64]),
         "bdh_stream_fastq": (C.c_int, [vp, u64, C.c_char_p, C.c_int]),
+        "bdh_bai_reference_stats": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_char_p, C.c_int]),
         "bdh_inflate_counters": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "bdh_stream_timings": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bdh_write_bam": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_int,
@@ -305,6 +306,53 @@ class BamStream:
 
     def __del__(self):
         self.close()
+
+
+def bam_reference_names(bam_path: str) -> List[str]:
+    """Reference sequence names of a bam's header; only the BGZF members that hold the header are read."""
+    import struct
+    import zlib
+    raw = b""
+    with open(bam_path, "rb") as f:
+        while True:
+            head = f.read(18)
+            if len(head) < 18 or head[:4] != b"\x1f\x8b\x08\x04":
+                raise RuntimeError(bam_path + " is not a valid bam file")
+            xlen, = struct.unpack_from("<H", head, 10)
+            bsize = struct.unpack_from("<H", head, 16)[0] + 1          # BC is the first extra field in every writer we know
+            body = f.read(bsize - 18)
+            raw += zlib.decompress(body[xlen - 6:len(body) - 8], -15)
+            if len(raw) >= 12:
+                if raw[:4] != b"BAM\x01":
+                    raise RuntimeError(bam_path + " is not a valid bam file")
+                o = 8 + struct.unpack_from("<I", raw, 4)[0]
+                if o + 4 <= len(raw):
+                    n_ref, = struct.unpack_from("<I", raw, o)
+                    o += 4
+                    names = []
+                    while len(names) < n_ref and o + 4 <= len(raw):
+                        l_name, = struct.unpack_from("<I", raw, o)
+                        if o + 4 + l_name + 4 > len(raw):
+                            break
+                        names.append(raw[o + 4:o + 4 + l_name - 1].decode())
+                        o += 4 + l_name + 4
+                    if len(names) == n_ref:
+                        return names
+
+
+def bai_reference_stats(bam_path: str):
+    """(records, bytes) per reference sequence from the bam's index, or None without one (include/bdk_host.h)."""
+    L = load_library()
+    err = C.create_string_buffer(512)
+    n = L.bdh_bai_reference_stats(bam_path.encode(), None, None, 0, err, 512)
+    if n == -1:
+        return None
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    rec = np.zeros(max(n, 1), dtype=np.int64)
+    byt = np.zeros(max(n, 1), dtype=np.int64)
+    L.bdh_bai_reference_stats(bam_path.encode(), rec.ctypes.data_as(C.POINTER(C.c_int64)), byt.ctypes.data_as(C.POINTER(C.c_int64)), n, err, 512)
+    return rec[:n], byt[:n]
 
 
 def inflate_counters():

@@ -680,6 +680,54 @@ BaiRange bai_reference_range(const std::string& bam_path, int tid) {
     return r;
 }
 
+// Per reference sequence: record counts from samtools' pseudo-bin 37450 (second chunk = mapped, unmapped) where the index has
+// it, and the compressed bytes its chunks span; what a planner needs to spread chromosomes over GPUs without decoding anything.
+// Returns the number of reference sequences in the index, or -1 without a usable index.
+int bai_reference_stats(const std::string& bam_path, std::vector<int64_t>& records, std::vector<int64_t>& bytes) {
+    std::vector<std::string> cand{bam_path + ".bai"};
+    if (bam_path.size() > 4 && bam_path.compare(bam_path.size() - 4, 4, ".bam") == 0) cand.push_back(bam_path.substr(0, bam_path.size() - 4) + ".bai");
+    std::vector<uint8_t> d;
+    for (auto const& c : cand) {
+        std::ifstream in(c, std::ios::binary);
+        if (!in) continue;
+        d.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+        break;
+    }
+    if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return -1;
+    size_t o = 4;
+    auto need = [&](size_t k) { if (o + k > d.size()) throw std::runtime_error(bam_path + ": truncated bam index"); };
+    need(4);
+    const int32_t n_ref = rdi32(&d[o]); o += 4;
+    if (n_ref < 0) return -1;
+    records.assign(n_ref, -1); bytes.assign(n_ref, 0);
+    for (int t = 0; t < n_ref; ++t) {
+        need(4);
+        const int32_t n_bin = rdi32(&d[o]); o += 4;
+        uint64_t lo = ~0ull, hi = 0;
+        for (int32_t b = 0; b < n_bin; ++b) {
+            need(8);
+            const uint32_t bin = rd32(&d[o]);
+            const int32_t n_chunk = rdi32(&d[o + 4]); o += 8;
+            if (n_chunk < 0) throw std::runtime_error(bam_path + ": truncated bam index");
+            need(16 * (size_t)n_chunk);
+            if (bin == 37450) {
+                if (n_chunk >= 2) records[t] = (int64_t)(rd64(&d[o + 16]) + rd64(&d[o + 24]));
+            } else {
+                for (int32_t c = 0; c < n_chunk; ++c) { lo = std::min(lo, rd64(&d[o + 16 * (size_t)c])); hi = std::max(hi, rd64(&d[o + 16 * (size_t)c + 8])); }
+            }
+            o += 16 * (size_t)n_chunk;
+        }
+        if (hi > 0 && lo != ~0ull) bytes[t] = (int64_t)((hi >> 16) - (lo >> 16)) + 1;
+        else if (records[t] < 0) records[t] = 0;
+        need(4);
+        const int32_t n_intv = rdi32(&d[o]); o += 4;
+        if (n_intv < 0) throw std::runtime_error(bam_path + ": truncated bam index");
+        need(8 * (size_t)n_intv);
+        o += 8 * (size_t)n_intv;
+    }
+    return n_ref;
+}
+
 // Returns false when there is no index to use (the caller then reads the whole file).
 bool inflate_region_with_index(const MappedFile& mf, const std::string& path, const char* region, int threads, BamData& bd, Region& rg) {
     {
@@ -934,6 +982,17 @@ const int32_t* bdh_stream_rg_bam(const bdh_stream* s) { return s->rg_bam.data();
 int bdh_stream_ntid(const bdh_stream* s) { return (int)s->tid_names.size(); }
 const char* bdh_stream_tid_name(const bdh_stream* s, int tid) {
     return tid >= 0 && tid < (int)s->tid_names.size() ? s->tid_names[tid].c_str() : "";
+}
+int bdh_bai_reference_stats(const char* bam_path, int64_t* records, int64_t* bytes, int cap, char* err, int errcap) {
+    try {
+        std::vector<int64_t> r, b;
+        const int n = bdh::bai_reference_stats(bam_path, r, b);
+        for (int i = 0; i < n && i < cap; ++i) { if (records) records[i] = r[i]; if (bytes) bytes[i] = b[i]; }
+        return n;
+    } catch (std::exception const& e) {
+        set_err2(err, errcap, e.what());
+        return -2;
+    }
 }
 void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone) {
     if (host_fallbacks) *host_fallbacks = bdh::g_inflate_fallbacks.load();

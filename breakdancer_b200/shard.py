@@ -61,6 +61,48 @@ def run_sharded(cols: Dict[str, np.ndarray], ntid: int, rank: int, world: int,
     return sorted(merged, key=lambda x: x[0])
 
 
+# ---- per-chromosome shards straight from indexed bam files ---------------------------------------------------------------
+def plan_from_index(bam_paths: Sequence[str], nranks: int):
+    """Chromosomes -> ranks from the bams' .bai files alone (no decoding): weights are the record counts the index holds
+    per reference sequence (samtools' pseudo-bin), or the compressed bytes the sequence's chunks span where an index has no
+    counts. Returns (weights, per-rank ascending tid lists), or None if a bam has no index."""
+    total = None
+    for path in bam_paths:
+        from . import api
+        st = api.bai_reference_stats(path)
+        if st is None:
+            return None
+        rec, byt = st
+        w = np.where(rec >= 0, rec, byt // 64)            # ~64 compressed bytes per record when only spans are known
+        total = w.copy() if total is None else total[:min(len(total), len(w))] + w[:min(len(total), len(w))]
+    return total, lpt_pack(total.tolist(), nranks)
+
+
+def run_sharded_bams(cfg, rank: int, world: int, run_chromosome: Callable[[int, str, object], object], gather: bool = True,
+                     threads: int = 0, pinned: bool = False):
+    """Like run_sharded, from the config's bam files: this rank opens only its chromosomes, each through the index (only that
+    sequence's BGZF members are inflated), and calls run_chromosome(tid, name, BamStream). Needs a .bai next to every bam."""
+    from . import api
+    plan = plan_from_index(cfg.bam_files, world)
+    if plan is None:
+        raise RuntimeError("per-chromosome shards need a .bai next to every bam file")
+    _, bins = plan
+    local = []
+    names = api.bam_reference_names(cfg.bam_files[0])      # BamMerger uses the first stream's header (BamMerger.cpp:78)
+    for t in bins[rank]:
+        st = api.BamStream(cfg, region=names[t], threads=threads, pinned=pinned)
+        local.append((t, run_chromosome(t, names[t], st)))
+        st.close()
+    if not gather or world == 1:
+        return sorted(local, key=lambda x: x[0]) if rank == 0 or not gather else None
+    import torch.distributed as dist
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(local, out, dst=0)
+    if rank != 0:
+        return None
+    return sorted([x for part in out for x in part], key=lambda x: x[0])
+
+
 # ---- one job over several GPUs (whole-genome / -t semantics, include/bdk.h "Multi-GPU") -----------------------------
 def stream_slices(n_records: int, world: int) -> List[slice]:
     """Contiguous, near-equal slices of the globally (tid, pos)-sorted record stream, one per rank in rank order.

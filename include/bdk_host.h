@@ -61,6 +61,12 @@ const char* bdh_stream_qname(const bdh_stream* s, uint64_t i);
 int bdh_stream_fastq(const bdh_stream* s, uint64_t i, char* buf, int cap);
 /* seconds spent in (inflate, parse+extract, merge) by the last open */
 void bdh_stream_timings(const bdh_stream* s, double* inflate_s, double* extract_s, double* merge_s);
+/* What `<bam>.bai` (or `<name>.bai`) says about every reference sequence, without touching the bam: records[t] = mapped + unmapped
+ * records placed on sequence t (samtools' pseudo-bin; -1 if the index has none), bytes[t] = compressed bytes its chunks span.
+ * Returns the number of sequences in the index (fills at most `cap`), -1 if there is no usable index, -2 on a damaged one
+ * (message in err). The planner of per-chromosome shards uses it (breakdancer_b200/shard.py); the reader itself uses the same
+ * index for -o regions (RegionLimitedBamReader.hpp:40-66 in the reference). */
+int bdh_bai_reference_stats(const char* bam_path, int64_t* records, int64_t* bytes, int cap, char* err, int errcap);
 /* Process-wide counters of the BGZF stage: members the host's table-driven decoder handed to zlib, and (BDK_GPU_INFLATE=1)
  * members the GPU decoder refused or got wrong and the host decoded again. */
 void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone);

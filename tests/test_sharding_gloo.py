@@ -97,3 +97,41 @@ def test_two_rank_stream_slices_and_communicator_id():
         assert p.exitcode == 0
     assert idlen == 128
     assert slices == [[0, 500, 500], [500, 1001, 501]]
+
+
+def test_plan_and_shards_from_indexed_bams(tmp_path):
+    """Per-chromosome shards straight from bam files: weights from the .bai alone, every rank decodes only its chromosomes
+    through the index; together the ranks see exactly the records of a whole-file decode, chromosome by chromosome."""
+    import subprocess
+    samtools = os.path.join(util.ROOT, "oracle", "_ref", "samtools")
+    if not os.path.exists(samtools):
+        pytest.skip("oracle/_ref/samtools not built")
+    w = synth.generate(util.GENOME3, util.LIBS4, 50000, seed=4, anomaly_frac=0.05)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        assert shard.plan_from_index(["missing.bam"], 2) is None
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(bam, [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=1)
+            subprocess.check_call([samtools, "index", bam])
+        cfg = api.BamConfig(text=w.config_text())
+        assert api.bam_reference_names(cfg.bam_files[0]) == [g[0] for g in w.genome]
+        whole = api.BamStream(cfg, threads=2)
+        true_counts = np.bincount(whole.cols["tid"], minlength=len(w.genome))
+        weights, bins = shard.plan_from_index(cfg.bam_files, 2)
+        assert weights.tolist() == true_counts.tolist()              # the synthetic bams hold primary, placed records only
+        assert bins == shard.lpt_pack(true_counts.tolist(), 2)
+        seen = {}
+        for rank in range(2):
+            def run(tid, name, st):
+                assert name == w.genome[tid][0]
+                return {k: v.copy() for k, v in st.cols.items()}
+            for tid, cols in shard.run_sharded_bams(cfg, rank, 2, run, gather=False):
+                seen[tid] = cols
+        assert sorted(seen) == [t for t in range(len(w.genome)) if true_counts[t]]
+        sl = shard.chromosome_slices(whole.cols, len(w.genome))
+        for tid, cols in seen.items():
+            for k in ("pos", "mpos", "tid", "mtid", "isize", "flag", "mapq", "qlen", "qid"):
+                assert np.array_equal(cols[k], whole.cols[k][sl[tid]]), (tid, k)
+    finally:
+        os.chdir(cwd)
