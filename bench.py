@@ -9,7 +9,9 @@ classify -> regions -> link graph -> scored SV table.  `value` is measured with 
 already resident in HBM (bdk_push_device); `e2e` is the same job through the C ABI with HOST (pinned)
 columns, so host->device copies and the device->host read of the SV table are inside the timed
 region.  `roofline` is the classify kernel (25 algorithmic bytes per record) against the measured HBM
-peak; `cpu_baseline` is the unmodified reference binary on the host cores on a bounded sample.
+peak; `cpu_baseline` is the unmodified reference binary on the host cores on a bounded sample;
+`bam_decode` (N = 1) is the host's BAM decode of a bounded sample on all host cores -- what bounds the
+drop-in executable on real files (no GPU work in it; reported next to e2e, not part of it).
 For N > 1 each rank runs its own chromosome-shaped shard (the path shards by chromosome with
 no data-path collective: weak scaling); torch.distributed/NCCL is used only for the barrier and the
 max-over-ranks of the device time.  One JSON line is printed by rank 0.  For N > 1 the line also carries
@@ -103,6 +105,39 @@ def cpu_baseline(pairs_total, nproc, seed0=20260101):
         return {"value": pairs / dt, "unit": UNIT, "cores": nproc if kind == "reference" else 1, "kind": kind,
                 "sample": f"{nproc} x {pairs // nproc} read pairs of the same workload as BAM, one single-threaded process each, {dt:.1f} s wall"}
     finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def bam_decode_sample(pairs, level=6):
+    """What bounds the drop-in executable on real input: the host's BAM decode (BGZF inflate, record boundaries, field extraction
+    into the columns the GPU reads), all host cores, on a bounded sample of the bench workload written as a BAM file. No GPU work
+    in here; the device side of a job of this size is microseconds. Reported next to e2e, not part of it."""
+    from breakdancer_b200 import api, synth
+    tmp = tempfile.mkdtemp(prefix="bdk_bam_", dir=os.environ.get("TMPDIR", "/tmp"))
+    cwd = os.getcwd()
+    try:
+        w = synth.config2(pairs, seed=20260105, chrom_len=max(1_000_000, 5 * pairs))
+        os.chdir(tmp)
+        size = 0
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(bam, [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=level)
+            size += os.path.getsize(bam)
+        cfg = api.BamConfig(text=w.config_text())
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            st = api.BamStream(cfg)
+            dt = time.perf_counter() - t0
+            stages, n = st.timings(), st.n
+            st.close()
+            if best is None or dt < best[0]:
+                best = (dt, stages, n)
+        dt, stages, n = best
+        return {"value": n / 2 / dt, "unit": UNIT, "records_per_s": n / dt, "cores": os.cpu_count() or 1, "bam_bytes": size,
+                "stages_s": {k: round(v, 4) for k, v in stages.items()}, "open_s": round(dt, 4),
+                "sample": f"{n // 2} read pairs of the same workload as one BAM (deflate level {level}), best of 3 decodes, host only"}
+    finally:
+        os.chdir(cwd)
         shutil.rmtree(tmp, ignore_errors=True)
 
 
@@ -396,6 +431,10 @@ def ours(args):
                 line["cpu_baseline"] = cpu_baseline(args.cpu_pairs, max(1, min(os.cpu_count() or 1, 32)))
             except Exception as ex:   # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+            try:
+                line["bam_decode"] = bam_decode_sample(args.bam_pairs)
+            except Exception as ex:   # reported, never required
+                line["bam_decode"] = {"value": None, "unit": UNIT, "sample": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -475,6 +514,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=6_000_000, help="total read pairs of the CPU baseline sample")
     ap.add_argument("--ref-pairs", type=int, default=400_000, help="read pairs per process and step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--bam-pairs", type=int, default=2_000_000, help="size of the BAM sample of the bam_decode leg")
     ap.add_argument("--no-genome", action="store_true", help="N > 1: skip the one-job-over-all-GPUs (NCCL exchange) measurements")
     args = ap.parse_args()
     if args.pairs is None:
