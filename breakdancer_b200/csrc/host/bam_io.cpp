@@ -13,6 +13,7 @@
 // straight into the columns the GPU consumes.
 #include "host.hpp"
 #include "fast_inflate.hpp"
+#include "../bam_records.h"
 
 #include <zlib.h>
 #include <fcntl.h>
@@ -270,20 +271,7 @@ struct BamData {
     }
 
     // Does a record that could be real start at o (its block_size field)? Only a guess: see find_records.
-    bool plausible(size_t o) const {
-        const uint8_t* p = raw.data();
-        const size_t n = rec_end;
-        if (o + 36 > n) return false;
-        const uint32_t bs = rd32(p + o);
-        if (bs < 32 || bs > (1u << 26) || o + 4 + bs > n) return false;
-        const uint8_t* r = p + o + 4;
-        const int32_t nref = (int32_t)tid_names.size();
-        const int32_t tid = rdi32(r), pos = rdi32(r + 4), lq = rdi32(r + 16), mtid = rdi32(r + 20), mpos = rdi32(r + 24);
-        const uint32_t l_qname = r[8], n_cigar = rd16(r + 12);
-        if (tid < -1 || tid >= nref || mtid < -1 || mtid >= nref || pos < -1 || mpos < -1 || lq < 0 || l_qname == 0) return false;
-        const uint64_t fixed = 32 + (uint64_t)l_qname + 4ull * n_cigar + ((uint64_t)lq + 1) / 2 + (uint64_t)lq;
-        return fixed <= bs && r[32 + l_qname - 1] == 0;
-    }
+    bool plausible(size_t o) const { return brec::plausible(raw.data(), rec_end, o, (int32_t)tid_names.size()); }
 
     // Record boundaries are a chain of block_size prefixes, serial by nature (0.2 s for 4 M records on one core: every step is a
     // cache miss). Here the buffer is cut into segments; every segment but the first GUESSES its first record (the first offset
@@ -362,74 +350,10 @@ struct BamData {
     }
 };
 
-// 32-byte BAM core (little-endian on disk)
-struct Core {
-    int32_t tid, pos; uint8_t l_qname, mapq; uint16_t bin; uint16_t n_cigar, flag; int32_t l_qseq, mtid, mpos, isize;
-};
-inline Core read_core(const uint8_t* r) {
-    Core c;
-    c.tid = rdi32(r); c.pos = rdi32(r + 4);
-    c.l_qname = r[8]; c.mapq = r[9]; c.bin = rd16(r + 10);
-    c.n_cigar = rd16(r + 12); c.flag = rd16(r + 14);
-    c.l_qseq = rdi32(r + 16); c.mtid = rdi32(r + 20); c.mpos = rdi32(r + 24); c.isize = rdi32(r + 28);
-    return c;
-}
-
-// samtools bam_calend: reference span from the CIGAR (ops M,D,N,=,X consume the reference)
-inline uint32_t calend(const Core& c, const uint8_t* cigar) {
-    uint32_t end = c.pos;
-    for (int k = 0; k < c.n_cigar; ++k) {
-        uint32_t v = rd32(cigar + 4 * k), op = v & 0xf;
-        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += v >> 4;
-    }
-    return end;
-}
-
-// Walk the aux area; return pointer to the value type byte of `tag` or null (bam_aux_get).
-const uint8_t* aux_get(const uint8_t* s, const uint8_t* e, const char tag[2]) {
-    while (s + 3 <= e) {
-        bool hit = s[0] == (uint8_t)tag[0] && s[1] == (uint8_t)tag[1];
-        const uint8_t* v = s + 2;
-        if (hit) return v;
-        uint8_t t = *v++;
-        switch (t) {
-            case 'A': case 'c': case 'C': v += 1; break;
-            case 's': case 'S': v += 2; break;
-            case 'i': case 'I': case 'f': v += 4; break;
-            case 'd': v += 8; break;
-            case 'Z': case 'H': while (v < e && *v) ++v; ++v; break;
-            case 'B': {
-                if (v + 5 > e) return 0;
-                uint8_t st = *v; uint32_t cnt = rd32(v + 1); v += 5;
-                size_t sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-                v += sz * cnt; break;
-            }
-            default: return 0;
-        }
-        s = v;
-    }
-    return 0;
-}
-
-inline int32_t aux2i(const uint8_t* v) {  // bam_aux2i
-    switch (*v) {
-        case 'c': return (int8_t)v[1];
-        case 'C': return v[1];
-        case 's': return (int16_t)rd16(v + 1);
-        case 'S': return rd16(v + 1);
-        case 'i': case 'I': return rdi32(v + 1);
-        default: return 0;
-    }
-}
-
-inline uint64_t hash_name(const uint8_t* s, size_t n) {  // 64-bit name key (wyhash-style multiply-mix)
-    auto mix = [](uint64_t a, uint64_t b) { __uint128_t r = (__uint128_t)a * b; return (uint64_t)r ^ (uint64_t)(r >> 64); };
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xA0761D6478BD642Full);
-    while (n >= 8) { uint64_t w; memcpy(&w, s, 8); h = mix(h ^ w, 0xE7037ED1A0B428DBull); s += 8; n -= 8; }
-    uint64_t w = 0; memcpy(&w, s, n);
-    h = mix(h ^ w ^ ((uint64_t)n << 56), 0x8EBC6AF09C88C6E3ull);
-    return mix(h, 0x589965CC75374CC3ull);
-}
+using brec::Core;
+using brec::read_core;
+using brec::aux2i;
+inline const uint8_t* aux_get(const uint8_t* s, const uint8_t* e, const char tag[2]) { return brec::aux_get(s, e, tag[0], tag[1]); }
 
 struct Region { bool on = false; int tid = -1; int beg = 0, end = 1 << 29; };
 
@@ -560,6 +484,7 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
     const uint8_t* raw = bd.raw.data();
     // pass 1: filter flags (primary && tid >= 0 [&& region overlap]) -> keep mask + prefix
     std::vector<uint8_t> keep(nrec);
+    const brec::RegionSel sel{region.on ? 1 : 0, region.tid, region.beg, region.end};
     const uint64_t G = 1 << 16;
     size_t ng = (nrec + G - 1) / G;
     std::vector<uint64_t> goff(ng + 1, 0);
@@ -567,14 +492,7 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
       for (uint64_t g = g0; g < g1; ++g) {
         uint64_t kept = 0;
         for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) {
-            const uint8_t* r = raw + bd.rec_off[i];
-            Core c = read_core(r);
-            bool ok = !(c.flag & (0x100 | 0x800)) && c.tid >= 0;
-            if (ok && region.on) {
-                // bam_iter_read's is_overlap(): rend > beg && pos < end within the target
-                uint32_t rend = c.n_cigar ? calend(c, r + 32 + c.l_qname) : (uint32_t)c.pos + 1;
-                ok = c.tid == region.tid && rend > (uint32_t)region.beg && c.pos < region.end;
-            }
+            const bool ok = brec::keep_record(raw + bd.rec_off[i], sel);
             keep[i] = ok;
             kept += ok;
         }
@@ -591,28 +509,13 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
             uint64_t o = goff[g];
             for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) {
                 if (!keep[i]) continue;
-                const uint8_t* r = raw + bd.rec_off[i];
-                uint32_t bs = rd32(r - 4);
-                Core c = read_core(r);
-                const uint8_t* name = r + 32;
-                const uint8_t* aux = name + c.l_qname + 4 * (size_t)c.n_cigar + ((size_t)c.l_qseq + 1) / 2 + (size_t)c.l_qseq;
-                const uint8_t* end = r + bs;
-                out.pos[o] = c.pos; out.mpos[o] = c.mpos; out.tid[o] = c.tid; out.mtid[o] = c.mtid;
-                out.isize[o] = c.isize; out.qlen[o] = c.l_qseq; out.flag[o] = c.flag;
-                uint8_t q = c.mapq;
-                if (aux <= end) {
-                    if (const uint8_t* am = aux_get(aux, end, "AM")) q = (uint8_t)aux2i(am);  // determine_bdqual
-                }
-                out.mapq[o] = q;
-                size_t nl = c.l_qname ? strnlen((const char*)name, c.l_qname) : 0;
-                out.qid[o] = hash_name(name, nl);
+                const brec::Fields f = brec::record_fields(raw + bd.rec_off[i]);
+                out.pos[o] = f.pos; out.mpos[o] = f.mpos; out.tid[o] = f.tid; out.mtid[o] = f.mtid;
+                out.isize[o] = f.isize; out.qlen[o] = f.qlen; out.flag[o] = f.flag;
+                out.mapq[o] = f.mapq;
+                out.qid[o] = f.qid;
                 if (out.want_rec) out.rec[o] = bd.rec_off[i];
-                const char* rgs = ""; size_t rgl = 0;
-                if (aux <= end) {
-                    if (const uint8_t* rg = aux_get(aux, end, "RG")) {
-                        if (*rg == 'Z' || *rg == 'H') { rgs = (const char*)rg + 1; rgl = strnlen(rgs, end - (rg + 1)); }
-                    }
-                }
+                const char* rgs = f.rg ? (const char*)f.rg : ""; const size_t rgl = f.rg_len;
                 if (!have_last || last_rg.size() != rgl || memcmp(last_rg.data(), rgs, rgl) != 0) {
                     last_rg.assign(rgs, rgl);
                     auto it = seen.find(last_rg);
