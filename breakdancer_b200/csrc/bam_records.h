@@ -124,6 +124,50 @@ BREC_HD bool plausible(const uint8_t* raw, size_t n, size_t o, int32_t nref) {
     return fixed <= bs && r[32 + l_qname - 1] == 0;
 }
 
+// ---- record boundaries by segments (the device form of bam_io.cpp find_records) ----------------------------------------------
+constexpr uint64_t NO_GUESS = ~0ull;
+struct Segment {
+    uint64_t guess;      // offset of the block_size field of the first record that starts in the segment (NO_GUESS: none found)
+    uint64_t end;        // where the chain from `guess` leaves the segment (offset of the first record starting at or after its end)
+    uint32_t count;      // records that start in the segment
+    uint32_t bad;        // the chain ran into a record that cannot be (block_size < 32 or past the end of the data)
+};
+
+// Segment [lo, hi) of raw[0 .. n): guess its first record (the first segment starts on one: `first`), follow the chain.
+BREC_HD Segment segment_guess(const uint8_t* raw, uint64_t n, uint64_t lo, uint64_t hi, bool first, int32_t nref) {
+    Segment s;
+    s.guess = NO_GUESS; s.end = hi; s.count = 0; s.bad = 0;
+    uint64_t o = lo;
+    if (!first) {
+        for (; o < hi; ++o) {
+            uint64_t q = o;
+            int depth = 0;
+            while (depth < 3 && plausible(raw, n, q, nref)) { q += 4 + (uint64_t)ld32(raw + q); ++depth; }
+            if (depth == 3 || (depth > 0 && q + 4 > n)) break;
+        }
+        if (o >= hi) return s;
+    }
+    s.guess = o;
+    while (o + 4 <= n && o < hi) {
+        const uint32_t bs = ld32(raw + o);
+        if (bs < 32 || o + 4 + bs > n) { s.bad = 1; break; }
+        ++s.count;
+        o += 4 + (uint64_t)bs;
+    }
+    s.end = o;
+    return s;
+}
+
+// Is segment k's part of the picture right? Every guess present, no broken record, every chain ending exactly on the next
+// segment's guess, the last one with the data (fewer than 4 stray bytes are ignored, as on the host). If this holds for all k,
+// the guessed chains ARE the serial chain (induction from the first segment, which starts on a true record); if it fails
+// anywhere the file goes to the host decoder.
+BREC_HD bool segment_consistent(const Segment* seg, uint32_t k, uint32_t nseg, uint64_t n) {
+    if (seg[k].guess == NO_GUESS || seg[k].bad) return false;
+    if (k + 1 < nseg) return seg[k + 1].guess == seg[k].end;
+    return seg[k].end + 4 > n;
+}
+
 struct RegionSel { int on, tid, beg, end; };
 
 // The reader's filter: primary records placed on a reference sequence (BamIo.cpp:11-18) and, with -o, bam_iter_read's

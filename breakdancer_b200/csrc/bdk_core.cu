@@ -18,6 +18,7 @@
 #include "../../include/bdk.h"
 #include "bdk_finalize.h"
 #include "bgzf_inflate.cuh"
+#include "bam_decode.cuh"
 #include "comm.cuh"
 #include "k1_classify.cuh"
 #include "k234_regions_links_sv.cuh"

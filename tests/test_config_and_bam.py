@@ -135,13 +135,12 @@ def _handmade_bam(records) -> bytes:
     return _bgzf(head + b"".join(records))
 
 
-def test_record_chain_segments_with_decoys(tmp_path, monkeypatch):
-    """Records whose aux bytes hold perfectly formed records (decoys): the parallel search for record boundaries must still
-    return the serial chain, however the buffer is cut (csrc/host/bam_io.cpp find_records)."""
-    rng = np.random.default_rng(5)
+def _decoy_records(seed=5, n=3000):
+    """Records whose aux bytes hold perfectly formed records: (records, their positions)."""
+    rng = np.random.default_rng(seed)
     recs, want_pos = [], []
     pos = 100
-    for i in range(3000):
+    for i in range(n):
         pos += int(rng.integers(1, 50))
         aux = b"RGZg\0"
         kind = i % 4
@@ -160,6 +159,13 @@ def test_record_chain_segments_with_decoys(tmp_path, monkeypatch):
             aux += b"XDBC" + np.uint32(len(big) + len(rest)).tobytes() + bytes(big) + rest
         recs.append(_bam_record(0, pos, "r%d" % i, 99 if i % 2 == 0 else 147, 36, 0, pos + 200, 236, aux))
         want_pos.append(pos)
+    return recs, want_pos
+
+
+def test_record_chain_segments_with_decoys(tmp_path, monkeypatch):
+    """Records whose aux bytes hold perfectly formed records (decoys): the parallel search for record boundaries must still
+    return the serial chain, however the buffer is cut (csrc/host/bam_io.cpp find_records)."""
+    recs, want_pos = _decoy_records()
     (tmp_path / "h.bam").write_bytes(_handmade_bam(recs))
     cfg = api.BamConfig(text="map:%s\tlib:L\tmean:300\tstd:30\treadlen:36\n" % (tmp_path / "h.bam"))
     results = []
@@ -269,3 +275,28 @@ def test_region_through_the_bam_index_equals_the_full_scan(tmp_path, monkeypatch
             api.BamStream(cfg, region="chrZ", threads=2)
     finally:
         os.chdir(cwd)
+
+
+def test_segment_form_of_the_record_chain_is_exact_or_refuses(tmp_path):
+    """csrc/bam_records.h segment_guess / segment_consistent (the bodies of the kernels in csrc/bam_decode.cuh), on the host:
+    consistent segments reproduce the serial chain; with decoy records the check refuses instead of returning another chain."""
+    import subprocess
+    src = os.path.join(util.ROOT, "tests", "hostsim", "bam_chain_host.cpp")
+    exe = os.path.join(util.ROOT, "tests", "_build", "bam_chain_host")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", src, "-o", exe, "-lz"])
+    w = synth.generate(util.GENOME3, util.LIBS4, 30000, seed=12, anomaly_frac=0.05)
+    for bam, cols in synth.split_by_bam(w).items():
+        api.write_bam(str(tmp_path / bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols)
+    normal = [str(tmp_path / b) for b in synth.split_by_bam(w)] + [os.path.join(util.CHR21, "NA19238_chr21_del_inv.bam")]
+    for path in normal:
+        p = subprocess.run([exe, path], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout
+        lines = p.stdout.strip().split("\n")
+        assert len(lines) == 4 and all("consistent=1 equal=1" in l for l in lines), p.stdout
+    recs, _ = _decoy_records()
+    (tmp_path / "decoy.bam").write_bytes(_handmade_bam(recs))
+    p = subprocess.run([exe, str(tmp_path / "decoy.bam")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout                                   # never consistent with another chain
+    assert "consistent=0" in p.stdout, p.stdout                          # and the decoys do derail some segment size
