@@ -902,7 +902,9 @@ void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone) {
     if (gpu_redone) *gpu_redone = bdh::g_gpu_inflate_redone.load();
 }
 void bdh_stream_timings(const bdh_stream* s, double* a, double* b, double* c) {
-    if (a) *a = s->t_inflate; if (b) *b = s->t_extract; if (c) *c = s->t_merge;
+    if (a) *a = s->t_inflate;
+    if (b) *b = s->t_extract;
+    if (c) *c = s->t_merge;
 }
 
 const char* bdh_stream_qname(const bdh_stream* s, uint64_t i) {
