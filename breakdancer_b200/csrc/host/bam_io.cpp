@@ -279,7 +279,9 @@ struct BamData {
     // then checked, in order: the chain that really arrives in a segment must land on an offset the segment's own chain visited;
     // until it does it is followed one record at a time (and it is the only chain allowed to report a broken file). The result
     // is exactly the serial chain whatever the guesses were.
-    void find_records(int threads) {
+    // partial_ok (windowed decode): the data may end inside a record; *tail = where that record starts (or rec_end, or the
+    // offset of fewer than 4 stray bytes) and the bytes from there on are carried into the next window.
+    void find_records(int threads, bool partial_ok = false, size_t* tail = nullptr) {
         const uint8_t* p = raw.data();
         const size_t n = rec_end;
         auto broken = [&]() { return std::runtime_error(path + ": truncated BAM record"); };
@@ -313,24 +315,33 @@ struct BamData {
             }
         });
         size_t cur = first_rec;
+        bool done = false;                                                           // partial_ok: the chain reached the cut-off record
         for (size_t k = 0; k < nseg; ++k) {
             Seg& sg = segs[k];
+            if (done) { sg.from = sg.own.size(); continue; }
             size_t j = 0;
             bool joined = false;
             while (cur + 4 <= n && cur < cut[k + 1]) {
                 while (j < sg.own.size() && sg.own[j] - 4 < cur) ++j;
                 if (j < sg.own.size() && sg.own[j] - 4 == cur) { joined = true; break; }
                 const uint32_t bs = rd32(p + cur);
-                if (bs < 32 || cur + 4 + bs > n) throw broken();
+                if (bs < 32 || cur + 4 + bs > n) {
+                    if (partial_ok && bs >= 32) { done = true; break; }
+                    throw broken();
+                }
                 sg.extra.push_back(cur + 4);
                 cur += 4 + (size_t)bs;
             }
             if (joined) {
                 sg.from = j;
                 cur = sg.end;
-                if (cur + 4 <= n && cur < cut[k + 1]) throw broken();                // the segment's chain stopped on a bad record
+                if (cur + 4 <= n && cur < cut[k + 1]) {                              // the segment's chain stopped on a record that cannot be
+                    if (partial_ok && rd32(p + cur) >= 32) done = true;              // ... or that the window cuts off
+                    else throw broken();
+                }
             } else sg.from = sg.own.size();
         }
+        if (tail) *tail = cur;
         if (getenv("BDK_DECODE_TRACE")) {
             size_t wrong = 0, walked = 0;
             for (auto const& sg : segs) { wrong += sg.from > 0 && sg.from <= sg.own.size() && !sg.own.empty(); walked += sg.extra.size(); }
@@ -408,6 +419,12 @@ template <class T> struct ColBuf {
     ColBuf(ColBuf&& o) noexcept : p(o.p), n(o.n), pinned(o.pinned) { o.p = nullptr; o.n = 0; }
     ~ColBuf() { col_free(p, pinned); }
     void resize(size_t m) { col_free(p, pinned); p = nullptr; n = 0; p = (T*)col_alloc(m * sizeof(T), pinned); n = m; }
+    void grow(size_t m) {                                   // keeps the first min(n, m) elements (windowed decode appends)
+        T* q = (T*)col_alloc(m * sizeof(T), pinned);
+        if (p && n) memcpy(q, p, std::min(n, m) * sizeof(T));
+        col_free(p, pinned);
+        p = q; n = m;
+    }
     T* take() { T* q = p; p = nullptr; n = 0; return q; }
     size_t size() const { return n; }
     bool empty() const { return n == 0; }
@@ -422,10 +439,23 @@ struct Columns {
     ColBuf<uint64_t> qid, rec;  // rec = offset of the raw record in its BamData
     bool want_rec = true;
     void set_pinned(int on) { pos.pinned = mpos.pinned = tid.pinned = mtid.pinned = isize.pinned = qlen.pinned = flag.pinned = rgid.pinned = mapq.pinned = qid.pinned = on; }
+    size_t cap = 0;             // allocated elements (windowed decode grows geometrically); size() of the members is the used count
     void resize(size_t n) {
         pos.resize(n); mpos.resize(n); tid.resize(n); mtid.resize(n); isize.resize(n); qlen.resize(n);
         flag.resize(n); rgid.resize(n); mapq.resize(n); qid.resize(n);
         if (want_rec) rec.resize(n);
+        cap = n;
+    }
+    void append_room(size_t used, size_t more) {            // afterwards every column holds used + more elements, the first `used` kept
+        const size_t need = used + more;
+        if (need > cap) {
+            cap = std::max(need, cap + cap / 2);
+            pos.grow(cap); mpos.grow(cap); tid.grow(cap); mtid.grow(cap); isize.grow(cap); qlen.grow(cap);
+            flag.grow(cap); rgid.grow(cap); mapq.grow(cap); qid.grow(cap);
+            if (want_rec) rec.grow(cap);
+        }
+        pos.n = mpos.n = tid.n = mtid.n = isize.n = qlen.n = flag.n = rgid.n = mapq.n = qid.n = need;
+        if (want_rec) rec.n = need;
     }
 };
 
@@ -479,7 +509,8 @@ struct bdh_stream {
 namespace bdh {
 namespace {
 
-void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, int threads, Columns& out) {
+// append = false: `out` receives exactly this file's kept records; append = true (windowed decode): they go behind what it holds.
+void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, int threads, Columns& out, bool append = false) {
     size_t nrec = bd.rec_off.size();
     const uint8_t* raw = bd.raw.data();
     // pass 1: filter flags (primary && tid >= 0 [&& region overlap]) -> keep mask + prefix
@@ -500,7 +531,11 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
       }
     });
     for (size_t g = 0; g < ng; ++g) goff[g + 1] += goff[g];
-    out.resize(goff[ng]);
+    if (append) {
+        const size_t used = out.pos.size();
+        out.append_room(used, goff[ng]);
+        for (size_t g = 0; g <= ng; ++g) goff[g] += used;
+    } else out.resize(goff[ng]);
     // pass 2: field extraction
     parallel_for(ng, 1, threads, [&](uint64_t g0, uint64_t g1) {
         std::string last_rg; int last_id = -1; bool have_last = false;
@@ -694,6 +729,50 @@ bool inflate_region_with_index(const MappedFile& mf, const std::string& path, co
     return true;
 }
 
+// ---- decode in windows: files whose inflated bytes do not fit in memory -------------------------------------------------------
+// The whole-file path holds all inflated bytes at once (3-4x the file: a 30x genome is some 400 GB). Here the members are
+// taken a window at a time: inflate, find the records (the window starts on a record; where it ends inside one, those bytes are
+// carried into the next window), extract behind what the columns already hold, drop the window. Same records, same order.
+void decode_bam_windowed(const MappedFile& mf, const std::string& path, const char* region, int threads, size_t window_bytes,
+                         BamData& bd, int bam_idx, RgTable& rgt, Columns& out, Region& rg) {
+    std::vector<Block> blocks;
+    size_t total = 0;
+    scan_members(mf, path, 0, (size_t)-1, blocks, total);
+    std::vector<uint8_t> carry;
+    size_t m = 0, windows = 0;
+    bool first = true;
+    while (first || m < blocks.size()) {
+        size_t j = m, bytes = 0;
+        while (j < blocks.size() && (j == m || bytes + blocks[j].out_len <= window_bytes)) bytes += blocks[j++].out_len;
+        std::vector<Block> wb(blocks.begin() + m, blocks.begin() + j);
+        for (auto& b : wb) b.out_off = carry.size() + (b.out_off - blocks[m].out_off);
+        BamData wd;
+        wd.path = path;
+        wd.raw.resize(carry.size() + bytes);
+        if (!carry.empty()) memcpy(wd.raw.data(), carry.data(), carry.size());
+        inflate_members(mf, path, threads, wb, wd.raw);
+        const bool last = j == blocks.size();
+        if (first) {
+            if (!BamData::header_complete(wd.raw.data(), wd.raw.size()) && !last) { window_bytes *= 2; continue; }     // a header larger than the window
+            wd.parse_header();
+            bd.text = wd.text; bd.tid_names = wd.tid_names; bd.tid_lens = wd.tid_lens;
+            if (region && region[0]) rg = parse_region(region, bd.tid_names, path);
+        } else {
+            wd.tid_names = bd.tid_names;
+            wd.first_rec = 0;
+            wd.rec_end = wd.raw.size();
+        }
+        size_t tail = wd.rec_end;
+        wd.find_records(threads, !last, &tail);
+        extract_bam(wd, bam_idx, rg, rgt, threads, out, true);
+        carry.assign(wd.raw.data() + tail, wd.raw.data() + wd.rec_end);
+        m = j;
+        first = false;
+        ++windows;
+    }
+    if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] %s: %.1f MB inflated in %zu windows\n", path.c_str(), total / 1e6, windows);
+}
+
 struct Head { int bam; uint64_t i; };
 
 }  // namespace
@@ -722,7 +801,18 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
         s->bams.resize(files.size());
         RgTable rgt; rgt.cfg = &cfg;
         std::vector<Columns> cols(files.size());
-        for (auto& c : cols) { c.want_rec = keep_records != 0; if (files.size() == 1) c.set_pinned(pinned); }
+        // Windowed decode (BDK_DECODE_WINDOW_MB, or by itself when the inflated file would take more than a third of the
+        // machine's memory) unless the records themselves are kept for the FASTQ dump.
+        bool windowed_any = false;
+        auto window_for = [&](size_t file_bytes) -> size_t {
+            if (keep_records) return 0;
+            if (const char* e = getenv("BDK_DECODE_WINDOW_MB")) return atoll(e) > 0 ? (size_t)atoll(e) << 20 : 0;
+            if (const char* e = getenv("BDK_DECODE_WINDOW_KB")) return atoll(e) > 0 ? (size_t)atoll(e) << 10 : 0;      // tests: a member per window
+            const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGESIZE);
+            if (pages > 0 && psz > 0 && (double)file_bytes * 4.0 > (double)pages * (double)psz / 3.0) return (size_t)4 << 30;
+            return 0;
+        };
+        for (auto& c : cols) c.want_rec = keep_records != 0;
         for (size_t b = 0; b < files.size(); ++b) {
             BamData& bd = s->bams[b];
             bd.path = files[b];
@@ -731,6 +821,15 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             {
                 MappedFile mf; mf.open(files[b]);
                 const bool ranged = region && region[0] && !getenv("BDK_NO_BAI") && inflate_region_with_index(mf, files[b], region, threads, bd, rg);
+                const size_t window = ranged ? 0 : window_for(mf.size);
+                if (window) {
+                    windowed_any = true;
+                    decode_bam_windowed(mf, files[b], region, threads, window, bd, (int)b, rgt, cols[b], rg);
+                    s->t_inflate += now_s() - t0;
+                    if (rgt.rg_lib.size() > 65536) throw std::runtime_error("more than 65536 (bam, read group) combinations");
+                    continue;
+                }
+                if (files.size() == 1) cols[b].set_pinned(pinned);
                 if (!ranged) {
                     bgzf_inflate_all(mf, files[b], threads, bd.raw);
                     bd.parse_header();
@@ -754,7 +853,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
         for (auto& c : cols) n += c.pos.size();
         s->n = n;
         double t3 = now_s();
-        if (files.size() == 1) {
+        if (files.size() == 1 && !windowed_any) {
             // nothing to merge: the extraction wrote the final arrays
             Columns& c = cols[0];
             s->pos = c.pos.take(); s->mpos = c.mpos.take(); s->tid = c.tid.take(); s->mtid = c.mtid.take(); s->isize = c.isize.take();
@@ -776,7 +875,9 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             s->mapq[o] = c.mapq[i]; s->qid[o] = c.qid[i];
             if (keep_records) { s->rec_bam[o] = (uint8_t)b; s->rec_off[o] = c.rec[i]; }
         };
-        {
+        if (files.size() == 1) {                             // one bam decoded in windows: a plain copy into the final arrays
+            parallel_for(n, 1 << 18, threads, [&](uint64_t a, uint64_t e) { for (uint64_t i = a; i < e; ++i) put(i, 0, i); });
+        } else {
             // Same container, comparator outcomes and push/pop sequence as the reference's BamMerger, so ties between bams
             // resolve the same way. Only the ORDER is decided serially, on one packed key per
             // record ((tid, pos, strand) lexicographic, the reference's comparison); the columns are moved afterwards by all

@@ -300,3 +300,57 @@ def test_segment_form_of_the_record_chain_is_exact_or_refuses(tmp_path):
     p = subprocess.run([exe, str(tmp_path / "decoy.bam")], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout                                   # never consistent with another chain
     assert "consistent=0" in p.stdout, p.stdout                          # and the decoys do derail some segment size
+
+
+def test_windowed_decode_equals_the_whole_file_decode(tmp_path, monkeypatch):
+    """Files too large to hold inflated are decoded a window of BGZF members at a time (records cut by a window's end are carried
+    over): same columns as the whole-file path, for one and two bams, with decoys, with -o without an index, and the same
+    refusal of a truncated file."""
+    w = synth.generate(util.GENOME3, util.LIBS4, 40000, seed=31, anomaly_frac=0.05)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(bam, [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=1)
+        recs, want_pos = _decoy_records(n=2000)
+        open("decoy.bam", "wb").write(_handmade_bam(recs))
+        raw = b"".join(recs)
+        import struct
+        text = b"@SQ\tSN:c1\tLN:100000000\n"
+        head = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1) + struct.pack("<I", 3) + b"c1\0" + struct.pack("<I", 100000000)
+        open("cut.bam", "wb").write(_bgzf(head + raw[:len(raw) - 23]))
+        cfg2 = api.BamConfig(text=w.config_text())
+        one = sorted(synth.split_by_bam(w))[0]
+        cases = [(cfg2, None, ""), (cfg2, [one], ""), (cfg2, None, w.genome[1][0]), (cfg2, None, w.genome[2][0] + ":1000-200000"),
+                 (api.BamConfig(text="map:decoy.bam\tlib:L\tmean:300\tstd:30\treadlen:36\n"), None, "")]
+        monkeypatch.setenv("BDK_NO_BAI", "1")
+        for cfg, paths, region in cases:
+            monkeypatch.delenv("BDK_DECODE_WINDOW_KB", raising=False)
+            monkeypatch.delenv("BDK_CHAIN_SEGMENTS", raising=False)
+            whole = api.BamStream(cfg, paths=paths, region=region, threads=4)
+            want = {k: v.copy() for k, v in whole.cols.items()}
+            want_lib = whole.rg_lib[whole.cols["rgid"]]
+            names = whole.tid_names
+            whole.close()
+            assert len(want["pos"]) > 0
+            for kb, nseg in ((1, None), (200, None), (1, 5), (1500, 3)):
+                monkeypatch.setenv("BDK_DECODE_WINDOW_KB", str(kb))
+                if nseg:
+                    monkeypatch.setenv("BDK_CHAIN_SEGMENTS", str(nseg))
+                else:
+                    monkeypatch.delenv("BDK_CHAIN_SEGMENTS", raising=False)
+                st = api.BamStream(cfg, paths=paths, region=region, threads=4)
+                assert st.tid_names == names
+                for k, v in want.items():
+                    if k == "rgid":           # ids are handed out in order of first sight, which depends on the threads
+                        continue
+                    assert np.array_equal(v, st.cols[k]), (region, kb, nseg, k)
+                assert np.array_equal(want_lib, st.rg_lib[st.cols["rgid"]])
+                st.close()
+        cfg_cut = api.BamConfig(text="map:cut.bam\tlib:L\tmean:300\tstd:30\treadlen:36\n")
+        for kb in (1, 100000):
+            monkeypatch.setenv("BDK_DECODE_WINDOW_KB", str(kb))
+            with pytest.raises(RuntimeError, match="truncated BAM record"):
+                api.BamStream(cfg_cut, threads=4)
+    finally:
+        os.chdir(cwd)
