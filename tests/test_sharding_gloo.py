@@ -135,3 +135,57 @@ def test_plan_and_shards_from_indexed_bams(tmp_path):
                 assert np.array_equal(cols[k], whole.cols[k][sl[tid]]), (tid, k)
     finally:
         os.chdir(cwd)
+
+
+def _bam_engine(w, cfg):
+    """run_chromosome for run_sharded_bams: the oracle on the columns the rank decoded for that chromosome (-o semantics)."""
+    def run(tid, name, st):
+        o = api.Options(chr=name)
+        b = api.ParamBundle.from_stream(o, cfg, st)
+        r = oracle.run(b, {k: v.copy() for k, v in st.cols.items()})
+        return st.n, r.table.sv.tobytes(), len(r.regions)
+    return run
+
+
+def _bam_worker(rank, world, port, d, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    os.chdir(d)
+    w = synth.generate(util.GENOME3, util.LIBS4, 40000, seed=6, anomaly_frac=0.05)
+    cfg = api.BamConfig(text=w.config_text())
+    res = shard.run_sharded_bams(cfg, rank, world, _bam_engine(w, cfg), threads=2)
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_from_indexed_bams_equal_the_single_rank_run(tmp_path):
+    import subprocess
+    samtools = os.path.join(util.ROOT, "oracle", "_ref", "samtools")
+    if not os.path.exists(samtools):
+        pytest.skip("oracle/_ref/samtools not built")
+    w = synth.generate(util.GENOME3, util.LIBS4, 40000, seed=6, anomaly_frac=0.05)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(bam, [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=1)
+            subprocess.check_call([samtools, "index", bam])
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_bam_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        cfg = api.BamConfig(text=w.config_text())
+        want = shard.run_sharded_bams(cfg, 0, 1, _bam_engine(w, cfg), threads=2)
+        assert [t for t, _ in got] == [0, 1, 2] and got == want
+        assert sum(r[0] for _, r in got) == w.n and sum(len(r[1]) for _, r in got) > 0
+    finally:
+        os.chdir(cwd)
