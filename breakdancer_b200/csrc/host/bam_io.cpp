@@ -210,6 +210,8 @@ void inflate_members(const MappedFile& f, const std::string& path, int threads, 
             zs.next_out = dst; zs.avail_out = b.out_len;
             int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0) bad = true;
+            // raw inflate checks nothing: a damaged member that still is a well-formed stream of the right length must not pass
+            else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b.out_len) != rd32(f.data + b.in_off + b.in_len)) bad = true;
         }
         inflateEnd(&zs);
         if (use_fast && fell_back) g_inflate_fallbacks += fell_back;
