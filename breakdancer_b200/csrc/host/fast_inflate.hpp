@@ -42,10 +42,10 @@ static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 
                                        8193, 12289, 16385, 24577};
 static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-inline uint32_t reverse_bits(uint32_t code, int len) {
-    uint32_t r = 0;
-    for (int i = 0; i < len; ++i) { r = (r << 1) | (code & 1); code >>= 1; }
-    return r;
+struct Rev8 { uint8_t t[256]; Rev8() { for (int i = 0; i < 256; ++i) { int r = 0; for (int b = 0; b < 8; ++b) r |= ((i >> b) & 1) << (7 - b); t[i] = (uint8_t)r; } } };
+inline uint32_t reverse_bits(uint32_t code, int len) {          // len <= 15: reverse 16 bits through a byte table, drop the rest
+    static const Rev8 R;
+    return (((uint32_t)R.t[code & 0xff] << 8) | R.t[(code >> 8) & 0xff]) >> (16 - len);
 }
 
 // Build a two-level decoding table from code lengths. is_dist selects the symbol semantics. Returns false for an
@@ -65,11 +65,14 @@ inline bool build_table(const uint8_t* lens, int nsym, bool is_dist, int first_b
     uint32_t code = 0;
     for (int l = 1; l <= MAX_LEN; ++l) { code = (code + count[l - 1]) << 1; next_code[l] = code; }
     const int first_size = 1 << first_bits;
-    for (int i = 0; i < first_size; ++i) table[i] = make_entry(0, 1, 4, 0);
+    // a complete code covers every first-level index with an entry or a link; only an incomplete one leaves holes
+    if (left > 0) for (int i = 0; i < first_size; ++i) table[i] = make_entry(0, 1, 4, 0);
+    int max_len = MAX_LEN;
+    while (max_len > 1 && !count[max_len]) --max_len;
     // longest code behind every first-level prefix that needs a subtable
     int sub_len[1 << LL_BITS];
-    memset(sub_len, 0, sizeof(int) * first_size);
-    {
+    if (max_len > first_bits) {
+        memset(sub_len, 0, sizeof(int) * first_size);
         uint32_t nc[MAX_LEN + 2];
         memcpy(nc, next_code, sizeof nc);
         for (int s = 0; s < nsym; ++s) {
@@ -81,7 +84,7 @@ inline bool build_table(const uint8_t* lens, int nsym, bool is_dist, int first_b
         }
     }
     int next_free = first_size;
-    for (int p = 0; p < first_size; ++p) {
+    for (int p = 0; max_len > first_bits && p < first_size; ++p) {
         if (!sub_len[p]) continue;
         const int w = sub_len[p];
         if (next_free + (1 << w) > table_cap) return false;
@@ -253,7 +256,16 @@ inline bool inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t o
             const uint8_t* src = op - dist;
             uint8_t* dst = op;
             op += len;
-            if (dist >= 8) {
+            if (dist >= 16) {                                   // most matches: at most two 16-byte moves, no loop
+                _mm_storeu_si128((__m128i*)dst, _mm_loadu_si128((const __m128i*)src));
+                if (len > 16) {
+                    _mm_storeu_si128((__m128i*)(dst + 16), _mm_loadu_si128((const __m128i*)(src + 16)));
+                    if (len > 32) {
+                        src += 32; dst += 32;
+                        do { _mm_storeu_si128((__m128i*)dst, _mm_loadu_si128((const __m128i*)src)); src += 16; dst += 16; } while (dst < op);
+                    }
+                }
+            } else if (dist >= 8) {
                 do { uint64_t w0, w1; memcpy(&w0, src, 8); memcpy(dst, &w0, 8); memcpy(&w1, src + 8, 8); memcpy(dst + 8, &w1, 8); src += 16; dst += 16; } while (dst < op);
             } else if (dist == 1) {
                 uint64_t w = 0x0101010101010101ull * src[0];
