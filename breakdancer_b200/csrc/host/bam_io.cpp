@@ -448,6 +448,15 @@ struct Columns {
         if (want_rec) rec.resize(n);
         cap = n;
     }
+    void reserve(size_t used, size_t want) {                // room for `want` elements, the first `used` kept
+        if (want <= cap) return;
+        cap = want;
+        pos.grow(cap); mpos.grow(cap); tid.grow(cap); mtid.grow(cap); isize.grow(cap); qlen.grow(cap);
+        flag.grow(cap); rgid.grow(cap); mapq.grow(cap); qid.grow(cap);
+        if (want_rec) rec.grow(cap);
+        pos.n = mpos.n = tid.n = mtid.n = isize.n = qlen.n = flag.n = rgid.n = mapq.n = qid.n = used;
+        if (want_rec) rec.n = used;
+    }
     void append_room(size_t used, size_t more) {            // afterwards every column holds used + more elements, the first `used` kept
         const size_t need = used + more;
         if (need > cap) {
@@ -768,6 +777,11 @@ void decode_bam_windowed(const MappedFile& mf, const std::string& path, const ch
         wd.find_records(threads, !last, &tail);
         extract_bam(wd, bam_idx, rg, rgt, threads, out, true);
         carry.assign(wd.raw.data() + tail, wd.raw.data() + wd.rec_end);
+        if (first && !last && bytes > 0) {
+            // the first window tells how many records to expect: one allocation instead of growing window by window
+            const size_t used = out.pos.size();
+            out.reserve(used, (size_t)((double)used / (double)bytes * (double)total * 1.05) + 4096);
+        }
         m = j;
         first = false;
         ++windows;
