@@ -524,6 +524,7 @@ namespace {
 void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, int threads, Columns& out, bool append = false) {
     size_t nrec = bd.rec_off.size();
     const uint8_t* raw = bd.raw.data();
+    const double tp0 = now_s();
     // pass 1: filter flags (primary && tid >= 0 [&& region overlap]) -> keep mask + prefix
     std::vector<uint8_t> keep(nrec);
     const brec::RegionSel sel{region.on ? 1 : 0, region.tid, region.beg, region.end};
@@ -534,6 +535,7 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
       for (uint64_t g = g0; g < g1; ++g) {
         uint64_t kept = 0;
         for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) {
+            if (i + 16 < nrec) __builtin_prefetch(raw + bd.rec_off[i + 16]);
             const bool ok = brec::keep_record(raw + bd.rec_off[i], sel);
             keep[i] = ok;
             kept += ok;
@@ -547,6 +549,7 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
         out.append_room(used, goff[ng]);
         for (size_t g = 0; g <= ng; ++g) goff[g] += used;
     } else out.resize(goff[ng]);
+    const double tp1 = now_s();
     // pass 2: field extraction
     parallel_for(ng, 1, threads, [&](uint64_t g0, uint64_t g1) {
         std::string last_rg; int last_id = -1; bool have_last = false;
@@ -555,6 +558,12 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
             uint64_t o = goff[g];
             for (uint64_t i = g * G; i < std::min<uint64_t>(nrec, (g + 1) * G); ++i) {
                 if (!keep[i]) continue;
+                if (i + 13 < nrec) {                           // a record is two or three cache lines: the core, and the aux fields at its end
+                    const uint8_t* nx = raw + bd.rec_off[i + 12];
+                    __builtin_prefetch(nx);
+                    __builtin_prefetch(raw + bd.rec_off[i + 13] - 68);
+                    __builtin_prefetch(nx + 64);
+                }
                 const brec::Fields f = brec::record_fields(raw + bd.rec_off[i]);
                 out.pos[o] = f.pos; out.mpos[o] = f.mpos; out.tid[o] = f.tid; out.mtid[o] = f.mtid;
                 out.isize[o] = f.isize; out.qlen[o] = f.qlen; out.flag[o] = f.flag;
@@ -574,6 +583,7 @@ void extract_bam(BamData& bd, int bam_idx, const Region& region, RgTable& rgt, i
             }
         }
     });
+    if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] extract: filter pass %.3f s, field pass %.3f s (%zu records)\n", tp1 - tp0, now_s() - tp1, nrec);
 }
 
 // ---- -o with a .bai: only the members that hold the reference sequence's records are inflated -----------------------------
