@@ -401,6 +401,8 @@ struct SoloTeam {
     BDK_HD int lane() const { return 0; }
     BDK_HD int width() const { return 1; }
     BDK_HD int sum(int v) const { return v; }
+    BDK_HD int min(int v) const { return v; }
+    BDK_HD int max(int v) const { return v; }
     BDK_HD bool any(bool p) const { return p; }
     BDK_HD void sync() const {}
     BDK_HD void add(int32_t* p, int v) const { *p += v; }
@@ -411,6 +413,8 @@ struct WarpTeam {
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
     __device__ __forceinline__ int width() const { return 32; }
     __device__ __forceinline__ int sum(int v) const { return (int)__reduce_add_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void add(int32_t* p, int v) const { atomicAdd(p, v); }
@@ -632,6 +636,303 @@ BDK_HD void k4_score_row(const K4Static& S, K4Mut& M, int row) {
     o.logp = logp; o.allele_frequency = af; o.cn_present = 0;
     o.order = 0;
     M.row_emit[row] = K4_ROW_EMIT;
+}
+
+// =================================================================================================
+// K4, second formulation: the connection walk WITHOUT walking.
+//
+// What the reference's build_connection / process_sv / is_region_final / clear_region do to the reads (the statements
+// cited at the top of this file) has a closed form once one fact per region is known -- the flush window in which the
+// region is cleared, del[region] (K4_NEVER: never):
+//
+//  * a pair (x, y) whose reads sit in two DIFFERENT stored regions rx < ry is only ever looked at by process_sv(rx, ry),
+//    which is called at most once, in the window of ry, iff the edge is followed (weight >= -r) and both regions still
+//    exist then; both reads are still held at that moment (nothing else can remove them), so the call consumes the pair;
+//  * a pair with both reads in ONE region is consumed by the first process_sv call that involves the region;
+//  * a read whose later mate sat in a rejected (collapsed) candidate is dropped by the first call involving its region
+//    after that collapse; a read whose mate is absent, or sat EARLIER in a collapsed candidate, is held for ever;
+//  * whether names were freed (the two early returns of process_sv) never matters: freed reads are no longer held.
+//
+// So "is read j still held at the end of window w, and does it keep its region from being final?" is a function of del[]
+// of the mate's region and of the set of windows in which the region takes part in a call, which again depends only on del[]
+// of its partners. The table is the fixed point of  del[v] = first active window of v in which no held read blocks
+// (k4n_region_deletion); every event depends only on strictly earlier events (windows in order, inside a window the
+// active nodes ascending), so the fixed point is unique and any iteration order reaches it. With the table known, the
+// calls of every window are independent of all other windows (k4n_window_calls gives build_connection's order, which
+// decides who is the FIRST call of a region; k4n_call counts the pairs of one call).
+// =================================================================================================
+enum : uint32_t { RI_STRONG = 1u << 24,        // the edge (own region, mate's region) has weight >= -r: process_sv is called for it
+                  RI_MATE_STORED = 1u << 25 }; // the mate's region kept its reads (ReadRegionData.cpp:118-121)
+
+struct alignas(16) ReadInfo2 {
+    int32_t mate;          // index of the mate in the anomalous-read stream, or -1
+    int32_t mate_region;   // region of the mate, or -1 (collapsed candidate / no mate)
+    int32_t wthr;          // mate later and collapsed: first flush window whose trigger lies behind that collapse
+    uint32_t meta;         // bdk_aread::meta | RI_*
+};
+
+struct K4N {
+    const ReadInfo2* ri;          // [A]
+    const bdk_aread* ar;
+    const RegionRec* reg;
+    int32_t nreg, period, chr_restricted, min_read_pair;
+};
+
+BDK_HD int32_t k4n_ld(const int32_t* p) {      // the table is rewritten in place by other warps during a sweep
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+BDK_HD int k4n_last_region(const K4N& S, int w) {          // last_region_idx() at the flush of window w
+    const int64_t trigger = ((int64_t)w + 1) * S.period - 1;
+    return trigger < S.nreg ? (int)trigger : S.nreg - 1;
+}
+BDK_HD bool k4n_before(int d, int w, int rm, int v) { return d < w || (d == w && rm < v); }   // rm cleared before (w, v)?
+
+// first flush window whose trigger candidate lies behind candidate `c` (the collapse of c has happened by then):
+// regions are in candidate order, g = index of the first region with cand > c, window = g / period
+BDK_HD int k4n_window_after_cand(const RegionRec* reg, int nreg, int period, int c) {
+    int a = 0, b = nreg;
+    while (a < b) { const int m = (a + b) >> 1; if (reg[m].cand > c) b = m; else a = m + 1; }
+    return a / period;
+}
+
+BDK_HD ReadInfo2 k4n_make_read_info(const bdk_aread* ar, const int32_t* mate, const int32_t* read_region, const int32_t* read_cand,
+                                    const RegionRec* reg, int nreg, int period, int j, bool strong) {
+    ReadInfo2 r;
+    r.mate = mate[j];
+    r.mate_region = r.mate >= 0 ? read_region[r.mate] : -1;
+    r.wthr = 0;
+    r.meta = ar[j].meta & 0x00ffffffu;
+    if (r.mate >= 0 && r.mate_region < 0 && r.mate > j) r.wthr = k4n_window_after_cand(reg, nreg, period, read_cand[r.mate]);
+    if (r.mate_region >= 0) {
+        if (strong) r.meta |= RI_STRONG;
+        if (reg[r.mate_region].stored) r.meta |= RI_MATE_STORED;
+    }
+    return r;
+}
+
+// A stored read that is held for ever with a name entry of size 1: is_region_final(v) is false in every window.
+template <class Team>
+BDK_HD bool k4n_never_final(const Team& T, const K4N& S, int v) {
+    const RegionRec R = S.reg[v];
+    bool bad = false;
+    if (R.stored)
+        for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
+            const ReadInfo2 I = S.ri[j];
+            if (S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX) continue;
+            if (I.mate < 0 || (I.mate_region < 0 && I.mate < j)) bad = true;
+        }
+    return T.any(bad);
+}
+
+// The flush window in which region v is cleared, given the deletion windows del[] of the other regions.
+template <class Team>
+BDK_HD int k4n_region_deletion(const Team& T, const K4N& S, const int32_t* del, int v) {
+    const RegionRec R = S.reg[v];
+    const int j0 = R.first_read, j1 = R.first_read + R.n_reads, wv = v / S.period;
+    int w = -1;
+    for (;;) {
+        // next window in which v is an active node: the windows of its edges = max(v, mate's region) / period
+        int wn = K4_NEVER, lc = -1, intra = 0;
+        for (int j = j0 + T.lane(); j < j1; j += T.width()) {
+            const ReadInfo2 I = S.ri[j];
+            const int rm = I.mate_region;
+            if (rm < 0) continue;
+            const int aw = (rm > v ? rm : v) / S.period;
+            if (aw > w && aw < wn) wn = aw;
+        }
+        wn = T.min(wn);
+        if (wn == K4_NEVER) return K4_NEVER;
+        w = wn;
+        if (v == k4n_last_region(S, w)) continue;
+        if (!R.stored) return w;                       // holds no reads: final the first time it is asked
+        // latest window <= w in which process_sv was called with v
+        for (int j = j0 + T.lane(); j < j1; j += T.width()) {
+            const ReadInfo2 I = S.ri[j];
+            const int rm = I.mate_region;
+            if (rm < 0) continue;
+            if (rm == v) { ++intra; continue; }
+            if (!(I.meta & RI_STRONG)) continue;
+            const int wp = (rm > v ? rm : v) / S.period;
+            if (wp <= w && wp > lc && k4n_ld(del + rm) >= wp) lc = wp;
+        }
+        lc = T.max(lc);
+        if (T.sum(intra) / 2 >= S.min_read_pair && wv > lc) lc = wv;       // the self loop: process_sv(v) in v's own window
+        bool bad = false;
+        for (int j = j0 + T.lane(); j < j1 && !bad; j += T.width()) {
+            const ReadInfo2 I = S.ri[j];
+            if (S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX) continue;
+            const int rm = I.mate_region;
+            if (rm == v) continue;                     // an unconsumed pair inside v has a name entry of size 2
+            if (rm < 0) {
+                if (I.mate < 0 || I.mate < j) bad = true;                  // (never final; callers filter these regions out)
+                else bad = !(lc >= I.wthr);                                // held until a call after the mate's collapse drops it
+                continue;
+            }
+            const int wp = (rm > v ? rm : v) / S.period;
+            if (w < wp) { bad = true; continue; }      // mate not registered yet
+            const int d = k4n_ld(del + rm);
+            if ((I.meta & (RI_STRONG | RI_MATE_STORED)) == (RI_STRONG | RI_MATE_STORED) && d >= wp) continue;   // consumed by process_sv(v, rm)
+            if ((I.meta & RI_MATE_STORED) && k4n_before(d, w, rm, v)) bad = true;  // clear_region(rm) took rm out of the name entry
+        }
+        if (!T.any(bad)) return w;
+    }
+}
+
+// first window in which process_sv is called with region v (K4_NEVER: never), given the final table
+template <class Team>
+BDK_HD int k4n_first_call(const Team& T, const K4N& S, const int32_t* del, int v) {
+    const RegionRec R = S.reg[v];
+    const int dv = del[v];
+    int c1 = K4_NEVER, intra = 0;
+    for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
+        const ReadInfo2 I = S.ri[j];
+        const int rm = I.mate_region;
+        if (rm < 0) continue;
+        if (rm == v) { ++intra; continue; }
+        if (!(I.meta & RI_STRONG)) continue;
+        const int wp = (rm > v ? rm : v) / S.period;
+        if (wp < c1 && del[rm] >= wp && dv >= wp) c1 = wp;
+    }
+    c1 = T.min(c1);
+    const int wv = v / S.period;
+    if (T.sum(intra) / 2 >= S.min_read_pair && wv < c1 && dv >= wv) c1 = wv;
+    return c1;
+}
+
+// ---- the calls of one flush window, in build_connection's order --------------------------------------------------
+// e[0..n): the directed copies (src, dst) of the followed edges (weight >= -r) of window w, sorted by (src, dst);
+// fl[0..n): scratch flags, zero on entry; queue: n + 1 entries. Sequential (one thread per window): vertices ascending,
+// BFS from each, a tail's edges ascending, every live edge followed once (BreakDancer.cpp:280-338). Call k goes to
+// slot0 + k; returns the number of calls. A call is FIRST for one of its regions when no earlier call (in an earlier
+// window: c1[] < w, or earlier in this one) involved that region.
+struct SEdge { int32_t src, dst; };
+enum : uint8_t { SE_ERASED = 1, SE_VDONE = 2, SE_TOUCHED = 4 };
+enum : uint8_t { K4_ROW_CALL = 4, K4_ROW_FIRST0 = 8, K4_ROW_FIRST1 = 16 };   // row_emit[] of a slot between k4n_window_calls and k4n_call
+
+BDK_HD int k4n_find_run(const SEdge* e, int n, int src) {
+    int a = 0, b = n;
+    while (a < b) { const int m = (a + b) >> 1; if (e[m].src < src) a = m + 1; else b = m; }
+    return (a < n && e[a].src == src) ? a : -1;
+}
+BDK_HD int k4n_find_edge(const SEdge* e, int n, int src, int dst) {
+    int a = 0, b = n;
+    while (a < b) { const int m = (a + b) >> 1; if (e[m].src < src || (e[m].src == src && e[m].dst < dst)) a = m + 1; else b = m; }
+    return (a < n && e[a].src == src && e[a].dst == dst) ? a : -1;
+}
+
+BDK_HD int k4n_window_calls(const int32_t* del, const int32_t* c1, const SEdge* e, int n, uint8_t* fl, int32_t* queue, int w, int slot0,
+                            bdk_sv* rows, uint64_t* row_key, uint8_t* row_emit) {
+    int slot = slot0;
+    for (int vi = 0; vi < n;) {
+        const int v = e[vi].src;
+        int vend = vi;
+        while (vend < n && e[vend].src == v) ++vend;
+        if (!(fl[vi] & SE_VDONE) && del[v] >= w) {
+            int qa = 0, qb = 1, qn;
+            queue[0] = v;
+            while (qa < qb) {
+                qn = qb;
+                for (int t = qa; t < qb; ++t) {
+                    const int tail = queue[t];
+                    if (del[tail] < w) continue;                               // !region_exists(tail)
+                    const int ts = k4n_find_run(e, n, tail);
+                    if (ts < 0 || (fl[ts] & SE_VDONE)) continue;               // graph.find(tail) == end
+                    for (int k = ts; k < n && e[k].src == tail; ++k) {
+                        if (fl[k] & SE_ERASED) continue;
+                        const int s1 = e[k].dst;
+                        if (del[s1] < w) continue;                             // !region_exists(s1)
+                        fl[k] |= SE_ERASED;
+                        int r1 = ts;
+                        if (s1 != tail) {
+                            const int rq = k4n_find_edge(e, n, s1, tail);       // erase_edge(s1, tail)
+                            if (rq >= 0) fl[rq] |= SE_ERASED;
+                            r1 = k4n_find_run(e, n, s1);
+                        }
+                        queue[qn++] = s1;
+                        const bool first_t = !(c1[tail] < w) && !(fl[ts] & SE_TOUCHED);
+                        const bool first_s = s1 == tail ? first_t : (!(c1[s1] < w) && !(fl[r1] & SE_TOUCHED));
+                        fl[ts] |= SE_TOUCHED; fl[r1] |= SE_TOUCHED;
+                        const int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
+                        bdk_sv& o = rows[slot];
+                        o.region[0] = a; o.region[1] = s1 != tail ? b : -1; o.window = w;
+                        row_key[slot] = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v;
+                        const bool f0 = a == tail ? first_t : first_s, f1 = a == tail ? first_s : first_t;
+                        row_emit[slot] = (uint8_t)(K4_ROW_CALL | (f0 ? K4_ROW_FIRST0 : 0) | (s1 != tail && f1 ? K4_ROW_FIRST1 : 0));
+                        ++slot;
+                    }
+                    fl[ts] |= SE_VDONE;                                         // graph.erase(tail)
+                }
+                qa = qb; qb = qn;
+            }
+        }
+        vi = vend;
+    }
+    return slot - slot0;
+}
+
+// process_sv's pairing (SvBuilder.cpp:101-118, BreakDancer.cpp:363-375) for the call in slot `row`: every pair between the
+// two regions, plus the pairs inside a region this call is the first for. Leaves the slot PENDING (to be scored) or NONE.
+struct K4NOut {
+    int32_t* sv_of_read; bdk_sv* rows; int32_t* row_lib_count; int32_t* row_lib_span; uint8_t* row_emit; int32_t nlib;
+};
+template <class Team>
+BDK_HD void k4n_call(const Team& T, const K4N& S, const K4NOut& M, int row) {
+    const uint8_t st = M.row_emit[row];
+    const int s0 = M.rows[row].region[0], s1 = M.rows[row].region[1];
+    T.sync();
+    const int n = s1 >= 0 ? 2 : 1;
+    const int sn[2] = {s0, s1};
+    const bool first[2] = {(st & K4_ROW_FIRST0) != 0, (st & K4_ROW_FIRST1) != 0};
+    int c[BDK_NUM_FLAGS];
+    for (int f = 0; f < BDK_NUM_FLAGS; ++f) c[f] = 0;
+    auto pairs = [&](int i, int y, const ReadInfo2& I) -> bool {        // is y the later read of a pair this call consumes?
+        const int x = I.mate;
+        if (x < 0 || x >= y) return false;
+        const int rx = I.mate_region;
+        if (rx < 0) return false;
+        if (rx == sn[i]) return first[i];
+        return i == 1 && rx == s0 && (I.meta & RI_MATE_STORED);
+    };
+    for (int i = 0; i < n; ++i) {
+        const RegionRec R = S.reg[sn[i]];
+        if (!R.stored) continue;
+        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width()) {
+            const ReadInfo2 I = S.ri[y];
+            if (pairs(i, y, I)) ++c[meta_flag(I.meta)];
+        }
+    }
+    int num_pairs = 0, flag = BDK_NA, best = 0;
+    for (int f = 0; f < BDK_NUM_FLAGS; ++f) { c[f] = T.sum(c[f]); num_pairs += c[f]; if (c[f] > best) { best = c[f]; flag = f; } }
+    const bool early = num_pairs < S.min_read_pair || c[flag] < S.min_read_pair;
+    int32_t* lib_count = M.row_lib_count + (int64_t)row * M.nlib;
+    int32_t* lib_span = M.row_lib_span + (int64_t)row * M.nlib;
+    if (!early) for (int l = T.lane(); l < M.nlib; l += T.width()) { lib_count[l] = 0; lib_span[l] = 0; }
+    T.sync();
+    if (num_pairs)
+        for (int i = 0; i < n; ++i) {
+            const RegionRec R = S.reg[sn[i]];
+            if (!R.stored) continue;
+            for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width()) {
+                const ReadInfo2 I = S.ri[y];
+                if (!pairs(i, y, I)) continue;
+                M.sv_of_read[I.mate] = row; M.sv_of_read[y] = row;
+                if (!early && meta_flag(I.meta) == flag) {
+                    const int l = meta_lib(I.meta);
+                    T.add(lib_count + l, 1);
+                    T.add(lib_span + l, S.ar[y].abs_isize);
+                }
+            }
+        }
+    T.sync();
+    if (T.lane() != 0) return;
+    if (early) { M.row_emit[row] = K4_ROW_NONE; return; }
+    bdk_sv& o = M.rows[row];
+    o.flag = flag; o.num_pairs = c[flag];
+    M.row_emit[row] = K4_ROW_PENDING;
 }
 
 // ---- in-place heap sort of a component's directed edges by (win, src, dst) --------------------

@@ -21,76 +21,6 @@
 
 using namespace bdk;
 
-// Host rendering of the piece-parallel walk the CUDA path uses for very large components (k4_component_cta): same
-// decomposition, pieces of a window walked in DESCENDING order (nothing may depend on their order), finality pass evaluated
-// against the earlier state and resolved afterwards.
-static int component_by_pieces(const K4Static& S, K4Mut& M, DEdge* e, int ne, int row0, int nrows) {
-    SoloTeam T;
-    if (S.rerun) {
-        for (int q = 0; q < ne; ++q) k4_reset_slot(S, M, e, q);
-        for (int r = 0; r < nrows; ++r) M.row_emit[row0 + r] = 0;
-    }
-    int row_base = row0, i = 0;
-    std::vector<int32_t> queue;
-    while (i < ne) {
-        const int w = e[i].win;
-        int j = i;
-        while (j < ne && e[j].win == w) ++j;
-        WindowInfo wi = k4_window_info(S, w);
-        std::vector<int> vtx, rs;
-        for (int t = i; t < j; ++t) if (t == i || e[t].src != e[t - 1].src) { vtx.push_back(e[t].src); rs.push_back(t); }
-        rs.push_back(j);
-        const int R = (int)vtx.size();
-        auto run_of = [&](int v) { return (int)(std::lower_bound(vtx.begin(), vtx.end(), v) - vtx.begin()); };
-        std::vector<int> label(R);
-        std::iota(label.begin(), label.end(), 0);
-        auto followable = [&](const DEdge& x) { return x.w >= S.min_read_pair && !M.deleted[x.dst] && !M.deleted[x.src]; };
-        for (bool changed = true; changed;) {
-            changed = false;
-            for (int r = 0; r < R; ++r)
-                for (int t = rs[r]; t < rs[r + 1]; ++t) {
-                    if (!followable(e[t])) continue;
-                    int r2 = run_of(e[t].dst);
-                    int m = std::min(label[r], label[r2]);
-                    if (label[r] != m || label[r2] != m) { label[r] = label[r2] = m; changed = true; }
-                }
-        }
-        std::vector<int> prow(R, 0), pq(R, 0);
-        for (int r = 0; r < R; ++r)
-            for (int t = rs[r]; t < rs[r + 1]; ++t)
-                if (followable(e[t])) { ++pq[label[r]]; if (e[t].src <= e[t].dst) ++prow[label[r]]; }
-        std::vector<int> pieces, rowoff;
-        int rows = 0;
-        for (int r = 0; r < R; ++r) if (label[r] == r && prow[r] > 0) { pieces.push_back(r); rowoff.push_back(rows); rows += prow[r]; }
-        for (int p = (int)pieces.size() - 1; p >= 0; --p) {
-            int row = row_base + rowoff[p];
-            queue.assign(pq[pieces[p]] + 2, 0);
-            for (int r = 0; r < R; ++r)
-                if (label[r] == pieces[p]) row = k4_bfs_from(T, S, M, e, i, j, w, wi, rs[r], rs[r + 1], queue.data(), row);
-            if (row - (row_base + rowoff[p]) != prow[pieces[p]]) return -1;      // every followable edge of a piece is followed exactly once
-        }
-        row_base += rows;
-        // finality pass
-        std::vector<int32_t> cand;
-        for (int r = 0; r < R; ++r) if (!S.never_final[vtx[r]] && !M.deleted[vtx[r]] && vtx[r] != wi.last_region) cand.push_back(vtx[r]);
-        std::vector<uint8_t> state(cand.size() + 1, K4_FIN_NOT);
-        for (size_t c = 0; c < cand.size(); ++c) state[c] = k4_region_final(T, S, M, cand[c], wi) ? K4_FIN_UNDECIDED : K4_FIN_NOT;
-        for (bool pending = true; pending;) {
-            pending = false;
-            for (int c = (int)cand.size() - 1; c >= 0; --c) {                    // descending on purpose
-                if (state[c] != K4_FIN_UNDECIDED) continue;
-                int d = k4_final_deps(T, S, M, cand[c], cand.data(), state.data(), (int)cand.size());
-                if (d & 1) state[c] = K4_FIN_NOT;
-                else if (!(d & 2)) state[c] = K4_FIN_CLEARED;
-                else pending = true;
-            }
-        }
-        for (size_t c = 0; c < cand.size(); ++c) if (state[c] == K4_FIN_CLEARED) { M.deleted[cand[c]] = 1; M.del_cur[cand[c]] = w; }
-        i = j;
-    }
-    return row_base - row0;
-}
-
 extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, bdo_output* out) {
     const bdk_params& p = *pp;
     int nkey = nkey_of(p), nlib = p.nlib;
@@ -193,116 +123,119 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
         ue.push_back({(int)(links[i] >> 32), (int)(links[i] & 0xffffffffu), (int)(j - i)});
         i = j;
     }
-    // ---- components (union-find, smaller root wins) ----------------------------------------------
-    std::vector<int> parent(nreg);
-    std::iota(parent.begin(), parent.end(), 0);
-    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    // components over the edges the walk can follow (weight >= -r); a weaker edge is kept as a directed copy in each end's component
-    for (auto const& e : ue) { if (e.w < p.min_read_pair) continue; int a = find(e.r0), b = find(e.r1); if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } }
-    std::vector<int32_t> root_of(nreg);
-    for (int r = 0; r < nreg; ++r) root_of[r] = find(r);
-    std::vector<int> comp_ne(nreg, 0), comp_strong(nreg, 0);
-    for (auto const& e : ue) {
-        ++comp_ne[root_of[e.r0]];
-        if (e.r0 != e.r1) ++comp_ne[root_of[e.r1]];
-        if (e.w >= p.min_read_pair) ++comp_strong[root_of[e.r0]];
+    // ---- K4 (closed form, bdk_logic.h "second formulation") ------------------------------------------------------
+    // strong bit per read, per-read info
+    std::unordered_map<uint64_t, int> weight;
+    for (auto const& e : ue) weight[((uint64_t)(uint32_t)e.r0 << 32) | (uint32_t)e.r1] = e.w;
+    std::vector<ReadInfo2> ri((size_t)std::max<int64_t>(A, 1));
+    for (int64_t j = 0; j < A; ++j) {
+        bool strong = false;
+        const int m = mate[j];
+        if (m >= 0 && read_region[j] >= 0 && read_region[m] >= 0) {
+            const int a = std::min(read_region[j], read_region[m]), b2 = std::max(read_region[j], read_region[m]);
+            strong = weight[((uint64_t)(uint32_t)a << 32) | (uint32_t)b2] >= p.min_read_pair;
+        }
+        ri[j] = k4n_make_read_info(ar.data(), mate.data(), read_region.data(), read_cand.data(), reg.data(), nreg, period, (int)j, strong);
     }
-    std::vector<int> de_off(nreg + 1, 0), row_off(nreg + 1, 0);
-    for (int r = 0; r < nreg; ++r) { de_off[r + 1] = de_off[r] + comp_ne[r]; row_off[r + 1] = row_off[r] + comp_strong[r]; }
-    std::vector<DEdge> de(de_off[nreg] + 1);
-    std::vector<int> fill(nreg, 0);
-    std::vector<int> win_first(nreg + 1, 0x7fffffff), win_last(nreg + 1, -1);
-    for (auto const& e : ue) {
-        int win = e.r1 / period;  // r0 <= r1: the edge is counted when r1 is registered
-        for (int v : {e.r0, e.r1}) { win_first[v] = std::min(win_first[v], win); win_last[v] = std::max(win_last[v], win); }
-        int r = root_of[e.r0];
-        de[de_off[r] + fill[r]++] = DEdge{win, e.r0, e.r1, e.w, 0};
-        if (e.r0 != e.r1) { r = root_of[e.r1]; de[de_off[r] + fill[r]++] = DEdge{win, e.r1, e.r0, e.w, 0}; }
+    K4N KS;
+    KS.ri = ri.data(); KS.ar = ar.data(); KS.reg = reg.data(); KS.nreg = nreg; KS.period = period;
+    KS.chr_restricted = p.chr_restricted; KS.min_read_pair = p.min_read_pair;
+    SoloTeam T;
+    // fixed point of the deletion table. Starting table: "cleared in the last window it is active in" (or an empty table),
+    // sweeps in Jacobi order (every region against the previous table) or in place in DESCENDING order -- nothing may depend
+    // on the order.
+    std::vector<int32_t> del(nreg + 1, K4_NEVER), del_next(nreg + 1, K4_NEVER);
+    std::vector<uint8_t> never_final(nreg + 1, 0), dirty(nreg + 1, 1), dirty_next(nreg + 1, 0);
+    for (int v = 0; v < nreg; ++v) {
+        never_final[v] = k4n_never_final(T, KS, v) ? 1 : 0;
+        if (never_final[v] || getenv("HOSTSIM_NO_GUESS")) continue;
+        int wl = -1;
+        for (int j = reg[v].first_read; j < reg[v].first_read + reg[v].n_reads; ++j)
+            if (ri[j].mate_region >= 0) wl = std::max(wl, std::max(v, ri[j].mate_region) / period);
+        if (wl >= 0 && v != nreg - 1) del[v] = wl;
     }
-    int nrow_cap = row_off[nreg];
-
-    // ---- K4 -----------------------------------------------------------------------------------
+    const bool in_place = getenv("HOSTSIM_INPLACE") != nullptr;
+    int sweeps = 0;
+    for (;; ++sweeps) {
+        if (sweeps > 1000000) return -101;
+        int nchanged = 0;
+        if (!in_place) del_next = del;
+        for (int v = nreg - 1; v >= 0; --v) {
+            if (never_final[v] || !dirty[v]) continue;
+            const int d = k4n_region_deletion(T, KS, del.data(), v);
+            const int old = del[v];
+            (in_place ? del : del_next)[v] = d;
+            if (d != old) {
+                ++nchanged;
+                for (int j = reg[v].first_read; j < reg[v].first_read + reg[v].n_reads; ++j)
+                    if (ri[j].mate_region >= 0 && ri[j].mate_region != v) dirty_next[ri[j].mate_region] = 1;
+            }
+        }
+        if (!in_place) del.swap(del_next);
+        dirty.swap(dirty_next);
+        std::fill(dirty_next.begin(), dirty_next.end(), 0);
+        if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: sweep %d -> %d regions changed\n", sweeps, nchanged);
+        if (!nchanged) break;
+    }
+    std::vector<uint8_t> deleted(nreg + 1, 0);
+    for (int v = 0; v < nreg; ++v) deleted[v] = del[v] != K4_NEVER;
+    // followed edges per window, directed copies sorted by (window, src, dst); slots in window order
+    struct WE { int win, src, dst; };
+    std::vector<WE> we;
+    for (auto const& e : ue) {
+        if (e.w < p.min_read_pair) continue;
+        const int win = e.r1 / period;
+        we.push_back({win, e.r0, e.r1});
+        if (e.r0 != e.r1) we.push_back({win, e.r1, e.r0});
+    }
+    std::sort(we.begin(), we.end(), [](const WE& a, const WE& b) { return a.win != b.win ? a.win < b.win : (a.src != b.src ? a.src < b.src : a.dst < b.dst); });
+    int nrow_cap = 0;
+    for (auto const& x : we) nrow_cap += x.src <= x.dst;
+    std::vector<int32_t> c1(nreg + 1, K4_NEVER);
+    for (int v = 0; v < nreg; ++v) c1[v] = k4n_first_call(T, KS, del.data(), v);
     std::vector<uint32_t> Pflat((size_t)nkey * std::max<int64_t>(A, 1));
     for (int k = 0; k < nkey; ++k) for (int64_t d = 0; d < A; ++d) Pflat[(size_t)d * nkey + k] = P[k][d];   // [A][nkey] like the device
-    std::vector<uint8_t> freed(A, 0), deleted(nreg, 0), row_emit(nrow_cap + 1, 0);
+    std::vector<uint8_t> row_emit(nrow_cap + 1, 0);
     std::vector<int32_t> sv_of_read(A, -1), row_lib_count((size_t)(nrow_cap + 1) * nlib), row_lib_span((size_t)(nrow_cap + 1) * nlib);
     std::vector<uint32_t> row_cn_count((size_t)(nrow_cap + 1) * nkey);
     std::vector<float> row_cn((size_t)(nrow_cap + 1) * nkey);
     std::vector<bdk_sv> rows(nrow_cap + 1);
     std::vector<uint64_t> row_key(nrow_cap + 1, 0);
-    std::vector<int32_t> del_prev(nreg + 1, K4_NEVER), del_cur(nreg + 1, K4_NEVER);
-    std::vector<uint8_t> dirty(nreg + 1, 0);
-    K4Static KS;
-    std::vector<ReadInfo> ri((size_t)std::max<int64_t>(A, 1));
-    for (int64_t j = 0; j < A; ++j) ri[j] = make_read_info(ar.data(), mate.data(), read_region.data(), read_cand.data(), (int)j);
-    KS.ri = ri.data();
-    KS.ar = ar.data(); KS.read_region = read_region.data(); KS.read_cand = read_cand.data(); KS.mate = mate.data();
-    KS.reg = reg.data(); KS.P = Pflat.data(); KS.cand_maxlen = cand_maxlen.data(); KS.lib_mean = lib_mean.data();
-    KS.hist = acc.hist.data(); KS.density = density.data(); KS.A = (uint64_t)A; KS.nreg = nreg; KS.ncand = ncand;
-    KS.period = period; KS.nkey = nkey; KS.nlib = nlib; KS.chr_restricted = p.chr_restricted;
-    KS.min_read_pair = p.min_read_pair; KS.score_threshold = p.score_threshold; KS.fisher = p.fisher;
-    KS.covered_ref_len = S.covered_ref_len;
-    KS.root_of = root_of.data(); KS.del_prev = del_prev.data(); KS.rerun = 0;
+    {
+        std::vector<SEdge> se; std::vector<uint8_t> fl; std::vector<int32_t> queue;
+        int slot0 = 0;
+        // windows in DESCENDING order on purpose (they are independent); slot bases are the counts of the earlier windows
+        std::vector<std::pair<size_t, size_t>> ranges;
+        for (size_t i = 0; i < we.size();) { size_t j = i; while (j < we.size() && we[j].win == we[i].win) ++j; ranges.push_back({i, j}); i = j; }
+        std::vector<int> base(ranges.size() + 1, 0);
+        for (size_t k = 0; k < ranges.size(); ++k) { int u = 0; for (size_t t = ranges[k].first; t < ranges[k].second; ++t) u += we[t].src <= we[t].dst; base[k + 1] = base[k] + u; }
+        for (size_t k = ranges.size(); k-- > 0;) {
+            const size_t i = ranges[k].first, j = ranges[k].second;
+            se.clear(); for (size_t t = i; t < j; ++t) se.push_back({we[t].src, we[t].dst});
+            fl.assign(j - i, 0); queue.assign(j - i + 2, 0);
+            slot0 = base[k];
+            const int used = k4n_window_calls(del.data(), c1.data(), se.data(), (int)(j - i), fl.data(), queue.data(), we[i].win, slot0, rows.data(), row_key.data(), row_emit.data());
+            if (used > base[k + 1] - base[k]) return -100;
+        }
+    }
+    K4NOut KO{sv_of_read.data(), rows.data(), row_lib_count.data(), row_lib_span.data(), row_emit.data(), nlib};
+    for (int r = nrow_cap - 1; r >= 0; --r) if (row_emit[r] & K4_ROW_CALL) k4n_call(T, KS, KO, r);
+    K4Static SS;
+    memset(&SS, 0, sizeof SS);
+    SS.ar = ar.data(); SS.reg = reg.data(); SS.P = Pflat.data(); SS.cand_maxlen = cand_maxlen.data(); SS.lib_mean = lib_mean.data();
+    SS.hist = acc.hist.data(); SS.density = density.data(); SS.A = (uint64_t)A; SS.nreg = nreg; SS.ncand = ncand;
+    SS.period = period; SS.nkey = nkey; SS.nlib = nlib; SS.chr_restricted = p.chr_restricted;
+    SS.min_read_pair = p.min_read_pair; SS.score_threshold = p.score_threshold; SS.fisher = p.fisher;
+    SS.covered_ref_len = S.covered_ref_len;
     K4Mut KM;
-    KM.alive = alive.data(); KM.freed = freed.data(); KM.deleted = deleted.data(); KM.sv_of_read = sv_of_read.data();
+    memset(&KM, 0, sizeof KM);
     KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
     KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
-    KM.del_cur = del_cur.data();
-    std::vector<uint8_t> never_final(nreg + 1, 0);
-    KS.never_final = never_final.data();
-    for (int v = 0; v < nreg; ++v) {
-        del_prev[v] = getenv("HOSTSIM_NO_GUESS") ? K4_NEVER : k4_guess_deletion(KS, alive.data(), v, win_last[v]);
-        never_final[v] = k4_never_final(KS, alive.data(), v) ? 1 : 0;
-    }
-    const int big = getenv("HOSTSIM_BIG") ? atoi(getenv("HOSTSIM_BIG")) : 4096;   // tests lower it to exercise the deferral of big components
-    int nsmall_prev = 1;
-    std::vector<int32_t> queue;
-    // sweeps over the components until the table of deletion times is stable (same driver as bdk_finish). The components are
-    // walked in DESCENDING root order on purpose: nothing may depend on the order inside a sweep.
-    int sweeps = 0;
-    for (;; ++sweeps) {
-        if (sweeps > 100000) return -101;
-        KS.rerun = sweeps ? 1 : 0;
-        std::vector<int> deferred;
-        for (int r = nreg - 1; r >= 0; --r) {
-            if (!comp_ne[r] || (sweeps && !dirty[r])) continue;
-            if (nsmall_prev && comp_ne[r] > big) { deferred.push_back(r); continue; }
-            queue.assign(comp_ne[r] + 2, 0);
-            DEdge* es = de.data() + de_off[r];
-            de_sort(es, comp_ne[r]);
-            const int pieces_min = getenv("HOSTSIM_PIECES") ? atoi(getenv("HOSTSIM_PIECES")) : 4096;   // tests lower it
-            int used = comp_ne[r] > pieces_min ? component_by_pieces(KS, KM, es, comp_ne[r], row_off[r], comp_strong[r])
-                                               : k4_component(SoloTeam(), KS, KM, es, comp_ne[r], queue.data(), row_off[r], comp_strong[r]);
-            if (used < 0) return -102;
-            if (used > comp_strong[r]) return -100;
-        }
-        std::fill(dirty.begin(), dirty.end(), 0);
-        int ndirty = 0, nsmall = 0;
-        for (int r : deferred) { dirty[r] = 1; ++ndirty; }
-        for (int r = 0; r < nreg; ++r)
-            for (int t = de_off[r]; t < de_off[r + 1]; ++t) {
-                const DEdge& x = de[t];
-                if (root_of[x.dst] == r) continue;
-                if (never_final[x.src]) continue;
-                if (!dirty[r] && k4_change_matters(x.src, x.dst, win_first[x.src], std::min(win_last[x.src], del_cur[x.src]), del_prev[x.dst], del_cur[x.dst])) {
-                    dirty[r] = 1; ++ndirty;
-                    if (comp_ne[r] <= big) ++nsmall;
-                }
-            }
-        for (int v = 0; v < nreg; ++v) del_prev[v] = del_cur[v];      // (the walk resets the regions of its own component)
-        nsmall_prev = nsmall;
-        if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: sweep %d -> %d components to walk again\n", sweeps, ndirty);
-        if (!ndirty) break;
-    }
-    if (getenv("HOSTSIM_VERBOSE")) {
-        int mx = 0, nf = 0; for (int r = 0; r < nreg; ++r) { mx = std::max(mx, comp_ne[r]); nf += never_final[r]; }
-        fprintf(stderr, "hostsim: %d regions (%d never final), %zu edges, largest component %d directed edges, %d sweeps\n", nreg, nf, ue.size(), mx, sweeps + 1);
-    }
-    for (int r = 0; r < nrow_cap; ++r) if (row_emit[r] == K4_ROW_PENDING) k4_score_row(KS, KM, r);
-    // final order: stable by (window, BFS start vertex), slot order inside
+    if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: %d regions, %zu edges, %d call slots, %d sweeps\n", nreg, ue.size(), nrow_cap, sweeps + 1);
+    for (int r = 0; r < nrow_cap; ++r) if (row_emit[r] == K4_ROW_PENDING) k4_score_row(SS, KM, r);
+    // output order = slot order: slots are numbered window by window, and inside a window in the order of the calls
     std::vector<int> order;
     for (int r = 0; r < nrow_cap; ++r) if (row_emit[r] == K4_ROW_EMIT) order.push_back(r);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_key[a] < row_key[b]; });
 
     // ---- pack outputs ---------------------------------------------------------------------------
     memset(out, 0, sizeof(*out));

@@ -24,18 +24,18 @@ def test_stage_decomposition_matches_oracle(seed, od):
 
 
 WALK_VARIANTS = {
-    "pieces_for_every_component": dict(HOSTSIM_PIECES="0"),                       # the CTA walker's decomposition (k4_component_cta)
-    "pieces_and_deferral_of_big_components": dict(HOSTSIM_PIECES="6", HOSTSIM_BIG="8"),
-    "deferral_only": dict(HOSTSIM_BIG="4"),
+    "jacobi_sweeps_from_the_guess": dict(),                                       # every region against the previous table
+    "in_place_sweeps_descending": dict(HOSTSIM_INPLACE="1"),                      # table rewritten while it is read, regions descending
     "no_starting_guess": dict(HOSTSIM_NO_GUESS="1"),                              # any starting table must converge to the same result
+    "in_place_no_guess": dict(HOSTSIM_INPLACE="1", HOSTSIM_NO_GUESS="1"),
 }
 
 
 @pytest.mark.parametrize("variant", list(WALK_VARIANTS))
 def test_connection_walk_variants_match_oracle(monkeypatch, variant):
-    """The decompositions of the connection walk that the CUDA path uses for large inputs, forced on small ones: window
-    pieces walked independently (in descending order) with the finality pass resolved afterwards, big components waiting for
-    the small ones, sweeps from an empty table. Dense config-3-shaped data (long followed-edge components) and sparse data."""
+    """The closed form of the connection walk (bdk_logic.h, K4 second formulation): the table of deletion windows as a fixed
+    point reached in any sweep order and from any starting table, windows evaluated independently (in descending order), calls
+    evaluated independently. Dense config-3-shaped data (long followed-edge chains) and sparse data."""
     import torch
     from breakdancer_b200 import synth_torch
     for k, v in WALK_VARIANTS[variant].items():
