@@ -80,12 +80,12 @@ struct bdk_ctx {
     DevBuf d_chunk[2][10];
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // finish() work space
-    DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region, d_alive,
-        d_freed, d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt, d_de_root,
-        d_parent, d_comp_ne, d_comp_strong, d_comp_fill, d_de_off, d_row_off,
-        d_deleted, d_de, d_de2, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_sort_k, d_sort_v, d_sort_k2, d_sort_v2, d_pois_l, d_pois_k, d_pois_o;
-    int k5_smem_rows = K5_SMEM_ROWS;   // tables up to this many row slots are ordered by the grid-wide rank sort
+    DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region,
+        d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt,
+        d_se, d_se2, d_wstart, d_wend, d_slot_base, d_sefl, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_pois_l, d_pois_k, d_pois_o;
     uint64_t d2h_bytes = 0;
+    uint32_t rows_guess = 0;      // rows the first result copy brings back (a second copy follows only when there are more)
+    uint32_t sort_single_max = 1u << 22;   // anomalous reads up to which the followed edges are sorted by one CTA (BDK_SORT_SINGLE_MAX)
     uint32_t n_slots = 0;
     void* h_pack = nullptr;       // pinned host block the row outputs + summary are copied into
     size_t h_pack_cap = 0;
@@ -111,14 +111,11 @@ struct bdk_ctx {
     int rank = 0, nranks = 1;
     uint32_t A_local = 0;             // anomalous reads of this rank's slice (c->A becomes the global count)
     uint64_t comm_bytes = 0;          // bytes this rank received in the exchanges of the last job
-    DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff, d_cuts;
-    DevBuf d_del_prev, d_del_cur, d_dirty, d_k4sync, d_win_range, d_never_final, d_big_list, d_ri;   // K4 sweeps: deletion-time tables, sweep stamps of the components, barrier / counters
+    DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff;
+    DevBuf d_del, d_stamp, d_k4sync, d_never_final, d_c1, d_ri;   // K4: table of deletion windows, sweep stamps, barrier / counters
     uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
-    uint32_t k4_cta_min = K4_CTA_MIN, k4_big_min = K4_BIG;   // BDK_K4_CTA_MIN / BDK_K4_BIG (tests)
-    int k4_maxr = K4C_MAXR;                   // BDK_K4_MAXR (tests)
-    bool k4_host_loop = false;                // BDK_K4_HOST_LOOP (tests): the per-phase launches also on a single GPU
-    std::vector<uint32_t> h_cuts;     // [2][nranks + 1] vertex / row-slot cuts of the last bdk_finish
+    bool k4_host_loop = false;                // BDK_K4_HOST_LOOP (tests): one launch per sweep instead of the persistent kernel
 };
 
 namespace {
@@ -395,12 +392,13 @@ void bdk_destroy(bdk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
     c->comm = nullptr;
-    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_cuts, &c->d_del_prev, &c->d_del_cur, &c->d_dirty, &c->d_k4sync, &c->d_win_range, &c->d_never_final, &c->d_big_list, &c->d_ri, &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
+    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_del, &c->d_stamp, &c->d_k4sync, &c->d_never_final, &c->d_c1, &c->d_ri,
+        &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
-        &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_alive, &c->d_freed, &c->d_mate, &c->d_sv_of_read,
-        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt, &c->d_de_root,
-        &c->d_parent, &c->d_comp_ne, &c->d_comp_strong, &c->d_comp_fill, &c->d_de_off, &c->d_row_off,
-        &c->d_deleted, &c->d_de, &c->d_de2, &c->d_queue, &c->d_rowpack, &c->d_outpack, &c->d_slot_order, &c->d_sort_hist, &c->d_sort_k, &c->d_sort_v, &c->d_sort_k2, &c->d_sort_v2, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
+        &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_mate, &c->d_sv_of_read,
+        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt,
+        &c->d_se, &c->d_se2, &c->d_wstart, &c->d_wend, &c->d_slot_base, &c->d_sefl, &c->d_queue, &c->d_rowpack, &c->d_outpack, &c->d_slot_order,
+        &c->d_sort_hist, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
@@ -525,18 +523,13 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         CUC(cudaMalloc(&c->d_carry_out.p, ncomp * 4)); c->d_carry_out.cap = ncomp * 4;
         {
             int k4bps = 0, nsm = kNumSMs;
-            CUC(cudaFuncSetAttribute(k4_sweeps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4CtaSmem)));
-            CUC(cudaFuncSetAttribute(k4_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4CtaSmem)));
-            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k4bps, k4_sweeps_kernel, K4_THREADS, sizeof(K4CtaSmem)));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k4bps, k4n_sweeps_kernel, K4_THREADS, 0));
             CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
             c->k4_grid_max = std::max(1, k4bps) * nsm;
             CUC(cudaMalloc(&c->d_k4sync.p, 64 + sizeof(K4Trace))); c->d_k4sync.cap = 64 + sizeof(K4Trace);
         }
-        if (const char* e = getenv("BDK_K4_CTA_MIN")) c->k4_cta_min = (uint32_t)std::max(0, atoi(e));
-        if (const char* e = getenv("BDK_K4_BIG")) c->k4_big_min = (uint32_t)std::max(0, atoi(e));
         if (const char* e = getenv("BDK_K4_HOST_LOOP")) c->k4_host_loop = atoi(e) != 0;
-        if (const char* e = getenv("BDK_K4_MAXR")) c->k4_maxr = std::max(0, std::min(atoi(e), (int)K4C_MAXR));
-        if (const char* e = getenv("BDK_K5_SMEM_ROWS")) c->k5_smem_rows = std::max(0, std::min(atoi(e), (int)K5_SMEM_ROWS));   // tests: force the radix ordering path
+        if (const char* e = getenv("BDK_SORT_SINGLE_MAX")) c->sort_single_max = (uint32_t)std::max(0, atoi(e));   // tests: force either sort
         if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
     }
     int rc = reset_job(c);
@@ -663,14 +656,12 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     CU(cudaSetDevice(c->device));
     memset(out, 0, sizeof(*out));
     out->nkey = c->nkey;
-    const int nkey = c->nkey, nlib = c->P.nlib;
+    const int nkey = c->nkey, nlib = c->P.nlib, period = c->period;
     cudaStream_t st = c->stream;
     uint32_t* d_cnt = c->d_cnt.as<uint32_t>();
     int rc = run_finalize(c);     // multi-GPU: exchange 1 happens here, c->A becomes the global count
     if (rc) return rc;
     const uint32_t A = c->A;
-    NcclApi* nc = c->comm ? nccl_api() : nullptr;
-    const int N = c->nranks;
     c->h_sv.clear(); c->h_lib_count.clear(); c->h_cn_count.clear(); c->h_copy_number.clear();
     c->h_regions.clear(); c->h_areads.clear(); c->h_read_region.clear(); c->h_sv_of_read.clear();
     memset(c->h_cnt, 0, sizeof(c->h_cnt));
@@ -682,18 +673,19 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         out->sv = c->h_sv.data(); out->lib_count = c->h_lib_count.data(); out->cn_count = c->h_cn_count.data(); out->copy_number = c->h_copy_number.data();
         return 0;
     }
+    // Everything downstream is sized from A alone (regions <= A + 1, followed edges <= A / 2, call slots <= A / 2): no count
+    // comes back to the host before the result does.
     const size_t A1 = (size_t)A + 2;
     { int rc2 = grow_out(c, A1); if (rc2) return rc2; }
-    ENS(c->d_read_cand, A1 * 4); ENS(c->d_read_region, A1 * 4); ENS(c->d_alive, A1); ENS(c->d_freed, A1);
+    ENS(c->d_read_cand, A1 * 4); ENS(c->d_read_region, A1 * 4);
     ENS(c->d_mate, A1 * 4); ENS(c->d_sv_of_read, A1 * 4); ENS(c->d_cand_first, A1 * 4); ENS(c->d_cand_maxlen, A1 * 4);
     ENS(c->d_cand_info, A1 * sizeof(CandInfo)); ENS(c->d_reg, A1 * sizeof(RegionRec));
     uint32_t tsize = 1024; while (tsize < 2 * (uint64_t)A) tsize <<= 1;
     ENS(c->d_table, (size_t)tsize * 4);
-    const size_t L1 = (size_t)A / 2 + 2;
-    ENS(c->d_parent, A1 * 4); ENS(c->d_comp_ne, A1 * 4); ENS(c->d_comp_strong, A1 * 4); ENS(c->d_comp_fill, A1 * 4);
-    ENS(c->d_de_off, A1 * 4); ENS(c->d_row_off, A1 * 4); ENS(c->d_deleted, A1);
-    ENS(c->d_del_prev, A1 * 4); ENS(c->d_del_cur, A1 * 4); ENS(c->d_dirty, A1 * 4); ENS(c->d_win_range, A1 * 8); ENS(c->d_never_final, A1); ENS(c->d_big_list, A1 * 4); ENS(c->d_ri, A1 * sizeof(ReadInfo));
-    ENS(c->d_de, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_de2, (2 * L1 + 2) * sizeof(DEdge)); ENS(c->d_queue, (4 * L1 + 2 * A1 + 8) * 4);
+    const size_t nwin_cap = A1 / (size_t)period + 2;
+    ENS(c->d_del, A1 * 4); ENS(c->d_stamp, A1 * 4); ENS(c->d_never_final, A1); ENS(c->d_c1, A1 * 4); ENS(c->d_ri, A1 * sizeof(ReadInfo2));
+    ENS(c->d_se, A1 * 8); ENS(c->d_se2, A1 * 8); ENS(c->d_sefl, A1); ENS(c->d_queue, (A1 + nwin_cap) * 4);
+    ENS(c->d_wstart, nwin_cap * 4); ENS(c->d_wend, nwin_cap * 4); ENS(c->d_slot_base, nwin_cap * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
     const int dummy = dummy_region_of(c->P);
@@ -705,7 +697,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
                                                          c->P.seq_coverage_lim, c->d_cand_maxlen.as<int32_t>(), c->d_cand_info.as<CandInfo>());
     device_scan(st, AcceptFlag{c->d_cand_info.as<CandInfo>()},
                 RegionOut{c->d_ar.as<bdk_aread>(), c->d_cand_first.as<uint32_t>(), c->d_cand_info.as<CandInfo>(), d_cnt, c->d_reg.as<RegionRec>(),
-                          c->d_read_region.as<int32_t>(), c->d_alive.as<uint8_t>(), dummy, c->P.chr_restricted, c->P.min_read_pair},
+                          c->d_read_region.as<int32_t>(), dummy, c->P.chr_restricted, c->P.min_read_pair},
                 d_cnt + CNT_NCAND, d_cnt + CNT_NREG, (uint32_t)dummy, ssc);
     c->launches += 3 + 1 + 3;   // two scans (3 kernels each) + the candidate kernel
     tstop(c, T_K2);
@@ -714,265 +706,196 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     // ---- K3 ----------------------------------------------------------------------------------
     tstart(c, T_K3);
     uint32_t esize = 1024; while (esize < (uint64_t)A + 2) esize <<= 1;    // edge table: at most A / 2 distinct (region, region) keys
-    ENS(c->d_ekeys, (size_t)esize * 8); ENS(c->d_ecnt, (size_t)esize * 4); ENS(c->d_de_root, (2 * L1 + 2) * 4);
+    ENS(c->d_ekeys, (size_t)esize * 8); ENS(c->d_ecnt, (size_t)esize * 4);
     CU(cudaMemsetAsync(c->d_table.p, 0xff, (size_t)tsize * 4, st));
     CU(cudaMemsetAsync(c->d_mate.p, 0xff, (size_t)A * 4, st));
-    CU(cudaMemsetAsync(c->d_sv_of_read.p, 0xff, (size_t)A * 4, st));
-    CU(cudaMemsetAsync(c->d_freed.p, 0, A, st));
     CU(cudaMemsetAsync(c->d_ekeys.p, 0xff, (size_t)esize * 8, st));
     CU(cudaMemsetAsync(c->d_ecnt.p, 0, (size_t)esize * 4, st));
+    CU(cudaMemsetAsync(c->d_wstart.p, 0, nwin_cap * 4, st));
+    CU(cudaMemsetAsync(c->d_wend.p, 0, nwin_cap * 4, st));
     unsigned long long* ekeys = c->d_ekeys.as<unsigned long long>();
     uint32_t* ecnt = c->d_ecnt.as<uint32_t>();
     k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
     k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
-    k3_init_regions_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(), c->d_comp_strong.as<uint32_t>(),
-                                                           c->d_comp_fill.as<uint32_t>(), c->d_deleted.as<uint8_t>(), c->d_win_range.as<int2>(), d_cnt);
-    k3_union_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->P.min_read_pair);
-    k3_flatten_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_parent.as<int32_t>(), d_cnt);
-    k3_comp_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_comp_ne.as<uint32_t>(),
-                                                         c->d_comp_strong.as<uint32_t>(), c->P.min_read_pair);
-    device_scan(st, LoadU32{c->d_comp_ne.as<uint32_t>()}, ExclOut{c->d_de_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NDE, 0, ssc);
-    device_scan(st, LoadU32{c->d_comp_strong.as<uint32_t>()}, ExclOut{c->d_row_off.as<uint32_t>()}, d_cnt + CNT_NREG, d_cnt + CNT_NROW, 0, ssc);
-    k3_scatter_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->d_parent.as<int32_t>(), c->d_de_off.as<uint32_t>(),
-                                                            c->d_comp_fill.as<uint32_t>(), c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->period, c->d_win_range.as<int2>(), c->d_comp_ne.as<uint32_t>(), d_cnt);
-    k3_rank_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), c->d_de_root.as<int32_t>(), c->d_de_off.as<uint32_t>(),
-                                                         c->d_comp_ne.as<uint32_t>(), c->d_de2.as<DEdge>(), d_cnt);
-    c->launches += 2 + 4 + 3 + 3 + 2;   // join, links, init/union/flatten/count, 2 scans, scatter, rank
+    k3_read_info_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), c->d_read_cand.as<int32_t>(),
+        c->d_reg.as<RegionRec>(), d_cnt, period, c->P.min_read_pair, ekeys, ecnt, esize - 1, A, c->d_ri.as<ReadInfo2>(), c->d_sv_of_read.as<int32_t>());
+    k3_strong_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->P.min_read_pair, c->d_se.as<unsigned long long>(), d_cnt);
+    c->launches += 4;
+    // the followed edges in the order (window, src, dst)
+    int vbits = 1; while ((1ull << vbits) < (uint64_t)A + 2) ++vbits;
+    int wbits = 1; while ((1ull << wbits) < (uint64_t)nwin_cap + 1) ++wbits;
+    const SEdgeDigit digit{(vbits + 7) / 8, period};
+    const int npasses = 2 * digit.nbv + (wbits + 7) / 8;
+    unsigned long long* se_sorted;
+    if (A <= c->sort_single_max) {
+        WindowRangesEpilogue epi{period, c->d_wstart.as<int32_t>(), c->d_wend.as<int32_t>(), c->d_slot_base.as<int32_t>(), d_cnt + CNT_NROW};
+        sort_single_cta_kernel<<<1, SORT1_THREADS, 0, st>>>(c->d_se.as<unsigned long long>(), c->d_se2.as<unsigned long long>(), d_cnt + CNT_NSE, digit, npasses, epi);
+        se_sorted = (npasses & 1) ? c->d_se2.as<unsigned long long>() : c->d_se.as<unsigned long long>();
+        c->launches += 1;
+    } else {
+        ENS(c->d_sort_hist, 256 * SS_GRID * 4);
+        SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_se2.as<unsigned long long>()};
+        se_sorted = device_radix_sort(st, c->d_se.as<unsigned long long>(), d_cnt + CNT_NSE, digit, npasses, sosc);
+        device_scan(st, SEdgeUndirected{se_sorted}, WindowRangesOut{se_sorted, period, c->d_wstart.as<int32_t>(), c->d_wend.as<int32_t>(), c->d_slot_base.as<int32_t>()},
+                    d_cnt + CNT_NSE, d_cnt + CNT_NROW, 0, ssc);
+        c->launches += 3 * (uint64_t)npasses + 3;
+    }
     tstop(c, T_K3);
     CU(cudaGetLastError());
-    c->h_cuts.assign(2 * (size_t)(N + 1), 0);
-    if (c->comm) {   // which components this GPU walks, and which row slots they fill
-        ENS(c->d_cuts, 2 * (size_t)(N + 1) * 4);
-        comm_cuts_kernel<<<1, std::max(32, N + 1), 0, st>>>(c->d_de_off.as<uint32_t>(), c->d_row_off.as<uint32_t>(), d_cnt, N, c->d_cuts.as<uint32_t>());
-        c->launches += 1;
-        CU(cudaMemcpyAsync(c->h_cuts.data(), c->d_cuts.p, 2 * (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaMemcpyAsync(c->h_cnt, d_cnt, CNT_N * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    tcollect(c);
-    if (c->h_cnt[CNT_ERR] & K3_ERR_DUPNAME)
-        return fail(c, BDK_ERR_DATA, "a read-name key occurs more than twice among the anomalous reads");
-    const uint32_t nrow = c->h_cnt[CNT_NROW], nreg = c->h_cnt[CNT_NREG];
-    bool all_sorted = false;
-    if (c->h_cnt[CNT_NBIG]) {   // some component is too large for the rank sort: radix-sort all directed edges (see k3_edge_keys_kernel)
-        const uint32_t nde = c->h_cnt[CNT_NDE];
-        int vbits = 1; while ((1ull << vbits) < (uint64_t)nreg + 1) ++vbits;
-        int wbits = 1; while ((1ull << wbits) < (uint64_t)nreg / c->period + 2) ++wbits;
-        int obits = 1; while ((1ull << obits) < (uint64_t)nde + 1) ++obits;
-        if (2 * vbits + wbits <= 64) {
-            tstart(c, T_K3);
-            ENS(c->d_sort_hist, 256 * SS_GRID * 4);
-            ENS(c->d_sort_k, (size_t)(nde + 1) * 8); ENS(c->d_sort_v, (size_t)(nde + 1) * 4);
-            ENS(c->d_sort_k2, (size_t)(nde + 1) * 8); ENS(c->d_sort_v2, (size_t)(nde + 1) * 4);
-            unsigned long long* kk = c->d_sort_k2.as<unsigned long long>(); uint32_t* vv = c->d_sort_v2.as<uint32_t>();
-            SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_sort_k.as<unsigned long long>(), c->d_sort_v.as<uint32_t>()};
-            k3_edge_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), d_cnt, vbits, kk, vv);
-            device_radix_sort(st, &kk, &vv, d_cnt + CNT_NDE, 0, 2 * vbits + wbits, sosc);
-            k3_edge_segment_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(vv, c->d_de_root.as<int32_t>(), c->d_de_off.as<uint32_t>(), d_cnt, kk);
-            device_radix_sort(st, &kk, &vv, d_cnt + CNT_NDE, 0, obits, sosc);
-            k3_edge_gather_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_de.as<DEdge>(), vv, d_cnt, c->d_de2.as<DEdge>());
-            c->launches += 3 + 3 * (uint64_t)((2 * vbits + wbits + 7) / 8 + (obits + 7) / 8);
-            tstop(c, T_K3);
-            CU(cudaGetLastError());
-            // the ping-pong may have swapped the scratch pointers: they all stay owned by the same DevBufs (sizes are equal)
-            all_sorted = true;
-        }
-    }
 
     // ---- K4 ----------------------------------------------------------------------------------
-    // per-row outputs by slot (K4 writes them) and, after ordering, by output position (one block, one copy to a
-    // pinned host block that the result pointers then refer to: the host never touches the rows)
-    const size_t R1 = (size_t)nrow + 1;
+    // per-call outputs by slot (K4 writes them) and, after compaction, by output position (copied to a pinned host
+    // block that the result pointers then refer to: the host never touches the rows)
+    const size_t R1 = (size_t)A / 2 + 2;                       // call slots: one per followed edge
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_rows = 0, o_lc = al(o_rows + R1 * sizeof(bdk_sv)), o_cc = al(o_lc + R1 * 4 * nlib), o_cn = al(o_cc + R1 * 4 * nkey),
-                 o_n = al(o_cn + R1 * 4 * nkey), o_sum = al(o_n + 16), out_bytes = al(o_sum + sizeof(bdk_summary_t));   // ordered block (device + host)
-    const size_t w_emit = al(out_bytes), w_key = al(w_emit + R1), w_span = al(w_key + R1 * 8), w_ekey = al(w_span + R1 * 4 * nlib),
-                 w_eslot = al(w_ekey + R1 * 8), w_order = al(w_eslot + R1 * 4), w_tmpk = al(w_order + R1 * 4), w_tmpv = al(w_tmpk + R1 * 8),
-                 work_bytes = al(w_tmpv + R1 * 4);                                                                  // slot-indexed block
+                 out_bytes = al(o_cn + R1 * 4 * nkey);                                                             // compacted block (device)
+    const size_t w_emit = al(out_bytes), w_key = al(w_emit + R1), w_span = al(w_key + R1 * 8), work_bytes = al(w_span + R1 * 4 * nlib);   // slot-indexed block
     ENS(c->d_rowpack, work_bytes); ENS(c->d_outpack, out_bytes); ENS(c->d_slot_order, R1 * 4);
-    if (c->h_pack_cap < out_bytes) {
-        if (c->h_pack) cudaFreeHost(c->h_pack);
-        c->h_pack = nullptr; c->h_pack_cap = 0;
-        const size_t want = out_bytes * 5 / 4 + 4096;
-        CU(cudaHostAlloc(&c->h_pack, want, cudaHostAllocDefault));
-        c->h_pack_cap = want;
-    }
     char* dp = (char*)c->d_rowpack.p;
     char* op = (char*)c->d_outpack.p;
     CU(cudaMemsetAsync(dp + w_emit, 0, R1, st));
-    CU(cudaMemsetAsync(c->d_slot_order.p, 0xff, R1 * 4, st));
+    CU(cudaMemsetAsync(c->d_sefl.p, 0, A1, st));
+    K4N KS;
+    KS.ri = c->d_ri.as<ReadInfo2>(); KS.ar = c->d_ar.as<bdk_aread>(); KS.reg = c->d_reg.as<RegionRec>();
+    KS.nreg = 0; KS.period = period; KS.chr_restricted = c->P.chr_restricted; KS.min_read_pair = c->P.min_read_pair;
+    K4Tab Tb;
+    Tb.del = c->d_del.as<int32_t>(); Tb.stamp = c->d_stamp.as<uint32_t>(); Tb.never_final = c->d_never_final.as<uint8_t>(); Tb.c1 = c->d_c1.as<int32_t>();
+    Tb.summary = c->d_summary.as<bdk_summary_t>(); Tb.d_cnt = d_cnt;
     K4Static S;
-    S.ri = c->d_ri.as<ReadInfo>();
-    S.ar = c->d_ar.as<bdk_aread>(); S.read_region = c->d_read_region.as<int32_t>(); S.read_cand = c->d_read_cand.as<int32_t>();
-    S.mate = c->d_mate.as<int32_t>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
+    memset(&S, 0, sizeof S);
+    S.ar = c->d_ar.as<bdk_aread>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
     S.cand_maxlen = c->d_cand_maxlen.as<int32_t>(); S.lib_mean = c->d_lib_mean.as<float>();
     S.hist = (uint32_t*)((char*)c->d_acc.p + c->off_hist); S.density = c->d_density.as<float>();
-    S.A = A; S.nreg = 0; S.ncand = 0; S.period = c->period; S.nkey = nkey; S.nlib = nlib;
-    S.chr_restricted = c->P.chr_restricted; S.min_read_pair = c->P.min_read_pair; S.score_threshold = c->P.score_threshold;
-    S.fisher = c->P.fisher; S.covered_ref_len = 0;
-    S.root_of = c->d_parent.as<int32_t>(); S.del_prev = c->d_del_prev.as<int32_t>(); S.rerun = 0; S.never_final = c->d_never_final.as<uint8_t>();
+    S.A = A; S.period = period; S.nkey = nkey; S.nlib = nlib;
+    S.chr_restricted = c->P.chr_restricted; S.min_read_pair = c->P.min_read_pair; S.score_threshold = c->P.score_threshold; S.fisher = c->P.fisher;
     K4Mut M;
-    M.alive = c->d_alive.as<uint8_t>(); M.freed = c->d_freed.as<uint8_t>(); M.deleted = c->d_deleted.as<uint8_t>();
-    M.sv_of_read = c->d_sv_of_read.as<int32_t>(); M.rows = (bdk_sv*)(dp + o_rows); M.del_cur = c->d_del_cur.as<int32_t>();
-    M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + w_span);
-    M.row_cn_count = (uint32_t*)(dp + o_cc); M.row_cn = (float*)(dp + o_cn);
-    M.row_emit = (uint8_t*)(dp + w_emit); M.row_key = (uint64_t*)(dp + w_key);
-    uint64_t* emit_key = (uint64_t*)(dp + w_ekey); uint32_t* emit_slot = (uint32_t*)(dp + w_eslot);
+    M.rows = (bdk_sv*)(dp + o_rows); M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + w_span);
+    M.row_cn_count = (uint32_t*)(dp + o_cc); M.row_cn = (float*)(dp + o_cn); M.row_emit = (uint8_t*)(dp + w_emit);
+    uint64_t* row_key = (uint64_t*)(dp + w_key);
+    K4NOut KO{c->d_sv_of_read.as<int32_t>(), M.rows, M.row_lib_count, M.row_lib_span, M.row_emit, nlib};
     tstart(c, T_K4);
-    const uint32_t v_lo = c->comm ? c->h_cuts[c->rank] : 0u, v_hi = c->comm ? c->h_cuts[c->rank + 1] : 0xffffffffu;
     c->k4_sweeps = 0;
-    bool sweeps_on_device = false, k4_ran = false;
-    K4Graph G_score;
-    memset(&G_score, 0, sizeof G_score);
-    if (nrow || c->h_cnt[CNT_NDE]) {
-        k4_ran = true;
-        // Sweeps over the components (bdk_logic.h, K4Static): the first walks all of them against an empty table of
-        // deletion times; each later one walks again the components that looked, across an edge that is never followed, at a
-        // region whose deletion time changed. Stable table = the reference's sequential result.
-        K4Graph G;
-        G.comp_ne = c->d_comp_ne.as<uint32_t>(); G.comp_strong = c->d_comp_strong.as<uint32_t>(); G.de_off = c->d_de_off.as<uint32_t>();
-        G.row_off = c->d_row_off.as<uint32_t>(); G.de = c->d_de.as<DEdge>(); G.de_sorted = c->d_de2.as<DEdge>(); G.de_root = c->d_de_root.as<int32_t>();
-        G.queue = c->d_queue.as<int32_t>(); G.stamp = c->d_dirty.as<uint32_t>(); G.del_prev = c->d_del_prev.as<int32_t>(); G.win_range = c->d_win_range.as<int2>(); G.never_final = c->d_never_final.as<uint8_t>();
-        G.summary = c->d_summary.as<bdk_summary_t>(); G.d_cnt = d_cnt; G.v_lo = v_lo; G.v_hi = v_hi; G.all_sorted = all_sorted ? 1 : 0;
-        G.big_list = c->d_big_list.as<uint32_t>(); G.big_count = d_cnt + CNT_K4_NBIGLIST;
-        G.cta_min = c->k4_cta_min; G.big_min = c->k4_big_min; G.maxr = c->k4_maxr;
-        G.defer_first = getenv("BDK_K4_DEFER_FIRST") ? atoi(getenv("BDK_K4_DEFER_FIRST")) : 1;
-        G.trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
-        if (G.trace) CU(cudaMemsetAsync(G.trace, 0, sizeof(K4Trace), st));
-        CU(cudaMemsetAsync(d_cnt + CNT_K4_NBIGLIST, 0, 8, st));   // list length and the multi-GPU walk's cursor
-        k4_read_info_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S.ar, S.mate, S.read_region, S.read_cand, A, c->d_ri.as<ReadInfo>());
-        k4_guess_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G);     // starting table, cleared stamps
-        c->launches += 2;
-        G_score = G;
-        const bool mine = v_lo < std::min(v_hi, nreg);
-        const uint64_t want = mine ? div_up<uint64_t>(std::min(v_hi, nreg) - v_lo, 32 * (K4_THREADS / 32)) : 1;
-        const bool multi = c->comm && N > 1;
-        bool host_loop = multi || c->k4_host_loop;
-        if (!host_loop) {           // one persistent cooperative kernel, grid-wide barriers between the phases
-            uint32_t* sync = c->d_k4sync.as<uint32_t>();
-            CU(cudaMemsetAsync(sync, 0, 64, st));
-            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->k4_grid_max));
-            K4Trace* trace = G.trace;
-            void* args[] = {&S, &M, &G, &sync, &trace};
-            const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)k4_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, sizeof(K4CtaSmem), st);
+    bool sweeps_on_device = false;
+    uint32_t* sync = c->d_k4sync.as<uint32_t>();
+    K4Trace* trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
+    {
+        const unsigned rgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(A1, 32 * (K4_THREADS / 32)), (uint64_t)kNumSMs * 8));
+        k4n_init_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb);
+        c->launches += 1;
+        bool host_loop = c->k4_host_loop;
+        CU(cudaMemsetAsync(sync, 0, 64, st));
+        if (trace) CU(cudaMemsetAsync(trace, 0, sizeof(K4Trace), st));
+        if (!host_loop) {           // one persistent cooperative kernel, a grid-wide barrier between the sweeps
+            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(A1, 32 * (K4_THREADS / 32)), (uint64_t)c->k4_grid_max));
+            void* args[] = {&KS, &Tb, &sync, &trace};
+            const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)k4n_sweeps_kernel, dim3(grid), dim3(K4_THREADS), args, 0, st);
             if (ce == cudaSuccess) { c->launches += 1; sweeps_on_device = true; }
             else if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorNotSupported || ce == cudaErrorLaunchOutOfResources) {
-                cudaGetLastError();      // the GPU is shared (MPS, another context): the CTAs cannot all be resident. One launch per phase instead.
+                cudaGetLastError();      // the GPU is shared (MPS, another context): the CTAs cannot all be resident. One launch per sweep instead.
                 host_loop = true;
-            } else return fail(c, BDK_ERR_CUDA, "cudaLaunchCooperativeKernel(k4_sweeps_kernel) failed: %s", cudaGetErrorString(ce));
+            } else return fail(c, BDK_ERR_CUDA, "cudaLaunchCooperativeKernel(k4n_sweeps_kernel) failed: %s", cudaGetErrorString(ce));
         }
-        if (host_loop) {            // one launch per phase; multi-GPU: the owners' deletion times go to every rank in between
-            if (multi && !nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
-            const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)kNumSMs * 16));
+        if (host_loop) {
             for (uint32_t sweep = 0;; ++sweep) {
-                if (sweep > 100000) return fail(c, BDK_ERR_STATE, "connection walk did not reach a fixed point");
-                if (sweep) { CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 4, st)); CU(cudaMemsetAsync(d_cnt + CNT_K4_BIGCUR, 0, 4, st)); }
-                if (mine) { k4_components_kernel<<<grid, K4_THREADS, sizeof(K4CtaSmem), st>>>(S, M, G, sweep, d_cnt + CNT_K4_TICKET, d_cnt + CNT_K4_BIGCUR); c->launches += 1; }
-                if (multi) {
-                    NC(nc->AllReduce(c->d_del_cur.p, c->d_del_cur.p, nreg, ncclInt32, ncclMin, c->comm, st));   // K4_NEVER where not the owner
-                    c->comm_bytes += (uint64_t)nreg * 4;
-                }
-                CU(cudaMemsetAsync(d_cnt + CNT_NDIRTY, 0, 4, st));
-                k4_mark_dirty_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G, sweep, d_cnt + CNT_NDIRTY);
-                k4_next_sweep_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G, sweep);
-                c->launches += 2;
-                uint32_t ndirty = 0;
-                CU(cudaMemcpyAsync(&ndirty, d_cnt + CNT_NDIRTY, 4, cudaMemcpyDeviceToHost, st));
+                if (sweep > 1000000) return fail(c, BDK_ERR_STATE, "the table of deletion windows did not reach a fixed point");
+                CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 8, st));
+                k4n_sweep_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb, sweep, d_cnt + CNT_K4_TICKET, d_cnt + CNT_K4_CHANGED);
+                c->launches += 1;
+                uint32_t nchanged = 0;
+                CU(cudaMemcpyAsync(&nchanged, d_cnt + CNT_K4_CHANGED, 4, cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
                 c->k4_sweeps = sweep + 1;
-                if (!ndirty) break;
+                if (!nchanged) break;
             }
         }
+        k4n_first_call_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb);
+        const unsigned wgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(nwin_cap, K4W_THREADS), (uint64_t)kNumSMs * 16));
+        k4n_windows_kernel<<<wgrid, K4W_THREADS, 0, st>>>(Tb, se_sorted, c->d_wstart.as<int32_t>(), c->d_wend.as<int32_t>(), c->d_slot_base.as<int32_t>(),
+                                                          c->d_sefl.as<uint8_t>(), c->d_queue.as<int32_t>(), period, M.rows, row_key, M.row_emit);
+        const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(R1, K4_THREADS / 32), (uint64_t)kNumSMs * 8));
+        k4n_calls_kernel<<<cgrid, K4_THREADS, 0, st>>>(KS, KO, d_cnt);
+        k4_score_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, c->d_summary.as<bdk_summary_t>(), d_cnt);
+        c->launches += 4;
     }
-    if (k4_ran) { k4_score_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, G_score); c->launches += 1; }
     tstop(c, T_K4);
     CU(cudaGetLastError());
-    if (c->comm && nrow) {   // exchange 2: every rank's row slots (contiguous per rank) to every rank
-        if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
-        tstart(c, T_COMM2);
-        std::vector<uint64_t> s_cut(N + 1);
-        for (int p = 0; p <= N; ++p) s_cut[p] = c->h_cuts[(size_t)N + 1 + p];
-        NC(nc->GroupStart());
-        int rc2 = gather_ranges(c, nc, M.rows, sizeof(bdk_sv), s_cut.data());
-        if (!rc2) rc2 = gather_ranges(c, nc, M.row_lib_count, (size_t)4 * nlib, s_cut.data());
-        if (!rc2) rc2 = gather_ranges(c, nc, M.row_cn_count, (size_t)4 * nkey, s_cut.data());
-        if (!rc2) rc2 = gather_ranges(c, nc, M.row_cn, (size_t)4 * nkey, s_cut.data());
-        if (!rc2) rc2 = gather_ranges(c, nc, M.row_emit, 1, s_cut.data());
-        if (!rc2) rc2 = gather_ranges(c, nc, M.row_key, 8, s_cut.data());
-        NC(nc->GroupEnd());
-        if (rc2) return rc2;
-        tstop(c, T_COMM2);
-    }
 
     // ---- output order + results to the host -----------------------------------------------------------
     tstart(c, T_D2H);
-    // the emitted rows of the whole table, from the per-slot flags (arrival order does not matter: the ordering sorts by
-    // (window, BFS start vertex, slot))
-    comm_emit_list_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(M.row_emit, M.row_key, d_cnt, d_cnt + CNT_NEMIT, emit_key, emit_slot);
-    c->launches += 1;
-    uint32_t* order_slot = (uint32_t*)(dp + w_order);
-    if (nrow <= (uint32_t)c->k5_smem_rows) {
-        const unsigned g5 = (unsigned)std::max<uint32_t>(1, div_up<uint32_t>(nrow, K5_THREADS));      // nrow bounds the emitted rows
-        uint32_t* rank = (uint32_t*)(dp + w_tmpv);
-        CU(cudaMemsetAsync(rank, 0, R1 * 4, st));
-        k5_rank_partial_kernel<<<dim3(g5, g5), K5_THREADS, 0, st>>>(emit_key, emit_slot, d_cnt, rank);
-        k5_rank_scatter_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(emit_slot, rank, d_cnt, order_slot);
-        c->launches += 1;
-        c->launches += 1;
-    } else {   // large tables: stable LSD radix sort by slot, BFS start vertex, window
-        int sbits = 1; while ((1ull << sbits) < (uint64_t)nrow + 1) ++sbits;
-        int vbits = 1; while ((1ull << vbits) < (uint64_t)nreg + 1) ++vbits;
-        ENS(c->d_sort_hist, 256 * SS_GRID * 4);
-        // pass 1: by slot (as the key), carrying the key as ... the sort moves (u64 key, u32 value) pairs, so sort twice:
-        // first (key = slot, value = index), then (key = row key, value = slot) stably
-        unsigned long long* k1 = (unsigned long long*)(dp + w_tmpk);
-        uint32_t* v1 = (uint32_t*)(dp + w_tmpv);
-        k5_slot_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(emit_key, emit_slot, d_cnt + CNT_NEMIT, k1, v1);
-        unsigned long long* kk = k1; uint32_t* vv = v1;
-        ENS(c->d_sort_k, R1 * 8); ENS(c->d_sort_v, R1 * 4);
-        SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_sort_k.as<unsigned long long>(), c->d_sort_v.as<uint32_t>()};
-        device_radix_sort(st, &kk, &vv, d_cnt + CNT_NEMIT, 0, sbits, sosc);           // by slot
-        k5_row_keys_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(M.row_key, d_cnt + CNT_NEMIT, kk);   // kk[i] (= slot) -> row key, vv[i] = slot
-        device_radix_sort(st, &kk, &vv, d_cnt + CNT_NEMIT, 0, vbits, sosc);           // by BFS start vertex
-        device_radix_sort(st, &kk, &vv, d_cnt + CNT_NEMIT, 32, 32 + vbits, sosc);     // by window
-        k5_copy_u32_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(vv, order_slot, d_cnt + CNT_NEMIT);
-        c->launches += 3 + 3 * (uint64_t)((sbits + 7) / 8 + 2 * ((vbits + 7) / 8));
-    }
     RowPack in{M.rows, M.row_lib_count, M.row_cn_count, M.row_cn};
     RowPack outp{(bdk_sv*)(op + o_rows), (int32_t*)(op + o_lc), (uint32_t*)(op + o_cc), (float*)(op + o_cn)};
-    k5_gather_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(in, outp, order_slot, c->d_slot_order.as<int32_t>(), nlib, nkey, d_cnt, (uint32_t*)(op + o_n));
-    c->launches += 1;
+    device_scan(st, EmitFlag{M.row_emit}, GatherOut{in, outp, c->d_slot_order.as<int32_t>(), nlib, nkey}, d_cnt + CNT_NROW, d_cnt + CNT_NEMIT, 0, ssc);
+    c->launches += 3;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(op + o_sum, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToDevice, st));
-    if (sweeps_on_device) CU(cudaMemcpyAsync(op + o_n + 4, c->d_k4sync.as<uint32_t>() + 5, 4, cudaMemcpyDeviceToDevice, st));
+    // The number of rows is only known on the device: the first copy brings the counters, the summary and the first `guess`
+    // rows (sized from the previous job on this context, else from A); a second copy follows only if there are more.
+    const size_t guess = std::min<size_t>(R1, std::max<size_t>(c->rows_guess, (size_t)A / 64 + 1024));
+    auto host_layout = [&](size_t cap, size_t* h_lc, size_t* h_cc, size_t* h_cn, size_t* h_cnt, size_t* h_sum, size_t* h_sync) {
+        *h_lc = al(cap * sizeof(bdk_sv)); *h_cc = al(*h_lc + cap * 4 * nlib); *h_cn = al(*h_cc + cap * 4 * nkey);
+        *h_cnt = al(*h_cn + cap * 4 * nkey); *h_sum = al(*h_cnt + CNT_N * 4); *h_sync = al(*h_sum + sizeof(bdk_summary_t));
+        return al(*h_sync + 64);
+    };
+    size_t h_lc, h_cc, h_cn, h_cnt, h_sum, h_sync;
+    size_t cap = guess;
+    size_t host_bytes = host_layout(cap, &h_lc, &h_cc, &h_cn, &h_cnt, &h_sum, &h_sync);
+    auto ensure_host = [&](size_t bytes) -> int {
+        if (c->h_pack_cap >= bytes) return 0;
+        if (c->h_pack) cudaFreeHost(c->h_pack);
+        c->h_pack = nullptr; c->h_pack_cap = 0;
+        const size_t want = bytes * 5 / 4 + 4096;
+        CU(cudaHostAlloc(&c->h_pack, want, cudaHostAllocDefault));
+        c->h_pack_cap = want;
+        return 0;
+    };
+    { int rc2 = ensure_host(host_bytes); if (rc2) return rc2; }
     char* hp = (char*)c->h_pack;
-    CU(cudaMemcpyAsync(hp, op, out_bytes, cudaMemcpyDeviceToHost, st));
-    c->d2h_bytes = out_bytes;
+    auto copy_rows = [&](size_t from, size_t to) -> int {       // rows [from, to) of the four arrays
+        if (to <= from) return 0;
+        CU(cudaMemcpyAsync(hp + from * sizeof(bdk_sv), op + o_rows + from * sizeof(bdk_sv), (to - from) * sizeof(bdk_sv), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hp + h_lc + from * 4 * nlib, op + o_lc + from * 4 * nlib, (to - from) * 4 * nlib, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hp + h_cc + from * 4 * nkey, op + o_cc + from * 4 * nkey, (to - from) * 4 * nkey, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hp + h_cn + from * 4 * nkey, op + o_cn + from * 4 * nkey, (to - from) * 4 * nkey, cudaMemcpyDeviceToHost, st));
+        c->d2h_bytes += (to - from) * (sizeof(bdk_sv) + 4 * (size_t)nlib + 8 * (size_t)nkey);
+        return 0;
+    };
+    c->d2h_bytes = CNT_N * 4 + sizeof(bdk_summary_t) + 64;
+    CU(cudaMemcpyAsync(hp + h_cnt, d_cnt, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hp + h_sum, c->d_summary.p, sizeof(bdk_summary_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hp + h_sync, sync, 64, cudaMemcpyDeviceToHost, st));
+    { int rc2 = copy_rows(0, guess); if (rc2) return rc2; }
     tstop(c, T_D2H);
     CU(cudaStreamSynchronize(st));
     tcollect(c);
-    memcpy(&c->h_summary, hp + o_sum, sizeof(bdk_summary_t));
-    const size_t ns = *(const uint32_t*)(hp + o_n);
-    if (sweeps_on_device) c->k4_sweeps = *(const uint32_t*)(hp + o_n + 4);
-    if (sweeps_on_device && getenv("BDK_K4_TRACE")) {
+    memcpy(c->h_cnt, hp + h_cnt, CNT_N * 4);
+    memcpy(&c->h_summary, hp + h_sum, sizeof(bdk_summary_t));
+    if (sweeps_on_device) c->k4_sweeps = ((const uint32_t*)(hp + h_sync))[7];
+    if (c->h_cnt[CNT_ERR] & K3_ERR_DUPNAME)
+        return fail(c, BDK_ERR_DATA, "a read-name key occurs more than twice among the anomalous reads");
+    const size_t ns = c->h_cnt[CNT_NEMIT];
+    if (c->h_cnt[CNT_NROW] > R1 || c->h_cnt[CNT_NSE] > A1) return fail(c, BDK_ERR_STATE, "internal: more followed edges than reads");
+    if (ns > cap) {            // more rows than the first copy brought: lay the host block out again and fetch everything
+        cap = ns;
+        host_bytes = host_layout(cap, &h_lc, &h_cc, &h_cn, &h_cnt, &h_sum, &h_sync);
+        { int rc2 = ensure_host(host_bytes); if (rc2) return rc2; }
+        hp = (char*)c->h_pack;
+        { int rc2 = copy_rows(0, ns); if (rc2) return rc2; }
+        CU(cudaStreamSynchronize(st));
+    }
+    c->rows_guess = (uint32_t)std::min<size_t>(ns + ns / 8 + 64, 0xffffffffu);
+    if (sweeps_on_device && trace) {
         K4Trace tr;
-        CU(cudaMemcpy(&tr, (char*)c->d_k4sync.p + 64, sizeof tr, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "bdk K4 trace: %u regions, %u directed edges, %u row slots, %u sweeps\n", nreg, c->h_cnt[CNT_NDE], nrow, c->k4_sweeps);
+        CU(cudaMemcpy(&tr, trace, sizeof tr, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "bdk K4 trace: %u regions, %u directed followed edges, %u call slots, %u sweeps\n", c->h_cnt[CNT_NREG], c->h_cnt[CNT_NSE], c->h_cnt[CNT_NROW], c->k4_sweeps);
         for (uint32_t sw = 0; sw < std::min<uint32_t>(c->k4_sweeps, K4_TRACE_SWEEPS); ++sw)
-            fprintf(stderr, "  sweep %2u: walk %7.1f us  mark %6.1f us  next %6.1f us  -> %u components to walk again\n", sw,
-                    (tr.t[1 + 3 * sw] - tr.t[3 * sw]) / 1e3, (tr.t[2 + 3 * sw] - tr.t[1 + 3 * sw]) / 1e3, (tr.t[3 + 3 * sw] - tr.t[2 + 3 * sw]) / 1e3, tr.ndirty[sw]);
-        if (tr.cta_windows)
-            fprintf(stderr, "  CTA walks of big components: %llu candidates passed their last 32 reads, %llu further 32-read chunks scanned, largest such region %llu reads\n",
-                    tr.cta_survivors, tr.cta_chunks, tr.cta_maxreads),
-            fprintf(stderr, "  CTA walks of big components: %llu windows, %llu pieces, %llu candidates, %llu rounds; ms: stage %.2f runs %.2f labels %.2f pieces %.2f walk %.2f final %.2f resolve %.2f\n",
-                    tr.cta_windows, tr.cta_pieces, tr.cta_cands, tr.cta_rounds, tr.cta[0] / 1e6, tr.cta[1] / 1e6, tr.cta[2] / 1e6, tr.cta[3] / 1e6, tr.cta[4] / 1e6, tr.cta[5] / 1e6, tr.cta[6] / 1e6);
+            fprintf(stderr, "  sweep %2u: %7.1f us -> %u regions changed\n", sw, (tr.t[1 + sw] - tr.t[sw]) / 1e3, tr.nchanged[sw]);
     }
     c->h_sv_of_read.assign(1, -2);   // marker: not fetched yet
-    c->n_slots = nrow;
+    c->n_slots = c->h_cnt[CNT_NROW];
     c->finished = true;
     out->n_sv = ns;
-    out->sv = (const bdk_sv*)(hp + o_rows); out->lib_count = (const int32_t*)(hp + o_lc); out->cn_count = (const uint32_t*)(hp + o_cc);
-    out->copy_number = (const float*)(hp + o_cn); out->nkey = nkey;
+    out->sv = (const bdk_sv*)hp; out->lib_count = (const int32_t*)(hp + h_lc); out->cn_count = (const uint32_t*)(hp + h_cc);
+    out->copy_number = (const float*)(hp + h_cn); out->nkey = nkey;
     return 0;
 }
 
@@ -1012,12 +935,6 @@ int bdk_get_support(bdk_ctx* c, const int32_t** sv_of_read, uint64_t* n) {
     CU(cudaSetDevice(c->device));
     if (c->h_sv_of_read.size() == 1 && c->h_sv_of_read[0] == -2) {
         std::vector<int32_t> slots(c->A), slot_order(c->n_slots);
-        if (c->comm && c->A) {   // every read was consumed on the rank that walked its component (-1 elsewhere). Collective.
-            NcclApi* nc = nccl_api();
-            if (!nc) return fail(c, BDK_ERR_NCCL, "%s", nccl_api_error());
-            NC(nc->AllReduce(c->d_sv_of_read.p, c->d_sv_of_read.p, c->A, ncclInt32, ncclMax, c->comm, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-        }
         if (c->A) CU(cudaMemcpy(slots.data(), c->d_sv_of_read.p, (size_t)c->A * 4, cudaMemcpyDeviceToHost));
         if (c->n_slots) CU(cudaMemcpy(slot_order.data(), c->d_slot_order.p, (size_t)c->n_slots * 4, cudaMemcpyDeviceToHost));
         for (auto& s : slots) s = (s >= 0 && (size_t)s < slot_order.size()) ? slot_order[s] : -1;

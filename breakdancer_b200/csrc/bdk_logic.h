@@ -7,7 +7,7 @@
 //   classify_record    IlluminaPEReadClassifier.cpp:13-101, Alignment.hpp:72-159,
 //                      BamSummary.cpp:70-113 (pass 1), BreakDancer.cpp:150-207 (pass 2)
 //   poisson_log_sf     boost poisson complement cdf as used by ComputeProbScore, BreakDancer.cpp:62-68
-//   k4_*               build_connection / process_sv / SvBuilder / is_region_final / clear_region,
+//   k4n_* / k4_*       build_connection / process_sv / SvBuilder / is_region_final / clear_region,
 //                      BreakDancer.cpp:266-512, SvBuilder.cpp:18-118, ReadRegionData.cpp:70-175
 #pragma once
 #include <stdint.h>
@@ -235,35 +235,8 @@ struct RegionRec {            // BasicRegion + bookkeeping
     int32_t cand;             // index of the candidate region it came from (time stamp)
 };
 
-struct DEdge {                // directed copy of one graph edge inside its flush window
-    int32_t win, src, dst, w;
-    int32_t flags;            // bit0: edge erased, bit1 (on the first edge of a src run): vertex erased
-};
-enum { DE_ERASED = 1, DE_VERASED = 2 };
-
-// Everything the walk needs to know about a read that never changes, in one 16-byte load: the walk is a chain of
-// dependent loads, and mate -> mate's region -> mate's candidate were three of its links.
-struct alignas(16) ReadInfo {
-    int32_t mate;          // index of the mate in the anomalous-read stream, or -1
-    int32_t mate_region;   // region of the mate, or -1 (collapsed candidate / no mate)
-    int32_t mate_cand;     // candidate region of the mate
-    uint32_t meta;         // bdk_aread::meta of the read itself
-};
-BDK_HD ReadInfo make_read_info(const bdk_aread* ar, const int32_t* mate, const int32_t* read_region, const int32_t* read_cand, int j) {
-    ReadInfo r;
-    r.mate = mate[j];
-    r.mate_region = r.mate >= 0 ? read_region[r.mate] : -1;
-    r.mate_cand = r.mate >= 0 ? read_cand[r.mate] : 0;
-    r.meta = ar[j].meta;
-    return r;
-}
-
-struct K4Static {
-    const ReadInfo* ri;           // [A]
+struct K4Static {                 // what the scoring of a call needs (k4_score_row)
     const bdk_aread* ar;
-    const int32_t* read_region;   // region index or -1 (collapsed)
-    const int32_t* read_cand;     // candidate index
-    const int32_t* mate;          // mate read index or -1
     const RegionRec* reg;
     const uint32_t* P;            // [A][nkey] inclusive proper-pair prefix counts per key
     const int32_t* cand_maxlen;   // [ncand] _max_readlen when the candidate was closed
@@ -274,36 +247,20 @@ struct K4Static {
     int32_t nreg, ncand, period, nkey, nlib;
     int32_t chr_restricted, min_read_pair, score_threshold, fisher;
     uint32_t covered_ref_len;
-    // Components are the connected components over the edges the walk can FOLLOW (weight >= -r). A weaker edge
-    // couples two components only through is_region_final(): "has the mate's region been cleared by now?". That
-    // one bit per region is read from a table of deletion times (the flush window in which the region was
-    // cleared) left by the previous sweep over the components; sweeps are repeated for the components whose
-    // inputs changed until the table is stable (a fixed point is the sequential result, because every event
-    // depends only on strictly earlier events).
-    const int32_t* root_of;       // [nreg] component root of a region
-    const int32_t* del_prev;      // [nreg] window in which the region was cleared according to the previous sweep (K4_NEVER: not)
-    int32_t rerun;                // 0: first sweep (state initialised by the caller); 1: the walk first resets its component
-    const uint8_t* never_final;   // [nreg] the region holds a read that can never be paired or dropped: is_region_final is false forever
 };
 constexpr int32_t K4_NEVER = 0x7f7f7f7f;   // byte pattern 0x7f: tables are initialised with memset
 
-struct K4Mut {
-    uint8_t* alive;         // [A] read still in its region's vector
-    uint8_t* freed;         // [A] name erased by erase_read (set on both mates)
-    uint8_t* deleted;       // [nreg] clear_region() happened
-    int32_t* del_cur;       // [nreg] window in which it happened (K4_NEVER: not), written by the region's own component
-    int32_t* sv_of_read;    // [A] row slot of the process_sv call that consumed the read, or -1
+struct K4Mut {                    // per call slot
     bdk_sv* rows;           // [nrow_cap]
     int32_t* row_lib_count; // [nrow_cap][nlib]
     int32_t* row_lib_span;  // [nrow_cap][nlib]
     uint32_t* row_cn_count; // [nrow_cap][nkey]
     float* row_cn;          // [nrow_cap][nkey]
     uint8_t* row_emit;      // [nrow_cap] K4_ROW_*
-    uint64_t* row_key;      // [nrow_cap] (window << 32 | BFS start vertex)
 };
 
 struct WindowInfo { int32_t cF; int32_t maxlen; int32_t last_region; int32_t w; };
-enum { K4_ROW_NONE = 0, K4_ROW_EMIT = 1, K4_ROW_PENDING = 2 };   // row_emit[]: no call / call to print / walked, not scored yet
+enum { K4_ROW_NONE = 0, K4_ROW_EMIT = 1, K4_ROW_PENDING = 2 };   // row_emit[]: no call / call to print / pairs counted, not scored yet
 
 BDK_HD WindowInfo k4_window_info(const K4Static& S, int w) {
     WindowInfo wi;
@@ -319,76 +276,6 @@ BDK_HD WindowInfo k4_window_info(const K4Static& S, int w) {
         wi.last_region = S.nreg - 1;
     }
     return wi;
-}
-
-// _read_regions.find(name) != end for read j (R = S.ri[j]) at the flush whose trigger candidate is cF
-BDK_HD bool k4_exists(const ReadInfo& R, const K4Mut& M, int j, int cF) {
-    const int m = R.mate;
-    if (m < 0) return true;
-    if (R.mate_region < 0)          // mate sat in a collapsed candidate: its collapse erased the name
-        return !(m > j && R.mate_cand < cF);
-    return !M.freed[j];
-}
-
-// _read_regions[name].size() == 2, asked while region v (the region of read j) is checked at the end of window w
-BDK_HD bool k4_size2(const K4Static& S, const ReadInfo& R, const K4Mut& M, int j, int v, int cF, int w) {
-    const int m = R.mate;
-    if (m < 0) return false;
-    const int rm = R.mate_region;
-    if (rm < 0) return false;
-    if (R.mate_cand > cF) return false;         // mate's region not registered yet
-    if (M.freed[j]) return false;
-    bool rm_deleted;
-    if (S.root_of[rm] == S.root_of[v]) rm_deleted = M.deleted[rm] != 0;      // same component: the walk's own state
-    else {                                        // other component: cleared before (w, v) in the reference's order?
-        const int dw = S.del_prev[rm];            // (windows in order; inside a window the active nodes ascending)
-        rm_deleted = dw < w || (dw == w && rm < v);
-    }
-    // M.alive[m] of another component's read never changes: the pair hangs on an edge that is never followed
-    if (rm_deleted && M.alive[m]) return false;  // clear_region(rm) dropped rm from the entry
-    return true;
-}
-
-// Does it matter to region v (checked by is_region_final in its active windows [wf, wl], wl already capped by v's own
-// deletion) that region rm's deletion window moved from `a` to `b`? k4_size2 asks "rm cleared before (w, v)", i.e.
-// d < w || (d == w && rm < v), which is monotone in w: the answers for a and b differ exactly for the windows between the
-// first one that sees the earlier deletion and the last one that does not see the later.
-BDK_HD bool k4_change_matters(int v, int rm, int wf, int wl, int a, int b) {
-    if (a == b) return false;
-    const int lo = a < b ? a : b, hi = a < b ? b : a;
-    const int tie = rm < v ? 0 : 1;
-    const int w0 = lo + tie, w1 = hi + tie - 1;        // windows w with before(lo, w) && !before(hi, w)
-    const int f = wf > w0 ? wf : w0, l = wl < w1 ? wl : w1;
-    return f <= l;
-}
-
-// Starting value of the deletion-time table (any table converges to the same fixed point; a good guess saves sweeps): a
-// region whose stored reads all have their mate in a registered region is usually cleared in the last window in which it
-// has an edge (by then every mate is registered); a region holding a read without such a mate is never cleared.
-BDK_HD int k4_guess_deletion(const K4Static& S, const uint8_t* alive, int v, int win_last) {
-    if (win_last < 0 || v == S.nreg - 1) return K4_NEVER;
-    const RegionRec& R = S.reg[v];
-    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) {
-        if (!alive[j]) continue;
-        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
-        const int m = S.mate[j];
-        if (m < 0 || S.read_region[m] < 0) return K4_NEVER;
-    }
-    return win_last;
-}
-
-// A stored read whose mate is not in the anomalous stream at all, or sits EARLIER in a collapsed candidate, keeps its
-// name entry forever with a single region in it (k4_exists stays true, so process_sv never drops it, and it has no
-// partner to be consumed with): is_region_final(v) is false in every window. `alive` = the initial stored flags.
-BDK_HD bool k4_never_final(const K4Static& S, const uint8_t* alive, int v) {
-    const RegionRec& R = S.reg[v];
-    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) {
-        if (!alive[j]) continue;
-        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
-        const int m = S.mate[j];
-        if (m < 0 || (S.read_region[m] < 0 && m < j)) return true;
-    }
-    return false;
 }
 
 // ---- execution policy of the connection walk --------------------------------------------------
@@ -422,139 +309,7 @@ struct WarpTeam {
 };
 #endif
 
-// does read j keep its region from being final (is_region_final's per-read test)?
-BDK_HD bool k4_read_blocks_final(const K4Static& S, const K4Mut& M, int j, int v, const WindowInfo& wi) {
-    if (!M.alive[j]) return false;
-    const ReadInfo R = S.ri[j];
-    if (S.chr_restricted && meta_flag(R.meta) == BDK_ARP_CTX) return false;
-    return !k4_exists(R, M, j, wi.cF) || !k4_size2(S, R, M, j, v, wi.cF, wi.w);
-}
-
-template <class Team>
-BDK_HD bool k4_region_final(const Team& T, const K4Static& S, const K4Mut& M, int v, const WindowInfo& wi) {
-    if (M.deleted[v] || v == wi.last_region) return false;
-    const RegionRec& R = S.reg[v];
-    // A team-wide chunk of reads at a time, stopping at the first blocking read. From the END of the region: the reads whose
-    // mates lie ahead (in regions that are not registered yet) are its last ones, so a region that is not final is usually
-    // found out in the first chunk.
-    for (int j1 = R.first_read + R.n_reads; j1 > R.first_read; j1 -= T.width()) {
-        const int j = j1 - 1 - T.lane();
-        const bool bad = j >= R.first_read && k4_read_blocks_final(S, M, j, v, wi);
-        if (T.any(bad)) return false;
-    }
-    return true;
-}
-
-// read y (Ry = S.ri[y]) is the later mate of a pair (x, y) whose both reads are still held by regions s0 / s1
-BDK_HD int k4_pair_of(const ReadInfo& Ry, const K4Mut& M, int y, int s0, int s1) {
-    const int x = Ry.mate;
-    if (x < 0 || x >= y) return -1;
-    const int rx = Ry.mate_region;
-    if ((rx != s0 && rx != s1) || rx < 0) return -1;
-    // x comes earlier in the reference's scan order, so by the time y is looked at x has already been
-    // dropped if its name no longer exists (BreakDancer.cpp:367-375 via SvBuilder's observe loop). The mate of x is y, which
-    // sits in a registered region, so "the name of x exists" is just "not freed".
-    if (!M.alive[x] || M.freed[x]) return -1;
-    return x;
-}
-
-// process_sv for snodes = {s0, s1} (s1 < 0: single region). Returns true if a row was emitted
-// into slot `row` (valid on lane 0).
-template <class Team>
-BDK_HD bool k4_process_sv(const Team& T, const K4Static& S, K4Mut& M, int s0, int s1, int w, int v0, const WindowInfo& wi, int row) {
-    int n = s1 >= 0 ? 2 : 1;
-    int sn[2] = {s0, s1};
-    T.sync();
-    // pass 1: count pairs per flag (flag of the second-seen mate, SvBuilder.cpp:101-118). What is decided per read here
-    // (nothing / name gone: drop it / pair with x) is exactly what pass 2 acts on -- nothing changes in between, and inside
-    // pass 2 a read is only touched by its own lane and by the lane of its later mate, which write the same values -- so when
-    // every lane has at most K4_DEC reads the decisions are kept and pass 2 issues no dependent loads of its own.
-    constexpr int K4_DEC = 6;
-    int dec[K4_DEC];                 // x >= 0: pair (x, y); -1: nothing; -2: drop y
-    uint32_t dmeta[K4_DEC];
-    int32_t dabs[K4_DEC];
-    int iters = 0;
-    for (int i = 0; i < n; ++i) iters += (S.reg[sn[i]].n_reads + T.width() - 1) / T.width();
-    const bool keep = iters <= K4_DEC;
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0, c9 = 0, c10 = 0;
-    int it = 0;
-    for (int i = 0; i < n; ++i) {
-        const RegionRec& R = S.reg[sn[i]];
-        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width(), ++it) {
-            int d = -1; uint32_t my = 0; int32_t ab = 0;
-            if (M.alive[y]) {
-                const ReadInfo Ry = S.ri[y];
-                if (!k4_exists(Ry, M, y, wi.cF)) d = -2;
-                else {
-                    d = k4_pair_of(Ry, M, y, s0, s1);
-                    if (d >= 0) {
-                        my = Ry.meta; ab = S.ar[y].abs_isize;
-                        int f = meta_flag(my);
-                        c0 += f == 0; c1 += f == 1; c2 += f == 2; c3 += f == 3; c4 += f == 4; c5 += f == 5;
-                        c6 += f == 6; c7 += f == 7; c8 += f == 8; c9 += f == 9; c10 += f == 10;
-                    }
-                }
-            }
-            if (keep) { dec[it] = d; dmeta[it] = my; dabs[it] = ab; }
-        }
-    }
-    int flag_counts[BDK_NUM_FLAGS] = {T.sum(c0), T.sum(c1), T.sum(c2), T.sum(c3), T.sum(c4), T.sum(c5),
-                                      T.sum(c6), T.sum(c7), T.sum(c8), T.sum(c9), T.sum(c10)};
-    int num_pairs = 0;
-    for (int i = 0; i < BDK_NUM_FLAGS; ++i) num_pairs += flag_counts[i];
-    int flag = BDK_NA, best = 0;
-    for (int i = 0; i < BDK_NUM_FLAGS; ++i)
-        if (flag_counts[i] > best) { best = flag_counts[i]; flag = i; }  // first maximum in enum order
-    bool early = num_pairs < S.min_read_pair || flag_counts[flag] < S.min_read_pair;
-    int32_t* lib_count = M.row_lib_count + (int64_t)row * S.nlib;
-    int32_t* lib_span = M.row_lib_span + (int64_t)row * S.nlib;
-    if (!early) for (int l = T.lane(); l < S.nlib; l += T.width()) { lib_count[l] = 0; lib_span[l] = 0; }
-    T.sync();
-    // pass 2: consume the pairs, drop reads whose name no longer exists. A read is touched only by its own
-    // lane and by the lane of its (later) mate, and both write the same values, so the lanes do not interfere.
-    it = 0;
-    for (int i = 0; i < n; ++i) {
-        const RegionRec& R = S.reg[sn[i]];
-        for (int y = R.first_read + T.lane(); y < R.first_read + R.n_reads; y += T.width(), ++it) {
-            int x; uint32_t my; int32_t ab;
-            if (keep) { x = dec[it]; my = dmeta[it]; ab = dabs[it]; }
-            else {
-                x = -1; my = 0; ab = 0;
-                if (M.alive[y]) {
-                    const ReadInfo Ry = S.ri[y];
-                    if (!k4_exists(Ry, M, y, wi.cF)) x = -2;
-                    else { x = k4_pair_of(Ry, M, y, s0, s1); if (x >= 0) { my = Ry.meta; ab = S.ar[y].abs_isize; } }
-                }
-            }
-            if (x == -2) { M.alive[y] = 0; continue; }
-            if (x < 0) continue;
-            // pair (x, y): remove_reads_in_region_if(is_supportive) (BreakDancer.cpp:367-368)
-            M.alive[x] = 0; M.alive[y] = 0;
-            M.sv_of_read[x] = row; M.sv_of_read[y] = row;
-            if (!early) {
-                M.freed[x] = 1; M.freed[y] = 1;     // erase_read at the end (BreakDancer.cpp:510-511)
-                if (meta_flag(my) == flag) {
-                    int l = meta_lib(my);
-                    T.add(lib_count + l, 1);
-                    T.add(lib_span + l, ab);
-                }
-            }
-        }
-    }
-    T.sync();
-    if (T.lane() != 0) return false;
-    // The walk goes on without the call itself: coordinates, copy number, size and the Poisson score do not feed back into
-    // the walk and are computed afterwards for all row slots at once (k4_score_row).
-    M.row_emit[row] = K4_ROW_NONE;
-    if (early) return false;
-    bdk_sv& o = M.rows[row];
-    o.region[0] = s0; o.region[1] = s1; o.flag = flag; o.num_pairs = flag_counts[flag]; o.window = w;
-    M.row_key[row] = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v0;       // the reference prints by (window, BFS start), calls of one BFS in slot order
-    M.row_emit[row] = K4_ROW_PENDING;
-    return true;
-}
-
-// Second half of process_sv for row slot `row` left PENDING by the walk (BreakDancer.cpp:377-497): breakpoint coordinates,
+// Second half of process_sv for row slot `row` left PENDING by k4n_call (BreakDancer.cpp:377-497): breakpoint coordinates,
 // copy number, size, ComputeProbScore, the -y cut. One thread per row.
 BDK_HD void k4_score_row(const K4Static& S, K4Mut& M, int row) {
     bdk_sv& o = M.rows[row];
@@ -809,7 +564,7 @@ BDK_HD int k4n_first_call(const Team& T, const K4N& S, const int32_t* del, int v
 // BFS from each, a tail's edges ascending, every live edge followed once (BreakDancer.cpp:280-338). Call k goes to
 // slot0 + k; returns the number of calls. A call is FIRST for one of its regions when no earlier call (in an earlier
 // window: c1[] < w, or earlier in this one) involved that region.
-struct SEdge { int32_t src, dst; };
+struct SEdge { int32_t dst, src; };   // as one u64: src << 32 | dst
 enum : uint8_t { SE_ERASED = 1, SE_VDONE = 2, SE_TOUCHED = 4 };
 enum : uint8_t { K4_ROW_CALL = 4, K4_ROW_FIRST0 = 8, K4_ROW_FIRST1 = 16 };   // row_emit[] of a slot between k4n_window_calls and k4n_call
 
@@ -933,213 +688,6 @@ BDK_HD void k4n_call(const Team& T, const K4N& S, const K4NOut& M, int row) {
     bdk_sv& o = M.rows[row];
     o.flag = flag; o.num_pairs = c[flag];
     M.row_emit[row] = K4_ROW_PENDING;
-}
-
-// ---- in-place heap sort of a component's directed edges by (win, src, dst) --------------------
-BDK_HD bool de_less(const DEdge& a, const DEdge& b) {
-    if (a.win != b.win) return a.win < b.win;
-    if (a.src != b.src) return a.src < b.src;
-    return a.dst < b.dst;
-}
-BDK_HD void de_sift(DEdge* e, int start, int end) {
-    int root = start;
-    while (2 * root + 1 <= end) {
-        int child = 2 * root + 1, sw = root;
-        if (de_less(e[sw], e[child])) sw = child;
-        if (child + 1 <= end && de_less(e[sw], e[child + 1])) sw = child + 1;
-        if (sw == root) return;
-        DEdge t = e[root]; e[root] = e[sw]; e[sw] = t;
-        root = sw;
-    }
-}
-BDK_HD void de_sort(DEdge* e, int n) {
-    for (int s = (n - 2) / 2; s >= 0; --s) de_sift(e, s, n - 1);
-    for (int end = n - 1; end > 0; --end) {
-        DEdge t = e[end]; e[end] = e[0]; e[0] = t;
-        de_sift(e, 0, end - 1);
-    }
-}
-
-// first edge index of the run of `src` inside [lo, hi) (sorted by src within one window), or -1
-BDK_HD int de_find_src(const DEdge* e, int lo, int hi, int src) {
-    int a = lo, b = hi;
-    while (a < b) { int m = (a + b) >> 1; if (e[m].src < src) a = m + 1; else b = m; }
-    return (a < hi && e[a].src == src) ? a : -1;
-}
-
-// One connected component (over all windows) of the region graph: its directed edges
-// e[0..ne) (sorted by (win, src, dst)), a queue scratch of ne + 2 ints, and row slots [row0, ...).
-// Walks the windows in order, doing for each what build_connection does for the part of the
-// graph that belongs to this component. Returns the number of row slots used.
-// All lanes of the team follow the same path; lane 0 alone writes the walk's state (edge flags,
-// queue, deleted[]), bracketed by sync() so that every lane reads the same values.
-// Sort a component's directed edges by (win, src, dst). Up to DE_RANK_SORT_MAX edges: rank sort spread over the
-// team (the keys are unique, so the rank of an edge is its final position) into `scratch`; beyond that the leader
-// heap-sorts in place. Returns the array that holds the sorted edges.
-constexpr int DE_RANK_SORT_MAX = 8192;
-template <class Team>
-BDK_HD DEdge* de_sort_team(const Team& T, DEdge* e, int ne, DEdge* scratch) {
-    T.sync();
-    if (ne <= 1) return e;
-    if (ne > DE_RANK_SORT_MAX || !scratch) {
-        if (T.lane() == 0) de_sort(e, ne);
-        T.sync();
-        return e;
-    }
-    for (int i = T.lane(); i < ne; i += T.width()) {
-        const DEdge x = e[i];
-        int r = 0;
-        for (int j = 0; j < ne; ++j) r += de_less(e[j], x) ? 1 : 0;
-        scratch[r] = x;
-    }
-    T.sync();
-    return scratch;
-}
-
-// One step of build_connection's outer loop: the BFS from vertex v (edge run e[vi..vend) inside the window e[i..j)) if v
-// still has an edge the walk would follow. Uses queue[0 .. edges reached + 1) and row slots row, row + 1, ...; returns the next
-// free row slot. Touches only the regions reachable from v over followable edges.
-template <class Team>
-BDK_HD int k4_bfs_from(const Team& T, const K4Static& S, K4Mut& M, DEdge* e, int i, int j, int w, const WindowInfo& wi, int vi, int vend,
-                       int32_t* queue, int row) {
-    const bool lead = T.lane() == 0;
-    const int v = e[vi].src;
-    bool live = false;          // v has an edge the BFS would follow; otherwise a BFS from v changes nothing
-    for (int k = vi; k < vend; ++k)
-        live = live || (!(e[k].flags & DE_ERASED) && e[k].w >= S.min_read_pair && !M.deleted[e[k].dst]);
-    if (!live || (e[vi].flags & DE_VERASED) || M.deleted[v]) return row;
-    // tails live in queue[qa..qb), newtails appended after
-    int qa = 0, qb = 0, qn;
-    T.sync();
-    if (lead) queue[0] = v;
-    T.sync();
-    qb = 1;
-    while (qa < qb) {
-        qn = qb;
-        for (int t = qa; t < qb; ++t) {
-            int tail = queue[t];
-            if (M.deleted[tail]) continue;                     // !region_exists(tail)
-            int ts = de_find_src(e, i, j, tail);
-            if (ts < 0 || (e[ts].flags & DE_VERASED)) continue; // graph.find(tail) == end
-            for (int k = ts; k < j && e[k].src == tail; ++k) {
-                if (e[k].flags & DE_ERASED) continue;
-                int s1 = e[k].dst, nlinks = e[k].w;
-                // An edge that is too weak or leads to a deleted region is erased without any other
-                // effect, and meeting it again (from either side, in this window) would again have no
-                // effect: it needs no mark. Only edges that are followed are erased both ways.
-                if (nlinks < S.min_read_pair || M.deleted[s1]) continue;
-                int rq = -1;
-                if (tail != s1) {                               // erase_edge(s1, tail)
-                    int rs = de_find_src(e, i, j, s1);
-                    if (rs >= 0)
-                        for (int q = rs; q < j && e[q].src == s1; ++q)
-                            if (e[q].dst == tail) { rq = q; break; }
-                }
-                T.sync();
-                if (lead) {
-                    e[k].flags |= DE_ERASED;
-                    if (rq >= 0) e[rq].flags |= DE_ERASED;
-                    queue[qn] = s1;                             // newtails.push_back(s1)
-                }
-                T.sync();
-                ++qn;
-                int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
-                k4_process_sv(T, S, M, a, tail != s1 ? b : -1, w, v, wi, row);
-                ++row;
-            }
-            T.sync();
-            if (lead) e[ts].flags |= DE_VERASED;                // graph.erase(tail)
-            T.sync();
-        }
-        qa = qb; qb = qn;
-    }
-    return row;
-}
-
-// a later sweep: one edge slot back to the state before the first one (and, once per run of a source, the region and its reads)
-BDK_HD void k4_reset_slot(const K4Static& S, K4Mut& M, DEdge* e, int q) {
-    e[q].flags = 0;
-    const int v = e[q].src;
-    if (q > 0 && e[q - 1].src == v) return;          // a region may have a run in several windows: all write the same values
-    M.deleted[v] = 0; M.del_cur[v] = K4_NEVER;
-    const RegionRec& R = S.reg[v];
-    for (int j = R.first_read; j < R.first_read + R.n_reads; ++j) { M.alive[j] = (uint8_t)R.stored; M.freed[j] = 0; M.sv_of_read[j] = -1; }
-}
-
-// build_connection for the part e[i..j) of one flush window that belongs to this component; returns the next free row slot
-template <class Team>
-BDK_HD int k4_window_seq(const Team& T, const K4Static& S, K4Mut& M, DEdge* e, int i, int j, int w, const WindowInfo& wi, int32_t* queue, int row) {
-    const bool lead = T.lane() == 0;
-    // outer loop over vertices ascending (graph.begin() .. end())
-    int vi = i;
-    while (vi < j) {
-        int vend = vi;
-        while (vend < j && e[vend].src == e[vi].src) ++vend;
-        row = k4_bfs_from(T, S, M, e, i, j, w, wi, vi, vend, queue, row);
-        vi = vend;
-    }
-    // is_region_final / clear_region over the active nodes, ascending
-    for (vi = i; vi < j;) {
-        int v = e[vi].src;
-        const bool fin = !S.never_final[v] && k4_region_final(T, S, M, v, wi);
-        T.sync();
-        if (fin && lead) { M.deleted[v] = 1; M.del_cur[v] = w; }
-        T.sync();
-        while (vi < j && e[vi].src == v) ++vi;
-    }
-    return row;
-}
-
-template <class Team>
-BDK_HD int k4_component(const Team& T, const K4Static& S, K4Mut& M, DEdge* e /* sorted by (win, src, dst) */, int ne, int32_t* queue, int row0, int nrows) {
-    T.sync();
-    if (S.rerun) {
-        for (int q = T.lane(); q < ne; q += T.width()) k4_reset_slot(S, M, e, q);
-        for (int r = T.lane(); r < nrows; r += T.width()) M.row_emit[row0 + r] = 0;
-        T.sync();
-    }
-    int row = row0;
-    int i = 0;
-    while (i < ne) {
-        int w = e[i].win;
-        int j = i;
-        while (j < ne && e[j].win == w) ++j;
-        row = k4_window_seq(T, S, M, e, i, j, w, k4_window_info(S, w), queue, row);
-        i = j;
-    }
-    return row - row0;
-}
-
-// ---- the same window, split into independent pieces (used for components too large for one sequential walk) --------
-// Inside one flush window the BFS trees that share no region do not interact: the window's graph falls into pieces
-// (connected over the edges the walk follows), each walked on its own, in any order or concurrently, with its own queue and
-// row slots (slot order only matters inside one BFS). The is_region_final pass over the active nodes is then evaluated for
-// all nodes against the state before the pass, and the ascending-order dependency (a node cleared earlier in the same pass
-// takes its reads' name entries along) is resolved afterwards:
-//   node v is cleared  <=>  it is final against the earlier state  and  no still-held read of v has its still-held mate in a
-//                            region rm < v that is cleared in this same pass.
-enum { K4_FIN_NOT = 0, K4_FIN_UNDECIDED = 1, K4_FIN_CLEARED = 2 };
-
-// dependencies of candidate v on the other candidates of this pass (cand[0..ncand) ascending, state[] their current state):
-// bit 0: some dependency is already cleared, bit 1: some dependency is still undecided
-template <class Team>
-BDK_HD int k4_final_deps(const Team& T, const K4Static& S, const K4Mut& M, int v, const int32_t* cand, const uint8_t* state, int ncand) {
-    const RegionRec& R = S.reg[v];
-    bool cleared = false, undecided = false;
-    for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
-        if (!M.alive[j]) continue;
-        if (S.chr_restricted && meta_flag(S.ar[j].meta) == BDK_ARP_CTX) continue;
-        const int m = S.mate[j];
-        if (m < 0 || !M.alive[m]) continue;
-        const int rm = S.read_region[m];
-        if (rm < 0 || rm >= v) continue;
-        int a = 0, b = ncand;                               // rm among the candidates?
-        while (a < b) { int mid = (a + b) >> 1; if (cand[mid] < rm) a = mid + 1; else b = mid; }
-        if (a >= ncand || cand[a] != rm) continue;
-        if (state[a] == K4_FIN_CLEARED) cleared = true;
-        else if (state[a] == K4_FIN_UNDECIDED) undecided = true;
-    }
-    return (T.any(cleared) ? 1 : 0) | (T.any(undecided) ? 2 : 0);
 }
 
 }  // namespace bdk

@@ -10,13 +10,10 @@
 //               min / max of (global record index, pos)); every rank rebases its anomalous-read stream
 //               (global record index, global inclusive proper-pair counts) straight into its slot of the
 //               global stream, and the slots are all-gathered over NVLink (one grouped NCCL call);
-//   replicated  K2 (regions) and K3 (mate join, edges, components) run on the global stream on every rank:
-//               region indices, flush windows and component roots are therefore global and identical;
-//   sharded     K4 (the latency-bound connection walk + scoring) is split by connected component: rank r walks the
-//               components whose root region lies in its vertex range (cut so that the directed-edge counts
-//               balance). Components never interact, and a component's row slots are contiguous, so
-//   exchange 2  is an all-gather of contiguous row-slot ranges; after it every rank orders and returns the
-//               complete SV table.
+//   replicated  K2 (regions) and K3 (mate join, edges) run on the global stream on every rank:
+//               region indices and flush windows are therefore global and identical;
+//   replicated  K4 as well (the table of deletion windows, the calls, the scores: a few hundred microseconds), so every
+//               rank returns the complete SV table and there is no second exchange.
 // NCCL is loaded with dlopen at the first use (a process that never attaches a communicator needs no NCCL).
 #pragma once
 #include <dlfcn.h>
@@ -99,40 +96,6 @@ __global__ void __launch_bounds__(GS_THREADS) comm_rebase_stream_kernel(const bd
         int4* dst = reinterpret_cast<int4*>(ar_g + i);
         dst[0] = lo; dst[1] = hi;
         for (int k = 0; k < nkey; ++k) P_g[(size_t)i * nkey + k] = P[(size_t)i * nkey + k] + koff[k];
-    }
-}
-
-// ---- K4 ownership -----------------------------------------------------------------------------------------
-// cuts[r] = first vertex of rank r (cuts[nranks] = nreg), chosen so that the directed-edge counts balance;
-// cuts[nranks + 1 + r] = first row slot of rank r (cuts[2 * nranks + 1] = nrow)
-__global__ void comm_cuts_kernel(const uint32_t* __restrict__ de_off, const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ d_cnt,
-                                 int nranks, uint32_t* __restrict__ cuts) {
-    const int r = threadIdx.x;
-    if (r > nranks) return;
-    const uint32_t nreg = d_cnt[CNT_NREG], nde = d_cnt[CNT_NDE], nrow = d_cnt[CNT_NROW];
-    uint32_t v;
-    if (r == 0) v = 0;
-    else if (r == nranks) v = nreg;
-    else {
-        const uint32_t target = (uint32_t)((unsigned long long)nde * (unsigned)r / (unsigned)nranks);
-        uint32_t lo = 0, hi = nreg;                      // first v with de_off[v] >= target
-        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (de_off[m] < target) lo = m + 1; else hi = m; }
-        v = lo;
-    }
-    cuts[r] = v;
-    cuts[nranks + 1 + r] = v < nreg ? row_off[v] : nrow;
-}
-
-// ---- exchange 2 -------------------------------------------------------------------------------------------
-// the emitted-row list of the whole table from the gathered per-slot flags (arrival order does not matter: the
-// ordering sorts by (window, BFS start vertex, slot))
-__global__ void __launch_bounds__(GS_THREADS) comm_emit_list_kernel(const uint8_t* __restrict__ row_emit, const uint64_t* __restrict__ row_key,
-        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ emit_count, uint64_t* __restrict__ emit_key, uint32_t* __restrict__ emit_slot) {
-    const uint32_t nrow = d_cnt[CNT_NROW];
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nrow; s += gridDim.x * blockDim.x) {
-        if (row_emit[s] != K4_ROW_EMIT) continue;
-        const uint32_t idx = atomicAdd(emit_count, 1u);
-        emit_key[idx] = row_key[s]; emit_slot[idx] = s;
     }
 }
 

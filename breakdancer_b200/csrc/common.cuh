@@ -40,6 +40,8 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
     uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 template <typename T>
 __host__ __device__ __forceinline__ T div_up(T a, T b) { return (a + b - 1) / b; }
 

@@ -2,10 +2,10 @@
 // (about 1-3 % of the records):
 //   K2  break flags -> candidate regions (segmented reductions) -> accepted regions
 //       (BreakDancer::push_read:209-241, process_breakpoint:244-264, ReadRegionData::add_region)
-//   K3  mate join by read-name key (hash table), region-region mate links, radix sort +
-//       run-length -> weighted edges (ReadRegionData.cpp:109-113, Graph.hpp:41-46)
-//   K4  connected components (lock-free union-find), per-component connection walk, SV
-//       evaluation and Poisson score (build_connection, process_sv, SvBuilder, ComputeProbScore)
+//   K3  mate join by read-name key (hash table), region-region mate links aggregated into weighted
+//       edges (ReadRegionData.cpp:109-113, Graph.hpp:41-46), followed edges sorted per flush window
+//   K4  table of region deletion windows (fixed point), calls per window, pairs per call, Poisson
+//       score (build_connection, process_sv, SvBuilder, is_region_final, ComputeProbScore)
 // All element counts stay on the device (d_cnt[]); kernels are grid-stride over fixed grids.
 #pragma once
 #include "common.cuh"
@@ -14,7 +14,7 @@
 
 namespace bdk {
 
-enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NLINK, CNT_NEDGE, CNT_NDE, CNT_NROW, CNT_ERR, CNT_NREG_REAL, CNT_K4_TICKET, CNT_NEMIT, CNT_NDIRTY, CNT_NBIG, CNT_K4_NBIGLIST, CNT_K4_BIGCUR, CNT_N };
+enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NSE, CNT_NROW, CNT_ERR, CNT_NEMIT, CNT_K4_TICKET, CNT_K4_CHANGED, CNT_N };
 constexpr uint32_t K3_ERR_DUPNAME = 1u;
 constexpr int GS_THREADS = 256;
 constexpr int GS_GRID = kNumSMs * 4;
@@ -72,11 +72,11 @@ struct AcceptFlag {
 };
 struct RegionOut {   // writes the region table and the read -> region map
     const bdk_aread* ar; const uint32_t* cand_first; const CandInfo* ci; const uint32_t* d_cnt;
-    RegionRec* reg; int32_t* read_region; uint8_t* alive; int32_t dummy, chr_restricted, min_read_pair;
+    RegionRec* reg; int32_t* read_region; int32_t dummy, chr_restricted, min_read_pair;
     __device__ void operator()(uint32_t c, uint32_t inc, uint32_t v, uint32_t ncand) const {
         const uint32_t A = d_cnt[CNT_A];
         const uint32_t s = cand_first[c], e = (c + 1 < ncand ? cand_first[c + 1] : A) - 1;
-        int32_t r = -1; uint8_t st = 0;
+        int32_t r = -1;
         if (v) {
             r = (int32_t)(inc - 1) + dummy;
             const CandInfo k = ci[c];
@@ -86,9 +86,8 @@ struct RegionOut {   // writes the region table and the read -> region map
             const int valid = chr_restricted ? k.nonctx : R.n_reads;
             R.stored = valid >= min_read_pair ? 1 : 0; R.cand = (int32_t)c;
             reg[r] = R;
-            st = (uint8_t)R.stored;
         }
-        for (uint32_t j = s; j <= e; ++j) { read_region[j] = r; alive[j] = st; }
+        for (uint32_t j = s; j <= e; ++j) read_region[j] = r;
         if (c == 0 && dummy) {   // region 0 of a run with -s < 0: registered from empty state
             RegionRec D; D.tid = -1; D.start = -1; D.end = -1; D.fwd = 0; D.rev = 0; D.first_read = 0; D.n_reads = 0; D.stored = 0; D.cand = -1;
             reg[0] = D;
@@ -144,511 +143,152 @@ __global__ void __launch_bounds__(GS_THREADS) k3_links_kernel(const int32_t* __r
     }
 }
 
-__device__ __forceinline__ int uf_find(int32_t* parent, int x) {
+// the weight of edge (r0 <= r1) from the link table (0: no such edge)
+__device__ __forceinline__ uint32_t k3_edge_weight(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t mask, int r0, int r1) {
+    const unsigned long long key = ((unsigned long long)(uint32_t)r0 << 32) | (uint32_t)r1;
+    uint32_t h = hash64(key) & mask;
     for (;;) {
-        int p = parent[x];
-        if (p == x) return x;
-        int gp = parent[p];
-        if (gp != p) parent[x] = gp;   // path halving (benign race: only ever points further up)
-        x = p;
-    }
-}
-__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
-    for (;;) {
-        a = uf_find(parent, a); b = uf_find(parent, b);
-        if (a == b) return;
-        if (a < b) { int t = a; a = b; b = t; }          // hook the larger root under the smaller
-        if (atomicCAS(parent + a, a, b) == a) return;
+        const unsigned long long k = tkeys[h];
+        if (k == key) return tcnt[h];
+        if (k == EDGE_EMPTY) return 0;
+        h = (h + 1) & mask;
     }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) k3_init_regions_kernel(int32_t* __restrict__ parent, uint32_t* __restrict__ comp_ne,
-        uint32_t* __restrict__ comp_strong, uint32_t* __restrict__ comp_fill, uint8_t* __restrict__ deleted, int2* __restrict__ win_range,
-        const uint32_t* __restrict__ d_cnt) {
-    const uint32_t nreg = d_cnt[CNT_NREG];
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nreg; r += gridDim.x * blockDim.x) {
-        parent[r] = (int32_t)r; comp_ne[r] = 0; comp_strong[r] = 0; comp_fill[r] = 0; deleted[r] = 0;
-        win_range[r] = make_int2(0x7fffffff, -1);      // first / last flush window in which the region has an edge
+// per-read static information for K4 (bdk_logic.h: ReadInfo2), one thread per anomalous read
+__global__ void __launch_bounds__(GS_THREADS) k3_read_info_kernel(const bdk_aread* __restrict__ ar, const int32_t* __restrict__ mate,
+        const int32_t* __restrict__ read_region, const int32_t* __restrict__ read_cand, const RegionRec* __restrict__ reg, const uint32_t* __restrict__ d_cnt,
+        int period, int min_read_pair, const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t mask, uint32_t A,
+        ReadInfo2* __restrict__ ri, int32_t* __restrict__ sv_of_read) {
+    const int nreg = (int)d_cnt[CNT_NREG];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A; j += gridDim.x * blockDim.x) {
+        const int m = mate[j];
+        bool strong = false;
+        if (m >= 0) {
+            const int rj = read_region[j], rm = read_region[m];
+            if (rj >= 0 && rm >= 0 && rj != rm) strong = (int)k3_edge_weight(tkeys, tcnt, mask, min(rj, rm), max(rj, rm)) >= min_read_pair;
+        }
+        ri[j] = k4n_make_read_info(ar, mate, read_region, read_cand, reg, nreg, period, (int)j, strong);
+        sv_of_read[j] = -1;
     }
 }
 
-// Components = connected components over the edges the connection walk can follow (weight >= -r): only those
-// couple two regions through shared reads. A weaker edge still makes both its ends "active" in its flush window
-// (is_region_final is asked for them) and is kept, as a directed copy, in the edge list of each end's component.
-__global__ void __launch_bounds__(GS_THREADS) k3_union_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
-                                                              int32_t* __restrict__ parent, int32_t min_read_pair) {
+// the followed edges (weight >= -r) as directed copies src << 32 | dst, in table order
+__global__ void __launch_bounds__(GS_THREADS) k3_strong_edges_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
+        int32_t min_read_pair, unsigned long long* __restrict__ se, uint32_t* __restrict__ d_cnt) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
         const unsigned long long k = tkeys[e];
         if (k == EDGE_EMPTY || (int32_t)tcnt[e] < min_read_pair) continue;
-        const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
-        if (r0 != r1) uf_union(parent, r0, r1);
+        const uint32_t r0 = (uint32_t)(k >> 32), r1 = (uint32_t)k;
+        const uint32_t n = r0 != r1 ? 2u : 1u;
+        const uint32_t at = atomicAdd(d_cnt + CNT_NSE, n);
+        se[at] = k;
+        if (n == 2) se[at + 1] = ((unsigned long long)r1 << 32) | r0;
     }
 }
 
-// parent[] -> root table (no unions after this)
-__global__ void __launch_bounds__(GS_THREADS) k3_flatten_kernel(int32_t* __restrict__ parent, const uint32_t* __restrict__ d_cnt) {
-    const uint32_t nreg = d_cnt[CNT_NREG];
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nreg; r += gridDim.x * blockDim.x) {
-        int x = (int)r;
-        for (int p = parent[x]; p != x; p = parent[x]) x = p;      // roots never change any more; concurrent writers store roots
-        parent[r] = x;
+// radix digits of a directed edge for the order (window, src, dst): nbv bytes of dst, nbv bytes of src, then the window
+struct SEdgeDigit {
+    int nbv, period;
+    __device__ __forceinline__ uint32_t operator()(unsigned long long k, int pass) const {
+        if (pass < nbv) return (uint32_t)(k >> (8 * pass)) & 0xffu;
+        if (pass < 2 * nbv) return (uint32_t)(k >> (32 + 8 * (pass - nbv))) & 0xffu;
+        const uint32_t src = (uint32_t)(k >> 32), dst = (uint32_t)k;
+        return ((max(src, dst) / (uint32_t)period) >> (8 * (pass - 2 * nbv))) & 0xffu;
     }
-}
+};
+__device__ __forceinline__ uint32_t se_window(unsigned long long k, int period) { return max((uint32_t)(k >> 32), (uint32_t)k) / (uint32_t)period; }
 
-__global__ void __launch_bounds__(GS_THREADS) k3_comp_count_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
-        const int32_t* __restrict__ root_of, uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ comp_strong, int32_t min_read_pair) {
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
-        const unsigned long long k = tkeys[e];
-        if (k == EDGE_EMPTY) continue;
-        const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
-        const int root0 = root_of[r0];
-        atomicAdd(comp_ne + root0, 1u);
-        if (r0 != r1) atomicAdd(comp_ne + root_of[r1], 1u);
-        if ((int32_t)tcnt[e] >= min_read_pair) atomicAdd(comp_strong + root0, 1u);   // a followed edge: both ends in one component
+// After the sort: where each window's edges start and end, and its first call slot (= the number of followed edges,
+// counted once, in the windows before it). wstart / wend are zeroed beforehand (windows without edges stay empty).
+struct SEdgeUndirected {
+    const unsigned long long* se;
+    __device__ uint32_t operator()(uint32_t i, uint32_t) const { const unsigned long long k = se[i]; return (uint32_t)(k >> 32) <= (uint32_t)k ? 1u : 0u; }
+};
+struct WindowRangesOut {
+    const unsigned long long* se; int period; int32_t* wstart; int32_t* wend; int32_t* slot_base;
+    __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t n) const {
+        const uint32_t w = se_window(se[i], period);
+        if (i == 0 || se_window(se[i - 1], period) != w) { wstart[w] = (int32_t)i; slot_base[w] = (int32_t)(inc - v); }
+        if (i + 1 == n || se_window(se[i + 1], period) != w) wend[w] = (int32_t)(i + 1);
     }
-}
-
-struct LoadU32 { const uint32_t* p; __device__ uint32_t operator()(uint32_t i, uint32_t) const { return p[i]; } };
-struct ExclOut { uint32_t* o; __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const { o[i] = inc - v; } };
-
-__global__ void __launch_bounds__(GS_THREADS) k3_scatter_edges_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
-        const int32_t* __restrict__ root_of, const uint32_t* __restrict__ de_off, uint32_t* __restrict__ comp_fill, DEdge* __restrict__ de,
-        int32_t* __restrict__ de_root, int32_t period, int2* __restrict__ win_range, const uint32_t* __restrict__ comp_ne, uint32_t* __restrict__ d_cnt) {
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
-        const unsigned long long k = tkeys[e];
-        if (k == EDGE_EMPTY) continue;
-        const int r0 = (int)(k >> 32), r1 = (int)(k & 0xffffffffu);
-        const int win = r1 / period;          // r0 <= r1: the pair is counted when r1 is registered
-        DEdge d; d.win = win; d.src = r0; d.dst = r1; d.w = (int)tcnt[e]; d.flags = 0;
-        atomicMin(&win_range[r0].x, win); atomicMax(&win_range[r0].y, win);
-        if (r0 != r1) { atomicMin(&win_range[r1].x, win); atomicMax(&win_range[r1].y, win); }
-        const int root0 = root_of[r0];
-        const uint32_t f0 = atomicAdd(comp_fill + root0, 1u), s0 = de_off[root0] + f0;
-        if (f0 == 0 && comp_ne[root0] > (uint32_t)DE_RANK_SORT_MAX) atomicAdd(d_cnt + CNT_NBIG, 1u);   // components too large for the rank sort
-        de[s0] = d; de_root[s0] = root0;
-        if (r0 != r1) {                       // the copy seen from r1 goes to r1's component (the same one iff the edge is followed)
-            const int root1 = root_of[r1];
-            const uint32_t f1 = atomicAdd(comp_fill + root1, 1u), s1 = de_off[root1] + f1;
-            if (f1 == 0 && comp_ne[root1] > (uint32_t)DE_RANK_SORT_MAX) atomicAdd(d_cnt + CNT_NBIG, 1u);
-            d.src = r1; d.dst = r0; de[s1] = d; de_root[s1] = root1;
+};
+// the same as the tail of the single-CTA sort (small inputs: no extra launches)
+struct WindowRangesEpilogue {
+    int period; int32_t* wstart; int32_t* wend; int32_t* slot_base; uint32_t* n_slots;
+    __device__ void operator()(const unsigned long long* se, uint32_t n, uint32_t* s_scratch /* [33] */) const {
+        uint32_t running = 0;
+        for (uint32_t base = 0; base < n; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            const unsigned long long k = i < n ? se[i] : 0ull;
+            const uint32_t u = (i < n && (uint32_t)(k >> 32) <= (uint32_t)k) ? 1u : 0u;
+            uint32_t total;
+            const uint32_t inc = ss_block_scan_any(u, s_scratch, &total) + running;
+            if (i < n) {
+                const uint32_t w = se_window(k, period);
+                if (i == 0 || se_window(se[i - 1], period) != w) { wstart[w] = (int32_t)i; slot_base[w] = (int32_t)(inc - u); }
+                if (i + 1 == n || se_window(se[i + 1], period) != w) wend[w] = (int32_t)(i + 1);
+            }
+            running += total;
         }
+        if (threadIdx.x == 0) *n_slots = running;
     }
-}
+};
 
-// Rank sort of every component's directed edges by (win, src, dst), one thread per edge: the keys are unique, so
-// the number of smaller edges in the component is the edge's final position. Components with more than
-// DE_RANK_SORT_MAX edges are left to the walk (in-place heap sort).
-__global__ void __launch_bounds__(GS_THREADS) k3_rank_edges_kernel(const DEdge* __restrict__ de, const int32_t* __restrict__ de_root,
-        const uint32_t* __restrict__ de_off, const uint32_t* __restrict__ comp_ne, DEdge* __restrict__ de_sorted, const uint32_t* __restrict__ d_cnt) {
-    const uint32_t nde = d_cnt[CNT_NDE];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nde; t += gridDim.x * blockDim.x) {
-        const int root = de_root[t];
-        const uint32_t lo = de_off[root], n = comp_ne[root];
-        if (n > (uint32_t)DE_RANK_SORT_MAX) continue;
-        const DEdge x = de[t];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < n; ++j) r += de_less(de[lo + j], x) ? 1u : 0u;
-        de_sorted[lo + r] = x;
-    }
-}
-
-// When some component is too large for the rank sort, ALL directed edges are sorted at once with the device radix sort:
-// by (win, src, dst) packed into one key, then stably by the offset of the edge's component, which leaves every
-// component's segment in place and sorted.
-__global__ void __launch_bounds__(GS_THREADS) k3_edge_keys_kernel(const DEdge* __restrict__ de, const uint32_t* __restrict__ d_cnt, int vbits,
-                                                                  unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const uint32_t nde = d_cnt[CNT_NDE];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nde; t += gridDim.x * blockDim.x) {
-        const DEdge x = de[t];
-        keys[t] = ((unsigned long long)(uint32_t)x.win << (2 * vbits)) | ((unsigned long long)(uint32_t)x.src << vbits) | (uint32_t)x.dst;
-        vals[t] = t;
-    }
-}
-__global__ void __launch_bounds__(GS_THREADS) k3_edge_segment_keys_kernel(const uint32_t* __restrict__ vals, const int32_t* __restrict__ de_root,
-        const uint32_t* __restrict__ de_off, const uint32_t* __restrict__ d_cnt, unsigned long long* __restrict__ keys) {
-    const uint32_t nde = d_cnt[CNT_NDE];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nde; i += gridDim.x * blockDim.x) keys[i] = de_off[de_root[vals[i]]];
-}
-__global__ void __launch_bounds__(GS_THREADS) k3_edge_gather_kernel(const DEdge* __restrict__ de, const uint32_t* __restrict__ vals,
-                                                                    const uint32_t* __restrict__ d_cnt, DEdge* __restrict__ de_sorted) {
-    const uint32_t nde = d_cnt[CNT_NDE];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nde; i += gridDim.x * blockDim.x) de_sorted[i] = de[vals[i]];
-}
-
-// ---- K4: one warp walks one connected component ------------------------------------------------------
-// Components are found 32 regions at a time (a region with edges is the root of its component); the warp
-// then walks them one after the other, its lanes sharing the loops over the reads of the regions involved.
-// The walks are repeated in sweeps (bdk_logic.h, K4Static) until the table of deletion times is stable:
-//   walk phase   sweep 0: every component; sweep s > 0: the components stamped s
-//   mark phase   one thread per directed edge: a component that looks across a never-followed edge at a region
-//                whose deletion time differs from the table it used is stamped s + 1
-//   next phase   del_prev <- del_cur; the regions of the stamped components start again from "never cleared"
-// Single GPU: one persistent cooperative kernel runs all sweeps with grid-wide barriers in between
-// (k4_sweeps_kernel). Multi-GPU: one launch per phase, the deletion times are all-reduced between walk and mark.
+// ---- K4: the connection walk in closed form (bdk_logic.h, "second formulation") ------------------------------------
+//   init     per region: can it ever be final; starting guess of its deletion window
+//   sweeps   one persistent cooperative kernel: regions whose inputs changed are re-evaluated against the table (rewritten
+//            in place) until a sweep changes nothing -- grid-wide barrier between sweeps
+//   calls    first call window per region; one thread per flush window orders the window's calls (build_connection);
+//            one warp per call counts its pairs (process_sv); one thread per call scores it (k4_score_kernel)
+// Regions are handed out 32 at a time: a lane evaluates a small region alone, the warp shares the large ones.
 constexpr int K4_THREADS = 256;
-constexpr int K4_TRACE_SWEEPS = 32;
-struct K4Trace {   // BDK_K4_TRACE=1: phase time stamps of the sweeps (ns) and, for CTA-walked components, time per stage (ns, summed)
-    unsigned long long t[1 + 3 * K4_TRACE_SWEEPS]; uint32_t ndirty[K4_TRACE_SWEEPS];
-    unsigned long long cta[8]; unsigned long long cta_windows, cta_pieces, cta_cands, cta_rounds, cta_chunks, cta_survivors, cta_maxreads;
-};
-struct K4Graph {
-    const uint32_t* comp_ne; const uint32_t* comp_strong; const uint32_t* de_off; const uint32_t* row_off;
-    DEdge* de; DEdge* de_sorted; const int32_t* de_root; int32_t* queue;
-    uint32_t* stamp;                 // [nreg] by root: sweep in which the component is walked again
-    int32_t* del_prev;               // = S.del_prev, writable for the next phase
-    const int2* win_range;           // [nreg] first / last flush window in which the region is active
-    uint8_t* never_final;            // = S.never_final, written by k4_guess_kernel
-    const bdk_summary_t* summary; uint32_t* d_cnt;
-    uint32_t v_lo, v_hi;             // this GPU walks the components whose root region is in [v_lo, v_hi); single GPU: [0, ~0)
-    int32_t all_sorted;              // de_sorted holds every component's sorted edges (radix path), not only the rank-sorted ones
-    uint32_t* big_list;              // roots of the components with more than K4_CTA_MIN directed edges (k4_guess_kernel), any order
-    uint32_t* big_count;
-    uint32_t cta_min, big_min;       // K4_CTA_MIN / K4_BIG (tests lower them to force those paths on small inputs)
-    int32_t maxr;                    // <= K4C_MAXR (tests lower it to force the sequential-window fallback)
-    int32_t defer_first;             // big components also sit out the first sweep (else they are walked once with everybody first)
-    K4Trace* trace;                  // or null
+constexpr int K4N_SOLO_MAX = 64;          // reads up to which one thread evaluates a region by itself
+constexpr int K4_TRACE_SWEEPS = 64;
+struct K4Trace { unsigned long long t[1 + K4_TRACE_SWEEPS]; uint32_t nchanged[K4_TRACE_SWEEPS]; };
+struct K4Tab {
+    int32_t* del;                    // [nreg] flush window in which the region is cleared (K4_NEVER: never)
+    uint32_t* stamp;                 // [nreg] sweep in which the region is evaluated again
+    uint8_t* never_final;            // [nreg]
+    int32_t* c1;                     // [nreg] first window with a call involving the region
+    const bdk_summary_t* summary; const uint32_t* d_cnt;
 };
 
-// ---- a whole CTA walks one large component ---------------------------------------------------------------------------
-// The sequential walk costs about 3 us per directed edge (a chain of dependent loads). For a component with more than
-// K4_CTA_MIN directed edges the windows are still taken one after the other, but inside a window the independent pieces
-// (bdk_logic.h: "the same window, split into independent pieces") are walked by the warps of the CTA concurrently, and the
-// is_region_final pass is evaluated for all active nodes at once and then resolved. tests/hostsim runs the same
-// decomposition on the host (component_by_pieces) against the oracle.
-constexpr uint32_t K4_CTA_MIN = 512;      // directed edges from which a component gets a CTA instead of a warp
-constexpr uint32_t K4_BIG = 4096;         // ... and from which it waits for the smaller components to settle before it is walked
-constexpr int K4C_MAXR = 1024;            // distinct regions of one component in one window handled in shared memory (else: sequential window)
-constexpr int K4C_MAXE = 1024;            // directed edges of one window staged in shared memory (the walk is a chain of dependent edge reads)
-struct K4CtaSmem {
-    DEdge edges[K4C_MAXE];
-    int32_t vtx[K4C_MAXR], rs[K4C_MAXR + 1], label[K4C_MAXR], prow[K4C_MAXR], pq[K4C_MAXR], piece[K4C_MAXR], prowoff[K4C_MAXR], pqoff[K4C_MAXR],
-            cand[K4C_MAXR];
-    uint8_t state[K4C_MAXR];
-    int32_t warp_tot[33];
-    int32_t next_piece, changed, pending, cur, row_base;
-};
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-
-// exclusive prefix of v over the CTA (all threads call it); total = sum over the CTA
-__device__ __forceinline__ int k4_block_excl_scan(int v, int32_t* warp_tot, int& total) {
+template <class Fn>
+__device__ __forceinline__ void k4n_for_block(const K4N& S, uint32_t base, uint32_t v_end, bool want, Fn fn) {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        const int t = lane < nw ? warp_tot[lane] : 0;
-        int ti = t;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, ti, d); if (lane >= d) ti += u; }
-        warp_tot[lane] = ti - t;
-        if (lane == 31) warp_tot[32] = ti;
+    const uint32_t v = base + lane_id();
+    const bool mine = v < v_end && want;
+    const int nr = mine ? S.reg[v].n_reads : 0;
+    if (mine && nr <= K4N_SOLO_MAX) fn(SoloTeam(), (int)v);
+    unsigned big = __ballot_sync(FULL, mine && nr > K4N_SOLO_MAX);
+    while (big) {
+        const int l = __ffs(big) - 1;
+        big &= big - 1;
+        fn(WarpTeam(), (int)(base + l));
     }
-    __syncthreads();
-    const int res = warp_tot[warp] + inc - v;
-    total = warp_tot[32];
-    __syncthreads();
-    return res;
 }
 
-// ordered compaction of the indices r in [0, n) with pred(r) into out[]; returns their number (uniform)
-template <class Pred>
-__device__ __forceinline__ int k4_block_compact(int n, int32_t* out, int cap, int32_t* warp_tot, Pred pred) {
-    int running = 0;
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int r = base + threadIdx.x;
-        const int p = (r < n && pred(r)) ? 1 : 0;
-        int tot;
-        const int pos = running + k4_block_excl_scan(p, warp_tot, tot);
-        if (p && pos < cap) out[pos] = r;
-        running += tot;
-    }
-    __syncthreads();          // out[] is complete for every thread
-    return running;
-}
-
-__device__ __forceinline__ int k4_run_of_edge(const K4CtaSmem& sm, int R, int t) {      // run whose edge range holds t
-    int a = 0, b = R;
-    while (a < b) { const int m = (a + b) >> 1; if (sm.rs[m + 1] <= t) a = m + 1; else b = m; }
-    return a;
-}
-__device__ __forceinline__ int k4_run_of_vtx(const K4CtaSmem& sm, int R, int v) {       // run of region v (it has one: the reverse copy of the edge)
-    int a = 0, b = R;
-    while (a < b) { const int m = (a + b) >> 1; if (sm.vtx[m] < v) a = m + 1; else b = m; }
-    return a < R && sm.vtx[a] == v ? a : -1;
-}
-
-__device__ void k4_component_cta(const K4Static& S, K4Mut& M, DEdge* e, int ne, int32_t* queue /* 2 * ne + 2 */, int row0, int nrows, K4CtaSmem& sm, int maxr, K4Trace* trace) {
-    const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
-    const WarpTeam T;
-    const bool tr = trace != nullptr && tid == 0;
-    unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = tr ? globaltimer_ns() : 0, n_win = 0, n_pc = 0, n_cd = 0, n_rd = 0, n_ch = 0, n_sv = 0, n_mx = 0;
-    auto lap = [&](int k) { if (tr) { const unsigned long long now = globaltimer_ns(); t_acc[k] += now - t_last; t_last = now; } };
-    if (S.rerun) {
-        for (int q = tid; q < ne; q += NT) k4_reset_slot(S, M, e, q);
-        for (int r = tid; r < nrows; r += NT) M.row_emit[row0 + r] = 0;
-    }
-    __syncthreads();
-    int i = 0, row_base = row0;
-    while (i < ne) {
-        const int w = e[i].win;
-        int lo = i + 1, hi = ne;                                     // e[] is sorted by window: end of this one
-        while (lo < hi) { const int m = (lo + hi) >> 1; if (e[m].win == w) lo = m + 1; else hi = m; }
-        const int j = lo;
-        const WindowInfo wi = k4_window_info(S, w);
-        // The window's edges in shared memory: every step of the walk reads edges (binary searches for a region's run, scans
-        // of a run, the flags). The erased marks only matter inside the window, so the copy is never written back.
-        const int nE = j - i;
-        DEdge* ew = e + i;                                            // the window's edges, indexed 0 .. nE
-        if (nE <= K4C_MAXE) {
-            const int* src = reinterpret_cast<const int*>(e + i);
-            int* dst = reinterpret_cast<int*>(sm.edges);
-            for (int t = tid; t < 5 * nE; t += NT) dst[t] = src[t];
-            ew = sm.edges;
-            __syncthreads();
-        }
-        lap(0);      // stage 0: window bounds + edge staging
-        // ---- runs of equal source = the active nodes of the window, ascending ----------------------------------
-        const int R = k4_block_compact(nE, sm.rs, K4C_MAXR, sm.warp_tot, [&](int t) { return t == 0 || ew[t].src != ew[t - 1].src; });
-        if (R > maxr) {                                               // too many for shared memory: this window sequentially, by one warp
-            if (warp == 0) { const int row = k4_window_seq(T, S, M, ew, 0, nE, w, wi, queue, row_base); if (lane == 0) sm.row_base = row; }
-            __syncthreads();
-            row_base = sm.row_base;
-            __syncthreads();
-            i = j;
-            continue;
-        }
-        for (int r = tid; r < R; r += NT) { sm.vtx[r] = ew[sm.rs[r]].src; sm.label[r] = r; sm.prow[r] = 0; sm.pq[r] = 0; }
-        if (tid == 0) sm.rs[R] = nE;
-        __syncthreads();
-        auto followable = [&](const DEdge& x) { return x.w >= S.min_read_pair && !M.deleted[x.dst] && !M.deleted[x.src]; };
-        lap(1);      // stage 1: runs
-        // ---- pieces: label propagation over the edges the walk would follow ------------------------------------
-        for (;;) {
-            if (tid == 0) sm.changed = 0;
-            __syncthreads();
-            for (int t = tid; t < nE; t += NT) {
-                const DEdge x = ew[t];
-                if (x.src == x.dst || !followable(x)) continue;
-                const int r = k4_run_of_edge(sm, R, t), r2 = k4_run_of_vtx(sm, R, x.dst);
-                if (r2 < 0) continue;
-                const int la = ((volatile int32_t*)sm.label)[r], lb = ((volatile int32_t*)sm.label)[r2];
-                if (la < lb) { atomicMin(&sm.label[r2], la); sm.changed = 1; }
-                else if (lb < la) { atomicMin(&sm.label[r], lb); sm.changed = 1; }
+__global__ void __launch_bounds__(K4_THREADS) k4n_init_kernel(K4N S, K4Tab Tb) {
+    S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
+    const uint32_t nreg = (uint32_t)S.nreg;
+    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; base < nreg; base += gridDim.x * (blockDim.x >> 5) * 32u)
+        k4n_for_block(S, base, nreg, true, [&](auto T, int v) {
+            const bool nf = k4n_never_final(T, S, v);
+            // starting guess: cleared in the last window it is an active node of
+            const RegionRec R = S.reg[v];
+            int wl = -1;
+            for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
+                const int rm = S.ri[j].mate_region;
+                if (rm >= 0) wl = max(wl, max(v, rm) / S.period);
             }
-            __syncthreads();
-            for (int r = tid; r < R; r += NT) {                        // pointer jumping (labels only ever decrease, within the piece)
-                int l = ((volatile int32_t*)sm.label)[r];
-                while (((volatile int32_t*)sm.label)[l] < l) l = ((volatile int32_t*)sm.label)[l];
-                sm.label[r] = l;
+            wl = T.max(wl);
+            if (T.lane() == 0) {
+                Tb.never_final[v] = nf ? 1 : 0;
+                Tb.del[v] = (nf || wl < 0 || v == S.nreg - 1) ? K4_NEVER : wl;
+                Tb.stamp[v] = 0;
             }
-            __syncthreads();
-            const int ch = sm.changed;
-            __syncthreads();
-            if (!ch) break;
-        }
-        lap(2);      // stage 2: piece labels
-        for (int t = tid; t < nE; t += NT) {                           // per piece: edges it will follow (= row slots), queue entries
-            const DEdge x = ew[t];
-            if (!followable(x)) continue;
-            const int root = sm.label[k4_run_of_edge(sm, R, t)];
-            atomicAdd(&sm.pq[root], 1);
-            if (x.src <= x.dst) atomicAdd(&sm.prow[root], 1);
-        }
-        __syncthreads();
-        const int np = k4_block_compact(R, sm.piece, K4C_MAXR, sm.warp_tot, [&](int r) { return sm.label[r] == r && sm.prow[r] > 0; });
-        int rows_total = 0, q_total = 0;
-        for (int base = 0; base < np; base += NT) {
-            const int p = base + tid;
-            const int v = p < np ? sm.prow[sm.piece[p]] : 0;
-            int tot, tot2;
-            const int o1 = k4_block_excl_scan(v, sm.warp_tot, tot);
-            const int o2 = k4_block_excl_scan(p < np ? v + 1 : 0, sm.warp_tot, tot2);
-            if (p < np) { sm.prowoff[p] = rows_total + o1; sm.pqoff[p] = q_total + o2; }
-            rows_total += tot; q_total += tot2;
-        }
-        if (tid == 0) sm.next_piece = 0;
-        __syncthreads();
-        lap(3);      // stage 3: piece list + offsets
-        n_win += 1; n_pc += np;
-        // ---- the pieces, a warp each ----------------------------------------------------------------------------
-        for (;;) {
-            int p = 0;
-            if (lane == 0) p = atomicAdd(&sm.next_piece, 1);
-            p = __shfl_sync(FULL, p, 0);
-            if (p >= np) break;
-            const int root = sm.piece[p];
-            int row = row_base + sm.prowoff[p];
-            int32_t* q = queue + sm.pqoff[p];
-            for (int rb = root; rb < R; rb += 32) {                    // members of the piece, ascending (the root is its smallest)
-                const int r = rb + lane;
-                unsigned mask = __ballot_sync(FULL, r < R && sm.label[r] == root);
-                while (mask) {
-                    const int rr = rb + __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    row = k4_bfs_from(T, S, M, ew, 0, nE, w, wi, sm.rs[rr], sm.rs[rr + 1], q, row);
-                }
-            }
-        }
-        __syncthreads();
-        lap(4);      // stage 4: the pieces' walks
-        row_base += rows_total;
-        // ---- is_region_final over the active nodes: evaluate against the state before the pass, then resolve ----
-        const int nc = k4_block_compact(R, sm.cand, K4C_MAXR, sm.warp_tot, [&](int r) {
-            const int v = sm.vtx[r];
-            return !S.never_final[v] && !M.deleted[v] && v != wi.last_region; });
-        for (int c = tid; c < nc; c += NT) sm.cand[c] = sm.vtx[sm.cand[c]];          // run index -> region (still ascending)
-        __syncthreads();
-        // first the last 32 reads of every candidate, a warp per candidate (the reads whose mates lie ahead are a region's last
-        // ones: most candidates are refused here); then all (candidate, 32 reads) chunks of the survivors spread over the warps
-        for (int c = warp; c < nc; c += NW) {
-            const RegionRec& Rg = S.reg[sm.cand[c]];
-            const int jr = Rg.first_read + Rg.n_reads - 1 - lane;
-            const bool bad = jr >= Rg.first_read && k4_read_blocks_final(S, M, jr, sm.cand[c], wi);
-            const bool refused = __any_sync(FULL, bad) != 0;
-            if (lane == 0) sm.state[c] = refused ? K4_FIN_NOT : K4_FIN_UNDECIDED;
-        }
-        __syncthreads();
-        int chunks_total = 0;
-        for (int base = 0; base < nc; base += NT) {
-            const int c = base + tid;
-            const int nr = c < nc && sm.state[c] == K4_FIN_UNDECIDED ? S.reg[sm.cand[c]].n_reads - 32 : 0;      // the last 32 are done
-            const int v = nr > 0 ? (nr + 31) >> 5 : 0;
-            int tot;
-            const int o = k4_block_excl_scan(v, sm.warp_tot, tot);
-            if (c < nc) sm.prowoff[c] = chunks_total + o;
-            chunks_total += tot;
-        }
-        __syncthreads();
-        if (tr) {
-            n_ch += chunks_total;
-            for (int c = 0; c < nc; ++c) if (sm.state[c] == K4_FIN_UNDECIDED) { n_sv += 1; if ((unsigned long long)S.reg[sm.cand[c]].n_reads > n_mx) n_mx = S.reg[sm.cand[c]].n_reads; }
-        }
-        for (int item = warp; item < chunks_total; item += NW) {
-            int a = 0, b = nc;                                         // last candidate whose first chunk is <= item
-            while (b - a > 1) { const int m = (a + b) >> 1; if (sm.prowoff[m] <= item) a = m; else b = m; }
-            const RegionRec& Rg = S.reg[sm.cand[a]];
-            const int jr = Rg.first_read + ((item - sm.prowoff[a]) << 5) + lane;
-            const bool bad = jr < Rg.first_read + Rg.n_reads - 32 && k4_read_blocks_final(S, M, jr, sm.cand[a], wi);
-            if (__any_sync(FULL, bad) && lane == 0) sm.state[a] = K4_FIN_NOT;
-        }
-        __syncthreads();
-        lap(5);      // stage 5: is_region_final of the candidates
-        n_cd += nc;
-        for (;;) {
-            if (tid == 0) sm.pending = 0;
-            __syncthreads();
-            for (int c = warp; c < nc; c += NW) {
-                if (((volatile uint8_t*)sm.state)[c] != K4_FIN_UNDECIDED) continue;
-                const int d = k4_final_deps(T, S, M, sm.cand[c], sm.cand, (const uint8_t*)sm.state, nc);
-                if (lane == 0) {
-                    if (d & 1) sm.state[c] = K4_FIN_NOT;
-                    else if (!(d & 2)) sm.state[c] = K4_FIN_CLEARED;
-                    else sm.pending = 1;
-                }
-            }
-            __syncthreads();
-            const int pend = sm.pending;
-            __syncthreads();
-            n_rd += 1;
-            if (!pend) break;
-        }
-        for (int c = tid; c < nc; c += NT)
-            if (sm.state[c] == K4_FIN_CLEARED) { M.deleted[sm.cand[c]] = 1; M.del_cur[sm.cand[c]] = w; }
-        __syncthreads();
-        lap(6);      // stage 6: resolution rounds + commit
-        i = j;
-    }
-    if (tr) {
-        for (int k = 0; k < 8; ++k) atomicAdd(&trace->cta[k], t_acc[k]);
-        atomicAdd(&trace->cta_windows, n_win); atomicAdd(&trace->cta_pieces, n_pc); atomicAdd(&trace->cta_cands, n_cd); atomicAdd(&trace->cta_rounds, n_rd);
-        atomicAdd(&trace->cta_chunks, n_ch); atomicAdd(&trace->cta_survivors, n_sv); atomicMax(&trace->cta_maxreads, n_mx);
-    }
-}
-
-__device__ __forceinline__ void k4_walk_phase(K4Static& S, K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* ticket, uint32_t* big_cursor,
-                                              K4CtaSmem& sm, bool defer_big = false, uint32_t* n_dirty = nullptr) {
-    const unsigned FULL = 0xffffffffu;
-    const WarpTeam T;
-    const uint32_t lane = lane_id();
-    S.rerun = sweep ? 1 : 0;
-    const uint32_t v_end = min(G.v_hi, (uint32_t)S.nreg);
-    for (;;) {                                  // 32 regions at a time, handed out dynamically (components differ a lot in size)
-        uint32_t base = 0;
-        if (lane == 0) base = G.v_lo + atomicAdd(ticket, 1u) * 32u;
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= v_end) break;
-        const uint32_t r = base + lane;
-        uint32_t ne = (r < v_end && (!sweep || G.stamp[r] == sweep)) ? G.comp_ne[r] : 0;
-        if (ne > G.cta_min) ne = 0;             // large components: below, a CTA each
-        unsigned m = __ballot_sync(FULL, ne != 0);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t rr = base + src;
-            const int n = (int)__shfl_sync(FULL, ne, src);
-            DEdge* e = G.de_sorted + G.de_off[rr];
-            k4_component(T, S, M, e, n, G.queue + 2 * (size_t)G.de_off[rr] + 2 * (size_t)rr, (int)G.row_off[rr], (int)G.comp_strong[rr]);
-        }
-    }
-    const uint32_t nbig = *G.big_count;
-    if (!nbig) return;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) sm.cur = (int32_t)atomicAdd(big_cursor, 1u);
-        __syncthreads();
-        const uint32_t idx = (uint32_t)sm.cur;
-        if (idx >= nbig) break;
-        const uint32_t rr = G.big_list[idx];
-        if (rr < G.v_lo || rr >= v_end || (sweep && G.stamp[rr] != sweep)) continue;
-        const uint32_t n = G.comp_ne[rr];
-        if (defer_big && n > G.big_min) {          // waits for the small components to settle: stays stamped for the next sweep
-            if (threadIdx.x == 0) { G.stamp[rr] = sweep + 1; atomicAdd(n_dirty, 1u); }
-            continue;
-        }
-        DEdge* e = (n <= (uint32_t)DE_RANK_SORT_MAX || G.all_sorted) ? G.de_sorted + G.de_off[rr] : G.de + G.de_off[rr];
-        if (!(n <= (uint32_t)DE_RANK_SORT_MAX || G.all_sorted)) {          // (only when the radix keys did not fit 64 bits)
-            if (threadIdx.x < 32) de_sort_team(T, e, (int)n, (DEdge*)nullptr);
-            __syncthreads();
-        }
-        k4_component_cta(S, M, e, (int)n, G.queue + 2 * (size_t)G.de_off[rr] + 2 * (size_t)rr, (int)G.row_off[rr], (int)G.comp_strong[rr], sm, G.maxr, n > G.big_min ? G.trace : nullptr);
-    }
-}
-
-__device__ __forceinline__ void k4_mark_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep, uint32_t* n_dirty,
-                                              uint32_t* n_small = nullptr) {
-    const uint32_t nde = G.d_cnt[CNT_NDE];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nde; t += gridDim.x * blockDim.x) {
-        const int root = G.de_root[t];
-        const DEdge x = G.de[t];                               // de[]: the component's edges as a set (sorted or not)
-        if (S.root_of[x.dst] == root) continue;
-        const int a = S.del_prev[x.dst], b = M.del_cur[x.dst];
-        if (a == b || G.stamp[root] == sweep + 1) continue;
-        if (S.never_final[x.src]) continue;                    // x.src is never checked against other regions' state
-        const int2 wr = G.win_range[x.src];
-        if (k4_change_matters(x.src, x.dst, wr.x, min(wr.y, M.del_cur[x.src]), a, b)) {
-            G.stamp[root] = sweep + 1; atomicAdd(n_dirty, 1u);
-            if (n_small && G.comp_ne[root] <= G.big_min) atomicAdd(n_small, 1u);
-        }
-    }
-}
-
-// reset_stamped: multi-GPU only -- every rank forgets the deletion times of the components that will be walked again (their
-// owner rewrites them, the min all-reduce then takes the owner's values); on a single GPU the walk resets its own regions.
-__device__ __forceinline__ void k4_next_phase(const K4Static& S, const K4Mut& M, const K4Graph& G, uint32_t sweep, bool reset_stamped) {
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < (uint32_t)S.nreg; v += gridDim.x * blockDim.x) {
-        G.del_prev[v] = M.del_cur[v];
-        if (reset_stamped && G.stamp[S.root_of[v]] == sweep + 1) M.del_cur[v] = K4_NEVER;
-    }
-}
-
-__device__ __forceinline__ void k4_load_counts(K4Static& S, const K4Graph& G) {
-    S.nreg = (int32_t)G.d_cnt[CNT_NREG]; S.ncand = (int32_t)G.d_cnt[CNT_NCAND];
-    S.covered_ref_len = G.summary->covered_ref_len;
+        });
 }
 
 // grid-wide barrier of a cooperative launch (all CTAs resident): monotone arrival counter. The spin uses relaxed loads
@@ -664,154 +304,118 @@ __device__ __forceinline__ void k4_grid_barrier(uint32_t* counter, uint32_t& epo
         for (;;) {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
             if (v >= target) break;
-            __nanosleep(64);
+            __nanosleep(32);
         }
         __threadfence();
     }
     __syncthreads();
 }
 
-// single GPU: all sweeps in one persistent kernel. sync[0]: barrier counter, sync[1..2]: walk tickets (alternating),
-// sync[3..4]: stamped-component counts (alternating), sync[5]: number of sweeps done (result), sync[6..7]: stamped small
-// components (alternating), sync[9..10]: cursors into the list of large components (alternating)
+// one sweep over the regions stamped `sweep` (sweep 0: all that can ever be final); returns through *changed
+__device__ __forceinline__ void k4n_sweep(const K4N& S, const K4Tab& Tb, uint32_t sweep, uint32_t* ticket, uint32_t* changed) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t nreg = (uint32_t)S.nreg;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(ticket, 1u) * 32u;
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= nreg) break;
+        const uint32_t v0 = base + lane_id();
+        const bool want = v0 < nreg && !Tb.never_final[v0] && (sweep == 0 || __ldcg(Tb.stamp + v0) == sweep);
+        k4n_for_block(S, base, nreg, want, [&](auto T, int v) {
+            const int d = k4n_region_deletion(T, S, Tb.del, v);
+            const int old = __ldcg(Tb.del + v);
+            if (d == old) return;
+            const RegionRec R = S.reg[v];
+            if (T.lane() == 0) { __stcg(Tb.del + v, d); atomicAdd(changed, 1u); }
+            for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
+                const int rm = S.ri[j].mate_region;
+                if (rm >= 0 && rm != v && !Tb.never_final[rm]) __stcg(Tb.stamp + rm, sweep + 1);
+            }
+        });
+    }
+}
 
-__global__ void __launch_bounds__(K4_THREADS, 3) k4_sweeps_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t* __restrict__ sync, K4Trace* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char k4_smem_raw[];
-    K4CtaSmem& sm = *reinterpret_cast<K4CtaSmem*>(k4_smem_raw);
-    k4_load_counts(S, G);
+// sync[0]: barrier counter; sync[1 + s % 3]: region tickets of sweep s; sync[4 + s % 3]: regions changed in sweep s;
+// sync[7]: number of sweeps (result)
+__global__ void __launch_bounds__(K4_THREADS) k4n_sweeps_kernel(K4N S, K4Tab Tb, uint32_t* __restrict__ sync, K4Trace* __restrict__ trace) {
+    S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
     uint32_t epoch = 0;
     const bool tr = trace && blockIdx.x == 0 && threadIdx.x == 0;
     if (tr) trace->t[0] = globaltimer_ns();
-    uint32_t nsmall_prev = G.defer_first ? 1 : 0;                  // sweep 0: the small components go first (or everybody at once)
     for (uint32_t sweep = 0;; ++sweep) {
-        // big components wait while small ones are still being corrected (they are walked at the latest when nothing else is left)
-        k4_walk_phase(S, M, G, sweep, sync + 1 + (sweep & 1), sync + 9 + (sweep & 1), sm, nsmall_prev != 0, sync + 3 + (sweep & 1));
+        // the counters of the next sweep were last read two barriers ago
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sync[1 + (sweep + 1) % 3] = 0; sync[4 + (sweep + 1) % 3] = 0; }
+        k4n_sweep(S, Tb, sweep, sync + 1 + sweep % 3, sync + 4 + sweep % 3);
         k4_grid_barrier(sync, epoch);
-        if (tr && sweep < K4_TRACE_SWEEPS) trace->t[1 + 3 * sweep] = globaltimer_ns();
-        if (blockIdx.x == 0 && threadIdx.x == 0) {     // the other parity's counters were last used before the barrier two phases back
-            sync[1 + ((sweep + 1) & 1)] = 0; sync[3 + ((sweep + 1) & 1)] = 0; sync[6 + ((sweep + 1) & 1)] = 0; sync[9 + ((sweep + 1) & 1)] = 0;
-        }
-        k4_mark_phase(S, M, G, sweep, sync + 3 + (sweep & 1), sync + 6 + (sweep & 1));
-        k4_grid_barrier(sync, epoch);
-        if (tr && sweep < K4_TRACE_SWEEPS) trace->t[2 + 3 * sweep] = globaltimer_ns();
-        const uint32_t ndirty = ld_acquire_u32(sync + 3 + (sweep & 1));
-        nsmall_prev = ld_acquire_u32(sync + 6 + (sweep & 1));
-        k4_next_phase(S, M, G, sweep, false);
-        k4_grid_barrier(sync, epoch);
-        if (tr && sweep < K4_TRACE_SWEEPS) { trace->t[3 + 3 * sweep] = globaltimer_ns(); trace->ndirty[sweep] = ndirty; }
-        if (!ndirty) { if (blockIdx.x == 0 && threadIdx.x == 0) sync[5] = sweep + 1; break; }
+        const uint32_t nchanged = ld_acquire_u32(sync + 4 + sweep % 3);
+        if (tr && sweep < K4_TRACE_SWEEPS) { trace->t[1 + sweep] = globaltimer_ns(); trace->nchanged[sweep] = nchanged; }
+        if (!nchanged) { if (blockIdx.x == 0 && threadIdx.x == 0) sync[7] = sweep + 1; break; }
     }
 }
 
-// per-read static information packed for the walk (bdk_logic.h: ReadInfo), one thread per anomalous read
-__global__ void __launch_bounds__(GS_THREADS) k4_read_info_kernel(const bdk_aread* __restrict__ ar, const int32_t* __restrict__ mate,
-        const int32_t* __restrict__ read_region, const int32_t* __restrict__ read_cand, uint32_t A, ReadInfo* __restrict__ ri) {
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A; j += gridDim.x * blockDim.x) ri[j] = make_read_info(ar, mate, read_region, read_cand, (int)j);
+// the same, one launch per sweep (when the cooperative launch cannot be resident)
+__global__ void __launch_bounds__(K4_THREADS) k4n_sweep_kernel(K4N S, K4Tab Tb, uint32_t sweep, uint32_t* __restrict__ ticket, uint32_t* __restrict__ changed) {
+    S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
+    k4n_sweep(S, Tb, sweep, ticket, changed);
 }
 
-// starting table of deletion times (bdk_logic.h: k4_guess_deletion), one thread per region
-__global__ void __launch_bounds__(GS_THREADS) k4_guess_kernel(K4Static S, K4Mut M, K4Graph G) {
-    k4_load_counts(S, G);
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < (uint32_t)S.nreg; v += gridDim.x * blockDim.x) {
-        G.del_prev[v] = k4_guess_deletion(S, M.alive, (int)v, G.win_range[v].y);
-        G.never_final[v] = k4_never_final(S, M.alive, (int)v) ? 1 : 0;
-        if (G.comp_ne[v] > G.cta_min) G.big_list[atomicAdd(G.big_count, 1u)] = v;
-        M.del_cur[v] = K4_NEVER;
-        G.stamp[v] = 0;
+__global__ void __launch_bounds__(K4_THREADS) k4n_first_call_kernel(K4N S, K4Tab Tb) {
+    S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
+    const uint32_t nreg = (uint32_t)S.nreg;
+    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; base < nreg; base += gridDim.x * (blockDim.x >> 5) * 32u)
+        k4n_for_block(S, base, nreg, true, [&](auto T, int v) {
+            const int c = k4n_first_call(T, S, Tb.del, v);
+            if (T.lane() == 0) Tb.c1[v] = c;
+        });
+}
+
+// one thread per flush window: the window's calls in build_connection's order (bdk_logic.h: k4n_window_calls)
+constexpr int K4W_THREADS = 32;
+__global__ void __launch_bounds__(K4W_THREADS) k4n_windows_kernel(K4Tab Tb, const unsigned long long* __restrict__ se, const int32_t* __restrict__ wstart,
+        const int32_t* __restrict__ wend, const int32_t* __restrict__ slot_base, uint8_t* __restrict__ fl, int32_t* __restrict__ queue, int period,
+        bdk_sv* __restrict__ rows, uint64_t* __restrict__ row_key, uint8_t* __restrict__ row_emit) {
+    const uint32_t nwin = Tb.d_cnt[CNT_NREG] / (uint32_t)period + 1;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nwin; w += gridDim.x * blockDim.x) {
+        const int s = wstart[w], e = wend[w];
+        if (e <= s) continue;
+        k4n_window_calls(Tb.del, Tb.c1, reinterpret_cast<const SEdge*>(se) + s, e - s, fl + s, queue + s + w, (int)w, slot_base[w], rows, row_key, row_emit);
     }
 }
 
-// after the sweeps: second half of process_sv for every row slot the walk left pending, one thread per slot
-__global__ void __launch_bounds__(GS_THREADS) k4_score_kernel(K4Static S, K4Mut M, K4Graph G) {
-    k4_load_counts(S, G);
-    const uint32_t nrow = G.d_cnt[CNT_NROW];
+// one warp per call slot: the pairs the call consumes (bdk_logic.h: k4n_call)
+__global__ void __launch_bounds__(K4_THREADS) k4n_calls_kernel(K4N S, K4NOut M, const uint32_t* __restrict__ d_cnt) {
+    S.nreg = (int32_t)d_cnt[CNT_NREG];
+    const uint32_t nrow = d_cnt[CNT_NROW];
+    const WarpTeam T;
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrow; r += gridDim.x * (blockDim.x >> 5))
+        if (M.row_emit[r] & K4_ROW_CALL) k4n_call(T, S, M, (int)r);
+}
+
+// second half of process_sv for every call slot left pending, one thread per slot
+__global__ void __launch_bounds__(GS_THREADS) k4_score_kernel(K4Static S, K4Mut M, const bdk_summary_t* __restrict__ summary, const uint32_t* __restrict__ d_cnt) {
+    S.nreg = (int32_t)d_cnt[CNT_NREG]; S.ncand = (int32_t)d_cnt[CNT_NCAND];
+    S.covered_ref_len = summary->covered_ref_len;
+    const uint32_t nrow = d_cnt[CNT_NROW];
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += gridDim.x * blockDim.x)
         if (M.row_emit[r] == K4_ROW_PENDING) k4_score_row(S, M, (int)r);
 }
 
-// multi-GPU: one launch per phase
-__global__ void __launch_bounds__(K4_THREADS, 3) k4_components_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep, uint32_t* __restrict__ ticket,
-                                                                   uint32_t* __restrict__ big_cursor) {
-    extern __shared__ __align__(16) unsigned char k4_smem_raw[];
-    K4CtaSmem& sm = *reinterpret_cast<K4CtaSmem*>(k4_smem_raw);
-    k4_load_counts(S, G);
-    k4_walk_phase(S, M, G, sweep, ticket, big_cursor, sm);
-}
-__global__ void __launch_bounds__(GS_THREADS) k4_mark_dirty_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep, uint32_t* __restrict__ n_dirty) {
-    k4_load_counts(S, G);
-    k4_mark_phase(S, M, G, sweep, n_dirty);
-}
-__global__ void __launch_bounds__(GS_THREADS) k4_next_sweep_kernel(K4Static S, K4Mut M, K4Graph G, uint32_t sweep) {
-    k4_load_counts(S, G);
-    k4_next_phase(S, M, G, sweep, true);
-}
-
 // ---- output order --------------------------------------------------------------------------------------
-// The reference prints window by window, BFS by BFS, and the calls of one BFS in the order they were made:
-// sort the emitted rows by (key = window << 32 | BFS start vertex, row slot). One CTA, bitonic sort in
-// shared memory (an SV table has thousands of rows, not millions).
-constexpr int K5_THREADS = 256;
-constexpr int K5_SMEM_ROWS = 16384;                       // tables up to this many row slots are ordered by the rank sort below
-// Rank sort over the whole grid: (key, slot) pairs are unique, so the number of smaller pairs is a row's final position.
-// CTA (bx, by) compares the 256 rows of block bx with the 256 rows of tile by (staged in shared memory) and adds its partial
-// counts to rank[]; a second kernel scatters. n^2 comparisons (16 K rows = 2.7e8) spread over up to 4096 CTAs: a few
-// microseconds, where a single-CTA bitonic sort of the same table took over 100 us.
-__global__ void __launch_bounds__(K5_THREADS) k5_rank_partial_kernel(const uint64_t* __restrict__ emit_key, const uint32_t* __restrict__ emit_slot,
-        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ rank) {
-    __shared__ uint64_t s_key[K5_THREADS];
-    __shared__ uint32_t s_slot[K5_THREADS];
-    const uint32_t n = d_cnt[CNT_NEMIT];
-    const uint32_t i = blockIdx.x * K5_THREADS + threadIdx.x, t0 = blockIdx.y * K5_THREADS;
-    if (blockIdx.x * K5_THREADS >= n || t0 >= n) return;           // uniform per CTA
-    const uint32_t j = t0 + threadIdx.x;
-    s_key[threadIdx.x] = j < n ? emit_key[j] : ~0ull;
-    s_slot[threadIdx.x] = j < n ? emit_slot[j] : 0xffffffffu;
-    __syncthreads();
-    if (i >= n) return;
-    const uint64_t ki = emit_key[i];
-    const uint32_t si = emit_slot[i];
-    const uint32_t m = min((uint32_t)K5_THREADS, n - t0);
-    uint32_t r = 0;
-    for (uint32_t q = 0; q < m; ++q) {
-        const uint64_t kq = s_key[q];
-        r += (kq < ki || (kq == ki && s_slot[q] < si)) ? 1u : 0u;
-    }
-    if (r) atomicAdd(rank + i, r);
-}
-__global__ void __launch_bounds__(GS_THREADS) k5_rank_scatter_kernel(const uint32_t* __restrict__ emit_slot, const uint32_t* __restrict__ rank,
-        const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ order_slot) {
-    const uint32_t n = d_cnt[CNT_NEMIT];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) order_slot[rank[i]] = emit_slot[i];
-}
-
-// large tables: order_slot comes from the device radix sort; this just seeds its value array
-__global__ void __launch_bounds__(GS_THREADS) k5_copy_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ n_ptr) {
-    const uint32_t n = *n_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-
-// (key = slot, value = slot) pairs of the emitted rows, and the replacement of those keys by the rows' sort keys
-__global__ void __launch_bounds__(GS_THREADS) k5_slot_keys_kernel(const uint64_t* __restrict__ emit_key, const uint32_t* __restrict__ emit_slot,
-        const uint32_t* __restrict__ n_ptr, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const uint32_t n = *n_ptr;
-    (void)emit_key;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { keys[i] = emit_slot[i]; vals[i] = emit_slot[i]; }
-}
-__global__ void __launch_bounds__(GS_THREADS) k5_row_keys_kernel(const uint64_t* __restrict__ row_key, const uint32_t* __restrict__ n_ptr,
-        unsigned long long* __restrict__ keys) {
-    const uint32_t n = *n_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) keys[i] = row_key[keys[i]];
-}
-
+// Call slots are numbered window by window and, inside a window, in the order build_connection makes the calls: slot
+// order IS the reference's output order (BreakDancer.cpp:280-338). The emitted rows are compacted by one scan.
 struct RowPack {           // per-row arrays, by slot (K4 output) or by output position (what the host receives)
     bdk_sv* rows; int32_t* lib_count; uint32_t* cn_count; float* cn;
 };
-__global__ void __launch_bounds__(GS_THREADS) k5_gather_kernel(RowPack in, RowPack out, const uint32_t* __restrict__ order_slot, int32_t* __restrict__ slot_order,
-        int nlib, int nkey, const uint32_t* __restrict__ d_cnt, uint32_t* __restrict__ n_out) {
-    const uint32_t n = d_cnt[CNT_NEMIT];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t s = order_slot[i];
+struct EmitFlag {
+    const uint8_t* row_emit;
+    __device__ uint32_t operator()(uint32_t s, uint32_t) const { return row_emit[s] == K4_ROW_EMIT ? 1u : 0u; }
+};
+struct GatherOut {
+    RowPack in, out; int32_t* slot_order; int nlib, nkey;
+    __device__ void operator()(uint32_t s, uint32_t inc, uint32_t v, uint32_t) const {
+        if (!v) { slot_order[s] = -1; return; }
+        const uint32_t i = inc - 1;
         bdk_sv r = in.rows[s];
         r.order = (int32_t)i;
         out.rows[i] = r;
@@ -819,7 +423,7 @@ __global__ void __launch_bounds__(GS_THREADS) k5_gather_kernel(RowPack in, RowPa
         for (int l = 0; l < nlib; ++l) out.lib_count[(size_t)i * nlib + l] = in.lib_count[(size_t)s * nlib + l];
         for (int k = 0; k < nkey; ++k) { out.cn_count[(size_t)i * nkey + k] = in.cn_count[(size_t)s * nkey + k]; out.cn[(size_t)i * nkey + k] = in.cn[(size_t)s * nkey + k]; }
     }
-}
+};
 
 // Poisson tail known-answer entry point
 __global__ void poisson_logsf_kernel(const double* __restrict__ lambda, const int32_t* __restrict__ k, double* __restrict__ out, uint64_t n) {

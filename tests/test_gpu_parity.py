@@ -132,13 +132,20 @@ def test_gpu_segment_overflow_retry(monkeypatch):
     _check(b, cols, "tiny segments, single-key path")
 
 
-def test_gpu_large_table_ordering_path(monkeypatch):
-    """Output ordering of SV tables too large for the single-CTA shared-memory sort (forced): radix path."""
-    monkeypatch.setenv("BDK_K5_SMEM_ROWS", "0")
+def test_gpu_large_table_needs_second_result_copy():
+    """More SV rows than the first device-to-host copy was sized for (a small job first, then a large one on the same context):
+    the rest is fetched by a second copy."""
     w = synth.generate(util.GENOME3, util.LIBS4, 200000, seed=31, anomaly_frac=0.05, somatic_frac=0.3)
     b, cols, *_ = util.workload_bundle(w, api.Options(min_read_pair=1, score_threshold=-100))
-    ro = _check(b, cols, "radix ordering")
-    assert len(ro.table.sv) > 500
+    ro = _check(b, cols, "many rows")
+    assert len(ro.table.sv) > 3000                       # > A / 64 + 1024 rows: the second copy ran
+    ctx = api.Context(b, 0)
+    small = {k: np.ascontiguousarray(v[:2000]) for k, v in cols.items()}
+    ctx.push(small); ctx.finish()
+    ctx.reset(); ctx.push(cols)
+    t = ctx.finish()
+    util.assert_tables_equal(ro.table, t, "large job after a small one")
+    ctx.close()
 
 
 def test_gpu_reset_and_reuse_is_idempotent():
@@ -203,20 +210,18 @@ def test_config3_device_generator_matches_oracle():
     assert len(ro.table.sv) > 300 and len(set(ro.table.sv["flag"].tolist())) >= 5
 
 
-# ---- the paths of the connection walk that only large inputs reach, forced on small ones ------------------------------
+# ---- alternative mechanics of K3 / K4, forced -------------------------------------------------------------------------
 K4_FORCED = {
-    "cta_walker_for_every_component": dict(BDK_K4_CTA_MIN="0"),
-    "cta_walker_sequential_window_fallback": dict(BDK_K4_CTA_MIN="0", BDK_K4_MAXR="3"),
-    "cta_walker_and_deferral": dict(BDK_K4_CTA_MIN="4", BDK_K4_BIG="8"),
-    "deferral_of_warp_walked_components": dict(BDK_K4_BIG="6"),
-    "one_launch_per_phase_instead_of_the_cooperative_kernel": dict(BDK_K4_HOST_LOOP="1"),
+    "one_launch_per_sweep_instead_of_the_cooperative_kernel": dict(BDK_K4_HOST_LOOP="1"),
+    "multi_kernel_radix_sort_of_the_followed_edges": dict(BDK_SORT_SINGLE_MAX="0"),
+    "both": dict(BDK_K4_HOST_LOOP="1", BDK_SORT_SINGLE_MAX="0"),
 }
 
 
 @pytest.mark.parametrize("name", list(K4_FORCED))
 def test_gpu_k4_forced_paths_match_oracle(monkeypatch, name):
-    """A CTA per component (pieces of a window in parallel, finality pass resolved afterwards), its sequential-window
-    fallback, and big components waiting for the small ones: all must give the oracle's result."""
+    """The sweeps over the table of deletion windows as one launch each (what a shared GPU falls back to) and the
+    multi-kernel radix sort that large inputs use for the followed edges: all must give the oracle's result."""
     for k, v in K4_FORCED[name].items():
         monkeypatch.setenv(k, v)
     w = synth.generate(util.GENOME3, util.LIBS4, 120000, seed=41, anomaly_frac=0.08, somatic_frac=0.3)
@@ -226,13 +231,13 @@ def test_gpu_k4_forced_paths_match_oracle(monkeypatch, name):
         assert len(ro.table.sv) > 3
     import torch
     from breakdancer_b200 import synth_torch
-    cols = synth_torch.config3_device(1_000_000, seed=13, device=torch.device("cuda", 0))     # dense noise: long strong components
+    cols = synth_torch.config3_device(1_000_000, seed=13, device=torch.device("cuda", 0))     # dense noise: long chains of followed edges
     b, _ = synth_torch.config3_bundle()
     _check(b, synth_torch.to_numpy(cols), f"{name} config3-shaped")
 
 
-def test_gpu_radix_sorted_edges_for_large_components(monkeypatch):
-    """A component with more directed edges than the rank sort takes (8192) switches the whole edge list to the radix sort."""
+def test_gpu_config3_shape_eight_million_pairs_matches_oracle():
+    """Dense config-3-shaped data at 8 M pairs (tens of thousands of followed edges per chromosome), bit-exact vs the oracle."""
     import torch
     from breakdancer_b200 import synth_torch
     cols = synth_torch.config3_device(8_000_000, seed=17, device=torch.device("cuda", 0))
