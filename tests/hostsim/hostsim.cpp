@@ -230,7 +230,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     K4Mut KM;
     memset(&KM, 0, sizeof KM);
     KM.rows = rows.data(); KM.row_lib_count = row_lib_count.data(); KM.row_lib_span = row_lib_span.data();
-    KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data(); KM.row_key = row_key.data();
+    KM.row_cn_count = row_cn_count.data(); KM.row_cn = row_cn.data(); KM.row_emit = row_emit.data();
     if (getenv("HOSTSIM_VERBOSE")) fprintf(stderr, "hostsim: %d regions, %zu edges, %d call slots, %d sweeps\n", nreg, ue.size(), nrow_cap, sweeps + 1);
     for (int r = 0; r < nrow_cap; ++r) if (row_emit[r] == K4_ROW_PENDING) k4_score_row(SS, KM, r);
     // output order = slot order: slots are numbered window by window, and inside a window in the order of the calls
@@ -314,31 +314,6 @@ extern "C" long hostsim_classify_hot_check(long* ncases) {
                                     ++n;
                                     if (ch != want) ++bad;
                                 }
-    if (ncases) *ncases = n;
-    return bad;
-}
-
-// k4_change_matters against its definition: the answers "rm cleared before (w, v)" for deletion windows a and b differ for some
-// window w in [wf, wl]. Exhaustive over a small range (K4_NEVER included). Returns the number of mismatches.
-extern "C" long hostsim_change_matters_check(long* ncases) {
-    long bad = 0, n = 0;
-    const int vals[] = {0, 1, 2, 3, 4, 5, 6, K4_NEVER};
-    auto before = [](int d, int rm, int w, int v) { return d < w || (d == w && rm < v); };
-    for (int v = 0; v < 3; ++v)
-        for (int rm = 0; rm < 3; ++rm) {
-            if (rm == v) continue;
-            for (int wf = 0; wf <= 6; ++wf)
-                for (int wl : {-1, 0, 1, 2, 3, 4, 5, 6, K4_NEVER})
-                    for (int a : vals)
-                        for (int b : vals) {
-                            bool want = false;
-                            for (int w = wf; w <= 6 && w <= wl; ++w) want = want || (before(a, rm, w, v) != before(b, rm, w, v));
-                            // windows beyond 6 (wl = K4_NEVER): both finite deletions are "before" there; K4_NEVER never is
-                            if (wl == K4_NEVER && ((a == K4_NEVER) != (b == K4_NEVER))) want = true;
-                            ++n;
-                            if (k4_change_matters(v, rm, wf, wl, a, b) != want) ++bad;
-                        }
-        }
     if (ncases) *ncases = n;
     return bad;
 }

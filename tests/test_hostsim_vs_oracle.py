@@ -83,17 +83,6 @@ def test_classify_hot_equals_classify_record():
     assert n.value > 10 ** 7
 
 
-def test_change_matters_equals_its_definition():
-    """The filter that decides whether a changed deletion time of a neighbour requires another walk of a component."""
-    import ctypes as C
-    hs = util.hostsim_lib()
-    hs.hostsim_change_matters_check.restype = C.c_long
-    hs.hostsim_change_matters_check.argtypes = [C.POINTER(C.c_long)]
-    n = C.c_long(0)
-    assert hs.hostsim_change_matters_check(C.byref(n)) == 0
-    assert n.value > 10000
-
-
 def test_classifier_truth_table():
     """pe_classify truth table (reference TestIlluminaPEReadClassifier.cpp only prints it; asserted here
     against IlluminaPEReadClassifier.cpp:13-101 by enumeration through the oracle's classifier)."""
