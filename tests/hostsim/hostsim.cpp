@@ -211,7 +211,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
         for (size_t k = 0; k < ranges.size(); ++k) { int u = 0; for (size_t t = ranges[k].first; t < ranges[k].second; ++t) u += we[t].src <= we[t].dst; base[k + 1] = base[k] + u; }
         for (size_t k = ranges.size(); k-- > 0;) {
             const size_t i = ranges[k].first, j = ranges[k].second;
-            se.clear(); for (size_t t = i; t < j; ++t) se.push_back({we[t].src, we[t].dst});
+            se.clear(); for (size_t t = i; t < j; ++t) { SEdge x; x.src = we[t].src; x.dst = we[t].dst; se.push_back(x); }
             fl.assign(j - i, 0); queue.assign(j - i + 2, 0);
             slot0 = base[k];
             const int used = k4n_window_calls(del.data(), c1.data(), se.data(), (int)(j - i), fl.data(), queue.data(), we[i].win, slot0, rows.data(), row_key.data(), row_emit.data());
