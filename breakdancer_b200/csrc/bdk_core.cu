@@ -82,10 +82,9 @@ struct bdk_ctx {
     // finish() work space
     DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region,
         d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt,
-        d_se, d_se2, d_wstart, d_wend, d_slot_base, d_sefl, d_queue, d_rowpack, d_outpack, d_slot_order, d_sort_hist, d_pois_l, d_pois_k, d_pois_o;
+        d_se, d_se2, d_wstart, d_wdir, d_wund, d_wfill, d_slot_base, d_sefl, d_queue, d_biglist, d_rowpack, d_outpack, d_slot_order, d_pois_l, d_pois_k, d_pois_o;
     uint64_t d2h_bytes = 0;
     uint32_t rows_guess = 0;      // rows the first result copy brings back (a second copy follows only when there are more)
-    uint32_t sort_single_max = 1u << 22;   // anomalous reads up to which the followed edges are sorted by one CTA (BDK_SORT_SINGLE_MAX)
     uint32_t n_slots = 0;
     void* h_pack = nullptr;       // pinned host block the row outputs + summary are copied into
     size_t h_pack_cap = 0;
@@ -112,10 +111,12 @@ struct bdk_ctx {
     uint32_t A_local = 0;             // anomalous reads of this rank's slice (c->A becomes the global count)
     uint64_t comm_bytes = 0;          // bytes this rank received in the exchanges of the last job
     DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff;
-    DevBuf d_del, d_stamp, d_k4sync, d_never_final, d_c1, d_ri;   // K4: table of deletion windows, sweep stamps, barrier / counters
+    DevBuf d_del, d_stamp, d_k4sync, d_c1, d_ri;   // K4: table of deletion windows, sweep stamps, barrier / counters
     uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
     bool k4_host_loop = false;                // BDK_K4_HOST_LOOP (tests): one launch per sweep instead of the persistent kernel
+    uint32_t k4w_cap = K4W_CAP;               // BDK_K4W_CAP (tests): directed edges up to which a window is handled by one warp
+    uint32_t rows_guess_min = 1024;           // BDK_ROWS_GUESS (tests): floor of the first result copy
 };
 
 namespace {
@@ -392,13 +393,13 @@ void bdk_destroy(bdk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) { if (NcclApi* nc = nccl_api()) nc->CommDestroy(c->comm); }
     c->comm = nullptr;
-    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_del, &c->d_stamp, &c->d_k4sync, &c->d_never_final, &c->d_c1, &c->d_ri,
+    DevBuf* all[] = {&c->d_hdr, &c->d_hdr_all, &c->d_ar_g, &c->d_P_g, &c->d_koff, &c->d_del, &c->d_stamp, &c->d_k4sync, &c->d_c1, &c->d_ri,
         &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_mate, &c->d_sv_of_read,
         &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt,
-        &c->d_se, &c->d_se2, &c->d_wstart, &c->d_wend, &c->d_slot_base, &c->d_sefl, &c->d_queue, &c->d_rowpack, &c->d_outpack, &c->d_slot_order,
-        &c->d_sort_hist, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
+        &c->d_se, &c->d_se2, &c->d_wstart, &c->d_wdir, &c->d_wund, &c->d_wfill, &c->d_slot_base, &c->d_sefl, &c->d_queue, &c->d_biglist, &c->d_rowpack, &c->d_outpack,
+        &c->d_slot_order, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
@@ -529,7 +530,8 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
             CUC(cudaMalloc(&c->d_k4sync.p, 64 + sizeof(K4Trace))); c->d_k4sync.cap = 64 + sizeof(K4Trace);
         }
         if (const char* e = getenv("BDK_K4_HOST_LOOP")) c->k4_host_loop = atoi(e) != 0;
-        if (const char* e = getenv("BDK_SORT_SINGLE_MAX")) c->sort_single_max = (uint32_t)std::max(0, atoi(e));   // tests: force either sort
+        if (const char* e = getenv("BDK_K4W_CAP")) c->k4w_cap = (uint32_t)std::max(0, std::min(atoi(e), (int)K4W_CAP));
+        if (const char* e = getenv("BDK_ROWS_GUESS")) c->rows_guess_min = (uint32_t)std::max(0, atoi(e));
         if (const char* e = getenv("BDK_SEG_CAP_MIN")) c->seg_cap_min = (uint32_t)std::max(1, atoi(e));   // tests: force the segment-overflow retry
     }
     int rc = reset_job(c);
@@ -683,9 +685,10 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     uint32_t tsize = 1024; while (tsize < 2 * (uint64_t)A) tsize <<= 1;
     ENS(c->d_table, (size_t)tsize * 4);
     const size_t nwin_cap = A1 / (size_t)period + 2;
-    ENS(c->d_del, A1 * 4); ENS(c->d_stamp, A1 * 4); ENS(c->d_never_final, A1); ENS(c->d_c1, A1 * 4); ENS(c->d_ri, A1 * sizeof(ReadInfo2));
-    ENS(c->d_se, A1 * 8); ENS(c->d_se2, A1 * 8); ENS(c->d_sefl, A1); ENS(c->d_queue, (A1 + nwin_cap) * 4);
-    ENS(c->d_wstart, nwin_cap * 4); ENS(c->d_wend, nwin_cap * 4); ENS(c->d_slot_base, nwin_cap * 4);
+    ENS(c->d_del, A1 * 4); ENS(c->d_stamp, A1 * 4); ENS(c->d_c1, A1 * 4); ENS(c->d_ri, A1 * sizeof(ReadInfo2));
+    ENS(c->d_se, A1 * 8); ENS(c->d_se2, 2 * A1 * 8); ENS(c->d_sefl, A1); ENS(c->d_queue, (A1 + nwin_cap) * 4);
+    ENS(c->d_wstart, nwin_cap * 4); ENS(c->d_wdir, nwin_cap * 4); ENS(c->d_wund, nwin_cap * 4); ENS(c->d_wfill, nwin_cap * 4);
+    ENS(c->d_slot_base, nwin_cap * 4); ENS(c->d_biglist, nwin_cap * 4);
 
     // ---- K2 ----------------------------------------------------------------------------------
     const int dummy = dummy_region_of(c->P);
@@ -711,35 +714,21 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     CU(cudaMemsetAsync(c->d_mate.p, 0xff, (size_t)A * 4, st));
     CU(cudaMemsetAsync(c->d_ekeys.p, 0xff, (size_t)esize * 8, st));
     CU(cudaMemsetAsync(c->d_ecnt.p, 0, (size_t)esize * 4, st));
-    CU(cudaMemsetAsync(c->d_wstart.p, 0, nwin_cap * 4, st));
-    CU(cudaMemsetAsync(c->d_wend.p, 0, nwin_cap * 4, st));
+    CU(cudaMemsetAsync(c->d_wdir.p, 0, nwin_cap * 4, st));
+    CU(cudaMemsetAsync(c->d_wund.p, 0, nwin_cap * 4, st));
     unsigned long long* ekeys = c->d_ekeys.as<unsigned long long>();
     uint32_t* ecnt = c->d_ecnt.as<uint32_t>();
     k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
     k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
     k3_read_info_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), c->d_read_cand.as<int32_t>(),
         c->d_reg.as<RegionRec>(), d_cnt, period, c->P.min_read_pair, ekeys, ecnt, esize - 1, A, c->d_ri.as<ReadInfo2>(), c->d_sv_of_read.as<int32_t>());
-    k3_strong_edges_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->P.min_read_pair, c->d_se.as<unsigned long long>(), d_cnt);
-    c->launches += 4;
-    // the followed edges in the order (window, src, dst)
-    int vbits = 1; while ((1ull << vbits) < (uint64_t)A + 2) ++vbits;
-    int wbits = 1; while ((1ull << wbits) < (uint64_t)nwin_cap + 1) ++wbits;
-    const SEdgeDigit digit{(vbits + 7) / 8, period};
-    const int npasses = 2 * digit.nbv + (wbits + 7) / 8;
-    unsigned long long* se_sorted;
-    if (A <= c->sort_single_max) {
-        WindowRangesEpilogue epi{period, c->d_wstart.as<int32_t>(), c->d_wend.as<int32_t>(), c->d_slot_base.as<int32_t>(), d_cnt + CNT_NROW};
-        sort_single_cta_kernel<<<1, SORT1_THREADS, 0, st>>>(c->d_se.as<unsigned long long>(), c->d_se2.as<unsigned long long>(), d_cnt + CNT_NSE, digit, npasses, epi);
-        se_sorted = (npasses & 1) ? c->d_se2.as<unsigned long long>() : c->d_se.as<unsigned long long>();
-        c->launches += 1;
-    } else {
-        ENS(c->d_sort_hist, 256 * SS_GRID * 4);
-        SortScratch sosc{c->d_sort_hist.as<uint32_t>(), c->d_se2.as<unsigned long long>()};
-        se_sorted = device_radix_sort(st, c->d_se.as<unsigned long long>(), d_cnt + CNT_NSE, digit, npasses, sosc);
-        device_scan(st, SEdgeUndirected{se_sorted}, WindowRangesOut{se_sorted, period, c->d_wstart.as<int32_t>(), c->d_wend.as<int32_t>(), c->d_slot_base.as<int32_t>()},
-                    d_cnt + CNT_NSE, d_cnt + CNT_NROW, 0, ssc);
-        c->launches += 3 * (uint64_t)npasses + 3;
-    }
+    // the followed edges, bucketed by flush window
+    k3_strong_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->P.min_read_pair, period, c->d_wdir.as<uint32_t>(), c->d_wund.as<uint32_t>());
+    k3_window_scan_kernel<<<1, K3S_THREADS, 0, st>>>(c->d_wdir.as<uint32_t>(), c->d_wund.as<uint32_t>(), period, c->d_wstart.as<uint32_t>(),
+                                                     c->d_slot_base.as<uint32_t>(), c->d_wfill.as<uint32_t>(), d_cnt);
+    k3_strong_scatter_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->P.min_read_pair, period, c->d_wstart.as<uint32_t>(), c->d_wfill.as<uint32_t>(),
+                                                             c->d_se.as<unsigned long long>());
+    c->launches += 6;
     tstop(c, T_K3);
     CU(cudaGetLastError());
 
@@ -750,18 +739,17 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_rows = 0, o_lc = al(o_rows + R1 * sizeof(bdk_sv)), o_cc = al(o_lc + R1 * 4 * nlib), o_cn = al(o_cc + R1 * 4 * nkey),
                  out_bytes = al(o_cn + R1 * 4 * nkey);                                                             // compacted block (device)
-    const size_t w_emit = al(out_bytes), w_key = al(w_emit + R1), w_span = al(w_key + R1 * 8), work_bytes = al(w_span + R1 * 4 * nlib);   // slot-indexed block
+    const size_t w_emit = al(out_bytes), w_span = al(w_emit + R1), work_bytes = al(w_span + R1 * 4 * nlib);   // slot-indexed block
     ENS(c->d_rowpack, work_bytes); ENS(c->d_outpack, out_bytes); ENS(c->d_slot_order, R1 * 4);
     char* dp = (char*)c->d_rowpack.p;
     char* op = (char*)c->d_outpack.p;
     CU(cudaMemsetAsync(dp + w_emit, 0, R1, st));
-    CU(cudaMemsetAsync(c->d_sefl.p, 0, A1, st));
     K4N KS;
     KS.ri = c->d_ri.as<ReadInfo2>(); KS.ar = c->d_ar.as<bdk_aread>(); KS.reg = c->d_reg.as<RegionRec>();
     KS.nreg = 0; KS.period = period; KS.chr_restricted = c->P.chr_restricted; KS.min_read_pair = c->P.min_read_pair;
     K4Tab Tb;
-    Tb.del = c->d_del.as<int32_t>(); Tb.stamp = c->d_stamp.as<uint32_t>(); Tb.never_final = c->d_never_final.as<uint8_t>(); Tb.c1 = c->d_c1.as<int32_t>();
-    Tb.summary = c->d_summary.as<bdk_summary_t>(); Tb.d_cnt = d_cnt;
+    Tb.del = c->d_del.as<int32_t>(); Tb.stamp = c->d_stamp.as<uint32_t>(); Tb.c1 = c->d_c1.as<int32_t>(); Tb.d_cnt = d_cnt;
+    Tb.count_changes = getenv("BDK_K4_TRACE") ? 1 : 0;
     K4Static S;
     memset(&S, 0, sizeof S);
     S.ar = c->d_ar.as<bdk_aread>(); S.reg = c->d_reg.as<RegionRec>(); S.P = c->d_P.as<uint32_t>();
@@ -772,7 +760,6 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     K4Mut M;
     M.rows = (bdk_sv*)(dp + o_rows); M.row_lib_count = (int32_t*)(dp + o_lc); M.row_lib_span = (int32_t*)(dp + w_span);
     M.row_cn_count = (uint32_t*)(dp + o_cc); M.row_cn = (float*)(dp + o_cn); M.row_emit = (uint8_t*)(dp + w_emit);
-    uint64_t* row_key = (uint64_t*)(dp + w_key);
     K4NOut KO{c->d_sv_of_read.as<int32_t>(), M.rows, M.row_lib_count, M.row_lib_span, M.row_emit, nlib};
     tstart(c, T_K4);
     c->k4_sweeps = 0;
@@ -781,10 +768,10 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     K4Trace* trace = getenv("BDK_K4_TRACE") ? (K4Trace*)((char*)c->d_k4sync.p + 64) : nullptr;
     {
         const unsigned rgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(A1, 32 * (K4_THREADS / 32)), (uint64_t)kNumSMs * 8));
-        k4n_init_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb);
-        c->launches += 1;
         bool host_loop = c->k4_host_loop;
         CU(cudaMemsetAsync(sync, 0, 64, st));
+        CU(cudaMemsetAsync(c->d_del.p, 0x7f, A1 * 4, st));           // K4_NEVER everywhere: the sweeps start from an empty table
+        CU(cudaMemsetAsync(c->d_stamp.p, 0, A1 * 4, st));
         if (trace) CU(cudaMemsetAsync(trace, 0, sizeof(K4Trace), st));
         if (!host_loop) {           // one persistent cooperative kernel, a grid-wide barrier between the sweeps
             const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(A1, 32 * (K4_THREADS / 32)), (uint64_t)c->k4_grid_max));
@@ -799,8 +786,8 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         if (host_loop) {
             for (uint32_t sweep = 0;; ++sweep) {
                 if (sweep > 1000000) return fail(c, BDK_ERR_STATE, "the table of deletion windows did not reach a fixed point");
-                CU(cudaMemsetAsync(d_cnt + CNT_K4_TICKET, 0, 8, st));
-                k4n_sweep_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb, sweep, d_cnt + CNT_K4_TICKET, d_cnt + CNT_K4_CHANGED);
+                CU(cudaMemsetAsync(d_cnt + CNT_K4_CHANGED, 0, 4, st));
+                k4n_sweep_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb, sweep, d_cnt + CNT_K4_CHANGED);
                 c->launches += 1;
                 uint32_t nchanged = 0;
                 CU(cudaMemcpyAsync(&nchanged, d_cnt + CNT_K4_CHANGED, 4, cudaMemcpyDeviceToHost, st));
@@ -810,13 +797,18 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
             }
         }
         k4n_first_call_kernel<<<rgrid, K4_THREADS, 0, st>>>(KS, Tb);
-        const unsigned wgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(nwin_cap, K4W_THREADS), (uint64_t)kNumSMs * 16));
-        k4n_windows_kernel<<<wgrid, K4W_THREADS, 0, st>>>(Tb, se_sorted, c->d_wstart.as<int32_t>(), c->d_wend.as<int32_t>(), c->d_slot_base.as<int32_t>(),
-                                                          c->d_sefl.as<uint8_t>(), c->d_queue.as<int32_t>(), period, M.rows, row_key, M.row_emit);
+        K4Windows W;
+        W.se = c->d_se.as<unsigned long long>(); W.wstart = c->d_wstart.as<uint32_t>(); W.wdir = c->d_wdir.as<uint32_t>(); W.slot_base = c->d_slot_base.as<uint32_t>();
+        W.scratch = c->d_se2.as<unsigned long long>(); W.fl = c->d_sefl.as<uint8_t>(); W.queue = c->d_queue.as<int32_t>();
+        W.big_list = c->d_biglist.as<uint32_t>(); W.big_count = d_cnt + CNT_K4_NBIGWIN;
+        W.rows = M.rows; W.row_emit = M.row_emit; W.period = period; W.cap = c->k4w_cap;
+        const unsigned wgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(nwin_cap, K4W_WARPS), (uint64_t)kNumSMs * 16));
+        k4n_windows_kernel<<<wgrid, K4W_WARPS * 32, 0, st>>>(Tb, W);
+        k4n_big_windows_kernel<<<kNumSMs, K4WB_THREADS, 0, st>>>(Tb, W);
         const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(R1, K4_THREADS / 32), (uint64_t)kNumSMs * 8));
         k4n_calls_kernel<<<cgrid, K4_THREADS, 0, st>>>(KS, KO, d_cnt);
         k4_score_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, c->d_summary.as<bdk_summary_t>(), d_cnt);
-        c->launches += 4;
+        c->launches += 5;
     }
     tstop(c, T_K4);
     CU(cudaGetLastError());
@@ -830,7 +822,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     CU(cudaGetLastError());
     // The number of rows is only known on the device: the first copy brings the counters, the summary and the first `guess`
     // rows (sized from the previous job on this context, else from A); a second copy follows only if there are more.
-    const size_t guess = std::min<size_t>(R1, std::max<size_t>(c->rows_guess, (size_t)A / 64 + 1024));
+    const size_t guess = std::min<size_t>(R1, std::max<size_t>(c->rows_guess, c->rows_guess_min == 1024 ? (size_t)A / 64 + 1024 : (size_t)c->rows_guess_min));
     auto host_layout = [&](size_t cap, size_t* h_lc, size_t* h_cc, size_t* h_cn, size_t* h_cnt, size_t* h_sum, size_t* h_sync) {
         *h_lc = al(cap * sizeof(bdk_sv)); *h_cc = al(*h_lc + cap * 4 * nlib); *h_cn = al(*h_cc + cap * 4 * nkey);
         *h_cnt = al(*h_cn + cap * 4 * nkey); *h_sum = al(*h_cnt + CNT_N * 4); *h_sync = al(*h_sum + sizeof(bdk_summary_t));

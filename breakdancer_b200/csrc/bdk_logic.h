@@ -469,72 +469,54 @@ BDK_HD ReadInfo2 k4n_make_read_info(const bdk_aread* ar, const int32_t* mate, co
     return r;
 }
 
-// A stored read that is held for ever with a name entry of size 1: is_region_final(v) is false in every window.
-template <class Team>
-BDK_HD bool k4n_never_final(const Team& T, const K4N& S, int v) {
-    const RegionRec R = S.reg[v];
-    bool bad = false;
-    if (R.stored)
-        for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
-            const ReadInfo2 I = S.ri[j];
-            if (S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX) continue;
-            if (I.mate < 0 || (I.mate_region < 0 && I.mate < j)) bad = true;
-        }
-    return T.any(bad);
-}
-
 // The flush window in which region v is cleared, given the deletion windows del[] of the other regions.
+// One pass over the region's reads finds its first active window (and whether a read is held for ever with a name entry
+// of size 1, which keeps the region from ever being final); then one pass per active window tried.
 template <class Team>
 BDK_HD int k4n_region_deletion(const Team& T, const K4N& S, const int32_t* del, int v) {
     const RegionRec R = S.reg[v];
     const int j0 = R.first_read, j1 = R.first_read + R.n_reads, wv = v / S.period;
-    int w = -1;
-    for (;;) {
-        // next window in which v is an active node: the windows of its edges = max(v, mate's region) / period
-        int wn = K4_NEVER, lc = -1, intra = 0;
+    int w = K4_NEVER;
+    bool never = false;
+    for (int j = j0 + T.lane(); j < j1; j += T.width()) {
+        const ReadInfo2 I = S.ri[j];
+        const int rm = I.mate_region;
+        if (rm >= 0) { const int aw = (rm > v ? rm : v) / S.period; if (aw < w) w = aw; }
+        else if (R.stored && !(S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX) && (I.mate < 0 || I.mate < j)) never = true;
+    }
+    if (T.any(never)) return K4_NEVER;
+    w = T.min(w);                                      // the windows of v's edges = max(v, mate's region) / period
+    while (w != K4_NEVER) {
+        // lc: latest window <= w in which process_sv was called with v; maxc: latest collapse a held read waits for
+        int wn = K4_NEVER, lc = -1, intra = 0, maxc = -1;
+        bool bad = false;
         for (int j = j0 + T.lane(); j < j1; j += T.width()) {
             const ReadInfo2 I = S.ri[j];
             const int rm = I.mate_region;
-            if (rm < 0) continue;
+            const bool skip = S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX;     // is_region_final does not look at these
+            if (rm < 0) { if (!skip && I.wthr > maxc) maxc = I.wthr; continue; }         // later mate collapsed: held until a call after that drops it
+            if (rm == v) { ++intra; continue; }                                           // an unconsumed pair inside v has a name entry of size 2 (its window, wv, is v's first)
             const int aw = (rm > v ? rm : v) / S.period;
             if (aw > w && aw < wn) wn = aw;
-        }
-        wn = T.min(wn);
-        if (wn == K4_NEVER) return K4_NEVER;
-        w = wn;
-        if (v == k4n_last_region(S, w)) continue;
-        if (!R.stored) return w;                       // holds no reads: final the first time it is asked
-        // latest window <= w in which process_sv was called with v
-        for (int j = j0 + T.lane(); j < j1; j += T.width()) {
-            const ReadInfo2 I = S.ri[j];
-            const int rm = I.mate_region;
-            if (rm < 0) continue;
-            if (rm == v) { ++intra; continue; }
-            if (!(I.meta & RI_STRONG)) continue;
-            const int wp = (rm > v ? rm : v) / S.period;
-            if (wp <= w && wp > lc && k4n_ld(del + rm) >= wp) lc = wp;
-        }
-        lc = T.max(lc);
-        if (T.sum(intra) / 2 >= S.min_read_pair && wv > lc) lc = wv;       // the self loop: process_sv(v) in v's own window
-        bool bad = false;
-        for (int j = j0 + T.lane(); j < j1 && !bad; j += T.width()) {
-            const ReadInfo2 I = S.ri[j];
-            if (S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX) continue;
-            const int rm = I.mate_region;
-            if (rm == v) continue;                     // an unconsumed pair inside v has a name entry of size 2
-            if (rm < 0) {
-                if (I.mate < 0 || I.mate < j) bad = true;                  // (never final; callers filter these regions out)
-                else bad = !(lc >= I.wthr);                                // held until a call after the mate's collapse drops it
-                continue;
-            }
-            const int wp = (rm > v ? rm : v) / S.period;
-            if (w < wp) { bad = true; continue; }      // mate not registered yet
             const int d = k4n_ld(del + rm);
-            if ((I.meta & (RI_STRONG | RI_MATE_STORED)) == (RI_STRONG | RI_MATE_STORED) && d >= wp) continue;   // consumed by process_sv(v, rm)
-            if ((I.meta & RI_MATE_STORED) && k4n_before(d, w, rm, v)) bad = true;  // clear_region(rm) took rm out of the name entry
+            if ((I.meta & RI_STRONG) && aw <= w && d >= aw) {                             // process_sv(v, rm) was called in window aw
+                if (aw > lc) lc = aw;
+                if (I.meta & RI_MATE_STORED) continue;                                    // ... and consumed the pair
+            }
+            if (skip) continue;
+            if (w < aw) bad = true;                                                       // mate not registered yet
+            else if ((I.meta & RI_MATE_STORED) && k4n_before(d, w, rm, v)) bad = true;    // clear_region(rm) took rm out of the name entry
         }
-        if (!T.any(bad)) return w;
+        wn = T.min(wn); lc = T.max(lc); maxc = T.max(maxc); intra = T.sum(intra);
+        const bool blocked = T.any(bad);
+        if (v != k4n_last_region(S, w)) {
+            if (!R.stored) return w;                   // holds no reads: final the first time it is asked
+            if (intra / 2 >= S.min_read_pair && wv > lc) lc = wv;                         // the self loop: process_sv(v) in v's own window
+            if (!blocked && !(maxc > lc)) return w;
+        }
+        w = wn;
     }
+    return K4_NEVER;
 }
 
 // first window in which process_sv is called with region v (K4_NEVER: never), given the final table
@@ -560,46 +542,53 @@ BDK_HD int k4n_first_call(const Team& T, const K4N& S, const int32_t* del, int v
 
 // ---- the calls of one flush window, in build_connection's order --------------------------------------------------
 // e[0..n): the directed copies (src, dst) of the followed edges (weight >= -r) of window w, sorted by (src, dst);
-// fl[0..n): scratch flags, zero on entry; queue: n + 1 entries. Sequential (one thread per window): vertices ascending,
-// BFS from each, a tail's edges ascending, every live edge followed once (BreakDancer.cpp:280-338). Call k goes to
-// slot0 + k; returns the number of calls. A call is FIRST for one of its regions when no earlier call (in an earlier
-// window: c1[] < w, or earlier in this one) involved that region.
+// fl[0..n): flags; queue: n + 1 entries.
+//   k4n_window_prepare  (per edge, independent): an edge one of whose regions is already cleared is as good as erased; a
+//                       region with a call in an earlier window (c1[] < w) starts out touched;
+//   k4n_window_calls    sequential, no table reads: vertices ascending, BFS from each, a tail's edges ascending, every live
+//                       edge followed once (BreakDancer.cpp:280-338). Call k goes to slot0 + k; returns the number of calls.
+// A call is FIRST for one of its regions when no earlier call (in an earlier window, or earlier in this one) involved it.
 struct SEdge { int32_t dst, src; };   // as one u64: src << 32 | dst
 enum : uint8_t { SE_ERASED = 1, SE_VDONE = 2, SE_TOUCHED = 4 };
 enum : uint8_t { K4_ROW_CALL = 4, K4_ROW_FIRST0 = 8, K4_ROW_FIRST1 = 16 };   // row_emit[] of a slot between k4n_window_calls and k4n_call
 
-BDK_HD int k4n_find_run(const SEdge* e, int n, int src) {
+template <class E> BDK_HD int k4n_find_run(const E* e, int n, int src) {
     int a = 0, b = n;
     while (a < b) { const int m = (a + b) >> 1; if (e[m].src < src) a = m + 1; else b = m; }
     return (a < n && e[a].src == src) ? a : -1;
 }
-BDK_HD int k4n_find_edge(const SEdge* e, int n, int src, int dst) {
+template <class E> BDK_HD int k4n_find_edge(const E* e, int n, int src, int dst) {
     int a = 0, b = n;
     while (a < b) { const int m = (a + b) >> 1; if (e[m].src < src || (e[m].src == src && e[m].dst < dst)) a = m + 1; else b = m; }
     return (a < n && e[a].src == src && e[a].dst == dst) ? a : -1;
 }
 
-BDK_HD int k4n_window_calls(const int32_t* del, const int32_t* c1, const SEdge* e, int n, uint8_t* fl, int32_t* queue, int w, int slot0,
-                            bdk_sv* rows, uint64_t* row_key, uint8_t* row_emit) {
+template <class E, class F> BDK_HD void k4n_window_prepare(const int32_t* del, const int32_t* c1, const E* e, int n, F* fl, int w, int k) {
+    const int src = e[k].src, dst = e[k].dst;
+    uint8_t f = (del[src] < w || del[dst] < w) ? SE_ERASED : 0;      // !region_exists(tail) / !region_exists(s1)
+    if ((k == 0 || e[k - 1].src != src) && c1[src] < w) f |= SE_TOUCHED;
+    fl[k] = f;
+}
+
+template <class E, class F, class Q>
+BDK_HD int k4n_window_calls(const E* e, int n, F* fl, Q* queue, int w, int slot0, bdk_sv* rows, uint8_t* row_emit) {
     int slot = slot0;
     for (int vi = 0; vi < n;) {
         const int v = e[vi].src;
         int vend = vi;
         while (vend < n && e[vend].src == v) ++vend;
-        if (!(fl[vi] & SE_VDONE) && del[v] >= w) {
+        if (!(fl[vi] & SE_VDONE)) {
             int qa = 0, qb = 1, qn;
             queue[0] = v;
             while (qa < qb) {
                 qn = qb;
                 for (int t = qa; t < qb; ++t) {
                     const int tail = queue[t];
-                    if (del[tail] < w) continue;                               // !region_exists(tail)
-                    const int ts = k4n_find_run(e, n, tail);
+                    const int ts = tail == v ? vi : k4n_find_run(e, n, tail);
                     if (ts < 0 || (fl[ts] & SE_VDONE)) continue;               // graph.find(tail) == end
                     for (int k = ts; k < n && e[k].src == tail; ++k) {
                         if (fl[k] & SE_ERASED) continue;
                         const int s1 = e[k].dst;
-                        if (del[s1] < w) continue;                             // !region_exists(s1)
                         fl[k] |= SE_ERASED;
                         int r1 = ts;
                         if (s1 != tail) {
@@ -608,13 +597,12 @@ BDK_HD int k4n_window_calls(const int32_t* del, const int32_t* c1, const SEdge* 
                             r1 = k4n_find_run(e, n, s1);
                         }
                         queue[qn++] = s1;
-                        const bool first_t = !(c1[tail] < w) && !(fl[ts] & SE_TOUCHED);
-                        const bool first_s = s1 == tail ? first_t : (!(c1[s1] < w) && !(fl[r1] & SE_TOUCHED));
+                        const bool first_t = !(fl[ts] & SE_TOUCHED);
+                        const bool first_s = s1 == tail ? first_t : !(fl[r1] & SE_TOUCHED);
                         fl[ts] |= SE_TOUCHED; fl[r1] |= SE_TOUCHED;
                         const int a = tail < s1 ? tail : s1, b = tail < s1 ? s1 : tail;
                         bdk_sv& o = rows[slot];
                         o.region[0] = a; o.region[1] = s1 != tail ? b : -1; o.window = w;
-                        row_key[slot] = ((uint64_t)(uint32_t)w << 32) | (uint32_t)v;
                         const bool f0 = a == tail ? first_t : first_s, f1 = a == tail ? first_s : first_t;
                         row_emit[slot] = (uint8_t)(K4_ROW_CALL | (f0 ? K4_ROW_FIRST0 : 0) | (s1 != tail && f1 ? K4_ROW_FIRST1 : 0));
                         ++slot;

@@ -14,7 +14,7 @@
 
 namespace bdk {
 
-enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NSE, CNT_NROW, CNT_ERR, CNT_NEMIT, CNT_K4_TICKET, CNT_K4_CHANGED, CNT_N };
+enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NSE, CNT_NROW, CNT_ERR, CNT_NEMIT, CNT_K4_CHANGED, CNT_K4_NBIGWIN, CNT_N };
 constexpr uint32_t K3_ERR_DUPNAME = 1u;
 constexpr int GS_THREADS = 256;
 constexpr int GS_GRID = kNumSMs * 4;
@@ -173,75 +173,57 @@ __global__ void __launch_bounds__(GS_THREADS) k3_read_info_kernel(const bdk_area
     }
 }
 
-// the followed edges (weight >= -r) as directed copies src << 32 | dst, in table order
-__global__ void __launch_bounds__(GS_THREADS) k3_strong_edges_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
-        int32_t min_read_pair, unsigned long long* __restrict__ se, uint32_t* __restrict__ d_cnt) {
+// ---- the followed edges (weight >= -r), bucketed by flush window ------------------------------------------------------
+// An edge (r0 <= r1) belongs to the window in which r1 is registered. Pass 1 counts per window the directed copies and
+// the edges themselves (= call slots); one CTA scans the windows; pass 2 puts the directed copies (src << 32 | dst) into
+// their window's range, in arrival order -- each window's warp sorts its own few edges (k4n_windows_kernel).
+__global__ void __launch_bounds__(GS_THREADS) k3_strong_count_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
+        int32_t min_read_pair, int period, uint32_t* __restrict__ wdir, uint32_t* __restrict__ wund) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
         const unsigned long long k = tkeys[e];
         if (k == EDGE_EMPTY || (int32_t)tcnt[e] < min_read_pair) continue;
-        const uint32_t r0 = (uint32_t)(k >> 32), r1 = (uint32_t)k;
+        const uint32_t r0 = (uint32_t)(k >> 32), r1 = (uint32_t)k, w = r1 / (uint32_t)period;
+        atomicAdd(wdir + w, r0 != r1 ? 2u : 1u);
+        atomicAdd(wund + w, 1u);
+    }
+}
+constexpr int K3S_THREADS = 1024;
+__global__ void __launch_bounds__(K3S_THREADS) k3_window_scan_kernel(const uint32_t* __restrict__ wdir, const uint32_t* __restrict__ wund, int period,
+        uint32_t* __restrict__ wstart, uint32_t* __restrict__ slot_base, uint32_t* __restrict__ wfill, uint32_t* __restrict__ d_cnt) {
+    __shared__ uint32_t s_a[33], s_b[33];
+    const uint32_t nwin = d_cnt[CNT_NREG] / (uint32_t)period + 1;
+    uint32_t run_a = 0, run_b = 0;
+    for (uint32_t base = 0; base < nwin; base += K3S_THREADS) {
+        const uint32_t w = base + threadIdx.x;
+        const uint32_t a = w < nwin ? wdir[w] : 0, b = w < nwin ? wund[w] : 0;
+        uint32_t ta, tb;
+        const uint32_t ia = ss_block_scan_any(a, s_a, &ta), ib = ss_block_scan_any(b, s_b, &tb);
+        if (w < nwin) { wstart[w] = run_a + ia - a; slot_base[w] = run_b + ib - b; wfill[w] = 0; }
+        run_a += ta; run_b += tb;
+    }
+    if (threadIdx.x == 0) { d_cnt[CNT_NSE] = run_a; d_cnt[CNT_NROW] = run_b; }
+}
+__global__ void __launch_bounds__(GS_THREADS) k3_strong_scatter_kernel(const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t tsize,
+        int32_t min_read_pair, int period, const uint32_t* __restrict__ wstart, uint32_t* __restrict__ wfill, unsigned long long* __restrict__ se) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < tsize; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = tkeys[e];
+        if (k == EDGE_EMPTY || (int32_t)tcnt[e] < min_read_pair) continue;
+        const uint32_t r0 = (uint32_t)(k >> 32), r1 = (uint32_t)k, w = r1 / (uint32_t)period;
         const uint32_t n = r0 != r1 ? 2u : 1u;
-        const uint32_t at = atomicAdd(d_cnt + CNT_NSE, n);
+        const uint32_t at = wstart[w] + atomicAdd(wfill + w, n);
         se[at] = k;
         if (n == 2) se[at + 1] = ((unsigned long long)r1 << 32) | r0;
     }
 }
 
-// radix digits of a directed edge for the order (window, src, dst): nbv bytes of dst, nbv bytes of src, then the window
-struct SEdgeDigit {
-    int nbv, period;
-    __device__ __forceinline__ uint32_t operator()(unsigned long long k, int pass) const {
-        if (pass < nbv) return (uint32_t)(k >> (8 * pass)) & 0xffu;
-        if (pass < 2 * nbv) return (uint32_t)(k >> (32 + 8 * (pass - nbv))) & 0xffu;
-        const uint32_t src = (uint32_t)(k >> 32), dst = (uint32_t)k;
-        return ((max(src, dst) / (uint32_t)period) >> (8 * (pass - 2 * nbv))) & 0xffu;
-    }
-};
-__device__ __forceinline__ uint32_t se_window(unsigned long long k, int period) { return max((uint32_t)(k >> 32), (uint32_t)k) / (uint32_t)period; }
-
-// After the sort: where each window's edges start and end, and its first call slot (= the number of followed edges,
-// counted once, in the windows before it). wstart / wend are zeroed beforehand (windows without edges stay empty).
-struct SEdgeUndirected {
-    const unsigned long long* se;
-    __device__ uint32_t operator()(uint32_t i, uint32_t) const { const unsigned long long k = se[i]; return (uint32_t)(k >> 32) <= (uint32_t)k ? 1u : 0u; }
-};
-struct WindowRangesOut {
-    const unsigned long long* se; int period; int32_t* wstart; int32_t* wend; int32_t* slot_base;
-    __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t n) const {
-        const uint32_t w = se_window(se[i], period);
-        if (i == 0 || se_window(se[i - 1], period) != w) { wstart[w] = (int32_t)i; slot_base[w] = (int32_t)(inc - v); }
-        if (i + 1 == n || se_window(se[i + 1], period) != w) wend[w] = (int32_t)(i + 1);
-    }
-};
-// the same as the tail of the single-CTA sort (small inputs: no extra launches)
-struct WindowRangesEpilogue {
-    int period; int32_t* wstart; int32_t* wend; int32_t* slot_base; uint32_t* n_slots;
-    __device__ void operator()(const unsigned long long* se, uint32_t n, uint32_t* s_scratch /* [33] */) const {
-        uint32_t running = 0;
-        for (uint32_t base = 0; base < n; base += blockDim.x) {
-            const uint32_t i = base + threadIdx.x;
-            const unsigned long long k = i < n ? se[i] : 0ull;
-            const uint32_t u = (i < n && (uint32_t)(k >> 32) <= (uint32_t)k) ? 1u : 0u;
-            uint32_t total;
-            const uint32_t inc = ss_block_scan_any(u, s_scratch, &total) + running;
-            if (i < n) {
-                const uint32_t w = se_window(k, period);
-                if (i == 0 || se_window(se[i - 1], period) != w) { wstart[w] = (int32_t)i; slot_base[w] = (int32_t)(inc - u); }
-                if (i + 1 == n || se_window(se[i + 1], period) != w) wend[w] = (int32_t)(i + 1);
-            }
-            running += total;
-        }
-        if (threadIdx.x == 0) *n_slots = running;
-    }
-};
-
 // ---- K4: the connection walk in closed form (bdk_logic.h, "second formulation") ------------------------------------
-//   init     per region: can it ever be final; starting guess of its deletion window
-//   sweeps   one persistent cooperative kernel: regions whose inputs changed are re-evaluated against the table (rewritten
-//            in place) until a sweep changes nothing -- grid-wide barrier between sweeps
-//   calls    first call window per region; one thread per flush window orders the window's calls (build_connection);
-//            one warp per call counts its pairs (process_sv); one thread per call scores it (k4_score_kernel)
-// Regions are handed out 32 at a time: a lane evaluates a small region alone, the warp shares the large ones.
+//   sweeps   one persistent cooperative kernel: the table of deletion windows starts empty; sweep 0 evaluates every region,
+//            a later sweep the regions stamped by a neighbour whose entry changed; the table is rewritten in place; grid-wide
+//            barrier between sweeps, done when a sweep changes nothing
+//   calls    first call window per region; one warp per flush window sorts the window's followed edges in shared memory and
+//            orders its calls (build_connection); one warp per call counts its pairs (process_sv); one thread per call
+//            scores it (k4_score_kernel)
+// Regions are taken 32 at a time: a lane evaluates a small region alone, the warp shares the large ones.
 constexpr int K4_THREADS = 256;
 constexpr int K4N_SOLO_MAX = 64;          // reads up to which one thread evaluates a region by itself
 constexpr int K4_TRACE_SWEEPS = 64;
@@ -249,9 +231,9 @@ struct K4Trace { unsigned long long t[1 + K4_TRACE_SWEEPS]; uint32_t nchanged[K4
 struct K4Tab {
     int32_t* del;                    // [nreg] flush window in which the region is cleared (K4_NEVER: never)
     uint32_t* stamp;                 // [nreg] sweep in which the region is evaluated again
-    uint8_t* never_final;            // [nreg]
     int32_t* c1;                     // [nreg] first window with a call involving the region
-    const bdk_summary_t* summary; const uint32_t* d_cnt;
+    const uint32_t* d_cnt;
+    int32_t count_changes;           // trace: count the changed regions (else: a flag)
 };
 
 template <class Fn>
@@ -267,28 +249,6 @@ __device__ __forceinline__ void k4n_for_block(const K4N& S, uint32_t base, uint3
         big &= big - 1;
         fn(WarpTeam(), (int)(base + l));
     }
-}
-
-__global__ void __launch_bounds__(K4_THREADS) k4n_init_kernel(K4N S, K4Tab Tb) {
-    S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
-    const uint32_t nreg = (uint32_t)S.nreg;
-    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; base < nreg; base += gridDim.x * (blockDim.x >> 5) * 32u)
-        k4n_for_block(S, base, nreg, true, [&](auto T, int v) {
-            const bool nf = k4n_never_final(T, S, v);
-            // starting guess: cleared in the last window it is an active node of
-            const RegionRec R = S.reg[v];
-            int wl = -1;
-            for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
-                const int rm = S.ri[j].mate_region;
-                if (rm >= 0) wl = max(wl, max(v, rm) / S.period);
-            }
-            wl = T.max(wl);
-            if (T.lane() == 0) {
-                Tb.never_final[v] = nf ? 1 : 0;
-                Tb.del[v] = (nf || wl < 0 || v == S.nreg - 1) ? K4_NEVER : wl;
-                Tb.stamp[v] = 0;
-            }
-        });
 }
 
 // grid-wide barrier of a cooperative launch (all CTAs resident): monotone arrival counter. The spin uses relaxed loads
@@ -311,53 +271,51 @@ __device__ __forceinline__ void k4_grid_barrier(uint32_t* counter, uint32_t& epo
     __syncthreads();
 }
 
-// one sweep over the regions stamped `sweep` (sweep 0: all that can ever be final); returns through *changed
-__device__ __forceinline__ void k4n_sweep(const K4N& S, const K4Tab& Tb, uint32_t sweep, uint32_t* ticket, uint32_t* changed) {
-    const unsigned FULL = 0xffffffffu;
+// one sweep: the regions stamped `sweep` (sweep 0: all) against the table, which is rewritten in place; a region whose
+// entry changes stamps the regions its reads' mates sit in for the next sweep
+__device__ __forceinline__ void k4n_sweep(const K4N& S, const K4Tab& Tb, uint32_t sweep, uint32_t* changed) {
     const uint32_t nreg = (uint32_t)S.nreg;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(ticket, 1u) * 32u;
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= nreg) break;
+    const uint32_t nwarp = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (uint32_t base = warp * 32u; base < nreg; base += nwarp * 32u) {
         const uint32_t v0 = base + lane_id();
-        const bool want = v0 < nreg && !Tb.never_final[v0] && (sweep == 0 || __ldcg(Tb.stamp + v0) == sweep);
+        const bool want = v0 < nreg && (sweep == 0 || __ldcg(Tb.stamp + v0) == sweep);
         k4n_for_block(S, base, nreg, want, [&](auto T, int v) {
             const int d = k4n_region_deletion(T, S, Tb.del, v);
             const int old = __ldcg(Tb.del + v);
             if (d == old) return;
             const RegionRec R = S.reg[v];
-            if (T.lane() == 0) { __stcg(Tb.del + v, d); atomicAdd(changed, 1u); }
+            if (T.lane() == 0) {
+                __stcg(Tb.del + v, d);
+                if (Tb.count_changes) atomicAdd(changed, 1u); else __stcg(changed, 1u);
+            }
             for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
                 const int rm = S.ri[j].mate_region;
-                if (rm >= 0 && rm != v && !Tb.never_final[rm]) __stcg(Tb.stamp + rm, sweep + 1);
+                if (rm >= 0 && rm != v) __stcg(Tb.stamp + rm, sweep + 1);
             }
         });
     }
 }
 
-// sync[0]: barrier counter; sync[1 + s % 3]: region tickets of sweep s; sync[4 + s % 3]: regions changed in sweep s;
-// sync[7]: number of sweeps (result)
+// sync[0]: barrier counter; sync[1 + s % 3]: regions changed in sweep s; sync[7]: number of sweeps (result)
 __global__ void __launch_bounds__(K4_THREADS) k4n_sweeps_kernel(K4N S, K4Tab Tb, uint32_t* __restrict__ sync, K4Trace* __restrict__ trace) {
     S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
     uint32_t epoch = 0;
     const bool tr = trace && blockIdx.x == 0 && threadIdx.x == 0;
     if (tr) trace->t[0] = globaltimer_ns();
     for (uint32_t sweep = 0;; ++sweep) {
-        // the counters of the next sweep were last read two barriers ago
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sync[1 + (sweep + 1) % 3] = 0; sync[4 + (sweep + 1) % 3] = 0; }
-        k4n_sweep(S, Tb, sweep, sync + 1 + sweep % 3, sync + 4 + sweep % 3);
+        if (blockIdx.x == 0 && threadIdx.x == 0) sync[1 + (sweep + 1) % 3] = 0;      // last read two barriers ago
+        k4n_sweep(S, Tb, sweep, sync + 1 + sweep % 3);
         k4_grid_barrier(sync, epoch);
-        const uint32_t nchanged = ld_acquire_u32(sync + 4 + sweep % 3);
+        const uint32_t nchanged = ld_acquire_u32(sync + 1 + sweep % 3);
         if (tr && sweep < K4_TRACE_SWEEPS) { trace->t[1 + sweep] = globaltimer_ns(); trace->nchanged[sweep] = nchanged; }
         if (!nchanged) { if (blockIdx.x == 0 && threadIdx.x == 0) sync[7] = sweep + 1; break; }
     }
 }
 
 // the same, one launch per sweep (when the cooperative launch cannot be resident)
-__global__ void __launch_bounds__(K4_THREADS) k4n_sweep_kernel(K4N S, K4Tab Tb, uint32_t sweep, uint32_t* __restrict__ ticket, uint32_t* __restrict__ changed) {
+__global__ void __launch_bounds__(K4_THREADS) k4n_sweep_kernel(K4N S, K4Tab Tb, uint32_t sweep, uint32_t* __restrict__ changed) {
     S.nreg = (int32_t)Tb.d_cnt[CNT_NREG];
-    k4n_sweep(S, Tb, sweep, ticket, changed);
+    k4n_sweep(S, Tb, sweep, changed);
 }
 
 __global__ void __launch_bounds__(K4_THREADS) k4n_first_call_kernel(K4N S, K4Tab Tb) {
@@ -370,16 +328,74 @@ __global__ void __launch_bounds__(K4_THREADS) k4n_first_call_kernel(K4N S, K4Tab
         });
 }
 
-// one thread per flush window: the window's calls in build_connection's order (bdk_logic.h: k4n_window_calls)
-constexpr int K4W_THREADS = 32;
-__global__ void __launch_bounds__(K4W_THREADS) k4n_windows_kernel(K4Tab Tb, const unsigned long long* __restrict__ se, const int32_t* __restrict__ wstart,
-        const int32_t* __restrict__ wend, const int32_t* __restrict__ slot_base, uint8_t* __restrict__ fl, int32_t* __restrict__ queue, int period,
-        bdk_sv* __restrict__ rows, uint64_t* __restrict__ row_key, uint8_t* __restrict__ row_emit) {
-    const uint32_t nwin = Tb.d_cnt[CNT_NREG] / (uint32_t)period + 1;
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nwin; w += gridDim.x * blockDim.x) {
-        const int s = wstart[w], e = wend[w];
-        if (e <= s) continue;
-        k4n_window_calls(Tb.del, Tb.c1, reinterpret_cast<const SEdge*>(se) + s, e - s, fl + s, queue + s + w, (int)w, slot_base[w], rows, row_key, row_emit);
+// ---- the calls of a flush window -------------------------------------------------------------------------------------
+// One warp per window: its followed edges (a few to a few hundred directed copies) are sorted by (src, dst) in shared
+// memory (bitonic), every lane resolves which of them are dead already (a region cleared before this window) and which
+// regions were touched by an earlier window, then lane 0 runs build_connection's walk over the window (bdk_logic.h:
+// k4n_window_calls) entirely out of shared memory. A window with more than K4W_CAP directed edges goes to the list of
+// big windows (k4n_big_windows_kernel: a CTA each, sorted in global memory).
+constexpr int K4W_CAP = 512, K4W_WARPS = 4;
+struct K4Windows {
+    const unsigned long long* se; const uint32_t* wstart; const uint32_t* wdir; const uint32_t* slot_base;
+    unsigned long long* scratch;      // [2 * (number of directed edges)] big windows: padded copy to sort
+    uint8_t* fl; int32_t* queue;      // big windows: flags [directed edges], queue [directed edges + windows]
+    uint32_t* big_list; uint32_t* big_count;
+    bdk_sv* rows; uint8_t* row_emit; int32_t period;
+    uint32_t cap;                     // <= K4W_CAP (tests lower it to send windows to the big-window kernel)
+};
+template <class KeyPtr>
+__device__ __forceinline__ void k4w_bitonic(KeyPtr key, uint32_t n2, uint32_t tid, uint32_t nthreads, bool cta) {
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < n2; i += nthreads) {
+                const uint32_t x = i ^ j;
+                if (x > i) {
+                    const unsigned long long a = key[i], b = key[x];
+                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[x] = a; }
+                }
+            }
+            if (cta) __syncthreads(); else __syncwarp();
+        }
+}
+__global__ void __launch_bounds__(K4W_WARPS * 32) k4n_windows_kernel(K4Tab Tb, K4Windows W) {
+    __shared__ unsigned long long s_key[K4W_WARPS][K4W_CAP];
+    __shared__ int32_t s_queue[K4W_WARPS][K4W_CAP + 1];
+    __shared__ uint8_t s_fl[K4W_WARPS][K4W_CAP];
+    const uint32_t nwin = Tb.d_cnt[CNT_NREG] / (uint32_t)W.period + 1;
+    const uint32_t wib = threadIdx.x >> 5, lane = lane_id();
+    for (uint32_t w = blockIdx.x * K4W_WARPS + wib; w < nwin; w += gridDim.x * K4W_WARPS) {
+        const uint32_t n = W.wdir[w];
+        if (!n) continue;
+        if (n > W.cap) { if (lane == 0) W.big_list[atomicAdd(W.big_count, 1u)] = w; continue; }
+        const uint32_t s = W.wstart[w];
+        uint32_t n2 = 32; while (n2 < n) n2 <<= 1;
+        unsigned long long* key = s_key[wib];
+        for (uint32_t i = lane; i < n2; i += 32) key[i] = i < n ? W.se[s + i] : ~0ull;
+        __syncwarp();
+        k4w_bitonic(key, n2, lane, 32, false);
+        const SEdge* e = reinterpret_cast<const SEdge*>(key);
+        for (uint32_t k = lane; k < n; k += 32) k4n_window_prepare(Tb.del, Tb.c1, e, (int)n, s_fl[wib], (int)w, (int)k);
+        __syncwarp();
+        if (lane == 0) k4n_window_calls(e, (int)n, s_fl[wib], s_queue[wib], (int)w, (int)W.slot_base[w], W.rows, W.row_emit);
+        __syncwarp();
+    }
+}
+constexpr int K4WB_THREADS = 512;
+__global__ void __launch_bounds__(K4WB_THREADS) k4n_big_windows_kernel(K4Tab Tb, K4Windows W) {
+    const uint32_t nbig = *W.big_count;
+    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const uint32_t w = W.big_list[b], n = W.wdir[w], s = W.wstart[w];
+        uint32_t n2 = 32; while (n2 < n) n2 <<= 1;
+        unsigned long long* key = W.scratch + 2 * (size_t)s;          // n2 < 2 n: the padded copies of different windows do not overlap
+        for (uint32_t i = threadIdx.x; i < n2; i += K4WB_THREADS) key[i] = i < n ? W.se[s + i] : ~0ull;
+        __syncthreads();
+        k4w_bitonic(key, n2, threadIdx.x, K4WB_THREADS, true);
+        const SEdge* e = reinterpret_cast<const SEdge*>(key);
+        uint8_t* fl = W.fl + s;
+        for (uint32_t k = threadIdx.x; k < n; k += K4WB_THREADS) k4n_window_prepare(Tb.del, Tb.c1, e, (int)n, fl, (int)w, (int)k);
+        __syncthreads();
+        if (threadIdx.x == 0) k4n_window_calls(e, (int)n, fl, W.queue + s + w, (int)w, (int)W.slot_base[w], W.rows, W.row_emit);
+        __syncthreads();
     }
 }
 

@@ -145,15 +145,14 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     // sweeps in Jacobi order (every region against the previous table) or in place in DESCENDING order -- nothing may depend
     // on the order.
     std::vector<int32_t> del(nreg + 1, K4_NEVER), del_next(nreg + 1, K4_NEVER);
-    std::vector<uint8_t> never_final(nreg + 1, 0), dirty(nreg + 1, 1), dirty_next(nreg + 1, 0);
-    for (int v = 0; v < nreg; ++v) {
-        never_final[v] = k4n_never_final(T, KS, v) ? 1 : 0;
-        if (never_final[v] || getenv("HOSTSIM_NO_GUESS")) continue;
-        int wl = -1;
-        for (int j = reg[v].first_read; j < reg[v].first_read + reg[v].n_reads; ++j)
-            if (ri[j].mate_region >= 0) wl = std::max(wl, std::max(v, ri[j].mate_region) / period);
-        if (wl >= 0 && v != nreg - 1) del[v] = wl;
-    }
+    std::vector<uint8_t> dirty(nreg + 1, 1), dirty_next(nreg + 1, 0);
+    if (!getenv("HOSTSIM_NO_GUESS"))
+        for (int v = 0; v < nreg; ++v) {
+            int wl = -1;
+            for (int j = reg[v].first_read; j < reg[v].first_read + reg[v].n_reads; ++j)
+                if (ri[j].mate_region >= 0) wl = std::max(wl, std::max(v, ri[j].mate_region) / period);
+            if (wl >= 0 && v != nreg - 1) del[v] = wl;
+        }
     const bool in_place = getenv("HOSTSIM_INPLACE") != nullptr;
     int sweeps = 0;
     for (;; ++sweeps) {
@@ -161,7 +160,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
         int nchanged = 0;
         if (!in_place) del_next = del;
         for (int v = nreg - 1; v >= 0; --v) {
-            if (never_final[v] || !dirty[v]) continue;
+            if (!dirty[v]) continue;
             const int d = k4n_region_deletion(T, KS, del.data(), v);
             const int old = del[v];
             (in_place ? del : del_next)[v] = d;
@@ -200,7 +199,6 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
     std::vector<uint32_t> row_cn_count((size_t)(nrow_cap + 1) * nkey);
     std::vector<float> row_cn((size_t)(nrow_cap + 1) * nkey);
     std::vector<bdk_sv> rows(nrow_cap + 1);
-    std::vector<uint64_t> row_key(nrow_cap + 1, 0);
     {
         std::vector<SEdge> se; std::vector<uint8_t> fl; std::vector<int32_t> queue;
         int slot0 = 0;
@@ -214,7 +212,8 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
             se.clear(); for (size_t t = i; t < j; ++t) { SEdge x; x.src = we[t].src; x.dst = we[t].dst; se.push_back(x); }
             fl.assign(j - i, 0); queue.assign(j - i + 2, 0);
             slot0 = base[k];
-            const int used = k4n_window_calls(del.data(), c1.data(), se.data(), (int)(j - i), fl.data(), queue.data(), we[i].win, slot0, rows.data(), row_key.data(), row_emit.data());
+            for (int k = (int)(j - i) - 1; k >= 0; --k) k4n_window_prepare(del.data(), c1.data(), se.data(), (int)(j - i), fl.data(), we[i].win, k);
+            const int used = k4n_window_calls(se.data(), (int)(j - i), fl.data(), queue.data(), we[i].win, slot0, rows.data(), row_emit.data());
             if (used > base[k + 1] - base[k]) return -100;
         }
     }
