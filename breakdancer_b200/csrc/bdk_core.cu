@@ -805,7 +805,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
         const unsigned wgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(nwin_cap, K4W_WARPS), (uint64_t)kNumSMs * 16));
         k4n_windows_kernel<<<wgrid, K4W_WARPS * 32, 0, st>>>(Tb, W);
         k4n_big_windows_kernel<<<kNumSMs, K4WB_THREADS, 0, st>>>(Tb, W);
-        const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(R1, K4_THREADS / 32), (uint64_t)kNumSMs * 8));
+        const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up<uint64_t>(R1, K4_THREADS / 8), (uint64_t)kNumSMs * 8));
         k4n_calls_kernel<<<cgrid, K4_THREADS, 0, st>>>(KS, KO, d_cnt);
         k4_score_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(S, M, c->d_summary.as<bdk_summary_t>(), d_cnt);
         c->launches += 5;

@@ -296,6 +296,17 @@ struct SoloTeam {
     BDK_HD uint32_t fetch_inc(uint32_t* p) const { return (*p)++; }
 };
 #if defined(__CUDACC__)
+struct Tile8Team {           // 8 consecutive lanes of a warp: four regions (or calls) per warp at a time, 128 contiguous bytes of ReadInfo2 per load
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 7u); }
+    __device__ __forceinline__ int width() const { return 8; }
+    __device__ __forceinline__ unsigned mask() const { return 0xffu << (threadIdx.x & 24u); }
+    __device__ __forceinline__ int sum(int v) const { const unsigned m = mask(); v += __shfl_xor_sync(m, v, 4); v += __shfl_xor_sync(m, v, 2); v += __shfl_xor_sync(m, v, 1); return v; }
+    __device__ __forceinline__ int min(int v) const { const unsigned m = mask(); v = ::min(v, __shfl_xor_sync(m, v, 4)); v = ::min(v, __shfl_xor_sync(m, v, 2)); v = ::min(v, __shfl_xor_sync(m, v, 1)); return v; }
+    __device__ __forceinline__ int max(int v) const { const unsigned m = mask(); v = ::max(v, __shfl_xor_sync(m, v, 4)); v = ::max(v, __shfl_xor_sync(m, v, 2)); v = ::max(v, __shfl_xor_sync(m, v, 1)); return v; }
+    __device__ __forceinline__ bool any(bool p) const { return __ballot_sync(mask(), p) != 0; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask()); }
+    __device__ __forceinline__ void add(int32_t* p, int v) const { atomicAdd(p, v); }
+};
 struct WarpTeam {
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
     __device__ __forceinline__ int width() const { return 32; }
@@ -476,16 +487,24 @@ template <class Team>
 BDK_HD int k4n_region_deletion(const Team& T, const K4N& S, const int32_t* del, int v) {
     const RegionRec R = S.reg[v];
     const int j0 = R.first_read, j1 = R.first_read + R.n_reads, wv = v / S.period;
-    int w = K4_NEVER;
+    int w = K4_NEVER, wlast = -1;
     bool never = false;
     for (int j = j0 + T.lane(); j < j1; j += T.width()) {
         const ReadInfo2 I = S.ri[j];
         const int rm = I.mate_region;
-        if (rm >= 0) { const int aw = (rm > v ? rm : v) / S.period; if (aw < w) w = aw; }
-        else if (R.stored && !(S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX) && (I.mate < 0 || I.mate < j)) never = true;
+        const bool skip = S.chr_restricted && meta_flag(I.meta) == BDK_ARP_CTX;
+        if (rm >= 0) {
+            const int aw = (rm > v ? rm : v) / S.period;
+            if (aw < w) w = aw;
+            if (!skip && rm != v && aw > wlast) wlast = aw;
+        } else if (R.stored && !skip && (I.mate < 0 || I.mate < j)) never = true;
     }
     if (T.any(never)) return K4_NEVER;
     w = T.min(w);                                      // the windows of v's edges = max(v, mate's region) / period
+    // A read whose mate is not registered yet blocks: nothing can happen before the window of the last mate (itself an
+    // active window). Without -o that is the region's last active window: it is cleared there or never.
+    wlast = T.max(wlast);
+    if (w != K4_NEVER && wlast > w) w = wlast;
     while (w != K4_NEVER) {
         // lc: latest window <= w in which process_sv was called with v; maxc: latest collapse a held read waits for
         int wn = K4_NEVER, lc = -1, intra = 0, maxc = -1;

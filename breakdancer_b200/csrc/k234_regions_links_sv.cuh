@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(GS_THREADS) k3_strong_scatter_kernel(const uns
 //   calls    first call window per region; one warp per flush window sorts the window's followed edges in shared memory and
 //            orders its calls (build_connection); one warp per call counts its pairs (process_sv); one thread per call
 //            scores it (k4_score_kernel)
-// Regions are taken 32 at a time: a lane evaluates a small region alone, the warp shares the large ones.
+// Regions are taken 32 at a time: a tile of eight lanes evaluates a region (four at a time per warp), the whole warp a large one.
 constexpr int K4_THREADS = 256;
-constexpr int K4N_SOLO_MAX = 64;          // reads up to which one thread evaluates a region by itself
+constexpr int K4N_TILE_MAX = 256;         // reads up to which eight lanes evaluate a region (the whole warp beyond)
 constexpr int K4_TRACE_SWEEPS = 64;
 struct K4Trace { unsigned long long t[1 + K4_TRACE_SWEEPS]; uint32_t nchanged[K4_TRACE_SWEEPS]; };
 struct K4Tab {
@@ -242,11 +242,18 @@ __device__ __forceinline__ void k4n_for_block(const K4N& S, uint32_t base, uint3
     const uint32_t v = base + lane_id();
     const bool mine = v < v_end && want;
     const int nr = mine ? S.reg[v].n_reads : 0;
-    if (mine && nr <= K4N_SOLO_MAX) fn(SoloTeam(), (int)v);
-    unsigned big = __ballot_sync(FULL, mine && nr > K4N_SOLO_MAX);
-    while (big) {
-        const int l = __ffs(big) - 1;
-        big &= big - 1;
+    const unsigned small = __ballot_sync(FULL, mine && nr <= K4N_TILE_MAX), big = __ballot_sync(FULL, mine && nr > K4N_TILE_MAX);
+    unsigned m = (small >> (lane_id() & 24u)) & 0xffu;         // the eight regions of this lane's tile
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        fn(Tile8Team(), (int)(base + (lane_id() & 24u) + l));
+    }
+    __syncwarp();
+    unsigned bg = big;
+    while (bg) {
+        const int l = __ffs(bg) - 1;
+        bg &= bg - 1;
         fn(WarpTeam(), (int)(base + l));
     }
 }
@@ -276,6 +283,7 @@ __device__ __forceinline__ void k4_grid_barrier(uint32_t* counter, uint32_t& epo
 __device__ __forceinline__ void k4n_sweep(const K4N& S, const K4Tab& Tb, uint32_t sweep, uint32_t* changed) {
     const uint32_t nreg = (uint32_t)S.nreg;
     const uint32_t nwarp = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t nchanged = 0;
     for (uint32_t base = warp * 32u; base < nreg; base += nwarp * 32u) {
         const uint32_t v0 = base + lane_id();
         const bool want = v0 < nreg && (sweep == 0 || __ldcg(Tb.stamp + v0) == sweep);
@@ -284,16 +292,15 @@ __device__ __forceinline__ void k4n_sweep(const K4N& S, const K4Tab& Tb, uint32_
             const int old = __ldcg(Tb.del + v);
             if (d == old) return;
             const RegionRec R = S.reg[v];
-            if (T.lane() == 0) {
-                __stcg(Tb.del + v, d);
-                if (Tb.count_changes) atomicAdd(changed, 1u); else __stcg(changed, 1u);
-            }
+            if (T.lane() == 0) { __stcg(Tb.del + v, d); ++nchanged; }
             for (int j = R.first_read + T.lane(); j < R.first_read + R.n_reads; j += T.width()) {
                 const int rm = S.ri[j].mate_region;
                 if (rm >= 0 && rm != v) __stcg(Tb.stamp + rm, sweep + 1);
             }
         });
     }
+    nchanged = __reduce_add_sync(0xffffffffu, nchanged);
+    if (nchanged && lane_id() == 0) { if (Tb.count_changes) atomicAdd(changed, nchanged); else __stcg(changed, 1u); }
 }
 
 // sync[0]: barrier counter; sync[1 + s % 3]: regions changed in sweep s; sync[7]: number of sweeps (result)
@@ -399,12 +406,12 @@ __global__ void __launch_bounds__(K4WB_THREADS) k4n_big_windows_kernel(K4Tab Tb,
     }
 }
 
-// one warp per call slot: the pairs the call consumes (bdk_logic.h: k4n_call)
+// eight lanes per call slot: the pairs the call consumes (bdk_logic.h: k4n_call)
 __global__ void __launch_bounds__(K4_THREADS) k4n_calls_kernel(K4N S, K4NOut M, const uint32_t* __restrict__ d_cnt) {
     S.nreg = (int32_t)d_cnt[CNT_NREG];
     const uint32_t nrow = d_cnt[CNT_NROW];
-    const WarpTeam T;
-    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrow; r += gridDim.x * (blockDim.x >> 5))
+    const Tile8Team T;
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); r < nrow; r += gridDim.x * (blockDim.x >> 3))
         if (M.row_emit[r] & K4_ROW_CALL) k4n_call(T, S, M, (int)r);
 }
 
