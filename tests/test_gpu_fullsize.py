@@ -1,6 +1,9 @@
-"""Full-size checks (BASELINE.json configs[1]: 50 M read pairs = 100 M records on one GPU) through the C ABI.
+"""Full-size checks (BASELINE.json configs[1]: 50 M read pairs = 100 M records on one GPU; configs[2]: 300 M pairs) through
+the C ABI.
 
-The oracle needs minutes for this size, so the full-size run is pinned by size-independent properties:
+The whole result of both full-size jobs is compared with the oracle run on the same records (summary, anomalous stream,
+regions, SV table, supporting reads: test_fullsize_matches_oracle, test_config3_fullsize_matches_oracle; the second needs
+~60 GB of host memory and is skipped where the box has less). Beside that, size-independent properties:
   * an independent vectorised (torch, on the device) evaluation of the classifier's decisions for this
     workload must reproduce the summary statistics K1 produces (record count, anomalous reads, per-library
     proper-pair count, flag histogram, covered reference length);
@@ -9,7 +12,6 @@ The oracle needs minutes for this size, so the full-size run is pinned by size-i
   * the SV table is invariant under how the records arrive (device-resident push, host pushes in ragged chunks
     from pinned memory with zero-copy side columns) and under reset + re-run (idempotence);
   * every SV row is supported by reads that K4 marked as consumed by exactly that row.
-The bit-exact comparison with the oracle at 2 M pairs of the same distribution is in test_gpu_parity.py.
 """
 import numpy as np
 import pytest
@@ -41,6 +43,23 @@ def big():
                support=ctx.support(), lib=cfg.libs[0], opts=api.Options())
     yield out
     ctx.close()
+
+
+def _host_gb_available():
+    import psutil
+    return psutil.virtual_memory().available / 2 ** 30
+
+
+def test_fullsize_matches_oracle(big):
+    """The bench workload itself (50 M pairs): everything the job returns, against the oracle on the same records."""
+    from breakdancer_b200 import synth_torch
+    from oracle import oracle
+    if _host_gb_available() < 16:
+        pytest.skip("needs 16 GB of host memory for the oracle's copy of the records")
+    ro = oracle.run(big["bundle"], synth_torch.to_numpy(big["cols"]))
+    ar, rr = big["areads"]
+    util.assert_result_matches_oracle(ro, big["table"], big["summary"], big["regions"], ar, rr, big["support"], "configs[1] full size")
+    assert len(ro.table.sv) > 5000
 
 
 def test_fullsize_summary_matches_vectorised_classifier(big):
@@ -175,6 +194,21 @@ def test_config3_fullsize_runs_and_calls_every_sv_type(big3):
         h = list(S.read_counts_by_flag[i])
         assert all(h[f] > 0 for f in want), h
     print("config 3 full size:", len(t.sv), "SV calls,", big3["sweeps"], "K4 sweeps, kernel ms", {k: round(v["ms"], 3) for k, v in big3["times"].items() if v["ms"]})
+
+
+def test_config3_fullsize_matches_oracle(big3):
+    """configs[2] at its stated size (300 M pairs, 12.8 M anomalous reads, ~9000 flush windows): the whole result against the
+    oracle on the same records."""
+    from breakdancer_b200 import synth_torch
+    from oracle import oracle
+    if _host_gb_available() < 90:
+        pytest.skip("needs ~60 GB of host memory (22 GB of records + the oracle's state)")
+    ctx = big3["ctx"]
+    bundle, _ = synth_torch.config3_bundle()
+    ro = oracle.run(bundle, synth_torch.to_numpy(big3["cols"]))
+    ar, rr = ctx.areads()
+    util.assert_result_matches_oracle(ro, big3["table"], big3["summary"], ctx.regions(), ar, rr, ctx.support(), "configs[2] full size")
+    assert len(ro.table.sv) > 100000
 
 
 def test_config3_fullsize_invariant_under_chunked_arrival(big3):
