@@ -16,7 +16,9 @@ For N > 1 each rank runs its own chromosome-shaped shard (the path shards by chr
 no data-path collective: weak scaling); torch.distributed/NCCL is used only for the barrier and the
 max-over-ranks of the device time.  One JSON line is printed by rank 0.  For N > 1 the line also carries
 `one_job_all_gpus`: ONE job spread over all ranks with whole-genome semantics (and a second one with -t),
-i.e. the NCCL exchanges of csrc/comm.cuh inside the timed region.
+i.e. the NCCL exchanges of csrc/comm.cuh inside the timed region, each with a `parity` block (all ranks return the same
+table, and it equals a single-GPU run of the concatenated stream), plus BASELINE configs[3] (24 GRCh38 chromosomes as -o
+shards, LPT-packed) and configs[4] (-t, 1 B pairs, 24 chromosomes over the N GPUs).
 --config 3 runs BASELINE configs[2] instead (300 M pairs, 4 libraries in 2 BAMs, all five SV types).
 
 --impl reference times the unmodified reference executable (oracle/_ref/breakdancer-max; the oracle
@@ -389,7 +391,12 @@ def ours(args):
     if world > 1 and not args.no_genome and args.config == 2:
         del cols, hcols, dsoa, hsoa
         torch.cuda.empty_cache()
-        genome = {"whole_genome": genome_mode(args, rank, world, local, dev, False), "ctx_only_t": genome_mode(args, rank, world, local, dev, True)}
+        genome = {"whole_genome": one_job_mode(args, rank, world, local, dev, False),
+                  "ctx_only_t": one_job_mode(args, rank, world, local, dev, True)}
+        if not args.no_configs45:
+            genome["config4_lpt_shards"] = lpt_shards_mode(args, rank, world, local, dev, args.genome_pairs)
+            genome["config5_ctx_t"] = one_job_mode(args, rank, world, local, dev, True, plan="grch38", total_pairs=args.ctx_pairs,
+                                                   name=f"one job, -t, 24 GRCh38 chromosomes, {args.ctx_pairs / 1e6:g}M read pairs + 2% inter-chromosomal pairs over {world} GPUs (BASELINE configs[4])")
 
     if rank == 0:
         peaks = {}
@@ -441,33 +448,71 @@ def ours(args):
         dist.destroy_process_group()
 
 
-def genome_mode(args, rank, world, local, dev, transchr):
-    """ONE job over all N GPUs with whole-genome semantics (BASELINE configs[4]; -t: CTX-only): rank r holds
-    chromosome r of an N-chromosome genome (a contiguous slice of the globally sorted stream) in HBM; per step:
-    reset, K1 on the local slice, the NCCL exchanges, replicated K2/K3, component-sharded K4, rows gathered to
-    every rank. Returns the block rank 0 prints (max over ranks of the device time)."""
+def _digest(summ, table):
+    """One hash over everything a job returns (summary statistics, SV rows in output order, per-library counts, copy numbers)."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    h.update(bytes(summ))
+    for a in (table.sv, table.lib_count, table.cn_count, table.copy_number):
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def _cat_cols(parts):
+    import torch
+    return {k: torch.cat([p[k] for p in parts]).contiguous() for k in parts[0]}
+
+
+def one_job_mode(args, rank, world, local, dev, transchr, plan=None, total_pairs=None, name=""):
+    """ONE job over all N GPUs (csrc/comm.cuh): rank r holds a contiguous slice of the globally (tid, pos)-sorted stream in
+    HBM; per step: reset, K1 on the local slice, the NCCL exchange of the anomalous reads, K2-K4 on the global stream, the
+    complete table on every rank. plan=None: N chromosomes of chr1's length with args.pairs each (whole-genome semantics, or -t);
+    plan="grch38": 24 GRCh38 chromosomes, `total_pairs` in total, contiguous chromosome ranges per rank (BASELINE configs[4] with -t).
+    `parity`: the digest of (summary, SV table) is the same on every rank AND equals a single-GPU run of the concatenated
+    stream on rank 0 (when that fits one GPU). Returns the block rank 0 prints (max over ranks of the device time)."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from breakdancer_b200 import api, synth, synth_torch
-    pairs = args.pairs
-    ctx_frac = 0.02 if transchr else 0.002
-    cols = synth_torch.genome_shard_device(pairs, 20260104, dev, rank, world, ctx_frac)
-    n = cols["pos"].numel()
+    seed = 20260104
+    if plan == "grch38":
+        lens = synth_torch.GRCH38
+        ctx_frac = 0.02
+        pairs_c, ctxm = synth_torch.genome_plan(total_pairs, ctx_frac, lens)
+        ntid = len(lens)
+        cuts, acc, tot = [0], 0, sum(pairs_c)               # contiguous chromosome ranges with about equal pairs
+        for t in range(ntid):
+            acc += pairs_c[t]
+            while len(cuts) < world and acc >= tot * len(cuts) / world:
+                cuts.append(t + 1)
+        while len(cuts) < world:
+            cuts.append(ntid)
+        cuts.append(ntid)
+        shard = lambda t: synth_torch.genome_shard_device(pairs_c[t], seed, dev, t, ntid, ctx_frac, ctx_counts=ctxm[t], lens=lens)
+        mine = list(range(cuts[rank], cuts[rank + 1]))
+        genome = [(f"chr{i + 1}", l) for i, l in enumerate(lens)]
+    else:
+        ctx_frac = 0.02 if transchr else 0.002
+        ntid = world
+        shard = lambda t: synth_torch.genome_shard_device(args.pairs, seed, dev, t, world, ctx_frac)
+        mine = [rank]
+        genome = [(f"chr{i + 1}", synth_torch.CHR1_LEN) for i in range(world)]
+    cols = _cat_cols([shard(t) for t in mine]) if mine else None
+    n = cols["pos"].numel() if cols is not None else 0
     lib = synth.LibSpec("lib1", "syn_genome.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
-    genome = [(f"chr{i + 1}", synth_torch.CHR1_LEN) for i in range(world)]
     wl = synth.Workload({}, genome, [lib], ["rg1"], ["lib1"], ["syn_genome.bam"])
     cfg = api.BamConfig(text=wl.config_text())
     opts = api.Options(transchr_rearrange=bool(transchr))
-    bundle = api.ParamBundle(opts, cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, world)
+    bundle = api.ParamBundle(opts, cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, ntid)
     ctx = api.Context(bundle, local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.comm_init_from_dist()
-    dsoa = synth_torch.soa_of(cols)
+    dsoa = synth_torch.soa_of(cols) if n else None
 
     def step():
         ctx.reset()
-        ctx.push_soa(dsoa, n, device=True)
+        if n:
+            ctx.push_soa(dsoa, n, device=True)
         return ctx.finish_raw()
 
     for _ in range(3):
@@ -484,23 +529,119 @@ def genome_mode(args, rank, world, local, dev, transchr):
     e1.record()
     dist.barrier(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    summ = ctx.summary()
-    t = torch.tensor([ms] + [kt.get(k, 0.0) for k in ("k1_classify", "comm_gather_reads", "k2_regions", "k3_links_graph", "k4_sv_score", "comm_gather_rows", "d2h_results")],
-                     device=dev, dtype=torch.float64)
+    names = ["k1_classify", "comm_gather_reads", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results"]
+    t = torch.tensor([ms] + [kt.get(k, 0.0) for k in names], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot = torch.tensor([n // 2, ctx.comm_bytes()], device=dev, dtype=torch.float64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    out = {"value": float(tot[0].item()) / (float(t[0].item()) / 1e3), "unit": UNIT, "ms_per_step": float(t[0].item()),
-           "workload": f"one job, {world} chromosomes x {pairs / 1e6:g}M pairs (config-2 records + {ctx_frac * 100:g}% inter-chromosomal pairs)"
-                       + (", -t" if transchr else ", whole-genome semantics"),
-           "k4_sweeps": ctx.k4_sweeps(), "records_total": int(summ.n_records), "anomalous_reads_total": int(summ.n_anomalous), "sv_calls": int(res.n_sv),
-           "nvlink_bytes_received_per_step_all_ranks": float(tot[1].item()),
-           "max_over_ranks_ms": dict(zip(["k1_classify", "comm_gather_reads", "k2_regions", "k3_links_graph", "k4_sv_score", "comm_gather_rows", "d2h_results"],
-                                         [float(x) for x in t[1:].tolist()]))}
+    # ---- parity: every rank holds the same result, and it is the single-GPU result of the concatenated stream
+    ctx.reset()
+    if n:
+        ctx.push_soa(dsoa, n, device=True)
+    summ = ctx.summary()
+    table = ctx.finish()
+    mine_digest = _digest(summ, table)
+    digests = [None] * world
+    dist.all_gather_object(digests, mine_digest)
+    parity = {"ranks_agree": len(set(digests)) == 1, "digest": digests[0]}
+    total_records = int(summ.n_records)
     ctx.close()
-    del cols
+    del cols, dsoa
     torch.cuda.empty_cache()
+    if total_records * HOST_BYTES_PER_RECORD < 90e9:
+        if rank == 0:
+            try:
+                allc = _cat_cols([shard(t) for t in range(ntid)])
+                c1 = api.Context(bundle, local)
+                c1.set_stream(torch.cuda.current_stream().cuda_stream)
+                c1.push_soa(synth_torch.soa_of(allc), allc["pos"].numel(), device=True)
+                s1 = c1.summary()
+                t1 = c1.finish()
+                parity["single_gpu_digest"] = _digest(s1, t1)
+                parity["single_gpu_sv_calls"] = int(len(t1.sv))
+                c1.close()
+                del allc
+            except Exception as ex:   # reported, never fatal
+                parity["single_gpu_digest"] = None
+                parity["single_gpu_error"] = str(ex)[:200]
+            torch.cuda.empty_cache()
+            parity["parity_ok"] = bool(parity["ranks_agree"] and parity.get("single_gpu_digest") == parity["digest"])
+        dist.barrier()
+    else:
+        parity["parity_ok"] = None
+        parity["single_gpu_digest"] = "skipped: the concatenated stream does not fit one GPU beside the generator's temporaries"
+    out = {"value": float(tot[0].item()) / (float(t[0].item()) / 1e3), "unit": UNIT, "ms_per_step": float(t[0].item()),
+           "workload": name or (f"one job, {world} chromosomes x {args.pairs / 1e6:g}M pairs (config-2 records + {ctx_frac * 100:g}% inter-chromosomal pairs)"
+                                + (", -t" if transchr else ", whole-genome semantics")),
+           "records_total": total_records, "anomalous_reads_total": int(summ.n_anomalous), "sv_calls": int(len(table.sv)),
+           "nvlink_bytes_received_per_step_all_ranks": float(tot[1].item()), "parity": parity,
+           "max_over_ranks_ms": dict(zip(names, [float(x) for x in t[1:].tolist()]))}
     return out
+
+
+def lpt_shards_mode(args, rank, world, local, dev, total_pairs):
+    """BASELINE configs[3]: a 30x whole genome (24 GRCh38 chromosomes) as per-chromosome shards, each an independent job with -o
+    semantics (own summary statistics, own window, own region indices), chromosomes LPT-packed onto the GPUs by their pair
+    counts (breakdancer_b200/shard.py). No data-path collective; total work is fixed, so this is strong scaling."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from breakdancer_b200 import api, shard, synth, synth_torch
+    lens = synth_torch.GRCH38
+    ctx_frac = 0.002
+    pairs_c, ctxm = synth_torch.genome_plan(total_pairs, ctx_frac, lens)
+    ntid = len(lens)
+    mine = shard.lpt_pack(pairs_c, world)[rank]
+    genome = [(f"chr{i + 1}", l) for i, l in enumerate(lens)]
+    lib = synth.LibSpec("lib1", "syn_genome.bam", synth_torch.MEAN, synth_torch.STD, synth_torch.READLEN, ["rg1"])
+    wl = synth.Workload({}, genome, [lib], ["rg1"], ["lib1"], ["syn_genome.bam"])
+    cfg = api.BamConfig(text=wl.config_text())
+    shards = []
+    for t in mine:
+        cols = synth_torch.genome_shard_device(pairs_c[t], 20260103, dev, t, ntid, ctx_frac, ctx_counts=ctxm[t], lens=lens)
+        bundle = api.ParamBundle(api.Options(chr=genome[t][0]), cfg.libs, cfg.nbam, np.zeros(1, np.int32), np.zeros(1, np.int32), cfg.window, ntid)
+        shards.append((t, cols, synth_torch.soa_of(cols), cols["pos"].numel(), bundle))
+    ctx = api.Context(shards[0][4], local) if shards else None      # the options of all shards are the same (-o: chr_restricted)
+    if ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def step():
+        calls = 0
+        for t, cols, soa, n, bundle in shards:
+            ctx.reset()
+            ctx.push_soa(soa, n, device=True)
+            calls += int(ctx.finish_raw().n_sv)
+        return calls
+
+    for _ in range(3):
+        calls = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 5))
+    e0.record()
+    for _ in range(steps):
+        calls = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    my_pairs = sum(s[3] for s in shards) // 2
+    t = torch.tensor([ms, -ms, float(my_pairs), -float(my_pairs)], device=dev, dtype=torch.float64)
+    tot = torch.tensor([my_pairs, calls], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if ctx:
+        ctx.close()
+    del shards
+    torch.cuda.empty_cache()
+    return {"value": float(tot[0].item()) / (float(t[0].item()) / 1e3), "unit": UNIT, "ms_per_step": float(t[0].item()), "scaling": "strong",
+            "workload": f"24 GRCh38 chromosomes, {tot[0].item() / 1e6:.1f}M read pairs in total, one -o shard per chromosome, LPT-packed onto {world} GPU(s) (BASELINE configs[3])",
+            "sv_calls": int(tot[1].item()), "slowest_rank_ms": float(t[0].item()), "fastest_rank_ms": -float(t[1].item()),
+            "pairs_on_fullest_rank": float(t[2].item()), "pairs_on_emptiest_rank": -float(t[3].item())}
 
 
 def main():
@@ -516,6 +657,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--bam-pairs", type=int, default=2_000_000, help="size of the BAM sample of the bam_decode leg")
     ap.add_argument("--no-genome", action="store_true", help="N > 1: skip the one-job-over-all-GPUs (NCCL exchange) measurements")
+    ap.add_argument("--no-configs45", action="store_true", help="N > 1: skip the BASELINE configs[3] (LPT shards) and configs[4] (-t, 1 B pairs) blocks")
+    ap.add_argument("--genome-pairs", type=int, default=617_700_000, help="read pairs of the configs[3] whole genome")
+    ap.add_argument("--ctx-pairs", type=int, default=1_000_000_000, help="read pairs of the configs[4] -t job")
     args = ap.parse_args()
     if args.pairs is None:
         args.pairs = 300_000_000 if args.config == 3 else 50_000_000

@@ -290,14 +290,15 @@ int push_common(bdk_ctx* c, uint64_t n, uint64_t max_launch, RunFn run) {
         if (r_ != ncclSuccess) return fail(c, BDK_ERR_NCCL, "%s failed: %s", #call, nc->GetErrorString(r_)); \
     } while (0)
 
-// in-place all-gather of per-rank ranges of one array: rank p owns elements [cut[p], cut[p + 1]) of `elt` bytes each
+// in-place all-gather of per-rank ranges of one array: rank p owns elements [cut[p], cut[p + 1]) of `elt` bytes each. Every rank
+// sends its range straight to every peer (point-to-point over NVSwitch; the caller groups the calls).
 int gather_ranges(bdk_ctx* c, NcclApi* nc, void* base, size_t elt, const uint64_t* cut) {
+    const uint64_t mine = cut[c->rank + 1] - cut[c->rank];
     for (int p = 0; p < c->nranks; ++p) {
+        if (p == c->rank) continue;
         const uint64_t cnt = cut[p + 1] - cut[p];
-        if (!cnt) continue;
-        char* ptr = (char*)base + cut[p] * elt;
-        NC(nc->Broadcast(ptr, ptr, cnt * elt, ncclUint8, p, c->comm, c->stream));
-        if (p != c->rank) c->comm_bytes += cnt * elt;
+        if (mine) NC(nc->Send((char*)base + cut[c->rank] * elt, mine * elt, ncclUint8, p, c->comm, c->stream));
+        if (cnt) { NC(nc->Recv((char*)base + cut[p] * elt, cnt * elt, ncclUint8, p, c->comm, c->stream)); c->comm_bytes += cnt * elt; }
     }
     return 0;
 }

@@ -28,14 +28,35 @@ def _mapq(n, gen, device):
     return m
 
 
-def config2_device(n_pairs: int, seed: int, device, chrom_len: int = CHR1_LEN, tid: int = 0) -> Dict[str, torch.Tensor]:
+# GRCh38 primary assembly, chr1..22, X, Y (3 088 269 832 bp: BASELINE configs[3] / configs[4])
+GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622, 133275309,
+          114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+
+
+def genome_plan(total_pairs: int, ctx_frac: float, lens=GRCH38):
+    """Read pairs per chromosome (proportional to length) and the symmetric matrix of inter-chromosomal pair counts
+    (ctx_frac of the pairs, proportional to the product of the lengths) of a whole-genome workload."""
+    tot = float(sum(lens))
+    pairs = [int(round(total_pairs * l / tot)) for l in lens]
+    denom = tot * tot - sum(float(l) * l for l in lens)
+    n = len(lens)
+    ctx = [[0] * n for _ in range(n)]
+    for i in range(n):
+        for j in range(i + 1, n):
+            ctx[i][j] = ctx[j][i] = int(round(2.0 * ctx_frac * total_pairs * lens[i] * lens[j] / denom))
+    return pairs, ctx
+
+
+def config2_device(n_pairs: int, seed: int, device, chrom_len: int = CHR1_LEN, tid: int = 0, fixed_length: bool = False) -> Dict[str, torch.Tensor]:
     """Position-sorted record columns (2 records per pair) on `device`.
-    Columns use torch dtypes with the bit patterns bdk_soa expects: flag/rgid int16, qid int64."""
+    Columns use torch dtypes with the bit patterns bdk_soa expects: flag/rgid int16, qid int64.
+    fixed_length: the chromosome keeps its length whatever the number of pairs (else it shrinks with the pairs below 50 M
+    so that the coverage stays 30x)."""
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     scale = n_pairs / 50_000_000
-    L = chrom_len if scale >= 1 else max(200000, int(chrom_len * scale))
+    L = chrom_len if (scale >= 1 or fixed_length) else max(200000, int(chrom_len * scale))
     n_noise = int(round(n_pairs * 0.005))
     n_normal = n_pairs - n_noise
     ncl = max(1, int(5000 * scale))
@@ -97,16 +118,18 @@ def config2_device(n_pairs: int, seed: int, device, chrom_len: int = CHR1_LEN, t
 
 
 def genome_shard_device(n_pairs: int, seed: int, device, tid: int, ntid: int, ctx_frac: float, clustered: float = 0.3,
-                        chrom_len: int = CHR1_LEN) -> Dict[str, torch.Tensor]:
+                        chrom_len: int = CHR1_LEN, ctx_counts=None, lens=None) -> Dict[str, torch.Tensor]:
     """Chromosome `tid` of an `ntid`-chromosome genome (BASELINE.json configs[3]/[4] shape): the config-2 records of
     the chromosome plus its side of the inter-chromosomal pairs (ctx_frac of the pairs; `clustered` of them in planted
     translocation clusters of Poisson(10) pairs, the rest uniform). The pairs between chromosomes i < j come from a
-    generator seeded by (seed, i, j), so the ranks that own i and j produce matching mates without talking."""
+    generator seeded by (seed, i, j), so the ranks that own i and j produce matching mates without talking.
+    With `lens` (all chromosome lengths) and `ctx_counts` (pairs with every other chromosome, genome_plan) the
+    chromosomes keep their real lengths and may differ in size."""
     dev = torch.device(device)
-    cols = config2_device(n_pairs, seed * 1000 + tid, dev, chrom_len, tid)
+    cols = config2_device(n_pairs, seed * 1000 + tid, dev, chrom_len if lens is None else lens[tid], tid, fixed_length=lens is not None)
     cols["qid"] += (tid + 1) << 40                                 # read names unique across chromosomes
     L = chrom_len if n_pairs >= 50_000_000 else max(200000, int(chrom_len * n_pairs / 50_000_000))
-    n_ctx = int(round(n_pairs * ctx_frac))
+    n_ctx = int(round(n_pairs * ctx_frac)) if ctx_counts is None else sum(ctx_counts)
     if ntid < 2 or n_ctx == 0:
         return cols
     per = max(1, n_ctx // (ntid - 1))
@@ -117,6 +140,11 @@ def genome_shard_device(n_pairs: int, seed: int, device, tid: int, ntid: int, ct
         i, j = min(tid, other), max(tid, other)
         gen = torch.Generator(device=dev)
         gen.manual_seed((seed * 1_000_003 + i) * 1009 + j)
+        Li, Lj = (L, L) if lens is None else (lens[i], lens[j])
+        if ctx_counts is not None:
+            per = ctx_counts[other]
+            if per <= 0:
+                continue
         ncl = max(1, int(per * clustered / 10))
         sizes = torch.poisson(torch.full((ncl,), 10.0, device=dev), generator=gen).to(torch.int64)
         n_cl = int(sizes.sum().item())
@@ -125,10 +153,10 @@ def genome_shard_device(n_pairs: int, seed: int, device, tid: int, ntid: int, ct
         def uni(n, lo, hi):
             return (lo + torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * (hi - lo)).to(torch.int64)
 
-        ci, cj = uni(ncl, 1000, L - 1000), uni(ncl, 1000, L - 1000)
+        ci, cj = uni(ncl, 1000, Li - 1000), uni(ncl, 1000, Lj - 1000)
         rep = torch.repeat_interleave(torch.arange(ncl, device=dev), sizes)
-        pi = torch.cat([ci[rep] - uni(n_cl, 0, 240), uni(n_un, 1000, L - 1000)])
-        pj = torch.cat([cj[rep] + uni(n_cl, 0, 240), uni(n_un, 1000, L - 1000)])
+        pi = torch.cat([ci[rep] - uni(n_cl, 0, 240), uni(n_un, 1000, Li - 1000)])
+        pj = torch.cat([cj[rep] + uni(n_cl, 0, 240), uni(n_un, 1000, Lj - 1000)])
         ri = torch.cat([torch.zeros(n_cl, dtype=torch.int64, device=dev), uni(n_un, 0, 2)])      # clusters: + on i, - on j
         rj = torch.cat([torch.ones(n_cl, dtype=torch.int64, device=dev), uni(n_un, 0, 2)])
         k = torch.arange(n_cl + n_un, device=dev, dtype=torch.int64)
@@ -142,6 +170,8 @@ def genome_shard_device(n_pairs: int, seed: int, device, tid: int, ntid: int, ct
         extra["mtid"].append(torch.full_like(k, other))
         extra["qid"].append(qid)
     ne = sum(int(x.numel()) for x in extra["pos"])
+    if ne == 0:
+        return cols
     add = {
         "pos": torch.cat(extra["pos"]).to(torch.int32), "mpos": torch.cat(extra["mpos"]).to(torch.int32),
         "mtid": torch.cat(extra["mtid"]).to(torch.int32), "flag": torch.cat(extra["flag"]).to(torch.int16),
