@@ -548,7 +548,14 @@ def one_job_mode(args, rank, world, local, dev, transchr, plan=None, total_pairs
     ctx.close()
     del cols, dsoa
     torch.cuda.empty_cache()
-    if total_records * HOST_BYTES_PER_RECORD < 90e9:
+    fits = total_records * HOST_BYTES_PER_RECORD < 45e9          # the stream, the generator's temporaries and the job's work space on one GPU
+    if not fits and plan == "grch38" and total_pairs > 300_000_000:
+        # too large for one GPU: the same plan (24 chromosomes, same options, same cuts) at 300 M pairs, all ranks + one GPU
+        small = one_job_mode(args, rank, world, local, dev, transchr, plan=plan, total_pairs=300_000_000, name="parity run")
+        parity["at_300M_pairs"] = small["parity"]
+        parity["parity_ok"] = small["parity"].get("parity_ok")
+        parity["single_gpu_digest"] = "full size does not fit one GPU: see at_300M_pairs (same plan, 300 M pairs)"
+    elif fits:
         if rank == 0:
             try:
                 allc = _cat_cols([shard(t) for t in range(ntid)])

@@ -63,7 +63,8 @@ def _run_rank(case_name, rank, world, device, unique_id):
         support = ctx.support()
         ro = oracle.run(b, cols)
         util.assert_result_matches_oracle(ro, table, summary, regions, areads, rr, support, f"{case_name} rank {rank}/{world} job {rep}")
-        assert world == 1 or ctx.comm_bytes() > 0 or len(areads) == 0
+        peers_have_records = e[rank] > 0 or e[rank + 1] < n
+        assert world == 1 or ctx.comm_bytes() > 0 or len(areads) == 0 or not peers_have_records
     nsv = len(table.sv)
     ctx.close()
     return nsv
@@ -81,6 +82,7 @@ def _worker(rank, world, port, case_name, q):
         q.put((rank, "ok", nsv))
     except BaseException as ex:   # report instead of hanging the peers' collectives silently
         q.put((rank, f"{type(ex).__name__}: {ex}", -1))
+        q.close(); q.join_thread()          # the feeder thread must get the message out before the process goes
         os._exit(1)
     dist.barrier()
     dist.destroy_process_group()
