@@ -90,6 +90,7 @@ struct bdk_ctx {
     size_t h_pack_cap = 0;
     bool finished = false, summary_ready = false;
     int k1_blocks_per_sm = 0;
+    bool k1_force_general = false;    // BDK_K1_GENERAL (tests): the general multi-key variant also where the four-key one applies
     size_t k1_smem = 0;
     uint64_t launches = 0;       // kernels launched since the last bdk_reset
     uint64_t h2d_bytes = 0;      // bytes the last bdk_push copied host -> device
@@ -172,9 +173,11 @@ int reset_job(bdk_ctx* c) {
 
 typedef void (*K1Fn)(const K1Args);
 K1Fn k1_fn(const bdk_ctx* c) {
-    const bool single = c->nkey == 1 && c->P.nbam == 1 && c->ncnt == 1, smem = c->P.nrg <= K1_RG_SMEM;   // FAST variant
-    return single ? (smem ? k1_classify_kernel<true, true> : k1_classify_kernel<true, false>)
-                  : (smem ? k1_classify_kernel<false, true> : k1_classify_kernel<false, false>);
+    const bool single = c->nkey == 1 && c->P.nbam == 1 && c->ncnt == 1, smem = c->P.nrg <= K1_RG_SMEM;
+    const bool keys4 = !single && c->nkey <= 4 && c->P.nbam <= 4 && c->ncnt >= 1 && c->ncnt <= 4 && !c->k1_force_general;
+    if (single) return smem ? k1_classify_kernel<K1_FAST, true> : k1_classify_kernel<K1_FAST, false>;
+    if (keys4) return smem ? k1_classify_kernel<K1_KEYS4, true> : k1_classify_kernel<K1_KEYS4, false>;
+    return smem ? k1_classify_kernel<K1_GENERAL, true> : k1_classify_kernel<K1_GENERAL, false>;
 }
 
 int grow_segments(bdk_ctx* c, uint64_t want);
@@ -511,6 +514,7 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
     CUC(cudaMalloc(&c->d_summary.p, sizeof(bdk_summary_t))); c->d_summary.cap = sizeof(bdk_summary_t);
     CUC(cudaMalloc(&c->d_density.p, (size_t)std::max(1, c->nkey) * 4)); c->d_density.cap = (size_t)std::max(1, c->nkey) * 4;
     CUC(cudaMalloc(&c->d_scan_sums.p, SS_GRID * 4)); c->d_scan_sums.cap = SS_GRID * 4;
+    if (const char* e = getenv("BDK_K1_GENERAL")) c->k1_force_general = atoi(e) != 0;
     {   // K1 launch shape: dynamic shared memory and resident CTAs per SM
         c->k1_smem = k1_smem_bytes(p->nrg, p->nlib, c->ncnt, c->nkey, c->nkey == 1, p->nrg <= K1_RG_SMEM);
         int bps = 0;

@@ -193,16 +193,22 @@ __host__ __device__ inline size_t k1_smem_bytes(int nrg, int nlib, int ncnt, int
     return b + 128;
 }
 
-// FAST: one copy-number key, one source bam, one (library, bam) pair -- the common single-bam run: the
+// MODE K1_FAST: one copy-number key, one source bam, one (library, bam) pair -- the common single-bam run: the
 // running counts live in registers and the hot loop has no per-record branches.
+// MODE K1_KEYS4: up to four keys, four (library, bam) pairs and four bams (tumor / normal pairs, -a with a few libraries):
+// the key of a record is kept as two bit planes next to the decision masks, so the per-key counts are the single-key
+// computation repeated on masked decision bits -- thread-local arithmetic and one warp scan per key and tile, no votes and no
+// shared-memory atomics in the hot loop; the pass-1 proper-pair counts are four byte counters in one register.
+// MODE K1_GENERAL: anything else (up to 64 keys).
 // RG_SMEM: the read-group table fits in shared memory.
-template <bool FAST, bool RG_SMEM>
+enum { K1_GENERAL = 0, K1_FAST = 1, K1_KEYS4 = 2 };
+template <int MODE, bool RG_SMEM>
 __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args a) {
-    constexpr bool SINGLE_KEY = FAST;
+    constexpr bool FAST = MODE == K1_FAST, K4 = MODE == K1_KEYS4, SINGLE_KEY = FAST, GEN = MODE == K1_GENERAL;
     extern __shared__ __align__(128) unsigned char s_dyn[];
     const int ncomp = 1 + a.nkey;
     const int nhist = a.nlib * BDK_NUM_FLAGS;
-    const int ncol = a.ncnt > 1 ? a.ncnt : 0;                                      // one column: a register does it
+    const int ncol = (a.ncnt > 1 && !K4) ? a.ncnt : 0;                             // one column (or K1_KEYS4): registers do it
     unsigned char* s_ring = s_dyn;                                                 // [K1_STAGES][K1_STAGE_BYTES]
     RgDev* s_rg = reinterpret_cast<RgDev*>(s_ring + K1_STAGES * K1_STAGE_BYTES);   // RG_SMEM: [nrg + 1]
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_rg + (RG_SMEM ? a.nrg + 1 : 0));   // [nlib * 11]
@@ -306,16 +312,21 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     bdk_aread* seg_ar = a.seg_ar + (size_t)blockIdx.x * a.seg_cap;
     uint32_t* seg_P = a.seg_P + (size_t)blockIdx.x * a.seg_cap * a.nkey;
     uint32_t prev_tile = 0, prev_amask = 0, prev_pmask = 0, prev_aex0 = 0, prev_aex1 = 0, prev_pex0 = 0, prev_pex1 = 0;
-    uint32_t prev_keys[K1_SUBS];
+    uint32_t prev_keys[GEN ? K1_SUBS : 1];
 #pragma unroll
-    for (int s = 0; s < K1_SUBS; ++s) prev_keys[s] = 0;
+    for (int s = 0; s < (GEN ? K1_SUBS : 1); ++s) prev_keys[s] = 0;
+    // K1_KEYS4: bit planes of the key per record, exclusive per-stage prefixes per key (a byte per stage), pass-1 counts per column
+    uint32_t prev_kb0 = 0, prev_kb1 = 0, prev_kpex[K4 ? 4 : 1][2], spc[K4 ? 4 : 1];
+#pragma unroll
+    for (int k = 0; k < (K4 ? 4 : 1); ++k) { prev_kpex[k][0] = 0; prev_kpex[k][1] = 0; spc[k] = 0; }
 
     for (uint32_t tile = tile0;; ++tile) {
         const int tb = (tile - tile0) & 1;
         const bool have = tile < tile1;
-        uint32_t amask = 0, pmask = 0, aex0 = 0, aex1 = 0, pex0 = 0, pex1 = 0, keys[K1_SUBS];
+        uint32_t amask = 0, pmask = 0, aex0 = 0, aex1 = 0, pex0 = 0, pex1 = 0, keys[GEN ? K1_SUBS : 1];
 #pragma unroll
-        for (int s = 0; s < K1_SUBS; ++s) keys[s] = 0;
+        for (int s = 0; s < (GEN ? K1_SUBS : 1); ++s) keys[s] = 0;
+        uint32_t kb0 = 0, kb1 = 0, kpex[K4 ? 4 : 1][2], spw = 0, bams32 = 0;
         if (have) {
             // ---------------- phase 1: four decisions per record, kept as bit masks ----------------------
             unsigned long long bams = 0;
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     const int nv = gi + 4 <= a.n ? 4 : (gi < a.n ? (int)(a.n - gi) : 0);
                     k1_load4_global(a.c, gi, nv, (uint32_t)a.pad_rg, r);
                 }
-                uint32_t kk = 0, a4 = 0, p4 = 0;
+                uint32_t kk = 0, a4 = 0, p4 = 0, k04 = 0, k14 = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t ri = min(r.rg[j], (uint32_t)a.nrg);
@@ -350,11 +361,15 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     bad |= L.info;
                     if (ch & CH_ANOM) a4 |= 1u << j;
                     if (ch & CH_MPROPER) p4 |= 1u << j;
-                    if (!SINGLE_KEY) kk |= ((L.info >> RGI_KEY_SHIFT) & 0x3fu) << (8 * j);
-                    if (!FAST && a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
+                    if (GEN) kk |= ((L.info >> RGI_KEY_SHIFT) & 0x3fu) << (8 * j);
+                    if (GEN && a.nbam > 1) bams |= 1ull << ((L.info >> RGI_BAM_SHIFT) & 0x3fu);
                     // pass-1 proper-pair count per (library, bam)
                     const uint32_t sp = (ch >> 3) & 1u;          // CH_SPROPER
-                    if (FAST || a.ncnt == 1) spcnt += sp;
+                    if (K4) {
+                        k04 |= ((L.info >> RGI_KEY_SHIFT) & 1u) << j; k14 |= ((L.info >> (RGI_KEY_SHIFT + 1)) & 1u) << j;
+                        bams32 |= 1u << ((L.info >> RGI_BAM_SHIFT) & 3u);
+                        spw += sp << (((L.info >> RGI_CNT_SHIFT) & 3u) * 8);          // at most 32 records per thread and tile: a byte per column
+                    } else if (FAST || a.ncnt == 1) spcnt += sp;
                     else if (a.ncnt) atomicAdd(my_cnt + ((L.info >> RGI_CNT_SHIFT) & 31u) * K1_CTHREADS, sp);   // private column: no conflicts
                     else {                                       // many (library, bam) pairs: one atomic per distinct read group and warp
                         const unsigned spm = __ballot_sync(FULL, sp && r.rg[j] < (uint32_t)a.nrg);
@@ -383,7 +398,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     ++g;
                 }
                 amask |= a4 << (4 * s); pmask |= p4 << (4 * s);
-                if (!SINGLE_KEY) keys[s] = kk;
+                if (GEN) keys[s] = kk;
+                if (K4) { kb0 |= k04 << (4 * s); kb1 |= k14 << (4 * s); }
             }
             // ---------------- warp level: ranks inside the warp's 8 x 128 records ------------------------
             {
@@ -397,6 +413,22 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 const uint32_t i0 = warp_incl_scan(c0), i1 = warp_incl_scan(c1);
                 pex0 = i0 - c0; pex1 = i1 - c1;
                 if (lane == 31) s_tot[((size_t)tb * ncomp + 1) * K1_CWARPS + warp] = make_uint2(i0, i1);
+            } else if (K4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k >= a.nkey) break;
+                    const uint32_t pm = pmask & ((k & 1) ? kb0 : ~kb0) & ((k & 2) ? kb1 : ~kb1);      // kept proper pairs of key k
+                    const uint32_t c0 = nibble_counts(pm & 0xffffu), c1 = nibble_counts(pm >> 16);
+                    const uint32_t i0 = warp_incl_scan(c0), i1 = warp_incl_scan(c1);
+                    kpex[k][0] = i0 - c0; kpex[k][1] = i1 - c1;
+                    if (lane == 31) s_tot[((size_t)tb * ncomp + 1 + k) * K1_CWARPS + warp] = make_uint2(i0, i1);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) spc[c] += (spw >> (8 * c)) & 0xffu;
+                if (a.nbam > 1) {
+                    bams32 = __reduce_or_sync(FULL, bams32);
+                    if (lane == 0) s_wb[tb][warp] = bams32;
+                }
             } else {
                 unsigned long long present = 0;
 #pragma unroll
@@ -420,7 +452,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     if (lane == 0) s_tot[((size_t)tb * ncomp + 1 + k) * K1_CWARPS + warp] = make_uint2(c0, c1);
                 }
             }
-            if (!FAST && a.nbam > 1) {
+            if (GEN && a.nbam > 1) {
                 bams = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)bams) | ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(bams >> 32)) << 32);
                 if (lane == 0) s_wb[tb][warp] = bams;
             }
@@ -457,9 +489,19 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     if (SINGLE_KEY) {
                         seg_P[o] = s_base[pb * ncomp + 1] + s_off[((size_t)pb * ncomp + 1) * 64 + s * 8 + warp] + byte_of2(prev_pex0, prev_pex1, s) + __popc(p4 & below);
                     }
+                    if (K4) {
+                        const uint32_t k04 = (prev_kb0 >> (4 * s)) & 0xFu, k14 = (prev_kb1 >> (4 * s)) & 0xFu;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k >= a.nkey) break;
+                            const uint32_t pk = p4 & ((k & 1) ? k04 : ~k04) & ((k & 2) ? k14 : ~k14);
+                            seg_P[(size_t)o * a.nkey + k] = s_base[pb * ncomp + 1 + k] + s_off[((size_t)pb * ncomp + 1 + k) * 64 + s * 8 + warp]
+                                                            + byte_of2(prev_kpex[k][0], prev_kpex[k][1], s) + __popc(pk & below);
+                        }
+                    }
                 }
             }
-            if (!SINGLE_KEY) {
+            if (GEN) {
                 // per key: proper pairs of lower lanes in the same stage come from warp votes (all lanes take part)
                 const uint32_t base_a = s_base[pb * ncomp];
                 const uint16_t* off_a = s_off + ((size_t)pb * ncomp) * 64;
@@ -501,14 +543,26 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
         if (!have) break;
         prev_have = true; prev_tile = tile; prev_amask = amask; prev_pmask = pmask;
         prev_aex0 = aex0; prev_aex1 = aex1; prev_pex0 = pex0; prev_pex1 = pex1;
-        if (!SINGLE_KEY) {
+        if (GEN) {
 #pragma unroll
             for (int s = 0; s < K1_SUBS; ++s) prev_keys[s] = keys[s];
+        }
+        if (K4) {
+            prev_kb0 = kb0; prev_kb1 = kb1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { prev_kpex[k][0] = kpex[k][0]; prev_kpex[k][1] = kpex[k][1]; }
         }
     }
     // ---------------- epilogue of the consumers: flush the accumulators --------------------------------------
     if (__any_sync(FULL, (bad & RGI_INVALID) != 0) && lane == 0) atomicOr(a.err, K1_ERR_RG);
-    if (FAST || a.ncnt == 1) {
+    if (K4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c >= a.ncnt) break;
+            const uint32_t t = __reduce_add_sync(FULL, spc[c]);
+            if (lane == 0 && t) atomicAdd(a.rg_sproper + a.cnt_rg[c], (unsigned long long)t);
+        }
+    } else if (FAST || a.ncnt == 1) {
         spcnt = __reduce_add_sync(FULL, spcnt);
         if (lane == 0 && spcnt) atomicAdd(a.rg_sproper + a.cnt_rg[0], (unsigned long long)spcnt);
     }

@@ -132,6 +132,18 @@ def test_gpu_segment_overflow_retry(monkeypatch):
     _check(b, cols, "tiny segments, single-key path")
 
 
+@pytest.mark.parametrize("od", [dict(), dict(CN_lib=True), dict(transchr_rearrange=True), dict(CN_lib=True, min_map_qual=10, cut_sd=2)],
+                         ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()) or "default")
+def test_gpu_general_multi_key_classifier_matches_oracle(monkeypatch, od):
+    """Two bams / four libraries normally take the four-key variant of the classify kernel (key bit planes); the general
+    variant (up to 64 keys, warp votes) is forced here on the same inputs. Both must give the oracle's stream and counts."""
+    monkeypatch.setenv("BDK_K1_GENERAL", "1")
+    w = synth.generate(util.GENOME3, util.LIBS4, 150000, seed=77, anomaly_frac=0.05, somatic_frac=0.3)
+    b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+    _check(b, cols, f"general K1 {od}")
+    _check(b, cols, f"general K1 {od}, 3 pushes", chunks=3)
+
+
 def test_gpu_more_rows_than_the_first_result_copy(monkeypatch):
     """More SV rows than the first device-to-host copy was sized for (forced: 16 rows): the rest comes with a second copy."""
     monkeypatch.setenv("BDK_ROWS_GUESS", "16")
