@@ -81,7 +81,7 @@ struct bdk_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // finish() work space
     DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region,
-        d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_reg, d_table, d_ekeys, d_ecnt,
+        d_mate, d_sv_of_read, d_cand_first, d_cand_maxlen, d_cand_info, d_cand_regs, d_reg, d_table, d_ekeys, d_ecnt,
         d_se, d_se2, d_wstart, d_wdir, d_wund, d_wfill, d_slot_base, d_sefl, d_queue, d_biglist, d_rowpack, d_outpack, d_slot_order, d_pois_l, d_pois_k, d_pois_o;
     uint64_t d2h_bytes = 0;
     uint32_t rows_guess = 0;      // rows the first result copy brings back (a second copy follows only when there are more)
@@ -401,7 +401,7 @@ void bdk_destroy(bdk_ctx* c) {
         &c->d_rgtab, &c->d_cnt_rg, &c->d_lib_mean, &c->d_blibs, &c->d_rg_lib, &c->d_rg_bam, &c->d_acc, &c->d_acc_bak, &c->d_seg_ar,
         &c->d_seg_P, &c->d_seg_cnt, &c->d_carry_out, &c->d_tile_bams, &c->d_stash, &c->d_cnt, &c->d_ar, &c->d_P, &c->d_summary,
         &c->d_density, &c->d_scan_sums, &c->d_read_cand, &c->d_read_region, &c->d_mate, &c->d_sv_of_read,
-        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt,
+        &c->d_cand_first, &c->d_cand_maxlen, &c->d_cand_info, &c->d_cand_regs, &c->d_reg, &c->d_table, &c->d_ekeys, &c->d_ecnt,
         &c->d_se, &c->d_se2, &c->d_wstart, &c->d_wdir, &c->d_wund, &c->d_wfill, &c->d_slot_base, &c->d_sefl, &c->d_queue, &c->d_biglist, &c->d_rowpack, &c->d_outpack,
         &c->d_slot_order, &c->d_pois_l, &c->d_pois_k, &c->d_pois_o};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
@@ -686,7 +686,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     { int rc2 = grow_out(c, A1); if (rc2) return rc2; }
     ENS(c->d_read_cand, A1 * 4); ENS(c->d_read_region, A1 * 4);
     ENS(c->d_mate, A1 * 4); ENS(c->d_sv_of_read, A1 * 4); ENS(c->d_cand_first, A1 * 4); ENS(c->d_cand_maxlen, A1 * 4);
-    ENS(c->d_cand_info, A1 * sizeof(CandInfo)); ENS(c->d_reg, A1 * sizeof(RegionRec));
+    ENS(c->d_cand_info, A1 * sizeof(CandInfo)); ENS(c->d_cand_regs, A1 * 4); ENS(c->d_reg, A1 * sizeof(RegionRec));
     uint32_t tsize = 1024; while (tsize < 2 * (uint64_t)A) tsize <<= 1;
     ENS(c->d_table, (size_t)tsize * 4);
     const size_t nwin_cap = A1 / (size_t)period + 2;
@@ -705,7 +705,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
                                                          c->P.seq_coverage_lim, c->d_cand_maxlen.as<int32_t>(), c->d_cand_info.as<CandInfo>());
     device_scan(st, AcceptFlag{c->d_cand_info.as<CandInfo>()},
                 RegionOut{c->d_ar.as<bdk_aread>(), c->d_cand_first.as<uint32_t>(), c->d_cand_info.as<CandInfo>(), d_cnt, c->d_reg.as<RegionRec>(),
-                          c->d_read_region.as<int32_t>(), dummy, c->P.chr_restricted, c->P.min_read_pair},
+                          c->d_read_region.as<int32_t>(), c->d_cand_regs.as<int32_t>(), dummy, c->P.chr_restricted, c->P.min_read_pair},
                 d_cnt + CNT_NCAND, d_cnt + CNT_NREG, (uint32_t)dummy, ssc);
     c->launches += 3 + 1 + 3;   // two scans (3 kernels each) + the candidate kernel
     tstop(c, T_K2);
@@ -726,7 +726,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
     k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
     k3_read_info_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), c->d_read_cand.as<int32_t>(),
-        c->d_reg.as<RegionRec>(), d_cnt, period, c->P.min_read_pair, ekeys, ecnt, esize - 1, A, c->d_ri.as<ReadInfo2>(), c->d_sv_of_read.as<int32_t>());
+        c->d_reg.as<RegionRec>(), c->d_cand_regs.as<int32_t>(), d_cnt, period, c->P.min_read_pair, ekeys, ecnt, esize - 1, A, c->d_ri.as<ReadInfo2>(), c->d_sv_of_read.as<int32_t>());
     // the followed edges, bucketed by flush window
     k3_strong_count_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(ekeys, ecnt, esize, c->P.min_read_pair, period, c->d_wdir.as<uint32_t>(), c->d_wund.as<uint32_t>());
     k3_window_scan_kernel<<<1, K3S_THREADS, 0, st>>>(c->d_wdir.as<uint32_t>(), c->d_wund.as<uint32_t>(), period, c->d_wstart.as<uint32_t>(),

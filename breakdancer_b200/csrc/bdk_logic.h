@@ -457,22 +457,16 @@ BDK_HD int k4n_last_region(const K4N& S, int w) {          // last_region_idx() 
 }
 BDK_HD bool k4n_before(int d, int w, int rm, int v) { return d < w || (d == w && rm < v); }   // rm cleared before (w, v)?
 
-// first flush window whose trigger candidate lies behind candidate `c` (the collapse of c has happened by then):
-// regions are in candidate order, g = index of the first region with cand > c, window = g / period
-BDK_HD int k4n_window_after_cand(const RegionRec* reg, int nreg, int period, int c) {
-    int a = 0, b = nreg;
-    while (a < b) { const int m = (a + b) >> 1; if (reg[m].cand > c) b = m; else a = m + 1; }
-    return a / period;
-}
-
+// cand_regs[c] = number of regions registered up to and including candidate c = index g of the first region behind c; the first
+// flush window whose trigger lies behind c (the collapse of c has happened by then) is g / period
 BDK_HD ReadInfo2 k4n_make_read_info(const bdk_aread* ar, const int32_t* mate, const int32_t* read_region, const int32_t* read_cand,
-                                    const RegionRec* reg, int nreg, int period, int j, bool strong) {
+                                    const RegionRec* reg, const int32_t* cand_regs, int period, int j, bool strong) {
     ReadInfo2 r;
     r.mate = mate[j];
     r.mate_region = r.mate >= 0 ? read_region[r.mate] : -1;
     r.wthr = 0;
     r.meta = ar[j].meta & 0x00ffffffu;
-    if (r.mate >= 0 && r.mate_region < 0 && r.mate > j) r.wthr = k4n_window_after_cand(reg, nreg, period, read_cand[r.mate]);
+    if (r.mate >= 0 && r.mate_region < 0 && r.mate > j) r.wthr = cand_regs[read_cand[r.mate]] / period;
     if (r.mate_region >= 0) {
         if (strong) r.meta |= RI_STRONG;
         if (reg[r.mate_region].stored) r.meta |= RI_MATE_STORED;

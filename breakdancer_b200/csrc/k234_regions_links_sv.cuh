@@ -72,9 +72,10 @@ struct AcceptFlag {
 };
 struct RegionOut {   // writes the region table and the read -> region map
     const bdk_aread* ar; const uint32_t* cand_first; const CandInfo* ci; const uint32_t* d_cnt;
-    RegionRec* reg; int32_t* read_region; int32_t dummy, chr_restricted, min_read_pair;
+    RegionRec* reg; int32_t* read_region; int32_t* cand_regs; int32_t dummy, chr_restricted, min_read_pair;
     __device__ void operator()(uint32_t c, uint32_t inc, uint32_t v, uint32_t ncand) const {
         const uint32_t A = d_cnt[CNT_A];
+        cand_regs[c] = (int32_t)inc + dummy;          // regions registered up to and including candidate c = index of the first region behind it
         const uint32_t s = cand_first[c], e = (c + 1 < ncand ? cand_first[c + 1] : A) - 1;
         int32_t r = -1;
         if (v) {
@@ -157,10 +158,10 @@ __device__ __forceinline__ uint32_t k3_edge_weight(const unsigned long long* __r
 
 // per-read static information for K4 (bdk_logic.h: ReadInfo2), one thread per anomalous read
 __global__ void __launch_bounds__(GS_THREADS) k3_read_info_kernel(const bdk_aread* __restrict__ ar, const int32_t* __restrict__ mate,
-        const int32_t* __restrict__ read_region, const int32_t* __restrict__ read_cand, const RegionRec* __restrict__ reg, const uint32_t* __restrict__ d_cnt,
-        int period, int min_read_pair, const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t mask, uint32_t A,
+        const int32_t* __restrict__ read_region, const int32_t* __restrict__ read_cand, const RegionRec* __restrict__ reg, const int32_t* __restrict__ cand_regs,
+        const uint32_t* __restrict__ d_cnt, int period, int min_read_pair, const unsigned long long* __restrict__ tkeys, const uint32_t* __restrict__ tcnt, uint32_t mask, uint32_t A,
         ReadInfo2* __restrict__ ri, int32_t* __restrict__ sv_of_read) {
-    const int nreg = (int)d_cnt[CNT_NREG];
+    (void)d_cnt;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A; j += gridDim.x * blockDim.x) {
         const int m = mate[j];
         bool strong = false;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(GS_THREADS) k3_read_info_kernel(const bdk_area
             const int rj = read_region[j], rm = read_region[m];
             if (rj >= 0 && rm >= 0 && rj != rm) strong = (int)k3_edge_weight(tkeys, tcnt, mask, min(rj, rm), max(rj, rm)) >= min_read_pair;
         }
-        ri[j] = k4n_make_read_info(ar, mate, read_region, read_cand, reg, nreg, period, (int)j, strong);
+        ri[j] = k4n_make_read_info(ar, mate, read_region, read_cand, reg, cand_regs, period, (int)j, strong);
         sv_of_read[j] = -1;
     }
 }

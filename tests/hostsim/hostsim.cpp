@@ -76,7 +76,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
         read_cand[j] = (int32_t)cand_first.size() - 1;
     }
     int ncand = (int)cand_first.size();
-    std::vector<int32_t> cand_maxlen(ncand);
+    std::vector<int32_t> cand_maxlen(ncand), cand_regs(ncand);
     std::vector<RegionRec> reg;
     int dummy = (A > 0) ? dummy_region_of(p) : 0;
     if (dummy) { RegionRec d; d.tid = -1; d.start = -1; d.end = -1; d.fwd = d.rev = 0; d.first_read = 0; d.n_reads = 0; d.stored = 0; d.cand = -1; reg.push_back(d); }
@@ -94,6 +94,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
             for (int64_t j = s; j <= e; ++j) { read_region[j] = (int32_t)reg.size(); alive[j] = R.stored; }
             reg.push_back(R);
         }
+        cand_regs[cidx] = (int32_t)reg.size();
     }
     int nreg = (int)reg.size();
     int period = period_of(p);
@@ -135,7 +136,7 @@ extern "C" int hostsim_run(const bdk_params* pp, const bdk_soa* c, uint64_t n, b
             const int a = std::min(read_region[j], read_region[m]), b2 = std::max(read_region[j], read_region[m]);
             strong = weight[((uint64_t)(uint32_t)a << 32) | (uint32_t)b2] >= p.min_read_pair;
         }
-        ri[j] = k4n_make_read_info(ar.data(), mate.data(), read_region.data(), read_cand.data(), reg.data(), nreg, period, (int)j, strong);
+        ri[j] = k4n_make_read_info(ar.data(), mate.data(), read_region.data(), read_cand.data(), reg.data(), cand_regs.data(), period, (int)j, strong);
     }
     K4N KS;
     KS.ri = ri.data(); KS.ar = ar.data(); KS.reg = reg.data(); KS.nreg = nreg; KS.period = period;
