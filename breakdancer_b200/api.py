@@ -106,6 +106,50 @@ class Options:
     score_threshold: int = 30     # -y
 
 
+class Packed(C.Structure):
+    """bdk_packed (include/bdk.h): one run of records in the 12-byte wire format."""
+    _fields_ = [("pos", C.c_void_p), ("meta", C.c_void_p), ("rel", C.c_void_p), ("qlen", C.c_void_p), ("qid", C.c_void_p),
+                ("tid", C.c_int32), ("reserved", C.c_uint32), ("nx", C.c_uint64),
+                ("x_index", C.c_void_p), ("x_mpos", C.c_void_p), ("x_mtid", C.c_void_p), ("x_isize", C.c_void_p),
+                ("x_flag", C.c_void_p), ("x_rgid", C.c_void_p)]
+
+
+class PackedRun:
+    """A packed run (bdk_pack) and the buffers behind it; keeps the source columns alive (pos / qlen / qid are used in place)."""
+
+    def __init__(self, soa: "Soa", n: int, keep=None, threads: int = 0):
+        L = load_library()
+        self.view, self._buf, self.n, self._keep = Packed(), C.c_void_p(), n, keep
+        rc = L.bdk_pack(C.byref(soa), n, threads, C.byref(self._buf), C.byref(self.view))
+        if rc != 0:
+            raise BdkError(f"bdk_pack failed ({rc}): {L.bdk_last_error(None).decode()}")
+
+    def close(self):
+        if self._buf:
+            load_library().bdk_pack_free(self._buf)
+            self._buf = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_runs(cols: Dict[str, np.ndarray]) -> List["PackedRun"]:
+    """Packed runs of (tid, pos)-sorted columns, one per reference sequence, in stream order."""
+    tid = cols["tid"]
+    n = len(tid)
+    if n == 0:
+        return []
+    edges = [0] + (np.flatnonzero(np.diff(tid)) + 1).tolist() + [n]
+    runs = []
+    for a, b in zip(edges[:-1], edges[1:]):
+        sub = {k: np.ascontiguousarray(v[a:b]) for k, v in cols.items()}
+        runs.append(PackedRun(make_soa(sub), b - a, keep=sub))
+    return runs
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -128,6 +172,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdk_reset": (C.c_int, [vp]),
         "bdk_push": (C.c_int, [vp, C.POINTER(Soa), u64]),
         "bdk_push_device": (C.c_int, [vp, C.POINTER(Soa), u64]),
+        "bdk_push_packed": (C.c_int, [vp, C.POINTER(Packed), u64]),
+        "bdk_pack": (C.c_int, [C.POINTER(Soa), u64, C.c_int, C.POINTER(vp), C.POINTER(Packed)]),
+        "bdk_pack_free": (None, [vp]),
         "bdk_summary": (C.c_int, [vp, C.POINTER(SummaryT)]),
         "bdk_finish": (C.c_int, [vp, C.POINTER(Result)]),
         "bdk_get_regions": (C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)]),
@@ -421,6 +468,9 @@ class Context:
         n = len(cols["pos"])
         soa = make_soa(cols)
         self._check(self._L.bdk_push(self._h, C.byref(soa), n), "bdk_push")
+
+    def push_packed(self, run: "PackedRun"):
+        self._check(self._L.bdk_push_packed(self._h, C.byref(run.view), run.n), "bdk_push_packed")
 
     def push_soa(self, soa: Soa, n: int, device: bool):
         fn = self._L.bdk_push_device if device else self._L.bdk_push

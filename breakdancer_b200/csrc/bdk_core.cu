@@ -13,6 +13,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bdk.h"
@@ -78,6 +79,7 @@ struct bdk_ctx {
     uint32_t seg_cap = 0, seg_cap_min = 8192;
     // chunk buffers for host pushes
     DevBuf d_chunk[2][10];
+    DevBuf d_pk[2][3], d_px[2][6];      // packed pushes: staging of the wire-format arrays and of a chunk's exceptions
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // finish() work space
     DevBuf d_cnt, d_ar, d_P, d_summary, d_density, d_scan_sums, d_read_cand, d_read_region,
@@ -407,6 +409,8 @@ void bdk_destroy(bdk_ctx* c) {
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 10; ++k) if (c->d_chunk[i][k].p) cudaFree(c->d_chunk[i][k].p);
+        for (int k = 0; k < 3; ++k) if (c->d_pk[i][k].p) cudaFree(c->d_pk[i][k].p);
+        for (int k = 0; k < 6; ++k) if (c->d_px[i][k].p) cudaFree(c->d_px[i][k].p);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
@@ -618,6 +622,162 @@ int bdk_push(bdk_ctx* c, const bdk_soa* h, uint64_t n) {
             d.mapq = c->d_chunk[b][6].as<uint8_t>(); d.rgid = c->d_chunk[b][7].as<uint16_t>();
             if (zero_copy) { d.qlen = (const int32_t*)side_dev[0] + off; d.qid = (const uint64_t*)side_dev[1] + off; }
             else { d.qlen = c->d_chunk[b][8].as<int32_t>(); d.qid = c->d_chunk[b][9].as<uint64_t>(); }
+            int rc = launch_k1(c, d, m, (uint32_t)(c->n_records + off), false);
+            if (rc) return rc;
+            CU(cudaEventRecord(c->ev_done[b], c->stream));
+            off += m; ++i;
+        }
+        tstop(c, T_H2D);
+        return 0;
+    });
+}
+
+struct bdk_packed_buf {
+    void* meta = nullptr; void* rel = nullptr; void* x = nullptr;      // pinned
+};
+
+void bdk_pack_free(bdk_packed_buf* b) {
+    if (!b) return;
+    if (b->meta) cudaFreeHost(b->meta);
+    if (b->rel) cudaFreeHost(b->rel);
+    if (b->x) cudaFreeHost(b->x);
+    delete b;
+}
+
+int bdk_pack(const bdk_soa* h, uint64_t n, int threads, bdk_packed_buf** out, bdk_packed* view) {
+    bdk_ctx* c = nullptr;
+    if (!h || !out || !view) return fail(c, BDK_ERR_ARG, "null argument");
+    *out = nullptr;
+    memset(view, 0, sizeof *view);
+    if (n > 0xffffffffull) return fail(c, BDK_ERR_ARG, "more than 2^32 records in one run");
+    bdk_packed_buf* b = new bdk_packed_buf;
+    if (cudaHostAlloc(&b->meta, std::max<uint64_t>(n, 4) * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&b->rel, std::max<uint64_t>(n, 4) * 4, cudaHostAllocDefault) != cudaSuccess) {
+        bdk_pack_free(b);
+        return fail(c, BDK_ERR_CUDA, "cudaHostAlloc failed in bdk_pack: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    uint32_t* meta = (uint32_t*)b->meta; uint32_t* rel = (uint32_t*)b->rel;
+    const int32_t tid = n ? h->tid[0] : 0;
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::max<uint64_t>(1, std::min<uint64_t>(T, n / 65536 + 1));
+    struct Exc { uint32_t index; int32_t mpos, mtid, isize; uint16_t flag, rgid; };
+    std::vector<std::vector<Exc>> exc(T);
+    std::vector<int> bad(T, 0);
+    auto work = [&](int t) {
+        const uint64_t lo = n * t / T, hi = n * (t + 1) / T;
+        for (uint64_t i = lo; i < hi; ++i) {
+            if (h->tid[i] != tid) { bad[t] = 1; return; }
+            const int32_t is = h->isize[i];
+            const int64_t dm = (int64_t)h->mpos[i] - h->pos[i];
+            const uint32_t fl = h->flag[i], rg = h->rgid[i];
+            const bool fits = h->mtid[i] == tid && is >= -32768 && is < 32768 && dm >= -32768 && dm < 32768 && fl < 4096u && rg < BDK_PACKED_EXCEPT;
+            meta[i] = (fl & 0xfffu) | ((uint32_t)h->mapq[i] << 12) | ((fits ? rg : BDK_PACKED_EXCEPT) << 20);
+            rel[i] = fits ? (((uint32_t)is & 0xffffu) | ((uint32_t)dm << 16)) : 0u;
+            if (!fits) exc[t].push_back(Exc{(uint32_t)i, h->mpos[i], h->mtid[i], is, (uint16_t)fl, (uint16_t)rg});
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) if (bad[t]) { bdk_pack_free(b); return fail(c, BDK_ERR_ARG, "bdk_pack: the records of a run must lie on one reference sequence"); }
+    uint64_t nx = 0;
+    for (auto& e : exc) nx += e.size();
+    const uint64_t nxa = (nx + 3) & ~3ull;                   // every exception array 16-byte aligned
+    if (cudaHostAlloc(&b->x, std::max<uint64_t>(nxa, 4) * 20, cudaHostAllocDefault) != cudaSuccess) {
+        bdk_pack_free(b);
+        return fail(c, BDK_ERR_CUDA, "cudaHostAlloc failed in bdk_pack");
+    }
+    uint32_t* xi = (uint32_t*)b->x; int32_t* xm = (int32_t*)(xi + nxa); int32_t* xt = xm + nxa; int32_t* xs = xt + nxa;
+    uint16_t* xf = (uint16_t*)(xs + nxa); uint16_t* xr = xf + nxa;
+    uint64_t k = 0;
+    for (auto& ev : exc) for (auto& e : ev) { xi[k] = e.index; xm[k] = e.mpos; xt[k] = e.mtid; xs[k] = e.isize; xf[k] = e.flag; xr[k] = e.rgid; ++k; }
+    view->pos = h->pos; view->meta = meta; view->rel = rel; view->qlen = h->qlen; view->qid = h->qid; view->tid = tid; view->nx = nx;
+    view->x_index = xi; view->x_mpos = xm; view->x_mtid = xt; view->x_isize = xs; view->x_flag = xf; view->x_rgid = xr;
+    *out = b;
+    return 0;
+}
+
+int bdk_push_packed(bdk_ctx* c, const bdk_packed* h, uint64_t n) {
+    if (!c || !h) return BDK_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (n && (!h->pos || !h->meta || !h->rel || !h->qlen || !h->qid)) return fail(c, BDK_ERR_ARG, "null array in bdk_packed");
+    if (h->nx && (!h->x_index || !h->x_mpos || !h->x_mtid || !h->x_isize || !h->x_flag || !h->x_rgid)) return fail(c, BDK_ERR_ARG, "null exception array in bdk_packed");
+    if (h->tid < 0 || h->tid >= c->P.ntid) return fail(c, BDK_ERR_ARG, "bdk_packed.tid out of range");
+    const uint64_t CH = (uint64_t)K1_TILE * 1024;
+    const uint64_t chunk_cap = std::min<uint64_t>(CH, div_up<uint64_t>(std::max<uint64_t>(n, 1), K1_TILE) * K1_TILE);
+    static const size_t width[10] = {4, 4, 4, 4, 4, 2, 1, 2, 4, 8};
+    const void* side[2] = {h->qlen, h->qid};
+    const void* side_dev[2] = {nullptr, nullptr};
+    bool zero_copy = n > 0 && !getenv("BDK_NO_ZEROCOPY");
+    for (int k = 0; k < 2 && zero_copy; ++k) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, side[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { cudaGetLastError(); zero_copy = false; }
+        else side_dev[k] = at.devicePointer;
+    }
+    // exceptions of every chunk: ranges of the ascending x_index
+    uint64_t max_x = 0;
+    for (uint64_t off = 0; off < n; off += CH) {
+        const uint32_t* lo = std::lower_bound(h->x_index, h->x_index + h->nx, (uint32_t)off);
+        const uint32_t* hi = std::lower_bound(lo, h->x_index + h->nx, (uint32_t)std::min<uint64_t>(off + CH, 0xffffffffull));
+        max_x = std::max<uint64_t>(max_x, (uint64_t)(hi - lo));
+    }
+    static const size_t xwidth[6] = {4, 4, 4, 4, 2, 2};
+    for (int b = 0; b < 2; ++b) {
+        for (int k = 0; k < (zero_copy ? 8 : 10); ++k) ENS(c->d_chunk[b][k], chunk_cap * width[k]);
+        for (int k = 0; k < 3; ++k) ENS(c->d_pk[b][k], chunk_cap * 4);
+        for (int k = 0; k < 6; ++k) ENS(c->d_px[b][k], (max_x + 8) * xwidth[k]);
+    }
+    c->h2d_bytes = 0;
+    return push_common(c, n, CH, [&]() -> int {
+        CU(cudaEventRecord(c->ev_done[0], c->stream));
+        CU(cudaEventRecord(c->ev_done[1], c->stream));
+        tstart(c, T_H2D);
+        uint64_t off = 0; int i = 0;
+        c->h2d_bytes = 0;
+        const void* pk[3] = {h->pos, h->meta, h->rel};
+        const void* xs[6] = {h->x_index, h->x_mpos, h->x_mtid, h->x_isize, h->x_flag, h->x_rgid};
+        while (off < n) {
+            const uint64_t m = std::min<uint64_t>(CH, n - off);
+            const int b = i & 1;
+            const uint32_t* xlo = std::lower_bound(h->x_index, h->x_index + h->nx, (uint32_t)off);
+            const uint32_t* xhi = std::lower_bound(xlo, h->x_index + h->nx, (uint32_t)std::min<uint64_t>(off + m, 0xffffffffull));
+            const uint64_t x0 = (uint64_t)(xlo - h->x_index), nxc = (uint64_t)(xhi - xlo);
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+            for (int k = 0; k < 3; ++k) {
+                CU(cudaMemcpyAsync(c->d_pk[b][k].p, (const char*)pk[k] + off * 4, m * 4, cudaMemcpyHostToDevice, c->copy_stream));
+                c->h2d_bytes += m * 4;
+            }
+            if (nxc)
+                for (int k = 0; k < 6; ++k) {
+                    CU(cudaMemcpyAsync(c->d_px[b][k].p, (const char*)xs[k] + x0 * xwidth[k], nxc * xwidth[k], cudaMemcpyHostToDevice, c->copy_stream));
+                    c->h2d_bytes += nxc * xwidth[k];
+                }
+            if (!zero_copy)
+                for (int k = 8; k < 10; ++k) {
+                    CU(cudaMemcpyAsync(c->d_chunk[b][k].p, (const char*)side[k - 8] + off * width[k], m * width[k], cudaMemcpyHostToDevice, c->copy_stream));
+                    c->h2d_bytes += m * width[k];
+                }
+            CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+            bdk_soa d;
+            d.pos = c->d_chunk[b][0].as<int32_t>(); d.mpos = c->d_chunk[b][1].as<int32_t>(); d.tid = c->d_chunk[b][2].as<int32_t>();
+            d.mtid = c->d_chunk[b][3].as<int32_t>(); d.isize = c->d_chunk[b][4].as<int32_t>(); d.flag = c->d_chunk[b][5].as<uint16_t>();
+            d.mapq = c->d_chunk[b][6].as<uint8_t>(); d.rgid = c->d_chunk[b][7].as<uint16_t>();
+            if (zero_copy) { d.qlen = (const int32_t*)side_dev[0] + off; d.qid = (const uint64_t*)side_dev[1] + off; }
+            else { d.qlen = c->d_chunk[b][8].as<int32_t>(); d.qid = c->d_chunk[b][9].as<uint64_t>(); }
+            k1_expand_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->d_pk[b][0].as<int32_t>(), c->d_pk[b][1].as<uint32_t>(), c->d_pk[b][2].as<uint32_t>(), m, h->tid,
+                (uint16_t)c->pad_rg, c->d_chunk[b][0].as<int32_t>(), c->d_chunk[b][1].as<int32_t>(), c->d_chunk[b][2].as<int32_t>(), c->d_chunk[b][3].as<int32_t>(),
+                c->d_chunk[b][4].as<int32_t>(), c->d_chunk[b][5].as<uint16_t>(), c->d_chunk[b][6].as<uint8_t>(), c->d_chunk[b][7].as<uint16_t>());
+            if (nxc)
+                k1_expand_exceptions_kernel<<<(unsigned)std::min<uint64_t>(div_up<uint64_t>(nxc, 256), kNumSMs * 4), 256, 0, c->stream>>>(
+                    c->d_px[b][0].as<uint32_t>(), c->d_px[b][1].as<int32_t>(), c->d_px[b][2].as<int32_t>(), c->d_px[b][3].as<int32_t>(), c->d_px[b][4].as<uint16_t>(),
+                    c->d_px[b][5].as<uint16_t>(), nxc, (uint32_t)off, c->d_chunk[b][1].as<int32_t>(), c->d_chunk[b][3].as<int32_t>(), c->d_chunk[b][4].as<int32_t>(),
+                    c->d_chunk[b][5].as<uint16_t>(), c->d_chunk[b][7].as<uint16_t>());
+            c->launches += nxc ? 2 : 1;
+            CU(cudaGetLastError());
             int rc = launch_k1(c, d, m, (uint32_t)(c->n_records + off), false);
             if (rc) return rc;
             CU(cudaEventRecord(c->ev_done[b], c->stream));

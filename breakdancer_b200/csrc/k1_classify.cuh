@@ -576,6 +576,33 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     }
 }
 
+// ---- wire format -> hot columns -------------------------------------------------------------------------
+// A chunk of a packed run (include/bdk.h: bdk_packed, 12 bytes per record) back into the eight 25-byte columns K1 reads;
+// the records that did not fit the packed form are then overwritten from the exception arrays. HBM traffic 12 + 25 bytes per
+// record, hidden behind the host-to-device copy of the next chunk.
+__global__ void __launch_bounds__(256) k1_expand_kernel(const int32_t* __restrict__ ppos, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ rel,
+        uint64_t n, int32_t tid, uint16_t pad_rg, int32_t* __restrict__ pos, int32_t* __restrict__ mpos, int32_t* __restrict__ otid, int32_t* __restrict__ mtid,
+        int32_t* __restrict__ isize, uint16_t* __restrict__ flag, uint8_t* __restrict__ mapq, uint16_t* __restrict__ rgid) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t p = ppos[i];
+        const uint32_t m = meta[i], r = rel[i];
+        const uint32_t rg = m >> 20;
+        pos[i] = p; mpos[i] = p + (int32_t)(int16_t)(r >> 16); otid[i] = tid; mtid[i] = tid;
+        isize[i] = (int32_t)(int16_t)(r & 0xffffu);
+        flag[i] = (uint16_t)(m & 0xfffu); mapq[i] = (uint8_t)((m >> 12) & 0xffu);
+        rgid[i] = rg == BDK_PACKED_EXCEPT ? pad_rg : (uint16_t)rg;        // (overwritten by k1_expand_exceptions_kernel)
+    }
+}
+__global__ void __launch_bounds__(256) k1_expand_exceptions_kernel(const uint32_t* __restrict__ x_index, const int32_t* __restrict__ x_mpos,
+        const int32_t* __restrict__ x_mtid, const int32_t* __restrict__ x_isize, const uint16_t* __restrict__ x_flag, const uint16_t* __restrict__ x_rgid,
+        uint64_t nx, uint32_t chunk_first, int32_t* __restrict__ mpos, int32_t* __restrict__ mtid, int32_t* __restrict__ isize, uint16_t* __restrict__ flag,
+        uint16_t* __restrict__ rgid) {
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < nx; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = x_index[k] - chunk_first;
+        mpos[i] = x_mpos[k]; mtid[i] = x_mtid[k]; isize[i] = x_isize[k]; flag[i] = x_flag[k]; rgid[i] = x_rgid[k];
+    }
+}
+
 // ---- move the per-CTA segments to their final place ---------------------------------------------------
 // Block b copies segment b to ar[carry[0] + sum of the anomalous counts of segments < b ...) and adds the
 // matching kept-proper-pair prefixes to its P rows. Launched with the same grid as K1. The last block leaves

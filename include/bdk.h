@@ -186,6 +186,42 @@ int bdk_push(bdk_ctx* ctx, const bdk_soa* host_cols, uint64_t n);
 /* Same, columns already resident in this GPU's memory (16-byte aligned). */
 int bdk_push_device(bdk_ctx* ctx, const bdk_soa* dev_cols, uint64_t n);
 
+/* The same records in the decoder's WIRE FORMAT: 12 bytes per record cross the bus instead of 25. A run holds position-sorted
+ * records of ONE reference sequence (tid; the mate is on the same sequence unless excepted):
+ *   pos[i]   core.pos
+ *   meta[i]  core.flag (bits 0-11) | bdqual (bits 12-19) | read-group id (bits 20-31; BDK_PACKED_EXCEPT: see below)
+ *   rel[i]   core.isize (low 16 bits, signed) | core.mpos - core.pos (high 16 bits, signed)
+ * A record that does not fit (mate on another sequence, |isize| or |mpos - pos| >= 32768, flag >= 4096, read group >= 4095)
+ * carries BDK_PACKED_EXCEPT in the read-group field and its exact fields in the exception arrays (x_index ascending = index of
+ * the record inside the run). The device expands a chunk back into the 25-byte columns (csrc/k1_classify.cuh: k1_expand_kernel)
+ * and classifies it as usual, so results are identical to bdk_push of the unpacked records. qlen / qid as in bdk_soa.
+ * bdk_pack builds a run from columns (host, multi-threaded; the BAM decoder writes the same layout); all arrays it returns are
+ * pinned and owned by the bdk_packed_buf. Replaces, like bdk_push, the per-record hand-over of AlignmentSource::next
+ * (src/lib/io/AlignmentSource.hpp:48-65). */
+#define BDK_PACKED_EXCEPT 0xFFFu
+typedef struct bdk_packed {
+    const int32_t* pos;
+    const uint32_t* meta;
+    const uint32_t* rel;
+    const int32_t* qlen;
+    const uint64_t* qid;
+    int32_t tid;
+    uint32_t reserved;
+    uint64_t nx;
+    const uint32_t* x_index;
+    const int32_t* x_mpos;
+    const int32_t* x_mtid;
+    const int32_t* x_isize;
+    const uint16_t* x_flag;
+    const uint16_t* x_rgid;
+} bdk_packed;
+typedef struct bdk_packed_buf bdk_packed_buf;
+/* Pack n records (all of one tid, else BDK_ERR_ARG) given as columns; *view then describes the run. threads <= 0: all cores. */
+int bdk_pack(const bdk_soa* host_cols, uint64_t n, int threads, bdk_packed_buf** out, bdk_packed* view);
+void bdk_pack_free(bdk_packed_buf* buf);
+/* Feed a packed run of n records from HOST memory (pinned: asynchronous copies overlapped with the kernels). */
+int bdk_push_packed(bdk_ctx* ctx, const bdk_packed* run, uint64_t n);
+
 /* Pass-1 statistics and the derived window (BamSummary + BreakDancerMax.cpp:83-116). */
 int bdk_summary(bdk_ctx* ctx, bdk_summary_t* out);
 

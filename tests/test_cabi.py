@@ -33,6 +33,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(api.Sv) == 80
     assert C.sizeof(api.Lib) == 28
     assert api.REGION_DTYPE.itemsize == 36 and api.AREAD_DTYPE.itemsize == 32
+    assert C.sizeof(api.Packed) == 5 * 8 + 8 + 8 + 6 * 8
     assert C.sizeof(api.SummaryT) == 8 + 16 + 4 * 64 + 8 * 64 + 4 * 255 + 4 * 11 * 255 + 4 * 255 + 4 * 255
 
 

@@ -144,6 +144,49 @@ def test_gpu_general_multi_key_classifier_matches_oracle(monkeypatch, od):
     _check(b, cols, f"general K1 {od}, 3 pushes", chunks=3)
 
 
+def _check_packed(b, cols, what, pinned_side=False):
+    """The same job fed as packed runs (12-byte wire format, include/bdk.h: bdk_packed), one per reference sequence."""
+    ro = oracle.run(b, cols)
+    runs = api.pack_runs(cols)
+    ctx = api.Context(b, 0)
+    nexc = 0
+    for r in runs:
+        ctx.push_packed(r)
+        nexc += int(r.view.nx)
+    summary = ctx.summary()
+    table = ctx.finish()
+    ar, rr = ctx.areads()
+    util.assert_result_matches_oracle(ro, table, summary, ctx.regions(), ar, rr, ctx.support(), what)
+    ctx.close()
+    return ro, nexc
+
+
+@pytest.mark.parametrize("od", [dict(), dict(CN_lib=True), dict(transchr_rearrange=True), dict(max_sd=10000)],
+                         ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()) or "default")
+def test_gpu_packed_runs_match_oracle(od):
+    """Records pushed in the packed wire format give the oracle's result: three chromosomes (three runs), inter-chromosomal
+    mates and inserts beyond 16 bits travel as exceptions."""
+    w = synth.generate(util.GENOME3, util.LIBS4, 120000, seed=91, anomaly_frac=0.06, somatic_frac=0.3)
+    b, cols, *_ = util.workload_bundle(w, api.Options(**od))
+    ro, nexc = _check_packed(b, cols, f"packed {od}")
+    assert nexc > 100 and len(ro.table.sv) > 5
+
+
+def test_gpu_packed_chunked_run_with_exceptions_in_every_chunk(monkeypatch):
+    """A run longer than one 8 Mi-record chunk (config-2 shape, 9 M pairs): exceptions are cut per chunk."""
+    w = synth.config2(9_000_000, seed=5)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    ro, nexc = _check_packed(b, cols, "packed 18 M records")
+    assert nexc > 1000 and len(cols["pos"]) > 2 * 8 * 1024 * 1024
+
+
+def test_gpu_packed_rejects_a_run_over_two_chromosomes():
+    w = synth.generate(util.GENOME3, util.LIBS4, 5000, seed=1)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    with pytest.raises(api.BdkError, match="one reference sequence"):
+        api.PackedRun(api.make_soa(cols), len(cols["pos"]))
+
+
 def test_gpu_more_rows_than_the_first_result_copy(monkeypatch):
     """More SV rows than the first device-to-host copy was sized for (forced: 16 rows): the rest comes with a second copy."""
     monkeypatch.setenv("BDK_ROWS_GUESS", "16")
