@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 TAG=${2:-r01}
 K=${1:-k1_classify}
 if [ -z "$SKIP_TESTS" ]; then
-timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
-grep -E "config 3 full size|passed|failed|rc=|Error|error" gpurun_out/test_$TAG.log | tail -8
+timeout 1500 python -m pytest tests -m gpu -x -q -s --durations=12 > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
+grep -E "config 3 full size|passed|failed|rc=|Error|error|s call|s setup" gpurun_out/test_$TAG.log | tail -22
 fi
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err

@@ -2,8 +2,9 @@
 the C ABI.
 
 The whole result of both full-size jobs is compared with the oracle run on the same records (summary, anomalous stream,
-regions, SV table, supporting reads: test_fullsize_matches_oracle, test_config3_fullsize_matches_oracle; the second needs
-~60 GB of host memory and is skipped where the box has less). Beside that, size-independent properties:
+regions, SV table, supporting reads: test_fullsize_matches_oracle, test_config3_fullsize_matches_oracle; the second takes
+about ten minutes and ~60 GB of host memory and runs only with BDK_FULLSIZE_ORACLE=1 -- test_gpu_parity.py compares the same
+generator's output with the oracle at 30 M pairs in every run). Beside that, size-independent properties:
   * an independent vectorised (torch, on the device) evaluation of the classifier's decisions for this
     workload must reproduce the summary statistics K1 produces (record count, anomalous reads, per-library
     proper-pair count, flag histogram, covered reference length);
@@ -13,6 +14,8 @@ regions, SV table, supporting reads: test_fullsize_matches_oracle, test_config3_
     from pinned memory with zero-copy side columns) and under reset + re-run (idempotence);
   * every SV row is supported by reads that K4 marked as consumed by exactly that row.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -201,6 +204,8 @@ def test_config3_fullsize_matches_oracle(big3):
     oracle on the same records."""
     from breakdancer_b200 import synth_torch
     from oracle import oracle
+    if not os.environ.get("BDK_FULLSIZE_ORACLE"):
+        pytest.skip("takes ~10 minutes (22 GB of records to the host, then the oracle): set BDK_FULLSIZE_ORACLE=1; last run green in profiles/test_fullsize_oracle_r13a.txt")
     if _host_gb_available() < 90:
         pytest.skip("needs ~60 GB of host memory (22 GB of records + the oracle's state)")
     ctx = big3["ctx"]

@@ -285,6 +285,17 @@ def test_gpu_k4_forced_paths_match_oracle(monkeypatch, name):
     _check(b, synth_torch.to_numpy(cols), f"{name} config3-shaped")
 
 
+def test_gpu_config3_shape_thirty_million_pairs_matches_oracle():
+    """configs[2]'s generator at a tenth of its size (30 M pairs, 1.3 M anomalous reads, ~900 flush windows), bit-exact vs the
+    oracle; the full 300 M pairs are compared in test_gpu_fullsize.py (BDK_FULLSIZE_ORACLE=1)."""
+    import torch
+    from breakdancer_b200 import synth_torch
+    cols = synth_torch.config3_device(30_000_000, seed=20260102, device=torch.device("cuda", 0))
+    b, _ = synth_torch.config3_bundle()
+    ro = _check(b, synth_torch.to_numpy(cols), "config3-shaped 30M pairs")
+    assert len(ro.table.sv) > 10000
+
+
 def test_gpu_config3_shape_eight_million_pairs_matches_oracle():
     """Dense config-3-shaped data at 8 M pairs (tens of thousands of followed edges per chromosome), bit-exact vs the oracle."""
     import torch
