@@ -10,8 +10,10 @@ already resident in HBM (bdk_push_device); `e2e` is the same job through the C A
 columns, so host->device copies and the device->host read of the SV table are inside the timed
 region.  `roofline` is the classify kernel (25 algorithmic bytes per record) against the measured HBM
 peak; `cpu_baseline` is the unmodified reference binary on the host cores on a bounded sample;
-`bam_decode` (N = 1) is the host's BAM decode of a bounded sample on all host cores -- what bounds the
-drop-in executable on real files (no GPU work in it; reported next to e2e, not part of it).
+`cpu_baseline_decode_free` is the reference's algorithm alone on records decoded into memory beforehand (the comparator of
+`e2e`, which also starts from decoded records); `file_e2e` is the drop-in executable from a BAM file to the SV table (whole
+process, wall clock: the comparator of `cpu_baseline`); `bam_decode` (N = 1) is the host's BAM decode of a bounded sample on
+all host cores -- what bounds the drop-in executable on real files. `comparisons` puts the like-for-like pairs side by side.
 For N > 1 each rank runs its own chromosome-shaped shard (the path shards by chromosome with
 no data-path collective: weak scaling); torch.distributed/NCCL is used only for the barrier and the
 max-over-ranks of the device time.  One JSON line is printed by rank 0.  For N > 1 the line also carries
@@ -99,13 +101,74 @@ def _run_reference_once(jobs):
     return time.perf_counter() - t0, sum(n for _, n in jobs), "port"
 
 
+def _run_reference_decode_free(jobs):
+    """The unmodified reference algorithm on records decoded into memory beforehand (oracle/_ref/breakdancer-max-nodecode:
+    its BAM readers are replaced by in-memory ones), one process per job, all concurrently. Returns the slowest process's
+    algorithm time (wall minus decoding) and the pairs."""
+    import re
+    from oracle import oracle
+    procs = [subprocess.Popen([oracle.REF_NODECODE, "cfg"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for d, _ in jobs]
+    algo = []
+    for p in procs:
+        err = p.communicate()[1]
+        m = re.search(r"nodecode wall_s=([0-9.]+) load_s=([0-9.]+) algorithm_s=([0-9.]+)", err)
+        if p.returncode != 0 or not m:
+            raise RuntimeError(f"decode-free reference failed rc={p.returncode}: {err[-300:]}")
+        algo.append(float(m.group(3)))
+    return max(algo), sum(n for _, n in jobs)
+
+
 def cpu_baseline(pairs_total, nproc, seed0=20260101):
+    """(cpu_baseline, cpu_baseline_decode_free): the reference executable from BAM files, and the reference's algorithm alone
+    (records already in memory: the comparator of a job that starts from decoded records), on the same samples."""
+    from oracle import oracle
     tmp = tempfile.mkdtemp(prefix="bdk_cpu_", dir=os.environ.get("TMPDIR", "/tmp"))
     try:
         jobs = _write_sample_bams(tmp, nproc, max(1000, pairs_total // nproc), seed0)
         dt, pairs, kind = _run_reference_once(jobs)
-        return {"value": pairs / dt, "unit": UNIT, "cores": nproc if kind == "reference" else 1, "kind": kind,
+        base = {"value": pairs / dt, "unit": UNIT, "cores": nproc if kind == "reference" else 1, "kind": kind,
                 "sample": f"{nproc} x {pairs // nproc} read pairs of the same workload as BAM, one single-threaded process each, {dt:.1f} s wall"}
+        free = None
+        if os.access(oracle.REF_NODECODE, os.X_OK):
+            try:
+                adt, apairs = _run_reference_decode_free(jobs)
+                free = {"value": apairs / adt, "unit": UNIT, "cores": nproc, "kind": "reference",
+                        "sample": f"the same {nproc} samples, BAM decoded into memory before the clock starts (the reference's readers replaced by "
+                                  f"in-memory ones, both of its passes timed), slowest process {adt:.2f} s"}
+            except Exception as ex:
+                free = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        return base, free
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def file_e2e_sample(pairs, level=6):
+    """From a BAM FILE to the SV table with the drop-in executable (breakdancer_b200/bin/breakdancer_max: decode on all host
+    cores, one GPU), wall clock of the whole process, on one BAM of the bench workload. Stage times from --stats-json."""
+    from breakdancer_b200 import api, synth
+    cli = os.path.join(ROOT, "breakdancer_b200", "bin", "breakdancer_max")
+    tmp = tempfile.mkdtemp(prefix="bdk_file_", dir=os.environ.get("TMPDIR", "/tmp"))
+    try:
+        w = synth.config2(pairs, seed=20260106, chrom_len=max(1_000_000, 5 * pairs))
+        size = 0
+        for bam, cols in synth.split_by_bam(w).items():
+            api.write_bam(os.path.join(tmp, bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=level)
+            size += os.path.getsize(os.path.join(tmp, bam))
+        open(os.path.join(tmp, "cfg"), "w").write(w.config_text())
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rc = subprocess.run([cli, "--stats-json", "stats.json", "cfg"], cwd=tmp, stdout=open(os.path.join(tmp, "out.tsv"), "w"), stderr=subprocess.PIPE, text=True)
+            dt = time.perf_counter() - t0
+            if rc.returncode != 0:
+                raise RuntimeError(f"breakdancer_max failed: {rc.stderr[-300:]}")
+            if best is None or dt < best[0]:
+                best = (dt, json.load(open(os.path.join(tmp, "stats.json"))))
+        dt, st = best
+        return {"value": (w.n // 2) / dt, "unit": UNIT, "wall_s": round(dt, 3), "cores": os.cpu_count() or 1, "bam_bytes": size,
+                "stages_s": {k: round(v, 4) for k, v in st.items() if k.endswith("_s") and k != "read_pairs_per_s"}, "sv_calls": st.get("sv_calls"),
+                "sample": f"one BAM of {w.n // 2} read pairs of the same workload (deflate level {level}), whole process (start, CUDA context, decode, GPU, "
+                          "output), best of 3"}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -478,9 +541,22 @@ def ours(args):
             line["one_job_all_gpus"] = genome
         if world == 1 and not args.no_cpu:
             try:
-                line["cpu_baseline"] = cpu_baseline(args.cpu_pairs, max(1, min(os.cpu_count() or 1, 32)))
+                line["cpu_baseline"], free = cpu_baseline(args.cpu_pairs, max(1, min(os.cpu_count() or 1, 32)))
+                if free:
+                    line["cpu_baseline_decode_free"] = free
             except Exception as ex:   # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+            try:
+                line["file_e2e"] = file_e2e_sample(args.file_pairs)
+            except Exception as ex:   # reported, never required
+                line["file_e2e"] = {"value": None, "unit": UNIT, "sample": str(ex)[:200]}
+            # what the headline ratios compare (the driver computes e2e / reference arm itself)
+            cb, cf, fe = line.get("cpu_baseline", {}), line.get("cpu_baseline_decode_free", {}), line.get("file_e2e", {})
+            line["comparisons"] = {
+                "records_in_host_memory_to_sv": {"ours": line["e2e"]["value"], "reference_decode_free": cf.get("value"),
+                                                 "ratio": (line["e2e"]["value"] / cf["value"]) if cf.get("value") else None},
+                "bam_file_to_sv": {"ours": fe.get("value"), "reference": cb.get("value"),
+                                   "ratio": (fe["value"] / cb["value"]) if fe.get("value") and cb.get("value") else None}}
             try:
                 line["bam_decode"] = bam_decode_sample(args.bam_pairs)
             except Exception as ex:   # reported, never required
@@ -706,6 +782,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=400_000, help="read pairs per process and step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--bam-pairs", type=int, default=2_000_000, help="size of the BAM sample of the bam_decode leg")
+    ap.add_argument("--file-pairs", type=int, default=6_000_000, help="read pairs of the BAM the file_e2e leg runs the drop-in executable on")
     ap.add_argument("--no-genome", action="store_true", help="N > 1: skip the one-job-over-all-GPUs (NCCL exchange) measurements")
     ap.add_argument("--no-configs45", action="store_true", help="N > 1: skip the BASELINE configs[3] (LPT shards) and configs[4] (-t, 1 B pairs) blocks")
     ap.add_argument("--genome-pairs", type=int, default=617_700_000, help="read pairs of the configs[3] whole genome")

@@ -8,7 +8,7 @@
 namespace bdh {
 
 struct CliOptions {
-    std::string chr, cache_file, restore_file, bam_config_path, prefix_fastq, dump_BED;
+    std::string chr, cache_file, restore_file, bam_config_path, prefix_fastq, dump_BED, stats_json;
     int min_len = 7, cut_sd = 3, max_sd = 1000000000, min_map_qual = 35, min_read_pair = 2, seq_coverage_lim = 1000,
         buffer_size = 100, score_threshold = 30;
     bool transchr_rearrange = false, fisher = false, Illumina_long_insert = false, CN_lib = false, print_AF = false;

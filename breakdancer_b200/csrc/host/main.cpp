@@ -5,6 +5,7 @@
 #include "host.hpp"
 #include "cli.hpp"
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -13,6 +14,7 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 using namespace bdh;
 
@@ -20,12 +22,18 @@ static void check(bdk_ctx* ctx, int rc, const char* what) {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + bdk_last_error(ctx));
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int main(int argc, char** argv) {
     bdk_ctx* ctx = nullptr;
     bdh_stream* stream = nullptr;
     int rv = 0;
+    const double t_start = now_s();
+    std::thread cuda_warmup;
     try {
         CliOptions o = parse_cli(argc, argv);
+        // the CUDA context takes a few hundred milliseconds to come up: let that happen while the BAMs are being inflated
+        cuda_warmup = std::thread([] { bdk_host_free(bdk_host_alloc(64)); });
         if (!o.restore_file.empty() || !o.cache_file.empty())
             throw std::runtime_error("-C/-R (boost XML summary cache) are not supported by this build");
         bdh_config cfgh;
@@ -42,6 +50,8 @@ int main(int argc, char** argv) {
         char err[512] = {0};
         stream = bdh_stream_open(&cfgh, nullptr, 0, o.chr.c_str(), 0, 1, want_reads ? 1 : 0, err, sizeof err);
         if (!stream) throw std::runtime_error(err);
+        const double t_decoded = now_s();
+        if (cuda_warmup.joinable()) cuda_warmup.join();
 
         bdk_params p;
         memset(&p, 0, sizeof p);
@@ -59,6 +69,7 @@ int main(int argc, char** argv) {
 
         bdk_soa cols;
         bdh_stream_cols(stream, &cols);
+        const double t_created = now_s();
         check(ctx, bdk_push(ctx, &cols, bdh_stream_n(stream)), "bdk_push");
         bdk_summary_t S;
         check(ctx, bdk_summary(ctx, &S), "bdk_summary");
@@ -74,8 +85,10 @@ int main(int argc, char** argv) {
         std::cout << std::endl;
         format_header(std::cout, p, S, cfg.lib_names, cfg.bam_files, o.print_AF);
 
+        const double t_pushed = now_s();
         bdk_result res;
         check(ctx, bdk_finish(ctx, &res), "bdk_finish");
+        const double t_finished = now_s();
         std::vector<std::string> tid_names;
         for (int t = 0; t < bdh_stream_ntid(stream); ++t) tid_names.push_back(bdh_stream_tid_name(stream, t));
         format_rows(std::cout, p, res, cfg.lib_names, cfg.bam_files, tid_names, o.print_AF);
@@ -85,10 +98,26 @@ int main(int argc, char** argv) {
             if (!o.dump_BED.empty()) bed.reset(new std::ofstream(o.dump_BED.c_str()));
             write_support_reads(ctx, stream, p, res, cfg.lib_names, tid_names, bed.get(), o.prefix_fastq);
         }
+        if (!o.stats_json.empty()) {        // SURVEY section 5, metrics row
+            std::cout.flush();
+            const double t_end = now_s();
+            const uint64_t n = bdh_stream_n(stream);
+            double stage[3] = {0, 0, 0};
+            bdh_stream_timings(stream, &stage[0], &stage[1], &stage[2]);
+            std::ofstream js(o.stats_json.c_str());
+            js << "{\"records\": " << n << ", \"read_pairs\": " << n / 2 << ", \"sv_calls\": " << res.n_sv
+               << ", \"anomalous_reads\": " << S.n_anomalous << ", \"total_s\": " << t_end - t_start
+               << ", \"decode_s\": " << t_decoded - t_start << ", \"decode_inflate_s\": " << stage[0] << ", \"decode_extract_s\": " << stage[1]
+               << ", \"decode_merge_s\": " << stage[2] << ", \"context_s\": " << t_created - t_decoded << ", \"push_s\": " << t_pushed - t_created
+               << ", \"finish_s\": " << t_finished - t_pushed << ", \"output_s\": " << t_end - t_finished
+               << ", \"h2d_bytes\": " << bdk_h2d_bytes(ctx) << ", \"d2h_bytes\": " << bdk_d2h_bytes(ctx)
+               << ", \"read_pairs_per_s\": " << (double)(n / 2) / (t_end - t_start) << "}\n";
+        }
     } catch (std::exception const& e) {
         std::cerr << "ERROR: " << e.what() << "\n";
         rv = 1;
     }
+    if (cuda_warmup.joinable()) cuda_warmup.join();
     if (ctx) bdk_destroy(ctx);
     if (stream) bdh_stream_free(stream);
     return rv;

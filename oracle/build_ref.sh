@@ -16,6 +16,7 @@
 #   samtools          vendored samtools 0.1.19 CLI (view/index for fixtures)
 #   score_ref         harness: boost-1.54 Poisson complement-cdf log-probabilities (see score_ref.cpp)
 #   breakdancer-max-trace   the reference with ComputeProbScore's Poisson calls traced to stderr (ref_trace.cpp)
+#   breakdancer-max-nodecode   the reference's algorithm on records decoded into memory beforehand (ref_nodecode.cpp)
 # Intermediates live in oracle/_ref/build (gpurun-ignored).
 set -euo pipefail
 REF=${REF:-/root/reference}
@@ -27,7 +28,7 @@ if [ ! -d "$REF/src" ]; then
   echo "build_ref.sh: $REF not present; keeping prebuilt oracle/_ref as is" >&2
   exit 0
 fi
-if [ -x "$OUT/breakdancer-max" ] && [ -x "$OUT/samtools" ] && [ -x "$OUT/score_ref" ] && [ -x "$OUT/breakdancer-max-trace" ] && [ "${FORCE:-0}" != 1 ]; then
+if [ -x "$OUT/breakdancer-max" ] && [ -x "$OUT/samtools" ] && [ -x "$OUT/score_ref" ] && [ -x "$OUT/breakdancer-max-trace" ] && [ -x "$OUT/breakdancer-max-nodecode" ] && [ "${FORCE:-0}" != 1 ]; then
   echo "build_ref.sh: oracle/_ref already built (FORCE=1 to rebuild)"
   exit 0
 fi
@@ -66,9 +67,12 @@ breakdancer/BedWriter.cpp breakdancer/BreakDancer.cpp breakdancer/ReadRegionData
 for t in $TUS; do echo "$t"; done | xargs -P "$JOBS" -I{} sh -c \
   "o=robj/\$(echo {} | tr / _).o; g++ $CXXF -c $REF/src/lib/{} -o \$o"
 g++ $CXXF -c "$REF/src/exe/breakdancer-max/BreakDancerMax.cpp" -o robj/main.o
-g++ -o "$OUT/breakdancer-max" robj/main.o $(ls robj/*.o | grep -v main.o) libboost_bd.a samtools-0.1.19/libbam.a -lz -lm -lpthread -lrt
+g++ -o "$OUT/breakdancer-max" robj/main.o $(ls robj/*.o | grep -v -E 'main.o|trace_|nodecode_') libboost_bd.a samtools-0.1.19/libbam.a -lz -lm -lpthread -lrt
 # 5. harnesses (our own sources, compiled against the reference's vendored headers)
 g++ -std=c++11 -O2 -w -Iboost-bd "$HERE/score_ref.cpp" -o "$OUT/score_ref"
 g++ $CXXF -c "$HERE/ref_trace.cpp" -o robj/trace_BreakDancer.o
 g++ -o "$OUT/breakdancer-max-trace" robj/main.o robj/trace_BreakDancer.o $(ls robj/*.o | grep -v -E 'main.o|breakdancer_BreakDancer.cpp.o|trace_') libboost_bd.a samtools-0.1.19/libbam.a -lz -lm -lpthread -lrt
+g++ $CXXF -Dmain=reference_main -c "$REF/src/exe/breakdancer-max/BreakDancerMax.cpp" -o robj/nodecode_main.o
+g++ $CXXF -c "$HERE/ref_nodecode.cpp" -o robj/nodecode_io.o
+g++ -o "$OUT/breakdancer-max-nodecode" robj/nodecode_main.o robj/nodecode_io.o $(ls robj/*.o | grep -v -E 'main.o|io_BamIo.cpp.o|trace_|nodecode_') libboost_bd.a samtools-0.1.19/libbam.a -lz -lm -lpthread -lrt
 echo "build_ref.sh: built $(ls "$OUT" | grep -v build | tr '\n' ' ')"

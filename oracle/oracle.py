@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libbdoracle.so")
 REF_DIR = os.path.join(_HERE, "_ref")
 REF_BIN = os.path.join(REF_DIR, "breakdancer-max")
+REF_NODECODE = os.path.join(REF_DIR, "breakdancer-max-nodecode")   # the reference on records decoded into memory beforehand (ref_nodecode.cpp)
 REF_SAMTOOLS = os.path.join(REF_DIR, "samtools")
 REF_SCORE = os.path.join(REF_DIR, "score_ref")
 
