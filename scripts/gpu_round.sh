@@ -21,3 +21,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -o gpurun_out/${K}_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1
 fi
 ls -la gpurun_out | tail -12
+if [ -n "$K1C3" ]; then   # full capture of the multi-key classify kernel on configs[2] data
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k1_classify -c 1 -o gpurun_out/k1_config3_$TAG -f python bench.py --config 3 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_k1c3_$TAG.log 2>&1
+ls -la gpurun_out | grep k1_config3
+fi
