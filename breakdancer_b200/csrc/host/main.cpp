@@ -15,6 +15,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <thread>
+#include <unistd.h>
 
 using namespace bdh;
 
@@ -44,11 +45,14 @@ int main(int argc, char** argv) {
         const Config& cfg = cfgh.cfg;
         if (cfg.bam_files.empty()) {
             std::cout << "Error: no bams files in config file!\n";
+            cuda_warmup.join();
             return 1;
         }
         const bool want_reads = !o.prefix_fastq.empty() || !o.dump_BED.empty();
         char err[512] = {0};
-        stream = bdh_stream_open(&cfgh, nullptr, 0, o.chr.c_str(), 0, 1, want_reads ? 1 : 0, err, sizeof err);
+        // pageable columns: pinning hundreds of megabytes costs more than the staged copy of a one-shot run saves, and the decoder
+        // would have to wait for the CUDA context
+        stream = bdh_stream_open(&cfgh, nullptr, 0, o.chr.c_str(), 0, getenv("BDK_CLI_PINNED") ? 1 : 0, want_reads ? 1 : 0, err, sizeof err);
         if (!stream) throw std::runtime_error(err);
         const double t_decoded = now_s();
         if (cuda_warmup.joinable()) cuda_warmup.join();
@@ -118,6 +122,11 @@ int main(int argc, char** argv) {
         rv = 1;
     }
     if (cuda_warmup.joinable()) cuda_warmup.join();
+    if (!getenv("BDK_CLEAN_EXIT")) {      // everything is written: leave without unmapping buffers and tearing the CUDA context down piece by piece
+        std::cout.flush(); std::cerr.flush();
+        fflush(nullptr);
+        _exit(rv);
+    }
     if (ctx) bdk_destroy(ctx);
     if (stream) bdh_stream_free(stream);
     return rv;
