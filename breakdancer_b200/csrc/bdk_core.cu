@@ -196,7 +196,7 @@ int launch_k1(bdk_ctx* c, const bdk_soa& cols, uint64_t n, uint32_t base_index, 
     a.rgtab = c->d_rgtab.as<RgDev>();
     a.nrg = c->P.nrg; a.nlib = c->P.nlib; a.nbam = c->P.nbam; a.nkey = c->nkey;
     a.pad_rg = c->pad_rg;
-    a.ncnt = c->ncnt; a.cnt_rg = c->d_cnt_rg.as<int32_t>();
+    a.ncnt = c->ncnt; a.cnt_rg = c->d_cnt_rg.as<int32_t>(); a.cn_lib = c->P.cn_lib;
     a.co.max_sd = c->P.max_sd; a.co.transchr = c->P.transchr_rearrange; a.co.long_insert = c->P.illumina_long_insert;
     a.seg_ar = c->d_seg_ar.as<bdk_aread>(); a.seg_P = c->d_seg_P.as<uint32_t>(); a.seg_cap = c->seg_cap;
     a.seg_cnt = c->d_seg_cnt.as<uint32_t>();

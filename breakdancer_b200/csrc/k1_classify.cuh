@@ -76,6 +76,7 @@ struct K1Args {
     int32_t nrg, nlib, nbam, nkey;
     int32_t pad_rg;            // a read group with a library, used by padding records
     int32_t ncnt;              // private counter columns in use (0: count with warp votes + global atomics)
+    int32_t cn_lib;            // -a: keys are libraries (else the source bams)
     const int32_t* cnt_rg;     // [ncnt] read group that receives the column's total
     ClassifyOpts co;
     bdk_aread* seg_ar;         // [grid][seg_cap] anomalous reads of each CTA's range, in stream order
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     const uint32_t sp = (ch >> 3) & 1u;          // CH_SPROPER
                     if (K4) {
                         k04 |= ((L.info >> RGI_KEY_SHIFT) & 1u) << j; k14 |= ((L.info >> (RGI_KEY_SHIFT + 1)) & 1u) << j;
-                        bams32 |= 1u << ((L.info >> RGI_BAM_SHIFT) & 3u);
+                        if (a.cn_lib) bams32 |= 1u << ((L.info >> RGI_BAM_SHIFT) & 3u);      // without -a the key IS the bam: taken from the key planes below
                         spw += sp << (((L.info >> RGI_CNT_SHIFT) & 3u) * 8);          // at most 32 records per thread and tile: a byte per column
                     } else if (FAST || a.ncnt == 1) spcnt += sp;
                     else if (a.ncnt) atomicAdd(my_cnt + ((L.info >> RGI_CNT_SHIFT) & 31u) * K1_CTHREADS, sp);   // private column: no conflicts
@@ -426,6 +427,12 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
 #pragma unroll
                 for (int c = 0; c < 4; ++c) spc[c] += (spw >> (8 * c)) & 0xffu;
                 if (a.nbam > 1) {
+                    if (!a.cn_lib) {
+                        // records beyond the end of the push are padding with key bits of pad_rg: its bam is present anyway or the
+                        // span search skips nothing it should not (a set bit only costs a look)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if ((((k & 1) ? kb0 : ~kb0) & ((k & 2) ? kb1 : ~kb1)) != 0u) bams32 |= 1u << k;
+                    }
                     bams32 = __reduce_or_sync(FULL, bams32);
                     if (lane == 0) s_wb[tb][warp] = bams32;
                 }
