@@ -191,6 +191,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdk_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "bdk_comm_bytes": (u64, [vp]),
         "bdk_k4_sweeps": (C.c_uint32, [vp]),
+        "bdk_duplicate_names": (C.c_uint32, [vp]),
         "bdk_poisson_logsf": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(C.c_double), u64]),
         "bdk_version": (C.c_char_p, []),
         "bdk_bgzf_inflate": (C.c_int, [C.c_int, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.POINTER(i32), C.POINTER(C.c_float)]),
@@ -218,6 +219,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdh_stream_fastq": (C.c_int, [vp, u64, C.c_char_p, C.c_int]),
         "bdh_bai_reference_stats": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_char_p, C.c_int]),
         "bdh_inflate_counters": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "bdh_stream_sorted": (C.c_int, [vp]),
         "bdh_stream_timings": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bdh_write_bam": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_int,
                                     C.POINTER(C.c_char_p), C.POINTER(Soa), u64, C.c_char_p, C.c_int, C.c_int,
@@ -545,6 +547,9 @@ class Context:
 
     def k4_sweeps(self) -> int:
         return int(self._L.bdk_k4_sweeps(self._h))
+
+    def duplicate_names(self) -> int:
+        return int(self._L.bdk_duplicate_names(self._h))
 
     def poisson_logsf(self, lam: np.ndarray, k: np.ndarray) -> np.ndarray:
         lam = np.ascontiguousarray(lam, np.float64)

@@ -78,6 +78,13 @@ BREC_HD const uint8_t* aux_get(const uint8_t* s, const uint8_t* e, char t0, char
     return 0;
 }
 
+// does the integer value at v (type byte first) lie inside [v, e)?
+BREC_HD bool aux_value_fits(const uint8_t* v, const uint8_t* e) {
+    if (v >= e) return false;
+    const size_t sz = (*v == 'c' || *v == 'C') ? 1 : (*v == 's' || *v == 'S') ? 2 : (*v == 'i' || *v == 'I') ? 4 : 0;
+    return v + 1 + sz <= e;
+}
+
 BREC_HD int32_t aux2i(const uint8_t* v) {  // bam_aux2i
     switch (*v) {
         case 'c': return (int8_t)v[1];
@@ -172,8 +179,16 @@ struct RegionSel { int on, tid, beg, end; };
 
 // The reader's filter: primary records placed on a reference sequence (BamIo.cpp:11-18) and, with -o, bam_iter_read's
 // is_overlap(): rend > beg && pos < end on the target. r points at the record's core.
+// do the variable-length parts the core announces fit inside the record (block_size precedes the core)?
+BREC_HD bool record_sizes_ok(const uint8_t* r, const Core& c) {
+    const uint64_t bs = ld32(r - 4);
+    if (c.l_qseq < 0) return false;
+    return 32ull + c.l_qname + 4ull * c.n_cigar + ((uint64_t)c.l_qseq + 1) / 2 + (uint64_t)c.l_qseq <= bs;
+}
+
 BREC_HD bool keep_record(const uint8_t* r, const RegionSel& region) {
     const Core c = read_core(r);
+    if (!record_sizes_ok(r, c)) return false;          // a corrupt record that still chains: dropped, never read through
     bool ok = !(c.flag & (0x100 | 0x800)) && c.tid >= 0;
     if (ok && region.on) {
         const uint32_t rend = c.n_cigar ? calend(c, r + 32 + c.l_qname) : (uint32_t)c.pos + 1;
@@ -203,7 +218,7 @@ BREC_HD Fields record_fields(const uint8_t* r) {
     f.mapq = c.mapq;
     f.rg = 0; f.rg_len = 0;
     if (aux <= end) {
-        if (const uint8_t* am = aux_get(aux, end, 'A', 'M')) f.mapq = (uint8_t)aux2i(am);       // determine_bdqual
+        if (const uint8_t* am = aux_get(aux, end, 'A', 'M')) if (aux_value_fits(am, end)) f.mapq = (uint8_t)aux2i(am);       // determine_bdqual
         if (const uint8_t* rg = aux_get(aux, end, 'R', 'G'))
             if (*rg == 'Z' || *rg == 'H') { f.rg = rg + 1; f.rg_len = bounded_strlen(rg + 1, (size_t)(end - (rg + 1))); }
     }

@@ -116,6 +116,7 @@ struct bdk_ctx {
     DevBuf d_hdr, d_hdr_all, d_ar_g, d_P_g, d_koff;
     DevBuf d_del, d_stamp, d_k4sync, d_c1, d_ri;   // K4: table of deletion windows, sweep stamps, barrier / counters
     uint32_t k4_sweeps = 0;                   // sweeps of the last bdk_finish
+    uint32_t dup_names = 0;                   // reads beyond the second of a read name among the anomalous reads of the last bdk_finish
     int k4_grid_max = 0;                      // co-resident CTAs of the persistent sweep kernel
     bool k4_host_loop = false;                // BDK_K4_HOST_LOOP (tests): one launch per sweep instead of the persistent kernel
     uint32_t k4w_cap = K4W_CAP;               // BDK_K4W_CAP (tests): directed edges up to which a window is handled by one warp
@@ -883,8 +884,9 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     CU(cudaMemsetAsync(c->d_wund.p, 0, nwin_cap * 4, st));
     unsigned long long* ekeys = c->d_ekeys.as<unsigned long long>();
     uint32_t* ecnt = c->d_ecnt.as<uint32_t>();
-    k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), d_cnt);
-    k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
+    CU(cudaMemsetAsync(c->d_sefl.p, 0, A1, st));            // (flags of names with more than two reads; the big-window kernel reuses the bytes later)
+    k3_mate_join_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), A, c->d_table.as<uint32_t>(), tsize - 1, c->d_mate.as<int32_t>(), c->d_sefl.as<uint8_t>(), d_cnt);
+    k3_links_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_mate.as<int32_t>(), c->d_sefl.as<uint8_t>(), c->d_read_region.as<int32_t>(), A, ekeys, ecnt, esize - 1);
     k3_read_info_kernel<<<GS_GRID, GS_THREADS, 0, st>>>(c->d_ar.as<bdk_aread>(), c->d_mate.as<int32_t>(), c->d_read_region.as<int32_t>(), c->d_read_cand.as<int32_t>(),
         c->d_reg.as<RegionRec>(), c->d_cand_regs.as<int32_t>(), d_cnt, period, c->P.min_read_pair, ekeys, ecnt, esize - 1, A, c->d_ri.as<ReadInfo2>(), c->d_sv_of_read.as<int32_t>());
     // the followed edges, bucketed by flush window
@@ -1027,8 +1029,7 @@ int bdk_finish(bdk_ctx* c, bdk_result* out) {
     memcpy(c->h_cnt, hp + h_cnt, CNT_N * 4);
     memcpy(&c->h_summary, hp + h_sum, sizeof(bdk_summary_t));
     if (sweeps_on_device) c->k4_sweeps = ((const uint32_t*)(hp + h_sync))[7];
-    if (c->h_cnt[CNT_ERR] & K3_ERR_DUPNAME)
-        return fail(c, BDK_ERR_DATA, "a read-name key occurs more than twice among the anomalous reads");
+    c->dup_names = c->h_cnt[CNT_NDUP];
     const size_t ns = c->h_cnt[CNT_NEMIT];
     if (c->h_cnt[CNT_NROW] > R1 || c->h_cnt[CNT_NSE] > A1) return fail(c, BDK_ERR_STATE, "internal: more followed edges than reads");
     if (ns > cap) {            // more rows than the first copy brought: lay the host block out again and fetch everything
@@ -1153,6 +1154,7 @@ int bdk_comm_init(bdk_ctx* c, const void* unique_id, int rank, int nranks) {
 
 uint64_t bdk_comm_bytes(bdk_ctx* c) { return c ? c->comm_bytes : 0; }
 uint32_t bdk_k4_sweeps(bdk_ctx* c) { return c ? c->k4_sweeps : 0; }
+uint32_t bdk_duplicate_names(bdk_ctx* c) { return c ? c->dup_names : 0; }
 
 int bdk_poisson_logsf(bdk_ctx* c, const double* lambda, const int32_t* k, double* out, uint64_t n) {
     if (!c || !lambda || !k || !out) return BDK_ERR_ARG;

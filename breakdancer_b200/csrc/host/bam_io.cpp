@@ -132,10 +132,12 @@ void scan_members(const MappedFile& f, const std::string& path, size_t off, size
         const uint8_t* h = f.data + off;
         if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) throw std::runtime_error(path + " is not a valid bam file");
         uint32_t xlen = rd16(h + 10);
+        if (off + 12 + (size_t)xlen + 8 > f.size) throw std::runtime_error(path + " is truncated");     // extra field + deflate trailer must be in the file
         uint32_t bsize = 0; bool found = false;
         size_t x = 12;
         while (x + 4 <= 12 + xlen) {
             uint8_t si1 = h[x], si2 = h[x + 1]; uint32_t slen = rd16(h + x + 2);
+            if (x + 4 + slen > 12 + (size_t)xlen) throw std::runtime_error(path + " is not a valid bam file");   // subfield runs past the extra field
             if (si1 == 'B' && si2 == 'C' && slen == 2) { bsize = rd16(h + x + 4); found = true; }
             x += 4 + slen;
         }
@@ -502,6 +504,7 @@ struct bdh_stream {
     uint16_t *flag = 0, *rgid = 0;
     uint8_t* mapq = 0;
     uint64_t* qid = 0;
+    int sorted = 1;                   // the merged stream is ordered by (tid, pos): what the summary statistics and the region builder assume
     std::vector<uint8_t> rec_bam;     // per merged record: source bam (keep_records)
     std::vector<uint64_t> rec_off;    // per merged record: raw offset (keep_records)
     std::vector<int32_t> rg_lib, rg_bam;
@@ -810,6 +813,18 @@ static void set_err2(char* err, int cap, const char* msg) {
 
 extern "C" {
 
+static void note_sortedness(bdh_stream* s, int threads) {
+    std::atomic<bool> ok(true);
+    const int32_t* tid = s->tid; const int32_t* pos = s->pos;
+    bdh::parallel_for(s->n, 1 << 20, threads, [&](uint64_t lo, uint64_t hi) {
+        bool good = true;
+        for (uint64_t i = std::max<uint64_t>(lo, 1); i < hi; ++i)
+            good &= tid[i - 1] < tid[i] || (tid[i - 1] == tid[i] && pos[i - 1] <= pos[i]);
+        if (!good) ok = false;
+    });
+    s->sorted = ok ? 1 : 0;
+}
+
 bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, int npaths, const char* region,
                             int threads, int pinned, int keep_records, char* err, int errcap) {
     using namespace bdh;
@@ -886,6 +901,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             s->qlen = c.qlen.take(); s->flag = c.flag.take(); s->rgid = c.rgid.take(); s->mapq = c.mapq.take(); s->qid = c.qid.take();
             if (keep_records) { s->rec_bam.assign(n, 0); s->rec_off.assign(c.rec.p, c.rec.p + n); }
             s->t_merge = now_s() - t3;
+            note_sortedness(s, threads);
             return s;
         }
         s->pos = (int32_t*)s->alloc(n * 4); s->mpos = (int32_t*)s->alloc(n * 4); s->tid = (int32_t*)s->alloc(n * 4);
@@ -965,6 +981,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
                     }
                 });
                 s->t_merge = now_s() - t3;
+                note_sortedness(s, threads);
                 return s;
             }
             auto greater = [&](const Head& x, const Head& y) { return keys[x.bam][x.i] > keys[y.bam][y.i]; };
@@ -992,6 +1009,7 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
             });
         }
         s->t_merge = now_s() - t3;
+        note_sortedness(s, threads);
         return s;
     } catch (std::exception const& e) {
         set_err2(err, errcap, e.what());
@@ -1028,6 +1046,7 @@ void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone) {
     if (host_fallbacks) *host_fallbacks = bdh::g_inflate_fallbacks.load();
     if (gpu_redone) *gpu_redone = bdh::g_gpu_inflate_redone.load();
 }
+int bdh_stream_sorted(const bdh_stream* s) { return s ? s->sorted : 1; }
 void bdh_stream_timings(const bdh_stream* s, double* a, double* b, double* c) {
     if (a) *a = s->t_inflate;
     if (b) *b = s->t_extract;

@@ -54,6 +54,9 @@ int main(int argc, char** argv) {
         // would have to wait for the CUDA context
         stream = bdh_stream_open(&cfgh, nullptr, 0, o.chr.c_str(), 0, getenv("BDK_CLI_PINNED") ? 1 : 0, want_reads ? 1 : 0, err, sizeof err);
         if (!stream) throw std::runtime_error(err);
+        if (!bdh_stream_sorted(stream))
+            std::cerr << "WARNING: the input is not sorted by reference sequence and position; the covered reference length, the window and "
+                         "the regions assume a coordinate-sorted bam (samtools sort).\n";
         const double t_decoded = now_s();
         if (cuda_warmup.joinable()) cuda_warmup.join();
 
@@ -93,6 +96,9 @@ int main(int argc, char** argv) {
         bdk_result res;
         check(ctx, bdk_finish(ctx, &res), "bdk_finish");
         const double t_finished = now_s();
+        if (uint32_t nd = bdk_duplicate_names(ctx))
+            std::cerr << "WARNING: " << nd << " anomalous read(s) share their name with two or more others (bams with overlapping read names?); "
+                         "the reads of such names are left unpaired.\n";
         std::vector<std::string> tid_names;
         for (int t = 0; t < bdh_stream_ntid(stream); ++t) tid_names.push_back(bdh_stream_tid_name(stream, t));
         format_rows(std::cout, p, res, cfg.lib_names, cfg.bam_files, tid_names, o.print_AF);

@@ -14,8 +14,7 @@
 
 namespace bdk {
 
-enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NSE, CNT_NROW, CNT_ERR, CNT_NEMIT, CNT_K4_CHANGED, CNT_K4_NBIGWIN, CNT_N };
-constexpr uint32_t K3_ERR_DUPNAME = 1u;
+enum { CNT_A = 0, CNT_NCAND, CNT_NREG, CNT_NSE, CNT_NROW, CNT_ERR, CNT_NEMIT, CNT_K4_CHANGED, CNT_K4_NBIGWIN, CNT_NDUP, CNT_N };
 constexpr int GS_THREADS = 256;
 constexpr int GS_GRID = kNumSMs * 4;
 
@@ -103,9 +102,12 @@ __device__ __forceinline__ uint32_t hash64(unsigned long long x) {
 }
 
 // Open-addressing table of read indices keyed by the read-name key; the second read of a name
-// finds the first one and both learn their mate.
+// finds the first one and both learn their mate. A name with MORE than two reads among the anomalous ones (bams with
+// overlapping read names, a 64-bit key collision) is flagged on its first read (the table entry every later read of the
+// name meets); k3_links_kernel then leaves all reads of such a name without a mate: they are never paired and keep their
+// regions from being cleared, the job goes on (the reference pairs whichever two of them a process_sv call meets first).
 __global__ void __launch_bounds__(GS_THREADS) k3_mate_join_kernel(const bdk_aread* __restrict__ ar, uint32_t A, uint32_t* __restrict__ table,
-        uint32_t mask, int32_t* __restrict__ mate, uint32_t* __restrict__ d_cnt) {
+        uint32_t mask, int32_t* __restrict__ mate, uint8_t* __restrict__ dup, uint32_t* __restrict__ d_cnt) {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < A; j += gridDim.x * blockDim.x) {
         const unsigned long long q = ar[j].qid;
         uint32_t h = hash64(q) & mask;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(GS_THREADS) k3_mate_join_kernel(const bdk_area
             if (prev == 0xffffffffu) break;
             if (ar[prev].qid == q) {
                 const int32_t old = atomicExch(mate + prev, (int32_t)j);
-                if (old != -1) atomicOr(d_cnt + CNT_ERR, K3_ERR_DUPNAME);
+                if (old != -1) { dup[prev] = 1; atomicAdd(d_cnt + CNT_NDUP, 1u); }
                 mate[j] = (int32_t)prev;
                 break;
             }
@@ -127,10 +129,13 @@ __global__ void __launch_bounds__(GS_THREADS) k3_mate_join_kernel(const bdk_area
 // Links are aggregated straight into weighted edges in an open-addressing table (key -> count); the edge list is
 // never sorted -- everything downstream is order-independent until each component's edges are ranked.
 constexpr unsigned long long EDGE_EMPTY = ~0ull;
-__global__ void __launch_bounds__(GS_THREADS) k3_links_kernel(const int32_t* __restrict__ mate, const int32_t* __restrict__ read_region, uint32_t A,
+__global__ void __launch_bounds__(GS_THREADS) k3_links_kernel(int32_t* __restrict__ mate, const uint8_t* __restrict__ dup, const int32_t* __restrict__ read_region, uint32_t A,
         unsigned long long* __restrict__ tkeys, uint32_t* __restrict__ tcnt, uint32_t mask) {
     for (uint32_t y = blockIdx.x * blockDim.x + threadIdx.x; y < A; y += gridDim.x * blockDim.x) {
-        const int32_t x = mate[y];
+        int32_t x = mate[y];
+        // every read of a name with more than two reads points at the name's first read (or is it): all lose their mate. Only
+        // this thread reads or writes mate[y] in this kernel.
+        if (x >= 0 && (dup[y] || dup[x])) { mate[y] = -1; x = -1; }
         if (x < 0 || (uint32_t)x >= y) continue;
         const int32_t rx = read_region[x], ry = read_region[y];
         if (rx < 0 || ry < 0) continue;

@@ -73,7 +73,9 @@ def plan_from_index(bam_paths: Sequence[str], nranks: int):
         if st is None:
             return None
         rec, byt = st
-        w = np.where(rec >= 0, rec, byt // 64)            # ~64 compressed bytes per record when only spans are known
+        # ~64 compressed bytes per record when only spans are known; a sequence that has chunks at all weighs at least 1, so that
+        # lpt_pack (which skips weight 0 = no records) never drops a small contig whose chunks lie inside one BGZF member
+        w = np.where(rec >= 0, rec, np.where(byt > 0, np.maximum(1, byt // 64), 0))
         total = w.copy() if total is None else total[:min(len(total), len(w))] + w[:min(len(total), len(w))]
     return total, lpt_pack(total.tolist(), nranks)
 

@@ -14,7 +14,7 @@
  * bdk_status; bdk_last_error() gives the message.  One context per GPU, calls on one context
  * are serialised by the caller.  Inputs must be sorted by (tid, pos) the way the reference's
  * BamMerger (src/lib/io/BamMerger.cpp:40-61) delivers them, contain only primary records with
- * tid >= 0 (src/lib/io/BamIo.cpp:11-18), and a read name key (qid) may occur at most twice.
+ * tid >= 0 (src/lib/io/BamIo.cpp:11-18); a read name key (qid) is expected at most twice (see bdk_duplicate_names).
  */
 #ifndef BDK_H
 #define BDK_H
@@ -246,6 +246,11 @@ uint64_t bdk_kernel_launches(bdk_ctx* ctx);
 /* Sweeps over the connected components the last bdk_finish needed until the connection walk was stable
  * (csrc/bdk_logic.h, K4Static: 1 = no component depends on another one). */
 uint32_t bdk_k4_sweeps(bdk_ctx* ctx);
+/* Reads beyond the second one of a read-name key among the anomalous reads of the last bdk_finish (bams with overlapping read
+ * names, a key collision). The reference keeps a list per name (ReadRegionData.cpp:99-114) and pairs whichever two a call meets
+ * first; here every read of such a name stays unpaired (never consumed, its region is never cleared) and the job goes on. 0 on
+ * well-formed input. */
+uint32_t bdk_duplicate_names(bdk_ctx* ctx);
 /* Bytes the last bdk_push copied host -> device with the copy engine. */
 uint64_t bdk_h2d_bytes(bdk_ctx* ctx);
 /* Bytes the last bdk_finish copied device -> host (ordered SV table + summary). */

@@ -59,6 +59,10 @@ const char* bdh_stream_tid_name(const bdh_stream* s, int tid);
  * (Alignment::to_fastq, src/lib/io/Alignment.cpp:66-84). Returns bytes written or -1. */
 const char* bdh_stream_qname(const bdh_stream* s, uint64_t i);
 int bdh_stream_fastq(const bdh_stream* s, uint64_t i, char* buf, int cap);
+/* 1 if the merged stream is ordered by (reference sequence, position), as BamMerger delivers sorted bams (BamMerger.cpp:40-61);
+ * 0: an input bam is not coordinate-sorted -- the covered reference length, the window and the regions are then not what a
+ * sorted file would give (the reference does not check either). */
+int bdh_stream_sorted(const bdh_stream* s);
 /* seconds spent in (inflate, parse+extract, merge) by the last open */
 void bdh_stream_timings(const bdh_stream* s, double* inflate_s, double* extract_s, double* merge_s);
 /* What `<bam>.bai` (or `<name>.bai`) says about every reference sequence, without touching the bam: records[t] = mapped + unmapped

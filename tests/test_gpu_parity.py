@@ -187,6 +187,37 @@ def test_gpu_packed_rejects_a_run_over_two_chromosomes():
         api.PackedRun(api.make_soa(cols), len(cols["pos"]))
 
 
+def test_gpu_read_name_with_three_reads_is_left_unpaired():
+    """A read name that occurs three times among the anomalous reads (bams with overlapping names, a key collision) no longer
+    aborts the job: its reads stay unpaired. Expected result = the oracle on the same records with those reads renamed apart."""
+    w = synth.generate(util.GENOME3, util.LIBS4, 60000, seed=15, anomaly_frac=0.05, somatic_frac=0.3)
+    b, cols, *_ = util.workload_bundle(w, api.Options())
+    ro = oracle.run(b, cols)
+    q = ro.areads["qid"]
+    u, cnt = np.unique(q, return_counts=True)
+    pairs = u[cnt == 2]
+    rec = ro.areads["record"]
+    cols3 = {k: v.copy() for k, v in cols.items()}
+    want = {k: v.copy() for k, v in cols.items()}
+    fresh = np.uint64(1) << np.uint64(63)
+    for t in range(5):                                  # five names get a third read (the later read of another anomalous pair)
+        name, other = pairs[10 + 2 * t], pairs[11 + 2 * t]
+        z = rec[q == other][1]
+        cols3["qid"][z] = name
+        for i, r in enumerate(list(rec[q == name]) + [z]):
+            want["qid"][r] = fresh + np.uint64(10 * t + i)
+    ctx = api.Context(b, 0)
+    ctx.push(cols3)
+    summary, table = ctx.summary(), ctx.finish()
+    assert ctx.duplicate_names() == 5
+    rw = oracle.run(b, want)
+    ar, rr = ctx.areads()
+    assert np.array_equal(ar["record"], rw.areads["record"]) and np.array_equal(rr, rw.aread_region)
+    util.assert_tables_equal(rw.table, table, "three reads of one name")
+    assert np.array_equal(ctx.support(), rw.sv_of_read)
+    ctx.close()
+
+
 def test_gpu_more_rows_than_the_first_result_copy(monkeypatch):
     """More SV rows than the first device-to-host copy was sized for (forced: 16 rows): the rest comes with a second copy."""
     monkeypatch.setenv("BDK_ROWS_GUESS", "16")
