@@ -20,7 +20,7 @@ ORA   := oracle/_build/libbdoracle.so
 
 HOST_SRCS := $(SRC)/host/config.cpp $(SRC)/host/bam_io.cpp $(SRC)/host/format.cpp $(SRC)/host/options.cpp $(SRC)/host/support.cpp
 HOST_OBJS := $(patsubst $(SRC)/host/%.cpp,$(B)/host_%.o,$(HOST_SRCS))
-CU_HDRS   := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/bdk.h
+CU_HDRS   := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.inl) include/bdk.h
 
 all: $(LIB) $(CLI) $(B2C) $(ORA)
 

@@ -114,6 +114,25 @@ class Packed(C.Structure):
                 ("x_flag", C.c_void_p), ("x_rgid", C.c_void_p)]
 
 
+class BamSource(C.Structure):
+    """bdk_bam_source (include/bdk.h): one BAM file for the device-resident decode."""
+    _fields_ = [("file", C.c_void_p), ("file_bytes", C.c_uint64), ("members", C.c_void_p), ("n_members", C.c_uint64),
+                ("first_record", C.c_uint64), ("end_offset", C.c_uint64), ("n_ref", C.c_int32),
+                ("region_on", C.c_int32), ("region_tid", C.c_int32), ("region_beg", C.c_int32), ("region_end", C.c_int32),
+                ("n_rg", C.c_uint32), ("rg_hash", C.c_void_p), ("rg_id", C.c_void_p), ("rg_other", C.c_uint16), ("reserved", C.c_uint16),
+                ("window_bytes", C.c_uint64)]
+
+
+class BamStats(C.Structure):
+    """bdk_bam_stats (include/bdk.h)."""
+    _fields_ = [("records", C.c_uint64), ("kept", C.c_uint64), ("h2d_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
+                ("windows", C.c_uint32), ("guess_misses", C.c_uint32), ("sorted", C.c_int32),
+                ("inflate_ms", C.c_float), ("chain_ms", C.c_float), ("extract_ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class PackedRun:
     """A packed run (bdk_pack) and the buffers behind it; keeps the source columns alive (pos / qlen / qid are used in place)."""
 
@@ -194,6 +213,20 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdk_duplicate_names": (C.c_uint32, [vp]),
         "bdk_poisson_logsf": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(C.c_double), u64]),
         "bdk_version": (C.c_char_p, []),
+        "bdk_push_bam": (C.c_int, [vp, C.POINTER(BamSource), C.POINTER(BamStats)]),
+        "bdk_hash_bytes": (u64, [C.c_void_p, u64]),
+        "bdh_bamdev_open": (vp, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+        "bdh_bamdev_free": (None, [vp]),
+        "bdh_bamdev_nrg": (C.c_int, [vp]),
+        "bdh_bamdev_rg_lib": (C.POINTER(i32), [vp]),
+        "bdh_bamdev_rg_bam": (C.POINTER(i32), [vp]),
+        "bdh_bamdev_ntid": (C.c_int, [vp]),
+        "bdh_bamdev_tid_name": (C.c_char_p, [vp, C.c_int]),
+        "bdh_bamdev_members": (u64, [vp]),
+        "bdh_bamdev_file_bytes": (u64, [vp]),
+        "bdh_bamdev_push": (C.c_int, [vp, vp, C.POINTER(BamStats)]),
+        "bdh_bamdev_decode": (C.c_int, [vp, vp, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
+        "bdk_decode_bam": (C.c_int, [vp, C.POINTER(BamSource), C.POINTER(Soa), u64, C.POINTER(BamStats)]),
         "bdk_bgzf_inflate": (C.c_int, [C.c_int, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.POINTER(i32), C.POINTER(C.c_float)]),
         "bdh_config_parse": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
         "bdh_config_load": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
@@ -357,6 +390,41 @@ class BamStream:
         self.close()
 
 
+class BamDevice:
+    """One BAM file opened for the device-resident decode (bdh_bamdev_*, include/bdk_host.h): the host maps the file, lists
+    its BGZF members and parses the header; Context.push_bam() then inflates, parses and classifies it on the GPU."""
+
+    def __init__(self, cfg: BamConfig, path: str = "", region: str = ""):
+        L = load_library()
+        err = C.create_string_buffer(512)
+        h = L.bdh_bamdev_open(cfg._h, path.encode(), region.encode(), err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode())
+        self._h, self._L, self.cfg = h, L, cfg
+        nrg = L.bdh_bamdev_nrg(h)
+        self.rg_lib = np.ctypeslib.as_array(L.bdh_bamdev_rg_lib(h), (nrg,)).copy()
+        self.rg_bam = np.ctypeslib.as_array(L.bdh_bamdev_rg_bam(h), (nrg,)).copy()
+        self.tid_names = [L.bdh_bamdev_tid_name(h, i).decode() for i in range(L.bdh_bamdev_ntid(h))]
+        self.n_members = int(L.bdh_bamdev_members(h))
+        self.file_bytes = int(L.bdh_bamdev_file_bytes(h))
+
+    def bundle(self, opts: "Options") -> "ParamBundle":
+        return ParamBundle(opts, self.cfg.libs, self.cfg.nbam, self.rg_lib, self.rg_bam, self.cfg.window, max(1, len(self.tid_names)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bdh_bamdev_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def hash_bytes(b: bytes) -> int:
+    """The decoders' 64-bit key of a byte string (read names, read-group strings)."""
+    return int(load_library().bdk_hash_bytes(b, len(b)))
+
+
 def bam_reference_names(bam_path: str) -> List[str]:
     """Reference sequence names of a bam's header; only the BGZF members that hold the header are read."""
     import struct
@@ -473,6 +541,20 @@ class Context:
 
     def push_packed(self, run: "PackedRun"):
         self._check(self._L.bdk_push_packed(self._h, C.byref(run.view), run.n), "bdk_push_packed")
+
+    def push_bam(self, dev: "BamDevice") -> Dict[str, float]:
+        """Decode the file on this GPU and classify its records (bdk_push_bam); returns bdk_bam_stats as a dict."""
+        st = BamStats()
+        self._check(self._L.bdh_bamdev_push(dev._h, self._h, C.byref(st)), "bdk_push_bam")
+        return st.as_dict()
+
+    def decode_bam(self, dev: "BamDevice", cap: int):
+        """The file's records decoded on this GPU, as host columns (bdk_decode_bam): (columns, stats)."""
+        cols = {k: np.empty(cap, dt) for k, dt in COLUMN_DTYPES.items()}
+        soa = make_soa(cols)
+        st = BamStats()
+        self._check(self._L.bdh_bamdev_decode(dev._h, self._h, C.byref(soa), cap, C.byref(st)), "bdk_decode_bam")
+        return {k: v[:st.kept] for k, v in cols.items()}, st.as_dict()
 
     def push_soa(self, soa: Soa, n: int, device: bool):
         fn = self._L.bdk_push_device if device else self._L.bdk_push

@@ -1,63 +1,162 @@
 // bam_decode.cuh -- record boundaries and field extraction on inflated BAM bytes that stay in HBM: the stages between the GPU
-// inflate (bgzf_inflate.cuh) and K1, so that a run from BAM files moves the COMPRESSED file over PCIe and nothing else
-// (DESIGN.md section 9 item 4). The per-record logic is csrc/bam_records.h, the code the host decoder runs and its tests pin.
+// inflate (bgzf_inflate_warp.cuh) and K1, so that a run from a BAM file moves the COMPRESSED file over PCIe and nothing else.
+// Launched by bdk_push_bam (bdk_bam.inl), window of BGZF members by window. The per-record logic is csrc/bam_records.h, the
+// code the host decoder runs and its tests pin. Replaces, for a run from files, samread + the Alignment constructor
+// (src/lib/io/BamReader.hpp:64-70, src/lib/io/Alignment.cpp:12-64) and the reader filter (src/lib/io/BamIo.cpp:11-18).
 //
-// STATUS: kernels only. They compile for sm_100a and are not launched by anything yet (no B200 time was left in the round
-// they were written in); the orchestration -- header on the host, read-group table, bdk_push_device of the columns -- and the
-// GPU tests come with the first measurement. Nothing in the product path depends on this file.
-//
-// Record boundaries, as on the host (bam_io.cpp find_records): the stream is cut into segments (one per BGZF member is the
-// natural choice: the inflate kernel already knows their output offsets); every segment guesses its first record (three
-// plausible records in a row) and follows the chain to its end; the guesses are right iff every segment's chain ends exactly
-// on the next segment's guess, which one comparison per segment checks. A wrong or missing guess (records that contain
-// record-like bytes, or a record longer than a segment) sends the file to the host path -- exactness never rests on the guess.
+// Record boundaries, as on the host (bam_io.cpp find_records): a window is cut into segments, one per BGZF member (the inflate
+// kernel knows their output offsets); every segment guesses its first record (three plausible records in a row) and follows the
+// chain of block_size prefixes to its end, all segments in parallel (chain_guess_kernel). chain_resolve_kernel then checks the
+// guesses against the chain that really arrives: if every chain ends exactly on the next segment's guess the guessed chains ARE
+// the serial chain (induction from the window's first byte, which is a true record start); wherever a guess is wrong or missing
+// one thread follows the true chain through that segment. Exactness never rests on a guess. A record cut off by the end of the
+// window is carried into the next one (`tail`).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "bam_records.h"
+#include "bgzf_inflate.cuh"
+#include "scan_sort.cuh"
 
 namespace bamdev {
 
 using brec::Segment;
 using brec::NO_GUESS;
+using bgz::Member;
 
-// One thread per segment k = [cut[k], cut[k + 1]); cut[0] is the first record (after the BAM header), cut[nseg] = n.
-__global__ void __launch_bounds__(128) chain_guess_kernel(const uint8_t* __restrict__ raw, uint64_t n, const uint64_t* __restrict__ cut, uint32_t nseg,
-                                                          int32_t nref, Segment* __restrict__ seg) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nseg) seg[k] = brec::segment_guess(raw, n, cut[k], cut[k + 1], k == 0, nref);
+enum { E_MEMBER = 1, E_RECORD = 2, E_TRUNCATED = 4 };
+
+struct WinInfo {                 // what the host needs to know about a window before it can go on
+    uint64_t tail;               // offset (in the window's bytes) of the first byte that belongs to the next window
+    uint32_t nrec;               // records that start (and end) in the window
+    uint32_t err;                // E_*
+    uint32_t bad_members, first_bad_member;
+    int32_t first_bad_status;
+    uint32_t guess_misses;       // segments the true chain had to be followed through
+};
+
+// segment k of a window = [lo, hi): bytes of member k (the first one also holds the bytes carried over)
+// `carry` = bytes carried over in front of member 0's output; negative in a file's first window, whose bytes begin at the first
+// record (behind the BAM header, which may span members)
+__device__ __forceinline__ uint64_t seg_clamp(int64_t v, uint64_t n) { return v <= 0 ? 0 : (uint64_t)v < n ? (uint64_t)v : n; }
+__device__ __forceinline__ uint64_t seg_lo(const Member* m, uint32_t k, int64_t carry, uint64_t n) { return k ? seg_clamp(carry + (int64_t)m[k].out_off, n) : 0; }
+__device__ __forceinline__ uint64_t seg_hi(const Member* m, uint32_t k, uint32_t nseg, int64_t carry, uint64_t n) {
+    return k + 1 < nseg ? seg_clamp(carry + (int64_t)m[k + 1].out_off, n) : n;
 }
 
-// flags[0] != 0 afterwards: some guess was missing or wrong, or a chain hit a broken record -> the host decodes this file
-__global__ void __launch_bounds__(256) chain_check_kernel(const Segment* __restrict__ seg, uint32_t nseg, uint64_t n, uint32_t* __restrict__ flags) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nseg && !brec::segment_consistent(seg, k, nseg, n)) atomicOr(flags, 1u);
-}
-
-// One thread per segment again, now with base[k] = number of records before the segment: writes the record offsets (of the
-// cores, i.e. after block_size), the order of the stream.
-__global__ void __launch_bounds__(128) chain_write_kernel(const uint8_t* __restrict__ raw, uint64_t n, const uint64_t* __restrict__ cut, uint32_t nseg,
-                                                          const Segment* __restrict__ seg, const uint64_t* __restrict__ base, uint64_t* __restrict__ rec_off) {
+// One thread per segment.
+__global__ void __launch_bounds__(64) chain_guess_kernel(const uint8_t* __restrict__ raw, uint64_t n, const Member* __restrict__ members, uint32_t nseg,
+                                                         int64_t carry, int32_t nref, Segment* __restrict__ seg) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nseg) return;
-    const uint64_t hi = cut[k + 1];
-    uint64_t o = seg[k].guess, i = base[k];
-    while (o + 4 <= n && o < hi) {
-        rec_off[i++] = o + 4;
+    const uint64_t lo = seg_lo(members, k, carry, n), hi = seg_hi(members, k, nseg, carry, n);
+    Segment s;
+    if (lo >= hi) { s.guess = NO_GUESS; s.end = hi; s.count = 0; s.bad = 0; }
+    else s = brec::segment_guess(raw, n, lo, hi, k == 0, nref);
+    seg[k] = s;
+}
+
+// One CTA. Member verdicts, the check of the guesses (in parallel; a serial walk by one thread only where the picture is not
+// the regular one), the records before every segment (base[k], exclusive scan of the counts) and the window's WinInfo.
+__global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __restrict__ raw, uint64_t n, const Member* __restrict__ members, uint32_t nseg,
+                                                             int64_t carry, int last_window, const int32_t* __restrict__ status,
+                                                             Segment* __restrict__ seg, uint32_t* __restrict__ base, WinInfo* __restrict__ info,
+                                                             uint32_t* __restrict__ nrec_out) {
+    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_irregular, s_bad, s_first_bad, s_carry;
+    __shared__ WinInfo s_info;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) { s_irregular = 0; s_bad = 0; s_first_bad = 0xffffffffu; s_carry = 0; s_info.tail = n; s_info.err = 0; s_info.guess_misses = 0; }
+    __syncthreads();
+    for (uint32_t k = t; k < nseg; k += blockDim.x) {
+        if (status[k] != 0) { atomicAdd(&s_bad, 1u); atomicMin(&s_first_bad, k); }
+        const Segment s = seg[k];
+        bool regular = s.guess != NO_GUESS && (k == 0 ? s.guess == 0 : seg[k - 1].end == s.guess && seg[k - 1].guess != NO_GUESS);
+        if (s.bad == 1) regular = false;
+        if (s.bad == 2 && k + 1 != nseg) regular = false;
+        if (!regular) atomicOr(&s_irregular, 1u);
+    }
+    __syncthreads();
+    if (s_bad) {                                    // a member did not inflate: nothing of this window is used
+        if (t == 0) {
+            s_info.err = E_MEMBER; s_info.nrec = 0; s_info.bad_members = s_bad; s_info.first_bad_member = s_first_bad;
+            s_info.first_bad_status = status[s_first_bad];
+            *info = s_info; *nrec_out = 0;
+        }
+        return;
+    }
+    if (t == 0) {
+        if (!s_irregular) {
+            const Segment s = seg[nseg - 1];
+            s_info.tail = s.end;                    // a cut-off record's start, or (fewer than 4 stray bytes aside) the end of the data
+            if (s.bad == 2 && last_window) s_info.err |= E_TRUNCATED;
+        } else {
+            uint64_t cur = 0;
+            bool done = false;
+            uint32_t misses = 0;
+            for (uint32_t k = 0; k < nseg; ++k) {
+                const uint64_t hi = seg_hi(members, k, nseg, carry, n);
+                Segment s = seg[k];
+                if (done || cur >= hi) { s.guess = NO_GUESS; s.count = 0; s.end = hi; seg[k] = s; continue; }
+                if (s.guess == cur) {
+                    if (s.bad == 1) { s_info.err |= E_RECORD; done = true; }
+                    if (s.bad == 2) { done = true; s_info.tail = s.end; }
+                    cur = s.end;
+                    continue;
+                }
+                ++misses;
+                uint64_t o = cur;
+                uint32_t cnt = 0;
+                while (o + 4 <= n && o < hi) {
+                    const uint32_t bs = brec::ld32(raw + o);
+                    if (bs < 32) { s_info.err |= E_RECORD; done = true; break; }
+                    if (o + 4 + (uint64_t)bs > n) { done = true; s_info.tail = o; break; }
+                    ++cnt;
+                    o += 4 + (uint64_t)bs;
+                }
+                s.guess = cur; s.count = cnt; s.end = o; s.bad = 0;
+                seg[k] = s;
+                cur = o;
+            }
+            if (!done) s_info.tail = cur;
+            else if (last_window && !(s_info.err & E_RECORD)) s_info.err |= E_TRUNCATED;
+            s_info.guess_misses = misses;
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the counts
+    for (uint32_t k0 = 0; k0 < nseg; k0 += blockDim.x) {
+        const uint32_t k = k0 + t;
+        const uint32_t v = k < nseg ? seg[k].count : 0;
+        uint32_t total;
+        const uint32_t inc = bdk::ss_block_scan_any(v, s_warp, &total);
+        if (k < nseg) base[k] = s_carry + inc - v;
+        __syncthreads();
+        if (t == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (t == 0) {
+        s_info.nrec = s_carry; s_info.bad_members = 0; s_info.first_bad_member = 0; s_info.first_bad_status = 0;
+        *info = s_info; *nrec_out = s_carry;
+    }
+}
+
+// One thread per segment: the offsets of the records' cores (behind block_size), in stream order.
+__global__ void __launch_bounds__(64) chain_write_kernel(const uint8_t* __restrict__ raw, const Segment* __restrict__ seg, const uint32_t* __restrict__ base,
+                                                         uint32_t nseg, uint32_t* __restrict__ rec_off) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nseg) return;
+    const Segment s = seg[k];
+    uint64_t o = s.guess;
+    uint32_t i = base[k];
+    for (uint32_t r = 0; r < s.count; ++r) {
+        rec_off[i++] = (uint32_t)(o + 4);
         o += 4 + (uint64_t)brec::ld32(raw + o);
     }
 }
 
-// One thread per record: the reader's filter (primary, placed, -o overlap).
-__global__ void __launch_bounds__(256) keep_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rec_off, uint64_t nrec, brec::RegionSel sel,
-                                                   uint8_t* __restrict__ keep) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrec) return;
-    keep[i] = brec::keep_record(raw + rec_off[i], sel) ? 1 : 0;
-}
-
-struct RgEntry { uint64_t hash; uint32_t id; uint32_t used; };     // read-group byte string (hashed) -> rgid, filled by the host
+struct RgEntry { uint64_t hash; uint32_t id; uint32_t used; };     // read-group string (hashed) -> rgid, filled by the host
 
 struct Columns {
     int32_t *pos, *mpos, *tid, *mtid, *isize, *qlen;
@@ -66,27 +165,45 @@ struct Columns {
     uint64_t* qid;
 };
 
-// One thread per record; out_idx[i] = position of record i among the kept ones (exclusive scan of keep). Read groups the table
-// does not know are reported (unknown[0] = count, unknown[1] = a record offset to look at) and get id 0xffff: the host adds
-// them and the kernel runs again (a handful of distinct read groups per file).
-__global__ void __launch_bounds__(256) extract_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rec_off, uint64_t nrec,
-                                                      const uint8_t* __restrict__ keep, const uint64_t* __restrict__ out_idx,
-                                                      const RgEntry* __restrict__ rg_table, uint32_t rg_slots, Columns out,
-                                                      unsigned long long* __restrict__ unknown) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrec || !keep[i]) return;
-    const brec::Fields f = brec::record_fields(raw + rec_off[i]);
-    const uint64_t o = out_idx[i];
-    out.pos[o] = f.pos; out.mpos[o] = f.mpos; out.tid[o] = f.tid; out.mtid[o] = f.mtid; out.isize[o] = f.isize; out.qlen[o] = f.qlen;
-    out.flag[o] = f.flag; out.mapq[o] = f.mapq; out.qid[o] = f.qid;
-    const uint64_t h = brec::hash_bytes(f.rg, f.rg_len);
-    uint32_t id = 0xffffu;
-    for (uint32_t p = (uint32_t)(h % rg_slots), tries = 0; tries < rg_slots; ++tries, p = p + 1 == rg_slots ? 0 : p + 1) {
-        if (!rg_table[p].used) break;
-        if (rg_table[p].hash == h) { id = rg_table[p].id; break; }
+// The reader's filter as the input of a device-wide scan, and the field extraction as its output: record i of the window goes to
+// position (kept records before it) of the columns.
+struct KeepFlag {
+    const uint8_t* raw; const uint32_t* rec_off; brec::RegionSel sel;
+    __device__ uint32_t operator()(uint32_t i, uint32_t) const { return brec::keep_record(raw + rec_off[i], sel) ? 1u : 0u; }
+};
+struct ExtractOut {
+    const uint8_t* raw; const uint32_t* rec_off; const RgEntry* rg_table; uint32_t rg_slots; uint32_t rg_other; Columns out;
+    __device__ void operator()(uint32_t i, uint32_t inc, uint32_t v, uint32_t) const {
+        if (!v) return;
+        const brec::Fields f = brec::record_fields(raw + rec_off[i]);
+        const uint32_t o = inc - 1;
+        out.pos[o] = f.pos; out.mpos[o] = f.mpos; out.tid[o] = f.tid; out.mtid[o] = f.mtid; out.isize[o] = f.isize; out.qlen[o] = f.qlen;
+        out.flag[o] = f.flag; out.mapq[o] = f.mapq; out.qid[o] = f.qid;
+        const uint64_t h = brec::hash_bytes(f.rg, f.rg_len);
+        uint32_t id = rg_other;
+        for (uint32_t p = (uint32_t)(h % rg_slots), tries = 0; tries < rg_slots; ++tries, p = p + 1 == rg_slots ? 0 : p + 1) {
+            if (!rg_table[p].used) break;
+            if (rg_table[p].hash == h) { id = rg_table[p].id; break; }
+        }
+        out.rgid[o] = (uint16_t)id;
     }
-    if (id == 0xffffu) { atomicAdd(&unknown[0], 1ull); unknown[1] = rec_off[i]; }
-    out.rgid[o] = (uint16_t)id;
+};
+
+// Is the kept stream ordered by (reference sequence, position)? prev[2 * (w & 1)] holds the last record of window w - 1,
+// prev[2 * ((w + 1) & 1)] receives this window's. unsorted[0] is set and stays set.
+__global__ void __launch_bounds__(256) sorted_check_kernel(const int32_t* __restrict__ tid, const int32_t* __restrict__ pos, const uint32_t* __restrict__ n_ptr,
+                                                           int32_t* __restrict__ prev, uint32_t window, uint32_t* __restrict__ unsorted) {
+    const uint32_t n = *n_ptr;
+    const int32_t* before = prev + 2 * (window & 1);
+    int32_t* after = prev + 2 * ((window + 1) & 1);
+    bool bad = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t t0 = i ? tid[i - 1] : before[0], p0 = i ? pos[i - 1] : before[1];
+        bad |= t0 > tid[i] || (t0 == tid[i] && p0 > pos[i]);
+        if (i + 1 == n) { after[0] = tid[i]; after[1] = pos[i]; }
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { after[0] = before[0]; after[1] = before[1]; }
+    if (bad) atomicOr(unsorted, 1u);
 }
 
 }  // namespace bamdev

@@ -137,7 +137,7 @@ struct Segment {
     uint64_t guess;      // offset of the block_size field of the first record that starts in the segment (NO_GUESS: none found)
     uint64_t end;        // where the chain from `guess` leaves the segment (offset of the first record starting at or after its end)
     uint32_t count;      // records that start in the segment
-    uint32_t bad;        // the chain ran into a record that cannot be (block_size < 32 or past the end of the data)
+    uint32_t bad;        // the chain ran into a record that cannot be: 1 = block_size < 32, 2 = it reaches past the end of the data
 };
 
 // Segment [lo, hi) of raw[0 .. n): guess its first record (the first segment starts on one: `first`), follow the chain.
@@ -157,7 +157,7 @@ BREC_HD Segment segment_guess(const uint8_t* raw, uint64_t n, uint64_t lo, uint6
     s.guess = o;
     while (o + 4 <= n && o < hi) {
         const uint32_t bs = ld32(raw + o);
-        if (bs < 32 || o + 4 + bs > n) { s.bad = 1; break; }
+        if (bs < 32 || o + 4 + bs > n) { s.bad = bs < 32 ? 1u : 2u; break; }
         ++s.count;
         o += 4 + (uint64_t)bs;
     }

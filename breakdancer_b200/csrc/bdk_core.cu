@@ -19,6 +19,7 @@
 #include "../../include/bdk.h"
 #include "bdk_finalize.h"
 #include "bgzf_inflate.cuh"
+#include "bgzf_inflate_warp.cuh"
 #include "bam_decode.cuh"
 #include "comm.cuh"
 #include "k1_classify.cuh"
@@ -46,10 +47,11 @@ struct StageTimer {
     bool pending = false;
 };
 
-enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_HOST, T_COMM1, T_COMM2, T_N };
+enum { T_H2D = 0, T_K1, T_SPAN, T_FINALIZE, T_K2, T_K3, T_K4, T_D2H, T_HOST, T_COMM1, T_COMM2, T_INFLATE, T_CHAIN, T_EXTRACT, T_N };
 const char* kTimerNames[T_N] = {"h2d_copy", "k1_classify", "k1_span", "finalize_summary", "k2_regions", "k3_links_graph", "k4_sv_score", "d2h_results",
                                 "host_order_rows",    // host wall time (output ordering), not a device timer
-                                "comm_gather_reads", "comm_gather_rows"};   // multi-GPU exchanges (NCCL over NVLink)
+                                "comm_gather_reads", "comm_gather_rows",    // multi-GPU exchanges (NCCL over NVLink)
+                                "bam_inflate", "bam_record_chain", "bam_extract"};   // bdk_push_bam: device-resident BAM decode (bdk_bam.inl)
 
 }  // namespace
 
@@ -121,9 +123,12 @@ struct bdk_ctx {
     bool k4_host_loop = false;                // BDK_K4_HOST_LOOP (tests): one launch per sweep instead of the persistent kernel
     uint32_t k4w_cap = K4W_CAP;               // BDK_K4W_CAP (tests): directed edges up to which a window is handled by one warp
     uint32_t rows_guess_min = 1024;           // BDK_ROWS_GUESS (tests): floor of the first result copy
+    void* bamdev = nullptr;                   // buffers and streams of bdk_push_bam (bdk_bam.inl), created at its first call
 };
 
 namespace {
+
+void bamdev_release(void* p);
 
 int fail(bdk_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -417,6 +422,7 @@ void bdk_destroy(bdk_ctx* c) {
     }
     for (int t = 0; t < T_N; ++t) { if (c->timers[t].e0) cudaEventDestroy(c->timers[t].e0); if (c->timers[t].e1) cudaEventDestroy(c->timers[t].e1); }
     if (c->h_pack) cudaFreeHost(c->h_pack);
+    bamdev_release(c->bamdev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -1250,3 +1256,5 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
 }
 
 }  // extern "C"
+
+#include "bdk_bam.inl"

@@ -1,0 +1,366 @@
+// bgzf_inflate_warp.cuh -- BGZF members inflated on the GPU, one WARP per member (v3; bgzf_inflate.cuh is the thread-per-member
+// decoder v2 of the opt-in host reader path). This is the decoder of the device-resident BAM decode (bam_device.cuh): inflated
+// bytes stay in HBM, so only the compressed file crosses PCIe.
+//
+// Why a warp per member: v2's ncu capture (profiles/bgzf_inflate_r03d.md) shows 6.2 of 32 lanes active per instruction and 6
+// warps per SM -- 32 members per warp diverge at every symbol, and the per-thread tables (36 KB of shared memory per warp) leave
+// nothing to hide latency with. Here ALL 32 LANES DECODE THE SAME BIT STREAM REDUNDANTLY (same registers, same branches: no
+// divergence, table look-ups and input loads are broadcasts), which costs the issue slots one decoding lane would, and
+//   * a match is copied by the whole warp (a byte per lane and round: one load + one store for matches up to 32 bytes),
+//   * the tables of a block are built by the whole warp (canonical decode of every table index, 32 indices at a time),
+//   * tables are per WARP: 6 KB, so 32 warps (4 CTAs of 8) are resident per SM and hide the look-up / load latencies.
+// Table entries carry base value and extra-bit count, so a length or distance needs no arithmetic on the symbol number.
+// Codes longer than the first-level index (10 bits literal/length, 8 bits distance) are decoded canonically (count / sorted
+// symbols, RFC 1951 section 3.2.2), rare by construction. Every access is bounds-checked: a damaged member stops with an error
+// code and never writes outside its own output range. bgzf_crc_kernel then checks every member's CRC32 against its footer.
+//
+// The member decoder is written as "phases": sections whose 32 lanes work on different data, separated by warp barriers. On
+// the host the same source runs the lanes of a phase one after the other (BGZW_PHASE), which is how tests/hostsim/
+// gpu_inflate_warp_host.cpp fuzzes the decoder against zlib under AddressSanitizer. Written from RFC 1951 / RFC 1952.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bgzf_inflate.cuh"     // bgz::Member, bgz::Bits / refill / take, bgz::Status
+
+namespace bgzw {
+
+using bgz::Bits;
+using bgz::Member;
+
+constexpr int LL_BITS = 10, D_BITS = 8, CL_BITS = 7;
+constexpr int LL_SIZE = 1 << LL_BITS, D_SIZE = 1 << D_BITS;
+constexpr int WARPS_PER_CTA = 8, CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int ERR_CRC = 7;
+
+// entry: bits 0-3 code length (0: no code of at most the index width starts with these bits), bits 4-7 extra bits,
+// bits 8-9 kind, bits 16-31 value (literal byte / base length / base distance)
+enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
+
+struct Tables {                    // one per warp, shared memory: 6080 bytes
+    uint32_t ll[LL_SIZE];
+    uint32_t d[D_SIZE];            // also the code-length code while a dynamic header is read
+    uint16_t sym_ll[288], sym_d[32];
+    uint16_t cnt_ll[16], cnt_d[16];
+    uint8_t lens[320];
+    uint32_t ok;                   // build verdict of the phase that checks the code lengths
+};
+
+#ifdef __CUDA_ARCH__
+#define BGZW_HD __device__ __forceinline__
+#define BGZW_LANE() ((int)(threadIdx.x & 31u))
+#define BGZW_PHASE_BEGIN(lane) __syncwarp(); { const int lane = BGZW_LANE();
+#define BGZW_PHASE_END() } __syncwarp();
+#define BGZW_LANE0(stmt) do { if (BGZW_LANE() == 0) { stmt; } } while (0)
+#else
+#define BGZW_HD inline
+#define BGZW_PHASE_BEGIN(lane) for (int lane = 0; lane < 32; ++lane) {
+#define BGZW_PHASE_END() }
+#define BGZW_LANE0(stmt) do { stmt; } while (0)
+#endif
+
+BGZW_HD uint32_t ll_entry(int sym, int len) {
+    if (sym < 256) return (uint32_t)len | (K_LIT << 8) | ((uint32_t)sym << 16);
+    if (sym == 256) return (uint32_t)len | (K_EOB << 8);
+    sym -= 257;
+    if (sym >= 29) return (uint32_t)len | (K_BAD << 8);
+    uint32_t base, extra;
+    if (sym < 8) { base = 3 + sym; extra = 0; }
+    else if (sym == 28) { base = 258; extra = 0; }
+    else { extra = (uint32_t)(sym >> 2) - 1; base = ((4u + (sym & 3)) << extra) + 3; }
+    return (uint32_t)len | (extra << 4) | (K_LEN << 8) | (base << 16);
+}
+BGZW_HD uint32_t d_entry(int sym, int len) {
+    if (sym >= 30) return (uint32_t)len | (K_BAD << 8);
+    uint32_t base, extra;
+    if (sym < 4) { base = 1 + sym; extra = 0; }
+    else { extra = (uint32_t)(sym >> 1) - 1; base = ((2u + (sym & 1)) << extra) + 1; }
+    return (uint32_t)len | (extra << 4) | (K_LEN << 8) | (base << 16);
+}
+
+// Canonical decode of the code that starts at bit 0 of `bits` (first bit of the code = bit 0), looking at code lengths up to
+// maxlen. Returns the symbol and its length, or -1.
+BGZW_HD int canonical(uint32_t bits, int maxlen, const uint16_t* cnt, const uint16_t* sym, int* len_out) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= maxlen; ++l) {
+        code |= (int)((bits >> (l - 1)) & 1);
+        const int c = cnt[l];
+        if (code - c < first) { *len_out = l; return sym[index + (code - first)]; }
+        index += c; first += c;
+        first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// Counts per code length and symbols sorted by (length, symbol) for the literal/length code (lanes 0-15: lane = length) and the
+// distance code (lanes 16-31) at once, then the over-subscription / completeness verdict, then the first-level tables.
+// `cl`: build only a code-length code of 19 symbols from T.lens into the distance table (entries sym << 4 | len).
+BGZW_HD bool build_tables(Tables& T, int hlit, int hdist, bool cl) {
+    BGZW_PHASE_BEGIN(lane)
+        const int l = lane & 15;
+        const bool dist = lane >= 16;
+        if (!(cl && !dist)) {
+            const uint8_t* lens = T.lens + (dist && !cl ? hlit : 0);
+            const int nsym = cl ? 19 : dist ? hdist : hlit;
+            uint16_t* cnt = dist ? T.cnt_d : T.cnt_ll;
+            int c = 0;
+            if (l) for (int s = 0; s < nsym; ++s) c += lens[s] == l;
+            cnt[l] = (uint16_t)c;
+        }
+    BGZW_PHASE_END()
+    BGZW_PHASE_BEGIN(lane)
+        const int l = lane & 15;
+        const bool dist = lane >= 16;
+        if (l && !(cl && !dist)) {
+            const uint8_t* lens = T.lens + (dist && !cl ? hlit : 0);
+            const int nsym = cl ? 19 : dist ? hdist : hlit;
+            const uint16_t* cnt = dist ? T.cnt_d : T.cnt_ll;
+            uint16_t* sym = dist ? T.sym_d : T.sym_ll;
+            int o = 0;
+            for (int k = 1; k < l; ++k) o += cnt[k];
+            if (cnt[l]) for (int s = 0; s < nsym; ++s) if (lens[s] == l) sym[o++] = (uint16_t)s;
+        }
+        if (lane == 0) {
+            bool ok = true;
+            for (int t = cl ? 1 : 0; t < 2; ++t) {
+                const uint16_t* cnt = t ? T.cnt_d : T.cnt_ll;
+                int left = 1, used = 0;
+                for (int k = 1; k < 16; ++k) { left = (left << 1) - cnt[k]; if (left < 0) { ok = false; break; } used += cnt[k]; }
+                if (left > 0 && used > 1) ok = false;      // incomplete codes only with a single code (RFC 1951 3.2.7, as zlib)
+            }
+            T.ok = ok ? 1u : 0u;
+        }
+    BGZW_PHASE_END()
+    if (!T.ok) return false;
+    BGZW_PHASE_BEGIN(lane)
+        if (cl) {
+            for (int i = lane; i < (1 << CL_BITS); i += 32) {
+                int len = 0;
+                const int s = canonical((uint32_t)i, CL_BITS, T.cnt_d, T.sym_d, &len);
+                T.d[i] = s < 0 ? 0u : ((uint32_t)s << 4 | (uint32_t)len);
+            }
+        } else {
+            for (int i = lane; i < LL_SIZE; i += 32) {
+                int len = 0;
+                const int s = canonical((uint32_t)i, LL_BITS, T.cnt_ll, T.sym_ll, &len);
+                T.ll[i] = s < 0 ? 0u : ll_entry(s, len);
+            }
+            for (int i = lane; i < D_SIZE; i += 32) {
+                int len = 0;
+                const int s = canonical((uint32_t)i, D_BITS, T.cnt_d, T.sym_d, &len);
+                T.d[i] = s < 0 ? 0u : d_entry(s, len);
+            }
+        }
+    BGZW_PHASE_END()
+    return true;
+}
+
+// Inflate one member: exactly out_len bytes from in[0 .. in_len). Called by all 32 lanes of a warp with the same arguments.
+BGZW_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, Tables& T) {
+    Bits b;
+    b.in = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0; b.ahead = 0; b.has_ahead = false;
+    uint32_t op = 0;
+    bool last = false;
+    while (!last) {
+        bgz::refill(b);
+        last = bgz::take(b, 1) != 0;
+        const uint32_t type = bgz::take(b, 2);
+        if (type == 3) return bgz::ERR_HEADER;
+        if (type == 0) {                                             // stored
+            bgz::take(b, b.cnt & 7);
+            bgz::refill(b);
+            const uint32_t len = bgz::take(b, 16);
+            bgz::refill(b);
+            const uint32_t nlen = bgz::take(b, 16);
+            if ((len ^ 0xffffu) != nlen) return bgz::ERR_HEADER;
+            const uint32_t src = b.pos - (uint32_t)(b.cnt >> 3);     // whole bytes still in the bit buffer belong to the data
+            b.buf = 0; b.cnt = 0;
+            if (src > in_len || in_len - src < len) return bgz::ERR_INPUT;
+            if (out_len - op < len) return bgz::ERR_OUTPUT;
+            BGZW_PHASE_BEGIN(lane)
+                for (uint32_t i = (uint32_t)lane; i < len; i += 32) out[op + i] = in[src + i];
+            BGZW_PHASE_END()
+            op += len; b.pos = src + len; b.has_ahead = false;
+            continue;
+        }
+        int hlit = 288, hdist = 32;
+        if (type == 1) {                                             // fixed codes
+            BGZW_PHASE_BEGIN(lane)
+                for (int i = lane; i < 320; i += 32) T.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+            BGZW_PHASE_END()
+        } else {                                                     // dynamic codes
+            bgz::refill(b);
+            hlit = (int)bgz::take(b, 5) + 257; hdist = (int)bgz::take(b, 5) + 1;
+            const int hclen = (int)bgz::take(b, 4) + 4;
+            if (hlit > 286 || hdist > 30) return bgz::ERR_HEADER;
+            BGZW_PHASE_BEGIN(lane)
+                if (lane < 19) T.lens[lane] = 0;
+            BGZW_PHASE_END()
+            for (int i = 0; i < hclen; ++i) {
+                // 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 (RFC 1951 3.2.7), five bits each
+                const uint64_t order_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+                const uint64_t order_hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+                const int which = (int)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31);
+                bgz::refill(b);
+                const uint8_t v = (uint8_t)bgz::take(b, 3);
+                BGZW_LANE0(T.lens[which] = v);
+            }
+            if (!build_tables(T, 0, 0, true)) return bgz::ERR_CODES;
+            int n = 0, prev = 0;
+            while (n < hlit + hdist) {
+                bgz::refill(b);
+                const uint32_t e = T.d[(uint32_t)b.buf & ((1u << CL_BITS) - 1)];
+                if (!e) return bgz::ERR_CODES;
+                bgz::take(b, (int)(e & 15));
+                const int s = (int)(e >> 4);
+                if (s < 16) { BGZW_LANE0(T.lens[n] = (uint8_t)s); prev = s; ++n; continue; }
+                int rep, val = 0;
+                if (s == 16) { if (n == 0) return bgz::ERR_CODES; val = prev; rep = 3 + (int)bgz::take(b, 2); }
+                else if (s == 17) rep = 3 + (int)bgz::take(b, 3);
+                else rep = 11 + (int)bgz::take(b, 7);
+                if (n + rep > hlit + hdist) return bgz::ERR_CODES;
+                BGZW_PHASE_BEGIN(lane)
+                    for (int i = lane; i < rep; i += 32) T.lens[n + i] = (uint8_t)val;
+                BGZW_PHASE_END()
+                n += rep; prev = val;
+            }
+            if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return bgz::ERR_INPUT;
+        }
+        // lens[256] is read by every lane after the barrier that build_tables starts with
+        if (!build_tables(T, hlit, hdist, false)) return bgz::ERR_CODES;
+        if (T.lens[256] == 0) return bgz::ERR_CODES;
+        // ---- the symbols of the block ----
+        for (;;) {
+            bgz::refill(b);
+            uint32_t e = T.ll[(uint32_t)b.buf & (LL_SIZE - 1)];
+            if ((e & 15) == 0) {                                     // a code longer than the table index (or none at all)
+                int len = 0;
+                const int s = canonical((uint32_t)b.buf, 15, T.cnt_ll, T.sym_ll, &len);
+                if (s < 0) return bgz::ERR_SYMBOL;
+                e = ll_entry(s, len);
+            }
+            bgz::take(b, (int)(e & 15));
+            const uint32_t kind = (e >> 8) & 3;
+            if (kind == K_LIT) {
+                if (op >= out_len) return bgz::ERR_OUTPUT;
+                BGZW_LANE0(out[op] = (uint8_t)(e >> 16));
+                ++op;
+                continue;
+            }
+            if (kind == K_EOB) break;
+            if (kind == K_BAD) return bgz::ERR_SYMBOL;
+            const uint32_t len = (e >> 16) + bgz::take(b, (int)((e >> 4) & 15));
+            bgz::refill(b);
+            uint32_t f = T.d[(uint32_t)b.buf & (D_SIZE - 1)];
+            if ((f & 15) == 0) {
+                int dl = 0;
+                const int s = canonical((uint32_t)b.buf, 15, T.cnt_d, T.sym_d, &dl);
+                if (s < 0) return bgz::ERR_DISTANCE;
+                f = d_entry(s, dl);
+            }
+            bgz::take(b, (int)(f & 15));
+            if (((f >> 8) & 3) == K_BAD) return bgz::ERR_DISTANCE;
+            const uint32_t dist = (f >> 16) + bgz::take(b, (int)((f >> 4) & 15));
+            if (dist > op) return bgz::ERR_DISTANCE;
+            if (len > out_len - op) return bgz::ERR_OUTPUT;
+            if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return bgz::ERR_INPUT;      // ran past the end of the input a while ago
+            // byte j of the match is byte (j mod dist) of the `dist` bytes before it: every lane reads bytes that were complete
+            // before this match began (the barrier that opens the phase orders them after the stores of all lanes)
+            BGZW_PHASE_BEGIN(lane)
+                const uint8_t* src = out + op - dist;
+                if (dist >= len) { for (uint32_t j = (uint32_t)lane; j < len; j += 32) out[op + j] = src[j]; }
+                else { for (uint32_t j = (uint32_t)lane; j < len; j += 32) out[op + j] = src[j % dist]; }
+            BGZW_PHASE_END()
+            op += len;
+        }
+    }
+    if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return bgz::ERR_INPUT;
+    return op == out_len ? bgz::OK : bgz::ERR_OUTPUT;
+}
+
+// ---- CRC-32 (RFC 1952 section 8; reflected polynomial 0xEDB88320) of a member's output, 32 slices combined -------------------
+// The CRC of a concatenation A|B is crc(A) * x^(8|B|) + crc(B) in GF(2)[x] modulo the polynomial (init and final complement
+// cancel), so every lane takes a slice, multiplies its CRC by x^(8 * bytes behind the slice), and the warp XORs the products.
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+BGZW_HD uint32_t crc_mulmod(uint32_t a, uint32_t b) {            // a * b mod P, bit 31 = x^0
+    uint32_t p = 0;
+    for (uint32_t m = 1u << 31; m; m >>= 1) {
+        if (a & m) p ^= b;
+        b = (b & 1) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+BGZW_HD uint32_t crc_x_pow8n(uint32_t nbytes) {                   // x^(8 * nbytes) mod P by square and multiply
+    uint32_t r = 1u << 31;                                         // x^0
+    uint32_t sq = 1u << 23;                                        // x^8
+    while (nbytes) {
+        if (nbytes & 1) r = crc_mulmod(sq, r);
+        sq = crc_mulmod(sq, sq);
+        nbytes >>= 1;
+    }
+    return r;
+}
+BGZW_HD uint32_t crc_table_entry(uint32_t k) {
+    uint32_t c = k;
+    for (int i = 0; i < 8; ++i) c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1;
+    return c;
+}
+BGZW_HD uint32_t crc_slice(const uint32_t* table, const uint8_t* p, uint32_t n) {
+    uint32_t c = 0xffffffffu;
+    for (uint32_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 255] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+// lane's share of crc32(p[0 .. n)): XOR over the 32 lanes gives the CRC
+BGZW_HD uint32_t crc_lane_part(const uint32_t* table, const uint8_t* p, uint32_t n, int lane) {
+    const uint32_t chunk = (n + 31) / 32;
+    const uint32_t lo = (uint32_t)lane * chunk < n ? (uint32_t)lane * chunk : n;
+    const uint32_t hi = lo + chunk < n ? lo + chunk : n;
+    if (hi == lo) return 0;
+    return crc_mulmod(crc_x_pow8n(n - hi), crc_slice(table, p + lo, hi - lo));
+}
+
+#ifdef __CUDACC__
+// One warp per member, members handed out by an atomic counter (counter[0], zeroed by the caller). status[m] = 0 or bgz::Status.
+__global__ void __launch_bounds__(CTA_THREADS, 4)
+bgzf_inflate_warp_kernel(const uint8_t* __restrict__ comp, const Member* __restrict__ members, uint32_t n_members, uint8_t* __restrict__ out,
+                         int32_t* __restrict__ status, uint32_t* __restrict__ counter) {
+    extern __shared__ __align__(16) uint8_t bgzw_smem[];
+    Tables& T = reinterpret_cast<Tables*>(bgzw_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t m = 0;
+        if (lane == 0) m = atomicAdd(counter, 1u);
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m >= n_members) break;
+        const Member mb = members[m];
+        int st = bgz::OK;
+        if (mb.out_len) st = inflate_member(comp + mb.in_off, mb.in_len, out + mb.out_off, mb.out_len, T);
+        if (lane == 0) status[m] = st;
+        __syncwarp();
+    }
+}
+
+// One warp per member: CRC-32 of the inflated bytes against the member's footer (the 4 bytes behind its DEFLATE stream).
+// Members whose status is already non-zero are skipped; a mismatch sets ERR_CRC.
+__global__ void __launch_bounds__(256)
+bgzf_crc_kernel(const uint8_t* __restrict__ comp, const Member* __restrict__ members, uint32_t n_members, const uint8_t* __restrict__ out,
+                int32_t* __restrict__ status) {
+    __shared__ uint32_t table[256];
+    table[threadIdx.x] = crc_table_entry(threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t m = warp; m < n_members; m += nwarps) {
+        if (status[m] != 0) continue;
+        const Member mb = members[m];
+        uint32_t part = crc_lane_part(table, out + mb.out_off, mb.out_len, lane);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, d);
+        const uint8_t* f = comp + mb.in_off + mb.in_len;
+        const uint32_t want = (uint32_t)f[0] | (uint32_t)f[1] << 8 | (uint32_t)f[2] << 16 | (uint32_t)f[3] << 24;
+        if (lane == 0 && part != want) status[m] = ERR_CRC;
+    }
+}
+#endif
+
+}  // namespace bgzw

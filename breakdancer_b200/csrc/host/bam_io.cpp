@@ -1077,6 +1077,168 @@ int bdh_stream_fastq(const bdh_stream* s, uint64_t i, char* buf, int cap) {
     return (int)out.size();
 }
 
+// ---- device-resident decode: the host's share (bdk_push_bam does the rest on the GPU) ---------------------------------------
+// Map the file, list its BGZF members (through the .bai for a region, like inflate_region_with_index), inflate and parse the
+// header members here (a few KB), and number the read groups: the config's read groups first, one more id for every other
+// string (the reference maps those to the first bam's library, BamConfig.hpp:63-72).
+struct bdh_bamdev {
+    bdh::MappedFile mf;
+    std::string path;
+    bdh::BamData hdr;
+    bdh::Region rg;
+    std::vector<bdk_bgzf_member> members;
+    uint64_t first_record = 0, end_offset = 0;
+    std::vector<uint64_t> rg_hash;
+    std::vector<uint16_t> rg_id;
+    std::vector<int32_t> rg_lib, rg_bam;
+    double t_open = 0;
+};
+
+bdh_bamdev* bdh_bamdev_open(const bdh_config* cfgh, const char* path, const char* region, char* err, int errcap) {
+    using namespace bdh;
+    bdh_bamdev* d = nullptr;
+    try {
+        const double t0 = now_s();
+        const Config& cfg = cfgh->cfg;
+        int bam_index = 0;
+        std::string file;
+        if (path && path[0]) {
+            file = path;
+            for (size_t b = 0; b < cfg.bam_files.size(); ++b) if (cfg.bam_files[b] == file) bam_index = (int)b;
+        } else {
+            if (cfg.bam_files.size() != 1) throw std::runtime_error("the device decode reads one bam file; the config lists " + std::to_string(cfg.bam_files.size()));
+            file = cfg.bam_files[0];
+        }
+        d = new bdh_bamdev;
+        d->path = file;
+        d->mf.open(file);
+        // header members, one at a time, until the header is complete
+        std::vector<Block> blocks;
+        size_t total = 0, off = 0;
+        std::vector<uint8_t> hraw;
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error(file + ": BGZF inflate failed");
+        for (;;) {
+            const size_t before = blocks.size();
+            scan_members(d->mf, file, off, off, blocks, total);
+            if (blocks.size() == before) { inflateEnd(&zs); throw std::runtime_error(file + " is not a valid bam file"); }
+            Block const& b = blocks.back();
+            hraw.resize(total);
+            if (b.out_len) {
+                inflateReset(&zs);
+                zs.next_in = (Bytef*)(d->mf.data + b.in_off); zs.avail_in = b.in_len;
+                zs.next_out = hraw.data() + b.out_off; zs.avail_out = b.out_len;
+                if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.avail_out != 0) { inflateEnd(&zs); throw std::runtime_error(file + ": BGZF inflate failed"); }
+                if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), hraw.data() + b.out_off, b.out_len) != rd32(d->mf.data + b.in_off + b.in_len)) { inflateEnd(&zs); throw std::runtime_error(file + ": BGZF inflate failed"); }
+            }
+            off = b.in_off + b.in_len + 8;
+            if (hraw.size() >= 4 && memcmp(hraw.data(), "BAM\1", 4) != 0) { inflateEnd(&zs); throw std::runtime_error(file + " is not a valid bam file"); }
+            if (BamData::header_complete(hraw.data(), hraw.size())) break;
+            if (off >= d->mf.size) { inflateEnd(&zs); throw std::runtime_error(file + " is not a valid bam file"); }
+        }
+        inflateEnd(&zs);
+        const size_t hdr_end_off = off;
+        d->hdr.path = file;
+        d->hdr.raw.resize(hraw.size());
+        if (!hraw.empty()) memcpy(d->hdr.raw.data(), hraw.data(), hraw.size());
+        d->hdr.parse_header();
+        size_t first_rec = d->hdr.first_rec, rec_end = 0;       // offsets in the concatenated output of `blocks`; rec_end 0 = to the end
+        bool none = false;
+        bool ranged = false;
+        if (region && region[0]) {
+            d->rg = parse_region(region, d->hdr.tid_names, file);
+            if (!getenv("BDK_NO_BAI")) {
+                const BaiRange br = bai_reference_range(file, d->rg.tid);
+                if (br.found) {
+                    ranged = true;
+                    if (!br.any) none = true;
+                    else {
+                        const uint64_t cb = br.beg >> 16, ub = br.beg & 0xffff, ce = br.end >> 16, ue = br.end & 0xffff;
+                        auto mismatch = [&]() { return std::runtime_error(file + ": the bam index does not match the file"); };
+                        if (br.beg > br.end || cb >= d->mf.size || ce > d->mf.size) throw mismatch();
+                        if (ue > 0 || ce > 0) scan_members(d->mf, file, std::max<size_t>(cb, hdr_end_off), ue ? (size_t)ce : (size_t)ce - 1, blocks, total);
+                        auto locate = [&](uint64_t coff, uint64_t uoff) -> size_t {
+                            auto it = std::lower_bound(blocks.begin(), blocks.end(), coff, [](Block const& b, uint64_t c) { return b.file_off < c; });
+                            if (it == blocks.end() || it->file_off != coff || uoff > it->out_len) throw mismatch();
+                            return it->out_off + uoff;
+                        };
+                        first_rec = std::max(first_rec, locate(cb, ub));
+                        rec_end = ue ? locate(ce, ue) : total;
+                        if (first_rec > rec_end) throw mismatch();
+                    }
+                }
+            }
+        }
+        if (!ranged) scan_members(d->mf, file, hdr_end_off, (size_t)-1, blocks, total);
+        if (!none) {
+            // from the member that holds the first record; members without output are left out
+            size_t i0 = 0;
+            while (i0 < blocks.size() && blocks[i0].out_off + blocks[i0].out_len <= first_rec) ++i0;
+            if (i0 < blocks.size()) {
+                const size_t shift = blocks[i0].out_off;
+                uint64_t o = 0;
+                for (size_t i = i0; i < blocks.size(); ++i) {
+                    if (!blocks[i].out_len) continue;
+                    if (blocks[i].out_off - shift != o) throw std::runtime_error(file + ": internal error in the member list");
+                    d->members.push_back(bdk_bgzf_member{(uint64_t)blocks[i].in_off, o, blocks[i].in_len, blocks[i].out_len});
+                    o += blocks[i].out_len;
+                }
+                d->first_record = first_rec - shift;
+                d->end_offset = rec_end ? rec_end - shift : 0;
+                if (rec_end && rec_end - shift == d->first_record) d->members.clear();
+            }
+        }
+        // read groups: the config's, in its map order, then "any other"
+        for (auto const& kv : cfg.readgroup_library) {
+            d->rg_hash.push_back(brec::hash_bytes((const uint8_t*)kv.first.data(), kv.first.size()));
+            d->rg_id.push_back((uint16_t)d->rg_lib.size());
+            d->rg_lib.push_back(cfg.rg_lib(kv.first));
+            d->rg_bam.push_back(bam_index);
+        }
+        if (d->rg_lib.size() >= 65535) throw std::runtime_error("more than 65535 read groups in the config");
+        {
+            auto li = cfg.lib_index.find(cfg.first_bam_library);
+            d->rg_lib.push_back(cfg.first_bam_library.empty() || li == cfg.lib_index.end() ? -1 : li->second);
+            d->rg_bam.push_back(bam_index);
+        }
+        d->t_open = now_s() - t0;
+        return d;
+    } catch (std::exception const& e) {
+        set_err2(err, errcap, e.what());
+        delete d;
+        return 0;
+    }
+}
+void bdh_bamdev_free(bdh_bamdev* d) { delete d; }
+int bdh_bamdev_nrg(const bdh_bamdev* d) { return (int)d->rg_lib.size(); }
+const int32_t* bdh_bamdev_rg_lib(const bdh_bamdev* d) { return d->rg_lib.data(); }
+const int32_t* bdh_bamdev_rg_bam(const bdh_bamdev* d) { return d->rg_bam.data(); }
+int bdh_bamdev_ntid(const bdh_bamdev* d) { return (int)d->hdr.tid_names.size(); }
+const char* bdh_bamdev_tid_name(const bdh_bamdev* d, int tid) { return tid >= 0 && tid < (int)d->hdr.tid_names.size() ? d->hdr.tid_names[tid].c_str() : ""; }
+uint64_t bdh_bamdev_members(const bdh_bamdev* d) { return d->members.size(); }
+uint64_t bdh_bamdev_file_bytes(const bdh_bamdev* d) { return d->mf.size; }
+static void bamdev_source(const bdh_bamdev* d, bdk_bam_source& s) {
+    memset(&s, 0, sizeof s);
+    s.file = d->mf.data; s.file_bytes = d->mf.size;
+    s.members = d->members.data(); s.n_members = d->members.size();
+    s.first_record = d->first_record; s.end_offset = d->end_offset;
+    s.n_ref = (int32_t)d->hdr.tid_names.size();
+    s.region_on = d->rg.on ? 1 : 0; s.region_tid = d->rg.tid; s.region_beg = d->rg.beg; s.region_end = d->rg.end;
+    s.n_rg = (uint32_t)d->rg_hash.size(); s.rg_hash = d->rg_hash.data(); s.rg_id = d->rg_id.data();
+    s.rg_other = (uint16_t)(d->rg_lib.size() - 1);
+}
+int bdh_bamdev_push(bdh_bamdev* d, bdk_ctx* ctx, bdk_bam_stats* stats) {
+    bdk_bam_source s;
+    bamdev_source(d, s);
+    return bdk_push_bam(ctx, &s, stats);
+}
+int bdh_bamdev_decode(bdh_bamdev* d, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
+    bdk_bam_source s;
+    bamdev_source(d, s);
+    return bdk_decode_bam(ctx, &s, host_out, cap, stats);
+}
+
 // ---- writer -------------------------------------------------------------------------------------
 int bdh_write_bam(const char* path, int ntid, const char* const* tid_names, const uint32_t* tid_lens,
                   int nrg, const char* const* rg_names, const bdk_soa* cols, uint64_t n,

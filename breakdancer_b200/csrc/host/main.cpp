@@ -50,16 +50,6 @@ int main(int argc, char** argv) {
         }
         const bool want_reads = !o.prefix_fastq.empty() || !o.dump_BED.empty();
         char err[512] = {0};
-        // pageable columns: pinning hundreds of megabytes costs more than the staged copy of a one-shot run saves, and the decoder
-        // would have to wait for the CUDA context
-        stream = bdh_stream_open(&cfgh, nullptr, 0, o.chr.c_str(), 0, getenv("BDK_CLI_PINNED") ? 1 : 0, want_reads ? 1 : 0, err, sizeof err);
-        if (!stream) throw std::runtime_error(err);
-        if (!bdh_stream_sorted(stream))
-            std::cerr << "WARNING: the input is not sorted by reference sequence and position; the covered reference length, the window and "
-                         "the regions assume a coordinate-sorted bam (samtools sort).\n";
-        const double t_decoded = now_s();
-        if (cuda_warmup.joinable()) cuda_warmup.join();
-
         bdk_params p;
         memset(&p, 0, sizeof p);
         p.min_len = o.min_len; p.max_sd = o.max_sd; p.min_map_qual = o.min_map_qual; p.min_read_pair = o.min_read_pair;
@@ -67,17 +57,66 @@ int main(int argc, char** argv) {
         p.transchr_rearrange = o.transchr_rearrange; p.fisher = o.fisher; p.illumina_long_insert = o.Illumina_long_insert;
         p.cn_lib = o.CN_lib; p.chr_restricted = !o.chr.empty(); p.initial_window = cfg.window;
         p.nlib = (int)cfg.libs.size(); p.nbam = (int)cfg.bam_files.size();
-        p.nrg = std::max(1, bdh_stream_nrg(stream)); p.ntid = std::max(1, bdh_stream_ntid(stream));
         p.libs = cfg.libs.data();
         static const int32_t zero = 0;
-        p.rg_lib = bdh_stream_nrg(stream) ? bdh_stream_rg_lib(stream) : &zero;
-        p.rg_bam = bdh_stream_nrg(stream) ? bdh_stream_rg_bam(stream) : &zero;
-        check(nullptr, bdk_create(&ctx, 0, &p), "bdk_create");
-
-        bdk_soa cols;
-        bdh_stream_cols(stream, &cols);
-        const double t_created = now_s();
-        check(ctx, bdk_push(ctx, &cols, bdh_stream_n(stream)), "bdk_push");
+        std::vector<std::string> tid_names;
+        uint64_t n_records = 0;
+        double t_decoded = 0, t_created = 0;
+        bdk_bam_stats bstats;
+        memset(&bstats, 0, sizeof bstats);
+        bool on_device = false;
+        // One bam and no read dump: the file is decoded on the GPU (bdk_push_bam: only the compressed bytes cross PCIe, inflate /
+        // record parsing / classification of consecutive windows overlap). BDK_GPU_DECODE=0 keeps the host decoder. A file the
+        // device path refuses (damaged member, truncated record) goes through the host decoder, which reports what is wrong.
+        const char* gd = getenv("BDK_GPU_DECODE");
+        if (cfg.bam_files.size() == 1 && !want_reads && !(gd && atoi(gd) == 0)) {
+            if (bdh_bamdev* dev = bdh_bamdev_open(&cfgh, nullptr, o.chr.c_str(), err, sizeof err)) {
+                t_decoded = now_s();
+                if (cuda_warmup.joinable()) cuda_warmup.join();
+                p.nrg = bdh_bamdev_nrg(dev); p.ntid = std::max(1, bdh_bamdev_ntid(dev));
+                p.rg_lib = bdh_bamdev_rg_lib(dev); p.rg_bam = bdh_bamdev_rg_bam(dev);
+                check(nullptr, bdk_create(&ctx, 0, &p), "bdk_create");
+                t_created = now_s();
+                const int rc = bdh_bamdev_push(dev, ctx, &bstats);
+                if (rc == 0) {
+                    on_device = true;
+                    n_records = bstats.kept;
+                    for (int t = 0; t < bdh_bamdev_ntid(dev); ++t) tid_names.push_back(bdh_bamdev_tid_name(dev, t));
+                    if (!bstats.sorted)
+                        std::cerr << "WARNING: the input is not sorted by reference sequence and position; the covered reference length, the window and "
+                                     "the regions assume a coordinate-sorted bam (samtools sort).\n";
+                    // the tables bdk_params points to were copied by bdk_create; the names are copied above
+                    bdh_bamdev_free(dev);
+                } else {
+                    if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode refused the file (%s); host decoder\n", bdk_last_error(ctx));
+                    const std::string why = bdk_last_error(ctx);
+                    bdk_destroy(ctx); ctx = nullptr;
+                    bdh_bamdev_free(dev);
+                    if (rc != BDK_ERR_DATA) throw std::runtime_error("bdk_push_bam: " + why);
+                }
+            } else if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode: %s; host decoder\n", err);
+        }
+        if (!on_device) {
+            // pageable columns: pinning hundreds of megabytes costs more than the staged copy of a one-shot run saves, and the decoder
+            // would have to wait for the CUDA context
+            stream = bdh_stream_open(&cfgh, nullptr, 0, o.chr.c_str(), 0, getenv("BDK_CLI_PINNED") ? 1 : 0, want_reads ? 1 : 0, err, sizeof err);
+            if (!stream) throw std::runtime_error(err);
+            if (!bdh_stream_sorted(stream))
+                std::cerr << "WARNING: the input is not sorted by reference sequence and position; the covered reference length, the window and "
+                             "the regions assume a coordinate-sorted bam (samtools sort).\n";
+            t_decoded = now_s();
+            if (cuda_warmup.joinable()) cuda_warmup.join();
+            p.nrg = std::max(1, bdh_stream_nrg(stream)); p.ntid = std::max(1, bdh_stream_ntid(stream));
+            p.rg_lib = bdh_stream_nrg(stream) ? bdh_stream_rg_lib(stream) : &zero;
+            p.rg_bam = bdh_stream_nrg(stream) ? bdh_stream_rg_bam(stream) : &zero;
+            check(nullptr, bdk_create(&ctx, 0, &p), "bdk_create");
+            bdk_soa cols;
+            bdh_stream_cols(stream, &cols);
+            t_created = now_s();
+            n_records = bdh_stream_n(stream);
+            check(ctx, bdk_push(ctx, &cols, n_records), "bdk_push");
+            for (int t = 0; t < bdh_stream_ntid(stream); ++t) tid_names.push_back(bdh_stream_tid_name(stream, t));
+        }
         bdk_summary_t S;
         check(ctx, bdk_summary(ctx, &S), "bdk_summary");
         for (int b = 0; b < p.nbam; ++b)
@@ -99,8 +138,6 @@ int main(int argc, char** argv) {
         if (uint32_t nd = bdk_duplicate_names(ctx))
             std::cerr << "WARNING: " << nd << " anomalous read(s) share their name with two or more others (bams with overlapping read names?); "
                          "the reads of such names are left unpaired.\n";
-        std::vector<std::string> tid_names;
-        for (int t = 0; t < bdh_stream_ntid(stream); ++t) tid_names.push_back(bdh_stream_tid_name(stream, t));
         format_rows(std::cout, p, res, cfg.lib_names, cfg.bam_files, tid_names, o.print_AF);
 
         if (want_reads) {
@@ -111,15 +148,17 @@ int main(int argc, char** argv) {
         if (!o.stats_json.empty()) {        // SURVEY section 5, metrics row
             std::cout.flush();
             const double t_end = now_s();
-            const uint64_t n = bdh_stream_n(stream);
+            const uint64_t n = n_records;
             double stage[3] = {0, 0, 0};
-            bdh_stream_timings(stream, &stage[0], &stage[1], &stage[2]);
+            if (stream) bdh_stream_timings(stream, &stage[0], &stage[1], &stage[2]);
             std::ofstream js(o.stats_json.c_str());
             js << "{\"records\": " << n << ", \"read_pairs\": " << n / 2 << ", \"sv_calls\": " << res.n_sv
                << ", \"anomalous_reads\": " << S.n_anomalous << ", \"total_s\": " << t_end - t_start
                << ", \"decode_s\": " << t_decoded - t_start << ", \"decode_inflate_s\": " << stage[0] << ", \"decode_extract_s\": " << stage[1]
                << ", \"decode_merge_s\": " << stage[2] << ", \"context_s\": " << t_created - t_decoded << ", \"push_s\": " << t_pushed - t_created
                << ", \"finish_s\": " << t_finished - t_pushed << ", \"output_s\": " << t_end - t_finished
+               << ", \"device_decode\": " << (on_device ? 1 : 0) << ", \"device_inflate_ms\": " << bstats.inflate_ms << ", \"device_chain_ms\": " << bstats.chain_ms
+               << ", \"device_extract_ms\": " << bstats.extract_ms << ", \"device_windows\": " << bstats.windows << ", \"inflated_bytes\": " << bstats.inflated_bytes
                << ", \"h2d_bytes\": " << bdk_h2d_bytes(ctx) << ", \"d2h_bytes\": " << bdk_d2h_bytes(ctx)
                << ", \"read_pairs_per_s\": " << (double)(n / 2) / (t_end - t_start) << "}\n";
         }

@@ -303,6 +303,55 @@ typedef struct bdk_bgzf_member {
 int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const bdk_bgzf_member* members, uint64_t n_members,
                      uint8_t* out, uint64_t out_bytes, int32_t* status, float* kernel_ms);
 
+/* One BAM file decoded ON THE DEVICE and classified: the compressed BGZF members cross PCIe, the GPU inflates them (one warp per
+ * member, CRC32 of every member checked against its footer), finds the record boundaries, applies the reader's filter, extracts
+ * the columns of bdk_soa and runs the classify kernel on them, window of members by window, with the copy, the inflate and the
+ * decode of consecutive windows overlapped (csrc/bdk_bam.inl, bgzf_inflate_warp.cuh, bam_decode.cuh). Replaces, for a run from
+ * one file, samread + inflate_block of the vendored samtools reached through src/lib/io/BamReader.hpp:64-70 (or
+ * RegionLimitedBamReader.hpp:40-66 with a region), the reader filter src/lib/io/BamIo.cpp:11-18, the Alignment constructor
+ * src/lib/io/Alignment.cpp:12-64 and the read-group look-up src/lib/io/AlignmentSource.hpp:48-65 -- and then does what bdk_push does.
+ * The records it pushes are the ones bdh_stream_open (host decoder) delivers for the same file, in the same order; read-group ids are
+ * the caller's: rg_id[i] for a record whose RG:Z string hashes (bdk_hash_bytes) to rg_hash[i], rg_other for every other string or
+ * no RG tag (the reference maps read groups its config does not know to the first bam's library, BamConfig.hpp:63-72).
+ * The caller parses the BAM header (text, reference names) itself and passes the members from the one that holds the first record.
+ * Errors: BDK_ERR_DATA for a member that does not inflate or fails its CRC, a truncated record, a record longer than 16 MiB; the
+ * job then holds an unspecified prefix of the file (bdk_reset before doing anything else with the context). */
+typedef struct bdk_bam_source {
+    const uint8_t* file;              /* host image of the BGZF file (for instance an mmap) */
+    uint64_t file_bytes;
+    const bdk_bgzf_member* members;   /* DEFLATE streams in file order, each followed in the file by its CRC32 + ISIZE footer;
+                                         out_off = running sum of out_len, 0 for members[0]; members without output may be left out */
+    uint64_t n_members;
+    uint64_t first_record;            /* offset, in the members' concatenated output, of the first record's block_size field;
+                                         must lie inside members[0] (or at least inside the first window) */
+    uint64_t end_offset;              /* where the records end (a record boundary), 0 = with the last member */
+    int32_t n_ref;                    /* reference sequences in the BAM header */
+    int32_t region_on, region_tid, region_beg, region_end;   /* -o: keep records overlapping [beg, end) of tid (0-based) */
+    uint32_t n_rg;
+    const uint64_t* rg_hash;          /* [n_rg] */
+    const uint16_t* rg_id;            /* [n_rg] */
+    uint16_t rg_other;
+    uint16_t reserved;
+    uint64_t window_bytes;            /* compressed bytes per pipeline step, 0 = default (32 MiB) */
+} bdk_bam_source;
+typedef struct bdk_bam_stats {
+    uint64_t records;                 /* records in the stream */
+    uint64_t kept;                    /* records that passed the reader's filter and were classified */
+    uint64_t h2d_bytes;               /* bytes copied host -> device */
+    uint64_t inflated_bytes;
+    uint32_t windows;
+    uint32_t guess_misses;            /* record-boundary guesses that were wrong or missing (resolved exactly, see bam_decode.cuh) */
+    int32_t sorted;                   /* 1 iff the kept records are ordered by (reference sequence, position) */
+    float inflate_ms, chain_ms, extract_ms;   /* device time of the inflate + CRC kernels, the boundary search, the extraction */
+} bdk_bam_stats;
+int bdk_push_bam(bdk_ctx* ctx, const bdk_bam_source* src, bdk_bam_stats* stats);
+/* The same decode, but the columns come back to the HOST (arrays of `cap` records the caller owns, written through the const
+ * pointers of *host_out) and nothing is classified: the device decoder as a drop-in for bdh_stream_open on one file, and what the
+ * parity tests compare with the host decoder column by column. stats->kept = records written. */
+int bdk_decode_bam(bdk_ctx* ctx, const bdk_bam_source* src, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
+/* The 64-bit key of a byte string the decoders use for read names (bdk_soa.qid) and read-group strings. */
+uint64_t bdk_hash_bytes(const void* bytes, uint64_t n);
+
 const char* bdk_version(void);
 
 #ifdef __cplusplus

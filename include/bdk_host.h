@@ -75,6 +75,28 @@ int bdh_bai_reference_stats(const char* bam_path, int64_t* records, int64_t* byt
  * members the GPU decoder refused or got wrong and the host decoded again. */
 void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone);
 
+/* ---- device-resident decode: the host's share ------------------------------------------------------------------------------
+ * bdk_push_bam (include/bdk.h) inflates, parses and classifies a BAM file on the GPU. What stays on the host is opening the
+ * file: mapping it, listing its BGZF members (with a region and a .bai only those of the reference sequence,
+ * RegionLimitedBamReader.hpp:40-66), inflating the few members of the BAM header and numbering the read groups -- the config's
+ * read groups in its own order, then one id for every other read-group string (BamConfig.hpp:63-72: unknown read groups get the
+ * first bam's library). path NULL/"" = the config's only bam. Order of use: bdh_bamdev_open, bdk_create with nrg / rg_lib /
+ * rg_bam / ntid from here, bdh_bamdev_push, bdk_summary / bdk_finish. The records pushed are those bdh_stream_open delivers for
+ * the same file and region, in the same order. One file per call; several bams (BamMerger) go through bdh_stream_open. */
+typedef struct bdh_bamdev bdh_bamdev;
+bdh_bamdev* bdh_bamdev_open(const bdh_config* cfg, const char* path, const char* region, char* err, int errcap);
+void bdh_bamdev_free(bdh_bamdev* d);
+int bdh_bamdev_nrg(const bdh_bamdev* d);
+const int32_t* bdh_bamdev_rg_lib(const bdh_bamdev* d);
+const int32_t* bdh_bamdev_rg_bam(const bdh_bamdev* d);
+int bdh_bamdev_ntid(const bdh_bamdev* d);
+const char* bdh_bamdev_tid_name(const bdh_bamdev* d, int tid);
+uint64_t bdh_bamdev_members(const bdh_bamdev* d);
+uint64_t bdh_bamdev_file_bytes(const bdh_bamdev* d);
+int bdh_bamdev_push(bdh_bamdev* d, bdk_ctx* ctx, bdk_bam_stats* stats);
+/* bdk_decode_bam of the opened file: the decoded columns into the caller's host arrays (cap records each). */
+int bdh_bamdev_decode(bdh_bamdev* d, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
+
 /* ---- BAM writer for synthetic inputs (stands in for samtools' bam_write1) ------------------
  * Writes n records from struct-of-arrays columns as a BGZF-compressed BAM with query names
  * "<prefix><qid>", one RG:Z tag per record (rg_names[rgid]), AM:i = mapq when write_am != 0,

@@ -1,0 +1,190 @@
+"""Device-resident BAM decode (bdk_push_bam / bdk_decode_bam: csrc/bdk_bam.inl, bgzf_inflate_warp.cuh, bam_decode.cuh).
+
+The GPU inflates the BGZF members (one warp per member, CRC32 checked on the device), finds the record boundaries, filters and
+extracts the columns and classifies them, window by window. Checked here against the host decoder (bdh_stream_open, itself
+pinned by the CPU tests): every column of every record, then the whole job (summary, anomalous reads, regions, SV table)
+against a job fed from the host-decoded columns -- for every deflate level, with a member per window (every record boundary
+case of the carry-over), on the bundled real BAMs whole / by region through the index / by region without it, on records that
+contain decoy records, and on damaged files, which must be refused. The CLI tests of test_gpu_parity.py run through this path
+too (one bam, no read dump)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from breakdancer_b200 import api, synth
+from tests import util
+from tests.test_config_and_bam import _bam_record, _bgzf, _decoy_records, _handmade_bam
+
+pytestmark = pytest.mark.gpu
+
+
+def _write(tmp_path, n_pairs, level, seed=21, libs=None):
+    w = synth.generate(util.GENOME3, libs or util.LIBS4, n_pairs, seed=seed, anomaly_frac=0.05)
+    d = tmp_path / ("l%d_%d" % (level, seed))
+    d.mkdir()
+    for bam, cols in synth.split_by_bam(w).items():
+        api.write_bam(str(d / bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=level)
+    return w, d
+
+
+def _compare_columns(cfg, path, region=""):
+    """Host decoder vs device decoder on one file: all columns, read groups through their library."""
+    host = api.BamStream(cfg, paths=[path], region=region, threads=4)
+    dev = api.BamDevice(cfg, path=path, region=region)
+    ctx = api.Context(dev.bundle(api.Options(chr=region)))
+    cols, st = ctx.decode_bam(dev, host.n + 64)
+    assert st["kept"] == host.n, (st, host.n)
+    for k in api.COLUMN_DTYPES:
+        if k == "rgid":
+            assert np.array_equal(host.rg_lib[host.cols[k]], dev.rg_lib[cols[k]]), k
+        else:
+            assert np.array_equal(host.cols[k], cols[k]), (k, path, region)
+    n = host.n
+    ctx.close(); dev.close(); host.close()
+    return st, n
+
+
+def _job_from_host(cfg, path, opts):
+    host = api.BamStream(cfg, paths=[path], region=opts.chr, threads=4)
+    b = api.ParamBundle(opts, cfg.libs, cfg.nbam, host.rg_lib, host.rg_bam, cfg.window, max(1, len(host.tid_names)))
+    ctx = api.Context(b)
+    ctx.push({k: np.ascontiguousarray(v) for k, v in host.cols.items()})
+    out = (ctx.summary(), ctx.finish(), ctx.regions(), ctx.areads())
+    ctx.close(); host.close()
+    return out
+
+
+def _job_from_device(cfg, path, opts):
+    dev = api.BamDevice(cfg, path=path, region=opts.chr)
+    ctx = api.Context(dev.bundle(opts))
+    st = ctx.push_bam(dev)
+    out = (ctx.summary(), ctx.finish(), ctx.regions(), ctx.areads())
+    times = ctx.kernel_times()
+    ctx.close(); dev.close()
+    return out, st, times
+
+
+def _assert_same_job(a, b):
+    (sa, ta, ra, (aa, rra)), (sb, tb, rb, (ab, rrb)) = a, b
+    assert bytes(sa) == bytes(sb)
+    assert ta.sv.tobytes() == tb.sv.tobytes() and np.array_equal(ta.lib_count, tb.lib_count) and np.array_equal(ta.cn_count, tb.cn_count)
+    assert ta.copy_number.tobytes() == tb.copy_number.tobytes()
+    assert np.array_equal(ra, rb) and np.array_equal(aa, ab) and np.array_equal(rra, rrb)
+
+
+@pytest.mark.parametrize("level", [6, 1, 9, 0])
+def test_device_decode_equals_host_decode_on_every_deflate_level(tmp_path, level):
+    w, d = _write(tmp_path, 60000, level)
+    cfg = api.BamConfig(text=w.config_text())
+    for bam in sorted(synth.split_by_bam(w)):
+        st, n = _compare_columns(cfg, str(d / bam))
+        assert st["records"] >= n and st["sorted"] == 1 and st["windows"] >= 1
+
+
+def test_a_member_per_window_carries_every_cut_record(tmp_path, monkeypatch):
+    w, d = _write(tmp_path, 40000, 6, seed=5)
+    cfg = api.BamConfig(text=w.config_text())
+    bam = str(d / sorted(synth.split_by_bam(w))[0])
+    monkeypatch.setenv("BDK_BAMDEV_WINDOW_KB", "1")          # every window is one member
+    st, n = _compare_columns(cfg, bam)
+    assert st["windows"] > 50
+    monkeypatch.setenv("BDK_BAMDEV_WINDOW_KB", "100")
+    st2, _ = _compare_columns(cfg, bam)
+    assert 1 < st2["windows"] < st["windows"]
+    for region in ("chrB", "chrB:100000-900000", "chrC"):     # the reader's overlap filter, no index
+        _compare_columns(cfg, bam, region)
+
+
+def test_whole_job_from_the_device_decode_equals_the_job_from_host_columns(tmp_path, monkeypatch):
+    libs = [synth.LibSpec("lib_a", "one.bam", 315, 44, 75, ["a1", "a2"]), synth.LibSpec("lib_b", "one.bam", 467, 32, 100, ["b1"])]
+    w, d = _write(tmp_path, 150000, 6, seed=9, libs=libs)
+    cfg = api.BamConfig(text=w.config_text())
+    bam = str(d / "one.bam")
+    for opts in (api.Options(), api.Options(CN_lib=True, min_read_pair=1), api.Options(chr="chrB")):
+        want = _job_from_host(cfg, bam, opts)
+        got, st, times = _job_from_device(cfg, bam, opts)
+        _assert_same_job(want, got)
+        assert len(got[1].sv) > 0 and times["bam_inflate"]["launches"] >= 2 and times["bam_extract"]["ms"] > 0
+    monkeypatch.setenv("BDK_BAMDEV_WINDOW_KB", "64")
+    got, st, _ = _job_from_device(cfg, bam, api.Options())
+    _assert_same_job(_job_from_host(cfg, bam, api.Options()), got)
+    assert st["windows"] > 3
+
+
+def test_bundled_real_bams_whole_by_index_and_by_scan(monkeypatch):
+    cfg = api.BamConfig(path=os.path.join(util.CHR21, "inv_del_bam_config"))
+    cwd = os.getcwd()
+    os.chdir(util.CHR21)
+    try:
+        for name in cfg.bam_files:
+            _compare_columns(cfg, name)
+            _compare_columns(cfg, name, "21")
+            _compare_columns(cfg, name, "21:15000000-30000000")
+            monkeypatch.setenv("BDK_NO_BAI", "1")
+            _compare_columns(cfg, name, "21:15000000-30000000")
+            monkeypatch.delenv("BDK_NO_BAI")
+    finally:
+        os.chdir(cwd)
+
+
+def test_records_that_contain_decoy_records(tmp_path, monkeypatch):
+    recs, want_pos = _decoy_records(n=3000)
+    bam = str(tmp_path / "decoy.bam")
+    open(bam, "wb").write(_handmade_bam(recs))
+    cfg = api.BamConfig(text="map:%s\tlib:L\tmean:300\tstd:30\treadlen:36\n" % bam)
+    for kb in ("", "1", "40"):
+        if kb:
+            monkeypatch.setenv("BDK_BAMDEV_WINDOW_KB", kb)
+        st, n = _compare_columns(cfg, bam)
+        assert n == len(want_pos)
+    assert st["guess_misses"] >= 0
+
+
+def test_damaged_files_are_refused(tmp_path):
+    w, d = _write(tmp_path, 30000, 6, seed=3)
+    cfg = api.BamConfig(text=w.config_text())
+    name = sorted(synth.split_by_bam(w))[0]
+    data = bytearray((d / name).read_bytes())
+    # a flipped bit in the middle of some member's DEFLATE stream: refused by the decoder or by the CRC
+    bad = bytearray(data)
+    bad[len(bad) // 2] ^= 0x10
+    p = tmp_path / "flipped.bam"
+    p.write_bytes(bytes(bad))
+    dev = api.BamDevice(cfg, path=str(p))
+    ctx = api.Context(dev.bundle(api.Options()))
+    with pytest.raises(api.BdkError) as e:
+        ctx.push_bam(dev)
+    assert "did not inflate" in str(e.value) or "truncated" in str(e.value)
+    ctx.close(); dev.close()
+    # the data ends inside a record: the last members are dropped at a member boundary (the EOF marker stays)
+    from tests.test_zz_gpu_inflate import _members
+    mem = _members(bytes(data))
+    cut = mem[len(mem) // 2][0] - 18                    # start of a member in the middle of the file
+    eof = bytes(data[-28:])
+    p2 = tmp_path / "cut.bam"
+    p2.write_bytes(bytes(data[:cut]) + eof)
+    dev = api.BamDevice(cfg, path=str(p2))
+    ctx = api.Context(dev.bundle(api.Options()))
+    with pytest.raises(api.BdkError) as e:
+        ctx.push_bam(dev)
+    assert "truncated" in str(e.value)
+    ctx.close(); dev.close()
+
+
+def test_cli_takes_the_device_path_and_falls_back_for_what_it_cannot_do(tmp_path):
+    libs = [synth.LibSpec("lib_a", "one.bam", 315, 44, 75, ["a1"])]
+    w, d = _write(tmp_path, 50000, 6, seed=4, libs=libs)
+    (d / "cfg").write_text(w.config_text())
+    outs = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, BDK_GPU_DECODE=mode)
+        stats = d / ("stats%s.json" % mode)
+        p = subprocess.run([util.CLI, "--stats-json", str(stats), "cfg"], cwd=d, env=env, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        outs[mode] = util.strip_header(p.stdout)
+        import json
+        js = json.loads(stats.read_text())
+        assert js["device_decode"] == int(mode)
+    assert outs["1"] == outs["0"] and outs["1"].count("\n") > 5
