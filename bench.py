@@ -50,6 +50,30 @@ BYTES_PER_RECORD = 25          # pos,mpos,tid,mtid,isize int32 + flag u16 + mapq
 HOST_BYTES_PER_RECORD = 37     # + qlen int32 + qid u64 side columns copied by bdk_push
 
 
+def k1_source_digest():
+    """Digest of the sources the classify kernel is built from: a DRAM-traffic capture is reported only for the kernel it was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("k1_classify.cuh", "bdk_logic.h", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "breakdancer_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def k1_traffic(n_records, config):
+    """(DRAM bytes of one K1 launch from the tracked ncu --set full capture, where it comes from) -- None unless the capture was
+    taken on this workload (same records per launch) with the kernel sources as they are now."""
+    name = "k1_traffic_config3.json" if config == 3 else "k1_traffic.json"
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", name)))
+    except Exception:
+        return None, f"no capture (profiles/{name})"
+    if int(t.get("records", -1)) != int(n_records):
+        return None, f"profiles/{name} ({t.get('tag')}) was captured on {t.get('records')} records, this launch has {n_records}"
+    if t.get("k1_source_digest") != k1_source_digest():
+        return None, f"profiles/{name} ({t.get('tag')}) was captured on other kernel sources; re-run scripts/gpu_round.sh"
+    return float(t["dram_bytes"]), f"profiles/{name}: ncu --set full {t.get('source')} ({t.get('tag')}), dram__bytes_read.sum + dram__bytes_write.sum of one launch"
+
+
 def workload_name(pairs, config=2):
     if config == 3:
         return f"synthetic 4-library tumor/normal chr1-3, all 5 SV types (-c 3 -q 35), {pairs / 1e6:g}M read pairs per GPU (BASELINE configs[2])"
@@ -143,11 +167,16 @@ def cpu_baseline(pairs_total, nproc, seed0=20260101):
 
 
 def file_e2e_sample(pairs, level=6):
-    """From a BAM FILE to the SV table with the drop-in executable (breakdancer_b200/bin/breakdancer_max: decode on all host
-    cores, one GPU), wall clock of the whole process, on one BAM of the bench workload. Stage times from --stats-json."""
+    """From a BAM FILE to the SV table with the drop-in executable (breakdancer_b200/bin/breakdancer_max), wall clock of the
+    whole process (start, CUDA context, decode, classification, SV calls, output), on one BAM of the bench workload:
+    `value` is the default path (the file is decoded ON THE GPU: bdk_push_bam, only compressed bytes cross PCIe);
+    `host_decoder` the same executable with BDK_GPU_DECODE=0 (BGZF inflate and record parsing on all host cores, columns pushed
+    to the GPU); `in_process` the device path without the process around it (bdk_push_bam + bdk_finish on an open context, best
+    of 3: what a long-running caller or a file much larger than the start-up cost sees). Stage times from --stats-json."""
     from breakdancer_b200 import api, synth
     cli = os.path.join(ROOT, "breakdancer_b200", "bin", "breakdancer_max")
     tmp = tempfile.mkdtemp(prefix="bdk_file_", dir=os.environ.get("TMPDIR", "/tmp"))
+    cwd = os.getcwd()
     try:
         w = synth.config2(pairs, seed=20260106, chrom_len=max(1_000_000, 5 * pairs))
         size = 0
@@ -155,21 +184,55 @@ def file_e2e_sample(pairs, level=6):
             api.write_bam(os.path.join(tmp, bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=level)
             size += os.path.getsize(os.path.join(tmp, bam))
         open(os.path.join(tmp, "cfg"), "w").write(w.config_text())
+        npairs = w.n // 2
+        del w
+
+        def run_cli(mode):
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                rc = subprocess.run([cli, "--stats-json", "stats.json", "cfg"], cwd=tmp, env=dict(os.environ, BDK_GPU_DECODE=mode),
+                                    stdout=open(os.path.join(tmp, f"out{mode}.tsv"), "w"), stderr=subprocess.PIPE, text=True)
+                dt = time.perf_counter() - t0
+                if rc.returncode != 0:
+                    raise RuntimeError(f"breakdancer_max failed: {rc.stderr[-300:]}")
+                if best is None or dt < best[0]:
+                    best = (dt, json.load(open(os.path.join(tmp, "stats.json"))))
+            dt, st = best
+            return {"value": npairs / dt, "unit": UNIT, "wall_s": round(dt, 3), "device_decode": st.get("device_decode"),
+                    "stages_s": {k: round(v, 4) for k, v in st.items() if k.endswith("_s") and k != "read_pairs_per_s"},
+                    "device_ms": {k: round(v, 2) for k, v in st.items() if k.startswith("device_") and k.endswith("_ms")},
+                    "h2d_bytes": st.get("h2d_bytes"), "sv_calls": st.get("sv_calls")}
+        dev, host = run_cli("1"), run_cli("0")
+        same = open(os.path.join(tmp, "out1.tsv")).read().split("\n", 2)[2] == open(os.path.join(tmp, "out0.tsv")).read().split("\n", 2)[2]
+        # the device path inside a running process
+        os.chdir(tmp)
+        cfg = api.BamConfig(path="cfg")
+        bd = api.BamDevice(cfg)
+        ctx = api.Context(bd.bundle(api.Options()))
         best = None
-        for _ in range(3):
+        for _ in range(4):
+            ctx.reset()
             t0 = time.perf_counter()
-            rc = subprocess.run([cli, "--stats-json", "stats.json", "cfg"], cwd=tmp, stdout=open(os.path.join(tmp, "out.tsv"), "w"), stderr=subprocess.PIPE, text=True)
+            st = ctx.push_bam(bd)
+            table = ctx.finish()
             dt = time.perf_counter() - t0
-            if rc.returncode != 0:
-                raise RuntimeError(f"breakdancer_max failed: {rc.stderr[-300:]}")
             if best is None or dt < best[0]:
-                best = (dt, json.load(open(os.path.join(tmp, "stats.json"))))
-        dt, st = best
-        return {"value": (w.n // 2) / dt, "unit": UNIT, "wall_s": round(dt, 3), "cores": os.cpu_count() or 1, "bam_bytes": size,
-                "stages_s": {k: round(v, 4) for k, v in st.items() if k.endswith("_s") and k != "read_pairs_per_s"}, "sv_calls": st.get("sv_calls"),
-                "sample": f"one BAM of {w.n // 2} read pairs of the same workload (deflate level {level}), whole process (start, CUDA context, decode, GPU, "
-                          "output), best of 3"}
+                best = (dt, st, len(table.sv))
+        ctx.close(); bd.close()
+        dt, st, nsv = best
+        inproc = {"value": npairs / dt, "unit": UNIT, "s": round(dt, 4), "sv_calls": nsv, "windows": st["windows"],
+                  "inflate_ms": round(st["inflate_ms"], 2), "inflate_GBps_of_output": round(st["inflated_bytes"] / 1e6 / max(st["inflate_ms"], 1e-6), 2),
+                  "record_chain_ms": round(st["chain_ms"], 2), "extract_ms": round(st["extract_ms"], 2), "host_staging_ms": round(st["stage_ms"], 2),
+                  "h2d_bytes": st["h2d_bytes"], "inflated_bytes": st["inflated_bytes"]}
+        out = dict(dev)
+        out.update({"cores": os.cpu_count() or 1, "bam_bytes": size, "host_decoder": host, "in_process": inproc, "same_output_both_decoders": same,
+                    "sample": f"one BAM of {npairs} read pairs of the same workload (deflate level {level}); whole process (start, CUDA context, decode, GPU, "
+                              "output), best of 3, for `value` (file decoded on the GPU) and `host_decoder` (BDK_GPU_DECODE=0); `in_process`: "
+                              "bdk_push_bam + bdk_finish on an open context, best of 4"})
+        return out
     finally:
+        os.chdir(cwd)
         shutil.rmtree(tmp, ignore_errors=True)
 
 
@@ -507,12 +570,7 @@ def ours(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         k1_ms = k1["ms"] / max(1, k1["launches"])
         achieved = n * BYTES_PER_RECORD / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_record")
-            traffic = traffic * n if traffic else None
-        except Exception:
-            pass
+        traffic, traffic_src = k1_traffic(n, args.config)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -520,7 +578,7 @@ def ours(args):
                        "sharding": "one chromosome-shaped shard per GPU, no data-path collective" if world > 1 else "single GPU",
                        "l2": f"inputs ({n * HOST_BYTES_PER_RECORD / 1e9:.1f} GB) are larger than L2, no flush needed", "options": "defaults (-c 3 -q 35 -r 2 -y 30)"},
             "roofline": {"bound": "hbm", "kernel": "k1_classify_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * BYTES_PER_RECORD, "kernel_ms": k1_ms},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in ktimes.items()},
             "host_call_ms_per_step": {k: v / args.steps for k, v in host_ms.items()},
@@ -556,7 +614,8 @@ def ours(args):
                 "records_in_host_memory_to_sv": {"ours": line["e2e"]["value"], "reference_decode_free": cf.get("value"),
                                                  "ratio": (line["e2e"]["value"] / cf["value"]) if cf.get("value") else None},
                 "bam_file_to_sv": {"ours": fe.get("value"), "reference": cb.get("value"),
-                                   "ratio": (fe["value"] / cb["value"]) if fe.get("value") and cb.get("value") else None}}
+                                   "ratio": (fe["value"] / cb["value"]) if fe.get("value") and cb.get("value") else None,
+                                   "ours_in_process": (fe.get("in_process") or {}).get("value")}}
             try:
                 line["bam_decode"] = bam_decode_sample(args.bam_pairs)
             except Exception as ex:   # reported, never required
@@ -782,7 +841,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=400_000, help="read pairs per process and step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--bam-pairs", type=int, default=2_000_000, help="size of the BAM sample of the bam_decode leg")
-    ap.add_argument("--file-pairs", type=int, default=6_000_000, help="read pairs of the BAM the file_e2e leg runs the drop-in executable on")
+    ap.add_argument("--file-pairs", type=int, default=24_000_000, help="read pairs of the BAM the file_e2e leg runs the drop-in executable on")
     ap.add_argument("--no-genome", action="store_true", help="N > 1: skip the one-job-over-all-GPUs (NCCL exchange) measurements")
     ap.add_argument("--no-configs45", action="store_true", help="N > 1: skip the BASELINE configs[3] (LPT shards) and configs[4] (-t, 1 B pairs) blocks")
     ap.add_argument("--genome-pairs", type=int, default=617_700_000, help="read pairs of the configs[3] whole genome")

@@ -127,7 +127,7 @@ class BamStats(C.Structure):
     """bdk_bam_stats (include/bdk.h)."""
     _fields_ = [("records", C.c_uint64), ("kept", C.c_uint64), ("h2d_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
                 ("windows", C.c_uint32), ("guess_misses", C.c_uint32), ("sorted", C.c_int32),
-                ("inflate_ms", C.c_float), ("chain_ms", C.c_float), ("extract_ms", C.c_float)]
+                ("inflate_ms", C.c_float), ("chain_ms", C.c_float), ("extract_ms", C.c_float), ("stage_ms", C.c_float), ("wall_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

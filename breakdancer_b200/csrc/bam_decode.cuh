@@ -4,8 +4,7 @@
 // code the host decoder runs and its tests pin. Replaces, for a run from files, samread + the Alignment constructor
 // (src/lib/io/BamReader.hpp:64-70, src/lib/io/Alignment.cpp:12-64) and the reader filter (src/lib/io/BamIo.cpp:11-18).
 //
-// Record boundaries, as on the host (bam_io.cpp find_records): a window is cut into segments, one per BGZF member (the inflate
-// kernel knows their output offsets); every segment guesses its first record (three plausible records in a row) and follows the
+// Record boundaries, as on the host (bam_io.cpp find_records): a window is cut into segments of 8 KiB; every segment guesses its first record (three plausible records in a row) and follows the
 // chain of block_size prefixes to its end, all segments in parallel (chain_guess_kernel). chain_resolve_kernel then checks the
 // guesses against the chain that really arrives: if every chain ends exactly on the next segment's guess the guessed chains ARE
 // the serial chain (induction from the window's first byte, which is a true record start); wherever a guess is wrong or missing
@@ -36,47 +35,58 @@ struct WinInfo {                 // what the host needs to know about a window b
     uint32_t guess_misses;       // segments the true chain had to be followed through
 };
 
-// segment k of a window = [lo, hi): bytes of member k (the first one also holds the bytes carried over)
-// `carry` = bytes carried over in front of member 0's output; negative in a file's first window, whose bytes begin at the first
-// record (behind the BAM header, which may span members)
-__device__ __forceinline__ uint64_t seg_clamp(int64_t v, uint64_t n) { return v <= 0 ? 0 : (uint64_t)v < n ? (uint64_t)v : n; }
-__device__ __forceinline__ uint64_t seg_lo(const Member* m, uint32_t k, int64_t carry, uint64_t n) { return k ? seg_clamp(carry + (int64_t)m[k].out_off, n) : 0; }
-__device__ __forceinline__ uint64_t seg_hi(const Member* m, uint32_t k, uint32_t nseg, int64_t carry, uint64_t n) {
-    return k + 1 < nseg ? seg_clamp(carry + (int64_t)m[k + 1].out_off, n) : n;
-}
+// segment k of a window = bytes [k * SEG_BYTES, (k + 1) * SEG_BYTES) of it (the last one shorter)
+constexpr uint32_t SEG_BYTES = 8192;
+__device__ __forceinline__ uint64_t seg_lo(uint32_t k) { return (uint64_t)k * SEG_BYTES; }
+__device__ __forceinline__ uint64_t seg_hi(uint32_t k, uint64_t n) { const uint64_t h = (uint64_t)(k + 1) * SEG_BYTES; return h < n ? h : n; }
 
 // One thread per segment.
-__global__ void __launch_bounds__(64) chain_guess_kernel(const uint8_t* __restrict__ raw, uint64_t n, const Member* __restrict__ members, uint32_t nseg,
-                                                         int64_t carry, int32_t nref, Segment* __restrict__ seg) {
+__global__ void __launch_bounds__(128) chain_guess_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint32_t nseg, int32_t nref, Segment* __restrict__ seg) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nseg) return;
-    const uint64_t lo = seg_lo(members, k, carry, n), hi = seg_hi(members, k, nseg, carry, n);
-    Segment s;
-    if (lo >= hi) { s.guess = NO_GUESS; s.end = hi; s.count = 0; s.bad = 0; }
-    else s = brec::segment_guess(raw, n, lo, hi, k == 0, nref);
-    seg[k] = s;
+    seg[k] = brec::segment_guess(raw, n, seg_lo(k), seg_hi(k, n), k == 0, nref);
+}
+
+// inclusive max-scan of one value per thread across a block of up to 1024 threads; s_warp: [33]
+__device__ __forceinline__ uint32_t block_max_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = max(inc, t); }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, wi, d); if (lane >= d) wi = max(wi, t); }
+        const uint32_t excl = __shfl_up_sync(FULL, wi, 1);
+        s_warp[lane] = lane ? excl : 0;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    inc = max(inc, s_warp[warp]);
+    *total = s_warp[32];
+    __syncthreads();
+    return inc;
 }
 
 // One CTA. Member verdicts, the check of the guesses (in parallel; a serial walk by one thread only where the picture is not
 // the regular one), the records before every segment (base[k], exclusive scan of the counts) and the window's WinInfo.
-__global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __restrict__ raw, uint64_t n, const Member* __restrict__ members, uint32_t nseg,
-                                                             int64_t carry, int last_window, const int32_t* __restrict__ status,
-                                                             Segment* __restrict__ seg, uint32_t* __restrict__ base, WinInfo* __restrict__ info,
-                                                             uint32_t* __restrict__ nrec_out) {
+// Regular picture: every segment in which a record starts guessed that start right -- its guess is where the chain of the
+// nearest earlier segment with a guess ends (the first segment starts on a record by construction) -- segments without a guess
+// lie inside a record that began earlier, no chain met a broken record, and only the last chain may stop at a cut-off record.
+__global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint32_t nseg, uint32_t nmem, int last_window,
+                                                             const int32_t* __restrict__ status, Segment* __restrict__ seg, uint32_t* __restrict__ base,
+                                                             WinInfo* __restrict__ info, uint32_t* __restrict__ nrec_out) {
     __shared__ uint32_t s_warp[33];
-    __shared__ uint32_t s_irregular, s_bad, s_first_bad, s_carry;
+    __shared__ uint32_t s_irregular, s_bad, s_first_bad, s_carry, s_last;
     __shared__ WinInfo s_info;
     const uint32_t t = threadIdx.x;
-    if (t == 0) { s_irregular = 0; s_bad = 0; s_first_bad = 0xffffffffu; s_carry = 0; s_info.tail = n; s_info.err = 0; s_info.guess_misses = 0; }
+    if (t == 0) { s_irregular = 0; s_bad = 0; s_first_bad = 0xffffffffu; s_carry = 0; s_last = 0; s_info.tail = n; s_info.err = 0; s_info.guess_misses = 0; }
     __syncthreads();
-    for (uint32_t k = t; k < nseg; k += blockDim.x) {
+    for (uint32_t k = t; k < nmem; k += blockDim.x)
         if (status[k] != 0) { atomicAdd(&s_bad, 1u); atomicMin(&s_first_bad, k); }
-        const Segment s = seg[k];
-        bool regular = s.guess != NO_GUESS && (k == 0 ? s.guess == 0 : seg[k - 1].end == s.guess && seg[k - 1].guess != NO_GUESS);
-        if (s.bad == 1) regular = false;
-        if (s.bad == 2 && k + 1 != nseg) regular = false;
-        if (!regular) atomicOr(&s_irregular, 1u);
-    }
     __syncthreads();
     if (s_bad) {                                    // a member did not inflate: nothing of this window is used
         if (t == 0) {
@@ -86,19 +96,55 @@ __global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __re
         }
         return;
     }
+    // nearest earlier segment with a guess (index + 1; 0 = none), by a max-scan
+    for (uint32_t k0 = 0; k0 < nseg; k0 += blockDim.x) {
+        const uint32_t k = k0 + t;
+        Segment s;
+        s.guess = NO_GUESS; s.end = 0; s.count = 0; s.bad = 0;
+        if (k < nseg) s = seg[k];
+        const bool has = s.guess != NO_GUESS;
+        uint32_t total;
+        const uint32_t inc = block_max_scan(has ? k + 1 : 0, s_warp, &total);
+        __shared__ uint32_t s_inc[1024];
+        s_inc[t] = inc;
+        __syncthreads();
+        const uint32_t prev = max(t ? s_inc[t - 1] : 0u, s_carry);          // exclusive: segments before k, earlier rounds included
+        if (k < nseg) {
+            bool regular;
+            if (has) {
+                regular = prev ? seg[prev - 1].end == s.guess : s.guess == 0;
+                if (s.bad == 1) regular = false;
+            } else regular = prev != 0 && seg[prev - 1].end >= seg_hi(k, n);
+            if (!regular) atomicOr(&s_irregular, 1u);
+        }
+        __syncthreads();
+        if (t == 0) s_carry = max(s_carry, total);
+        __syncthreads();
+    }
+    if (t == 0) {
+        s_last = s_carry;                           // last segment with a guess (index + 1)
+        s_carry = 0;
+    }
+    __syncthreads();
+    // a chain that stopped at a cut-off record must be the last one
+    for (uint32_t k = t; k < nseg; k += blockDim.x)
+        if (seg[k].guess != NO_GUESS && seg[k].bad == 2 && k + 1 != s_last) atomicOr(&s_irregular, 1u);
+    __syncthreads();
     if (t == 0) {
         if (!s_irregular) {
-            const Segment s = seg[nseg - 1];
-            s_info.tail = s.end;                    // a cut-off record's start, or (fewer than 4 stray bytes aside) the end of the data
-            if (s.bad == 2 && last_window) s_info.err |= E_TRUNCATED;
+            if (s_last) {
+                const Segment s = seg[s_last - 1];
+                s_info.tail = s.end;                // a cut-off record's start, or (fewer than 4 stray bytes aside) the end of the data
+                if (s.bad == 2 && last_window) s_info.err |= E_TRUNCATED;
+            } else s_info.tail = 0;
         } else {
             uint64_t cur = 0;
             bool done = false;
             uint32_t misses = 0;
             for (uint32_t k = 0; k < nseg; ++k) {
-                const uint64_t hi = seg_hi(members, k, nseg, carry, n);
+                const uint64_t hi = seg_hi(k, n);
                 Segment s = seg[k];
-                if (done || cur >= hi) { s.guess = NO_GUESS; s.count = 0; s.end = hi; seg[k] = s; continue; }
+                if (done || cur >= hi) { s.guess = NO_GUESS; s.count = 0; s.end = hi; s.bad = 0; seg[k] = s; continue; }
                 if (s.guess == cur) {
                     if (s.bad == 1) { s_info.err |= E_RECORD; done = true; }
                     if (s.bad == 2) { done = true; s_info.tail = s.end; }
@@ -128,7 +174,7 @@ __global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __re
     // exclusive scan of the counts
     for (uint32_t k0 = 0; k0 < nseg; k0 += blockDim.x) {
         const uint32_t k = k0 + t;
-        const uint32_t v = k < nseg ? seg[k].count : 0;
+        const uint32_t v = k < nseg && seg[k].guess != NO_GUESS ? seg[k].count : 0;
         uint32_t total;
         const uint32_t inc = bdk::ss_block_scan_any(v, s_warp, &total);
         if (k < nseg) base[k] = s_carry + inc - v;
@@ -143,11 +189,12 @@ __global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __re
 }
 
 // One thread per segment: the offsets of the records' cores (behind block_size), in stream order.
-__global__ void __launch_bounds__(64) chain_write_kernel(const uint8_t* __restrict__ raw, const Segment* __restrict__ seg, const uint32_t* __restrict__ base,
-                                                         uint32_t nseg, uint32_t* __restrict__ rec_off) {
+__global__ void __launch_bounds__(128) chain_write_kernel(const uint8_t* __restrict__ raw, const Segment* __restrict__ seg, const uint32_t* __restrict__ base,
+                                                          uint32_t nseg, uint32_t* __restrict__ rec_off) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nseg) return;
     const Segment s = seg[k];
+    if (s.guess == NO_GUESS) return;
     uint64_t o = s.guess;
     uint32_t i = base[k];
     for (uint32_t r = 0; r < s.count; ++r) {

@@ -28,18 +28,16 @@ namespace bgzw {
 using bgz::Bits;
 using bgz::Member;
 
-constexpr int LL_BITS = 10, D_BITS = 8, CL_BITS = 7;
+constexpr int LL_BITS = 11, D_BITS = 9, CL_BITS = 7;
 constexpr int LL_SIZE = 1 << LL_BITS, D_SIZE = 1 << D_BITS;
 constexpr int WARPS_PER_CTA = 8, CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int ERR_CRC = 7;
 
-// entry: bits 0-3 code length (0: no code of at most the index width starts with these bits), bits 4-7 extra bits,
-// bits 8-9 kind, bits 16-31 value (literal byte / base length / base distance)
-enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
-
-struct Tables {                    // one per warp, shared memory: 6080 bytes
-    uint32_t ll[LL_SIZE];
-    uint32_t d[D_SIZE];            // also the code-length code while a dynamic header is read
+// First-level table entry (16 bits): bits 0-3 code length, bits 4-12 symbol; 0 = no code of at most the index width starts with
+// these bits, or the symbol is not a legal one (literal/length 286, 287, distance 30, 31): the slow path sorts that out.
+struct Tables {                    // one per warp, shared memory: 6.1 KB
+    uint16_t ll[LL_SIZE];
+    uint16_t d[D_SIZE];            // also the code-length code while a dynamic header is read
     uint16_t sym_ll[288], sym_d[32];
     uint16_t cnt_ll[16], cnt_d[16];
     uint8_t lens[320];
@@ -59,29 +57,94 @@ struct Tables {                    // one per warp, shared memory: 6080 bytes
 #define BGZW_LANE0(stmt) do { stmt; } while (0)
 #endif
 
-BGZW_HD uint32_t ll_entry(int sym, int len) {
-    if (sym < 256) return (uint32_t)len | (K_LIT << 8) | ((uint32_t)sym << 16);
-    if (sym == 256) return (uint32_t)len | (K_EOB << 8);
-    sym -= 257;
-    if (sym >= 29) return (uint32_t)len | (K_BAD << 8);
-    uint32_t base, extra;
-    if (sym < 8) { base = 3 + sym; extra = 0; }
-    else if (sym == 28) { base = 258; extra = 0; }
-    else { extra = (uint32_t)(sym >> 2) - 1; base = ((4u + (sym & 3)) << extra) + 3; }
-    return (uint32_t)len | (extra << 4) | (K_LEN << 8) | (base << 16);
+// Base value and extra-bit count of length symbols 257.. and distance symbols (RFC 1951 3.2.5): base << 4 | extra
+BGZW_HD uint32_t len_base_extra(uint32_t idx) {                 // idx = symbol - 257, < 29
+    if (idx < 8) return (3 + idx) << 4;
+    if (idx == 28) return 258u << 4;
+    const uint32_t extra = (idx >> 2) - 1;
+    return ((((4u + (idx & 3)) << extra) + 3) << 4) | extra;
 }
-BGZW_HD uint32_t d_entry(int sym, int len) {
-    if (sym >= 30) return (uint32_t)len | (K_BAD << 8);
-    uint32_t base, extra;
-    if (sym < 4) { base = 1 + sym; extra = 0; }
-    else { extra = (uint32_t)(sym >> 1) - 1; base = ((2u + (sym & 1)) << extra) + 1; }
-    return (uint32_t)len | (extra << 4) | (K_LEN << 8) | (base << 16);
+BGZW_HD uint32_t dist_base_extra(uint32_t sym) {                // < 30
+    if (sym < 4) return (1 + sym) << 4;
+    const uint32_t extra = (sym >> 1) - 1;
+    return ((((2u + (sym & 1)) << extra) + 1) << 4) | extra;
 }
+
+// Bit reader of the warp decoder. Device: a window of three consecutive aligned words (lo, hi, hi2) of the input plus one more
+// already requested (ahead); the read position is a bit offset `off` into lo. normalize() slides the window while off >= 32, so
+// behind it 64 + (32 - off) > 64 bits are valid: a whole literal/length code with its extra bits (<= 20 bits, peek()) and a whole
+// distance code with its (<= 28 bits, peek2()) are read without looking at the window again. Extracting is one funnel shift, the
+// 64-bit shift-and-or of a classic bit buffer is gone, and the load of `ahead` has three words of decoding to arrive. The
+// compressed bytes sit in a buffer that is readable a few words beyond every member (its CRC32 / ISIZE footer and the next
+// member follow; bdk_bam.inl pads the last one): words beyond `wlim` are not loaded, a damaged stream that runs on decodes the
+// last word again until one of the over_end() checks or the output bound stops it. Host build (fuzz harness, exact-size buffers
+// under AddressSanitizer): the checked byte-wise reader of bgzf_inflate.cuh behind the same interface.
+#if defined(__CUDA_ARCH__) || defined(BGZW_WINDOW_READER_ON_HOST)
+#define BGZW_WINDOW_READER 1
+#endif
+#ifndef __CUDA_ARCH__
+inline uint32_t bgzw_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+inline uint32_t bgzw_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+#else
+__device__ __forceinline__ uint32_t bgzw_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+__device__ __forceinline__ uint32_t bgzw_min(uint32_t a, uint32_t b) { return min(a, b); }
+#endif
+struct Reader {
+#ifdef BGZW_WINDOW_READER
+    const uint32_t* w0;
+    uint32_t lo, hi, hi2, ahead;
+    uint32_t off;               // bit offset of the read position in lo
+    uint32_t widx, wlim;        // index (from w0) of the word in `ahead`; last index that may be loaded
+    int32_t bits_base;          // bits in front of lo, counted from the byte the window was opened at (negative while lo
+                                // holds bytes in front of it)
+    uint32_t origin;            // that byte's offset in the member (0, or where a stored block ended)
+    BGZW_HD void init(const uint8_t* in, uint32_t n, uint32_t at = 0) {
+        origin = at;
+        const uint32_t mis = (uint32_t)((uintptr_t)in & 3);
+        w0 = (const uint32_t*)(in - mis);
+        wlim = (mis + n + 4) >> 2;                                  // the word that holds in[n + 4], inside the 8-byte footer
+        lo = w0[0]; hi = w0[bgzw_min(1u, wlim)]; hi2 = w0[bgzw_min(2u, wlim)]; ahead = w0[bgzw_min(3u, wlim)];
+        widx = 3;
+        off = 8 * mis;
+        bits_base = -(int32_t)(8 * mis);
+    }
+    BGZW_HD void slide() {
+        lo = hi; hi = hi2; hi2 = ahead;
+        ++widx;
+        ahead = w0[bgzw_min(widx, wlim)];
+        off -= 32; bits_base += 32;
+    }
+    // at most two slides are ever due: off < 32 after a normalize, and no more than 48 bits are dropped before the next one
+    // (written as two tests: left as a loop, the compiler unrolls it sixteen-fold with look-ahead loads)
+    BGZW_HD void normalize() { if (off >= 32) { slide(); if (off >= 32) slide(); } }
+    BGZW_HD uint32_t peek() const { return bgzw_funnel_r(lo, hi, off); }                      // off < 32
+    BGZW_HD uint32_t peek2() const { return off < 32 ? bgzw_funnel_r(lo, hi, off) : bgzw_funnel_r(hi, hi2, off); }   // off < 64
+    BGZW_HD void drop(uint32_t n) { off += n; }
+    BGZW_HD uint32_t take(uint32_t n) { normalize(); const uint32_t v = peek() & ((1u << n) - 1u); off += n; return v; }   // n <= 16
+    BGZW_HD bool over_end(uint32_t in_len) const { return bits_base + (int32_t)off > (int32_t)(8 * (in_len - origin)); }
+    BGZW_HD uint32_t consumed() const { return origin + ((uint32_t)(bits_base + (int32_t)off + 7) >> 3); }    // bytes of the member, a started byte counts
+    BGZW_HD void align_byte() { off = (off + 7) & ~7u; }
+    BGZW_HD void seek(const uint8_t* in, uint32_t at, uint32_t n) { init(in + at, n - at, at); }
+#else
+    Bits b;
+    void init(const uint8_t* in, uint32_t n) { b.in = in; b.n = n; b.pos = 0; b.buf = 0; b.cnt = 0; b.ahead = 0; b.has_ahead = false; }
+    void normalize() { bgz::refill(b); }
+    uint32_t peek() const { return (uint32_t)b.buf; }
+    uint32_t peek2() { bgz::refill(b); return (uint32_t)b.buf; }
+    void drop(uint32_t n) { b.buf >>= n; b.cnt -= (int)n; }
+    uint32_t take(uint32_t n) { bgz::refill(b); return bgz::take(b, (int)n); }
+    bool over_end(uint32_t in_len) const { return b.pos - (uint32_t)(b.cnt >> 3) > in_len; }
+    uint32_t consumed() const { return b.pos - (uint32_t)(b.cnt >> 3); }
+    void align_byte() { drop((uint32_t)(b.cnt & 7)); }
+    void seek(const uint8_t*, uint32_t at, uint32_t) { b.pos = at; b.buf = 0; b.cnt = 0; b.has_ahead = false; }
+#endif
+};
 
 // Canonical decode of the code that starts at bit 0 of `bits` (first bit of the code = bit 0), looking at code lengths up to
 // maxlen. Returns the symbol and its length, or -1.
 BGZW_HD int canonical(uint32_t bits, int maxlen, const uint16_t* cnt, const uint16_t* sym, int* len_out) {
     int code = 0, first = 0, index = 0;
+#pragma unroll 1
     for (int l = 1; l <= maxlen; ++l) {
         code |= (int)((bits >> (l - 1)) & 1);
         const int c = cnt[l];
@@ -94,7 +157,7 @@ BGZW_HD int canonical(uint32_t bits, int maxlen, const uint16_t* cnt, const uint
 
 // Counts per code length and symbols sorted by (length, symbol) for the literal/length code (lanes 0-15: lane = length) and the
 // distance code (lanes 16-31) at once, then the over-subscription / completeness verdict, then the first-level tables.
-// `cl`: build only a code-length code of 19 symbols from T.lens into the distance table (entries sym << 4 | len).
+// `cl`: build only a code-length code of 19 symbols from T.lens into the distance table.
 BGZW_HD bool build_tables(Tables& T, int hlit, int hdist, bool cl) {
     BGZW_PHASE_BEGIN(lane)
         const int l = lane & 15;
@@ -137,18 +200,18 @@ BGZW_HD bool build_tables(Tables& T, int hlit, int hdist, bool cl) {
             for (int i = lane; i < (1 << CL_BITS); i += 32) {
                 int len = 0;
                 const int s = canonical((uint32_t)i, CL_BITS, T.cnt_d, T.sym_d, &len);
-                T.d[i] = s < 0 ? 0u : ((uint32_t)s << 4 | (uint32_t)len);
+                T.d[i] = s < 0 ? (uint16_t)0 : (uint16_t)(s << 4 | len);
             }
         } else {
             for (int i = lane; i < LL_SIZE; i += 32) {
                 int len = 0;
                 const int s = canonical((uint32_t)i, LL_BITS, T.cnt_ll, T.sym_ll, &len);
-                T.ll[i] = s < 0 ? 0u : ll_entry(s, len);
+                T.ll[i] = s < 0 || s > 285 ? (uint16_t)0 : (uint16_t)(s << 4 | len);
             }
             for (int i = lane; i < D_SIZE; i += 32) {
                 int len = 0;
                 const int s = canonical((uint32_t)i, D_BITS, T.cnt_d, T.sym_d, &len);
-                T.d[i] = s < 0 ? 0u : d_entry(s, len);
+                T.d[i] = s < 0 || s > 29 ? (uint16_t)0 : (uint16_t)(s << 4 | len);
             }
         }
     BGZW_PHASE_END()
@@ -156,31 +219,31 @@ BGZW_HD bool build_tables(Tables& T, int hlit, int hdist, bool cl) {
 }
 
 // Inflate one member: exactly out_len bytes from in[0 .. in_len). Called by all 32 lanes of a warp with the same arguments.
+// `out` must be writable for 512 bytes beyond out_len: a damaged stream is stopped at the next window slide or match, not at
+// every literal (the member is then refused; what it scribbled over belongs to a job that fails).
 BGZW_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, Tables& T) {
-    Bits b;
-    b.in = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0; b.ahead = 0; b.has_ahead = false;
+    Reader b;
+    b.init(in, in_len);
     uint32_t op = 0;
     bool last = false;
     while (!last) {
-        bgz::refill(b);
-        last = bgz::take(b, 1) != 0;
-        const uint32_t type = bgz::take(b, 2);
+        if (b.over_end(in_len)) return bgz::ERR_INPUT;
+        last = b.take(1) != 0;
+        const uint32_t type = b.take(2);
         if (type == 3) return bgz::ERR_HEADER;
         if (type == 0) {                                             // stored
-            bgz::take(b, b.cnt & 7);
-            bgz::refill(b);
-            const uint32_t len = bgz::take(b, 16);
-            bgz::refill(b);
-            const uint32_t nlen = bgz::take(b, 16);
+            b.align_byte();
+            const uint32_t len = b.take(16);
+            const uint32_t nlen = b.take(16);
             if ((len ^ 0xffffu) != nlen) return bgz::ERR_HEADER;
-            const uint32_t src = b.pos - (uint32_t)(b.cnt >> 3);     // whole bytes still in the bit buffer belong to the data
-            b.buf = 0; b.cnt = 0;
+            const uint32_t src = b.consumed();                       // whole bytes still in the bit buffer belong to the data
             if (src > in_len || in_len - src < len) return bgz::ERR_INPUT;
-            if (out_len - op < len) return bgz::ERR_OUTPUT;
+            if (op > out_len || out_len - op < len) return bgz::ERR_OUTPUT;
             BGZW_PHASE_BEGIN(lane)
                 for (uint32_t i = (uint32_t)lane; i < len; i += 32) out[op + i] = in[src + i];
             BGZW_PHASE_END()
-            op += len; b.pos = src + len; b.has_ahead = false;
+            op += len;
+            b.seek(in, src + len, in_len);
             continue;
         }
         int hlit = 288, hdist = 32;
@@ -189,9 +252,8 @@ BGZW_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uin
                 for (int i = lane; i < 320; i += 32) T.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
             BGZW_PHASE_END()
         } else {                                                     // dynamic codes
-            bgz::refill(b);
-            hlit = (int)bgz::take(b, 5) + 257; hdist = (int)bgz::take(b, 5) + 1;
-            const int hclen = (int)bgz::take(b, 4) + 4;
+            hlit = (int)b.take(5) + 257; hdist = (int)b.take(5) + 1;
+            const int hclen = (int)b.take(4) + 4;
             if (hlit > 286 || hdist > 30) return bgz::ERR_HEADER;
             BGZW_PHASE_BEGIN(lane)
                 if (lane < 19) T.lens[lane] = 0;
@@ -201,69 +263,80 @@ BGZW_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uin
                 const uint64_t order_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
                 const uint64_t order_hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
                 const int which = (int)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31);
-                bgz::refill(b);
-                const uint8_t v = (uint8_t)bgz::take(b, 3);
+                const uint8_t v = (uint8_t)b.take(3);
                 BGZW_LANE0(T.lens[which] = v);
             }
             if (!build_tables(T, 0, 0, true)) return bgz::ERR_CODES;
             int n = 0, prev = 0;
             while (n < hlit + hdist) {
-                bgz::refill(b);
-                const uint32_t e = T.d[(uint32_t)b.buf & ((1u << CL_BITS) - 1)];
+                b.normalize();
+                const uint32_t e = T.d[b.peek() & ((1u << CL_BITS) - 1)];
                 if (!e) return bgz::ERR_CODES;
-                bgz::take(b, (int)(e & 15));
+                b.drop(e & 15);
                 const int s = (int)(e >> 4);
                 if (s < 16) { BGZW_LANE0(T.lens[n] = (uint8_t)s); prev = s; ++n; continue; }
                 int rep, val = 0;
-                if (s == 16) { if (n == 0) return bgz::ERR_CODES; val = prev; rep = 3 + (int)bgz::take(b, 2); }
-                else if (s == 17) rep = 3 + (int)bgz::take(b, 3);
-                else rep = 11 + (int)bgz::take(b, 7);
+                if (s == 16) { if (n == 0) return bgz::ERR_CODES; val = prev; rep = 3 + (int)b.take(2); }
+                else if (s == 17) rep = 3 + (int)b.take(3);
+                else rep = 11 + (int)b.take(7);
                 if (n + rep > hlit + hdist) return bgz::ERR_CODES;
                 BGZW_PHASE_BEGIN(lane)
                     for (int i = lane; i < rep; i += 32) T.lens[n + i] = (uint8_t)val;
                 BGZW_PHASE_END()
                 n += rep; prev = val;
             }
-            if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return bgz::ERR_INPUT;
+            if (b.over_end(in_len)) return bgz::ERR_INPUT;
         }
         // lens[256] is read by every lane after the barrier that build_tables starts with
         if (!build_tables(T, hlit, hdist, false)) return bgz::ERR_CODES;
         if (T.lens[256] == 0) return bgz::ERR_CODES;
         // ---- the symbols of the block ----
         for (;;) {
-            bgz::refill(b);
-            uint32_t e = T.ll[(uint32_t)b.buf & (LL_SIZE - 1)];
-            if ((e & 15) == 0) {                                     // a code longer than the table index (or none at all)
-                int len = 0;
-                const int s = canonical((uint32_t)b.buf, 15, T.cnt_ll, T.sym_ll, &len);
-                if (s < 0) return bgz::ERR_SYMBOL;
-                e = ll_entry(s, len);
+#ifdef BGZW_WINDOW_READER
+            if (b.off >= 32) {                                       // every 32 bits of input: slide the window, look at the bounds
+                b.normalize();
+                if (op > out_len) return bgz::ERR_OUTPUT;
+                if (b.over_end(in_len)) return bgz::ERR_INPUT;
             }
-            bgz::take(b, (int)(e & 15));
-            const uint32_t kind = (e >> 8) & 3;
-            if (kind == K_LIT) {
-                if (op >= out_len) return bgz::ERR_OUTPUT;
-                BGZW_LANE0(out[op] = (uint8_t)(e >> 16));
+#else
+            b.normalize();
+            if (op > out_len) return bgz::ERR_OUTPUT;
+#endif
+            const uint32_t p = b.peek();
+            uint32_t e = T.ll[p & (LL_SIZE - 1)];
+            if ((e & 15) == 0) {                                     // a code longer than the table index, an illegal symbol, or no code
+                int len = 0;
+                const int s = canonical(p, 15, T.cnt_ll, T.sym_ll, &len);
+                if (s < 0 || s > 285) return bgz::ERR_SYMBOL;
+                e = (uint32_t)(s << 4 | len);
+            }
+            const uint32_t l = e & 15, sym = e >> 4;
+            if (sym < 256) {
+                b.drop(l);
+#ifndef BGZW_WINDOW_READER
+                if (op >= out_len) return bgz::ERR_OUTPUT;           // checked reader: exact buffers; the window reader looks at the bound every 32 input bits
+#endif
+                BGZW_LANE0(out[op] = (uint8_t)sym);
                 ++op;
                 continue;
             }
-            if (kind == K_EOB) break;
-            if (kind == K_BAD) return bgz::ERR_SYMBOL;
-            const uint32_t len = (e >> 16) + bgz::take(b, (int)((e >> 4) & 15));
-            bgz::refill(b);
-            uint32_t f = T.d[(uint32_t)b.buf & (D_SIZE - 1)];
+            if (sym == 256) { b.drop(l); break; }
+            const uint32_t lbe = len_base_extra(sym - 257), lx = lbe & 15;
+            const uint32_t len = (lbe >> 4) + ((p >> l) & ((1u << lx) - 1u));
+            b.drop(l + lx);
+            const uint32_t q = b.peek2();
+            uint32_t f = T.d[q & (D_SIZE - 1)];
             if ((f & 15) == 0) {
                 int dl = 0;
-                const int s = canonical((uint32_t)b.buf, 15, T.cnt_d, T.sym_d, &dl);
-                if (s < 0) return bgz::ERR_DISTANCE;
-                f = d_entry(s, dl);
+                const int s = canonical(q, 15, T.cnt_d, T.sym_d, &dl);
+                if (s < 0 || s > 29) return bgz::ERR_DISTANCE;
+                f = (uint32_t)(s << 4 | dl);
             }
-            bgz::take(b, (int)(f & 15));
-            if (((f >> 8) & 3) == K_BAD) return bgz::ERR_DISTANCE;
-            const uint32_t dist = (f >> 16) + bgz::take(b, (int)((f >> 4) & 15));
+            const uint32_t dl = f & 15, dbe = dist_base_extra(f >> 4), dx = dbe & 15;
+            const uint32_t dist = (dbe >> 4) + ((q >> dl) & ((1u << dx) - 1u));
+            b.drop(dl + dx);
             if (dist > op) return bgz::ERR_DISTANCE;
-            if (len > out_len - op) return bgz::ERR_OUTPUT;
-            if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return bgz::ERR_INPUT;      // ran past the end of the input a while ago
+            if (op + len > out_len) return bgz::ERR_OUTPUT;
             // byte j of the match is byte (j mod dist) of the `dist` bytes before it: every lane reads bytes that were complete
             // before this match began (the barrier that opens the phase orders them after the stores of all lanes)
             BGZW_PHASE_BEGIN(lane)
@@ -274,7 +347,7 @@ BGZW_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uin
             op += len;
         }
     }
-    if (b.pos - (uint32_t)(b.cnt >> 3) > in_len) return bgz::ERR_INPUT;
+    if (b.over_end(in_len)) return bgz::ERR_INPUT;
     return op == out_len ? bgz::OK : bgz::ERR_OUTPUT;
 }
 

@@ -342,7 +342,10 @@ typedef struct bdk_bam_stats {
     uint32_t windows;
     uint32_t guess_misses;            /* record-boundary guesses that were wrong or missing (resolved exactly, see bam_decode.cuh) */
     int32_t sorted;                   /* 1 iff the kept records are ordered by (reference sequence, position) */
-    float inflate_ms, chain_ms, extract_ms;   /* device time of the inflate + CRC kernels, the boundary search, the extraction */
+    float inflate_ms, chain_ms, extract_ms;   /* device time: first inflate launch to the end of the last one (windows overlap);
+                                                 the boundary search; the filter + extraction */
+    float stage_ms;                   /* host time of the producer thread copying file bytes into its pinned staging buffers */
+    float wall_ms;                    /* the whole call */
 } bdk_bam_stats;
 int bdk_push_bam(bdk_ctx* ctx, const bdk_bam_source* src, bdk_bam_stats* stats);
 /* The same decode, but the columns come back to the HOST (arrays of `cap` records the caller owns, written through the const

@@ -38,7 +38,7 @@ for it in range(4):
     dt = time.perf_counter() - t0
     kt = ctx.kernel_times()
     runs.append({"push_bam_s": round(dt, 4), "inflate_ms": round(st["inflate_ms"], 2), "chain_ms": round(st["chain_ms"], 2), "extract_ms": round(st["extract_ms"], 2),
-                 "k1_ms": round(kt["k1_classify"]["ms"], 3), "windows": st["windows"], "guess_misses": st["guess_misses"], "records": st["records"], "kept": st["kept"],
+                 "stage_ms": round(st["stage_ms"], 2), "wall_ms": round(st["wall_ms"], 2), "k1_ms": round(kt["k1_classify"]["ms"], 3), "windows": st["windows"], "guess_misses": st["guess_misses"], "records": st["records"], "kept": st["kept"],
                  "inflate_GBps_out": round(st["inflated_bytes"] / 1e6 / max(st["inflate_ms"], 1e-6), 2), "pairs_per_s": round(st["kept"] / 2 / dt)})
 table = ctx.finish()
 out["in_process_device"] = runs

@@ -98,15 +98,22 @@ def report(tag, rep):
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         return x * scale.get(u, 1)
     if "k1_classify" in kname:
+        # DRAM bytes of ONE launch of the classify kernel, with the workload it was captured on (records of the launch from the
+        # bench line of the same command) and a digest of the kernel's sources: bench.py reports it as roofline.traffic only for
+        # the same workload and the same sources (profiles/k1_traffic.json = configs[1], k1_traffic_config3.json = configs[2]).
         total = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        c3 = "config3" in os.path.basename(rep)
         n = None
         try:
-            n = json.load(open(os.path.join(ROOT, "gpurun_out", f"bench_{tag}.json")))["config"]["records_per_gpu"]
+            n = json.load(open(os.path.join(ROOT, "gpurun_out", f"bench_c3_{tag}.json" if c3 else f"bench_{tag}.json")))["config"]["records_per_gpu"]
         except Exception:
             pass
         if n:
-            json.dump({"tag": tag, "dram_bytes": total, "records": n, "dram_bytes_per_record": total / n,
-                       "source": os.path.basename(rep)}, open(os.path.join(ROOT, "profiles", "k1_traffic.json"), "w"), indent=1)
+            sys.path.insert(0, ROOT)
+            from bench import k1_source_digest
+            json.dump({"tag": tag, "dram_bytes": total, "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_written": num("dram__bytes_write.sum"),
+                       "records": n, "dram_bytes_per_record": total / n, "kernel": kname[:80], "k1_source_digest": k1_source_digest(),
+                       "source": os.path.basename(rep)}, open(os.path.join(ROOT, "profiles", "k1_traffic_config3.json" if c3 else "k1_traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

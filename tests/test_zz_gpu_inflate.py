@@ -29,6 +29,22 @@ def test_member_decoder_differential_and_corruption_fuzz_on_the_host():
     assert "refused_good=0 mismatched=0" in p.stdout, p.stdout
 
 
+def test_warp_member_decoder_and_sliced_crc_fuzz_on_the_host():
+    """bgzf_inflate_warp.cuh (the decoder of the device-resident BAM decode): the 32 lanes of a phase run one after the other on
+    the host; once with the checked byte-wise bit reader and once with the device's word-window reader (member at every alignment
+    inside a buffer shaped like the device's, 512 bytes of output slack)."""
+    src = os.path.join(util.ROOT, "tests", "hostsim", "gpu_inflate_warp_host.cpp")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    os.makedirs(os.path.join(util.ROOT, "tests", "_build"), exist_ok=True)
+    for flag, name in (([], "gpu_inflate_warp_host"), (["-DBGZW_WINDOW_READER_ON_HOST"], "gpu_inflate_warp_host_w")):
+        exe = os.path.join(util.ROOT, "tests", "_build", name)
+        subprocess.check_call([cxx, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer",
+                               *flag, src, "-o", exe, "-lz"])
+        p = subprocess.run([exe, "400"], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout + p.stderr
+        assert "refused_good=0 mismatched=0 crc_bad=0" in p.stdout, p.stdout
+
+
 def _members(data: bytes):
     """(in_off, in_len, out_len) of every BGZF member of a file image."""
     out, off = [], 0
