@@ -47,43 +47,29 @@ __global__ void __launch_bounds__(128) chain_guess_kernel(const uint8_t* __restr
     seg[k] = brec::segment_guess(raw, n, seg_lo(k), seg_hi(k, n), k == 0, nref);
 }
 
-// inclusive max-scan of one value per thread across a block of up to 1024 threads; s_warp: [33]
-__device__ __forceinline__ uint32_t block_max_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = max(inc, t); }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = lane < nw ? s_warp[lane] : 0, wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, wi, d); if (lane >= d) wi = max(wi, t); }
-        const uint32_t excl = __shfl_up_sync(FULL, wi, 1);
-        s_warp[lane] = lane ? excl : 0;
-        if (lane == 31) s_warp[32] = wi;
-    }
-    __syncthreads();
-    inc = max(inc, s_warp[warp]);
-    *total = s_warp[32];
-    __syncthreads();
-    return inc;
+// neighbours read a segment while its owner rewrites it (rounds of chain_resolve_kernel): two 16-byte halves, each consistent
+__device__ __forceinline__ void seg_store(Segment* p, const Segment& s) {
+    volatile uint64_t* q = reinterpret_cast<volatile uint64_t*>(p);
+    q[0] = s.guess; q[1] = s.end; q[2] = (uint64_t)s.count | ((uint64_t)s.bad << 32);
 }
 
-// One CTA. Member verdicts, the check of the guesses (in parallel; a serial walk by one thread only where the picture is not
-// the regular one), the records before every segment (base[k], exclusive scan of the counts) and the window's WinInfo.
-// Regular picture: every segment in which a record starts guessed that start right -- its guess is where the chain of the
-// nearest earlier segment with a guess ends (the first segment starts on a record by construction) -- segments without a guess
-// lie inside a record that began earlier, no chain met a broken record, and only the last chain may stop at a cut-off record.
+// One CTA. Member verdicts, the check of the guesses, the records before every segment (base[k], exclusive scan of the counts)
+// and the window's WinInfo.
+// The chain enters segment k where it left segment k - 1 (segment 0 at byte 0, a record start by construction). Rounds over all
+// segments in parallel: a segment that does not stand where its predecessor's chain ends is walked again from there (at most a
+// segment's worth of records) -- but only once the predecessor itself stands where ITS predecessor ends, so a wrong guess never
+// sends its neighbours off. A round that finds nothing to do proves the picture is the serial chain (the lowest segment out of
+// place always has a predecessor in place, so it moves). Right guesses need one round; a wrong or missing guess two; a run of
+// m wrong segments in a row (decoy records, a record spanning m segments) m + 1. If the rounds do not settle, one thread follows
+// the chain through the window. Checked against the serial chain on the host (tests/hostsim/bam_chain_rounds.cpp).
 __global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint32_t nseg, uint32_t nmem, int last_window,
                                                              const int32_t* __restrict__ status, Segment* __restrict__ seg, uint32_t* __restrict__ base,
                                                              WinInfo* __restrict__ info, uint32_t* __restrict__ nrec_out) {
     __shared__ uint32_t s_warp[33];
-    __shared__ uint32_t s_irregular, s_bad, s_first_bad, s_carry, s_last;
+    __shared__ uint32_t s_changed, s_bad, s_first_bad, s_carry, s_misses, s_flags;
     __shared__ WinInfo s_info;
     const uint32_t t = threadIdx.x;
-    if (t == 0) { s_irregular = 0; s_bad = 0; s_first_bad = 0xffffffffu; s_carry = 0; s_last = 0; s_info.tail = n; s_info.err = 0; s_info.guess_misses = 0; }
+    if (t == 0) { s_changed = 0; s_bad = 0; s_first_bad = 0xffffffffu; s_carry = 0; s_misses = 0; s_flags = 0; s_info.tail = n; s_info.err = 0; s_info.guess_misses = 0; }
     __syncthreads();
     for (uint32_t k = t; k < nmem; k += blockDim.x)
         if (status[k] != 0) { atomicAdd(&s_bad, 1u); atomicMin(&s_first_bad, k); }
@@ -96,85 +82,52 @@ __global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __re
         }
         return;
     }
-    // nearest earlier segment with a guess (index + 1; 0 = none), by a max-scan
-    for (uint32_t k0 = 0; k0 < nseg; k0 += blockDim.x) {
-        const uint32_t k = k0 + t;
-        Segment s;
-        s.guess = NO_GUESS; s.end = 0; s.count = 0; s.bad = 0;
-        if (k < nseg) s = seg[k];
-        const bool has = s.guess != NO_GUESS;
-        uint32_t total;
-        const uint32_t inc = block_max_scan(has ? k + 1 : 0, s_warp, &total);
-        __shared__ uint32_t s_inc[1024];
-        s_inc[t] = inc;
-        __syncthreads();
-        const uint32_t prev = max(t ? s_inc[t - 1] : 0u, s_carry);          // exclusive: segments before k, earlier rounds included
-        if (k < nseg) {
-            bool regular;
-            if (has) {
-                regular = prev ? seg[prev - 1].end == s.guess : s.guess == 0;
-                if (s.bad == 1) regular = false;
-            } else regular = prev != 0 && seg[prev - 1].end >= seg_hi(k, n);
-            if (!regular) atomicOr(&s_irregular, 1u);
+    bool settled = false;
+    for (int round = 0; round < 96 && !settled; ++round) {
+        for (uint32_t k = 1 + t; k < nseg; k += blockDim.x) {
+            const Segment prev = seg[k - 1];
+            const Segment s = seg[k];
+            if (brec::segment_in_place(s, prev)) continue;
+            s_changed = 1;
+            // repair from the predecessor's end only if the predecessor itself stands where its own predecessor left the chain:
+            // the end of a wrongly guessed chain can lie anywhere, and walking on from it would push the error down the window
+            if (k > 1 && !brec::segment_in_place(prev, seg[k - 2])) continue;
+            seg_store(seg + k, brec::segment_after(raw, n, seg_hi(k, n), prev));
+            atomicAdd(&s_misses, 1u);
         }
         __syncthreads();
-        if (t == 0) s_carry = max(s_carry, total);
+        settled = s_changed == 0;
+        __syncthreads();
+        if (t == 0) s_changed = 0;
         __syncthreads();
     }
-    if (t == 0) {
-        s_last = s_carry;                           // last segment with a guess (index + 1)
-        s_carry = 0;
-    }
-    __syncthreads();
-    // a chain that stopped at a cut-off record must be the last one
-    for (uint32_t k = t; k < nseg; k += blockDim.x)
-        if (seg[k].guess != NO_GUESS && seg[k].bad == 2 && k + 1 != s_last) atomicOr(&s_irregular, 1u);
-    __syncthreads();
-    if (t == 0) {
-        if (!s_irregular) {
-            if (s_last) {
-                const Segment s = seg[s_last - 1];
-                s_info.tail = s.end;                // a cut-off record's start, or (fewer than 4 stray bytes aside) the end of the data
-                if (s.bad == 2 && last_window) s_info.err |= E_TRUNCATED;
-            } else s_info.tail = 0;
-        } else {
-            uint64_t cur = 0;
-            bool done = false;
-            uint32_t misses = 0;
-            for (uint32_t k = 0; k < nseg; ++k) {
-                const uint64_t hi = seg_hi(k, n);
-                Segment s = seg[k];
-                if (done || cur >= hi) { s.guess = NO_GUESS; s.count = 0; s.end = hi; s.bad = 0; seg[k] = s; continue; }
-                if (s.guess == cur) {
-                    if (s.bad == 1) { s_info.err |= E_RECORD; done = true; }
-                    if (s.bad == 2) { done = true; s_info.tail = s.end; }
-                    cur = s.end;
-                    continue;
-                }
-                ++misses;
-                uint64_t o = cur;
-                uint32_t cnt = 0;
-                while (o + 4 <= n && o < hi) {
-                    const uint32_t bs = brec::ld32(raw + o);
-                    if (bs < 32) { s_info.err |= E_RECORD; done = true; break; }
-                    if (o + 4 + (uint64_t)bs > n) { done = true; s_info.tail = o; break; }
-                    ++cnt;
-                    o += 4 + (uint64_t)bs;
-                }
-                s.guess = cur; s.count = cnt; s.end = o; s.bad = 0;
-                seg[k] = s;
-                cur = o;
+    if (!settled && t == 0) {                       // one thread, the chain from the start
+        uint64_t cur = 0;
+        uint32_t ended = 0;
+        for (uint32_t k = 0; k < nseg; ++k) {
+            const uint64_t hi = seg_hi(k, n);
+            Segment s;
+            s.guess = cur; s.count = 0; s.bad = ended;
+            uint64_t o = cur;
+            while (!ended && o + 4 <= n && o < hi) {
+                const uint32_t bs = brec::ld32(raw + o);
+                if (bs < 32) { ended = 1; break; }
+                if (o + 4 + (uint64_t)bs > n) { ended = 2; break; }
+                ++s.count;
+                o += 4 + (uint64_t)bs;
             }
-            if (!done) s_info.tail = cur;
-            else if (last_window && !(s_info.err & E_RECORD)) s_info.err |= E_TRUNCATED;
-            s_info.guess_misses = misses;
+            s.end = o; s.bad = ended;
+            seg[k] = s;
+            cur = o;
         }
+        s_misses += nseg;
     }
     __syncthreads();
-    // exclusive scan of the counts
+    // what the chain met, and the exclusive scan of the counts
     for (uint32_t k0 = 0; k0 < nseg; k0 += blockDim.x) {
         const uint32_t k = k0 + t;
-        const uint32_t v = k < nseg && seg[k].guess != NO_GUESS ? seg[k].count : 0;
+        uint32_t v = 0;
+        if (k < nseg) { const Segment s = seg[k]; v = s.count; if (s.bad) atomicOr(&s_flags, s.bad == 1 ? 1u : 2u); }
         uint32_t total;
         const uint32_t inc = bdk::ss_block_scan_any(v, s_warp, &total);
         if (k < nseg) base[k] = s_carry + inc - v;
@@ -183,6 +136,10 @@ __global__ void __launch_bounds__(1024) chain_resolve_kernel(const uint8_t* __re
         __syncthreads();
     }
     if (t == 0) {
+        s_info.tail = nseg ? seg[nseg - 1].end : 0;  // a cut-off record's start, or (fewer than 4 stray bytes aside) the end of the data
+        if (s_flags & 1u) s_info.err |= E_RECORD;
+        else if ((s_flags & 2u) && last_window) s_info.err |= E_TRUNCATED;
+        s_info.guess_misses = s_misses;
         s_info.nrec = s_carry; s_info.bad_members = 0; s_info.first_bad_member = 0; s_info.first_bad_status = 0;
         *info = s_info; *nrec_out = s_carry;
     }

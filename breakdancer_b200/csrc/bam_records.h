@@ -175,6 +175,31 @@ BREC_HD bool segment_consistent(const Segment* seg, uint32_t k, uint32_t nseg, u
     return seg[k].end + 4 > n;
 }
 
+// ---- repair rounds (bam_decode.cuh chain_resolve_kernel; tests/hostsim/bam_chain_rounds.cpp runs the same two functions) ----
+// Does segment `cur` stand where `prev` left the chain? A chain that met a broken or cut-off record ends there: the segments
+// behind it are empty and carry its end and verdict on.
+BREC_HD bool segment_in_place(const Segment& cur, const Segment& prev) {
+    if (cur.guess != prev.end) return false;
+    if (prev.bad) return cur.count == 0 && cur.end == prev.end && cur.bad == prev.bad;
+    return true;
+}
+// The segment that ends at `hi`, entered where `prev` left the chain.
+BREC_HD Segment segment_after(const uint8_t* raw, uint64_t n, uint64_t hi, const Segment& prev) {
+    Segment s;
+    s.guess = prev.end; s.end = prev.end; s.count = 0; s.bad = prev.bad;
+    if (prev.bad) return s;
+    uint64_t o = prev.end;
+    while (o + 4 <= n && o < hi) {
+        const uint32_t bs = ld32(raw + o);
+        if (bs < 32) { s.bad = 1; break; }
+        if (o + 4 + (uint64_t)bs > n) { s.bad = 2; break; }
+        ++s.count;
+        o += 4 + (uint64_t)bs;
+    }
+    s.end = o;
+    return s;
+}
+
 struct RegionSel { int on, tid, beg, end; };
 
 // The reader's filter: primary records placed on a reference sequence (BamIo.cpp:11-18) and, with -o, bam_iter_read's

@@ -354,3 +354,47 @@ def test_windowed_decode_equals_the_whole_file_decode(tmp_path, monkeypatch):
                 api.BamStream(cfg_cut, threads=4)
     finally:
         os.chdir(cwd)
+
+
+def test_repair_rounds_of_the_device_record_chain_reach_the_serial_chain(tmp_path):
+    """The rule chain_resolve_kernel (csrc/bam_decode.cuh) uses on the GPU -- 8 KiB segments guess their first record, a segment
+    out of place is re-entered from its predecessor's end once the predecessor is in place -- run on the host with the same
+    bam_records.h functions, on generated records, on records that contain decoy records, with a cut-off last record and with
+    spoiled guesses (singly, in runs, at the window's end): always the serial chain, in a few rounds."""
+    import struct
+    import subprocess
+    import zlib
+    exe = os.path.join(util.ROOT, "tests", "_build", "bam_chain_rounds")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", os.path.join(util.ROOT, "tests", "hostsim", "bam_chain_rounds.cpp"), "-o", exe])
+
+    def record_bytes(path):
+        data = open(path, "rb").read()
+        out, off = bytearray(), 0
+        while off + 18 <= len(data):
+            xlen = struct.unpack_from("<H", data, off + 10)[0]
+            bsize = struct.unpack_from("<H", data, off + 16)[0] + 1
+            out += zlib.decompress(data[off + 12 + xlen:off + bsize - 8], -15)
+            off += bsize
+        o = 8 + struct.unpack_from("<I", out, 4)[0]
+        nref = struct.unpack_from("<I", out, o)[0]
+        o += 4
+        for _ in range(nref):
+            o += 4 + struct.unpack_from("<I", out, o)[0] + 4
+        return bytes(out[o:]), nref
+
+    w = synth.generate(util.GENOME3, util.LIBS4, 60000, seed=8, anomaly_frac=0.05)
+    bam, cols = sorted(synth.split_by_bam(w).items())[0]
+    api.write_bam(str(tmp_path / bam), [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, cols, level=1)
+    recs, _ = _decoy_records(n=3000)
+    (tmp_path / "decoy.bam").write_bytes(_handmade_bam(recs))
+    for name in (bam, "decoy.bam"):
+        raw, nref = record_bytes(str(tmp_path / name))
+        (tmp_path / "raw.bin").write_bytes(raw)
+        nseg = (len(raw) + 8191) // 8192
+        for cut, spoiled in ((0, []), (777, []), (0, [1, 2, 3, 4, 5]), (50, [nseg // 2]), (3, [nseg - 1, nseg - 2]), (0, list(range(7, nseg, 11)))):
+            p = subprocess.run([exe, str(tmp_path / "raw.bin"), str(nref), str(cut)] + [str(k) for k in spoiled], capture_output=True, text=True)
+            assert p.returncode == 0 and " OK" in p.stdout, (name, cut, spoiled[:5], p.stdout)
+            rounds = int(p.stdout.split("rounds=")[1].split()[0])
+            assert rounds <= len(spoiled) + 40, p.stdout
