@@ -127,7 +127,8 @@ class BamStats(C.Structure):
     """bdk_bam_stats (include/bdk.h)."""
     _fields_ = [("records", C.c_uint64), ("kept", C.c_uint64), ("h2d_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
                 ("windows", C.c_uint32), ("guess_misses", C.c_uint32), ("sorted", C.c_int32),
-                ("inflate_ms", C.c_float), ("chain_ms", C.c_float), ("extract_ms", C.c_float), ("stage_ms", C.c_float), ("wall_ms", C.c_float)]
+                ("inflate_ms", C.c_float), ("chain_ms", C.c_float), ("extract_ms", C.c_float), ("stage_ms", C.c_float), ("wall_ms", C.c_float),
+                ("merge_parts", C.c_uint32), ("merge_longest_part", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -226,6 +227,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdh_bamdev_file_bytes": (u64, [vp]),
         "bdh_bamdev_push": (C.c_int, [vp, vp, C.POINTER(BamStats)]),
         "bdh_bamdev_decode": (C.c_int, [vp, vp, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
+        "bdh_bamdev_open_next": (vp, [vp, vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+        "bdh_bamdev_push2": (C.c_int, [vp, vp, vp, C.POINTER(BamStats)]),
+        "bdh_bamdev_decode2": (C.c_int, [vp, vp, vp, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
+        "bdk_push_bams": (C.c_int, [vp, C.POINTER(BamSource), C.c_int, C.POINTER(BamStats)]),
+        "bdk_decode_bams": (C.c_int, [vp, C.POINTER(BamSource), C.c_int, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
         "bdk_decode_bam": (C.c_int, [vp, C.POINTER(BamSource), C.POINTER(Soa), u64, C.POINTER(BamStats)]),
         "bdk_bgzf_inflate": (C.c_int, [C.c_int, C.c_void_p, u64, C.c_void_p, u64, C.c_void_p, u64, C.POINTER(i32), C.POINTER(C.c_float)]),
         "bdh_config_parse": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
@@ -394,10 +400,13 @@ class BamDevice:
     """One BAM file opened for the device-resident decode (bdh_bamdev_*, include/bdk_host.h): the host maps the file, lists
     its BGZF members and parses the header; Context.push_bam() then inflates, parses and classifies it on the GPU."""
 
-    def __init__(self, cfg: BamConfig, path: str = "", region: str = ""):
+    def __init__(self, cfg: BamConfig, path: str = "", region: str = "", after: Optional["BamDevice"] = None):
         L = load_library()
         err = C.create_string_buffer(512)
-        h = L.bdh_bamdev_open(cfg._h, path.encode(), region.encode(), err, 512)
+        if after is not None:       # the second bam of a two-bam run: read-group ids behind the first bam's
+            h = L.bdh_bamdev_open_next(cfg._h, after._h, path.encode(), region.encode(), err, 512)
+        else:
+            h = L.bdh_bamdev_open(cfg._h, path.encode(), region.encode(), err, 512)
         if not h:
             raise RuntimeError(err.value.decode())
         self._h, self._L, self.cfg = h, L, cfg
@@ -547,6 +556,21 @@ class Context:
         st = BamStats()
         self._check(self._L.bdh_bamdev_push(dev._h, self._h, C.byref(st)), "bdk_push_bam")
         return st.as_dict()
+
+    def push_bams(self, first: "BamDevice", second: "BamDevice"):
+        """Two bams decoded on this GPU, merged there in BamMerger's order and classified (bdk_push_bams); the two stats dicts."""
+        st = (BamStats * 2)()
+        self._check(self._L.bdh_bamdev_push2(first._h, second._h, self._h, st), "bdk_push_bams")
+        return st[0].as_dict(), st[1].as_dict()
+
+    def decode_bams(self, first: "BamDevice", second: "BamDevice", cap: int):
+        """The merged records of two bams as host columns (bdk_decode_bams): (columns, stats of the two files)."""
+        cols = {k: np.empty(cap, dt) for k, dt in COLUMN_DTYPES.items()}
+        soa = make_soa(cols)
+        st = (BamStats * 2)()
+        self._check(self._L.bdh_bamdev_decode2(first._h, second._h, self._h, C.byref(soa), cap, st), "bdk_decode_bams")
+        n = st[0].kept + st[1].kept
+        return {k: v[:n] for k, v in cols.items()}, (st[0].as_dict(), st[1].as_dict())
 
     def decode_bam(self, dev: "BamDevice", cap: int):
         """The file's records decoded on this GPU, as host columns (bdk_decode_bam): (columns, stats)."""

@@ -62,12 +62,23 @@ struct BamWindow { uint64_t m0, m1, in_begin, in_bytes, out_begin, out_bytes; ui
 
 void bamdev_release(void* p) { bamdev_free((BamDev*)p); }
 
-// host_out == nullptr: classify the records (bdk_push_bam); else copy the decoded columns into the caller's host arrays of
-// `cap` records and classify nothing (bdk_decode_bam).
-int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, const bdk_soa* host_out, uint64_t cap) {
+// the decoded records of one whole bam, kept on the device (two-bam runs: bdk_push_bams)
+struct BamCollect {
+    DevBuf cols[10];
+    uint64_t n = 0;
+    bamdev::Columns view() const {
+        return bamdev::Columns{cols[0].as<int32_t>(), cols[1].as<int32_t>(), cols[2].as<int32_t>(), cols[3].as<int32_t>(), cols[4].as<int32_t>(),
+                               cols[8].as<int32_t>(), cols[5].as<uint16_t>(), cols[7].as<uint16_t>(), cols[6].as<uint8_t>(), cols[9].as<uint64_t>()};
+    }
+    void release() { for (auto& b : cols) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; } n = 0; }
+};
+
+// host_out == nullptr && collect == nullptr: classify the records (bdk_push_bam); host_out: copy the decoded columns into the
+// caller's host arrays of `cap` records and classify nothing (bdk_decode_bam); collect: keep them on the device (bdk_push_bams).
+int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, const bdk_soa* host_out, uint64_t cap, BamCollect* collect = nullptr) {
     if (!c || !src) return BDK_ERR_ARG;
     if (stats) memset(stats, 0, sizeof *stats);
-    if (c->finished && !host_out) return fail(c, BDK_ERR_STATE, "bdk_push_bam after bdk_finish (call bdk_reset first)");
+    if (c->finished && !host_out && !collect) return fail(c, BDK_ERR_STATE, "bdk_push_bam after bdk_finish (call bdk_reset first)");
     if (!src->file || (!src->members && src->n_members)) return fail(c, BDK_ERR_ARG, "null file image or member list");
     if (src->n_rg && (!src->rg_hash || !src->rg_id)) return fail(c, BDK_ERR_ARG, "null read-group table");
     if (src->n_ref < 0) return fail(c, BDK_ERR_ARG, "n_ref < 0");
@@ -167,7 +178,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
         // them (it knows a window's record count before it extracts)
         const uint64_t guess = std::min<uint64_t>(max_rec, max_n / 96 + 1024);
         ENS(B->d_recoff, guess * 4);
-        for (int k = 0; k < 10; ++k) ENS(B->d_cols[k], guess * width[k]);
+        if (!collect) for (int k = 0; k < 10; ++k) ENS(B->d_cols[k], guess * width[k]);
     }
     // read-group table: open addressing, at most half full
     uint32_t rg_slots = 16;
@@ -323,11 +334,21 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
             uint32_t kept = 0;
             if (nrec) {
                 ENS(B->d_recoff, (size_t)nrec * 4);
-                for (int k = 0; k < 10; ++k) ENS(B->d_cols[k], (size_t)nrec * width[k]);
+                bamdev::Columns cols;
+                if (collect) {              // behind what the bam's columns hold; sized once from the first window's record density
+                    uint64_t want = kept_total + nrec;
+                    if (want * 4 > collect->cols[0].cap && n) want = std::max<uint64_t>(want, (uint64_t)((double)nrec / (double)n * (double)(end_off - src->first_record) * 1.03) + 65536);
+                    for (int k = 0; k < 10; ++k) { int erc = ensure(c, collect->cols[k], (size_t)want * width[k], true); if (erc) return erc; }
+                    const bamdev::Columns v = collect->view();
+                    cols = bamdev::Columns{v.pos + kept_total, v.mpos + kept_total, v.tid + kept_total, v.mtid + kept_total, v.isize + kept_total, v.qlen + kept_total,
+                                           v.flag + kept_total, v.rgid + kept_total, v.mapq + kept_total, v.qid + kept_total};
+                } else {
+                    for (int k = 0; k < 10; ++k) ENS(B->d_cols[k], (size_t)nrec * width[k]);
+                    cols = bamdev::Columns{B->d_cols[0].as<int32_t>(), B->d_cols[1].as<int32_t>(), B->d_cols[2].as<int32_t>(), B->d_cols[3].as<int32_t>(), B->d_cols[4].as<int32_t>(),
+                                           B->d_cols[8].as<int32_t>(), B->d_cols[5].as<uint16_t>(), B->d_cols[7].as<uint16_t>(), B->d_cols[6].as<uint8_t>(), B->d_cols[9].as<uint64_t>()};
+                }
                 tstart(c, T_EXTRACT);
                 bamdev::chain_write_kernel<<<div_up<uint32_t>(nseg, 128), 128, 0, c->stream>>>(raw, seg, B->d_base.as<uint32_t>(), nseg, B->d_recoff.as<uint32_t>());
-                bamdev::Columns cols{B->d_cols[0].as<int32_t>(), B->d_cols[1].as<int32_t>(), B->d_cols[2].as<int32_t>(), B->d_cols[3].as<int32_t>(), B->d_cols[4].as<int32_t>(),
-                                     B->d_cols[8].as<int32_t>(), B->d_cols[5].as<uint16_t>(), B->d_cols[7].as<uint16_t>(), B->d_cols[6].as<uint8_t>(), B->d_cols[9].as<uint64_t>()};
                 const brec::RegionSel sel{src->region_on, src->region_tid, src->region_beg, src->region_end};
                 device_scan(c->stream, bamdev::KeepFlag{raw, B->d_recoff.as<uint32_t>(), sel},
                             bamdev::ExtractOut{raw, B->d_recoff.as<uint32_t>(), B->d_rgtab.as<bamdev::RgEntry>(), rg_slots, src->rg_other, cols},
@@ -347,6 +368,8 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
                     for (int k = 0; k < 10; ++k)
                         CU(cudaMemcpyAsync((char*)dst[k] + kept_total * width[k], B->d_cols[k].p, (size_t)kept * width[k], cudaMemcpyDeviceToHost, c->stream));
                     CU(cudaStreamSynchronize(c->stream));
+                } else if (kept && collect) {
+                    collect->n = kept_total + kept;
                 } else if (kept) {
                     bdk_soa d;
                     d.pos = cols.pos; d.mpos = cols.mpos; d.tid = cols.tid; d.mtid = cols.mtid; d.isize = cols.isize; d.flag = cols.flag; d.mapq = cols.mapq;
@@ -403,6 +426,98 @@ extern "C" {
 uint64_t bdk_hash_bytes(const void* p, uint64_t n) { return brec::hash_bytes((const uint8_t*)p, (size_t)n); }
 
 int bdk_push_bam(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats) { return bam_pipeline(c, src, stats, nullptr, 0); }
+
+// Two bams of one config, decoded on the device one after the other, merged in the reference's order (bam_merge.cuh) and
+// classified; host_out != nullptr: the merged columns go to the host instead (tests). srcs[0] must be the config's first bam.
+static int push_two_bams(bdk_ctx* c, const bdk_bam_source* srcs, bdk_bam_stats* stats, const bdk_soa* host_out, uint64_t cap) {
+    static const size_t width[10] = {4, 4, 4, 4, 4, 2, 1, 2, 4, 8};
+    BamCollect col[2], merged;
+    DevBuf d_k[2], d_cutx, d_cuty, d_partx, d_party, d_order, d_small;
+    auto cleanup = [&]() {
+        col[0].release(); col[1].release(); merged.release();
+        for (DevBuf* b : {&d_k[0], &d_k[1], &d_cutx, &d_cuty, &d_partx, &d_party, &d_order, &d_small}) if (b->p) { cudaFree(b->p); b->p = nullptr; }
+    };
+    bdk_bam_stats local_stats[2];
+    if (!stats) stats = local_stats;
+    auto run = [&]() -> int {
+        for (int b = 0; b < 2; ++b) {
+            const int rc = bam_pipeline(c, &srcs[b], &stats[b], nullptr, 0, &col[b]);
+            if (rc) return rc;
+            if (!stats[b].sorted) return fail(c, BDK_ERR_DATA, "bam %d is not sorted by reference sequence and position: the two-bam device merge needs sorted input", b);
+        }
+        const uint64_t n0 = col[0].n, n1 = col[1].n, n = n0 + n1;
+        if (n > 0x7ffffff0ull) return fail(c, BDK_ERR_ARG, "more than 2^31 records in a two-bam device merge");
+        if (n == 0) return 0;
+        cudaStream_t st = c->stream;
+        tstart(c, T_EXTRACT);
+        for (int k = 0; k < 10; ++k) ENS(merged.cols[k], (size_t)n * width[k]);
+        for (int b = 0; b < 2; ++b) {
+            ENS(d_k[b], (col[b].n + 1) * 8);
+            if (col[b].n) {
+                const bamdev::Columns v = col[b].view();
+                bammerge::keys_kernel<<<kNumSMs * 8, 256, 0, st>>>(v.tid, v.pos, v.flag, (uint32_t)col[b].n, d_k[b].as<unsigned long long>());
+            }
+        }
+        // cuts from the larger bam
+        const int X = n1 > n0 ? 1 : 0, Y = 1 - X;
+        const uint32_t nx = (uint32_t)col[X].n, ny = (uint32_t)col[Y].n;
+        const uint32_t nblocks = div_up<uint32_t>(std::max<uint32_t>(nx, 1), bammerge::CUT_EVERY);
+        ENS(d_cutx, (size_t)nblocks * 4); ENS(d_cuty, (size_t)nblocks * 4); ENS(d_partx, ((size_t)nblocks + 2) * 4); ENS(d_party, ((size_t)nblocks + 2) * 4);
+        ENS(d_order, (size_t)n * 4); ENS(d_small, 64);
+        uint32_t* small = d_small.as<uint32_t>();          // [0] blocks, [1] cuts found, [2] longest part
+        const uint32_t init[3] = {nblocks, 0, 0};
+        CU(cudaMemcpyAsync(small, init, 12, cudaMemcpyHostToDevice, st));
+        bammerge::find_cuts_kernel<<<div_up<uint32_t>(nblocks, 128), 128, 0, st>>>(d_k[X].as<unsigned long long>(), nx, d_k[Y].as<unsigned long long>(), ny, nblocks,
+                                                                                   d_cutx.as<uint32_t>(), d_cuty.as<uint32_t>());
+        device_scan(st, bammerge::CutFlag{d_cutx.as<uint32_t>()}, bammerge::CutOut{d_cutx.as<uint32_t>(), d_cuty.as<uint32_t>(), d_partx.as<uint32_t>(), d_party.as<uint32_t>()},
+                    small, small + 1, 0, ScanScratch{c->d_scan_sums.as<uint32_t>()});
+        const uint32_t* part_a = X == 0 ? d_partx.as<uint32_t>() : d_party.as<uint32_t>();
+        const uint32_t* part_b = X == 0 ? d_party.as<uint32_t>() : d_partx.as<uint32_t>();
+        bammerge::merge_parts_kernel<<<div_up<uint32_t>(nblocks + 1, 128), 128, 0, st>>>(d_k[0].as<unsigned long long>(), (uint32_t)n0, d_k[1].as<unsigned long long>(), (uint32_t)n1,
+                                                                                        part_a, part_b, small + 1, d_order.as<uint32_t>(), small + 2);
+        bammerge::gather_kernel<<<kNumSMs * 16, 256, 0, st>>>(d_order.as<uint32_t>(), (uint32_t)n, col[0].view(), col[1].view(), merged.view());
+        tstop(c, T_EXTRACT);
+        c->launches += 8;
+        CU(cudaGetLastError());
+        uint32_t hs[3];
+        CU(cudaMemcpyAsync(hs, small, 12, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        tcollect(c);
+        stats[0].merge_parts = hs[1] + 1; stats[0].merge_longest_part = hs[2];
+        col[0].release(); col[1].release();
+        const bamdev::Columns m = merged.view();
+        if (host_out) {
+            if (n > cap) return fail(c, BDK_ERR_ARG, "bdk_decode_bams: more than %llu records", (unsigned long long)cap);
+            void* dst[10] = {(void*)host_out->pos, (void*)host_out->mpos, (void*)host_out->tid, (void*)host_out->mtid, (void*)host_out->isize,
+                             (void*)host_out->flag, (void*)host_out->mapq, (void*)host_out->rgid, (void*)host_out->qlen, (void*)host_out->qid};
+            for (int k = 0; k < 10; ++k) CU(cudaMemcpyAsync(dst[k], merged.cols[k].p, (size_t)n * width[k], cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            return 0;
+        }
+        bdk_soa d;
+        d.pos = m.pos; d.mpos = m.mpos; d.tid = m.tid; d.mtid = m.mtid; d.isize = m.isize; d.flag = m.flag; d.mapq = m.mapq; d.rgid = m.rgid; d.qlen = m.qlen; d.qid = m.qid;
+        return push_common(c, n, n, [&]() -> int { return launch_k1(c, d, n, (uint32_t)c->n_records, true); });
+    };
+    const int rc = run();
+    cudaStreamSynchronize(c->stream);
+    cleanup();
+    return rc;
+}
+
+int bdk_push_bams(bdk_ctx* c, const bdk_bam_source* srcs, int n, bdk_bam_stats* stats) {
+    if (!c || !srcs) return BDK_ERR_ARG;
+    if (n == 1) return bam_pipeline(c, srcs, stats, nullptr, 0);
+    if (n != 2) return fail(c, BDK_ERR_ARG, "bdk_push_bams merges one or two bams on the device (%d given): use the host reader for more", n);
+    if (c->finished) return fail(c, BDK_ERR_STATE, "bdk_push_bams after bdk_finish (call bdk_reset first)");
+    return push_two_bams(c, srcs, stats, nullptr, 0);
+}
+
+int bdk_decode_bams(bdk_ctx* c, const bdk_bam_source* srcs, int n, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
+    if (!c || !srcs || !host_out) return BDK_ERR_ARG;
+    if (n == 1) return bam_pipeline(c, srcs, stats, host_out, cap);
+    if (n != 2) return fail(c, BDK_ERR_ARG, "bdk_decode_bams: one or two bams");
+    return push_two_bams(c, srcs, stats, host_out, cap);
+}
 
 int bdk_decode_bam(bdk_ctx* c, const bdk_bam_source* src, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
     if (!host_out) return BDK_ERR_ARG;

@@ -21,6 +21,7 @@
 #include "bgzf_inflate.cuh"
 #include "bgzf_inflate_warp.cuh"
 #include "bam_decode.cuh"
+#include "bam_merge.cuh"
 #include "comm.cuh"
 #include "k1_classify.cuh"
 #include "k234_regions_links_sv.cuh"

@@ -1092,9 +1092,10 @@ struct bdh_bamdev {
     std::vector<uint16_t> rg_id;
     std::vector<int32_t> rg_lib, rg_bam;
     double t_open = 0;
+    int id_base = 0;                  // first read-group id of this file (second bam of a two-bam run: behind the first bam's ids)
 };
 
-bdh_bamdev* bdh_bamdev_open(const bdh_config* cfgh, const char* path, const char* region, char* err, int errcap) {
+static bdh_bamdev* bamdev_open_impl(const bdh_config* cfgh, const char* path, const char* region, int id_base, char* err, int errcap) {
     using namespace bdh;
     bdh_bamdev* d = nullptr;
     try {
@@ -1192,11 +1193,12 @@ bdh_bamdev* bdh_bamdev_open(const bdh_config* cfgh, const char* path, const char
         // read groups: the config's, in its map order, then "any other"
         for (auto const& kv : cfg.readgroup_library) {
             d->rg_hash.push_back(brec::hash_bytes((const uint8_t*)kv.first.data(), kv.first.size()));
-            d->rg_id.push_back((uint16_t)d->rg_lib.size());
+            d->rg_id.push_back((uint16_t)(id_base + d->rg_lib.size()));
             d->rg_lib.push_back(cfg.rg_lib(kv.first));
             d->rg_bam.push_back(bam_index);
         }
-        if (d->rg_lib.size() >= 65535) throw std::runtime_error("more than 65535 read groups in the config");
+        if (id_base + d->rg_lib.size() >= 65535) throw std::runtime_error("more than 65535 read groups in the config");
+        d->id_base = id_base;
         {
             auto li = cfg.lib_index.find(cfg.first_bam_library);
             d->rg_lib.push_back(cfg.first_bam_library.empty() || li == cfg.lib_index.end() ? -1 : li->second);
@@ -1209,6 +1211,13 @@ bdh_bamdev* bdh_bamdev_open(const bdh_config* cfgh, const char* path, const char
         delete d;
         return 0;
     }
+}
+bdh_bamdev* bdh_bamdev_open(const bdh_config* cfgh, const char* path, const char* region, char* err, int errcap) {
+    return bamdev_open_impl(cfgh, path, region, 0, err, errcap);
+}
+bdh_bamdev* bdh_bamdev_open_next(const bdh_config* cfgh, const bdh_bamdev* first, const char* path, const char* region, char* err, int errcap) {
+    if (!first || !path || !path[0]) { set_err2(err, errcap, "bdh_bamdev_open_next: the first bam and a path are needed"); return 0; }
+    return bamdev_open_impl(cfgh, path, region, first->id_base + (int)first->rg_lib.size(), err, errcap);
 }
 void bdh_bamdev_free(bdh_bamdev* d) { delete d; }
 int bdh_bamdev_nrg(const bdh_bamdev* d) { return (int)d->rg_lib.size(); }
@@ -1226,12 +1235,22 @@ static void bamdev_source(const bdh_bamdev* d, bdk_bam_source& s) {
     s.n_ref = (int32_t)d->hdr.tid_names.size();
     s.region_on = d->rg.on ? 1 : 0; s.region_tid = d->rg.tid; s.region_beg = d->rg.beg; s.region_end = d->rg.end;
     s.n_rg = (uint32_t)d->rg_hash.size(); s.rg_hash = d->rg_hash.data(); s.rg_id = d->rg_id.data();
-    s.rg_other = (uint16_t)(d->rg_lib.size() - 1);
+    s.rg_other = (uint16_t)(d->id_base + d->rg_lib.size() - 1);
 }
 int bdh_bamdev_push(bdh_bamdev* d, bdk_ctx* ctx, bdk_bam_stats* stats) {
     bdk_bam_source s;
     bamdev_source(d, s);
     return bdk_push_bam(ctx, &s, stats);
+}
+int bdh_bamdev_push2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, bdk_bam_stats* stats2) {
+    bdk_bam_source s[2];
+    bamdev_source(first, s[0]); bamdev_source(second, s[1]);
+    return bdk_push_bams(ctx, s, 2, stats2);
+}
+int bdh_bamdev_decode2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats2) {
+    bdk_bam_source s[2];
+    bamdev_source(first, s[0]); bamdev_source(second, s[1]);
+    return bdk_decode_bams(ctx, s, 2, host_out, cap, stats2);
 }
 int bdh_bamdev_decode(bdh_bamdev* d, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
     bdk_bam_source s;

@@ -65,36 +65,53 @@ int main(int argc, char** argv) {
         bdk_bam_stats bstats;
         memset(&bstats, 0, sizeof bstats);
         bool on_device = false;
-        // One bam and no read dump: the file is decoded on the GPU (bdk_push_bam: only the compressed bytes cross PCIe, inflate /
+        // One or two bams and no read dump: the files are decoded on the GPU (two: merged there in BamMerger's order) (bdk_push_bam: only the compressed bytes cross PCIe, inflate /
         // record parsing / classification of consecutive windows overlap). BDK_GPU_DECODE=0 keeps the host decoder. A file the
         // device path refuses (damaged member, truncated record) goes through the host decoder, which reports what is wrong.
         const char* gd = getenv("BDK_GPU_DECODE");
-        if (cfg.bam_files.size() == 1 && !want_reads && !(gd && atoi(gd) == 0)) {
-            if (bdh_bamdev* dev = bdh_bamdev_open(&cfgh, nullptr, o.chr.c_str(), err, sizeof err)) {
+        if (cfg.bam_files.size() <= 2 && !want_reads && !(gd && atoi(gd) == 0)) {
+            const bool two = cfg.bam_files.size() == 2;
+            bdh_bamdev* dev = bdh_bamdev_open(&cfgh, cfg.bam_files[0].c_str(), o.chr.c_str(), err, sizeof err);
+            bdh_bamdev* dev2 = dev && two ? bdh_bamdev_open_next(&cfgh, dev, cfg.bam_files[1].c_str(), o.chr.c_str(), err, sizeof err) : nullptr;
+            if (dev && (!two || dev2)) {
                 t_decoded = now_s();
                 if (cuda_warmup.joinable()) cuda_warmup.join();
-                p.nrg = bdh_bamdev_nrg(dev); p.ntid = std::max(1, bdh_bamdev_ntid(dev));
-                p.rg_lib = bdh_bamdev_rg_lib(dev); p.rg_bam = bdh_bamdev_rg_bam(dev);
-                check(nullptr, bdk_create(&ctx, 0, &p), "bdk_create");
+                std::vector<int32_t> rg_lib(bdh_bamdev_rg_lib(dev), bdh_bamdev_rg_lib(dev) + bdh_bamdev_nrg(dev));
+                std::vector<int32_t> rg_bam(bdh_bamdev_rg_bam(dev), bdh_bamdev_rg_bam(dev) + bdh_bamdev_nrg(dev));
+                if (two) {      // the second bam's read-group ids follow the first bam's
+                    rg_lib.insert(rg_lib.end(), bdh_bamdev_rg_lib(dev2), bdh_bamdev_rg_lib(dev2) + bdh_bamdev_nrg(dev2));
+                    rg_bam.insert(rg_bam.end(), bdh_bamdev_rg_bam(dev2), bdh_bamdev_rg_bam(dev2) + bdh_bamdev_nrg(dev2));
+                }
+                p.nrg = (int)rg_lib.size(); p.ntid = std::max(1, bdh_bamdev_ntid(dev));
+                p.rg_lib = rg_lib.data(); p.rg_bam = rg_bam.data();
+                check(nullptr, bdk_create(&ctx, 0, &p), "bdk_create");      // (copies the tables)
+                p.rg_lib = nullptr; p.rg_bam = nullptr;
                 t_created = now_s();
-                const int rc = bdh_bamdev_push(dev, ctx, &bstats);
+                bdk_bam_stats st2[2];
+                memset(st2, 0, sizeof st2);
+                const int rc = two ? bdh_bamdev_push2(dev, dev2, ctx, st2) : bdh_bamdev_push(dev, ctx, &st2[0]);
                 if (rc == 0) {
                     on_device = true;
+                    bstats = st2[0];
+                    if (two) {
+                        bstats.kept += st2[1].kept; bstats.records += st2[1].records; bstats.h2d_bytes += st2[1].h2d_bytes; bstats.inflated_bytes += st2[1].inflated_bytes;
+                        bstats.windows += st2[1].windows; bstats.inflate_ms += st2[1].inflate_ms; bstats.sorted = st2[0].sorted && st2[1].sorted;
+                        bstats.chain_ms = st2[1].chain_ms; bstats.extract_ms = st2[1].extract_ms;       // (timers accumulate over the job)
+                    }
                     n_records = bstats.kept;
-                    for (int t = 0; t < bdh_bamdev_ntid(dev); ++t) tid_names.push_back(bdh_bamdev_tid_name(dev, t));
+                    for (int t = 0; t < bdh_bamdev_ntid(dev); ++t) tid_names.push_back(bdh_bamdev_tid_name(dev, t));      // BamMerger: the first stream's header
                     if (!bstats.sorted)
                         std::cerr << "WARNING: the input is not sorted by reference sequence and position; the covered reference length, the window and "
                                      "the regions assume a coordinate-sorted bam (samtools sort).\n";
-                    // the tables bdk_params points to were copied by bdk_create; the names are copied above
-                    bdh_bamdev_free(dev);
                 } else {
-                    if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode refused the file (%s); host decoder\n", bdk_last_error(ctx));
                     const std::string why = bdk_last_error(ctx);
+                    if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode refused the input (%s); host decoder\n", why.c_str());
                     bdk_destroy(ctx); ctx = nullptr;
-                    bdh_bamdev_free(dev);
-                    if (rc != BDK_ERR_DATA) throw std::runtime_error("bdk_push_bam: " + why);
+                    if (rc != BDK_ERR_DATA) { bdh_bamdev_free(dev); bdh_bamdev_free(dev2); throw std::runtime_error("bdk_push_bam: " + why); }
                 }
             } else if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode: %s; host decoder\n", err);
+            bdh_bamdev_free(dev);
+            bdh_bamdev_free(dev2);
         }
         if (!on_device) {
             // pageable columns: pinning hundreds of megabytes costs more than the staged copy of a one-shot run saves, and the decoder

@@ -346,8 +346,18 @@ typedef struct bdk_bam_stats {
                                                  the boundary search; the filter + extraction */
     float stage_ms;                   /* host time of the producer thread copying file bytes into its pinned staging buffers */
     float wall_ms;                    /* the whole call */
+    uint32_t merge_parts;             /* bdk_push_bams with two bams (in stats[0]): independent parts the merge was cut into ... */
+    uint32_t merge_longest_part;      /* ... and the records of the longest one (merged by one thread) */
 } bdk_bam_stats;
 int bdk_push_bam(bdk_ctx* ctx, const bdk_bam_source* src, bdk_bam_stats* stats);
+/* One or TWO bams of one config: each is decoded on the device as above, the two record streams are merged on the device in the
+ * order the reference's BamMerger delivers them (src/lib/io/BamMerger.cpp:40-126: a priority queue over the streams' heads by
+ * (tid, pos, strand); for two streams its tie behaviour has a closed form, csrc/bam_merge.cuh) and classified. srcs[0] must be
+ * the config's first bam (BamMerger pushes the streams in that order), the read-group ids of the two sources must not overlap,
+ * stats (may be NULL) has n entries. Both bams must be sorted by (reference sequence, position), else BDK_ERR_DATA. Three or more
+ * bams: BDK_ERR_ARG (use bdh_stream_open + bdk_push). bdk_decode_bams: the merged columns to the host instead (tests). */
+int bdk_push_bams(bdk_ctx* ctx, const bdk_bam_source* srcs, int n, bdk_bam_stats* stats);
+int bdk_decode_bams(bdk_ctx* ctx, const bdk_bam_source* srcs, int n, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
 /* The same decode, but the columns come back to the HOST (arrays of `cap` records the caller owns, written through the const
  * pointers of *host_out) and nothing is classified: the device decoder as a drop-in for bdh_stream_open on one file, and what the
  * parity tests compare with the host decoder column by column. stats->kept = records written. */

@@ -85,6 +85,10 @@ void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone);
  * the same file and region, in the same order. One file per call; several bams (BamMerger) go through bdh_stream_open. */
 typedef struct bdh_bamdev bdh_bamdev;
 bdh_bamdev* bdh_bamdev_open(const bdh_config* cfg, const char* path, const char* region, char* err, int errcap);
+/* The SECOND bam of a two-bam config (tumor / normal): its read-group ids follow the first bam's, so the two sources can be handed to
+ * bdk_push_bams together. bdk_create then takes nrg = bdh_bamdev_nrg(first) + bdh_bamdev_nrg(second) and the two rg_lib / rg_bam
+ * arrays one after the other. `first` must be the config's first bam (sorted bam list), `path` its second. */
+bdh_bamdev* bdh_bamdev_open_next(const bdh_config* cfg, const bdh_bamdev* first, const char* path, const char* region, char* err, int errcap);
 void bdh_bamdev_free(bdh_bamdev* d);
 int bdh_bamdev_nrg(const bdh_bamdev* d);
 const int32_t* bdh_bamdev_rg_lib(const bdh_bamdev* d);
@@ -94,6 +98,10 @@ const char* bdh_bamdev_tid_name(const bdh_bamdev* d, int tid);
 uint64_t bdh_bamdev_members(const bdh_bamdev* d);
 uint64_t bdh_bamdev_file_bytes(const bdh_bamdev* d);
 int bdh_bamdev_push(bdh_bamdev* d, bdk_ctx* ctx, bdk_bam_stats* stats);
+/* bdk_push_bams / bdk_decode_bams of two opened files: decoded on the device, merged there in BamMerger's order, classified (or the
+ * merged columns copied to the host). stats2 = two entries or NULL. */
+int bdh_bamdev_push2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, bdk_bam_stats* stats2);
+int bdh_bamdev_decode2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats2);
 /* bdk_decode_bam of the opened file: the decoded columns into the caller's host arrays (cap records each). */
 int bdh_bamdev_decode(bdh_bamdev* d, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
 

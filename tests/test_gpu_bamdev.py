@@ -188,3 +188,84 @@ def test_cli_takes_the_device_path_and_falls_back_for_what_it_cannot_do(tmp_path
         js = json.loads(stats.read_text())
         assert js["device_decode"] == int(mode)
     assert outs["1"] == outs["0"] and outs["1"].count("\n") > 5
+
+
+def _two_bam_columns(cfg, paths, region=""):
+    host = api.BamStream(cfg, paths=paths, region=region, threads=4)
+    d0 = api.BamDevice(cfg, path=paths[0], region=region)
+    d1 = api.BamDevice(cfg, path=paths[1], region=region, after=d0)
+    rg_lib = np.concatenate([d0.rg_lib, d1.rg_lib])
+    rg_bam = np.concatenate([d0.rg_bam, d1.rg_bam])
+    b = api.ParamBundle(api.Options(chr=region), cfg.libs, cfg.nbam, rg_lib, rg_bam, cfg.window, max(1, len(d0.tid_names)))
+    ctx = api.Context(b)
+    cols, (s0, s1) = ctx.decode_bams(d0, d1, host.n + 64)
+    assert len(cols["pos"]) == host.n, (len(cols["pos"]), host.n)
+    for k in api.COLUMN_DTYPES:
+        if k == "rgid":
+            assert np.array_equal(host.rg_lib[host.cols[k]], rg_lib[cols[k]]) and np.array_equal(host.rg_bam[host.cols[k]], rg_bam[cols[k]]), k
+        else:
+            assert np.array_equal(host.cols[k], cols[k]), (k, region)
+    n = host.n
+    ctx.close(); d0.close(); d1.close(); host.close()
+    return s0, s1, n
+
+
+def test_two_bams_merged_on_the_device_in_the_reference_order(tmp_path, monkeypatch):
+    """Tumor / normal: both bams decoded on the GPU, merged there with BamMerger's tie rule -- every column of the merged stream
+    against the host decoder's merge (itself tested against the priority queue and the reference binary), also with a region,
+    with tiny decode windows, and on tie-heavy input (the same reads in both bams)."""
+    w, d = _write(tmp_path, 120000, 6, seed=31)
+    cfg = api.BamConfig(text=w.config_text())
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        assert cfg.bam_files == ["normal.bam", "tumor.bam"]
+        s0, s1, n = _two_bam_columns(cfg, cfg.bam_files)
+        assert s0["merge_parts"] > 10 and s0["merge_longest_part"] < n
+        _two_bam_columns(cfg, cfg.bam_files, "chrB")
+        monkeypatch.setenv("BDK_BAMDEV_WINDOW_KB", "64")
+        _two_bam_columns(cfg, cfg.bam_files)
+        monkeypatch.delenv("BDK_BAMDEV_WINDOW_KB")
+        # ties everywhere: the second bam holds the first bam's records again (other read names do not matter for the order)
+        import shutil
+        shutil.copy("normal.bam", "tumor.bam")
+        s0, s1, n = _two_bam_columns(cfg, cfg.bam_files)
+        assert s0["merge_parts"] == 1            # no position occurs in one bam only: one part, merged by one thread
+    finally:
+        os.chdir(cwd)
+
+
+def test_two_bam_job_and_cli_on_the_device_equal_the_host_decoder(tmp_path):
+    w, d = _write(tmp_path, 150000, 6, seed=32)
+    (d / "cfg").write_text(w.config_text())
+    cfg = api.BamConfig(text=w.config_text())
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        for opts in (api.Options(), api.Options(CN_lib=True)):
+            host = api.BamStream(cfg, threads=4)
+            b = api.ParamBundle.from_stream(opts, cfg, host)
+            ctx = api.Context(b)
+            ctx.push({k: np.ascontiguousarray(v) for k, v in host.cols.items()})
+            want = (ctx.summary(), ctx.finish(), ctx.regions(), ctx.areads())
+            ctx.close(); host.close()
+            d0 = api.BamDevice(cfg, path=cfg.bam_files[0])
+            d1 = api.BamDevice(cfg, path=cfg.bam_files[1], after=d0)
+            b = api.ParamBundle(opts, cfg.libs, cfg.nbam, np.concatenate([d0.rg_lib, d1.rg_lib]), np.concatenate([d0.rg_bam, d1.rg_bam]), cfg.window, len(d0.tid_names))
+            ctx = api.Context(b)
+            ctx.push_bams(d0, d1)
+            got = (ctx.summary(), ctx.finish(), ctx.regions(), ctx.areads())
+            ctx.close(); d0.close(); d1.close()
+            _assert_same_job(want, got)
+            assert len(got[1].sv) > 0
+    finally:
+        os.chdir(cwd)
+    outs = {}
+    for mode in ("1", "0"):
+        stats = d / ("stats%s.json" % mode)
+        p = subprocess.run([util.CLI, "--stats-json", str(stats), "cfg"], cwd=d, env=dict(os.environ, BDK_GPU_DECODE=mode), capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        outs[mode] = util.strip_header(p.stdout)
+        import json
+        assert json.loads(stats.read_text())["device_decode"] == int(mode)
+    assert outs["1"] == outs["0"] and outs["1"].count("\n") > 5
