@@ -203,6 +203,9 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
         CU(cudaStreamSynchronize(c->stream));                // tab / prev0 are locals; the producer's kernels need the zeroed counters
     }
 
+    const bool trace = getenv("BDK_DECODE_TRACE") != nullptr;
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count() * 1e3; };
+    if (trace) fprintf(stderr, "[bamdev] %.1f ms: %zu windows, %zu chunks planned, buffers ready\n", since(), nwin, nchunk);
     // ---- producer ----------------------------------------------------------------------------------------------------
     int nstreams = 8;             // measured (profiles/bamdev_sweep_*): 16 MiB chunks on 8 streams; smaller chunks lose to launch tails
     if (const char* e = getenv("BDK_BAMDEV_STREAMS")) nstreams = std::max(1, std::min(atoi(e), (int)BamDev::NSTREAMS));
@@ -283,6 +286,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
             }
             if ((e = cudaGetLastError()) != cudaSuccess) return bad("bgzf inflate launch", e);
             launched.store((int64_t)g + 1, std::memory_order_release);
+            if (trace && (g == 0 || g + 1 == nchunk)) fprintf(stderr, "[bamdev] %.1f ms: chunk %zu of %zu launched (staging so far %.1f ms)\n", since(), g + 1, nchunk, stage_s * 1e3);
         }
     });
 
@@ -391,6 +395,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
                     CU(cudaMemcpyAsync((uint8_t*)B->d_raw[s2].p + BamDev::CARRY_CAP - new_carry, raw + hinfo->tail, new_carry, cudaMemcpyDeviceToDevice, c->stream));
             }
             carry = new_carry;
+            if (trace && (w == 0 || w + 1 == nwin)) fprintf(stderr, "[bamdev] %.1f ms: window %zu of %zu decoded (%u records)\n", since(), w + 1, nwin, nrec);
             CU(cudaEventRecord(B->ev_decoded[s], c->stream));
             decoded.store((int64_t)w + 1, std::memory_order_release);
         }

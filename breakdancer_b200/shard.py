@@ -105,6 +105,48 @@ def run_sharded_bams(cfg, rank: int, world: int, run_chromosome: Callable[[int, 
     return sorted([x for part in out for x in part], key=lambda x: x[0])
 
 
+def run_sharded_bams_device(cfg, rank: int, world: int, opts, device: int = 0, gather: bool = True):
+    """The per-chromosome shards of this rank from the config's bam file(s), DECODED ON THE GPU: for every chromosome of the rank
+    only that sequence's BGZF members (through the .bai) cross PCIe, are inflated, parsed and classified on `device`
+    (api.BamDevice + Context.push_bam / push_bams; one or two bams), with `-o <chromosome>` semantics like the reference's own
+    one-process-per-chromosome runs (README:31). Returns the (tid, name, summary, SvTable) of all ranks on rank 0 (or of this
+    rank with gather=False). No collective on the data path."""
+    import dataclasses
+    from . import api
+    if not 1 <= len(cfg.bam_files) <= 2:
+        raise RuntimeError("the device decode takes one or two bams; use run_sharded_bams for more")
+    plan = plan_from_index(cfg.bam_files, world)
+    if plan is None:
+        raise RuntimeError("per-chromosome shards need a .bai next to every bam file")
+    _, bins = plan
+    names = api.bam_reference_names(cfg.bam_files[0])
+    local = []
+    for t in bins[rank]:
+        o = dataclasses.replace(opts, chr=names[t])
+        d0 = api.BamDevice(cfg, path=cfg.bam_files[0], region=names[t])
+        d1 = api.BamDevice(cfg, path=cfg.bam_files[1], region=names[t], after=d0) if len(cfg.bam_files) == 2 else None
+        rg_lib = d0.rg_lib if d1 is None else np.concatenate([d0.rg_lib, d1.rg_lib])
+        rg_bam = d0.rg_bam if d1 is None else np.concatenate([d0.rg_bam, d1.rg_bam])
+        ctx = api.Context(api.ParamBundle(o, cfg.libs, cfg.nbam, rg_lib, rg_bam, cfg.window, max(1, len(d0.tid_names))), device)
+        if d1 is None:
+            ctx.push_bam(d0)
+        else:
+            ctx.push_bams(d0, d1)
+        local.append((t, names[t], ctx.summary(), ctx.finish()))
+        ctx.close()
+        d0.close()
+        if d1 is not None:
+            d1.close()
+    if not gather or world == 1:
+        return sorted(local, key=lambda x: x[0])
+    import torch.distributed as dist
+    out = [None] * world if rank == 0 else None
+    dist.gather_object([(t, n, bytes(s), tb) for t, n, s, tb in local], out, dst=0)
+    if rank != 0:
+        return None
+    return sorted([x for part in out for x in part], key=lambda x: x[0])
+
+
 # ---- one job over several GPUs (whole-genome / -t semantics, include/bdk.h "Multi-GPU") -----------------------------
 def stream_slices(n_records: int, world: int) -> List[slice]:
     """Contiguous, near-equal slices of the globally (tid, pos)-sorted record stream, one per rank in rank order.

@@ -269,3 +269,49 @@ def test_two_bam_job_and_cli_on_the_device_equal_the_host_decoder(tmp_path):
         import json
         assert json.loads(stats.read_text())["device_decode"] == int(mode)
     assert outs["1"] == outs["0"] and outs["1"].count("\n") > 5
+
+
+def test_per_chromosome_shards_decoded_on_the_device(tmp_path):
+    """shard.run_sharded_bams_device: every chromosome through the index and the device decode (-o semantics), against the same
+    chromosome through the host decoder; the plan comes from the .bai alone. The index is written by the reference's samtools
+    when oracle/_ref has it (else the test is the no-index error)."""
+    from breakdancer_b200 import shard
+    from oracle import oracle
+    libs = [synth.LibSpec("lib_a", "one.bam", 315, 44, 75, ["a1", "a2"])]
+    w, d = _write(tmp_path, 90000, 6, seed=12, libs=libs)
+    cfg_text = w.config_text()
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        cfg = api.BamConfig(text=cfg_text)
+        samtools = oracle.REF_SAMTOOLS
+        if not os.access(samtools, os.X_OK):
+            with pytest.raises(RuntimeError):
+                shard.run_sharded_bams_device(cfg, 0, 1, api.Options())
+            return
+        subprocess.check_call([samtools, "index", "one.bam"])
+        got = shard.run_sharded_bams_device(cfg, 0, 1, api.Options())
+        assert [t for t, *_ in got] == [0, 1, 2]
+        for t, name, summ, table in got:
+            want = _job_from_host(cfg, "one.bam", api.Options(chr=name))
+            assert bytes(summ) == bytes(want[0]) and table.sv.tobytes() == want[1].sv.tobytes(), name
+    finally:
+        os.chdir(cwd)
+
+
+def test_read_groups_the_config_does_not_know_and_records_without_am_tag(tmp_path):
+    """A read group missing from the config falls back to the first bam's library (BamConfig.hpp:63-72) on both decoders; without
+    AM tags bdqual is MAPQ (Alignment.cpp:12-23)."""
+    libs = [synth.LibSpec("lib_a", "one.bam", 315, 44, 75, ["a1", "a2"]), synth.LibSpec("lib_b", "one.bam", 467, 32, 100, ["b1"])]
+    w = synth.generate(util.GENOME3, libs, 50000, seed=14, anomaly_frac=0.05)
+    bam = str(tmp_path / "one.bam")
+    api.write_bam(bam, [g[0] for g in w.genome], [g[1] for g in w.genome], w.rg_names, synth.split_by_bam(w)["one.bam"], write_am=False, level=6)
+    full = w.config_text()
+    partial = "".join(l for l in full.splitlines(True) if "readgroup:a2" not in l)
+    assert partial != full
+    for text in (full, partial):
+        cfg = api.BamConfig(text=text)
+        _compare_columns(cfg, bam)
+        want = _job_from_host(cfg, bam, api.Options())
+        got, _, _ = _job_from_device(cfg, bam, api.Options())
+        _assert_same_job(want, got)
