@@ -273,7 +273,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
             uint8_t* dout = (uint8_t*)B->d_raw[ws].p + BamDev::CARRY_CAP;
             int32_t* dst = B->d_status[ws].as<int32_t>() + k0;
             if (g == 0) cudaEventRecord(B->ev_first, ist);
-            const unsigned grid = (unsigned)std::min<uint64_t>((nmem + bgzw::WARPS_PER_CTA - 1) / bgzw::WARPS_PER_CTA, (uint64_t)kNumSMs * 4);
+            const unsigned grid = (unsigned)std::min<uint64_t>((nmem + bgzw::WARPS_PER_CTA - 1) / bgzw::WARPS_PER_CTA, (uint64_t)kNumSMs * bgzw::CTAS_PER_SM);
             bgzw::bgzf_inflate_warp_kernel<<<grid, bgzw::CTA_THREADS, sizeof(bgzw::Tables) * bgzw::WARPS_PER_CTA, ist>>>(
                 dcomp, dm, (uint32_t)nmem, dout, dst, B->d_counter.as<uint32_t>() + g);
             bgzw::bgzf_crc_kernel<<<(unsigned)std::min<uint64_t>((nmem + 7) / 8, (uint64_t)kNumSMs * 8), 256, 0, ist>>>(dcomp, dm, (uint32_t)nmem, dout, dst);

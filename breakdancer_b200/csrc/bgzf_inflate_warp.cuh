@@ -30,7 +30,13 @@ using bgz::Member;
 
 constexpr int LL_BITS = 11, D_BITS = 9, CL_BITS = 7;
 constexpr int LL_SIZE = 1 << LL_BITS, D_SIZE = 1 << D_BITS;
-constexpr int WARPS_PER_CTA = 8, CTA_THREADS = WARPS_PER_CTA * 32;
+#ifndef BGZW_WARPS_PER_CTA
+#define BGZW_WARPS_PER_CTA 8
+#endif
+#ifndef BGZW_CTAS_PER_SM
+#define BGZW_CTAS_PER_SM 4
+#endif
+constexpr int WARPS_PER_CTA = BGZW_WARPS_PER_CTA, CTA_THREADS = WARPS_PER_CTA * 32, CTAS_PER_SM = BGZW_CTAS_PER_SM;
 constexpr int ERR_CRC = 7;
 
 // First-level table entry (16 bits): bits 0-3 code length, bits 4-12 symbol; 0 = no code of at most the index width starts with
@@ -95,8 +101,8 @@ struct Reader {
     uint32_t lo, hi, hi2, ahead;
     uint32_t off;               // bit offset of the read position in lo
     uint32_t widx, wlim;        // index (from w0) of the word in `ahead`; last index that may be loaded
-    int32_t bits_base;          // bits in front of lo, counted from the byte the window was opened at (negative while lo
-                                // holds bytes in front of it)
+    uint32_t bits_skip;         // 32 * 3 + bits in front of the byte the window was opened at: the bits consumed since then are
+                                // 32 * widx + off - bits_skip (nothing to keep up to date when the window slides)
     uint32_t origin;            // that byte's offset in the member (0, or where a stored block ended)
     BGZW_HD void init(const uint8_t* in, uint32_t n, uint32_t at = 0) {
         origin = at;
@@ -106,23 +112,23 @@ struct Reader {
         lo = w0[0]; hi = w0[bgzw_min(1u, wlim)]; hi2 = w0[bgzw_min(2u, wlim)]; ahead = w0[bgzw_min(3u, wlim)];
         widx = 3;
         off = 8 * mis;
-        bits_base = -(int32_t)(8 * mis);
+        bits_skip = 96 + 8 * mis;
     }
     BGZW_HD void slide() {
         lo = hi; hi = hi2; hi2 = ahead;
         ++widx;
         ahead = w0[bgzw_min(widx, wlim)];
-        off -= 32; bits_base += 32;
+        off -= 32;
     }
     // at most two slides are ever due: off < 32 after a normalize, and no more than 48 bits are dropped before the next one
     // (written as two tests: left as a loop, the compiler unrolls it sixteen-fold with look-ahead loads)
-    BGZW_HD void normalize() { if (off >= 32) { slide(); if (off >= 32) slide(); } }
+    BGZW_HD void normalize() { if (off >= 32) { slide(); if (__builtin_expect(off >= 32, 0)) slide(); } }
     BGZW_HD uint32_t peek() const { return bgzw_funnel_r(lo, hi, off); }                      // off < 32
     BGZW_HD uint32_t peek2() const { return off < 32 ? bgzw_funnel_r(lo, hi, off) : bgzw_funnel_r(hi, hi2, off); }   // off < 64
     BGZW_HD void drop(uint32_t n) { off += n; }
     BGZW_HD uint32_t take(uint32_t n) { normalize(); const uint32_t v = peek() & ((1u << n) - 1u); off += n; return v; }   // n <= 16
-    BGZW_HD bool over_end(uint32_t in_len) const { return bits_base + (int32_t)off > (int32_t)(8 * (in_len - origin)); }
-    BGZW_HD uint32_t consumed() const { return origin + ((uint32_t)(bits_base + (int32_t)off + 7) >> 3); }    // bytes of the member, a started byte counts
+    BGZW_HD bool over_end(uint32_t in_len) const { return 32 * widx + off > 8 * (in_len - origin) + bits_skip; }
+    BGZW_HD uint32_t consumed() const { return origin + ((32 * widx + off - bits_skip + 7) >> 3); }    // bytes of the member, a started byte counts
     BGZW_HD void align_byte() { off = (off + 7) & ~7u; }
     BGZW_HD void seek(const uint8_t* in, uint32_t at, uint32_t n) { init(in + at, n - at, at); }
 #else
@@ -394,7 +400,7 @@ BGZW_HD uint32_t crc_lane_part(const uint32_t* table, const uint8_t* p, uint32_t
 
 #ifdef __CUDACC__
 // One warp per member, members handed out by an atomic counter (counter[0], zeroed by the caller). status[m] = 0 or bgz::Status.
-__global__ void __launch_bounds__(CTA_THREADS, 4)
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
 bgzf_inflate_warp_kernel(const uint8_t* __restrict__ comp, const Member* __restrict__ members, uint32_t n_members, uint8_t* __restrict__ out,
                          int32_t* __restrict__ status, uint32_t* __restrict__ counter) {
     extern __shared__ __align__(16) uint8_t bgzw_smem[];
