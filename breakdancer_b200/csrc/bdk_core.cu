@@ -1192,14 +1192,12 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BDK_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return BDK_ERR_CUDA;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BDK_ERR_CUDA;
-    const size_t smem = (size_t)bgz::CTA_THREADS * bgz::LUT_PER_THREAD * sizeof(uint16_t);
-    if (cudaFuncSetAttribute(bgz::bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BDK_ERR_CUDA;
-    const unsigned grid = (unsigned)prop.multiProcessorCount;
+    // the warp-per-member decoder of the device-resident BAM decode (bgzf_inflate_warp.cuh) and its CRC-32 check
+    const size_t smem = sizeof(bgzw::Tables) * bgzw::WARPS_PER_CTA;
+    if (cudaFuncSetAttribute(bgzw::bgzf_inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BDK_ERR_CUDA;
     // batches of members: at most 256 MiB of input and 1 GiB of output on the device at a time
     const uint64_t IN_CAP = 256ull << 20, OUT_CAP = 1ull << 30;
-    uint8_t *d_in = 0, *d_out = 0; bgz::Member* d_mem = 0; bgz::Scratch* d_scr = 0; int32_t* d_st = 0;
+    uint8_t *d_in = 0, *d_out = 0; bgz::Member* d_mem = 0; uint32_t* d_counter = 0; int32_t* d_st = 0;
     cudaEvent_t e0 = 0, e1 = 0;
     cudaStream_t st = 0;
     std::vector<bgz::Member> batch;
@@ -1220,7 +1218,7 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
     ck(cudaStreamCreate(&st)); ck(cudaEventCreate(&e0)); ck(cudaEventCreate(&e1));
     ck(cudaMalloc(&d_in, std::min<uint64_t>(IN_CAP, file_bytes) + (1 << 17))); ck(cudaMalloc(&d_out, std::min<uint64_t>(OUT_CAP, out_bytes) + (1 << 17)));
     ck(cudaMalloc(&d_mem, max_members * sizeof(bgz::Member))); ck(cudaMalloc(&d_st, max_members * sizeof(int32_t)));
-    ck(cudaMalloc(&d_scr, (size_t)grid * bgz::CTA_THREADS * sizeof(bgz::Scratch)));
+    ck(cudaMalloc(&d_counter, 4));
     uint64_t i = 0;
     while (!rc && i < n_members) {
         uint64_t j = i, in_b = 0, out_b = 0;
@@ -1235,10 +1233,15 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
         // members are in file order but need not be contiguous in `out`: copy back member by member only if they are not
         bool contiguous = true;
         for (uint64_t k = i + 1; k < j; ++k) contiguous &= members[k].out_off == members[k - 1].out_off + members[k - 1].out_len;
-        if (!ck(cudaMemcpyAsync(d_in, file + members[i].in_off, in_b, cudaMemcpyHostToDevice, st))) break;
+        // (with the 8 bytes behind the last stream: the CRC-32 the device checks, and the words the bit reader looks ahead to)
+        if (!ck(cudaMemcpyAsync(d_in, file + members[i].in_off, std::min<uint64_t>(in_b + 8, file_bytes - members[i].in_off), cudaMemcpyHostToDevice, st))) break;
         if (!ck(cudaMemcpyAsync(d_mem, batch.data(), batch.size() * sizeof(bgz::Member), cudaMemcpyHostToDevice, st))) break;
         ck(cudaEventRecord(e0, st));
-        bgz::bgzf_inflate_kernel<<<grid, bgz::CTA_THREADS, smem, st>>>(d_in, d_mem, batch.size(), d_out, d_scr, d_st);
+        ck(cudaMemsetAsync(d_counter, 0, 4, st));
+        const uint32_t nb = (uint32_t)batch.size();
+        const unsigned grid = (unsigned)std::min<uint64_t>((nb + bgzw::WARPS_PER_CTA - 1) / bgzw::WARPS_PER_CTA, (uint64_t)kNumSMs * bgzw::CTAS_PER_SM);
+        bgzw::bgzf_inflate_warp_kernel<<<grid, bgzw::CTA_THREADS, smem, st>>>(d_in, d_mem, nb, d_out, d_st, d_counter);
+        bgzw::bgzf_crc_kernel<<<(unsigned)std::min<uint64_t>((nb + 7) / 8, (uint64_t)kNumSMs * 8), 256, 0, st>>>(d_in, d_mem, nb, d_out, d_st);
         ck(cudaGetLastError());
         ck(cudaEventRecord(e1, st));
         if (contiguous) ck(cudaMemcpyAsync(out + members[i].out_off, d_out, out_b, cudaMemcpyDeviceToHost, st));
@@ -1249,7 +1252,7 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
         if (ck(cudaEventElapsedTime(&ms, e0, e1)) && kernel_ms) *kernel_ms += ms;
         i = j;
     }
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_mem); cudaFree(d_st); cudaFree(d_scr);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_mem); cudaFree(d_st); cudaFree(d_counter);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);

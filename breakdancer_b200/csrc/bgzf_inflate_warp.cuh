@@ -39,14 +39,25 @@ constexpr int LL_SIZE = 1 << LL_BITS, D_SIZE = 1 << D_BITS;
 constexpr int WARPS_PER_CTA = BGZW_WARPS_PER_CTA, CTA_THREADS = WARPS_PER_CTA * 32, CTAS_PER_SM = BGZW_CTAS_PER_SM;
 constexpr int ERR_CRC = 7;
 
-// First-level table entry (16 bits): bits 0-3 code length, bits 4-12 symbol; 0 = no code of at most the index width starts with
-// these bits, or the symbol is not a legal one (literal/length 286, 287, distance 30, 31): the slow path sorts that out.
+// First-level table entries, 16 bits. Bits 0-3: the code length; 0 = the first level does not settle it (LL_LONGER / D_LONGER: the
+// code is longer than the index, or there is none: canonical_tail(); *_ILLEGAL: a code of at most the index width for a symbol
+// that may not occur -- literal/length 286, 287, distance 30, 31). The other bits hold what the symbol MEANS, so that no
+// arithmetic on symbol numbers and no second table is needed (RFC 1951 3.2.5):
+//   literal/length  bit 12 clear: a literal, the byte in bits 4-11
+//                   bit 12 set:   a length, 3 + B + extra with B = base - 3 (0..255) in bits 4-11 and the extra-bit count in bits
+//                                 13-15; end of block: B = 255 with 7 extra bits (no length has more than 5), so a decoder that
+//                                 treats it as a length sees one of 258 or more. Entries without a code length have bit 12 set
+//                                 as well: one test separates the literals from everything else.
+//   distance        1 + (m << x) + extra with x in bits 4-7 and m in bits 8-9 (symbols 0-3: m = symbol, x = 0; others: m = 2 + symbol % 2,
+//                   x = symbol / 2 - 1)
+constexpr uint32_t LL_NOT_LITERAL = 0x1000, LL_EOB = 0xfff0, LL_LONGER = 0x1000, LL_ILLEGAL = 0x1010, D_LONGER = 0, D_ILLEGAL = 0x10;
 struct Tables {                    // one per warp, shared memory: 6.1 KB
     uint16_t ll[LL_SIZE];
     uint16_t d[D_SIZE];            // also the code-length code while a dynamic header is read
     uint16_t sym_ll[288], sym_d[32];
     uint16_t cnt_ll[16], cnt_d[16];
     uint8_t lens[320];
+    uint16_t tail_first_ll, tail_index_ll, tail_first_d, tail_index_d;   // canonical() state behind the first-level widths (canonical_tail)
     uint32_t ok;                   // build verdict of the phase that checks the code lengths
 };
 
@@ -55,25 +66,29 @@ struct Tables {                    // one per warp, shared memory: 6.1 KB
 #define BGZW_LANE() ((int)(threadIdx.x & 31u))
 #define BGZW_PHASE_BEGIN(lane) __syncwarp(); { const int lane = BGZW_LANE();
 #define BGZW_PHASE_END() } __syncwarp();
+#define BGZW_PHASE_END_OPEN() }
 #define BGZW_LANE0(stmt) do { if (BGZW_LANE() == 0) { stmt; } } while (0)
 #else
 #define BGZW_HD inline
 #define BGZW_PHASE_BEGIN(lane) for (int lane = 0; lane < 32; ++lane) {
 #define BGZW_PHASE_END() }
+#define BGZW_PHASE_END_OPEN() }
 #define BGZW_LANE0(stmt) do { stmt; } while (0)
 #endif
 
-// Base value and extra-bit count of length symbols 257.. and distance symbols (RFC 1951 3.2.5): base << 4 | extra
-BGZW_HD uint32_t len_base_extra(uint32_t idx) {                 // idx = symbol - 257, < 29
-    if (idx < 8) return (3 + idx) << 4;
-    if (idx == 28) return 258u << 4;
-    const uint32_t extra = (idx >> 2) - 1;
-    return ((((4u + (idx & 3)) << extra) + 3) << 4) | extra;
+BGZW_HD uint32_t ll_entry(uint32_t sym, uint32_t len) {          // sym <= 285
+    if (sym < 256) return sym << 4 | len;
+    if (sym == 256) return LL_EOB | len;
+    const uint32_t idx = sym - 257;
+    uint32_t base, x;
+    if (idx < 8) { base = idx; x = 0; }
+    else if (idx == 28) { base = 255; x = 0; }
+    else { x = (idx >> 2) - 1; base = (4 + (idx & 3)) << x; }
+    return x << 13 | LL_NOT_LITERAL | base << 4 | len;
 }
-BGZW_HD uint32_t dist_base_extra(uint32_t sym) {                // < 30
-    if (sym < 4) return (1 + sym) << 4;
-    const uint32_t extra = (sym >> 1) - 1;
-    return ((((2u + (sym & 1)) << extra) + 1) << 4) | extra;
+BGZW_HD uint32_t d_entry(uint32_t sym, uint32_t len) {           // sym <= 29
+    const uint32_t x = sym < 4 ? 0 : (sym >> 1) - 1, m = sym < 4 ? sym : 2 + (sym & 1);
+    return m << 8 | x << 4 | len;
 }
 
 // Bit reader of the warp decoder. Device: a window of three consecutive aligned words (lo, hi, hi2) of the input plus one more
@@ -123,6 +138,7 @@ struct Reader {
     // at most two slides are ever due: off < 32 after a normalize, and no more than 48 bits are dropped before the next one
     // (written as two tests: left as a loop, the compiler unrolls it sixteen-fold with look-ahead loads)
     BGZW_HD void normalize() { if (off >= 32) { slide(); if (__builtin_expect(off >= 32, 0)) slide(); } }
+    BGZW_HD void normalize1() { if (off >= 32) slide(); }                                       // where off < 64 is known
     BGZW_HD uint32_t peek() const { return bgzw_funnel_r(lo, hi, off); }                      // off < 32
     BGZW_HD uint32_t peek2() const { return off < 32 ? bgzw_funnel_r(lo, hi, off) : bgzw_funnel_r(hi, hi2, off); }   // off < 64
     BGZW_HD void drop(uint32_t n) { off += n; }
@@ -135,6 +151,7 @@ struct Reader {
     Bits b;
     void init(const uint8_t* in, uint32_t n) { b.in = in; b.n = n; b.pos = 0; b.buf = 0; b.cnt = 0; b.ahead = 0; b.has_ahead = false; }
     void normalize() { bgz::refill(b); }
+    void normalize1() { bgz::refill(b); }
     uint32_t peek() const { return (uint32_t)b.buf; }
     uint32_t peek2() { bgz::refill(b); return (uint32_t)b.buf; }
     void drop(uint32_t n) { b.buf >>= n; b.cnt -= (int)n; }
@@ -146,12 +163,49 @@ struct Reader {
 #endif
 };
 
+// j mod d for the offsets of an overlapping match (j < 258, 1 <= d < 258) without an integer division: (j + 0.5) / d is at
+// least 0.5 / 258 away from every integer, the quotient is below 258, so a division that is good to a few ulp (the device's
+// approximate one: 2 ulp) truncates to floor(j / d).
+BGZW_HD uint32_t small_mod(uint32_t j, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    const uint32_t qt = (uint32_t)__fdividef((float)j + 0.5f, (float)d);
+#else
+    const uint32_t qt = (uint32_t)(((float)j + 0.5f) / (float)d);
+#endif
+    return j - qt * d;
+}
+
 // Canonical decode of the code that starts at bit 0 of `bits` (first bit of the code = bit 0), looking at code lengths up to
 // maxlen. Returns the symbol and its length, or -1.
 BGZW_HD int canonical(uint32_t bits, int maxlen, const uint16_t* cnt, const uint16_t* sym, int* len_out) {
     int code = 0, first = 0, index = 0;
 #pragma unroll 1
     for (int l = 1; l <= maxlen; ++l) {
+        code |= (int)((bits >> (l - 1)) & 1);
+        const int c = cnt[l];
+        if (code - c < first) { *len_out = l; return sym[index + (code - first)]; }
+        index += c; first += c;
+        first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// The same decode entered behind the first l0 lengths, for a code the first-level table has no entry for (so none of the first l0
+// lengths is a hit): `first` and `index` as canonical() has them after l0 rounds (Tables::tail_*), the code so far is the first l0
+// bits, first bit most significant.
+BGZW_HD uint32_t bit_reverse(uint32_t v, int n) {                // the low n bits of v, reversed
+#ifdef __CUDA_ARCH__
+    return __brev(v) >> (32 - n);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+#endif
+}
+BGZW_HD int canonical_tail(uint32_t bits, int l0, int first, int index, const uint16_t* cnt, const uint16_t* sym, int* len_out) {
+    int code = (int)(bit_reverse(bits, l0) << 1);
+#pragma unroll 1
+    for (int l = l0 + 1; l <= 15; ++l) {
         code |= (int)((bits >> (l - 1)) & 1);
         const int c = cnt[l];
         if (code - c < first) { *len_out = l; return sym[index + (code - first)]; }
@@ -198,6 +252,14 @@ BGZW_HD bool build_tables(Tables& T, int hlit, int hdist, bool cl) {
                 if (left > 0 && used > 1) ok = false;      // incomplete codes only with a single code (RFC 1951 3.2.7, as zlib)
             }
             T.ok = ok ? 1u : 0u;
+            if (!cl) {
+                int first = 0, index = 0;
+                for (int k = 1; k <= LL_BITS; ++k) { index += T.cnt_ll[k]; first = (first + T.cnt_ll[k]) << 1; }
+                T.tail_first_ll = (uint16_t)first; T.tail_index_ll = (uint16_t)index;
+                first = 0; index = 0;
+                for (int k = 1; k <= D_BITS; ++k) { index += T.cnt_d[k]; first = (first + T.cnt_d[k]) << 1; }
+                T.tail_first_d = (uint16_t)first; T.tail_index_d = (uint16_t)index;
+            }
         }
     BGZW_PHASE_END()
     if (!T.ok) return false;
@@ -212,17 +274,160 @@ BGZW_HD bool build_tables(Tables& T, int hlit, int hdist, bool cl) {
             for (int i = lane; i < LL_SIZE; i += 32) {
                 int len = 0;
                 const int s = canonical((uint32_t)i, LL_BITS, T.cnt_ll, T.sym_ll, &len);
-                T.ll[i] = s < 0 || s > 285 ? (uint16_t)0 : (uint16_t)(s << 4 | len);
+                T.ll[i] = (uint16_t)(s < 0 ? LL_LONGER : s > 285 ? LL_ILLEGAL : ll_entry((uint32_t)s, (uint32_t)len));
             }
             for (int i = lane; i < D_SIZE; i += 32) {
                 int len = 0;
                 const int s = canonical((uint32_t)i, D_BITS, T.cnt_d, T.sym_d, &len);
-                T.d[i] = s < 0 || s > 29 ? (uint16_t)0 : (uint16_t)(s << 4 | len);
+                T.d[i] = (uint16_t)(s < 0 ? D_LONGER : s > 29 ? D_ILLEGAL : d_entry((uint32_t)s, (uint32_t)len));
             }
         }
     BGZW_PHASE_END()
     return true;
 }
+
+#if defined(__CUDA_ARCH__) && !defined(BGZW_NO_FAST_LOOP)
+#define BGZW_FAST_LOOP 1
+// The symbols the first-level tables settle -- literals, and matches of up to 32 bytes whose length and distance codes are in
+// the tables -- decoded in a loop written in PTX, for two things the compiler will not do with the C++ below: every branch is
+// `bra.uni` (all 32 lanes hold the same decoder state, so no branch here ever diverges; compiled from C++ each `if` is wrapped
+// in reconvergence instructions and every way out of the loop costs a chain of them at every check), and the window registers
+// are rotated in place. It stops IN FRONT of the first symbol it leaves to the C++ step that follows it (a longer or illegal
+// code, end of block, a long match, anything that fails a check) with the reader state and `op` as that step expects them, so
+// what the loop does NOT handle needs no cases here. Invariants as in the C++ loop: off < 48 on entry and at the top, one slide
+// there (with the bounds check of every 32 input bits), off <= 51 where the distance code is looked at, <= 79 behind a match
+// (one slide there). 17 instructions per literal, about 60 per match (the C++ loop: 31 and 95).
+__device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* out, uint32_t out_len, uint32_t in_len, const Tables& T) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const float lane_half = (float)lane + 0.5f;
+    const uint32_t t_ll = (uint32_t)__cvta_generic_to_shared(T.ll), t_d = (uint32_t)__cvta_generic_to_shared(T.d);
+    const uint32_t bitlim = 8 * (in_len - b.origin) + b.bits_skip;     // over_end(): 32 * widx + off > bitlim
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, pl, pq;\n\t"
+        ".reg .b32 v, a, e, l, t, u, lx, len, f, dl, dx, dist, noff, so, j;\n\t"
+        ".reg .b64 ad;\n\t"
+        ".reg .f32 fd, fq, fj;\n\t"
+        "BGZW_TOP:\n\t"
+        "setp.lt.u32 p, %4, 32;\n\t"
+        "@p bra.uni BGZW_LOOK;\n\t"
+        // slide the window by one word; the bounds of input and output, once per 32 bits
+        "mov.b32 %0, %1;\n\t"
+        "mov.b32 %1, %2;\n\t"
+        "mov.b32 %2, %3;\n\t"
+        "add.u32 %5, %5, 1;\n\t"
+        "min.u32 t, %5, %7;\n\t"
+        "mad.wide.u32 ad, t, 4, %8;\n\t"
+        "ld.global.u32 %3, [ad];\n\t"
+        "sub.u32 %4, %4, 32;\n\t"
+        "setp.gt.u32 p, %6, %10;\n\t"
+        "shl.b32 t, %5, 5;\n\t"
+        "add.u32 t, t, %4;\n\t"
+        "setp.gt.or.u32 p, t, %11, p;\n\t"
+        "@p bra.uni BGZW_OUT;\n\t"
+        "BGZW_LOOK:\n\t"
+        "shf.r.wrap.b32 v, %0, %1, %4;\n\t"
+        "and.b32 a, v, 2047;\n\t"
+        "mad.lo.u32 a, a, 2, %12;\n\t"
+        "ld.shared.u16 e, [a];\n\t"
+        "and.b32 l, e, 15;\n\t"
+        "and.b32 t, e, 0x1000;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "@p bra.uni BGZW_MATCH;\n\t"
+        // a literal (every lane stores the same byte to the same place)
+        "add.u32 %4, %4, l;\n\t"
+        "shr.u32 t, e, 4;\n\t"
+        "mad.wide.u32 ad, %6, 1, %9;\n\t"
+        "st.global.u8 [ad], t;\n\t"
+        "add.u32 %6, %6, 1;\n\t"
+        "bra.uni BGZW_TOP;\n\t"
+        "BGZW_MATCH:\n\t"
+        // no code length in the entry (a longer code, an illegal symbol) or the end of the block (7 "extra bits"): the long way
+        "setp.eq.u32 p, l, 0;\n\t"
+        "setp.ge.or.u32 p, e, 0xf000, p;\n\t"
+        "@p bra.uni BGZW_OUT;\n\t"
+        "shr.u32 lx, e, 13;\n\t"
+        "shr.u32 len, e, 4;\n\t"
+        "and.b32 len, len, 255;\n\t"
+        "shr.u32 t, v, l;\n\t"
+        "shl.b32 u, 0xffffffff, lx;\n\t"
+        "not.b32 u, u;\n\t"
+        "and.b32 t, t, u;\n\t"
+        "add.u32 len, len, t;\n\t"
+        "add.u32 len, len, 3;\n\t"
+        "add.u32 noff, %4, l;\n\t"
+        "add.u32 noff, noff, lx;\n\t"
+        // the distance code: noff < 64
+        "setp.lt.u32 p, noff, 32;\n\t"
+        "@p shf.r.wrap.b32 v, %0, %1, noff;\n\t"
+        "@!p shf.r.wrap.b32 v, %1, %2, noff;\n\t"
+        "and.b32 a, v, 511;\n\t"
+        "mad.lo.u32 a, a, 2, %13;\n\t"
+        "ld.shared.u16 f, [a];\n\t"
+        "and.b32 dl, f, 15;\n\t"
+        "shr.u32 dx, f, 4;\n\t"
+        "and.b32 dx, dx, 15;\n\t"
+        "shr.u32 dist, f, 8;\n\t"
+        "shl.b32 dist, dist, dx;\n\t"
+        "shr.u32 t, v, dl;\n\t"
+        "shl.b32 u, 0xffffffff, dx;\n\t"
+        "not.b32 u, u;\n\t"
+        "and.b32 t, t, u;\n\t"
+        "add.u32 dist, dist, t;\n\t"
+        "add.u32 dist, dist, 1;\n\t"
+        "add.u32 noff, noff, dl;\n\t"
+        "add.u32 noff, noff, dx;\n\t"
+        // no entry for the distance, a distance beyond the start, a match beyond the end: the long way
+        "setp.eq.u32 p, dl, 0;\n\t"
+        "setp.gt.or.u32 p, dist, %6, p;\n\t"
+        "add.u32 t, %6, len;\n\t"
+        "setp.gt.or.u32 p, t, %10, p;\n\t"
+        "@p bra.uni BGZW_OUT;\n\t"
+        // the copy: byte j of the match is byte (j mod dist) of the dist bytes in front of it, 32 bytes a round, lane = j mod 32.
+        // (j + 0.5) / dist truncates to floor(j / dist) for all j < 258 and dist >= 1 with a quotient good to 2 ulp: small_mod()
+        "bar.warp.sync 0xffffffff;\n\t"
+        "sub.u32 so, %6, dist;\n\t"
+        "cvt.rn.f32.u32 fd, dist;\n\t"
+        "rcp.approx.ftz.f32 fd, fd;\n\t"
+        "mov.b32 j, %14;\n\t"
+        "mov.f32 fq, %15;\n\t"
+        "BGZW_COPY:\n\t"
+        "setp.lt.u32 pl, j, len;\n\t"
+        "mul.ftz.f32 fj, fq, fd;\n\t"
+        "cvt.rzi.u32.f32 u, fj;\n\t"
+        "mul.lo.u32 u, u, dist;\n\t"
+        "sub.u32 u, j, u;\n\t"
+        "add.u32 u, u, so;\n\t"
+        "mad.wide.u32 ad, u, 1, %9;\n\t"
+        "ld.global.u8 u, [ad];\n\t"                 // (lanes beyond the match read a byte in front of it: valid, unused)
+        "add.u32 a, %6, j;\n\t"
+        "mad.wide.u32 ad, a, 1, %9;\n\t"
+        "@pl st.global.u8 [ad], u;\n\t"
+        "add.u32 j, j, 32;\n\t"
+        "add.f32 fq, fq, 0f42000000;\n\t"
+        "sub.u32 a, j, %14;\n\t"
+        "setp.lt.u32 p, a, len;\n\t"
+        "@p bra.uni BGZW_COPY;\n\t"
+        "mov.b32 %6, t;\n\t"
+        "mov.b32 %4, noff;\n\t"
+        "setp.lt.u32 p, noff, 32;\n\t"
+        "@p bra.uni BGZW_LOOK;\n\t"
+        "mov.b32 %0, %1;\n\t"
+        "mov.b32 %1, %2;\n\t"
+        "mov.b32 %2, %3;\n\t"
+        "add.u32 %5, %5, 1;\n\t"
+        "min.u32 t, %5, %7;\n\t"
+        "mad.wide.u32 ad, t, 4, %8;\n\t"
+        "ld.global.u32 %3, [ad];\n\t"
+        "sub.u32 %4, %4, 32;\n\t"
+        "bra.uni BGZW_TOP;\n\t"
+        "BGZW_OUT:\n\t"
+        "}"
+        : "+r"(b.lo), "+r"(b.hi), "+r"(b.hi2), "+r"(b.ahead), "+r"(b.off), "+r"(b.widx), "+r"(op)
+        : "r"(b.wlim), "l"(b.w0), "l"(out), "r"(out_len), "r"(bitlim), "r"(t_ll), "r"(t_d), "r"(lane), "f"(lane_half)
+        : "memory");
+}
+#endif
 
 // Inflate one member: exactly out_len bytes from in[0 .. in_len). Called by all 32 lanes of a warp with the same arguments.
 // `out` must be writable for 512 bytes beyond out_len: a damaged stream is stopped at the next window slide or match, not at
@@ -297,61 +502,80 @@ BGZW_HD int inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uin
         if (!build_tables(T, hlit, hdist, false)) return bgz::ERR_CODES;
         if (T.lens[256] == 0) return bgz::ERR_CODES;
         // ---- the symbols of the block ----
+        // One loop, one way out: what goes wrong sets `st` and leaves the loop (early returns from inside it cost a chain of
+        // predicated-off reconvergence instructions at every check, every symbol). Window reader: off < 32 at the top, <= 47
+        // behind a literal, <= 51 when the distance code is looked at (peek2), <= 79 behind a match (one slide there, one at
+        // the top); the bounds are looked at once per slide at the top and at every match.
+        int st = bgz::OK;
         for (;;) {
+#ifdef BGZW_FAST_LOOP
+            fast_symbols(b, op, out, out_len, in_len, T);            // everything the tables settle; then one symbol the long way
+#endif
 #ifdef BGZW_WINDOW_READER
-            if (b.off >= 32) {                                       // every 32 bits of input: slide the window, look at the bounds
-                b.normalize();
-                if (op > out_len) return bgz::ERR_OUTPUT;
-                if (b.over_end(in_len)) return bgz::ERR_INPUT;
+            {
+#ifdef BGZW_FAST_LOOP
+                bool look = true;                                    // the fast loop may have stopped because of the bounds
+#else
+                bool look = false;
+#endif
+                if (b.off >= 32) { b.slide(); look = true; }
+                if (look && (op > out_len || b.over_end(in_len))) { st = op > out_len ? bgz::ERR_OUTPUT : bgz::ERR_INPUT; break; }
             }
 #else
             b.normalize();
-            if (op > out_len) return bgz::ERR_OUTPUT;
+            if (op > out_len) { st = bgz::ERR_OUTPUT; break; }
 #endif
             const uint32_t p = b.peek();
             uint32_t e = T.ll[p & (LL_SIZE - 1)];
             if ((e & 15) == 0) {                                     // a code longer than the table index, an illegal symbol, or no code
                 int len = 0;
-                const int s = canonical(p, 15, T.cnt_ll, T.sym_ll, &len);
-                if (s < 0 || s > 285) return bgz::ERR_SYMBOL;
-                e = (uint32_t)(s << 4 | len);
+                const int s = e != LL_LONGER ? -1 : canonical_tail(p, LL_BITS, T.tail_first_ll, T.tail_index_ll, T.cnt_ll, T.sym_ll, &len);
+                if (s < 0 || s > 285) { st = bgz::ERR_SYMBOL; break; }
+                e = ll_entry((uint32_t)s, (uint32_t)len);
             }
-            const uint32_t l = e & 15, sym = e >> 4;
-            if (sym < 256) {
+            const uint32_t l = e & 15;
+            if (!(e & LL_NOT_LITERAL)) {
                 b.drop(l);
 #ifndef BGZW_WINDOW_READER
-                if (op >= out_len) return bgz::ERR_OUTPUT;           // checked reader: exact buffers; the window reader looks at the bound every 32 input bits
+                if (op >= out_len) { st = bgz::ERR_OUTPUT; break; }  // checked reader: exact buffers
 #endif
-                BGZW_LANE0(out[op] = (uint8_t)sym);
+                BGZW_LANE0(out[op] = (uint8_t)(e >> 4));
                 ++op;
                 continue;
             }
-            if (sym == 256) { b.drop(l); break; }
-            const uint32_t lbe = len_base_extra(sym - 257), lx = lbe & 15;
-            const uint32_t len = (lbe >> 4) + ((p >> l) & ((1u << lx) - 1u));
+            if (e >= LL_EOB) { b.drop(l); break; }
+            const uint32_t lx = e >> 13;
+            const uint32_t len = 3 + ((e >> 4) & 255u) + ((p >> l) & ((1u << lx) - 1u));
             b.drop(l + lx);
             const uint32_t q = b.peek2();
             uint32_t f = T.d[q & (D_SIZE - 1)];
             if ((f & 15) == 0) {
                 int dl = 0;
-                const int s = canonical(q, 15, T.cnt_d, T.sym_d, &dl);
-                if (s < 0 || s > 29) return bgz::ERR_DISTANCE;
-                f = (uint32_t)(s << 4 | dl);
+                const int s = f != D_LONGER ? -1 : canonical_tail(q, D_BITS, T.tail_first_d, T.tail_index_d, T.cnt_d, T.sym_d, &dl);
+                if (s < 0 || s > 29) { st = bgz::ERR_DISTANCE; break; }
+                f = d_entry((uint32_t)s, (uint32_t)dl);
             }
-            const uint32_t dl = f & 15, dbe = dist_base_extra(f >> 4), dx = dbe & 15;
-            const uint32_t dist = (dbe >> 4) + ((q >> dl) & ((1u << dx) - 1u));
+            const uint32_t dl = f & 15, dx = (f >> 4) & 15;
+            const uint32_t dist = 1 + ((f >> 8) << dx) + ((q >> dl) & ((1u << dx) - 1u));
             b.drop(dl + dx);
-            if (dist > op) return bgz::ERR_DISTANCE;
-            if (op + len > out_len) return bgz::ERR_OUTPUT;
+            if (dist > op || op + len > out_len) { st = dist > op ? bgz::ERR_DISTANCE : bgz::ERR_OUTPUT; break; }
             // byte j of the match is byte (j mod dist) of the `dist` bytes before it: every lane reads bytes that were complete
-            // before this match began (the barrier that opens the phase orders them after the stores of all lanes)
+            // before this match began (the barrier that opens the phase orders them after the stores of all lanes). No barrier
+            // behind it: until the next match's, lane 0 only stores literals beyond this match, where nothing is read.
             BGZW_PHASE_BEGIN(lane)
-                const uint8_t* src = out + op - dist;
-                if (dist >= len) { for (uint32_t j = (uint32_t)lane; j < len; j += 32) out[op + j] = src[j]; }
-                else { for (uint32_t j = (uint32_t)lane; j < len; j += 32) out[op + j] = src[j % dist]; }
-            BGZW_PHASE_END()
+                const uint32_t so = op - dist;
+                if (len <= 32) {
+                    if ((uint32_t)lane < len) out[op + (uint32_t)lane] = out[so + (dist < len ? small_mod((uint32_t)lane, dist) : (uint32_t)lane)];
+                } else if (dist >= len) {
+                    for (uint32_t j = (uint32_t)lane; j < len; j += 32) out[op + j] = out[so + j];
+                } else {
+                    for (uint32_t j = (uint32_t)lane; j < len; j += 32) out[op + j] = out[so + small_mod(j, dist)];
+                }
+            BGZW_PHASE_END_OPEN()
             op += len;
+            b.normalize1();
         }
+        if (st != bgz::OK) return st;
     }
     if (b.over_end(in_len)) return bgz::ERR_INPUT;
     return op == out_len ? bgz::OK : bgz::ERR_OUTPUT;

@@ -165,7 +165,7 @@ void inflate_members(const MappedFile& f, const std::string& path, int threads, 
     // CRC32 (BGZF footer, checked by carry-less multiplication) matches, otherwise zlib decodes the block. 1.4x zlib's inflate
     // on real BAM blocks, about even on very compressible files (the synthetic BAMs of the tests). BDK_FAST_INFLATE=0: zlib only.
     static const bool use_fast = !(getenv("BDK_FAST_INFLATE") && atoi(getenv("BDK_FAST_INFLATE")) == 0) && !getenv("BDK_ZLIB_ONLY");
-    // BDK_GPU_INFLATE=1: all members are inflated by the GPU first (csrc/bgzf_inflate.cuh through bdk_bgzf_inflate); the workers
+    // BDK_GPU_INFLATE=1: all members are inflated by the GPU first (csrc/bgzf_inflate_warp.cuh through bdk_bgzf_inflate); the workers
     // below then only check the CRC32 of every member and re-inflate on the host whatever the device refused or got wrong.
     std::vector<int32_t> gpu_status;
     if (getenv("BDK_GPU_INFLATE") && atoi(getenv("BDK_GPU_INFLATE")) > 0 && !blocks.empty()) {

@@ -287,12 +287,13 @@ uint64_t bdk_comm_bytes(bdk_ctx* ctx);
  * evaluated on the device (for known-answer tests). */
 int bdk_poisson_logsf(bdk_ctx* ctx, const double* lambda, const int32_t* k, double* out, uint64_t n);
 
-/* BGZF members inflated on the GPU (csrc/bgzf_inflate.cuh; replaces the zlib calls under the reference's samtools reader,
+/* BGZF members inflated on the GPU (csrc/bgzf_inflate_warp.cuh, one warp per member, the decoder of bdk_push_bam; replaces the zlib calls under the reference's samtools reader,
  * `inflate_block` in bgzf.c of vendor/samtools-0.1.19.tar.gz, reached through `samread` in src/lib/io/BamReader.hpp:65,
  * for whole files at once). `file` is the host image of the BGZF file, `members`
  * its DEFLATE streams (offsets into `file` and into `out`; out_len from the member's ISIZE footer), `out` a host buffer of
- * out_bytes. status[i] = 0 if member i decoded to exactly out_len bytes, else a positive error code: the caller checks the
- * members' CRC32 and re-inflates whatever failed. Needs no context; returns 0 or BDK_ERR_*. kernel_ms (may be NULL) receives
+ * out_bytes. status[i] = 0 if member i decoded to exactly out_len bytes whose CRC-32 equals the 4 bytes behind the stream (the
+ * member's footer; the input must be readable 8 bytes beyond every stream, as in a BGZF file), else a positive error code: the
+ * caller re-inflates whatever failed. Needs no context; returns 0 or BDK_ERR_*. kernel_ms (may be NULL) receives
  * the summed duration of the inflate kernel launches. */
 typedef struct bdk_bgzf_member {
     uint64_t in_off;

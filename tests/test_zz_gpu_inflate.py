@@ -1,9 +1,10 @@
-"""BGZF members inflated on the GPU (csrc/bgzf_inflate.cuh, C ABI bdk_bgzf_inflate, BDK_GPU_INFLATE=1 in the BAM reader).
+"""BGZF members inflated on the GPU (csrc/bgzf_inflate_warp.cuh: the warp-per-member decoder of bdk_push_bam, also behind the C ABI
+bdk_bgzf_inflate and BDK_GPU_INFLATE=1 in the host BAM reader).
 
-CPU: the member decoder every GPU thread runs, compiled for the host, differential- and corruption-fuzzed against zlib under
-AddressSanitizer / UBSan (tests/hostsim/gpu_inflate_host.cpp). GPU: the kernel against zlib on the members of generated BAM
-files and on damaged members, then the reader itself with the device path switched on: same columns as the host path and
-not one member redone by the host. (The file sorts last on purpose: it covers an opt-in path.)"""
+CPU: the member decoder every warp runs, compiled for the host, differential- and corruption-fuzzed against zlib under
+AddressSanitizer / UBSan (tests/hostsim/gpu_inflate_warp_host.cpp). GPU: the kernel (with its CRC-32 check) against zlib on the
+members of generated BAM files, on streams made of overlapping matches of every distance, and on damaged members; then the host
+reader with the device stage switched on: same columns as the host path and not one member redone by the host."""
 import ctypes as C
 import os
 import struct
@@ -15,18 +16,6 @@ import pytest
 
 from breakdancer_b200 import api, synth
 from tests import util
-
-
-def test_member_decoder_differential_and_corruption_fuzz_on_the_host():
-    src = os.path.join(util.ROOT, "tests", "hostsim", "gpu_inflate_host.cpp")
-    exe = os.path.join(util.ROOT, "tests", "_build", "gpu_inflate_host")
-    os.makedirs(os.path.dirname(exe), exist_ok=True)
-    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.check_call([cxx, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer",
-                           src, "-o", exe, "-lz"])
-    p = subprocess.run([exe, "500"], capture_output=True, text=True)
-    assert p.returncode == 0, p.stdout + p.stderr
-    assert "refused_good=0 mismatched=0" in p.stdout, p.stdout
 
 
 def test_warp_member_decoder_and_sliced_crc_fuzz_on_the_host():
@@ -103,6 +92,39 @@ def test_kernel_against_zlib_on_bam_members(tmp_path):
         got, status, _, _ = _gpu_inflate(data, members)
         assert np.all(status == 0)
         assert got.tobytes() == b"".join(zlib.decompress(data[a:a + n], -15) for a, n, _ in members)
+
+
+def _member_file(payloads, level=6, strategy=zlib.Z_DEFAULT_STRATEGY):
+    """A buffer shaped like a BGZF file (18 bytes of header, the raw DEFLATE stream, CRC-32 and ISIZE) for each payload, and
+    its member list."""
+    data, members = bytearray(), []
+    for raw in payloads:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        comp = co.compress(raw) + co.flush()
+        data += b"\x1f\x8b\x08\x04" + bytes(14)
+        members.append((len(data), len(comp), len(raw)))
+        data += comp + struct.pack("<II", zlib.crc32(raw) & 0xffffffff, len(raw))
+    return bytes(data) + bytes(64), members
+
+
+@pytest.mark.gpu
+def test_kernel_on_overlapping_matches_of_every_distance_and_other_shapes():
+    """Matches whose source overlaps their destination (byte j = byte j mod distance of the bytes before: the warp copy does that
+    modulo without an integer division), for every distance 1..300 and lengths up to 258; stored blocks, fixed codes, Huffman-only
+    and incompressible members, empty and one-byte members."""
+    rng = np.random.default_rng(11)
+    payloads = []
+    for d in range(1, 301):
+        unit = rng.integers(0, 256, size=d, dtype=np.uint8).tobytes()
+        payloads.append((unit * (900 // d + 3))[:900 + d] + rng.integers(0, 4, size=40, dtype=np.uint8).tobytes())
+    payloads += [b"", b"A", bytes(65000), rng.integers(0, 256, size=60000, dtype=np.uint8).tobytes(),
+                 (b"ACGT" * 9 + b"FFFFFFFFFFFFFFFFFFFFFFFF#######" * 3) * 300]
+    for level, strategy in ((6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY),
+                            (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+        data, members = _member_file(payloads, level, strategy)
+        got, status, arr, _ = _gpu_inflate(data, members)
+        assert np.all(status == 0), (level, strategy, np.nonzero(status)[0][:10], status[status != 0][:10])
+        assert got.tobytes() == b"".join(payloads), (level, strategy)
 
 
 @pytest.mark.gpu
