@@ -20,7 +20,7 @@
 namespace {
 
 struct BamDev {
-    static constexpr int WSLOTS = 3;                        // windows resident on the device (compressed + inflated)
+    static constexpr int WSLOTS = 6;                        // most windows resident on the device (compressed + inflated); `wslots` are used
     static constexpr int PSLOTS = 4;                        // pinned staging buffers (one chunk each)
     static constexpr int NSTREAMS = 32;                     // inflate streams created; `nstreams` of them are used (chunks inflated concurrently)
     static constexpr size_t CARRY_CAP = 16u << 20;          // longest partial record carried between windows
@@ -99,25 +99,44 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
     if (end_off == src->first_record || nm == 0) { if (stats) stats->sorted = 1; return 0; }
 
     // ---- windows and their chunks --------------------------------------------------------------------------------
-    uint64_t WIN_IN = 64ull << 20, WIN_OUT = 512ull << 20, CHUNK_IN = 16ull << 20;
+    // Sizes (compressed bytes). Every window costs two host round trips and a dozen small launches, every inflate launch a tail
+    // of warps waiting for the slowest member, so both want to be large; but the first window is not overlapped with anything
+    // and the last one's decode is not either, so a file wants a dozen windows or more. Measured on a 2.7 GB file (sweep b14 /
+    // b15 in profiles/): 128 MiB windows of four 32 MiB chunks 188 ms, 64 MiB / 16 MiB 217 ms, 32 MiB / 16 MiB 247 ms.
+    uint64_t WIN_IN = 64ull << 20, WIN_OUT = 512ull << 20, CHUNK_IN = 0;
+    {
+        const uint64_t total_in = nm ? M[nm - 1].in_off + M[nm - 1].in_len - M[0].in_off : 0;
+        WIN_IN = std::min<uint64_t>(128ull << 20, std::max<uint64_t>(16ull << 20, (total_in / 12 + (1ull << 20)) & ~((1ull << 20) - 1)));
+    }
     if (src->window_bytes) WIN_IN = src->window_bytes;
     if (const char* e = getenv("BDK_BAMDEV_WINDOW_KB")) if (atoll(e) > 0) WIN_IN = (uint64_t)atoll(e) << 10;      // tests: many small windows
+    CHUNK_IN = std::max<uint64_t>(4ull << 20, WIN_IN / 4);
     if (const char* e = getenv("BDK_BAMDEV_CHUNK_KB")) if (atoll(e) > 0) CHUNK_IN = (uint64_t)atoll(e) << 10;
     CHUNK_IN = std::min(CHUNK_IN, WIN_IN);
     std::vector<BamWindow> wins;
     std::vector<BamChunk> chunks;
+    const bool sizes_given = src->window_bytes || getenv("BDK_BAMDEV_WINDOW_KB") || getenv("BDK_BAMDEV_CHUNK_KB");
+    const uint64_t in_end = nm ? M[nm - 1].in_off + M[nm - 1].in_len : 0;
     for (uint64_t i = 0; i < nm;) {
         if (M[i].out_off >= end_off) break;                  // members behind the end of the records
         BamWindow w{i, i, M[i].in_off, 0, M[i].out_off, 0, (uint32_t)chunks.size(), 0};
+        // nothing overlaps the copy and inflate of the first window or the decode of the last one: the windows grow from 16 MiB
+        // to the full size at the start and shrink again towards the end
+        uint64_t win_in = WIN_IN, chunk_in = CHUNK_IN;
+        if (!sizes_given) {
+            win_in = std::min<uint64_t>(WIN_IN, (16ull << 20) << std::min<size_t>(wins.size(), 8));
+            win_in = std::min<uint64_t>(win_in, std::max<uint64_t>(16ull << 20, (in_end - M[i].in_off) / 2));
+            chunk_in = std::max<uint64_t>(4ull << 20, win_in / 4);
+        }
         while (w.m1 < nm && M[w.m1].out_off < end_off &&
-               (w.m1 == w.m0 || (M[w.m1].in_off + M[w.m1].in_len + 8 - w.in_begin <= WIN_IN && w.out_bytes + M[w.m1].out_len <= WIN_OUT))) {
+               (w.m1 == w.m0 || (M[w.m1].in_off + M[w.m1].in_len + 8 - w.in_begin <= win_in && w.out_bytes + M[w.m1].out_len <= WIN_OUT))) {
             w.in_bytes = M[w.m1].in_off + M[w.m1].in_len + 8 - w.in_begin;         // the CRC32 + ISIZE footer travels along
             w.out_bytes += M[w.m1].out_len;
             ++w.m1;
         }
         for (uint64_t j = w.m0; j < w.m1;) {
             BamChunk ch{j, j, M[j].in_off, 0, (uint32_t)wins.size()};
-            while (ch.m1 < w.m1 && (ch.m1 == ch.m0 || M[ch.m1].in_off + M[ch.m1].in_len + 8 - ch.in_begin <= CHUNK_IN)) {
+            while (ch.m1 < w.m1 && (ch.m1 == ch.m0 || M[ch.m1].in_off + M[ch.m1].in_len + 8 - ch.in_begin <= chunk_in)) {
                 ch.in_bytes = M[ch.m1].in_off + M[ch.m1].in_len + 8 - ch.in_begin;
                 ++ch.m1;
             }
@@ -143,7 +162,12 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
     if (!c->bamdev) c->bamdev = new BamDev;
     BamDev* B = (BamDev*)c->bamdev;
     if (!B->ready) {
-        for (int k = 0; k < BamDev::NSTREAMS; ++k) CU(cudaStreamCreateWithFlags(&B->inflate_stream[k], cudaStreamNonBlocking));
+        // the inflate kernels fill every warp slot for as long as there are members; the record-boundary / extraction / classify
+        // launches of the context's stream (highest priority, bdk_create) take the slots that come free first
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        if (getenv("BDK_BAMDEV_NOPRIO")) prio_lo = prio_hi = 0;
+        for (int k = 0; k < BamDev::NSTREAMS; ++k) CU(cudaStreamCreateWithPriority(&B->inflate_stream[k], cudaStreamNonBlocking, prio_lo));
         CU(cudaStreamCreateWithFlags(&B->copy_stream, cudaStreamNonBlocking));
         for (int s = 0; s < BamDev::WSLOTS; ++s) CU(cudaEventCreateWithFlags(&B->ev_decoded[s], cudaEventDisableTiming));
         CU(cudaEventCreate(&B->ev_first)); CU(cudaEventCreate(&B->ev_last));
@@ -159,7 +183,9 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
         CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming)); B->ev_inflated.push_back(b);
     }
     const size_t tab_bytes = (max_members * sizeof(bgz::Member) + 255) & ~size_t(255);
-    const int nslots = (int)std::min<size_t>(BamDev::WSLOTS, nwin);
+    int wslots = 4;               // windows resident: one being decoded, the others being inflated / copied
+    if (const char* e = getenv("BDK_BAMDEV_WSLOTS")) wslots = std::max(2, std::min(atoi(e), (int)BamDev::WSLOTS));
+    const int nslots = (int)std::min<size_t>((size_t)wslots, nwin);
     const uint64_t max_n = BamDev::CARRY_CAP + max_out;                 // bytes of a window incl. the carry
     const uint64_t max_seg = max_n / bamdev::SEG_BYTES + 2, max_rec = max_n / 36 + 2;
     for (int s = 0; s < nslots; ++s) {
@@ -207,7 +233,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
     auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count() * 1e3; };
     if (trace) fprintf(stderr, "[bamdev] %.1f ms: %zu windows, %zu chunks planned, buffers ready\n", since(), nwin, nchunk);
     // ---- producer ----------------------------------------------------------------------------------------------------
-    int nstreams = 8;             // measured (profiles/bamdev_sweep_*): 16 MiB chunks on 8 streams; smaller chunks lose to launch tails
+    int nstreams = 8;             // chunks inflated concurrently (measured: 4 streams lose 20 % to empty warp slots, 16 change nothing)
     if (const char* e = getenv("BDK_BAMDEV_STREAMS")) nstreams = std::max(1, std::min(atoi(e), (int)BamDev::NSTREAMS));
     std::atomic<int64_t> launched(0), decoded(0);            // chunks whose inflate is launched; windows decoded
     std::atomic<int> producer_rc(0);
@@ -224,14 +250,14 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
         for (size_t g = 0; g < nchunk && !stop; ++g) {
             BamChunk const& C = chunks[g];
             BamWindow const& W = wins[C.window];
-            const int ws = (int)(C.window % BamDev::WSLOTS), ps = (int)(g % BamDev::PSLOTS);
+            const int ws = (int)(C.window % wslots), ps = (int)(g % BamDev::PSLOTS);
             cudaStream_t ist = B->inflate_stream[g % nstreams];
             const size_t ev = g % ring;
             if (g >= (size_t)BamDev::PSLOTS)              // the pinned buffer is free once the copy of chunk g - PSLOTS is through
                 if ((e = cudaEventSynchronize(B->ev_copied[(g - BamDev::PSLOTS) % ring])) != cudaSuccess) return bad("cudaEventSynchronize", e);
             const bool first_of_window = g == W.c0;
-            if (first_of_window && C.window >= (uint32_t)BamDev::WSLOTS) {      // the device slot is free once window w - WSLOTS is decoded
-                while (decoded.load(std::memory_order_acquire) < (int64_t)C.window - BamDev::WSLOTS + 1 && !stop) std::this_thread::sleep_for(std::chrono::microseconds(50));
+            if (first_of_window && C.window >= (uint32_t)wslots) {      // the device slot is free once window w - wslots is decoded
+                while (decoded.load(std::memory_order_acquire) < (int64_t)C.window - wslots + 1 && !stop) std::this_thread::sleep_for(std::chrono::microseconds(50));
                 if (stop) break;
                 if ((e = cudaStreamWaitEvent(B->copy_stream, B->ev_decoded[ws], 0)) != cudaSuccess) return bad("cudaStreamWaitEvent", e);
             }
@@ -300,16 +326,22 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
     uint32_t* dnrec = (uint32_t*)(dinfo + 1);
     uint32_t* dkept = dnrec + 1;
     uint32_t* dunsorted = dnrec + 2;
+    const bool inflate_only = getenv("BDK_BAMDEV_INFLATE_ONLY") != nullptr;
     auto consume = [&]() -> int {
         CU(cudaMemsetAsync(dunsorted, 0, 4, c->stream));
         for (size_t w = 0; w < nwin; ++w) {
-            const int s = (int)(w % BamDev::WSLOTS);
+            const int s = (int)(w % wslots);
             BamWindow const& W = wins[w];
             while (launched.load(std::memory_order_acquire) < (int64_t)W.c1) std::this_thread::sleep_for(std::chrono::microseconds(20));
             if (producer_rc) return fail(c, producer_rc.load(), "bdk_push_bam: %s", producer_err.c_str());
             for (uint32_t g = W.c0; g < W.c1; ++g) CU(cudaStreamWaitEvent(c->stream, B->ev_inflated[g % ring], 0));
             const bool last = w + 1 == nwin;
             const uint64_t nmem = W.m1 - W.m0;
+            if (inflate_only) {                              // measurement aid (BDK_BAMDEV_INFLATE_ONLY): the producer's side alone
+                CU(cudaEventRecord(B->ev_decoded[s], c->stream));
+                decoded.store((int64_t)w + 1, std::memory_order_release);
+                continue;
+            }
             // the window's bytes: [carry][members' output], the first window from the first record, the last one up to end_off
             const uint64_t skip = w == 0 ? src->first_record - W.out_begin : 0;
             const uint8_t* raw = (const uint8_t*)B->d_raw[s].p + BamDev::CARRY_CAP + skip - carry;
@@ -390,7 +422,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
             const uint64_t new_carry = n - hinfo->tail;
             if (!last) {
                 if (new_carry > BamDev::CARRY_CAP) return fail(c, BDK_ERR_DATA, "a BAM record longer than %zu bytes: not supported by the device decode", BamDev::CARRY_CAP);
-                const int s2 = (int)((w + 1) % BamDev::WSLOTS);
+                const int s2 = (int)((w + 1) % wslots);
                 if (new_carry)
                     CU(cudaMemcpyAsync((uint8_t*)B->d_raw[s2].p + BamDev::CARRY_CAP - new_carry, raw + hinfo->tail, new_carry, cudaMemcpyDeviceToDevice, c->stream));
             }

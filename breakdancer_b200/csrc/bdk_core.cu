@@ -469,7 +469,12 @@ int bdk_create(bdk_ctx** out, int device, const bdk_params* p) {
         }                                                                                           \
     } while (0)
     CUC(cudaSetDevice(device));
-    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    {   // highest priority: beside the inflate kernels of bdk_push_bam (lowest) these launches get the warp slots that come free
+        int prio_lo = 0, prio_hi = 0;
+        CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        if (getenv("BDK_BAMDEV_NOPRIO")) prio_hi = 0;
+        CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) { CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)); CUC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming)); }

@@ -304,14 +304,17 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
     const uint32_t bitlim = 8 * (in_len - b.origin) + b.bits_skip;     // over_end(): 32 * widx + off > bitlim
     asm volatile(
         "{\n\t"
-        ".reg .pred p, pl, pq;\n\t"
-        ".reg .b32 v, a, e, l, t, u, lx, len, f, dl, dx, dist, noff, so, j;\n\t"
-        ".reg .b64 ad;\n\t"
+        ".reg .pred p, pq, ppend;\n\t"
+        ".reg .b32 v, a, e, l, t, u, lx, len, f, dl, dx, dist, noff, so, j, pval;\n\t"
+        ".reg .b64 ad, pad;\n\t"
+        "setp.eq.u32 ppend, %14, 0xffffffff;\n\t"           // no store waiting
+        "mov.b32 pval, 0;\n\t"
+        "mov.b64 pad, %9;\n\t"
         ".reg .f32 fd, fq, fj;\n\t"
-        "BGZW_TOP:\n\t"
         "setp.lt.u32 p, %4, 32;\n\t"
         "@p bra.uni BGZW_LOOK;\n\t"
         // slide the window by one word; the bounds of input and output, once per 32 bits
+        "BGZW_SLIDE:\n\t"
         "mov.b32 %0, %1;\n\t"
         "mov.b32 %1, %2;\n\t"
         "mov.b32 %2, %3;\n\t"
@@ -340,7 +343,9 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "mad.wide.u32 ad, %6, 1, %9;\n\t"
         "st.global.u8 [ad], t;\n\t"
         "add.u32 %6, %6, 1;\n\t"
-        "bra.uni BGZW_TOP;\n\t"
+        "setp.lt.u32 p, %4, 32;\n\t"
+        "@p bra.uni BGZW_LOOK;\n\t"
+        "bra.uni BGZW_SLIDE;\n\t"
         "BGZW_MATCH:\n\t"
         // no code length in the entry (a longer code, an illegal symbol) or the end of the block (7 "extra bits"): the long way
         "setp.eq.u32 p, l, 0;\n\t"
@@ -384,30 +389,52 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "setp.gt.or.u32 p, t, %10, p;\n\t"
         "@p bra.uni BGZW_OUT;\n\t"
         // the copy: byte j of the match is byte (j mod dist) of the dist bytes in front of it, 32 bytes a round, lane = j mod 32.
-        // (j + 0.5) / dist truncates to floor(j / dist) for all j < 258 and dist >= 1 with a quotient good to 2 ulp: small_mod()
+        // The store of a match's last round waits in registers (pad, pval, ppend) until the next match begins (or the loop
+        // ends): issued right behind its load it would hold the warp for the load's whole latency at every match; this way
+        // the next symbols are decoded meanwhile. Nothing reads those bytes before the next match's loads.
         "bar.warp.sync 0xffffffff;\n\t"
+        "@ppend st.global.u8 [pad], pval;\n\t"
         "sub.u32 so, %6, dist;\n\t"
+        "mov.b32 j, %14;\n\t"
+        "setp.ge.u32 pq, dist, len;\n\t"
+        "@pq bra.uni BGZW_PLAIN;\n\t"
+        // source and destination overlap (dist < len <= 258): (j + 0.5) / dist truncates to floor(j / dist) with a quotient good
+        // to 2 ulp (small_mod())
         "cvt.rn.f32.u32 fd, dist;\n\t"
         "rcp.approx.ftz.f32 fd, fd;\n\t"
-        "mov.b32 j, %14;\n\t"
         "mov.f32 fq, %15;\n\t"
-        "BGZW_COPY:\n\t"
-        "setp.lt.u32 pl, j, len;\n\t"
+        "BGZW_OVER:\n\t"
+        "setp.lt.u32 ppend, j, len;\n\t"
         "mul.ftz.f32 fj, fq, fd;\n\t"
         "cvt.rzi.u32.f32 u, fj;\n\t"
         "mul.lo.u32 u, u, dist;\n\t"
         "sub.u32 u, j, u;\n\t"
         "add.u32 u, u, so;\n\t"
         "mad.wide.u32 ad, u, 1, %9;\n\t"
-        "ld.global.u8 u, [ad];\n\t"                 // (lanes beyond the match read a byte in front of it: valid, unused)
+        "ld.global.u8 pval, [ad];\n\t"              // (lanes beyond the match read a byte in front of it: valid, unused)
         "add.u32 a, %6, j;\n\t"
-        "mad.wide.u32 ad, a, 1, %9;\n\t"
-        "@pl st.global.u8 [ad], u;\n\t"
+        "mad.wide.u32 pad, a, 1, %9;\n\t"
         "add.u32 j, j, 32;\n\t"
         "add.f32 fq, fq, 0f42000000;\n\t"
         "sub.u32 a, j, %14;\n\t"
         "setp.lt.u32 p, a, len;\n\t"
-        "@p bra.uni BGZW_COPY;\n\t"
+        "@!p bra.uni BGZW_COPIED;\n\t"
+        "@ppend st.global.u8 [pad], pval;\n\t"
+        "bra.uni BGZW_OVER;\n\t"
+        "BGZW_PLAIN:\n\t"
+        "setp.lt.u32 ppend, j, len;\n\t"
+        "add.u32 u, so, j;\n\t"
+        "mad.wide.u32 ad, u, 1, %9;\n\t"
+        "ld.global.u8 pval, [ad];\n\t"
+        "add.u32 a, %6, j;\n\t"
+        "mad.wide.u32 pad, a, 1, %9;\n\t"
+        "add.u32 j, j, 32;\n\t"
+        "sub.u32 a, j, %14;\n\t"
+        "setp.lt.u32 p, a, len;\n\t"
+        "@!p bra.uni BGZW_COPIED;\n\t"
+        "@ppend st.global.u8 [pad], pval;\n\t"
+        "bra.uni BGZW_PLAIN;\n\t"
+        "BGZW_COPIED:\n\t"
         "mov.b32 %6, t;\n\t"
         "mov.b32 %4, noff;\n\t"
         "setp.lt.u32 p, noff, 32;\n\t"
@@ -420,8 +447,11 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "mad.wide.u32 ad, t, 4, %8;\n\t"
         "ld.global.u32 %3, [ad];\n\t"
         "sub.u32 %4, %4, 32;\n\t"
-        "bra.uni BGZW_TOP;\n\t"
+        "setp.lt.u32 p, %4, 32;\n\t"
+        "@p bra.uni BGZW_LOOK;\n\t"
+        "bra.uni BGZW_SLIDE;\n\t"
         "BGZW_OUT:\n\t"
+        "@ppend st.global.u8 [pad], pval;\n\t"
         "}"
         : "+r"(b.lo), "+r"(b.hi), "+r"(b.hi2), "+r"(b.ahead), "+r"(b.off), "+r"(b.widx), "+r"(op)
         : "r"(b.wlim), "l"(b.w0), "l"(out), "r"(out_len), "r"(bitlim), "r"(t_ll), "r"(t_d), "r"(lane), "f"(lane_half)

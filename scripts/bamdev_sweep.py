@@ -11,12 +11,17 @@ for bam, cols in synth.split_by_bam(w).items():
 open(os.path.join(tmp, "cfg"), "w").write(w.config_text())
 os.chdir(tmp)
 cfg = api.BamConfig(path="cfg")
-settings = [dict(BDK_BAMDEV_CHUNK_KB="16384", BDK_BAMDEV_STREAMS="4"), dict(BDK_BAMDEV_CHUNK_KB="16384", BDK_BAMDEV_STREAMS="8"),
-            dict(BDK_BAMDEV_CHUNK_KB="16384", BDK_BAMDEV_STREAMS="12"), dict(BDK_BAMDEV_CHUNK_KB="32768", BDK_BAMDEV_STREAMS="3"),
-            dict(BDK_BAMDEV_CHUNK_KB="32768", BDK_BAMDEV_STREAMS="6"), dict(BDK_BAMDEV_CHUNK_KB="16384", BDK_BAMDEV_STREAMS="8", BDK_BAMDEV_WINDOW_KB="131072"),
-            dict(BDK_BAMDEV_CHUNK_KB="32768", BDK_BAMDEV_STREAMS="4", BDK_BAMDEV_WINDOW_KB="131072"), dict(BDK_BAMDEV_CHUNK_KB="65536", BDK_BAMDEV_STREAMS="3", BDK_BAMDEV_WINDOW_KB="131072")]
+settings = [dict(BDK_BAMDEV_NOPRIO="1"), dict(), dict(BDK_BAMDEV_WSLOTS="4"), dict(BDK_BAMDEV_WSLOTS="6"),
+            dict(BDK_BAMDEV_CHUNK_KB="32768", BDK_BAMDEV_STREAMS="4", BDK_BAMDEV_WSLOTS="4"),
+            dict(BDK_BAMDEV_CHUNK_KB="32768", BDK_BAMDEV_STREAMS="8", BDK_BAMDEV_WSLOTS="4", BDK_BAMDEV_WINDOW_KB="131072"),
+            dict(BDK_BAMDEV_CHUNK_KB="65536", BDK_BAMDEV_STREAMS="4", BDK_BAMDEV_WSLOTS="4", BDK_BAMDEV_WINDOW_KB="131072"),
+            dict(BDK_BAMDEV_CHUNK_KB="8192", BDK_BAMDEV_STREAMS="16", BDK_BAMDEV_WSLOTS="4"),
+            dict(BDK_BAMDEV_WSLOTS="4", BDK_BAMDEV_WINDOW_KB="32768")]
+if len(sys.argv) > 2:
+    settings = json.loads(sys.argv[2])
+KNOBS = ("BDK_BAMDEV_STREAMS", "BDK_BAMDEV_CHUNK_KB", "BDK_BAMDEV_WINDOW_KB", "BDK_BAMDEV_WSLOTS", "BDK_BAMDEV_NOPRIO")
 for s in settings:
-    for k in ("BDK_BAMDEV_STREAMS", "BDK_BAMDEV_CHUNK_KB", "BDK_BAMDEV_WINDOW_KB"):
+    for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update(s)
     dev = api.BamDevice(cfg)
