@@ -15,13 +15,18 @@
 // of window w and the copies of window w + 2. A window's inflated bytes are written at a fixed offset of its buffer; the bytes of
 // a record cut off by the end of window w are copied in front of window w + 1's (`carry`), so records are parsed where they lie.
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 namespace {
 
 struct BamDev {
     static constexpr int WSLOTS = 6;                        // most windows resident on the device (compressed + inflated); `wslots` are used
-    static constexpr int PSLOTS = 4;                        // pinned staging buffers (one chunk each)
+    static constexpr int PSLOTS = 4;                        // pinned staging buffers (one piece of PIECE bytes each)
+    static constexpr size_t PIECE = 16u << 20;              // what is staged and copied at a time (a chunk is one or more pieces)
+    cudaEvent_t ev_piece[PSLOTS] = {};                      // the copy out of a staging buffer is through
     static constexpr int NSTREAMS = 32;                     // inflate streams created; `nstreams` of them are used (chunks inflated concurrently)
     static constexpr size_t CARRY_CAP = 16u << 20;          // longest partial record carried between windows
     cudaStream_t inflate_stream[NSTREAMS] = {}, copy_stream = nullptr;
@@ -39,7 +44,7 @@ struct BamDev {
 
 void bamdev_free(BamDev* B) {
     if (!B) return;
-    for (int s = 0; s < BamDev::PSLOTS; ++s) if (B->h_slot[s]) cudaFreeHost(B->h_slot[s]);
+    for (int s = 0; s < BamDev::PSLOTS; ++s) { if (B->h_slot[s]) cudaFreeHost(B->h_slot[s]); if (B->ev_piece[s]) cudaEventDestroy(B->ev_piece[s]); }
     for (int s = 0; s < BamDev::WSLOTS; ++s) {
         if (B->h_tab[s]) cudaFreeHost(B->h_tab[s]);
         for (DevBuf* b : {&B->d_slot[s], &B->d_raw[s], &B->d_status[s]}) if (b->p) cudaFree(b->p);
@@ -73,6 +78,52 @@ struct BamCollect {
     void release() { for (auto& b : cols) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; } n = 0; }
 };
 
+// A few threads that copy ranges of one buffer side by side (the staging of the compressed file into pinned memory): started
+// once per pipeline, woken per piece.
+class CopyPool {
+public:
+    explicit CopyPool(int n) : n_(std::max(1, n)) {
+        for (int t = 1; t < n_; ++t) th_.emplace_back([this, t] { work(t); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(m_); quit_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // fn(lo, hi) over [0, bytes) cut into one range per thread (fewer for small sizes); returns when all are done
+    template <class F> void run(uint64_t bytes, F fn) {
+        const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_, bytes >> 20));
+        job_ = [&fn, bytes, parts](int t) { if (t < parts) fn(bytes * (uint64_t)t / parts, bytes * (uint64_t)(t + 1) / parts); };
+        { std::lock_guard<std::mutex> g(m_); pending_ = n_ - 1; ++gen_; }
+        cv_.notify_all();
+        job_(0);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+private:
+    void work(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) return;
+            }
+            job_(t);
+            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::function<void(int)> job_;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool quit_ = false;
+};
+
 // host_out == nullptr && collect == nullptr: classify the records (bdk_push_bam); host_out: copy the decoded columns into the
 // caller's host arrays of `cap` records and classify nothing (bdk_decode_bam); collect: keep them on the device (bdk_push_bams).
 int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, const bdk_soa* host_out, uint64_t cap, BamCollect* collect = nullptr) {
@@ -99,34 +150,33 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
     if (end_off == src->first_record || nm == 0) { if (stats) stats->sorted = 1; return 0; }
 
     // ---- windows and their chunks --------------------------------------------------------------------------------
-    // Sizes (compressed bytes). Every window costs two host round trips and a dozen small launches, every inflate launch a tail
-    // of warps waiting for the slowest member, so both want to be large; but the first window is not overlapped with anything
-    // and the last one's decode is not either, so a file wants a dozen windows or more. Measured on a 2.7 GB file (sweep b14 /
-    // b15 in profiles/): 128 MiB windows of four 32 MiB chunks 188 ms, 64 MiB / 16 MiB 217 ms, 32 MiB / 16 MiB 247 ms.
-    uint64_t WIN_IN = 64ull << 20, WIN_OUT = 512ull << 20, CHUNK_IN = 0;
+    // Sizes (compressed bytes). The decode of a window is a dozen dependent launches and two host round trips on the context's
+    // stream while the inflate kernels of the next windows hold every warp slot: about 5 ms per window whatever its size, and
+    // the windows are decoded one after the other -- with 64 MiB windows that chain, not the inflate, bounded the run (trace:
+    // the producer waited 82 of 175 ms for window slots). So windows are as large as the file allows with a dozen of them left
+    // to overlap, up to 256 MiB; an inflate launch is a 32 MiB chunk of a window (1600 members: eight in flight fill the warp
+    // slots, and a chunk starts as soon as its bytes are there). Measured on a 2.7 GB file (sweeps b14 / b15 / b22 in profiles/).
+    uint64_t WIN_IN = 64ull << 20, WIN_OUT = 1024ull << 20, CHUNK_IN = 0;
     {
         const uint64_t total_in = nm ? M[nm - 1].in_off + M[nm - 1].in_len - M[0].in_off : 0;
-        WIN_IN = std::min<uint64_t>(128ull << 20, std::max<uint64_t>(16ull << 20, (total_in / 12 + (1ull << 20)) & ~((1ull << 20) - 1)));
+        WIN_IN = std::min<uint64_t>(256ull << 20, std::max<uint64_t>(16ull << 20, (total_in / 12 + (1ull << 20)) & ~((1ull << 20) - 1)));
     }
     if (src->window_bytes) WIN_IN = src->window_bytes;
     if (const char* e = getenv("BDK_BAMDEV_WINDOW_KB")) if (atoll(e) > 0) WIN_IN = (uint64_t)atoll(e) << 10;      // tests: many small windows
-    CHUNK_IN = std::max<uint64_t>(4ull << 20, WIN_IN / 4);
+    CHUNK_IN = std::min<uint64_t>(32ull << 20, std::max<uint64_t>(4ull << 20, WIN_IN / 4));
     if (const char* e = getenv("BDK_BAMDEV_CHUNK_KB")) if (atoll(e) > 0) CHUNK_IN = (uint64_t)atoll(e) << 10;
     CHUNK_IN = std::min(CHUNK_IN, WIN_IN);
     std::vector<BamWindow> wins;
     std::vector<BamChunk> chunks;
     const bool sizes_given = src->window_bytes || getenv("BDK_BAMDEV_WINDOW_KB") || getenv("BDK_BAMDEV_CHUNK_KB");
-    const uint64_t in_end = nm ? M[nm - 1].in_off + M[nm - 1].in_len : 0;
     for (uint64_t i = 0; i < nm;) {
         if (M[i].out_off >= end_off) break;                  // members behind the end of the records
         BamWindow w{i, i, M[i].in_off, 0, M[i].out_off, 0, (uint32_t)chunks.size(), 0};
-        // nothing overlaps the copy and inflate of the first window or the decode of the last one: the windows grow from 16 MiB
-        // to the full size at the start and shrink again towards the end
+        // nothing overlaps the copy and inflate of the first window: the first two are small (16 and 64 MiB)
         uint64_t win_in = WIN_IN, chunk_in = CHUNK_IN;
-        if (!sizes_given) {
-            win_in = std::min<uint64_t>(WIN_IN, (16ull << 20) << std::min<size_t>(wins.size(), 8));
-            win_in = std::min<uint64_t>(win_in, std::max<uint64_t>(16ull << 20, (in_end - M[i].in_off) / 2));
-            chunk_in = std::max<uint64_t>(4ull << 20, win_in / 4);
+        if (!sizes_given && wins.size() < 2) {
+            win_in = std::min<uint64_t>(WIN_IN, (16ull << 20) << (2 * wins.size()));
+            chunk_in = std::min<uint64_t>(CHUNK_IN, std::max<uint64_t>(4ull << 20, win_in / 4));
         }
         while (w.m1 < nm && M[w.m1].out_off < end_off &&
                (w.m1 == w.m0 || (M[w.m1].in_off + M[w.m1].in_len + 8 - w.in_begin <= win_in && w.out_bytes + M[w.m1].out_len <= WIN_OUT))) {
@@ -170,6 +220,7 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
         for (int k = 0; k < BamDev::NSTREAMS; ++k) CU(cudaStreamCreateWithPriority(&B->inflate_stream[k], cudaStreamNonBlocking, prio_lo));
         CU(cudaStreamCreateWithFlags(&B->copy_stream, cudaStreamNonBlocking));
         for (int s = 0; s < BamDev::WSLOTS; ++s) CU(cudaEventCreateWithFlags(&B->ev_decoded[s], cudaEventDisableTiming));
+        for (int s = 0; s < BamDev::PSLOTS; ++s) CU(cudaEventCreateWithFlags(&B->ev_piece[s], cudaEventDisableTiming));
         CU(cudaEventCreate(&B->ev_first)); CU(cudaEventCreate(&B->ev_last));
         CU(cudaHostAlloc((void**)&B->h_info, 256, cudaHostAllocDefault));
         CU(cudaFuncSetAttribute(bgzw::bgzf_inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(bgzw::Tables) * bgzw::WARPS_PER_CTA)));
@@ -239,8 +290,11 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
     std::atomic<int> producer_rc(0);
     std::atomic<bool> stop(false);
     std::string producer_err;
-    double stage_s = 0;
-    const int copy_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    double stage_s = 0, wait_pinned_s = 0, wait_slot_s = 0;
+    int copy_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("BDK_BAMDEV_COPY_THREADS")) copy_threads = std::max(1, std::min(atoi(e), 64));
+    CopyPool copiers(copy_threads);
+    uint64_t piece = 0;
     std::thread producer([&]() {
         auto bad = [&](const char* what, cudaError_t e) { producer_err = std::string(what) + ": " + cudaGetErrorString(e); producer_rc = BDK_ERR_CUDA; launched = (int64_t)nchunk + 1; };
         cudaError_t e = cudaSetDevice(c->device);
@@ -250,16 +304,16 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
         for (size_t g = 0; g < nchunk && !stop; ++g) {
             BamChunk const& C = chunks[g];
             BamWindow const& W = wins[C.window];
-            const int ws = (int)(C.window % wslots), ps = (int)(g % BamDev::PSLOTS);
+            const int ws = (int)(C.window % wslots);
             cudaStream_t ist = B->inflate_stream[g % nstreams];
             const size_t ev = g % ring;
-            if (g >= (size_t)BamDev::PSLOTS)              // the pinned buffer is free once the copy of chunk g - PSLOTS is through
-                if ((e = cudaEventSynchronize(B->ev_copied[(g - BamDev::PSLOTS) % ring])) != cudaSuccess) return bad("cudaEventSynchronize", e);
+            const auto tw1 = std::chrono::steady_clock::now();
             const bool first_of_window = g == W.c0;
             if (first_of_window && C.window >= (uint32_t)wslots) {      // the device slot is free once window w - wslots is decoded
                 while (decoded.load(std::memory_order_acquire) < (int64_t)C.window - wslots + 1 && !stop) std::this_thread::sleep_for(std::chrono::microseconds(50));
                 if (stop) break;
                 if ((e = cudaStreamWaitEvent(B->copy_stream, B->ev_decoded[ws], 0)) != cudaSuccess) return bad("cudaStreamWaitEvent", e);
+                wait_slot_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw1).count();
             }
             if (first_of_window) {                            // the window's member table
                 bgz::Member* tab = (bgz::Member*)B->h_tab[ws];
@@ -270,28 +324,29 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
                 }
                 if ((e = cudaMemcpyAsync(B->d_slot[ws].p, tab, nmem * sizeof(bgz::Member), cudaMemcpyHostToDevice, B->copy_stream)) != cudaSuccess) return bad("cudaMemcpyAsync (member table)", e);
             }
-            if (B->h_cap[ps] < max_chunk + 64) {
-                if (B->h_slot[ps]) cudaFreeHost(B->h_slot[ps]);
-                B->h_slot[ps] = nullptr; B->h_cap[ps] = 0;
-                if ((e = cudaHostAlloc(&B->h_slot[ps], max_chunk + 64, cudaHostAllocDefault)) != cudaSuccess) return bad("cudaHostAlloc (staging buffer)", e);
-                B->h_cap[ps] = max_chunk + 64;
-            }
-            uint8_t* hs = (uint8_t*)B->h_slot[ps];
-            {   // file bytes -> pinned buffer, a few threads (page-cache reads through the caller's mapping)
-                const auto ts0 = std::chrono::steady_clock::now();
-                std::vector<std::thread> th;
-                const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)copy_threads, C.in_bytes >> 20));
-                auto part = [&](int t) {
-                    const uint64_t lo = C.in_bytes * t / T, hi = C.in_bytes * (t + 1) / T;
-                    memcpy(hs + lo, src->file + C.in_begin + lo, hi - lo);
-                };
-                for (int t = 1; t < T; ++t) th.emplace_back(part, t);
-                part(0);
-                for (auto& x : th) x.join();
-                stage_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
-            }
+            // file bytes -> pinned buffer (a few threads; page-cache reads through the caller's mapping) -> device, piece by piece
             uint8_t* dcomp = (uint8_t*)B->d_slot[ws].p + tab_bytes;
-            if ((e = cudaMemcpyAsync(dcomp + (C.in_begin - W.in_begin), hs, C.in_bytes, cudaMemcpyHostToDevice, B->copy_stream)) != cudaSuccess) return bad("cudaMemcpyAsync (compressed chunk)", e);
+            for (uint64_t p0 = 0; p0 < C.in_bytes; p0 += BamDev::PIECE, ++piece) {
+                const uint64_t pn = std::min<uint64_t>(BamDev::PIECE, C.in_bytes - p0);
+                const int ps = (int)(piece % BamDev::PSLOTS);
+                const auto tp0 = std::chrono::steady_clock::now();
+                if (piece >= (uint64_t)BamDev::PSLOTS)      // the buffer is free once the copy of piece - PSLOTS is through
+                    if ((e = cudaEventSynchronize(B->ev_piece[ps])) != cudaSuccess) return bad("cudaEventSynchronize", e);
+                if (B->h_cap[ps] < BamDev::PIECE + 64) {
+                    if (B->h_slot[ps]) cudaFreeHost(B->h_slot[ps]);
+                    B->h_slot[ps] = nullptr; B->h_cap[ps] = 0;
+                    if ((e = cudaHostAlloc(&B->h_slot[ps], BamDev::PIECE + 64, cudaHostAllocDefault)) != cudaSuccess) return bad("cudaHostAlloc (staging buffer)", e);
+                    B->h_cap[ps] = BamDev::PIECE + 64;
+                }
+                uint8_t* hs = (uint8_t*)B->h_slot[ps];
+                const auto ts0 = std::chrono::steady_clock::now();
+                wait_pinned_s += std::chrono::duration<double>(ts0 - tp0).count();
+                const uint8_t* from = src->file + C.in_begin + p0;
+                copiers.run(pn, [&](uint64_t lo, uint64_t hi) { memcpy(hs + lo, from + lo, hi - lo); });
+                stage_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
+                if ((e = cudaMemcpyAsync(dcomp + (C.in_begin - W.in_begin) + p0, hs, pn, cudaMemcpyHostToDevice, B->copy_stream)) != cudaSuccess) return bad("cudaMemcpyAsync (compressed bytes)", e);
+                cudaEventRecord(B->ev_piece[ps], B->copy_stream);
+            }
             cudaEventRecord(B->ev_copied[ev], B->copy_stream);
             cudaStreamWaitEvent(ist, B->ev_copied[ev], 0);
             const uint64_t k0 = C.m0 - W.m0, nmem = C.m1 - C.m0;
@@ -312,7 +367,9 @@ int bam_pipeline(bdk_ctx* c, const bdk_bam_source* src, bdk_bam_stats* stats, co
             }
             if ((e = cudaGetLastError()) != cudaSuccess) return bad("bgzf inflate launch", e);
             launched.store((int64_t)g + 1, std::memory_order_release);
-            if (trace && (g == 0 || g + 1 == nchunk)) fprintf(stderr, "[bamdev] %.1f ms: chunk %zu of %zu launched (staging so far %.1f ms)\n", since(), g + 1, nchunk, stage_s * 1e3);
+            if (trace && (g == 0 || g + 1 == nchunk))
+                fprintf(stderr, "[bamdev] %.1f ms: chunk %zu of %zu launched (so far: staging %.1f ms, waiting for a pinned buffer %.1f ms, for a window slot %.1f ms)\n",
+                        since(), g + 1, nchunk, stage_s * 1e3, wait_pinned_s * 1e3, wait_slot_s * 1e3);
         }
     });
 

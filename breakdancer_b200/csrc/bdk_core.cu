@@ -1212,9 +1212,9 @@ int bdk_bgzf_inflate(int device, const uint8_t* file, uint64_t file_bytes, const
     {   // size the buffers for the largest batch
         uint64_t i = 0;
         while (i < n_members) {
-            uint64_t j = i, in_b = 0, out_b = 0;
+            uint64_t j = i, out_b = 0;
             while (j < n_members && (j == i || (members[j].in_off + members[j].in_len - members[i].in_off <= IN_CAP && out_b + members[j].out_len <= OUT_CAP))) {
-                in_b = members[j].in_off + members[j].in_len - members[i].in_off; out_b += members[j].out_len; ++j;
+                out_b += members[j].out_len; ++j;
             }
             max_members = std::max(max_members, j - i);
             i = j;

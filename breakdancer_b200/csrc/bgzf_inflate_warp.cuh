@@ -91,11 +91,12 @@ BGZW_HD uint32_t d_entry(uint32_t sym, uint32_t len) {           // sym <= 29
     return m << 8 | x << 4 | len;
 }
 
-// Bit reader of the warp decoder. Device: a window of three consecutive aligned words (lo, hi, hi2) of the input plus one more
-// already requested (ahead); the read position is a bit offset `off` into lo. normalize() slides the window while off >= 32, so
-// behind it 64 + (32 - off) > 64 bits are valid: a whole literal/length code with its extra bits (<= 20 bits, peek()) and a whole
+// Bit reader of the warp decoder. Device: a window of three consecutive aligned words (lo, hi, hi2) of the input plus two more
+// already requested (ahead, ahead2: a word is asked for two slides -- 64 input bits, half a dozen symbols -- before it is used;
+// with one word in flight the warps sat 16 % of their stall samples on that load, profiles/inflate_warp_b20.md); the read
+// position is a bit offset `off` into lo. normalize() slides the window while off >= 32, so behind it 64 + (32 - off) > 64 bits are valid: a whole literal/length code with its extra bits (<= 20 bits, peek()) and a whole
 // distance code with its (<= 28 bits, peek2()) are read without looking at the window again. Extracting is one funnel shift, the
-// 64-bit shift-and-or of a classic bit buffer is gone, and the load of `ahead` has three words of decoding to arrive. The
+// 64-bit shift-and-or of a classic bit buffer is gone, and a load has two words of decoding to arrive. The
 // compressed bytes sit in a buffer that is readable a few words beyond every member (its CRC32 / ISIZE footer and the next
 // member follow; bdk_bam.inl pads the last one): words beyond `wlim` are not loaded, a damaged stream that runs on decodes the
 // last word again until one of the over_end() checks or the output bound stops it. Host build (fuzz harness, exact-size buffers
@@ -113,10 +114,10 @@ __device__ __forceinline__ uint32_t bgzw_min(uint32_t a, uint32_t b) { return mi
 struct Reader {
 #ifdef BGZW_WINDOW_READER
     const uint32_t* w0;
-    uint32_t lo, hi, hi2, ahead;
+    uint32_t lo, hi, hi2, ahead, ahead2;
     uint32_t off;               // bit offset of the read position in lo
-    uint32_t widx, wlim;        // index (from w0) of the word in `ahead`; last index that may be loaded
-    uint32_t bits_skip;         // 32 * 3 + bits in front of the byte the window was opened at: the bits consumed since then are
+    uint32_t widx, wlim;        // index (from w0) of the word in `ahead2`; last index that may be loaded
+    uint32_t bits_skip;         // 32 * 4 + bits in front of the byte the window was opened at: the bits consumed since then are
                                 // 32 * widx + off - bits_skip (nothing to keep up to date when the window slides)
     uint32_t origin;            // that byte's offset in the member (0, or where a stored block ended)
     BGZW_HD void init(const uint8_t* in, uint32_t n, uint32_t at = 0) {
@@ -124,15 +125,15 @@ struct Reader {
         const uint32_t mis = (uint32_t)((uintptr_t)in & 3);
         w0 = (const uint32_t*)(in - mis);
         wlim = (mis + n + 4) >> 2;                                  // the word that holds in[n + 4], inside the 8-byte footer
-        lo = w0[0]; hi = w0[bgzw_min(1u, wlim)]; hi2 = w0[bgzw_min(2u, wlim)]; ahead = w0[bgzw_min(3u, wlim)];
-        widx = 3;
+        lo = w0[0]; hi = w0[bgzw_min(1u, wlim)]; hi2 = w0[bgzw_min(2u, wlim)]; ahead = w0[bgzw_min(3u, wlim)]; ahead2 = w0[bgzw_min(4u, wlim)];
+        widx = 4;
         off = 8 * mis;
-        bits_skip = 96 + 8 * mis;
+        bits_skip = 128 + 8 * mis;
     }
     BGZW_HD void slide() {
-        lo = hi; hi = hi2; hi2 = ahead;
+        lo = hi; hi = hi2; hi2 = ahead; ahead = ahead2;
         ++widx;
-        ahead = w0[bgzw_min(widx, wlim)];
+        ahead2 = w0[bgzw_min(widx, wlim)];
         off -= 32;
     }
     // at most two slides are ever due: off < 32 after a normalize, and no more than 48 bits are dropped before the next one
@@ -307,9 +308,9 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         ".reg .pred p, pq, ppend;\n\t"
         ".reg .b32 v, a, e, l, t, u, lx, len, f, dl, dx, dist, noff, so, j, pval;\n\t"
         ".reg .b64 ad, pad;\n\t"
-        "setp.eq.u32 ppend, %14, 0xffffffff;\n\t"           // no store waiting
+        "setp.eq.u32 ppend, %15, 0xffffffff;\n\t"           // no store waiting
         "mov.b32 pval, 0;\n\t"
-        "mov.b64 pad, %9;\n\t"
+        "mov.b64 pad, %10;\n\t"
         ".reg .f32 fd, fq, fj;\n\t"
         "setp.lt.u32 p, %4, 32;\n\t"
         "@p bra.uni BGZW_LOOK;\n\t"
@@ -318,20 +319,21 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "mov.b32 %0, %1;\n\t"
         "mov.b32 %1, %2;\n\t"
         "mov.b32 %2, %3;\n\t"
+        "mov.b32 %3, %7;\n\t"
         "add.u32 %5, %5, 1;\n\t"
-        "min.u32 t, %5, %7;\n\t"
-        "mad.wide.u32 ad, t, 4, %8;\n\t"
-        "ld.global.u32 %3, [ad];\n\t"
+        "min.u32 t, %5, %8;\n\t"
+        "mad.wide.u32 ad, t, 4, %9;\n\t"
+        "ld.global.u32 %7, [ad];\n\t"
         "sub.u32 %4, %4, 32;\n\t"
-        "setp.gt.u32 p, %6, %10;\n\t"
+        "setp.gt.u32 p, %6, %11;\n\t"
         "shl.b32 t, %5, 5;\n\t"
         "add.u32 t, t, %4;\n\t"
-        "setp.gt.or.u32 p, t, %11, p;\n\t"
+        "setp.gt.or.u32 p, t, %12, p;\n\t"
         "@p bra.uni BGZW_OUT;\n\t"
         "BGZW_LOOK:\n\t"
         "shf.r.wrap.b32 v, %0, %1, %4;\n\t"
         "and.b32 a, v, 2047;\n\t"
-        "mad.lo.u32 a, a, 2, %12;\n\t"
+        "mad.lo.u32 a, a, 2, %13;\n\t"
         "ld.shared.u16 e, [a];\n\t"
         "and.b32 l, e, 15;\n\t"
         "and.b32 t, e, 0x1000;\n\t"
@@ -340,7 +342,7 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         // a literal (every lane stores the same byte to the same place)
         "add.u32 %4, %4, l;\n\t"
         "shr.u32 t, e, 4;\n\t"
-        "mad.wide.u32 ad, %6, 1, %9;\n\t"
+        "mad.wide.u32 ad, %6, 1, %10;\n\t"
         "st.global.u8 [ad], t;\n\t"
         "add.u32 %6, %6, 1;\n\t"
         "setp.lt.u32 p, %4, 32;\n\t"
@@ -367,7 +369,7 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "@p shf.r.wrap.b32 v, %0, %1, noff;\n\t"
         "@!p shf.r.wrap.b32 v, %1, %2, noff;\n\t"
         "and.b32 a, v, 511;\n\t"
-        "mad.lo.u32 a, a, 2, %13;\n\t"
+        "mad.lo.u32 a, a, 2, %14;\n\t"
         "ld.shared.u16 f, [a];\n\t"
         "and.b32 dl, f, 15;\n\t"
         "shr.u32 dx, f, 4;\n\t"
@@ -386,7 +388,7 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "setp.eq.u32 p, dl, 0;\n\t"
         "setp.gt.or.u32 p, dist, %6, p;\n\t"
         "add.u32 t, %6, len;\n\t"
-        "setp.gt.or.u32 p, t, %10, p;\n\t"
+        "setp.gt.or.u32 p, t, %11, p;\n\t"
         "@p bra.uni BGZW_OUT;\n\t"
         // the copy: byte j of the match is byte (j mod dist) of the dist bytes in front of it, 32 bytes a round, lane = j mod 32.
         // The store of a match's last round waits in registers (pad, pval, ppend) until the next match begins (or the loop
@@ -395,14 +397,14 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "bar.warp.sync 0xffffffff;\n\t"
         "@ppend st.global.u8 [pad], pval;\n\t"
         "sub.u32 so, %6, dist;\n\t"
-        "mov.b32 j, %14;\n\t"
+        "mov.b32 j, %15;\n\t"
         "setp.ge.u32 pq, dist, len;\n\t"
         "@pq bra.uni BGZW_PLAIN;\n\t"
         // source and destination overlap (dist < len <= 258): (j + 0.5) / dist truncates to floor(j / dist) with a quotient good
         // to 2 ulp (small_mod())
         "cvt.rn.f32.u32 fd, dist;\n\t"
         "rcp.approx.ftz.f32 fd, fd;\n\t"
-        "mov.f32 fq, %15;\n\t"
+        "mov.f32 fq, %16;\n\t"
         "BGZW_OVER:\n\t"
         "setp.lt.u32 ppend, j, len;\n\t"
         "mul.ftz.f32 fj, fq, fd;\n\t"
@@ -410,13 +412,13 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "mul.lo.u32 u, u, dist;\n\t"
         "sub.u32 u, j, u;\n\t"
         "add.u32 u, u, so;\n\t"
-        "mad.wide.u32 ad, u, 1, %9;\n\t"
+        "mad.wide.u32 ad, u, 1, %10;\n\t"
         "ld.global.u8 pval, [ad];\n\t"              // (lanes beyond the match read a byte in front of it: valid, unused)
         "add.u32 a, %6, j;\n\t"
-        "mad.wide.u32 pad, a, 1, %9;\n\t"
+        "mad.wide.u32 pad, a, 1, %10;\n\t"
         "add.u32 j, j, 32;\n\t"
         "add.f32 fq, fq, 0f42000000;\n\t"
-        "sub.u32 a, j, %14;\n\t"
+        "sub.u32 a, j, %15;\n\t"
         "setp.lt.u32 p, a, len;\n\t"
         "@!p bra.uni BGZW_COPIED;\n\t"
         "@ppend st.global.u8 [pad], pval;\n\t"
@@ -424,12 +426,12 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "BGZW_PLAIN:\n\t"
         "setp.lt.u32 ppend, j, len;\n\t"
         "add.u32 u, so, j;\n\t"
-        "mad.wide.u32 ad, u, 1, %9;\n\t"
+        "mad.wide.u32 ad, u, 1, %10;\n\t"
         "ld.global.u8 pval, [ad];\n\t"
         "add.u32 a, %6, j;\n\t"
-        "mad.wide.u32 pad, a, 1, %9;\n\t"
+        "mad.wide.u32 pad, a, 1, %10;\n\t"
         "add.u32 j, j, 32;\n\t"
-        "sub.u32 a, j, %14;\n\t"
+        "sub.u32 a, j, %15;\n\t"
         "setp.lt.u32 p, a, len;\n\t"
         "@!p bra.uni BGZW_COPIED;\n\t"
         "@ppend st.global.u8 [pad], pval;\n\t"
@@ -442,10 +444,11 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "mov.b32 %0, %1;\n\t"
         "mov.b32 %1, %2;\n\t"
         "mov.b32 %2, %3;\n\t"
+        "mov.b32 %3, %7;\n\t"
         "add.u32 %5, %5, 1;\n\t"
-        "min.u32 t, %5, %7;\n\t"
-        "mad.wide.u32 ad, t, 4, %8;\n\t"
-        "ld.global.u32 %3, [ad];\n\t"
+        "min.u32 t, %5, %8;\n\t"
+        "mad.wide.u32 ad, t, 4, %9;\n\t"
+        "ld.global.u32 %7, [ad];\n\t"
         "sub.u32 %4, %4, 32;\n\t"
         "setp.lt.u32 p, %4, 32;\n\t"
         "@p bra.uni BGZW_LOOK;\n\t"
@@ -453,7 +456,7 @@ __device__ __forceinline__ void fast_symbols(Reader& b, uint32_t& op, uint8_t* o
         "BGZW_OUT:\n\t"
         "@ppend st.global.u8 [pad], pval;\n\t"
         "}"
-        : "+r"(b.lo), "+r"(b.hi), "+r"(b.hi2), "+r"(b.ahead), "+r"(b.off), "+r"(b.widx), "+r"(op)
+        : "+r"(b.lo), "+r"(b.hi), "+r"(b.hi2), "+r"(b.ahead), "+r"(b.off), "+r"(b.widx), "+r"(op), "+r"(b.ahead2)
         : "r"(b.wlim), "l"(b.w0), "l"(out), "r"(out_len), "r"(bitlim), "r"(t_ll), "r"(t_d), "r"(lane), "f"(lane_half)
         : "memory");
 }

@@ -19,7 +19,7 @@ settings = [dict(BDK_BAMDEV_NOPRIO="1"), dict(), dict(BDK_BAMDEV_WSLOTS="4"), di
             dict(BDK_BAMDEV_WSLOTS="4", BDK_BAMDEV_WINDOW_KB="32768")]
 if len(sys.argv) > 2:
     settings = json.loads(sys.argv[2])
-KNOBS = ("BDK_BAMDEV_STREAMS", "BDK_BAMDEV_CHUNK_KB", "BDK_BAMDEV_WINDOW_KB", "BDK_BAMDEV_WSLOTS", "BDK_BAMDEV_NOPRIO")
+KNOBS = ("BDK_BAMDEV_STREAMS", "BDK_BAMDEV_CHUNK_KB", "BDK_BAMDEV_WINDOW_KB", "BDK_BAMDEV_WSLOTS", "BDK_BAMDEV_NOPRIO", "BDK_BAMDEV_INFLATE_ONLY", "BDK_BAMDEV_COPY_THREADS")
 for s in settings:
     for k in KNOBS:
         os.environ.pop(k, None)

@@ -32,3 +32,5 @@ open(os.path.join(tmp, "cfg"), "w").write(w.config_text())
 for lib in sys.argv[2:]:
     p = subprocess.run([sys.executable, __file__, "--child", os.path.abspath(lib), tmp], capture_output=True, text=True)
     print(p.stdout.strip() or p.stderr[-500:], flush=True)
+    if os.environ.get("BDK_DECODE_TRACE"):
+        print("\n".join(p.stderr.strip().split("\n")[-14:]), flush=True)
