@@ -19,12 +19,23 @@
 
 namespace brec {
 
-BREC_HD uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+// Unaligned little-endian loads. Device: the two aligned words around p and one funnel shift (records lie at any alignment in the
+// inflated stream; four byte loads and three shifts per field made the extraction pass load-issue bound). This reads up to 7
+// bytes beyond p + 4: the device buffers of bdk_bam.inl end in slack for that (d_raw: + 1024 bytes).
 BREC_HD uint32_t ld32(const uint8_t* p) {
 #ifdef __CUDA_ARCH__
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
 #else
     uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+BREC_HD uint32_t ld16(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+    return ld32(p) & 0xffffu;
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8);
 #endif
 }
 BREC_HD int32_t ldi32(const uint8_t* p) { return (int32_t)ld32(p); }
