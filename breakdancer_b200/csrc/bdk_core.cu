@@ -181,12 +181,17 @@ int reset_job(bdk_ctx* c) {
 }
 
 typedef void (*K1Fn)(const K1Args);
+template <int MODE> K1Fn k1_pick(bool smem, bool plain) {
+    if (smem) return plain ? k1_classify_kernel<MODE, true, true> : k1_classify_kernel<MODE, true, false>;
+    return plain ? k1_classify_kernel<MODE, false, true> : k1_classify_kernel<MODE, false, false>;
+}
 K1Fn k1_fn(const bdk_ctx* c) {
     const bool single = c->nkey == 1 && c->P.nbam == 1 && c->ncnt == 1, smem = c->P.nrg <= K1_RG_SMEM;
     const bool keys4 = !single && c->nkey <= 4 && c->P.nbam <= 4 && c->ncnt >= 1 && c->ncnt <= 4 && !c->k1_force_general;
-    if (single) return smem ? k1_classify_kernel<K1_FAST, true> : k1_classify_kernel<K1_FAST, false>;
-    if (keys4) return smem ? k1_classify_kernel<K1_KEYS4, true> : k1_classify_kernel<K1_KEYS4, false>;
-    return smem ? k1_classify_kernel<K1_GENERAL, true> : k1_classify_kernel<K1_GENERAL, false>;
+    const bool plain = !c->P.transchr_rearrange && !c->P.illumina_long_insert;
+    if (single) return k1_pick<K1_FAST>(smem, plain);
+    if (keys4) return k1_pick<K1_KEYS4>(smem, plain);
+    return k1_pick<K1_GENERAL>(smem, plain);
 }
 
 int grow_segments(bdk_ctx* c, uint64_t want);

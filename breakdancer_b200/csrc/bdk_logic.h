@@ -131,14 +131,15 @@ BDK_HD uint32_t classify_hot(int32_t pos, int32_t mpos, int32_t tid, int32_t mti
     const float af = (float)a;
     const bool inter = tid != mtid;
     const bool rr = (flag & 0x10u) != 0;
-    const bool opposite = (((flag >> 4) ^ (flag >> 5)) & 1u) != 0;          // read and mate on different strands
+    const bool opposite = ((flag ^ (flag >> 1)) & 0x10u) != 0;              // read and mate on different strands (bits 4 and 5 differ)
     const bool rf = (pos < mpos) == rr;                                      // reverse read leftmost
     const bool lt_lower = af < lower;
     const bool fr_pair = !inter && opposite;
     bool normal2 = fr_pair && !rf && !(af > upper) && !lt_lower;             // NORMAL_FR
     if (o.long_insert) normal2 = normal2 || (fr_pair && rf && af < upper && !lt_lower);   // ARP_RF re-flagged NORMAL_RF
-    const bool proper = (flag & 0x40Fu) == 0x3u;
-    const bool base_ok = (flag & 0x40Du) == 0x1u && !(o.transchr && !inter);
+    const bool mapped_pair = (flag & 0x40Du) == 0x1u;                        // paired, read and mate mapped, not a duplicate
+    const bool proper = mapped_pair && (flag & 0x2u) != 0;                   // (flag & 0x40F) == 0x3
+    const bool base_ok = mapped_pair && !(o.transchr && !inter);
     const bool mapq_ok = (int32_t)bdqual > min_mapq;
     const bool pre = mapq_ok && base_ok;
     const bool kept = pre && (inter || a <= o.max_sd);

@@ -202,8 +202,10 @@ __host__ __device__ inline size_t k1_smem_bytes(int nrg, int nlib, int ncnt, int
 // shared-memory atomics in the hot loop; the pass-1 proper-pair counts are four byte counters in one register.
 // MODE K1_GENERAL: anything else (up to 64 keys).
 // RG_SMEM: the read-group table fits in shared memory.
+// PLAIN: a run without -t and without -l (the defaults): the two options are compile-time zeros in the classifier (eight of 66
+// instructions per record; the kernel sits on the integer pipe: 0.554 -> 0.516 ms per 100 M records, profiles/k1_classify_r22a.md).
 enum { K1_GENERAL = 0, K1_FAST = 1, K1_KEYS4 = 2 };
-template <int MODE, bool RG_SMEM>
+template <int MODE, bool RG_SMEM, bool PLAIN>
 __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args a) {
     constexpr bool FAST = MODE == K1_FAST, K4 = MODE == K1_KEYS4, SINGLE_KEY = FAST, GEN = MODE == K1_GENERAL;
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     }
 
     // =============================== consumer warps ==================================================
+    ClassifyOpts co = a.co;
+    if (PLAIN) { co.transchr = 0; co.long_insert = 0; }
     uint32_t* my_cnt = s_cnt + threadIdx.x;                                        // this thread's private counter column
     uint32_t spcnt = 0;                                                            // ncnt == 1: pass-1 proper pairs seen by this thread
     uint32_t bad = 0;                                                              // OR of the info words (bit 31: invalid read group)
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     if (RG_SMEM) L = s_rg[ri];
                     else { const int4 q = __ldg(reinterpret_cast<const int4*>(a.rgtab) + ri); L.upper = __int_as_float(q.x); L.lower = __int_as_float(q.y); L.min_mapq = q.z; L.info = (uint32_t)q.w; }
                     const uint32_t ch = classify_hot(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
-                                                     L.upper, L.lower, L.min_mapq, a.co);
+                                                     L.upper, L.lower, L.min_mapq, co);
                     bad |= L.info;
                     if (ch & CH_ANOM) a4 |= 1u << j;
                     if (ch & CH_MPROPER) p4 |= 1u << j;
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                     }
                     if (ch & CH_HIST) {                          // ~1-3 % of the records: full classification, histogram, stash
                         const uint32_t cr = classify_record(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
-                                                            L.upper, L.lower, L.min_mapq, a.co);
+                                                            L.upper, L.lower, L.min_mapq, co);
                         const uint32_t hf = (cr >> CR_HIST_SHIFT) & 0xFu;
                         if (hf) atomicAdd(&s_hist[(L.info & RGI_LIB_MASK) * BDK_NUM_FLAGS + hf], 1u);
                         if (cr & CR_ANOM) {
