@@ -107,20 +107,8 @@ __device__ __forceinline__ void k1_unpack(const int4 a, const int4 b, const int4
     r.rg[0] = rg.x & 0xffffu; r.rg[1] = rg.x >> 16; r.rg[2] = rg.y & 0xffffu; r.rg[3] = rg.y >> 16;
 }
 
-// 4 consecutive records of this lane from a ring stage
-__device__ __forceinline__ void k1_load4_smem(const unsigned char* st, int idx, K1Rec4& r) {
-    const int4 a = *reinterpret_cast<const int4*>(st + K1_OFF_POS + idx * 4);
-    const int4 b = *reinterpret_cast<const int4*>(st + K1_OFF_MPOS + idx * 4);
-    const int4 d = *reinterpret_cast<const int4*>(st + K1_OFF_TID + idx * 4);
-    const int4 e = *reinterpret_cast<const int4*>(st + K1_OFF_MTID + idx * 4);
-    const int4 f = *reinterpret_cast<const int4*>(st + K1_OFF_ISZ + idx * 4);
-    const uint2 fl = *reinterpret_cast<const uint2*>(st + K1_OFF_FLAG + idx * 2);
-    const uint2 rg = *reinterpret_cast<const uint2*>(st + K1_OFF_RG + idx * 2);
-    const uint32_t mq = *reinterpret_cast<const uint32_t*>(st + K1_OFF_MAPQ + idx);
-    k1_unpack(a, b, d, e, f, fl, mq, rg, r);
-}
-
-// the same straight from global memory, with a ragged end (last, partial stage of a push)
+// 4 consecutive records of this lane straight from global memory, with a ragged end (last, partial stage of a push; whole stages
+// come through the ring: k1_load4_stage)
 __device__ __forceinline__ void k1_load4_global(const bdk_soa& c, uint64_t g, int nv, uint32_t pad_rg, K1Rec4& r) {
     if (nv == 4) {
         k1_unpack(ld_stream_v4(c.pos + g), ld_stream_v4(c.mpos + g), ld_stream_v4(c.tid + g), ld_stream_v4(c.mtid + g), ld_stream_v4(c.isize + g),
@@ -160,9 +148,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -174,9 +159,49 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ uint32_t keep_u32(uint32_t v) { uint32_t r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(addr) : "memory");
+}
+// shared-memory loads through 32-bit addresses computed once per kernel: from generic pointers the compiler rebuilds the shared
+// window address (S2R + LEA) at every use inside the stage loop
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 4 consecutive records of this lane from a ring stage, the stage given by its shared-memory address
+__device__ __forceinline__ void k1_load4_stage(uint32_t st, int idx, K1Rec4& r) {
+    const int4 a = lds128(st + K1_OFF_POS + idx * 4);
+    const int4 b = lds128(st + K1_OFF_MPOS + idx * 4);
+    const int4 d = lds128(st + K1_OFF_TID + idx * 4);
+    const int4 e = lds128(st + K1_OFF_MTID + idx * 4);
+    const int4 f = lds128(st + K1_OFF_ISZ + idx * 4);
+    const uint2 fl = lds64(st + K1_OFF_FLAG + idx * 2);
+    const uint2 rg = lds64(st + K1_OFF_RG + idx * 2);
+    const uint32_t mq = lds32(st + K1_OFF_MAPQ + idx);
+    k1_unpack(a, b, d, e, f, fl, mq, rg, r);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
@@ -311,7 +336,10 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
     uint32_t spcnt = 0;                                                            // ncnt == 1: pass-1 proper pairs seen by this thread
     uint32_t bad = 0;                                                              // OR of the info words (bit 31: invalid read group)
     K1Stash* my_stash = a.stash + ((size_t)blockIdx.x * 2 * K1_CTHREADS + threadIdx.x) * K1_STASH;   // + tb * K1_CTHREADS * K1_STASH
-    uint32_t g = 0;                                                                // ring uses so far (same sequence as the producer)
+    uint32_t cstage = 0, cphase = 0;                                               // ring position and its parity (same sequence as the producer)
+    // (through an opaque move: left to itself the compiler rebuilds these from S2R SR_CgaCtaId + LEA at every use)
+    const uint32_t ring_addr = keep_u32(smem_u32(s_ring)), full_addr = keep_u32(smem_u32(s_full)), empty_addr = keep_u32(smem_u32(s_empty));
+    const uint32_t rg_addr = RG_SMEM ? keep_u32(smem_u32(s_rg)) : 0u;
     // state of the previous tile, whose anomalous reads are written out after the current tile is classified
     bool prev_have = false;
     bdk_aread* seg_ar = a.seg_ar + (size_t)blockIdx.x * a.seg_cap;
@@ -338,18 +366,22 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
             uint32_t nst = 0;                                                  // stash slots used by this thread
             K1Stash* stash = my_stash + (size_t)tb * K1_CTHREADS * K1_STASH;
 #pragma unroll 1      // (unrolling the stage loop of the multi-key variant made 11 K instructions: instruction-cache misses were its top stall)
-            for (int s = 0; s < K1_SUBS; ++s) {
-                const uint64_t rec0 = (uint64_t)tile * K1_TILE + (uint64_t)s * K1_SUB;
-                if (rec0 >= a.n) break;
-                const int idx = (warp << 7) + (lane << 2);                     // first of this lane's 4 records inside the stage
+            // stages of this tile that are whole (they come through the ring) and stages that hold records at all: one 64-bit
+            // look at the end of the records per tile instead of two per stage
+            const uint64_t tile_rec0 = (uint64_t)tile * K1_TILE;
+            const uint64_t tile_left = a.n > tile_rec0 ? a.n - tile_rec0 : 0;
+            const int s_whole = (int)(tile_left / K1_SUB < (uint64_t)K1_SUBS ? tile_left / K1_SUB : (uint64_t)K1_SUBS);
+            const int s_any = (int)((tile_left + K1_SUB - 1) / K1_SUB < (uint64_t)K1_SUBS ? (tile_left + K1_SUB - 1) / K1_SUB : (uint64_t)K1_SUBS);
+            const int idx = (warp << 7) + (lane << 2);                         // first of this lane's 4 records inside a stage
+            for (int s = 0; s < s_any; ++s) {
                 K1Rec4 r;
-                const bool staged = rec0 + K1_SUB <= a.n;
-                int stage = 0;
+                const bool staged = s < s_whole;
+                const uint32_t stage = cstage;
                 if (staged) {
-                    stage = g % K1_STAGES;
-                    mbar_wait(&s_full[stage], (g / K1_STAGES) & 1);
-                    k1_load4_smem(s_ring + stage * K1_STAGE_BYTES, idx, r);
+                    mbar_wait_addr(full_addr + stage * 8, cphase);
+                    k1_load4_stage(ring_addr + stage * K1_STAGE_BYTES, idx, r);
                 } else {
+                    const uint64_t rec0 = tile_rec0 + (uint64_t)s * K1_SUB;
                     const uint64_t gi = rec0 + idx;
                     const int nv = gi + 4 <= a.n ? 4 : (gi < a.n ? (int)(a.n - gi) : 0);
                     k1_load4_global(a.c, gi, nv, (uint32_t)a.pad_rg, r);
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t ri = min(r.rg[j], (uint32_t)a.nrg);
                     RgDev L;
-                    if (RG_SMEM) L = s_rg[ri];
+                    if (RG_SMEM) { const int4 q = lds128(rg_addr + ri * 16); L.upper = __int_as_float(q.x); L.lower = __int_as_float(q.y); L.min_mapq = q.z; L.info = (uint32_t)q.w; }
                     else { const int4 q = __ldg(reinterpret_cast<const int4*>(a.rgtab) + ri); L.upper = __int_as_float(q.x); L.lower = __int_as_float(q.y); L.min_mapq = q.z; L.info = (uint32_t)q.w; }
                     const uint32_t ch = classify_hot(r.pos[j], r.mpos[j], r.tid[j], r.mtid[j], r.isz[j], r.flag[j], r.mapq[j],
                                                      L.upper, L.lower, L.min_mapq, co);
@@ -399,8 +431,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_classify_kernel(const K1Args
                 }
                 if (staged) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_empty[stage]);
-                    ++g;
+                    if (lane == 0) mbar_arrive_addr(empty_addr + stage * 8);
+                    if (++cstage == K1_STAGES) { cstage = 0; cphase ^= 1u; }
                 }
                 amask |= a4 << (4 * s); pmask |= p4 << (4 * s);
                 if (GEN) keys[s] = kk;
