@@ -38,7 +38,10 @@ constexpr int K1_THREADS = K1_CTHREADS + 64;                // + producer warp +
 constexpr int K1_SUB = 1024;                                // records per ring stage (128 per consumer warp)
 constexpr int K1_SUBS = 8;                                  // stages per look-back tile
 constexpr int K1_TILE = K1_SUB * K1_SUBS;                   // 8192
-constexpr int K1_STAGES = 3;                                // ring depth
+#ifndef K1_STAGES_N
+#define K1_STAGES_N 3
+#endif
+constexpr int K1_STAGES = K1_STAGES_N;                                // ring depth
 constexpr int K1_STAGE_BYTES = K1_SUB * 25;                 // 25 600
 constexpr int K1_STASH = 32;                                // stash slots per thread and tile (= records per thread)
 constexpr int K1_MAXK = 64;                                 // copy-number keys (bams, or libraries with -a)
