@@ -229,6 +229,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bdh_bamdev_decode": (C.c_int, [vp, vp, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
         "bdh_bamdev_open_next": (vp, [vp, vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
         "bdh_bamdev_push2": (C.c_int, [vp, vp, vp, C.POINTER(BamStats)]),
+        "bdh_bamdev_pushn": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.POINTER(BamStats)]),
+        "bdh_bamdev_decoden": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
         "bdh_bamdev_decode2": (C.c_int, [vp, vp, vp, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
         "bdk_push_bams": (C.c_int, [vp, C.POINTER(BamSource), C.c_int, C.POINTER(BamStats)]),
         "bdk_decode_bams": (C.c_int, [vp, C.POINTER(BamSource), C.c_int, C.POINTER(Soa), u64, C.POINTER(BamStats)]),
@@ -571,6 +573,26 @@ class Context:
         self._check(self._L.bdh_bamdev_decode2(first._h, second._h, self._h, C.byref(soa), cap, st), "bdk_decode_bams")
         n = st[0].kept + st[1].kept
         return {k: v[:n] for k, v in cols.items()}, (st[0].as_dict(), st[1].as_dict())
+
+    def push_bams_n(self, devs):
+        """Any number of bams (config order) decoded on this GPU, merged in BamMerger's order and classified (bdk_push_bams):
+        one stats dict per file. Three or more: the merge order is the priority queue's, computed on the host from device keys."""
+        n = len(devs)
+        hs = (C.c_void_p * n)(*[d._h for d in devs])
+        st = (BamStats * n)()
+        self._check(self._L.bdh_bamdev_pushn(hs, n, self._h, st), "bdk_push_bams")
+        return [st[i].as_dict() for i in range(n)]
+
+    def decode_bams_n(self, devs, cap: int):
+        """The merged records of any number of bams as host columns (bdk_decode_bams): (columns, stats per file)."""
+        n = len(devs)
+        cols = {k: np.empty(cap, dt) for k, dt in COLUMN_DTYPES.items()}
+        soa = make_soa(cols)
+        hs = (C.c_void_p * n)(*[d._h for d in devs])
+        st = (BamStats * n)()
+        self._check(self._L.bdh_bamdev_decoden(hs, n, self._h, C.byref(soa), cap, st), "bdk_decode_bams")
+        kept = sum(st[i].kept for i in range(n))
+        return {k: v[:kept] for k, v in cols.items()}, [st[i].as_dict() for i in range(n)]
 
     def decode_bam(self, dev: "BamDevice", cap: int):
         """The file's records decoded on this GPU, as host columns (bdk_decode_bam): (columns, stats)."""

@@ -99,4 +99,17 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict_
     }
 }
 
+// Three or more bams: the order comes from the host (csrc/host/nway_merge.hpp: the priority queue itself; its tie order depends on
+// the heap's history, so there is nothing to cut) as index | bam << BAM_SHIFT; the columns are gathered through it here.
+constexpr int MAX_BAMS = 16, BAM_SHIFT = 28;
+struct ColumnsN { Columns c[MAX_BAMS]; };
+__global__ void __launch_bounds__(256) gather_n_kernel(const uint32_t* __restrict__ order, uint32_t n, ColumnsN src, Columns out) {
+    for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+        const uint32_t s = order[o], i = s & ((1u << BAM_SHIFT) - 1u);
+        const Columns& c = src.c[s >> BAM_SHIFT];
+        out.pos[o] = c.pos[i]; out.mpos[o] = c.mpos[i]; out.tid[o] = c.tid[i]; out.mtid[o] = c.mtid[i]; out.isize[o] = c.isize[i];
+        out.qlen[o] = c.qlen[i]; out.flag[o] = c.flag[i]; out.rgid[o] = c.rgid[i]; out.mapq[o] = c.mapq[i]; out.qid[o] = c.qid[i];
+    }
+}
+
 }  // namespace bammerge

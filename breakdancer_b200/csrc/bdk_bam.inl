@@ -14,6 +14,8 @@
 // fixed cost, so they want windows as large as memory allows. The inflate of window w + 1 overlaps the decode and classification
 // of window w and the copies of window w + 2. A window's inflated bytes are written at a fixed offset of its buffer; the bytes of
 // a record cut off by the end of window w are copied in front of window w + 1's (`carry`), so records are parsed where they lie.
+#include "host/nway_merge.hpp"
+
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -598,19 +600,104 @@ static int push_two_bams(bdk_ctx* c, const bdk_bam_source* srcs, bdk_bam_stats* 
     return rc;
 }
 
+// Three or more bams (up to bammerge::MAX_BAMS): each decoded on the device into columns that stay there, the packed
+// (tid, pos, strand) keys copied to the host, the reference's merge order computed there by the priority queue itself
+// (csrc/host/nway_merge.hpp: for three or more streams its tie order depends on the heap's history, so it cannot be cut into
+// independent parts the way the two-stream merge is), the order copied back and the columns gathered through it. 12 bytes per record
+// cross PCIe on top of the compressed files. Unsorted bams are fine here: the queue defines the order whatever the keys are.
+int push_many_bams(bdk_ctx* c, const bdk_bam_source* srcs, int nb, bdk_bam_stats* stats, const bdk_soa* host_out, uint64_t cap) {
+    static const size_t width[10] = {4, 4, 4, 4, 4, 2, 1, 2, 4, 8};
+    std::vector<BamCollect> col((size_t)nb);
+    BamCollect merged;
+    std::vector<DevBuf> d_k((size_t)nb);
+    DevBuf d_order;
+    auto cleanup = [&]() {
+        for (auto& x : col) x.release();
+        merged.release();
+        for (auto& b : d_k) if (b.p) { cudaFree(b.p); b.p = nullptr; }
+        if (d_order.p) { cudaFree(d_order.p); d_order.p = nullptr; }
+    };
+    std::vector<bdk_bam_stats> local_stats((size_t)nb);
+    if (!stats) stats = local_stats.data();
+    auto run = [&]() -> int {
+        uint64_t n = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int rc = bam_pipeline(c, &srcs[b], &stats[b], nullptr, 0, &col[b]);
+            if (rc) return rc;
+            if (col[b].n >= (1ull << bammerge::BAM_SHIFT)) return fail(c, BDK_ERR_ARG, "bam %d has 2^%d records or more: too many for the device merge of several bams", b, bammerge::BAM_SHIFT);
+            n += col[b].n;
+        }
+        if (n > 0x7ffffff0ull) return fail(c, BDK_ERR_ARG, "more than 2^31 records in a device merge");
+        if (n == 0) return 0;
+        cudaStream_t st = c->stream;
+        tstart(c, T_EXTRACT);
+        std::vector<std::vector<uint64_t>> hk((size_t)nb);
+        for (int b = 0; b < nb; ++b) {
+            if (!col[b].n) continue;
+            ENS(d_k[b], col[b].n * 8);
+            const bamdev::Columns v = col[b].view();
+            bammerge::keys_kernel<<<kNumSMs * 8, 256, 0, st>>>(v.tid, v.pos, v.flag, (uint32_t)col[b].n, d_k[b].as<unsigned long long>());
+            hk[b].resize(col[b].n);
+            CU(cudaMemcpyAsync(hk[b].data(), d_k[b].p, col[b].n * 8, cudaMemcpyDeviceToHost, st));
+            c->launches += 1;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        std::vector<uint32_t> order(n);
+        {
+            std::vector<const uint64_t*> kp((size_t)nb);
+            std::vector<uint64_t> counts((size_t)nb);
+            for (int b = 0; b < nb; ++b) { kp[b] = hk[b].data(); counts[b] = hk[b].size(); }
+            bdh::nway_merge_order(kp.data(), counts.data(), nb, bammerge::BAM_SHIFT, order.data());
+        }
+        ENS(d_order, (size_t)n * 4);
+        CU(cudaMemcpyAsync(d_order.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < 10; ++k) ENS(merged.cols[k], (size_t)n * width[k]);
+        bammerge::ColumnsN all;
+        memset(&all, 0, sizeof all);
+        for (int b = 0; b < nb; ++b) all.c[b] = col[b].view();
+        bammerge::gather_n_kernel<<<kNumSMs * 16, 256, 0, st>>>(d_order.as<uint32_t>(), (uint32_t)n, all, merged.view());
+        tstop(c, T_EXTRACT);
+        c->launches += 1;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));           // `order` is a local
+        tcollect(c);
+        stats[0].merge_parts = 1; stats[0].merge_longest_part = (uint32_t)std::min<uint64_t>(n, 0xffffffffu);
+        for (auto& x : col) x.release();
+        const bamdev::Columns m = merged.view();
+        if (host_out) {
+            if (n > cap) return fail(c, BDK_ERR_ARG, "bdk_decode_bams: more than %llu records", (unsigned long long)cap);
+            void* dst[10] = {(void*)host_out->pos, (void*)host_out->mpos, (void*)host_out->tid, (void*)host_out->mtid, (void*)host_out->isize,
+                             (void*)host_out->flag, (void*)host_out->mapq, (void*)host_out->rgid, (void*)host_out->qlen, (void*)host_out->qid};
+            for (int k = 0; k < 10; ++k) CU(cudaMemcpyAsync(dst[k], merged.cols[k].p, (size_t)n * width[k], cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            return 0;
+        }
+        bdk_soa d;
+        d.pos = m.pos; d.mpos = m.mpos; d.tid = m.tid; d.mtid = m.mtid; d.isize = m.isize; d.flag = m.flag; d.mapq = m.mapq; d.rgid = m.rgid; d.qlen = m.qlen; d.qid = m.qid;
+        return push_common(c, n, n, [&]() -> int { return launch_k1(c, d, n, (uint32_t)c->n_records, true); });
+    };
+    const int rc = run();
+    cudaStreamSynchronize(c->stream);
+    cleanup();
+    return rc;
+}
+
 int bdk_push_bams(bdk_ctx* c, const bdk_bam_source* srcs, int n, bdk_bam_stats* stats) {
     if (!c || !srcs) return BDK_ERR_ARG;
     if (n == 1) return bam_pipeline(c, srcs, stats, nullptr, 0);
-    if (n != 2) return fail(c, BDK_ERR_ARG, "bdk_push_bams merges one or two bams on the device (%d given): use the host reader for more", n);
+    if (n < 1 || n > bammerge::MAX_BAMS) return fail(c, BDK_ERR_ARG, "bdk_push_bams merges up to %d bams on the device (%d given): use the host reader for more", bammerge::MAX_BAMS, n);
     if (c->finished) return fail(c, BDK_ERR_STATE, "bdk_push_bams after bdk_finish (call bdk_reset first)");
-    return push_two_bams(c, srcs, stats, nullptr, 0);
+    if (n == 2) return push_two_bams(c, srcs, stats, nullptr, 0);
+    return push_many_bams(c, srcs, n, stats, nullptr, 0);
 }
 
 int bdk_decode_bams(bdk_ctx* c, const bdk_bam_source* srcs, int n, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
     if (!c || !srcs || !host_out) return BDK_ERR_ARG;
     if (n == 1) return bam_pipeline(c, srcs, stats, host_out, cap);
-    if (n != 2) return fail(c, BDK_ERR_ARG, "bdk_decode_bams: one or two bams");
-    return push_two_bams(c, srcs, stats, host_out, cap);
+    if (n < 1 || n > bammerge::MAX_BAMS) return fail(c, BDK_ERR_ARG, "bdk_decode_bams: 1 to %d bams", bammerge::MAX_BAMS);
+    if (n == 2) return push_two_bams(c, srcs, stats, host_out, cap);
+    return push_many_bams(c, srcs, n, stats, host_out, cap);
 }
 
 int bdk_decode_bam(bdk_ctx* c, const bdk_bam_source* src, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {

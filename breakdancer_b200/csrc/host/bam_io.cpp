@@ -1252,6 +1252,18 @@ int bdh_bamdev_decode2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, cons
     bamdev_source(first, s[0]); bamdev_source(second, s[1]);
     return bdk_decode_bams(ctx, s, 2, host_out, cap, stats2);
 }
+int bdh_bamdev_pushn(bdh_bamdev* const* devs, int n, bdk_ctx* ctx, bdk_bam_stats* stats) {
+    if (!devs || n < 1) return BDK_ERR_ARG;
+    std::vector<bdk_bam_source> s((size_t)n);
+    for (int b = 0; b < n; ++b) { if (!devs[b]) return BDK_ERR_ARG; bamdev_source(devs[b], s[b]); }
+    return bdk_push_bams(ctx, s.data(), n, stats);
+}
+int bdh_bamdev_decoden(bdh_bamdev* const* devs, int n, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
+    if (!devs || n < 1) return BDK_ERR_ARG;
+    std::vector<bdk_bam_source> s((size_t)n);
+    for (int b = 0; b < n; ++b) { if (!devs[b]) return BDK_ERR_ARG; bamdev_source(devs[b], s[b]); }
+    return bdk_decode_bams(ctx, s.data(), n, host_out, cap, stats);
+}
 int bdh_bamdev_decode(bdh_bamdev* d, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats) {
     bdk_bam_source s;
     bamdev_source(d, s);

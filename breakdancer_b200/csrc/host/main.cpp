@@ -65,38 +65,44 @@ int main(int argc, char** argv) {
         bdk_bam_stats bstats;
         memset(&bstats, 0, sizeof bstats);
         bool on_device = false;
-        // One or two bams and no read dump: the files are decoded on the GPU (two: merged there in BamMerger's order) (bdk_push_bam: only the compressed bytes cross PCIe, inflate /
-        // record parsing / classification of consecutive windows overlap). BDK_GPU_DECODE=0 keeps the host decoder. A file the
+        // Up to 16 bams and no read dump: the files are decoded on the GPU (two: merged there in BamMerger's order; three or more: the
+        // order from the priority queue on the host, the gather on the GPU) (bdk_push_bam: only the compressed bytes cross PCIe,
+        // inflate / record parsing / classification of consecutive windows overlap). BDK_GPU_DECODE=0 keeps the host decoder. A file the
         // device path refuses (damaged member, truncated record) goes through the host decoder, which reports what is wrong.
         const char* gd = getenv("BDK_GPU_DECODE");
-        if (cfg.bam_files.size() <= 2 && !want_reads && !(gd && atoi(gd) == 0)) {
-            const bool two = cfg.bam_files.size() == 2;
-            bdh_bamdev* dev = bdh_bamdev_open(&cfgh, cfg.bam_files[0].c_str(), o.chr.c_str(), err, sizeof err);
-            bdh_bamdev* dev2 = dev && two ? bdh_bamdev_open_next(&cfgh, dev, cfg.bam_files[1].c_str(), o.chr.c_str(), err, sizeof err) : nullptr;
-            if (dev && (!two || dev2)) {
+        if (cfg.bam_files.size() <= 16 && !want_reads && !(gd && atoi(gd) == 0)) {
+            const size_t nb = cfg.bam_files.size();
+            std::vector<bdh_bamdev*> devs;
+            for (size_t b = 0; b < nb; ++b) {
+                bdh_bamdev* d = b == 0 ? bdh_bamdev_open(&cfgh, cfg.bam_files[0].c_str(), o.chr.c_str(), err, sizeof err)
+                                       : bdh_bamdev_open_next(&cfgh, devs.back(), cfg.bam_files[b].c_str(), o.chr.c_str(), err, sizeof err);
+                if (!d) break;
+                devs.push_back(d);
+            }
+            if (devs.size() == nb) {
                 t_decoded = now_s();
                 if (cuda_warmup.joinable()) cuda_warmup.join();
-                std::vector<int32_t> rg_lib(bdh_bamdev_rg_lib(dev), bdh_bamdev_rg_lib(dev) + bdh_bamdev_nrg(dev));
-                std::vector<int32_t> rg_bam(bdh_bamdev_rg_bam(dev), bdh_bamdev_rg_bam(dev) + bdh_bamdev_nrg(dev));
-                if (two) {      // the second bam's read-group ids follow the first bam's
-                    rg_lib.insert(rg_lib.end(), bdh_bamdev_rg_lib(dev2), bdh_bamdev_rg_lib(dev2) + bdh_bamdev_nrg(dev2));
-                    rg_bam.insert(rg_bam.end(), bdh_bamdev_rg_bam(dev2), bdh_bamdev_rg_bam(dev2) + bdh_bamdev_nrg(dev2));
+                std::vector<int32_t> rg_lib, rg_bam;      // the read-group ids of a bam follow those of the bam before it
+                for (bdh_bamdev* d : devs) {
+                    rg_lib.insert(rg_lib.end(), bdh_bamdev_rg_lib(d), bdh_bamdev_rg_lib(d) + bdh_bamdev_nrg(d));
+                    rg_bam.insert(rg_bam.end(), bdh_bamdev_rg_bam(d), bdh_bamdev_rg_bam(d) + bdh_bamdev_nrg(d));
                 }
+                bdh_bamdev* dev = devs[0];
                 p.nrg = (int)rg_lib.size(); p.ntid = std::max(1, bdh_bamdev_ntid(dev));
                 p.rg_lib = rg_lib.data(); p.rg_bam = rg_bam.data();
                 check(nullptr, bdk_create(&ctx, 0, &p), "bdk_create");      // (copies the tables)
                 p.rg_lib = nullptr; p.rg_bam = nullptr;
                 t_created = now_s();
-                bdk_bam_stats st2[2];
-                memset(st2, 0, sizeof st2);
-                const int rc = two ? bdh_bamdev_push2(dev, dev2, ctx, st2) : bdh_bamdev_push(dev, ctx, &st2[0]);
+                std::vector<bdk_bam_stats> stn(nb);
+                memset(stn.data(), 0, nb * sizeof(bdk_bam_stats));
+                const int rc = nb == 1 ? bdh_bamdev_push(dev, ctx, &stn[0]) : bdh_bamdev_pushn(devs.data(), (int)nb, ctx, stn.data());
                 if (rc == 0) {
                     on_device = true;
-                    bstats = st2[0];
-                    if (two) {
-                        bstats.kept += st2[1].kept; bstats.records += st2[1].records; bstats.h2d_bytes += st2[1].h2d_bytes; bstats.inflated_bytes += st2[1].inflated_bytes;
-                        bstats.windows += st2[1].windows; bstats.inflate_ms += st2[1].inflate_ms; bstats.sorted = st2[0].sorted && st2[1].sorted;
-                        bstats.chain_ms = st2[1].chain_ms; bstats.extract_ms = st2[1].extract_ms;       // (timers accumulate over the job)
+                    bstats = stn[0];
+                    for (size_t b = 1; b < nb; ++b) {
+                        bstats.kept += stn[b].kept; bstats.records += stn[b].records; bstats.h2d_bytes += stn[b].h2d_bytes; bstats.inflated_bytes += stn[b].inflated_bytes;
+                        bstats.windows += stn[b].windows; bstats.inflate_ms += stn[b].inflate_ms; bstats.sorted = bstats.sorted && stn[b].sorted;
+                        bstats.chain_ms = stn[b].chain_ms; bstats.extract_ms = stn[b].extract_ms;       // (timers accumulate over the job)
                     }
                     n_records = bstats.kept;
                     for (int t = 0; t < bdh_bamdev_ntid(dev); ++t) tid_names.push_back(bdh_bamdev_tid_name(dev, t));      // BamMerger: the first stream's header
@@ -107,11 +113,10 @@ int main(int argc, char** argv) {
                     const std::string why = bdk_last_error(ctx);
                     if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode refused the input (%s); host decoder\n", why.c_str());
                     bdk_destroy(ctx); ctx = nullptr;
-                    if (rc != BDK_ERR_DATA) { bdh_bamdev_free(dev); bdh_bamdev_free(dev2); throw std::runtime_error("bdk_push_bam: " + why); }
+                    if (rc != BDK_ERR_DATA) { for (bdh_bamdev* d : devs) bdh_bamdev_free(d); throw std::runtime_error("bdk_push_bam: " + why); }
                 }
             } else if (getenv("BDK_DECODE_TRACE")) fprintf(stderr, "[decode] device decode: %s; host decoder\n", err);
-            bdh_bamdev_free(dev);
-            bdh_bamdev_free(dev2);
+            for (bdh_bamdev* d : devs) bdh_bamdev_free(d);
         }
         if (!on_device) {
             // pageable columns: pinning hundreds of megabytes costs more than the staged copy of a one-shot run saves, and the decoder

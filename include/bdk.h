@@ -351,12 +351,14 @@ typedef struct bdk_bam_stats {
     uint32_t merge_longest_part;      /* ... and the records of the longest one (merged by one thread) */
 } bdk_bam_stats;
 int bdk_push_bam(bdk_ctx* ctx, const bdk_bam_source* src, bdk_bam_stats* stats);
-/* One or TWO bams of one config: each is decoded on the device as above, the two record streams are merged on the device in the
- * order the reference's BamMerger delivers them (src/lib/io/BamMerger.cpp:40-126: a priority queue over the streams' heads by
- * (tid, pos, strand); for two streams its tie behaviour has a closed form, csrc/bam_merge.cuh) and classified. srcs[0] must be
- * the config's first bam (BamMerger pushes the streams in that order), the read-group ids of the two sources must not overlap,
- * stats (may be NULL) has n entries. Both bams must be sorted by (reference sequence, position), else BDK_ERR_DATA. Three or more
- * bams: BDK_ERR_ARG (use bdh_stream_open + bdk_push). bdk_decode_bams: the merged columns to the host instead (tests). */
+/* The bams of one config, up to 16: each is decoded on the device as above, the record streams are merged in the order the
+ * reference's BamMerger delivers them (src/lib/io/BamMerger.cpp:40-126: a priority queue over the streams' heads by
+ * (tid, pos, strand)) and classified. TWO bams: merged on the device -- for two streams the queue's tie behaviour has a closed form,
+ * csrc/bam_merge.cuh; both bams must be sorted by (reference sequence, position), else BDK_ERR_DATA. THREE OR MORE: the tie order
+ * depends on the heap's history, so the order is computed by the queue itself on the host from the packed keys the device hands
+ * back (csrc/host/nway_merge.hpp; 12 bytes per record over PCIe) and the columns are gathered through it on the device. srcs must
+ * be in the config's bam order (BamMerger pushes the streams in that order), the read-group ids of the sources must not overlap,
+ * stats (may be NULL) has n entries. bdk_decode_bams: the merged columns to the host instead (tests). */
 int bdk_push_bams(bdk_ctx* ctx, const bdk_bam_source* srcs, int n, bdk_bam_stats* stats);
 int bdk_decode_bams(bdk_ctx* ctx, const bdk_bam_source* srcs, int n, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
 /* The same decode, but the columns come back to the HOST (arrays of `cap` records the caller owns, written through the const

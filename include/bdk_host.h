@@ -82,12 +82,14 @@ void bdh_inflate_counters(uint64_t* host_fallbacks, uint64_t* gpu_redone);
  * read groups in its own order, then one id for every other read-group string (BamConfig.hpp:63-72: unknown read groups get the
  * first bam's library). path NULL/"" = the config's only bam. Order of use: bdh_bamdev_open, bdk_create with nrg / rg_lib /
  * rg_bam / ntid from here, bdh_bamdev_push, bdk_summary / bdk_finish. The records pushed are those bdh_stream_open delivers for
- * the same file and region, in the same order. One file per call; several bams (BamMerger) go through bdh_stream_open. */
+ * the same file and region, in the same order. One file per call; several bams (BamMerger): bdh_bamdev_open_next and
+ * bdh_bamdev_push2 / bdh_bamdev_pushn below (or the host decoder, bdh_stream_open). */
 typedef struct bdh_bamdev bdh_bamdev;
 bdh_bamdev* bdh_bamdev_open(const bdh_config* cfg, const char* path, const char* region, char* err, int errcap);
-/* The SECOND bam of a two-bam config (tumor / normal): its read-group ids follow the first bam's, so the two sources can be handed to
- * bdk_push_bams together. bdk_create then takes nrg = bdh_bamdev_nrg(first) + bdh_bamdev_nrg(second) and the two rg_lib / rg_bam
- * arrays one after the other. `first` must be the config's first bam (sorted bam list), `path` its second. */
+/* The NEXT bam of a config with several (tumor / normal, one bam per lane ...): its read-group ids follow those of the bam opened
+ * before it (`first`: the config's first bam for the second one, the second for the third ...), so the sources can be handed to
+ * bdk_push_bams together. bdk_create then takes nrg = the sum of bdh_bamdev_nrg over the bams and their rg_lib / rg_bam arrays one
+ * after the other, in the order of the config's (sorted) bam list. */
 bdh_bamdev* bdh_bamdev_open_next(const bdh_config* cfg, const bdh_bamdev* first, const char* path, const char* region, char* err, int errcap);
 void bdh_bamdev_free(bdh_bamdev* d);
 int bdh_bamdev_nrg(const bdh_bamdev* d);
@@ -102,6 +104,11 @@ int bdh_bamdev_push(bdh_bamdev* d, bdk_ctx* ctx, bdk_bam_stats* stats);
  * merged columns copied to the host). stats2 = two entries or NULL. */
 int bdh_bamdev_push2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, bdk_bam_stats* stats2);
 int bdh_bamdev_decode2(bdh_bamdev* first, bdh_bamdev* second, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats2);
+/* The same for n opened files in the config's order (n = 1, 2, or 3 .. 16: for three or more the merge order is computed by the
+ * reference's priority queue on the host from keys the device hands back, BamMerger.cpp:40-126, and the columns are gathered
+ * through it on the device). stats = n entries or NULL. */
+int bdh_bamdev_pushn(bdh_bamdev* const* devs, int n, bdk_ctx* ctx, bdk_bam_stats* stats);
+int bdh_bamdev_decoden(bdh_bamdev* const* devs, int n, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
 /* bdk_decode_bam of the opened file: the decoded columns into the caller's host arrays (cap records each). */
 int bdh_bamdev_decode(bdh_bamdev* d, bdk_ctx* ctx, const bdk_soa* host_out, uint64_t cap, bdk_bam_stats* stats);
 

@@ -271,6 +271,93 @@ def test_two_bam_job_and_cli_on_the_device_equal_the_host_decoder(tmp_path):
     assert outs["1"] == outs["0"] and outs["1"].count("\n") > 5
 
 
+LIBS_4BAMS = [synth.LibSpec("lane1", "lane1.bam", 315, 44, 75, ["l1a", "l1b"]),
+              synth.LibSpec("lane2", "lane2.bam", 312, 43, 75, ["l2"]),
+              synth.LibSpec("lane3", "lane3.bam", 467, 32, 75, ["l3"], tumor=True),
+              synth.LibSpec("lane4", "lane4.bam", 476, 29, 100, ["l4"], tumor=True)]
+
+
+def _n_bam_columns(cfg, paths, region=""):
+    host = api.BamStream(cfg, paths=paths, region=region, threads=4)
+    devs = []
+    for p in paths:
+        devs.append(api.BamDevice(cfg, path=p, region=region, after=devs[-1] if devs else None))
+    rg_lib = np.concatenate([d.rg_lib for d in devs])
+    rg_bam = np.concatenate([d.rg_bam for d in devs])
+    b = api.ParamBundle(api.Options(chr=region), cfg.libs, cfg.nbam, rg_lib, rg_bam, cfg.window, max(1, len(devs[0].tid_names)))
+    ctx = api.Context(b)
+    cols, stats = ctx.decode_bams_n(devs, host.n + 64)
+    assert len(cols["pos"]) == host.n, (len(cols["pos"]), host.n)
+    for k in api.COLUMN_DTYPES:
+        if k == "rgid":
+            assert np.array_equal(host.rg_lib[host.cols[k]], rg_lib[cols[k]]) and np.array_equal(host.rg_bam[host.cols[k]], rg_bam[cols[k]]), k
+        else:
+            assert np.array_equal(host.cols[k], cols[k]), (k, region, len(paths))
+    n = host.n
+    ctx.close(); host.close()
+    for d in devs:
+        d.close()
+    return n
+
+
+@pytest.mark.gpu
+def test_three_and_four_bams_on_the_device_in_the_reference_order(tmp_path):
+    """One bam per lane: every bam decoded on the GPU, the merge order from the priority queue itself (host, on keys the device
+    hands back), the columns gathered on the GPU -- every column of the merged stream against the host decoder's priority-queue
+    merge (itself tested against the reference binary), for three and four bams, with a region, and on tie-heavy input (the same
+    records in three bams: the order among equal keys is the heap's, history and all). Then the whole job and the CLI."""
+    import json
+    import shutil
+    w, d = _write(tmp_path, 120000, 6, seed=41, libs=LIBS_4BAMS)
+    (d / "cfg").write_text(w.config_text())
+    cfg = api.BamConfig(text=w.config_text())
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        assert cfg.bam_files == ["lane1.bam", "lane2.bam", "lane3.bam", "lane4.bam"]
+        n4 = _n_bam_columns(cfg, cfg.bam_files)
+        assert n4 == w.n
+        _n_bam_columns(cfg, cfg.bam_files, "chrB")
+        # whole job: device decode of four bams against the job from host-decoded columns
+        opts = api.Options()
+        host = api.BamStream(cfg, threads=4)
+        b = api.ParamBundle.from_stream(opts, cfg, host)
+        ctx = api.Context(b)
+        ctx.push({k: np.ascontiguousarray(v) for k, v in host.cols.items()})
+        want = (ctx.summary(), ctx.finish(), ctx.regions(), ctx.areads())
+        ctx.close(); host.close()
+        devs = []
+        for p in cfg.bam_files:
+            devs.append(api.BamDevice(cfg, path=p, after=devs[-1] if devs else None))
+        b = api.ParamBundle(opts, cfg.libs, cfg.nbam, np.concatenate([x.rg_lib for x in devs]), np.concatenate([x.rg_bam for x in devs]), cfg.window, len(devs[0].tid_names))
+        ctx = api.Context(b)
+        ctx.push_bams_n(devs)
+        got = (ctx.summary(), ctx.finish(), ctx.regions(), ctx.areads())
+        ctx.close()
+        for x in devs:
+            x.close()
+        _assert_same_job(want, got)
+        assert len(got[1].sv) > 0
+    finally:
+        os.chdir(cwd)
+    outs = {}
+    for mode in ("1", "0"):
+        stats = d / ("stats%s.json" % mode)
+        p = subprocess.run([util.CLI, "--stats-json", str(stats), "cfg"], cwd=d, env=dict(os.environ, BDK_GPU_DECODE=mode), capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        outs[mode] = util.strip_header(p.stdout)
+        assert json.loads(stats.read_text())["device_decode"] == int(mode)
+    assert outs["1"] == outs["0"] and outs["1"].count("\n") > 5
+    # ties everywhere: three bams with the same records
+    os.chdir(d)
+    try:
+        shutil.copy("lane1.bam", "lane2.bam")
+        shutil.copy("lane1.bam", "lane3.bam")
+        _n_bam_columns(cfg, cfg.bam_files[:3])
+    finally:
+        os.chdir(cwd)
+
+
 def test_per_chromosome_shards_decoded_on_the_device(tmp_path):
     """shard.run_sharded_bams_device: every chromosome through the index and the device decode (-o semantics), against the same
     chromosome through the host decoder; the plan comes from the .bai alone. The index is written by the reference's samtools
