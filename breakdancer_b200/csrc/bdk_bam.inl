@@ -648,7 +648,15 @@ int push_many_bams(bdk_ctx* c, const bdk_bam_source* srcs, int nb, bdk_bam_stats
             std::vector<const uint64_t*> kp((size_t)nb);
             std::vector<uint64_t> counts((size_t)nb);
             for (int b = 0; b < nb; ++b) { kp[b] = hk[b].data(); counts[b] = hk[b].size(); }
-            bdh::nway_merge_order(kp.data(), counts.data(), nb, bammerge::BAM_SHIFT, order.data());
+            // up to five sorted bams and enough cores: the parts of the merge in parallel, one run per valid heap layout at a cut
+            // (exact: nway_merge.hpp); else -- or when it declines -- the queue on one thread
+            bool all_sorted = true;
+            for (int b = 0; b < nb; ++b) all_sorted = all_sorted && stats[b].sorted;
+            const int hw = (int)std::thread::hardware_concurrency();
+            int mthreads = hw >= 8 && !getenv("BDK_MERGE_HEAP") ? std::min(hw, 32) : 1;
+            if (const char* e = getenv("BDK_MERGE_THREADS")) mthreads = std::max(1, atoi(e));
+            if (!(all_sorted && mthreads >= 2 && bdh::nway_merge_order_parallel(kp.data(), counts.data(), nb, bammerge::BAM_SHIFT, order.data(), mthreads)))
+                bdh::nway_merge_order(kp.data(), counts.data(), nb, bammerge::BAM_SHIFT, order.data());
         }
         ENS(d_order, (size_t)n * 4);
         CU(cudaMemcpyAsync(d_order.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
