@@ -12,6 +12,7 @@
 // blocks are inflated in parallel into one buffer, and fields are extracted by all cores
 // straight into the columns the GPU consumes.
 #include "host.hpp"
+#include "nway_merge.hpp"
 #include "fast_inflate.hpp"
 #include "../bam_records.h"
 
@@ -979,6 +980,25 @@ bdh_stream* bdh_stream_open(const bdh_config* cfgh, const char* const* paths, in
                         while (i < e0) put(o++, 0, i++);
                         while (j < e1) put(o++, 1, j++);
                     }
+                });
+                s->t_merge = now_s() - t3;
+                note_sortedness(s, threads);
+                return s;
+            }
+            // Three or more bams (or unsorted input): the queue itself. Up to 16 bams of fewer than 2^28 records each go through
+            // nway_merge.hpp -- libstdc++'s heap on a fixed array and, for up to five sorted bams, its exact parallel form (parts
+            // cut at position boundaries, one run per valid heap layout at the cut); BDK_MERGE_HEAP keeps the plain queue below.
+            bool small = nb <= 16 && !getenv("BDK_MERGE_HEAP");
+            for (size_t b = 0; b < nb; ++b) small = small && keys[b].size() < (1ull << 28);
+            if (small) {
+                std::vector<const uint64_t*> kp(nb);
+                std::vector<uint64_t> counts(nb);
+                for (size_t b = 0; b < nb; ++b) { kp[b] = keys[b].data(); counts[b] = keys[b].size(); }
+                std::vector<uint32_t> order(n);
+                if (!(sorted && threads >= 8 && bdh::nway_merge_order_parallel(kp.data(), counts.data(), (int)nb, 28, order.data(), std::min(threads, 32))))
+                    bdh::nway_merge_order(kp.data(), counts.data(), (int)nb, 28, order.data());
+                parallel_for(n, 1 << 16, threads, [&](uint64_t o0, uint64_t o1) {
+                    for (uint64_t o = o0; o < o1; ++o) put(o, (int)(order[o] >> 28), order[o] & ((1u << 28) - 1u));
                 });
                 s->t_merge = now_s() - t3;
                 note_sortedness(s, threads);

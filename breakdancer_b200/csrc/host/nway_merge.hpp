@@ -105,8 +105,7 @@ inline bool nway_merge_order_parallel(const uint64_t* const* keys, const uint64_
     // valid heap layouts of the heads at a boundary: arrangements of the non-exhausted streams with no parent greater than its child
     auto layouts = [&](const uint64_t* cur, std::vector<Variant>& out) {
         uint32_t ids[5]; int m = 0;
-        for (int b = 0; b < n; ++b) if (cur[b] < counts[b]) ids[m++] = (uint32_t)b;
-        std::sort(ids, ids + m);
+        for (int b = 0; b < n; ++b) if (cur[b] < counts[b]) ids[m++] = (uint32_t)b;      // ascending: the first permutation
         out.clear();
         do {
             bool ok = true;
